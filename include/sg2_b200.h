@@ -1,0 +1,177 @@
+/* sg2_b200.h -- C ABI of libsg2_b200.so: the B200 (sm_100a) StyleGAN2 synthesis path.
+ *
+ * Drop-in boundary for the hot path of seva100/stylegan-for-facerec.
+ * Every entry point is `extern "C"`, takes raw device pointers, sizes, a dtype enum and a
+ * cudaStream_t (as void*), returns an int status (0 = ok) and never allocates, frees or
+ * synchronises: the caller (PyTorch host code) owns all memory and the stream, so every call is
+ * CUDA-graph capturable.  On failure the message is available from sg2_last_error().
+ *
+ * Reference interfaces replaced (paths relative to /root/reference/backbone/stylegan2, identical
+ * under restyle-encoder/models/stylegan2):
+ *   sg2_fused_bias_act        <- pybind `fused.fused_bias_act`      op/fused_bias_act.cpp:11-21
+ *                                 (kernel op/fused_bias_act_kernel.cu:18-99)
+ *   sg2_bias_act_grad_bias    <- `grad_input.sum(dim)`              op/fused_act.py:31-36
+ *   sg2_upfirdn2d             <- pybind `upfirdn2d.upfirdn2d`       op/upfirdn2d.cpp:12-23
+ *                                 (kernel op/upfirdn2d_kernel.cu:52-272)
+ *   sg2_equal_linear_fwd      <- EqualLinear.forward                model.py:147-157
+ *   sg2_mapping_fwd           <- Generator.style (PixelNorm + MLP)  model.py:10-15,378-387
+ *   sg2_modulation_fwd        <- modulation affine + demod coeffs   model.py:235-240
+ *   sg2_modconv2d_*           <- ModulatedConv2d.forward            model.py:232-273
+ *   sg2_noise_bias_act        <- NoiseInjection + FusedLeakyReLU    model.py:282-287,335
+ *   sg2_torgb_combine         <- ToRGB bias + Upsample(skip) + add  model.py:350-359
+ *   sg2_synth_*               <- Generator.forward synthesis loop   model.py:520-542
+ */
+#ifndef SG2_B200_H
+#define SG2_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SG2_ABI_VERSION 1
+
+/* status codes */
+#define SG2_OK 0
+#define SG2_ERR_BAD_ARG 1      /* null pointer, non-positive size, unknown enum */
+#define SG2_ERR_UNSUPPORTED 2  /* configuration outside what the kernels implement */
+#define SG2_ERR_CUDA 3         /* a CUDA runtime / driver call failed (see sg2_last_error) */
+#define SG2_ERR_NO_DEVICE 4    /* no sm_100 device visible */
+
+/* storage dtypes (arithmetic is always fp32 accumulate) */
+#define SG2_F32 0
+#define SG2_F16 1
+#define SG2_BF16 2
+
+typedef void *sg2_stream_t; /* cudaStream_t */
+
+int sg2_abi_version(void);
+/* thread-local, valid until the next failing call on this thread */
+const char *sg2_last_error(void);
+/* number of kernel launches issued through this library by the calling process (all threads) */
+int64_t sg2_launch_count(void);
+/* CPU-only self check of the multiply-shift division used by the vector kernels: 0 if n/d matches */
+int sg2_selftest_fastdiv(uint32_t d, uint32_t n);
+
+/* ---------------------------------------------------------------------------------------------
+ * fused bias + activation.   out[i] = act(x[i] + bias[(i / step_b) % size_b]) * scale
+ * act: 1 linear, 3 leaky-relu(alpha).  grad: 0 value, 1 first derivative gated on ref[i] > 0,
+ * 2 second derivative (zero).  bias / ref may be NULL.  In-place (out == x) is allowed.          */
+int sg2_fused_bias_act(void *out, const void *x, const void *bias, const void *ref, int64_t n,
+                       int64_t step_b, int64_t size_b, int act, int grad, float alpha, float scale,
+                       int dtype, sg2_stream_t stream);
+
+/* grad_bias[c] = sum over b, hw of grad_input[b, c, hw]   (grad_input laid out [B, C, HW]);
+ * grad_bias is always fp32 [C] (bit-deterministic unless C < 2*SMs, where slices are combined
+ * with fp32 atomics). */
+int sg2_bias_act_grad_bias(void *grad_bias, const void *grad_input, int64_t B, int64_t C,
+                           int64_t HW, int dtype, sg2_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * upfirdn2d on x[major, in_h, in_w, minor] -> out[major, out_h, out_w, minor],
+ * out_h = (in_h*up_y + pad_y0 + pad_y1 - kh) / down_y + 1 (likewise out_w).
+ * kernel: kh*kw fp32 taps on the device, as the caller holds them (the op applies them flipped,
+ * i.e. a true convolution).  Supported: 1 <= up, down <= 4 per axis, kh, kw <= 16, any pads
+ * (negative pads crop).  Anything else returns SG2_ERR_UNSUPPORTED (the reference returns
+ * uninitialised memory there, upfirdn2d_kernel.cu:172-268).                                     */
+int sg2_upfirdn2d(void *out, const void *x, const float *kernel, int64_t major, int in_h, int in_w,
+                  int minor, int kh, int kw, int up_x, int up_y, int down_x, int down_y,
+                  int pad_x0, int pad_x1, int pad_y0, int pad_y1, int dtype, sg2_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * EqualLinear: out[b,o] = act( (sum_j x[b,j] * w[o,j]) * w_scale + bias[o] * lr_mul )
+ * act = 0: linear; act = 1: leaky-relu(0.2) * sqrt(2).  bias may be NULL.  x/w/bias/out in dtype. */
+int sg2_equal_linear_fwd(void *out, const void *x, const void *w, const void *bias, int64_t B,
+                         int in_dim, int out_dim, float w_scale, float lr_mul, int act, int dtype,
+                         sg2_stream_t stream);
+
+/* Mapping network: w = MLP(pixel_norm(z)); weights[n_mlp][dim][dim], biases[n_mlp][dim] given as
+ * arrays of n_mlp device pointers (host arrays).  dim must be a multiple of 32 and <= 1024.     */
+int sg2_mapping_fwd(void *w_out, const void *z, const void *const *weights,
+                    const void *const *biases, int n_mlp, int64_t B, int dim, float lr_mul,
+                    int pixel_norm, int dtype, sg2_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Modulated convolution, exact fp32-accumulate path (NCHW, SIMT).  Three calls:
+ *  1. sg2_modconv2d_prep: weight[Cout,Cin,k,k] (dtype) -> wt fp32 [Cin*k*k, Cout] (scaled by
+ *     conv_scale, the caller passes 1/sqrt(Cin*k*k), model.py:214-215) and, if wsq != NULL,
+ *     wsq fp32 [Cin, Cout] = conv_scale^2 * sum_k w^2.
+ *  2. sg2_modulation_fwd: style[b,ci] = latent[b,:] . mod_w[ci,:] * mod_scale + mod_b[ci]*lr_mul
+ *     (fp32) and, if demod != NULL, demod[b,co] = rsqrt(sum_ci style^2 * wsq[ci,co] + 1e-8).
+ *  3. sg2_modconv2d_fwd: out[b,co] = demod[b,co] * conv(x[b] * style[b], wt)   with
+ *     mode 0: stride 1, zero pad k/2            out H x W
+ *     mode 1: transposed, stride 2, pad 0       out (2H+k-2) x (2W+k-2)   (blur is a separate
+ *             sg2_upfirdn2d call, model.py:254-257)
+ *     mode 2: stride 2, pad 0                   out ((H-k)/2+1) x ((W-k)/2+1)
+ *     demod may be NULL (ToRGB); style may be NULL (plain shared-weight conv, used by the
+ *     backward pass).  k in {1, 3}.                                                   */
+int sg2_modconv2d_prep(float *wt, float *wsq, const void *weight, int Cin, int Cout, int k,
+                       float conv_scale, int dtype, sg2_stream_t stream);
+int sg2_modulation_fwd(float *style, float *demod, const void *latent, int64_t latent_stride,
+                       const void *mod_w, const void *mod_b, const float *wsq, int64_t B,
+                       int style_dim, int Cin, int Cout, float mod_scale, float lr_mul, int dtype,
+                       sg2_stream_t stream);
+int sg2_modconv2d_fwd(void *out, const void *x, const float *wt, const float *style,
+                      const float *demod, int64_t B, int Cin, int Cout, int H, int W, int k,
+                      int mode, int dtype, sg2_stream_t stream);
+
+/* out = act(x + noise_weight[0] * noise[b or 0, 0, h, w] + bias[c]) * act_scale    (NCHW)
+ * noise_bstride = H*W for per-sample noise, 0 for one noise map broadcast over the batch.
+ * noise or bias may be NULL; act: 1 linear, 3 leaky-relu(alpha).                                */
+int sg2_noise_bias_act(void *out, const void *x, const void *noise, int64_t noise_bstride,
+                       const void *noise_weight, const void *bias, int64_t B, int C, int64_t HW,
+                       int act, float alpha, float act_scale, int dtype, sg2_stream_t stream);
+
+/* ToRGB tail: out[b,c,y,x] = conv[b,c,y,x] + bias[c] + upfirdn2d(skip, kernel, up=2, pad)[b,c,y,x]
+ * skip [B,C,H/2,W/2] may be NULL (first ToRGB).  kernel: kh*kw fp32 taps (already x4).          */
+int sg2_torgb_combine(void *out, const void *conv, const void *bias, const void *skip,
+                      const float *kernel, int kh, int kw, int pad0, int pad1, int64_t B, int C,
+                      int H, int W, int dtype, sg2_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Whole-network bf16 synthesis engine (NHWC activations, tcgen05/TMEM implicit GEMM fed by TMA,
+ * fused epilogues).  Replaces the loop of Generator.forward, model.py:520-533.
+ *
+ * Per-layer parameter table handed over by the host (device pointers to the fp32 master
+ * parameters exactly as the module's state_dict holds them).                                    */
+typedef struct sg2_conv_params {
+    const float *weight;      /* [1,Cout,Cin,k,k] */
+    const float *mod_weight;  /* [Cin, style_dim] */
+    const float *mod_bias;    /* [Cin] */
+    const float *noise_weight;/* [1]        (styled convs; NULL for ToRGB) */
+    const float *act_bias;    /* [Cout]     (styled convs) or ToRGB bias [1,3,1,1] */
+    int32_t cin, cout, ksize; /* ksize 3 (styled conv) or 1 (ToRGB) */
+    int32_t upsample;         /* 1: transposed stride-2 conv + blur (model.py:246-257) */
+    int32_t latent_index;     /* which row of latent[b, :, :] modulates this layer */
+    int32_t resolution;       /* output resolution of the layer */
+} sg2_conv_params;
+
+typedef struct sg2_synth sg2_synth; /* opaque launch plan */
+
+/* Builds the static launch plan for Generator(size, style_dim, channel_multiplier) at up to
+ * max_batch samples.  layers: conv1, to_rgb1, then per octave (up conv, conv, to_rgb) in network
+ * order; n_layers = 2 + 3*(log2(size)-2).  const_input: [1,C,4,4] fp32.  blur_taps: 4x4 fp32 HOST
+ * array (make_kernel([1,3,3,1])*4, model.py:18-26,77-78).  Does not touch the GPU.              */
+int sg2_synth_create(sg2_synth **plan, int size, int style_dim, int max_batch,
+                     const sg2_conv_params *layers, int n_layers, const float *const_input,
+                     const float *blur_taps_host);
+void sg2_synth_destroy(sg2_synth *plan);
+/* bytes of device workspace the caller must provide (packed weights + activations + scratch) */
+int64_t sg2_synth_workspace_bytes(const sg2_synth *plan);
+/* human-readable launch plan (one line per kernel), for tests and DESIGN.md; returns chars written */
+int sg2_synth_describe(const sg2_synth *plan, char *buf, int buflen);
+/* (re)pack the master weights into the engine layouts inside `workspace`; call once after
+ * create and again whenever the parameters change.                                              */
+int sg2_synth_pack(sg2_synth *plan, void *workspace, sg2_stream_t stream);
+/* latent [B, n_latent, style_dim] fp32; noise[l] fp32 [B or 1, 1, r, r] for each styled conv
+ * (n_noise = 2*log2(size)-3 pointers, host array), noise_bstride[l] = r*r or 0;
+ * image [B,3,size,size] fp32 (NCHW, as the reference returns it).                               */
+int sg2_synth_forward(sg2_synth *plan, void *workspace, const float *latent, int64_t B,
+                      const float *const *noise, const int64_t *noise_bstride, float *image,
+                      sg2_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SG2_B200_H */

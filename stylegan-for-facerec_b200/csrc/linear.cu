@@ -1,0 +1,332 @@
+// linear.cu -- the small dense pieces around the convolutions (all warp-shuffle kernels):
+//   * EqualLinear (model.py:147-157)                      -> equal_linear_kernel
+//   * mapping network PixelNorm + n_mlp x EqualLinear     -> mapping_kernel, one launch
+//     (model.py:10-15, 378-387; 36 launches in the reference)
+//   * modulation affine + demodulation coefficients       -> modulation kernels
+//     (model.py:235-240), computed WITHOUT materialising per-sample weights:
+//         demod[b,co] = rsqrt( sum_ci style[b,ci]^2 * wsq[ci,co] + 1e-8 ),
+//         wsq[ci,co]  = conv_scale^2 * sum_k weight[co,ci,k]^2
+//     which is algebraically the reference's rsqrt(sum (scale*W*s)^2 + 1e-8).
+#include "common.cuh"
+
+namespace sg2 {
+
+constexpr float kLreluSlope = 0.2f;
+constexpr float kLreluGain = 1.41421356237309515f;   // 2 ** 0.5 as the reference's Python float
+
+// out[b,o] = act((x[b,:] . w[o,:]) * w_scale + bias[o]*lr_mul); one warp per output feature o,
+// the weight row lives in registers and is reused for every sample of the batch chunk.
+template <typename T, int MAXJ>   // in_dim <= 32*MAXJ
+__global__ void __launch_bounds__(256)
+equal_linear_kernel(T *__restrict__ out, const T *__restrict__ x, const T *__restrict__ w,
+                    const T *__restrict__ bias, int64_t B, int in_dim, int out_dim, float w_scale,
+                    float lr_mul, int act, int64_t b_chunk) {
+    const int lane = threadIdx.x & 31;
+    const int o = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (o >= out_dim) return;
+    float wr[MAXJ];
+#pragma unroll
+    for (int j = 0; j < MAXJ; ++j) {
+        const int idx = lane + 32 * j;
+        wr[j] = idx < in_dim ? Cvt<T>::to_f(w[(int64_t)o * in_dim + idx]) : 0.f;
+    }
+    const float bv = bias ? Cvt<T>::to_f(bias[o]) * lr_mul : 0.f;
+    const int64_t b0 = (int64_t)blockIdx.y * b_chunk;
+    const int64_t b1 = b0 + b_chunk < B ? b0 + b_chunk : B;
+    for (int64_t b = b0; b < b1; ++b) {
+        const T *xr = x + b * in_dim;
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < MAXJ; ++j) {
+            const int idx = lane + 32 * j;
+            if (idx < in_dim) acc += Cvt<T>::to_f(xr[idx]) * wr[j];
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) {
+            float v = acc * w_scale + bv;
+            if (act) v = (v > 0.f ? v : v * kLreluSlope) * kLreluGain;
+            out[b * out_dim + o] = Cvt<T>::from_f(v);
+        }
+    }
+}
+
+// same contract for wide inputs (in_dim > 2048, e.g. the discriminator's 8192 -> 512 layer):
+// the weight row is re-read through L1/L2 instead of being held in registers
+template <typename T>
+__global__ void __launch_bounds__(256)
+equal_linear_wide_kernel(T *__restrict__ out, const T *__restrict__ x, const T *__restrict__ w,
+                         const T *__restrict__ bias, int64_t B, int in_dim, int out_dim,
+                         float w_scale, float lr_mul, int act, int64_t b_chunk) {
+    const int lane = threadIdx.x & 31;
+    const int o = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (o >= out_dim) return;
+    const float bv = bias ? Cvt<T>::to_f(bias[o]) * lr_mul : 0.f;
+    const int64_t b0 = (int64_t)blockIdx.y * b_chunk;
+    const int64_t b1 = b0 + b_chunk < B ? b0 + b_chunk : B;
+    const T *wr = w + (int64_t)o * in_dim;
+    for (int64_t b = b0; b < b1; ++b) {
+        const T *xr = x + b * in_dim;
+        float acc = 0.f;
+        for (int idx = lane; idx < in_dim; idx += 32) acc += Cvt<T>::to_f(xr[idx]) * Cvt<T>::to_f(wr[idx]);
+        acc = warp_sum(acc);
+        if (lane == 0) {
+            float v = acc * w_scale + bv;
+            if (act) v = (v > 0.f ? v : v * kLreluSlope) * kLreluGain;
+            out[b * out_dim + o] = Cvt<T>::from_f(v);
+        }
+    }
+}
+
+// weight [Cout,Cin,k,k] -> wt[(ci*kk + t)*Cout + co] = conv_scale*w ; wsq[ci*Cout+co] = conv_scale^2*sum_t w^2
+template <typename T>
+__global__ void __launch_bounds__(256)
+modconv_prep_kernel(float *__restrict__ wt, float *__restrict__ wsq, const T *__restrict__ weight,
+                    int Cin, int Cout, int kk, float conv_scale) {
+    // tile transpose through smem: block handles 32 co x 32 ci
+    __shared__ float tile[32][9][33];
+    const int co0 = blockIdx.x * 32, ci0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    for (int r = ty; r < 32; r += 8) {           // r: co within tile, tx: ci within tile
+        const int co = co0 + r, ci = ci0 + tx;
+        for (int t = 0; t < kk; ++t)
+            tile[r][t][tx] = (co < Cout && ci < Cin)
+                                 ? Cvt<T>::to_f(weight[((int64_t)co * Cin + ci) * kk + t]) * conv_scale : 0.f;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {           // r: ci within tile, tx: co within tile
+        const int ci = ci0 + r, co = co0 + tx;
+        if (ci < Cin && co < Cout) {
+            float ss = 0.f;
+            for (int t = 0; t < kk; ++t) {
+                const float v = tile[tx][t][r];
+                wt[((int64_t)ci * kk + t) * Cout + co] = v;
+                ss += v * v;
+            }
+            if (wsq) wsq[(int64_t)ci * Cout + co] = ss;
+        }
+    }
+}
+
+// style[b,ci] = (latent[b,:] . mod_w[ci,:]) * mod_scale + mod_b[ci]*lr_mul  (fp32 out); warp per ci
+template <typename T, int MAXJ>
+__global__ void __launch_bounds__(256)
+modulation_style_kernel(float *__restrict__ style, const T *__restrict__ latent,
+                        int64_t latent_stride, const T *__restrict__ mod_w,
+                        const T *__restrict__ mod_b, int64_t B, int style_dim, int Cin,
+                        float mod_scale, float lr_mul) {
+    const int lane = threadIdx.x & 31;
+    const int ci = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (ci >= Cin) return;
+    float wr[MAXJ];
+#pragma unroll
+    for (int j = 0; j < MAXJ; ++j) {
+        const int idx = lane + 32 * j;
+        wr[j] = idx < style_dim ? Cvt<T>::to_f(mod_w[(int64_t)ci * style_dim + idx]) : 0.f;
+    }
+    const float bv = Cvt<T>::to_f(mod_b[ci]) * lr_mul;
+    for (int64_t b = blockIdx.y; b < B; b += gridDim.y) {
+        const T *lr = latent + b * latent_stride;
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < MAXJ; ++j) {
+            const int idx = lane + 32 * j;
+            if (idx < style_dim) acc += Cvt<T>::to_f(lr[idx]) * wr[j];
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) style[b * Cin + ci] = acc * mod_scale + bv;
+    }
+}
+
+// demod[b,co] = rsqrt(sum_ci style[b,ci]^2 * wsq[ci,co] + 1e-8); thread per (b,co), coalesced on co
+__global__ void __launch_bounds__(256)
+modulation_demod_kernel(float *__restrict__ demod, const float *__restrict__ style,
+                        const float *__restrict__ wsq, int Cin, int Cout) {
+    extern __shared__ float s_s2[];   // [Cin]
+    const int64_t b = blockIdx.y;
+    for (int i = threadIdx.x; i < Cin; i += 256) {
+        const float s = style[b * Cin + i];
+        s_s2[i] = s * s;
+    }
+    __syncthreads();
+    const int co = blockIdx.x * 256 + threadIdx.x;
+    if (co >= Cout) return;
+    float acc = 0.f;
+    for (int ci = 0; ci < Cin; ++ci) acc += s_s2[ci] * wsq[(int64_t)ci * Cout + co];
+    demod[b * Cout + co] = rsqrtf(acc + 1e-8f);
+}
+
+}  // namespace sg2
+
+using namespace sg2;
+
+extern "C" int sg2_equal_linear_fwd(void *out, const void *x, const void *w, const void *bias,
+                                    int64_t B, int in_dim, int out_dim, float w_scale, float lr_mul,
+                                    int act, int dtype, sg2_stream_t stream) {
+    SG2_REQUIRE(B >= 0 && in_dim >= 1 && out_dim >= 1, SG2_ERR_BAD_ARG, "equal_linear: bad shape");
+    if (B == 0) return SG2_OK;
+    SG2_REQUIRE(out && x && w, SG2_ERR_BAD_ARG, "equal_linear: null tensor pointer");
+    SG2_REQUIRE(in_dim <= 8192, SG2_ERR_UNSUPPORTED, "equal_linear: in_dim %d > 8192", in_dim);
+    cudaStream_t st = as_stream(stream);
+    const int sms = sm_count();
+    const unsigned gx = (out_dim + 7) / 8;
+    // split the batch so the grid covers the chip about twice
+    int64_t splits = std::max<int64_t>(1, std::min<int64_t>(B, (2 * sms + gx - 1) / gx));
+    splits = std::min<int64_t>(splits, 65535);
+    const int64_t chunk = ceil_div64(B, splits);
+    dim3 grid(gx, (unsigned)ceil_div64(B, chunk));
+#define SG2_EL(MJ) equal_linear_kernel<T, MJ><<<grid, 256, 0, st>>>((T *)out, (const T *)x, (const T *)w, (const T *)bias, B, in_dim, out_dim, w_scale, lr_mul, act, chunk)
+    SG2_DISPATCH_DTYPE(dtype, {
+        if (in_dim <= 512) SG2_EL(16);
+        else if (in_dim <= 1024) SG2_EL(32);
+        else if (in_dim <= 2048) SG2_EL(64);
+        else
+            equal_linear_wide_kernel<T><<<grid, 256, 0, st>>>((T *)out, (const T *)x, (const T *)w, (const T *)bias, B, in_dim, out_dim, w_scale, lr_mul, act, chunk);
+        SG2_LAUNCH_CHECK();
+    });
+#undef SG2_EL
+    return SG2_OK;
+}
+
+namespace sg2 {
+// Pointer tables travel by value in the kernel's parameter bank: no device allocation, no copy.
+struct PtrTables { const void *w[32]; const void *b[32]; };
+
+// Whole mapping network for TS samples per block; activations ping-pong in shared memory, every
+// warp owns output features o = warp, warp+8, ... and streams that weight row once per layer.
+template <typename T, int TS>
+__global__ void __launch_bounds__(256)
+mapping_kernel(T *__restrict__ w_out, const T *__restrict__ z, PtrTables tabs, int n_mlp, int64_t B,
+               int dim, float w_scale, float lr_mul, int pixel_norm) {
+    extern __shared__ float s_act[];   // [2][TS][dim]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t b0 = (int64_t)blockIdx.x * TS;
+    float *cur = s_act, *nxt = s_act + TS * dim;
+    for (int s = warp; s < TS; s += 8) {   // load + pixel norm (model.py:14-15): one warp per sample
+        const int64_t b = b0 + s;
+        float ss = 0.f;
+        for (int j = lane; j < dim; j += 32) {
+            const float v = b < B ? Cvt<T>::to_f(z[b * dim + j]) : 0.f;
+            cur[s * dim + j] = v;
+            ss += v * v;
+        }
+        ss = warp_sum(ss);
+        if (pixel_norm) {
+            const float r = rsqrtf(ss / (float)dim + 1e-8f);
+            for (int j = lane; j < dim; j += 32) cur[s * dim + j] *= r;
+        }
+    }
+    __syncthreads();
+    const int nj = dim / 32;   // dim is a multiple of 32, <= 1024
+    for (int l = 0; l < n_mlp; ++l) {
+        const T *W = (const T *)tabs.w[l];
+        const T *Bv = (const T *)tabs.b[l];
+        for (int o = warp; o < dim; o += 8) {
+            float acc[TS];
+#pragma unroll
+            for (int s = 0; s < TS; ++s) acc[s] = 0.f;
+            for (int j = 0; j < nj; ++j) {
+                const float wv = Cvt<T>::to_f(W[(int64_t)o * dim + lane + 32 * j]);
+#pragma unroll
+                for (int s = 0; s < TS; ++s) acc[s] += cur[s * dim + lane + 32 * j] * wv;
+            }
+            const float bv = Cvt<T>::to_f(Bv[o]) * lr_mul;
+#pragma unroll
+            for (int s = 0; s < TS; ++s) {
+                float v = warp_sum(acc[s]) * w_scale + bv;
+                v = (v > 0.f ? v : v * kLreluSlope) * kLreluGain;
+                if (lane == 0) nxt[s * dim + o] = v;
+            }
+        }
+        __syncthreads();
+        float *t = cur; cur = nxt; nxt = t;
+    }
+    for (int i = threadIdx.x; i < TS * dim; i += 256) {
+        const int s = i / dim;
+        const int64_t b = b0 + s;
+        if (b < B) w_out[b * dim + (i - s * dim)] = Cvt<T>::from_f(cur[i]);
+    }
+}
+
+template <typename T, int TS>
+static int launch_mapping(void *w_out, const void *z, const PtrTables &tabs, int n_mlp, int64_t B,
+                          int dim, float w_scale, float lr_mul, int pixel_norm, cudaStream_t st) {
+    const size_t smem = sizeof(float) * 2 * TS * dim;
+    if (smem > 48 * 1024)
+        SG2_CUDA_OK(cudaFuncSetAttribute(mapping_kernel<T, TS>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mapping_kernel<T, TS><<<(unsigned)ceil_div64(B, TS), 256, smem, st>>>(
+        (T *)w_out, (const T *)z, tabs, n_mlp, B, dim, w_scale, lr_mul, pixel_norm);
+    SG2_LAUNCH_CHECK();
+    return SG2_OK;
+}
+}  // namespace sg2
+
+extern "C" int sg2_mapping_fwd(void *w_out, const void *z, const void *const *weights,
+                               const void *const *biases, int n_mlp, int64_t B, int dim,
+                               float lr_mul, int pixel_norm, int dtype, sg2_stream_t stream) {
+    SG2_REQUIRE(B >= 0 && n_mlp >= 0 && n_mlp <= 32, SG2_ERR_BAD_ARG, "mapping: bad n_mlp/B");
+    SG2_REQUIRE(dim >= 32 && dim <= 1024 && dim % 32 == 0, SG2_ERR_UNSUPPORTED,
+                "mapping: style_dim must be a multiple of 32 in [32,1024], got %d", dim);
+    SG2_REQUIRE(B <= 0x7fffffffll, SG2_ERR_UNSUPPORTED, "mapping: batch too large");
+    if (B == 0) return SG2_OK;
+    SG2_REQUIRE(w_out && z && (n_mlp == 0 || (weights && biases)), SG2_ERR_BAD_ARG,
+                "mapping: null pointer");
+    PtrTables tabs;
+    for (int i = 0; i < 32; ++i) {
+        tabs.w[i] = i < n_mlp ? weights[i] : nullptr;
+        tabs.b[i] = i < n_mlp ? biases[i] : nullptr;
+        SG2_REQUIRE(i >= n_mlp || (tabs.w[i] && tabs.b[i]), SG2_ERR_BAD_ARG, "mapping: null layer pointer");
+    }
+    const float w_scale = lr_mul / sqrtf((float)dim);   // model.py:144
+    cudaStream_t st = as_stream(stream);
+    const int sms = sm_count();
+    SG2_DISPATCH_DTYPE(dtype, {
+        // few samples: 2 per block for latency; many: 8 per block to amortise the weight stream
+        if (B <= 4 * (int64_t)sms)
+            return launch_mapping<T, 2>(w_out, z, tabs, n_mlp, B, dim, w_scale, lr_mul, pixel_norm, st);
+        return launch_mapping<T, 8>(w_out, z, tabs, n_mlp, B, dim, w_scale, lr_mul, pixel_norm, st);
+    });
+    return SG2_OK;
+}
+
+extern "C" int sg2_modconv2d_prep(float *wt, float *wsq, const void *weight, int Cin, int Cout,
+                                  int k, float conv_scale, int dtype, sg2_stream_t stream) {
+    SG2_REQUIRE(Cin >= 1 && Cout >= 1, SG2_ERR_BAD_ARG, "modconv2d_prep: bad channel counts");
+    SG2_REQUIRE(k == 1 || k == 3, SG2_ERR_UNSUPPORTED, "modconv2d: kernel size must be 1 or 3, got %d", k);
+    SG2_REQUIRE(wt && weight, SG2_ERR_BAD_ARG, "modconv2d_prep: null pointer");
+    dim3 grid((Cout + 31) / 32, (Cin + 31) / 32);
+    SG2_DISPATCH_DTYPE(dtype, {
+        modconv_prep_kernel<T><<<grid, 256, 0, as_stream(stream)>>>(wt, wsq, (const T *)weight, Cin, Cout, k * k, conv_scale);
+        SG2_LAUNCH_CHECK();
+    });
+    return SG2_OK;
+}
+
+extern "C" int sg2_modulation_fwd(float *style, float *demod, const void *latent,
+                                  int64_t latent_stride, const void *mod_w, const void *mod_b,
+                                  const float *wsq, int64_t B, int style_dim, int Cin, int Cout,
+                                  float mod_scale, float lr_mul, int dtype, sg2_stream_t stream) {
+    SG2_REQUIRE(B >= 0 && style_dim >= 1 && Cin >= 1, SG2_ERR_BAD_ARG, "modulation: bad shape");
+    if (B == 0) return SG2_OK;
+    SG2_REQUIRE(style && latent && mod_w && mod_b, SG2_ERR_BAD_ARG, "modulation: null pointer");
+    SG2_REQUIRE(style_dim <= 2048, SG2_ERR_UNSUPPORTED, "modulation: style_dim %d > 2048", style_dim);
+    SG2_REQUIRE(!demod || (wsq && Cout >= 1), SG2_ERR_BAD_ARG, "modulation: demod needs wsq and Cout");
+    SG2_REQUIRE(B <= 65535 * 64ll, SG2_ERR_UNSUPPORTED, "modulation: batch too large");
+    cudaStream_t st = as_stream(stream);
+    dim3 grid((Cin + 7) / 8, (unsigned)std::min<int64_t>(B, 4096));
+    SG2_DISPATCH_DTYPE(dtype, {
+        if (style_dim <= 512)
+            modulation_style_kernel<T, 16><<<grid, 256, 0, st>>>(style, (const T *)latent, latent_stride, (const T *)mod_w, (const T *)mod_b, B, style_dim, Cin, mod_scale, lr_mul);
+        else
+            modulation_style_kernel<T, 64><<<grid, 256, 0, st>>>(style, (const T *)latent, latent_stride, (const T *)mod_w, (const T *)mod_b, B, style_dim, Cin, mod_scale, lr_mul);
+        SG2_LAUNCH_CHECK();
+    });
+    if (demod) {
+        SG2_REQUIRE(B <= 65535, SG2_ERR_UNSUPPORTED, "modulation: batch > 65535 with demodulation");
+        SG2_REQUIRE(Cin <= 12000, SG2_ERR_UNSUPPORTED, "modulation: Cin too large");
+        dim3 g2((Cout + 255) / 256, (unsigned)B);
+        modulation_demod_kernel<<<g2, 256, sizeof(float) * Cin, st>>>(demod, style, wsq, Cin, Cout);
+        SG2_LAUNCH_CHECK();
+    }
+    return SG2_OK;
+}

@@ -1,0 +1,176 @@
+// modconv_simt.cu -- exact (fp32 FFMA) modulated convolution, NCHW, any storage dtype.
+//
+// This is the fp32-parity path of ModulatedConv2d.forward (model.py:232-273): tcgen05 has no
+// fp32 input kind, so the <=1e-3 max-abs gate against the reference's fp32 output is met with
+// CUDA-core FFMA; the bf16 tensor-core engine lives in synth_*.cu.  Formulation (shared with
+// the engine): the weight operand is shared across the batch,
+//     out[b,co,p] = demod[b,co] * sum_{ci,t} wt[ci,t,co] * (style[b,ci] * x[b,ci,p+t])
+// i.e. activations are modulated while they are staged into shared memory and demodulation is
+// a per-(b,co) scale in the epilogue -- no [B,Cout,Cin,k,k] weights, no groups=B.
+//
+// Implicit GEMM: M = Cout, N = (sample, output pixel) flattened over the whole batch so that the
+// 4x4 / 8x8 layers still fill tiles, K = Cin x taps.  The three geometries (stride-1 "same" conv,
+// stride-2 transposed conv as four polyphase sub-convolutions that never multiply inserted zeros,
+// stride-2 conv) differ only in a small tap table.
+#include "common.cuh"
+
+namespace sg2 {
+
+constexpr int BM = 64, BN = 64, KC = 8, MAXT = 9;
+
+struct ConvGeo {
+    int B, Cin, Cout, H, W, OH, OW, kk;   // kk = k*k taps in the weight tensor
+    int PH, PW;                            // phase-local output extent
+    int in_sy, in_sx;                      // input step per phase-local output step
+    int out_sy, out_sx, out_oy, out_ox;    // output pixel = local * out_s + out_o
+    int ntaps;
+    int dy[MAXT], dx[MAXT], widx[MAXT];    // input offset and weight tap index per active tap
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+modconv_simt_kernel(T *__restrict__ out, const T *__restrict__ x, const float *__restrict__ wt,
+                    const float *__restrict__ style, const float *__restrict__ demod, ConvGeo g) {
+    __shared__ __align__(16) float Ws[KC * MAXT][BM];
+    __shared__ __align__(16) float Xs[KC * MAXT][BN];
+
+    __shared__ int s_dy[MAXT], s_dx[MAXT], s_wi[MAXT];   // tap table (dynamic indexing of params spills)
+
+    const int tid = threadIdx.x;
+    if (tid < g.ntaps) { s_dy[tid] = g.dy[tid]; s_dx[tid] = g.dx[tid]; s_wi[tid] = g.widx[tid]; }
+    const int tx = tid & 15, ty = tid >> 4;
+    const int co0 = blockIdx.y * BM;
+    const int64_t n0 = (int64_t)blockIdx.x * BN;
+    const int P = g.PH * g.PW;
+    const int64_t Ntot = (int64_t)g.B * P;
+
+    // staging role: this thread always fills column ln of Xs / Ws, rows lk, lk+4, ...
+    const int ln = tid & 63, lk = tid >> 6;
+    const int64_t n_st = n0 + ln;
+    const bool n_ok = n_st < Ntot;
+    int sb = 0, soy = 0, sox = 0;
+    if (n_ok) {
+        sb = (int)(n_st / P);
+        const int r = (int)(n_st - (int64_t)sb * P);
+        soy = r / g.PW;
+        sox = r - soy * g.PW;
+    }
+    const int iy_base = soy * g.in_sy, ix_base = sox * g.in_sx;
+    const T *xb = x + (int64_t)sb * g.Cin * g.H * g.W;
+    const float *sty = style ? style + (int64_t)sb * g.Cin : nullptr;
+    const int co_st = co0 + ln;
+    const bool co_ok = co_st < g.Cout;
+
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (int ci0 = 0; ci0 < g.Cin; ci0 += KC) {
+        const int nk = KC * g.ntaps;
+        __syncthreads();
+        for (int kk = lk; kk < nk; kk += 4) {
+            const int cil = kk / g.ntaps, t = kk - cil * g.ntaps;
+            const int ci = ci0 + cil;
+            float xv = 0.f, wv = 0.f;
+            if (ci < g.Cin) {
+                if (co_ok) wv = __ldg(wt + ((int64_t)ci * g.kk + s_wi[t]) * g.Cout + co_st);
+                const int iy = iy_base + s_dy[t], ix = ix_base + s_dx[t];
+                if (n_ok && iy >= 0 && ix >= 0 && iy < g.H && ix < g.W)
+                    xv = Cvt<T>::to_f(xb[((int64_t)ci * g.H + iy) * g.W + ix]) * (sty ? __ldg(sty + ci) : 1.f);
+            }
+            Ws[kk][ln] = wv;
+            Xs[kk][ln] = xv;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int kk = 0; kk < nk; ++kk) {
+            const float4 a = *reinterpret_cast<const float4 *>(&Ws[kk][ty * 4]);
+            const float4 b = *reinterpret_cast<const float4 *>(&Xs[kk][tx * 4]);
+            acc[0][0] += a.x * b.x; acc[0][1] += a.x * b.y; acc[0][2] += a.x * b.z; acc[0][3] += a.x * b.w;
+            acc[1][0] += a.y * b.x; acc[1][1] += a.y * b.y; acc[1][2] += a.y * b.z; acc[1][3] += a.y * b.w;
+            acc[2][0] += a.z * b.x; acc[2][1] += a.z * b.y; acc[2][2] += a.z * b.z; acc[2][3] += a.z * b.w;
+            acc[3][0] += a.w * b.x; acc[3][1] += a.w * b.y; acc[3][2] += a.w * b.z; acc[3][3] += a.w * b.w;
+        }
+    }
+
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int64_t n = n0 + tx * 4 + j;
+        if (n >= Ntot) continue;
+        const int b = (int)(n / P);
+        const int r = (int)(n - (int64_t)b * P);
+        const int ly = r / g.PW, lx = r - ly * g.PW;
+        const int oy = ly * g.out_sy + g.out_oy, ox = lx * g.out_sx + g.out_ox;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int co = co0 + ty * 4 + i;
+            if (co >= g.Cout) continue;
+            float v = acc[i][j];
+            if (demod) v *= __ldg(demod + (int64_t)b * g.Cout + co);
+            out[(((int64_t)b * g.Cout + co) * g.OH + oy) * g.OW + ox] = Cvt<T>::from_f(v);
+        }
+    }
+}
+
+}  // namespace sg2
+
+using namespace sg2;
+
+extern "C" int sg2_modconv2d_fwd(void *out, const void *x, const float *wt, const float *style,
+                                 const float *demod, int64_t B, int Cin, int Cout, int H, int W,
+                                 int k, int mode, int dtype, sg2_stream_t stream) {
+    SG2_REQUIRE(B >= 0 && Cin >= 1 && Cout >= 1 && H >= 1 && W >= 1, SG2_ERR_BAD_ARG,
+                "modconv2d: bad shape");
+    SG2_REQUIRE(k == 1 || k == 3, SG2_ERR_UNSUPPORTED, "modconv2d: kernel size must be 1 or 3, got %d", k);
+    SG2_REQUIRE(mode >= 0 && mode <= 2, SG2_ERR_BAD_ARG, "modconv2d: mode must be 0, 1 or 2");
+    SG2_REQUIRE(mode != 2 || (H >= k && W >= k), SG2_ERR_BAD_ARG, "modconv2d: input smaller than kernel");
+    if (B == 0) return SG2_OK;
+    SG2_REQUIRE(out && x && wt, SG2_ERR_BAD_ARG, "modconv2d: null tensor pointer");
+    SG2_REQUIRE(B <= (1 << 20), SG2_ERR_UNSUPPORTED, "modconv2d: batch too large");
+    cudaStream_t st = as_stream(stream);
+
+    ConvGeo g;
+    g.B = (int)B; g.Cin = Cin; g.Cout = Cout; g.H = H; g.W = W; g.kk = k * k;
+    const int nphase = mode == 1 ? 4 : 1;
+    for (int ph = 0; ph < nphase; ++ph) {
+        g.ntaps = 0;
+        if (mode == 0) {          // out[y,x] = sum_t w[t] * in[y + ty - k/2, x + tx - k/2]
+            g.OH = H; g.OW = W; g.PH = H; g.PW = W;
+            g.in_sy = g.in_sx = 1; g.out_sy = g.out_sx = 1; g.out_oy = g.out_ox = 0;
+            for (int a = 0; a < k; ++a)
+                for (int b = 0; b < k; ++b) {
+                    g.dy[g.ntaps] = a - k / 2; g.dx[g.ntaps] = b - k / 2; g.widx[g.ntaps] = a * k + b;
+                    ++g.ntaps;
+                }
+        } else if (mode == 2) {   // out[y,x] = sum_t w[t] * in[2y + ty, 2x + tx]
+            g.OH = (H - k) / 2 + 1; g.OW = (W - k) / 2 + 1; g.PH = g.OH; g.PW = g.OW;
+            g.in_sy = g.in_sx = 2; g.out_sy = g.out_sx = 1; g.out_oy = g.out_ox = 0;
+            for (int a = 0; a < k; ++a)
+                for (int b = 0; b < k; ++b) {
+                    g.dy[g.ntaps] = a; g.dx[g.ntaps] = b; g.widx[g.ntaps] = a * k + b;
+                    ++g.ntaps;
+                }
+        } else {                  // transposed: out[2i+a, 2j+b] += in[i,j] * w[a,b]; phase = parity
+            const int py = ph >> 1, px = ph & 1;
+            g.OH = (H - 1) * 2 + k; g.OW = (W - 1) * 2 + k;
+            g.PH = (g.OH - py + 1) / 2; g.PW = (g.OW - px + 1) / 2;
+            if (g.PH <= 0 || g.PW <= 0) continue;
+            g.in_sy = g.in_sx = 1; g.out_sy = g.out_sx = 2; g.out_oy = py; g.out_ox = px;
+            for (int a = py; a < k; a += 2)
+                for (int b = px; b < k; b += 2) {   // out row 2*ly+py takes tap a from input row ly-(a-py)/2
+                    g.dy[g.ntaps] = -(a - py) / 2; g.dx[g.ntaps] = -(b - px) / 2; g.widx[g.ntaps] = a * k + b;
+                    ++g.ntaps;
+                }
+        }
+        const int64_t Ntot = B * (int64_t)g.PH * g.PW;
+        SG2_REQUIRE(ceil_div64(Ntot, BN) <= 0x7fffffffll, SG2_ERR_UNSUPPORTED, "modconv2d: too many pixels");
+        dim3 grid((unsigned)ceil_div64(Ntot, BN), (Cout + BM - 1) / BM);
+        SG2_DISPATCH_DTYPE(dtype, {
+            modconv_simt_kernel<T><<<grid, 256, 0, st>>>((T *)out, (const T *)x, wt, style, demod, g);
+            SG2_LAUNCH_CHECK();
+        });
+    }
+    return SG2_OK;
+}

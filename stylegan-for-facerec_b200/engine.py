@@ -1,0 +1,150 @@
+"""SynthesisEngine -- host side of the whole-network bf16 tcgen05 engine (`sg2_synth_*` in the C ABI).
+
+Replaces the synthesis loop of Generator.forward (model.py:520-533 of the reference) by ONE C call
+that walks a static launch plan: style/demod tables for every layer, then per layer a TMA-fed
+tcgen05/TMEM implicit-GEMM kernel with demodulation, noise, bias, leaky-relu, the next layer's
+modulation and the ToRGB 1x1 projection fused into its epilogue, plus the FIR kernels of the
+up-sampling layers and the RGB skip chain.  The C side allocates nothing: this class owns the
+workspace (a torch uint8 tensor), hands over pointers to the fp32 master parameters and re-packs
+them into the engine's bf16 layouts whenever they change.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+
+class SynthesisEngine:
+    def __init__(self, generator, max_batch=8):
+        self.G = generator
+        self.lib = _lib.load()
+        self.plan = None
+        self.max_batch = 0
+        self.workspace = None
+        self._packed_version = None
+        self._keep = []
+        if generator.input.input.is_cuda:
+            self._ensure(max_batch)
+
+    # -- plan -------------------------------------------------------------------------------------
+    def _layer_table(self):
+        G = self.G
+        dev = G.input.input.device
+        keep = []
+
+        def f32(t):
+            t = t.detach()
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                t = t.float().contiguous()
+            keep.append(t)
+            return t.data_ptr()
+
+        rows = []
+
+        def styled(m, latent_index, res):
+            c = m.conv
+            rows.append(_lib.ConvParams(f32(c.weight), f32(c.modulation.weight), f32(c.modulation.bias),
+                                        f32(m.noise.weight), f32(m.activate.bias), c.in_channel, c.out_channel,
+                                        c.kernel_size, 1 if c.upsample else 0, latent_index, res))
+
+        def rgb(m, latent_index, res):
+            c = m.conv
+            rows.append(_lib.ConvParams(f32(c.weight), f32(c.modulation.weight), f32(c.modulation.bias),
+                                        None, f32(m.bias), c.in_channel, c.out_channel, c.kernel_size, 0,
+                                        latent_index, res))
+
+        styled(G.conv1, 0, 4)
+        rgb(G.to_rgb1, 1, 4)
+        i = 1
+        for j in range(G.log_size - 2):
+            res = 2 ** (j + 3)
+            styled(G.convs[2 * j], i, res)
+            styled(G.convs[2 * j + 1], i + 1, res)
+            rgb(G.to_rgbs[j], i + 2, res)
+            i += 2
+        const = f32(G.input.input)
+        taps = (G.convs[0].conv.blur.kernel.detach().float().cpu().contiguous() if len(G.convs)
+                else torch.zeros(4, 4))
+        self._keep = keep + [taps]
+        return rows, const, taps, dev
+
+    def _version(self):
+        ps = list(self.G.parameters())
+        return tuple(p._version for p in ps) + tuple(p.data_ptr() for p in ps)
+
+    def _ensure(self, batch):
+        """(re)build plan + workspace + packed weights when the batch outgrows the plan or any
+        parameter changed (in-place update, .to(), load_state_dict)."""
+        v = self._version()
+        if self.plan is not None and batch <= self.max_batch and v == self._packed_version:
+            return
+        if self.plan is not None:
+            self.lib.sg2_synth_destroy(self.plan)
+            self.plan = None
+        rows, const, taps, dev = self._layer_table()
+        if taps.shape != (4, 4):
+            raise RuntimeError("sg2_b200 engine: blur kernel must have 4x4 taps (blur_kernel=[1,3,3,1])")
+        arr = (_lib.ConvParams * len(rows))(*rows)
+        plan = C.c_void_p()
+        mb = max(batch, self.max_batch, 1)
+        _lib.check(self.lib.sg2_synth_create(C.byref(plan), self.G.size, self.G.style_dim, mb, arr, len(rows),
+                                             const, taps.numpy().ctypes.data_as(C.POINTER(C.c_float))),
+                   "synth_create")
+        self.plan, self.max_batch = plan, mb
+        nbytes = self.lib.sg2_synth_workspace_bytes(plan)
+        if self.workspace is None or self.workspace.numel() < nbytes or self.workspace.device != dev:
+            self.workspace = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        with _lib.device_of(self.workspace):
+            _lib.check(self.lib.sg2_synth_pack(self.plan, self.workspace.data_ptr(),
+                                               _lib.stream_of(self.workspace)), "synth_pack")
+        self._packed_version = v
+
+    def describe(self):
+        buf = C.create_string_buffer(1 << 16)
+        self.lib.sg2_synth_describe(self.plan, buf, len(buf))
+        return buf.value.decode()
+
+    # -- forward ----------------------------------------------------------------------------------
+    @torch.no_grad()
+    def synthesize(self, latent, noise):
+        """latent [B, n_latent, style_dim]; noise: list (num_layers) of [B or 1, 1, r, r] tensors or
+        None entries (fresh N(0,1) is drawn, model.py:283-285).  Returns the image [B,3,size,size]."""
+        G = self.G
+        _lib.require_cuda(latent, "latent")
+        B = latent.shape[0]
+        self._ensure(B)
+        lat = latent.detach().float().contiguous()
+        out_dtype = G.input.input.dtype
+        n_layers = G.num_layers
+        ptrs = (C.c_void_p * n_layers)()
+        strides = (C.c_int64 * n_layers)()
+        keep = []
+        for i in range(n_layers):
+            r = 2 ** ((i + 5) // 2)
+            n = noise[i] if noise is not None else None
+            if n is None:
+                n = torch.randn(B, 1, r, r, device=lat.device, dtype=torch.float32)
+            n = n.detach().float().contiguous()
+            if n.numel() == B * r * r and B > 1:
+                strides[i] = r * r
+            elif n.numel() == r * r:
+                strides[i] = 0
+            elif n.numel() == B * r * r:
+                strides[i] = r * r
+            else:
+                raise RuntimeError(f"noise[{i}] of shape {tuple(n.shape)} does not match [{B} or 1, 1, {r}, {r}]")
+            keep.append(n)
+            ptrs[i] = n.data_ptr()
+        image = torch.empty(B, 3, G.size, G.size, device=lat.device, dtype=torch.float32)
+        with _lib.device_of(lat):
+            _lib.check(self.lib.sg2_synth_forward(self.plan, self.workspace.data_ptr(), lat.data_ptr(), B, ptrs,
+                                                  strides, image.data_ptr(), _lib.stream_of(lat)), "synth_forward")
+        return image if out_dtype == torch.float32 else image.to(out_dtype)
+
+    def __del__(self):
+        try:
+            if self.plan is not None:
+                self.lib.sg2_synth_destroy(self.plan)
+        except Exception:
+            pass

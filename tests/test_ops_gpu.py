@@ -1,0 +1,205 @@
+"""GPU parity tests of the op API (through the C ABI) against the oracle and the golden vectors."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _tol(dtype):
+    return {torch.float32: 0.0, torch.float16: 2e-3, torch.bfloat16: 1.6e-2}[dtype]
+
+
+# ---- fused_leaky_relu -------------------------------------------------------------------------------
+def test_lrelu_golden_bit_exact(sg2, oracle, golden, cases):
+    for name, shape in cases.LRELU_CASES:
+        x = oracle.named_randn("lrelu:" + name, shape, 3)
+        b = oracle.named_randn("lrelu_b:" + name, (shape[1],), 3)
+        y = sg2.fused_leaky_relu(x.to(DEV), b.to(DEV)).cpu()
+        assert torch.equal(y, torch.from_numpy(golden["ops"]["lrelu/" + name])), name   # fp32: bit-exact
+
+
+@pytest.mark.parametrize("shape", [(4, 512), (3, 7), (2, 512, 4, 4), (2, 64, 33, 31), (1, 3, 256, 256),
+                                   (5, 17, 9), (2, 32, 128, 128), (1, 1, 1, 1), (0, 8, 4, 4)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+def test_lrelu_vs_oracle(sg2, oracle, shape, dtype):
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(shape, generator=g).to(dtype)
+    b = torch.randn(shape[1], generator=g).to(dtype)
+    y = sg2.fused_leaky_relu(x.to(DEV), b.to(DEV), 0.1, 1.7)
+    assert y.dtype == dtype and y.shape == x.shape
+    ref = oracle.fused_leaky_relu(x.float(), b.float(), 0.1, 1.7)
+    if dtype == torch.float32:
+        assert torch.equal(y.cpu(), ref)
+    else:
+        assert torch.equal(y.cpu(), ref.to(dtype))      # fp32 math then one rounding -> same bits
+
+
+def test_lrelu_all_modes_vs_oracle(sg2, oracle):
+    from importlib import import_module
+    fa = import_module("stylegan-for-facerec_b200.stylegan2.op.fused_act")
+    g = torch.Generator().manual_seed(2)
+    x, ref, b = torch.randn(3, 10, 6, 6, generator=g), torch.randn(3, 10, 6, 6, generator=g), torch.randn(10, generator=g)
+    for act in (1, 3):
+        for grad in (0, 1, 2):
+            y = fa.bias_act(x.to(DEV), b.to(DEV), ref.to(DEV), act, grad, 0.2, 1.5).cpu()
+            assert torch.equal(y, oracle.bias_act(x, b, ref, act, grad, 0.2, 1.5)), (act, grad)
+    y = fa.bias_act(x.to(DEV), None, None, 3, 0, 0.2, 1.0).cpu()
+    assert torch.equal(y, oracle.bias_act(x, None, None, 3, 0, 0.2, 1.0))
+
+
+def test_lrelu_noncontiguous_and_unaligned(sg2, oracle):
+    x = torch.randn(4, 6, 10, 10)
+    b = torch.randn(6)
+    xt = x.to(DEV).permute(0, 1, 3, 2)             # non-contiguous view
+    assert torch.equal(sg2.fused_leaky_relu(xt, b.to(DEV)).cpu(), oracle.fused_leaky_relu(x.permute(0, 1, 3, 2), b))
+    big = torch.randn(4 * 6 * 9 * 9 + 1, device=DEV)
+    xo = big[1:].view(4, 6, 9, 9)                   # 4-byte aligned only -> scalar path
+    assert torch.equal(sg2.fused_leaky_relu(xo, b.to(DEV)).cpu(), oracle.fused_leaky_relu(xo.cpu(), b))
+
+
+def test_lrelu_backward_and_double_backward(sg2, oracle, golden, cases):
+    for name, shape in cases.LRELU_CASES:
+        x = oracle.named_randn("lrelu:" + name, shape, 3).to(DEV).requires_grad_(True)
+        b = oracle.named_randn("lrelu_b:" + name, (shape[1],), 3).to(DEV).requires_grad_(True)
+        gy = oracle.named_randn("lrelu_gy:" + name, shape, 3).to(DEV)
+        y = sg2.fused_leaky_relu(x, b)
+        gx, gb = torch.autograd.grad(y, [x, b], gy, create_graph=True)
+        np.testing.assert_allclose(gx.detach().cpu().numpy(), golden["ops"]["lrelu_gx/" + name], rtol=0, atol=1e-6)
+        np.testing.assert_allclose(gb.detach().cpu().numpy(), golden["ops"]["lrelu_gb/" + name], rtol=1e-5, atol=1e-5)
+        # second order: d/dgy of (gx . v) = act'(out) * v * scale  (op/fused_act.py:41-47)
+        gy2 = gy.clone().requires_grad_(True)
+        gx2, _ = torch.autograd.grad(sg2.fused_leaky_relu(x, b), [x, b], gy2, create_graph=True)
+        v = torch.randn_like(gx2)
+        ggy, = torch.autograd.grad(gx2, gy2, v)
+        mask = (y.detach() > 0).float()
+        expect = v * (mask + (1 - mask) * 0.2) * 2 ** 0.5
+        np.testing.assert_allclose(ggy.cpu().numpy(), expect.cpu().numpy(), rtol=1e-6, atol=1e-6)
+
+
+def test_lrelu_module(sg2):
+    m = sg2.FusedLeakyReLU(8).to(DEV)
+    assert list(m.state_dict()) == ["bias"] and m.negative_slope == 0.2 and m.scale == 2 ** 0.5
+    x = torch.randn(2, 8, 5, 5, device=DEV)
+    assert torch.equal(m(x), torch.nn.functional.leaky_relu(x, 0.2) * (2 ** 0.5))
+
+
+@pytest.mark.parametrize("n", [64 * 128 * 256 * 256])      # BASELINE config 2's largest activation
+def test_lrelu_full_size_properties(sg2, n):
+    """size-independent properties at full size: positive homogeneity and the exact 0.2 ratio."""
+    x = torch.randn(64, 128, 256, 256, device=DEV, dtype=torch.bfloat16)
+    zero = torch.zeros(128, device=DEV, dtype=torch.bfloat16)
+    y = sg2.fused_leaky_relu(x, zero, 0.25, 2.0)       # powers of two: exact in bf16
+    assert torch.equal(y, torch.where(x > 0, x * 2, x * 0.5))
+    del y
+    torch.cuda.empty_cache()
+
+
+# ---- upfirdn2d ----------------------------------------------------------------------------------------
+def test_upfirdn2d_golden(sg2, oracle, golden, cases):
+    for name, shape, kspec, up, down, pad in cases.UPFIRDN_CASES:
+        x = oracle.named_randn("upfirdn:" + name, shape, 3)
+        y = sg2.upfirdn2d(x.to(DEV), cases.fir(kspec).to(DEV), up, down, pad).cpu()
+        ref = torch.from_numpy(golden["ops"]["upfirdn2d/" + name])
+        assert y.shape == ref.shape, name
+        np.testing.assert_allclose(y.numpy(), ref.numpy(), rtol=0, atol=3e-6, err_msg=name)
+
+
+UFD_SWEEP = [
+    # shape, k, up, down, pad
+    ((2, 8, 257, 257), 4, 1, 1, (1, 1)), ((2, 3, 128, 128), 4, 2, 1, (2, 1)), ((2, 8, 256, 256), 4, 1, 2, (1, 1)),
+    ((3, 5, 4, 4), 4, 1, 1, (1, 1)), ((3, 5, 4, 4), 4, 2, 1, (2, 1)), ((1, 2, 5, 5), 4, 1, 2, (1, 1)),
+    ((1, 4, 33, 65), 3, 1, 1, (1, 1)), ((1, 4, 33, 65), 2, 2, 1, (1, 0)), ((1, 3, 40, 24), 4, 2, 1, (1, 2)),
+    ((1, 3, 40, 24), 4, 2, 1, (3, 0)), ((1, 2, 31, 31), 5, 1, 1, (2, 2)), ((1, 2, 20, 20), 6, 3, 1, (3, 2)),
+    ((1, 2, 20, 20), 4, 2, 2, (1, 1)), ((1, 2, 30, 30), 7, 1, 3, (3, 3)), ((2, 2, 16, 16), 4, 1, 1, (-1, -1)),
+    ((1, 1, 9, 9), 1, 1, 1, (0, 0)), ((1, 2, 12, 12), 12, 1, 1, (6, 5)), ((1, 2, 16, 16), 4, 4, 1, (3, 0)),
+]
+
+
+@pytest.mark.parametrize("shape,k,up,down,pad", UFD_SWEEP)
+def test_upfirdn2d_sweep_vs_oracle(sg2, oracle, shape, k, up, down, pad):
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(shape, generator=g)
+    taps = torch.randn(k, k, generator=g)             # asymmetric: the flip matters
+    y = sg2.upfirdn2d(x.to(DEV), taps.to(DEV), up, down, pad).cpu()
+    ref = oracle.upfirdn2d(x.double(), taps.double(), up, down, pad).float()
+    assert y.shape == ref.shape
+    np.testing.assert_allclose(y.numpy(), ref.numpy(), rtol=0, atol=2e-5 * k)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_upfirdn2d_low_precision_accumulates_in_fp32(sg2, oracle, dtype):
+    x = torch.randn(2, 4, 64, 64).to(dtype)
+    taps = sg2.make_kernel([1, 3, 3, 1]) * 4
+    for up, down, pad in ((1, 1, (1, 1)), (2, 1, (2, 1)), (1, 2, (1, 1))):
+        y = sg2.upfirdn2d(x.to(DEV), taps.to(DEV), up, down, pad)
+        assert y.dtype == dtype
+        ref = oracle.upfirdn2d(x.float(), taps, up, down, pad)
+        assert torch.equal(y.cpu(), ref.to(dtype)) or (y.cpu().float() - ref).abs().max() <= _tol(dtype) * ref.abs().max()
+
+
+def test_upfirdn2d_rectangular_taps_and_minor_dim(sg2, oracle):
+    from importlib import import_module
+    um = import_module("stylegan-for-facerec_b200.stylegan2.op.upfirdn2d")
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(3, 10, 12, 5, generator=g)                       # [major, h, w, minor]
+    taps = torch.randn(3, 4, generator=g)
+    y = um.upfirdn2d_raw(x.to(DEV), taps.to(DEV), 2, 1, 1, 2, 1, 2, 0, 1).cpu()
+    xr = x.permute(0, 3, 1, 2).reshape(1, 15, 10, 12)
+    ref = oracle.upfirdn2d_xy(xr, taps, 2, 1, 1, 2, 1, 2, 0, 1)
+    ref = ref.reshape(3, 5, ref.shape[2], ref.shape[3]).permute(0, 2, 3, 1)
+    np.testing.assert_allclose(y.numpy(), ref.numpy(), rtol=0, atol=1e-5)
+
+
+def test_upfirdn2d_unsupported_config_raises(sg2):
+    x = torch.randn(1, 1, 8, 8, device=DEV)
+    with pytest.raises(RuntimeError, match="unsupported configuration"):
+        sg2.upfirdn2d(x, torch.ones(4, 4, device=DEV), up=5)          # reference: silent garbage
+    with pytest.raises(RuntimeError, match="unsupported configuration"):
+        sg2.upfirdn2d(x, torch.ones(17, 17, device=DEV), pad=(8, 8))
+    with pytest.raises(RuntimeError, match="empty output"):
+        sg2.upfirdn2d(x, torch.ones(4, 4, device=DEV), pad=(-4, -4))
+
+
+def test_upfirdn2d_backward_is_the_adjoint(sg2, oracle):
+    g = torch.Generator().manual_seed(5)
+    for shape, k, up, down, pad in [((2, 3, 17, 17), 4, 1, 1, (1, 1)), ((2, 3, 8, 8), 4, 2, 1, (2, 1)),
+                                    ((1, 2, 16, 16), 4, 1, 2, (1, 1)), ((1, 2, 9, 7), 3, 2, 1, (1, 1))]:
+        x = torch.randn(shape, generator=g)
+        taps = torch.randn(k, k, generator=g)
+        xd = x.to(DEV).requires_grad_(True)
+        y = sg2.upfirdn2d(xd, taps.to(DEV), up, down, pad)
+        gy = torch.randn(y.shape, generator=g)
+        gx, = torch.autograd.grad(y, xd, gy.to(DEV), create_graph=True)
+        xo = x.double().requires_grad_(True)
+        go, = torch.autograd.grad(oracle.upfirdn2d(xo, taps.double(), up, down, pad), xo, gy.double())
+        np.testing.assert_allclose(gx.detach().cpu().numpy(), go.float().numpy(), rtol=0, atol=1e-4)
+        # double backward: linear op -> d(gx.v)/dgy = upfirdn2d(v)
+        gyd = gy.to(DEV).requires_grad_(True)
+        gx2, = torch.autograd.grad(sg2.upfirdn2d(xd, taps.to(DEV), up, down, pad), xd, gyd, create_graph=True)
+        v = torch.randn(shape, generator=g)
+        ggy, = torch.autograd.grad(gx2, gyd, v.to(DEV))
+        np.testing.assert_allclose(ggy.cpu().numpy(), oracle.upfirdn2d(v.double(), taps.double(), up, down, pad).float().numpy(),
+                                   rtol=0, atol=1e-4)
+
+
+def test_upfirdn2d_full_size_properties(sg2):
+    """BASELINE config 2's largest blur: [64*128, 257, 257] -> 256^2, bf16.  Properties that hold
+    at any size: DC gain (taps sum to 4 -> constant in, 4*constant out away from the border),
+    linearity, and up2 of a constant image reproduces the constant in the interior."""
+    taps = (sg2.make_kernel([1, 3, 3, 1]) * 4).to(DEV)
+    x = torch.full((64, 128, 257, 257), 0.5, device=DEV, dtype=torch.bfloat16)
+    y = sg2.upfirdn2d(x, taps, pad=(1, 1))
+    assert y.shape == (64, 128, 256, 256)
+    assert torch.all(y[:, :, 1:-1, 1:-1] == 2.0)
+    del x, y
+    torch.cuda.empty_cache()
+    a = torch.randn(8, 16, 128, 128, device=DEV)
+    b = torch.randn(8, 16, 128, 128, device=DEV)
+    ya, yb, yab = (sg2.upfirdn2d(t, taps, up=2, pad=(2, 1)) for t in (a, b, a + 2 * b))
+    assert (yab - (ya + 2 * yb)).abs().max() < 2e-5
+    c = sg2.upfirdn2d(torch.ones(1, 1, 64, 64, device=DEV), taps, up=2, pad=(2, 1))
+    assert torch.allclose(c[:, :, 2:-2, 2:-2], torch.ones(1, 1, 124, 124, device=DEV))

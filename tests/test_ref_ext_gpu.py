@@ -1,0 +1,61 @@
+"""GPU: our kernels against the REFERENCE's own compiled CUDA extensions (oracle/_ref/*.so, built
+from /root/reference/backbone/stylegan2/op by oracle/build_ref.py in the authoring container).
+Same inputs, fp32 -> fused_bias_act bit-exact, upfirdn2d to fp32 rounding of a 16-tap sum."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+
+
+def _load(name):
+    path = os.path.join(REF_DIR, name + ".so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref not built (needs /root/reference; run `make -C oracle ref` in the authoring container)")
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_fused_bias_act_vs_reference_extension(sg2):
+    ref = _load("fused")
+    fa = importlib.import_module("stylegan-for-facerec_b200.stylegan2.op.fused_act")
+    g = torch.Generator().manual_seed(11)
+    for shape in [(4, 512), (2, 16, 31, 33), (2, 512, 4, 4), (1, 32, 256, 256)]:
+        x = torch.randn(shape, generator=g).to(DEV)
+        b = torch.randn(shape[1], generator=g).to(DEV)
+        empty = x.new_empty(0)
+        out = ref.fused_bias_act(x, b, empty, 3, 0, 0.2, 2 ** 0.5)
+        assert torch.equal(sg2.fused_leaky_relu(x, b), out)
+        gy = torch.randn(shape, generator=g).to(DEV)
+        assert torch.equal(fa.bias_act(gy, None, out, 3, 1, 0.2, 2 ** 0.5),
+                           ref.fused_bias_act(gy, empty, out, 3, 1, 0.2, 2 ** 0.5))
+    xh = torch.randn(2, 8, 16, 16, generator=g).half().to(DEV)
+    bh = torch.randn(8, generator=g).half().to(DEV)
+    ours, theirs = sg2.fused_leaky_relu(xh, bh), ref.fused_bias_act(xh, bh, xh.new_empty(0), 3, 0, 0.2, 2 ** 0.5)
+    assert (ours.float() - theirs.float()).abs().max() <= 4e-3 * theirs.float().abs().max()   # ref rounds every step to fp16
+
+
+def test_upfirdn2d_vs_reference_extension(sg2):
+    ref = _load("upfirdn2d")
+    g = torch.Generator().manual_seed(12)
+    # the six modes the reference implements (upfirdn2d_kernel.cu:177-211)
+    for shape, k, up, down, pad in [((2, 4, 65, 65), 4, 1, 1, (1, 1)), ((2, 4, 40, 40), 3, 1, 1, (1, 1)),
+                                    ((2, 3, 32, 32), 4, 2, 1, (2, 1)), ((2, 3, 32, 32), 2, 2, 1, (1, 0)),
+                                    ((2, 4, 64, 64), 4, 1, 2, (1, 1)), ((2, 4, 64, 64), 2, 1, 2, (0, 0)),
+                                    ((64, 3, 4, 4), 4, 2, 1, (2, 1)), ((1, 8, 257, 257), 4, 1, 1, (1, 1))]:
+        x = torch.randn(shape, generator=g).to(DEV)
+        taps = torch.randn(k, k, generator=g).to(DEV)
+        b, c, h, w = shape
+        theirs = ref.upfirdn2d(x.reshape(-1, h, w, 1), taps, up, up, down, down, pad[0], pad[1], pad[0], pad[1])
+        ours = sg2.upfirdn2d(x, taps, up, down, pad)
+        theirs = theirs.view(b, c, ours.shape[2], ours.shape[3])
+        np.testing.assert_allclose(ours.cpu().numpy(), theirs.cpu().numpy(), rtol=0, atol=1e-5)
