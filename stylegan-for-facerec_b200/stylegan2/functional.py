@@ -191,11 +191,12 @@ class SharedConvFunction(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             import torch.nn.grad as G
             xf, gf = x.detach().float(), gy.detach().float()
-            if mode == 0:
-                gw = G.conv2d_weight(xf, weight4.shape, gf, padding=k // 2)
-            elif mode == 2:
-                gw = G.conv2d_weight(xf, weight4.shape, gf, stride=2)
-            else:   # y = conv_transpose(x, W^T): dW[co,ci] = corr(gy[co], x[ci]) at stride 2
-                gw = G.conv2d_weight(gf, (cin, cout, k, k), xf, stride=2).transpose(0, 1)
+            with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):   # true-fp32 wgrad
+                if mode == 0:
+                    gw = G.conv2d_weight(xf, weight4.shape, gf, padding=k // 2)
+                elif mode == 2:
+                    gw = G.conv2d_weight(xf, weight4.shape, gf, stride=2)
+                else:   # y = conv_transpose(x, W^T): dW[co,ci] = corr(gy[co], x[ci]) at stride 2
+                    gw = G.conv2d_weight(gf, (cin, cout, k, k), xf, stride=2).transpose(0, 1)
             gw = gw.to(weight4.dtype)
         return gx, gw, None

@@ -1,0 +1,91 @@
+#!/usr/bin/env python
+"""Op microbench sweep (BASELINE.json config 5): upfirdn2d {blur, up2, down2} and fused_leaky_relu /
+noise+bias+act across resolutions and channel widths, achieved GB/s vs the measured HBM peak.
+
+Algorithmic bytes: lrelu 2*N*s + C*s; upfirdn2d (N_in + N_out)*s + 64;
+noise-add 2*N*s + B*r^2*s.  Timing: CUDA events, 5 warm-up + 20 timed launches; every tensor is
+>= 2x L2 where the shape allows (inputs larger than L2), otherwise an L2 flush buffer is written
+between launches.   python tools/opbench.py [--quick] > profiles/opbench_rNN.jsonl
+"""
+import argparse
+import importlib
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p))["hbm_gbs"], "measured"
+    return 6650.0, "fallback"
+
+
+def timeit(fn, flush, iters=20, warm=5):
+    for _ in range(warm):
+        fn()
+    evs = []
+    for _ in range(iters):
+        if flush is not None:
+            flush.add_(1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    ts = sorted(a.elapsed_time(b) for a, b in evs)
+    return ts[len(ts) // 2] * 1e-3
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--quick", action="store_true")
+    args = ap.parse_args()
+    sg2 = importlib.import_module("stylegan-for-facerec_b200")
+    dev = "cuda:0"
+    peak, which = peak_gbs()
+    flush = torch.zeros(256 << 20, dtype=torch.uint8, device=dev)   # 256 MiB > 126 MB L2
+    taps = (sg2.make_kernel([1, 3, 3, 1])).to(dev)
+    res_list = [4, 16, 64, 256, 1024] if args.quick else [4, 8, 16, 32, 64, 128, 256, 512, 1024]
+    ch_list = [3, 64, 512] if args.quick else [3, 32, 64, 128, 256, 512]
+    target_elems = 1 << 28 if not args.quick else 1 << 26     # ~256 Mi elements per tensor
+    for dtype in (torch.float32, torch.bfloat16):
+        s = torch.finfo(dtype).bits // 8
+        for r in res_list:
+            for c in ch_list:
+                B = max(1, min(4096, target_elems // (c * r * r)))
+                n = B * c * r * r
+                if n * s > 6 << 30:
+                    continue
+                x = torch.randn(B, c, r, r, device=dev, dtype=dtype)
+                bias = torch.randn(c, device=dev, dtype=dtype)
+                need_flush = flush if n * s < (256 << 20) else None
+                rows = []
+                t = timeit(lambda: sg2.fused_leaky_relu(x, bias), need_flush)
+                rows.append(("fused_leaky_relu", 2 * n * s + c * s, t))
+                if r >= 4 and r <= 512:
+                    t = timeit(lambda: sg2.upfirdn2d(x, taps * 4, up=2, pad=(2, 1)), need_flush)
+                    rows.append(("upfirdn2d_up2", (n + 4 * n) * s + 64, t))
+                if r >= 8:
+                    t = timeit(lambda: sg2.upfirdn2d(x, taps, down=2, pad=(1, 1)), need_flush)
+                    rows.append(("upfirdn2d_down2", (n + n // 4) * s + 64, t))
+                xb = torch.randn(B, c, r + 1, r + 1, device=dev, dtype=dtype)
+                t = timeit(lambda: sg2.upfirdn2d(xb, taps * 4, pad=(1, 1)), need_flush)
+                rows.append(("upfirdn2d_blur", (xb.numel() + n) * s + 64, t))
+                del xb
+                for op, nbytes, t in rows:
+                    print(json.dumps({"op": op, "dtype": str(dtype).split(".")[1], "B": B, "C": c, "res": r,
+                                      "bytes": nbytes, "ms": round(t * 1e3, 4), "GBps": round(nbytes / t / 1e9, 1),
+                                      "frac_of_hbm_peak": round(nbytes / t / 1e9 / peak, 3), "peak": which}), flush=True)
+                del x
+                torch.cuda.empty_cache()
+
+
+if __name__ == "__main__":
+    main()
