@@ -1,0 +1,290 @@
+// synth_gemm.cu -- ModulatedConv2d as ONE tcgen05/TMEM implicit-GEMM kernel fed by TMA (sm_100a).
+//
+// Replaces the ~12 PyTorch ops + cuDNN grouped conv of ModulatedConv2d.forward / StyledConv.forward
+// (model.py:232-273, 331-337 of the reference).  Formulation:
+//     y[b,p,co] = demod[b,co] * sum_{tap,ci} Wp[tap,co,ci] * Xm[b, p+tap, ci]
+// with Xm = x * style already applied by the PRODUCER of x (previous layer's epilogue), Wp the
+// batch-shared bf16 weights (conv_scale folded in), demod a per-(b,co) epilogue scale.  So the
+// whole batch is one GEMM  [M = B*H*W pixels] x [N = Cout] x [K = taps*Cin]  -- no per-sample
+// weights, no groups=B.
+//
+//   A (activations): NHWC bf16, TMA 4-D tiled loads {64 ch, TW, TH, NB}; the filter tap is a
+//       coordinate offset and TMA's out-of-bounds zero fill is the convolution's zero padding.
+//   B (weights): [tap][Cout][Cin] bf16, TMA 3-D loads {64, BLOCK_N, 1}.  Both land in shared memory
+//       as K-major SWIZZLE_128B tiles, which is the canonical UMMA operand layout.
+//   D: fp32 accumulators in TMEM, 128 lanes x BLOCK_N columns, double buffered (2 x 256 columns)
+//       so the epilogue of tile i overlaps the MMAs of tile i+1.
+//   Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) + TMEM allocator,
+//       warps 2..5 = epilogue (tcgen05.ld -> demod, +noise, +bias, lrelu, ToRGB partial dot,
+//       x next layer's style, bf16 pack, store).
+//   The transposed stride-2 convolution of the up-sampling layers runs as four polyphase
+//   sub-problems (4/2/2/1 taps) of the same kernel: no multiplies by inserted zeros.
+//   Persistent: grid = #SMs, static round-robin tile schedule.
+#include "common.cuh"
+#include "synth_gemm.cuh"
+#include "tc_ptx.cuh"
+
+namespace sg2 {
+
+using namespace tc;
+
+constexpr int kGemmThreads = 192;
+constexpr int kABytes = kBlockM * kBlockK * 2;          // 16 KiB
+constexpr int kBBytesMax = kMaxBlockN * kBlockK * 2;    // 32 KiB
+constexpr int kEpiCap = 512;                            // NB * BLOCK_N entries of per-sample epilogue params
+constexpr float kSlope = 0.2f;
+
+struct __align__(1024) GemmSmem {
+    uint8_t a[kStages][kABytes];
+    uint8_t b[kStages][kBBytesMax];
+    float e_demod[kEpiCap];
+    float e_next[kEpiCap];
+    float e_wrgb[3][kEpiCap];
+    float e_bias[kMaxBlockN];
+    uint64_t full[kStages], empty[kStages];
+    uint64_t tmem_full[2], tmem_empty[2];
+    uint32_t tmem_base;
+};
+
+struct TileCoord {
+    int sub, nt, x0, y0, b0;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const GemmParams &p, int tile) {
+    TileCoord t;
+    int s = 0;
+#pragma unroll
+    for (int i = 1; i < kGemmMaxSub; ++i)
+        if (i < p.nsub && tile >= p.sub[i].tile_begin) s = i;
+    const GemmSub &g = p.sub[s];
+    const int local = tile - g.tile_begin;
+    t.sub = s;
+    t.nt = local % p.n_tiles_n;
+    int mt = local / p.n_tiles_n;
+    const int bx = mt % g.tiles_x;
+    mt /= g.tiles_x;
+    const int by = mt % g.tiles_y;
+    const int bb = mt / g.tiles_y;
+    t.x0 = bx * g.TW;
+    t.y0 = by * g.TH;
+    t.b0 = bb * g.NB;
+    return t;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t *>(&v);
+}
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+modconv_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ CUtensorMap tmA0,
+                    const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
+                    const __grid_constant__ CUtensorMap tmA3, const __grid_constant__ CUtensorMap tmB) {
+    extern __shared__ uint8_t smem_raw[];
+    GemmSmem &sm = *reinterpret_cast<GemmSmem *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA0);
+        tma_prefetch_desc(&tmB);
+        for (int i = 0; i < kStages; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&sm.tmem_full[i], 1); mbar_init(&sm.tmem_empty[i], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(&sm.tmem_base, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = sm.tmem_base;
+    const uint32_t b_bytes = (uint32_t)p.block_n * kBlockK * 2;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const TileCoord t = decode_tile(p, tile);
+                const GemmSub &g = p.sub[t.sub];
+                const CUtensorMap *tmA = t.sub == 0 ? &tmA0 : (t.sub == 1 ? &tmA1 : (t.sub == 2 ? &tmA2 : &tmA3));
+                const uint32_t a_bytes = (uint32_t)(g.TH * g.TW * g.NB) * kBlockK * 2;
+                for (int kc = 0; kc < p.kchunks; ++kc) {
+                    for (int tap = 0; tap < g.ntaps; ++tap) {
+                        mbar_wait(&sm.empty[stage], phase ^ 1);
+                        mbar_arrive_expect_tx(&sm.full[stage], a_bytes + b_bytes);
+                        tma_load_4d(sm.a[stage], tmA, &sm.full[stage], kc * kBlockK, t.x0 + g.dx[tap],
+                                    t.y0 + g.dy[tap], t.b0);
+                        tma_load_3d(sm.b[stage], &tmB, &sm.full[stage], kc * kBlockK, t.nt * p.block_n,
+                                    g.wtap[tap]);
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_bf16(kBlockM, (uint32_t)p.block_n);
+            uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const TileCoord t = decode_tile(p, tile);
+                const int nstage = p.kchunks * p.sub[t.sub].ntaps;
+                mbar_wait(&sm.tmem_empty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * kMaxBlockN;
+                for (int s = 0; s < nstage; ++s) {
+                    mbar_wait(&sm.full[stage], phase);
+                    tc_fence_after();
+                    const uint64_t adesc = make_smem_desc(smem_u32(sm.a[stage]), 128);
+                    const uint64_t bdesc = make_smem_desc(smem_u32(sm.b[stage]), 128);
+#pragma unroll
+                    for (int k = 0; k < kBlockK / 16; ++k)   // advance 32 bytes (>>4 = 2) inside the swizzle row
+                        umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (s | k) != 0);
+                    umma_commit(&sm.empty[stage]);           // frees the smem slot when these MMAs retire
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&sm.tmem_full[acc]);             // accumulator complete -> epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ===================== epilogue (4 warps = 128 TMEM lanes) =====================
+        const int q = warp & 3;                      // TMEM lane quarter this warp may access
+        const int m = q * 32 + lane;                 // accumulator row = pixel of the tile
+        const int et = threadIdx.x - 64;             // 0..127 within the epilogue group
+        const float nw = (p.mode == 0 && p.noise) ? __ldg(p.noise_weight) : 0.f;
+        uint32_t acc = 0, acc_phase = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            const TileCoord t = decode_tile(p, tile);
+            const GemmSub &g = p.sub[t.sub];
+            const int n0 = t.nt * p.block_n;
+            const int N = p.block_n;
+            // ---- stage the per-(sample, channel) epilogue parameters of this tile ----
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            for (int i = et; i < g.NB * N; i += 128) {
+                const int nb = i / N, col = i - nb * N;
+                const int b = t.b0 + nb < p.B ? t.b0 + nb : p.B - 1;
+                const long long o = (long long)b * p.Cout + n0 + col;
+                sm.e_demod[i] = __ldg(p.demod + o);
+                if (p.mode == 0) {
+                    sm.e_next[i] = p.next_style ? __ldg(p.next_style + o) : 0.f;
+                    if (p.wrgb) {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c)
+                            sm.e_wrgb[c][i] = __ldg(p.wrgb + ((long long)b * 3 + c) * p.Cout + n0 + col);
+                    }
+                }
+            }
+            if (p.mode == 0)
+                for (int i = et; i < N; i += 128) sm.e_bias[i] = __ldg(p.bias + n0 + i);
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+
+            // ---- which pixel does this lane own ----
+            const int per = g.TH * g.TW;
+            const int nb = m / per;
+            const int rem = m - nb * per;
+            const int ty = rem / g.TW, tx = rem - ty * g.TW;
+            const int y = t.y0 + ty, x = t.x0 + tx, b = t.b0 + nb;
+            const bool valid = nb < g.NB && y < g.PH && x < g.PW && b < p.B;
+            const int pb = (nb < g.NB ? nb : 0) * N;    // row of the staged per-sample params
+            float nz = 0.f;
+            if (valid && p.mode == 0 && p.noise)
+                nz = nw * __ldg(p.noise + (long long)b * p.noise_bstride + (long long)y * g.PW + x);
+            __nv_bfloat16 *orow = nullptr;
+            if (valid && p.out)
+                orow = p.out + g.out_off + (((long long)b * g.out_H + y) * g.out_W + x) * p.Cout + n0;
+
+            mbar_wait(&sm.tmem_full[acc], acc_phase);
+            tc_fence_after();
+            float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
+            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kMaxBlockN;
+            for (int c0 = 0; c0 < N; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(t_row + c0, r);
+                tmem_ld_wait();
+                uint32_t packed[16];
+                if (p.mode == 0) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 d4 = *reinterpret_cast<const float4 *>(&sm.e_demod[pb + c0 + j]);
+                        const float4 b4 = *reinterpret_cast<const float4 *>(&sm.e_bias[c0 + j]);
+                        const float4 s4 = *reinterpret_cast<const float4 *>(&sm.e_next[pb + c0 + j]);
+                        float v[4];
+                        v[0] = fmaf(__uint_as_float(r[j + 0]), d4.x, nz) + b4.x;
+                        v[1] = fmaf(__uint_as_float(r[j + 1]), d4.y, nz) + b4.y;
+                        v[2] = fmaf(__uint_as_float(r[j + 2]), d4.z, nz) + b4.z;
+                        v[3] = fmaf(__uint_as_float(r[j + 3]), d4.w, nz) + b4.w;
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], kSlope * v[e]);   // lrelu (gain folded downstream)
+                        if (p.wrgb) {
+                            const float4 w0 = *reinterpret_cast<const float4 *>(&sm.e_wrgb[0][pb + c0 + j]);
+                            const float4 w1 = *reinterpret_cast<const float4 *>(&sm.e_wrgb[1][pb + c0 + j]);
+                            const float4 w2 = *reinterpret_cast<const float4 *>(&sm.e_wrgb[2][pb + c0 + j]);
+                            rgb0 += v[0] * w0.x + v[1] * w0.y + v[2] * w0.z + v[3] * w0.w;
+                            rgb1 += v[0] * w1.x + v[1] * w1.y + v[2] * w1.z + v[3] * w1.w;
+                            rgb2 += v[0] * w2.x + v[1] * w2.y + v[2] * w2.z + v[3] * w2.w;
+                        }
+                        packed[j / 2 + 0] = pack_bf16(v[0] * s4.x, v[1] * s4.y);
+                        packed[j / 2 + 1] = pack_bf16(v[2] * s4.z, v[3] * s4.w);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 d4 = *reinterpret_cast<const float4 *>(&sm.e_demod[pb + c0 + j]);
+                        packed[j / 2 + 0] = pack_bf16(__uint_as_float(r[j + 0]) * d4.x, __uint_as_float(r[j + 1]) * d4.y);
+                        packed[j / 2 + 1] = pack_bf16(__uint_as_float(r[j + 2]) * d4.z, __uint_as_float(r[j + 3]) * d4.w);
+                    }
+                }
+                if (orow) {
+                    uint4 *dst = reinterpret_cast<uint4 *>(orow + c0);
+#pragma unroll
+                    for (int v4 = 0; v4 < 4; ++v4)
+                        dst[v4] = make_uint4(packed[4 * v4], packed[4 * v4 + 1], packed[4 * v4 + 2], packed[4 * v4 + 3]);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.tmem_empty[acc]);
+            if (valid && p.mode == 0 && p.wrgb) {
+                const long long plane = (long long)g.PH * g.PW;
+                float *rp = p.rgb_part + (((long long)t.nt * p.B + b) * 3) * plane + (long long)y * g.PW + x;
+                rp[0] = rgb0;
+                rp[plane] = rgb1;
+                rp[2 * plane] = rgb2;
+            }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+int launch_modconv_gemm(const GemmParams &p, const CUtensorMap *tmA, const CUtensorMap &tmB, int sms,
+                        cudaStream_t st) {
+    static_assert(sizeof(GemmSmem) + 1024 <= 227 * 1024, "GemmSmem exceeds the 227 KiB CTA limit");
+    static_assert(sizeof(GemmParams) + 5 * sizeof(CUtensorMap) <= 4000, "kernel parameter space");
+    const size_t smem = sizeof(GemmSmem) + 1024;
+    static std::atomic<int> configured{0};
+    if (!configured.load(std::memory_order_acquire)) {
+        SG2_CUDA_OK(cudaFuncSetAttribute(modconv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured.store(1, std::memory_order_release);
+    }
+    SG2_REQUIRE(p.block_n % 16 == 0 && p.block_n >= 16 && p.block_n <= kMaxBlockN, SG2_ERR_BAD_ARG, "gemm: bad BLOCK_N %d", p.block_n);
+    SG2_REQUIRE(p.Cin % kBlockK == 0 && p.Cout % p.block_n == 0, SG2_ERR_UNSUPPORTED,
+                "gemm: Cin %d must be a multiple of 64 and Cout %d of BLOCK_N %d", p.Cin, p.Cout, p.block_n);
+    for (int s = 0; s < p.nsub; ++s)
+        SG2_REQUIRE(p.sub[s].NB * p.block_n <= kEpiCap && p.sub[s].TH * p.sub[s].TW * p.sub[s].NB <= kBlockM,
+                    SG2_ERR_BAD_ARG, "gemm: tile of sub-problem %d too large", s);
+    const int grid = p.total_tiles < sms ? p.total_tiles : sms;
+    if (grid <= 0) return SG2_OK;
+    const CUtensorMap &a0 = tmA[0];
+    const CUtensorMap &a1 = tmA[p.nsub > 1 ? 1 : 0];
+    const CUtensorMap &a2 = tmA[p.nsub > 2 ? 2 : 0];
+    const CUtensorMap &a3 = tmA[p.nsub > 3 ? 3 : 0];
+    modconv_gemm_kernel<<<grid, kGemmThreads, smem, st>>>(p, a0, a1, a2, a3, tmB);
+    SG2_LAUNCH_CHECK();
+    return SG2_OK;
+}
+
+}  // namespace sg2

@@ -1,0 +1,50 @@
+// synth_gemm.cuh -- parameter blocks of the tcgen05 implicit-GEMM modulated-convolution kernel.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace sg2 {
+
+constexpr int kGemmMaxSub = 4;    // polyphase sub-problems per launch (1 plain conv, 4 transposed conv)
+constexpr int kGemmMaxTaps = 9;
+constexpr int kBlockM = 128;      // pixels per tile = TMEM lanes
+constexpr int kBlockK = 64;       // bf16 channels per stage = one 128-byte swizzle row
+constexpr int kStages = 4;
+constexpr int kMaxBlockN = 256;
+
+// One polyphase sub-problem: an output plane [B, PH, PW, Cout] whose pixel (y, x) is
+// sum over taps t of  W[wtap[t]] . X[y + dy[t], x + dx[t], :]   (zero outside X).
+struct GemmSub {
+    int PH, PW;                  // valid output extent of this plane
+    int TH, TW, NB;              // tile extent: TH x TW pixels of NB samples (TH*TW*NB <= 128)
+    int tiles_x, tiles_y, tiles_b;
+    int tile_begin;              // first global tile index of this sub-problem
+    int ntaps;
+    int dy[kGemmMaxTaps], dx[kGemmMaxTaps], wtap[kGemmMaxTaps];
+    long long out_off;           // element offset of the plane inside `out`
+    int out_H, out_W;            // allocated plane extent (row pitch = out_W * Cout)
+};
+
+struct GemmParams {
+    int nsub;
+    GemmSub sub[kGemmMaxSub];
+    int B, Cin, Cout;
+    int block_n, n_tiles_n, total_tiles, kchunks;   // kchunks = Cin / 64
+    // epilogue
+    int mode;                       // 0: styled conv (noise, bias, lrelu, next-style, ToRGB); 1: plain scaled store
+    const float *demod;             // [B, Cout]
+    const float *noise;             // [B or 1, PH*PW] fp32 or null
+    long long noise_bstride;
+    const float *noise_weight;      // [1]
+    const float *bias;              // [Cout]
+    const float *next_style;        // [B, Cout]  sqrt(2) * style of the consumer conv, or null (no store)
+    const float *wrgb;              // [B, 3, Cout] sqrt(2)-scaled per-sample ToRGB weights, or null
+    float *rgb_part;                // [n_tiles_n, B, 3, PH, PW] fp32 partial ToRGB sums
+    __nv_bfloat16 *out;             // NHWC bf16
+};
+
+int launch_modconv_gemm(const GemmParams &p, const CUtensorMap *tmA /*[nsub]*/, const CUtensorMap &tmB,
+                        int sm_count, cudaStream_t st);
+
+}  // namespace sg2
