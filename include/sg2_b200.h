@@ -171,6 +171,12 @@ int sg2_synth_forward(sg2_synth *plan, void *workspace, const float *latent, int
                       const float *const *noise, const int64_t *noise_bstride, float *image,
                       sg2_stream_t stream);
 
+/* Optional per-kernel timing: the caller passes CUDA events it created (cudaEvent_t handles);
+ * every forward records events[0] before the first launch and events[k] after the k-th launch, in
+ * the order sg2_synth_describe lists them.  Pass NULL / 0 to switch it off.                     */
+int sg2_synth_set_profile_events(sg2_synth *plan, void **events, int n_events);
+int sg2_synth_profile_events_used(const sg2_synth *plan);
+
 #ifdef __cplusplus
 }
 #endif

@@ -62,6 +62,8 @@ SIGNATURES = {
     "sg2_synth_pack": (c_int, [c_void_p, c_void_p, c_void_p]),
     "sg2_synth_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, C.POINTER(c_void_p),
                                   C.POINTER(c_i64), c_void_p, c_void_p]),
+    "sg2_synth_set_profile_events": (c_int, [c_void_p, C.POINTER(c_void_p), c_int]),
+    "sg2_synth_profile_events_used": (c_int, [c_void_p]),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -1,14 +1,473 @@
-// synth.cu -- whole-network bf16 engine (placeholder while the tcgen05 path is brought up).
+// synth.cu -- whole-network bf16 synthesis engine: static launch plan + C ABI (sg2_synth_*).
+//
+// Replaces the synthesis loop of Generator.forward (model.py:520-533 of the reference, ~250
+// kernel launches) by a fixed sequence of ~3 launches per octave:
+//     styles (all layers) -> demod (all layers) -> const input
+//     conv1 GEMM [+ToRGB in its epilogue] -> rgb combine
+//     per octave: up-conv GEMM (4 polyphase sub-problems) -> FIR+noise+bias+lrelu+modulate
+//                 -> conv GEMM [+ToRGB] -> rgb combine (+ 2x up-sampled skip)
+// Activations are NHWC bf16 and are stored ALREADY MODULATED by the style of the conv that will
+// consume them, so every conv is a batch-shared-weight GEMM.  The host owns all memory: the plan
+// only holds offsets into the caller's workspace and (cached) TMA descriptors.
+#include <string>
+#include <vector>
+
 #include "common.cuh"
+#include "synth_gemm.cuh"
+#include "synth_kernels.cuh"
+#include "tc_ptx.cuh"
+
 using namespace sg2;
-struct sg2_synth { int size; };
-extern "C" int sg2_synth_create(sg2_synth **plan, int, int, int, const sg2_conv_params *, int, const float *, const float *) {
-    if (plan) *plan = nullptr;
-    set_error("synthesis engine not built yet");
-    return SG2_ERR_UNSUPPORTED;
+
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
 }
+
+size_t align_up(size_t v, size_t a = 1024) { return (v + a - 1) / a * a; }
+
+struct Layer {
+    sg2_conv_params p;
+    bool rgb;
+    int res_in, res_out;
+    // workspace offsets (bytes)
+    size_t wp = 0, wsq = 0, rgbw = 0, style = 0, demod = 0;
+    // GEMM tiling (styled convs)
+    int block_n = 0;
+    GemmParams gp;        // static part, pointers filled per forward
+    CUtensorMap tmA[kGemmMaxSub], tmB;
+};
+
+}  // namespace
+
+struct sg2_synth {
+    int size, style_dim, max_batch, log_size, n_latent, num_layers;
+    std::vector<Layer> layers;
+    const float *const_input;
+    float kf[16];                 // flipped blur taps (x4)
+    size_t off_act[2], off_T, off_rgb[2], off_part, ws_bytes;
+    // descriptor cache
+    void *cached_ws = nullptr;
+    int cached_B = -1;
+    // profiling hooks
+    cudaEvent_t *events = nullptr;
+    int n_events = 0, events_used = 0;
+    std::string description;
+    int sms = 148;
+};
+
+namespace {
+
+// choose the spatial tile of a PH x PW plane: TH*TW <= 128 with the fewest tiles, wide tiles preferred
+void choose_tile(int PH, int PW, int maxB, int &TH, int &TW, int &NB) {
+    if (PH * PW <= kBlockM) {
+        TH = PH; TW = PW;
+        NB = std::max(1, std::min(maxB, kBlockM / (PH * PW)));
+        return;
+    }
+    NB = 1;
+    long best = -1;
+    for (int tw = 4; tw <= std::min(PW, kBlockM); ++tw) {
+        const int th = std::min(PH, kBlockM / tw);
+        if (th < 1) continue;
+        const long tiles = (long)((PH + th - 1) / th) * ((PW + tw - 1) / tw);
+        if (best < 0 || tiles < best || (tiles == best && tw > TW)) { best = tiles; TH = th; TW = tw; }
+    }
+}
+
+int plan_gemm(sg2_synth *S, Layer &L) {
+    const int B = S->max_batch;
+    GemmParams &g = L.gp;
+    memset(&g, 0, sizeof(g));
+    const int cin = L.p.cin, cout = L.p.cout;
+    const bool up = L.p.upsample != 0;
+    const int r = L.res_in;
+    g.Cin = cin; g.Cout = cout; g.kchunks = cin / kBlockK;
+    g.mode = up ? 1 : 0;
+    g.nsub = up ? 4 : 1;
+    // sub-problems
+    for (int s = 0; s < g.nsub; ++s) {
+        GemmSub &q = g.sub[s];
+        if (!up) {
+            q.PH = q.PW = r; q.out_H = q.out_W = r; q.out_off = 0;
+            q.ntaps = 0;
+            for (int a = 0; a < 3; ++a)
+                for (int b = 0; b < 3; ++b) { q.dy[q.ntaps] = a - 1; q.dx[q.ntaps] = b - 1; q.wtap[q.ntaps] = a * 3 + b; ++q.ntaps; }
+        } else {
+            // transposed stride-2 conv: T[2i+a, 2j+b] += x[i,j] * w[a,b]; plane (py,px) holds T[2y+py, 2x+px]
+            const int py = s >> 1, px = s & 1;
+            q.PH = r + 1 - py; q.PW = r + 1 - px; q.out_H = q.out_W = r + 1;
+            q.ntaps = 0;
+            for (int a = py; a < 3; a += 2)
+                for (int b = px; b < 3; b += 2) { q.dy[q.ntaps] = -(a - py) / 2; q.dx[q.ntaps] = -(b - px) / 2; q.wtap[q.ntaps] = a * 3 + b; ++q.ntaps; }
+        }
+        choose_tile(q.PH, q.PW, B, q.TH, q.TW, q.NB);
+    }
+    // BLOCK_N: as wide as possible while the launch still has >= 2 waves of tiles, and the staged
+    // per-sample epilogue parameters fit (NB * BLOCK_N <= 512)
+    int best_n = 0;
+    for (int bn : {256, 128, 64, 32, 16}) {
+        if (cout % bn) continue;
+        bool fits = true;
+        long tiles = 0;
+        for (int s = 0; s < g.nsub; ++s) {
+            const GemmSub &q = g.sub[s];
+            if (q.NB * bn > 512) fits = false;
+            tiles += (long)((q.PH + q.TH - 1) / q.TH) * ((q.PW + q.TW - 1) / q.TW) * ((B + q.NB - 1) / q.NB) * (cout / bn);
+        }
+        if (!fits) continue;
+        best_n = bn;
+        if (tiles >= 2L * S->sms || bn <= 64) break;
+    }
+    SG2_REQUIRE(best_n > 0, SG2_ERR_UNSUPPORTED, "engine: no BLOCK_N for Cout=%d", cout);
+    g.block_n = L.block_n = best_n;
+    g.n_tiles_n = cout / best_n;
+    return SG2_OK;
+}
+
+void finalize_tiles(GemmParams &g, int B) {
+    int t = 0;
+    for (int s = 0; s < g.nsub; ++s) {
+        GemmSub &q = g.sub[s];
+        q.tiles_x = (q.PW + q.TW - 1) / q.TW;
+        q.tiles_y = (q.PH + q.TH - 1) / q.TH;
+        q.tiles_b = (B + q.NB - 1) / q.NB;
+        q.tile_begin = t;
+        t += q.tiles_x * q.tiles_y * q.tiles_b * g.n_tiles_n;
+    }
+    g.total_tiles = t;
+    g.B = B;
+}
+
+int encode_maps(sg2_synth *S, Layer &L, const __nv_bfloat16 *x, const __nv_bfloat16 *wp, int B) {
+    EncodeTiledFn enc = get_encode();
+    SG2_REQUIRE(enc, SG2_ERR_CUDA, "engine: cuTensorMapEncodeTiled entry point not available");
+    const int C = L.p.cin, r = L.res_in;
+    for (int s = 0; s < L.gp.nsub; ++s) {
+        const GemmSub &q = L.gp.sub[s];
+        cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)r, (cuuint64_t)r, (cuuint64_t)B};
+        cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)r * C * 2, (cuuint64_t)r * r * C * 2};
+        cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)q.TW, (cuuint32_t)q.TH, (cuuint32_t)q.NB};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        CUresult rc = enc(&L.tmA[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void *)x, dims, strides, box, es,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        SG2_REQUIRE(rc == CUDA_SUCCESS, SG2_ERR_CUDA, "engine: cuTensorMapEncodeTiled(A) failed with %d (C=%d r=%d box %d,%d,%d)",
+                    (int)rc, C, r, q.TW, q.TH, q.NB);
+    }
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)L.p.cout, 9};
+        cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)C * L.p.cout * 2};
+        cuuint32_t box[3] = {(cuuint32_t)kBlockK, (cuuint32_t)L.block_n, 1};
+        cuuint32_t es[3] = {1, 1, 1};
+        CUresult rc = enc(&L.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void *)wp, dims, strides, box, es,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        SG2_REQUIRE(rc == CUDA_SUCCESS, SG2_ERR_CUDA, "engine: cuTensorMapEncodeTiled(B) failed with %d", (int)rc);
+    }
+    return SG2_OK;
+}
+
+// after every launch: optional timing event; with SG2_SYNTH_DEBUG=1 also a sync that names the
+// first failing kernel (debug only -- never set while capturing a CUDA graph)
+inline int rec(sg2_synth *S, cudaStream_t st, const char *what = "") {
+    if (S->events && S->events_used < S->n_events) cudaEventRecord(S->events[S->events_used++], st);
+    static const bool debug = getenv("SG2_SYNTH_DEBUG") != nullptr;
+    if (debug) {
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { set_error("engine: kernel '%s' failed: %s", what, cudaGetErrorString(e)); return SG2_ERR_CUDA; }
+    }
+    return SG2_OK;
+}
+
+}  // namespace
+
+extern "C" int sg2_synth_create(sg2_synth **plan, int size, int style_dim, int max_batch,
+                                const sg2_conv_params *layers, int n_layers, const float *const_input,
+                                const float *blur_taps_host) {
+    SG2_REQUIRE(plan, SG2_ERR_BAD_ARG, "synth_create: null plan pointer");
+    *plan = nullptr;
+    int log_size = 0;
+    while ((1 << log_size) < size) ++log_size;
+    SG2_REQUIRE((1 << log_size) == size && size >= 8 && size <= 1024, SG2_ERR_UNSUPPORTED,
+                "synth_create: size must be a power of two in [8, 1024], got %d", size);
+    SG2_REQUIRE(style_dim >= 32 && style_dim <= 512 && style_dim % 32 == 0, SG2_ERR_UNSUPPORTED,
+                "synth_create: style_dim must be a multiple of 32 in [32, 512], got %d", style_dim);
+    SG2_REQUIRE(max_batch >= 1 && max_batch <= 4096, SG2_ERR_BAD_ARG, "synth_create: bad max_batch %d", max_batch);
+    SG2_REQUIRE(layers && n_layers == 2 + 3 * (log_size - 2) && n_layers <= kMaxJobs, SG2_ERR_BAD_ARG,
+                "synth_create: expected %d layer rows, got %d", 2 + 3 * (log_size - 2), n_layers);
+    SG2_REQUIRE(const_input && blur_taps_host, SG2_ERR_BAD_ARG, "synth_create: null pointer");
+    sg2_synth *S = new sg2_synth();
+    S->size = size; S->style_dim = style_dim; S->max_batch = max_batch; S->log_size = log_size;
+    S->n_latent = 2 * log_size - 2; S->num_layers = 2 * (log_size - 2) + 1;
+    S->const_input = const_input;
+    S->sms = 148;
+    for (int a = 0; a < 4; ++a)
+        for (int b = 0; b < 4; ++b) S->kf[a * 4 + b] = blur_taps_host[(3 - a) * 4 + (3 - b)];
+    const int B = max_batch;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes); return o; };
+    size_t max_act = 0, max_T = 0, max_part = 0;
+    int prev_cout = 0;
+    for (int i = 0; i < n_layers; ++i) {
+        Layer L;
+        L.p = layers[i];
+        L.rgb = (i % 3 == 1) || (i >= 2 && (i - 2) % 3 == 2);
+        const bool ok_ptrs = L.p.weight && L.p.mod_weight && L.p.mod_bias && L.p.act_bias && (L.rgb || L.p.noise_weight);
+        if (!ok_ptrs) { delete S; set_error("synth_create: layer %d has a null parameter pointer", i); return SG2_ERR_BAD_ARG; }
+        const int expect_k = L.rgb ? 1 : 3;
+        if (L.p.ksize != expect_k || (L.rgb && L.p.cout != 3) || L.p.cin % 8 || (!L.rgb && L.p.cout % 8) ||
+            L.p.latent_index < 0 || L.p.latent_index >= S->n_latent || (i > 0 && !L.rgb && L.p.cin != prev_cout)) {
+            delete S;
+            set_error("synth_create: layer %d (cin %d cout %d k %d up %d) does not fit the StyleGAN2 synthesis topology",
+                      i, L.p.cin, L.p.cout, L.p.ksize, L.p.upsample);
+            return SG2_ERR_UNSUPPORTED;
+        }
+        L.res_out = L.p.resolution;
+        L.res_in = L.p.upsample ? L.res_out / 2 : L.res_out;
+        L.style = take(sizeof(float) * B * L.p.cin);
+        if (L.rgb) {
+            L.rgbw = take(sizeof(float) * 3 * L.p.cin);
+        } else {
+            if (L.p.cin % kBlockK || L.p.cout % 16 || (L.p.upsample && L.p.cout % 64)) {
+                delete S;
+                set_error("engine: styled conv %d with Cin %d / Cout %d needs Cin %% 64 == 0 (and Cout %% 64 == 0 for "
+                          "up-sampling layers); the 32-channel 1024^2 tail is not on the tensor-core path yet",
+                          i, L.p.cin, L.p.cout);
+                return SG2_ERR_UNSUPPORTED;
+            }
+            L.wp = take(sizeof(__nv_bfloat16) * 9 * L.p.cout * L.p.cin);
+            L.wsq = take(sizeof(float) * L.p.cin * L.p.cout);
+            L.demod = take(sizeof(float) * B * L.p.cout);
+            int rc = plan_gemm(S, L);
+            if (rc) { delete S; return rc; }
+            finalize_tiles(L.gp, B);
+            prev_cout = L.p.cout;
+            max_act = std::max(max_act, sizeof(__nv_bfloat16) * (size_t)B * L.res_in * L.res_in * L.p.cin);
+            max_act = std::max(max_act, sizeof(__nv_bfloat16) * (size_t)B * L.res_out * L.res_out * L.p.cout);
+            if (L.p.upsample)
+                max_T = std::max(max_T, sizeof(__nv_bfloat16) * 4 * (size_t)B * (L.res_in + 1) * (L.res_in + 1) * L.p.cout);
+            else
+                max_part = std::max(max_part, sizeof(float) * (size_t)L.gp.n_tiles_n * B * 3 * L.res_out * L.res_out);
+        }
+        S->layers.push_back(L);
+    }
+    S->off_act[0] = take(max_act); S->off_act[1] = take(max_act);
+    S->off_T = take(max_T);
+    S->off_rgb[0] = take(sizeof(float) * (size_t)B * 3 * size * size);
+    S->off_rgb[1] = take(sizeof(float) * (size_t)B * 3 * size * size);
+    S->off_part = take(max_part);
+    S->ws_bytes = off;
+    // description (one line per launch of a forward pass, in launch order)
+    char line[512];
+    std::string d;
+    int k = 0;
+    auto add = [&](const char *kind, const char *what, double flops, double bytes, int tiles, int bn) {
+        snprintf(line, sizeof(line), "%d %s %s flops=%.6g bytes=%.6g tiles=%d block_n=%d\n", k++, kind, what, flops, bytes, tiles, bn);
+        d += line;
+    };
+    add("styles", "all", 0, 0, 0, 0);
+    add("demod", "all", 0, 0, 0, 0);
+    add("const_input", "input", 0, 0, 0, 0);
+    for (size_t i = 0; i < S->layers.size(); ++i) {
+        const Layer &L = S->layers[i];
+        char name[64];
+        snprintf(name, sizeof(name), "L%zu_%dx%d_%d->%d%s", i, L.res_out, L.res_out, L.p.cin, L.p.cout, L.p.upsample ? "_up" : "");
+        const double px_in = (double)L.res_in * L.res_in, px_out = (double)L.res_out * L.res_out;
+        if (L.rgb) {
+            add("rgb_combine", name, 2.0 * 3 * L.p.cin * px_out, 0, 0, 0);
+        } else {
+            // algorithmic FLOPs per image in the reference's formulation
+            const double fl = 2.0 * 9 * L.p.cin * L.p.cout * (L.p.upsample ? px_in : px_out);
+            add("gemm", name, fl, 2.0 * (px_in * L.p.cin + px_out * L.p.cout), L.gp.total_tiles, L.block_n);
+            if (L.p.upsample) add("upfir", name, 0, 2.0 * ((2 * L.res_in + 1.0) * (2 * L.res_in + 1.0) + px_out) * L.p.cout, 0, 0);
+        }
+    }
+    S->description = d;
+    *plan = S;
+    return SG2_OK;
+}
+
 extern "C" void sg2_synth_destroy(sg2_synth *p) { delete p; }
-extern "C" int64_t sg2_synth_workspace_bytes(const sg2_synth *) { return 0; }
-extern "C" int sg2_synth_describe(const sg2_synth *, char *, int) { return 0; }
-extern "C" int sg2_synth_pack(sg2_synth *, void *, sg2_stream_t) { set_error("synthesis engine not built yet"); return SG2_ERR_UNSUPPORTED; }
-extern "C" int sg2_synth_forward(sg2_synth *, void *, const float *, int64_t, const float *const *, const int64_t *, float *, sg2_stream_t) { set_error("synthesis engine not built yet"); return SG2_ERR_UNSUPPORTED; }
+extern "C" int64_t sg2_synth_workspace_bytes(const sg2_synth *p) { return p ? (int64_t)p->ws_bytes : 0; }
+extern "C" int sg2_synth_describe(const sg2_synth *p, char *buf, int buflen) {
+    if (!p || !buf || buflen <= 0) return 0;
+    const int n = std::min<int>((int)p->description.size(), buflen - 1);
+    memcpy(buf, p->description.data(), n);
+    buf[n] = 0;
+    return n;
+}
+
+extern "C" int sg2_synth_set_profile_events(sg2_synth *p, void **events, int n_events) {
+    SG2_REQUIRE(p, SG2_ERR_BAD_ARG, "synth_set_profile_events: null plan");
+    p->events = reinterpret_cast<cudaEvent_t *>(events);
+    p->n_events = events ? n_events : 0;
+    p->events_used = 0;
+    return SG2_OK;
+}
+extern "C" int sg2_synth_profile_events_used(const sg2_synth *p) { return p ? p->events_used : 0; }
+
+extern "C" int sg2_synth_pack(sg2_synth *S, void *workspace, sg2_stream_t stream) {
+    SG2_REQUIRE(S && workspace, SG2_ERR_BAD_ARG, "synth_pack: null pointer");
+    SG2_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, SG2_ERR_BAD_ARG, "synth_pack: workspace must be 1 KiB aligned");
+    int dev = 0, major = 0;
+    SG2_CUDA_OK(cudaGetDevice(&dev));
+    SG2_CUDA_OK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    SG2_REQUIRE(major == 10, SG2_ERR_NO_DEVICE, "engine: needs an sm_100 device (tcgen05/TMEM), found compute capability %d.x", major);
+    S->sms = sm_count();
+    cudaStream_t st = as_stream(stream);
+    uint8_t *ws = static_cast<uint8_t *>(workspace);
+    for (Layer &L : S->layers) {
+        if (L.rgb) {
+            int rc = launch_pack_rgb_weight((float *)(ws + L.rgbw), L.p.weight, 3 * L.p.cin, 1.0f / sqrtf((float)L.p.cin), st);
+            if (rc) return rc;
+        } else {
+            int rc = launch_pack_conv_weight((__nv_bfloat16 *)(ws + L.wp), (float *)(ws + L.wsq), L.p.weight, L.p.cin,
+                                             L.p.cout, 9, 1.0f / sqrtf((float)L.p.cin * 9), st);
+            if (rc) return rc;
+        }
+    }
+    S->cached_ws = nullptr;   // descriptors are rebuilt by the next forward
+    return SG2_OK;
+}
+
+extern "C" int sg2_synth_forward(sg2_synth *S, void *workspace, const float *latent, int64_t B64,
+                                 const float *const *noise, const int64_t *noise_bstride, float *image,
+                                 sg2_stream_t stream) {
+    SG2_REQUIRE(S && workspace && latent && image && noise && noise_bstride, SG2_ERR_BAD_ARG, "synth_forward: null pointer");
+    SG2_REQUIRE(B64 >= 0 && B64 <= S->max_batch, SG2_ERR_BAD_ARG, "synth_forward: batch %lld exceeds the plan's max_batch %d",
+                (long long)B64, S->max_batch);
+    if (B64 == 0) return SG2_OK;
+    const int B = (int)B64;
+    cudaStream_t st = as_stream(stream);
+    uint8_t *ws = static_cast<uint8_t *>(workspace);
+    __nv_bfloat16 *act[2] = {(__nv_bfloat16 *)(ws + S->off_act[0]), (__nv_bfloat16 *)(ws + S->off_act[1])};
+    __nv_bfloat16 *Tbuf = (__nv_bfloat16 *)(ws + S->off_T);
+    float *rgbbuf[2] = {(float *)(ws + S->off_rgb[0]), (float *)(ws + S->off_rgb[1])};
+    float *part = (float *)(ws + S->off_part);
+    S->events_used = 0;
+
+    // (re)build tile tables + TMA descriptors when the workspace or the batch changed
+    if (S->cached_ws != workspace || S->cached_B != B) {
+        int cur = 0;   // buffer holding the input of the next styled conv (const -> act[0])
+        for (Layer &L : S->layers) {
+            if (L.rgb) continue;
+            finalize_tiles(L.gp, B);
+            const __nv_bfloat16 *x = L.p.upsample ? act[1] : act[0];   // conv out -> act[1]; upfir out -> act[0]
+            (void)cur;
+            int rc = encode_maps(S, L, x, (const __nv_bfloat16 *)(ws + L.wp), B);
+            if (rc) return rc;
+        }
+        S->cached_ws = workspace;
+        S->cached_B = B;
+    }
+
+    // 1. styles of all layers, demod of all styled convs
+    StyleJobs sj; sj.n = 0;
+    DemodJobs dj; dj.n = 0;
+    int blocks = 0, max_cin = 0, max_cout = 0;
+    for (Layer &L : S->layers) {
+        StyleJob &j = sj.job[sj.n++];
+        j.mod_w = L.p.mod_weight; j.mod_b = L.p.mod_bias; j.out = (float *)(ws + L.style);
+        j.cin = L.p.cin; j.latent_index = L.p.latent_index; j.block_begin = blocks;
+        blocks += (L.p.cin + 7) / 8;
+        if (!L.rgb) {
+            DemodJob &d = dj.job[dj.n++];
+            d.style = (const float *)(ws + L.style); d.wsq = (const float *)(ws + L.wsq); d.demod = (float *)(ws + L.demod);
+            d.cin = L.p.cin; d.cout = L.p.cout;
+            max_cin = std::max(max_cin, L.p.cin); max_cout = std::max(max_cout, L.p.cout);
+        }
+    }
+    int rc = rec(S, st, "begin");
+    if (rc) return rc;
+    rc = launch_styles(sj, blocks, latent, B, S->n_latent, S->style_dim, st);
+    if (rc) return rc;
+    if ((rc = rec(S, st, "styles"))) return rc;
+    rc = launch_demod(dj, max_cin, max_cout, B, st);
+    if (rc) return rc;
+    if ((rc = rec(S, st, "demod"))) return rc;
+    // 2. constant input pre-modulated by conv1's style
+    Layer &L0 = S->layers[0];
+    rc = launch_const_input(act[0], S->const_input, (const float *)(ws + L0.style), B, L0.p.cin, 16, st);
+    if (rc) return rc;
+    if ((rc = rec(S, st, "const_input"))) return rc;
+
+    // 3. the layers
+    int noise_idx = 0;
+    int rgb_cur = -1;      // which rgb buffer holds the running skip image (-1: none yet)
+    const size_t nL = S->layers.size();
+    for (size_t i = 0; i < nL; ++i) {
+        Layer &L = S->layers[i];
+        if (L.rgb) continue;   // handled together with the conv that feeds it
+        // consumer of this conv's output: the next styled conv (if any); ToRGB if the next row is rgb
+        Layer *next_conv = nullptr, *rgb = nullptr;
+        for (size_t j = i + 1; j < nL; ++j) {
+            if (S->layers[j].rgb) { if (j == i + 1) rgb = &S->layers[j]; }
+            else { next_conv = &S->layers[j]; break; }
+        }
+        GemmParams g = L.gp;
+        g.demod = (const float *)(ws + L.demod);
+        const float *nz = noise[noise_idx];
+        const int64_t nzs = noise_bstride[noise_idx];
+        ++noise_idx;
+        if (!L.p.upsample) {
+            g.noise = nz; g.noise_bstride = nzs; g.noise_weight = L.p.noise_weight;
+            g.bias = L.p.act_bias;
+            g.next_style = next_conv ? (const float *)(ws + next_conv->style) : nullptr;
+            g.out = next_conv ? act[1] : nullptr;
+            if (rgb) {
+                g.rgb_w = (const float *)(ws + rgb->rgbw);
+                g.rgb_style = (const float *)(ws + rgb->style);
+                g.rgb_part = part;
+            }
+            rc = launch_modconv_gemm(g, L.tmA, L.tmB, S->sms, st);
+            if (rc) return rc;
+            if ((rc = rec(S, st, "gemm(conv)"))) return rc;
+            if (rgb) {
+                RgbParams rp;
+                const bool last = next_conv == nullptr;
+                const int dst = rgb_cur == 0 ? 1 : 0;
+                rp.out = last ? image : rgbbuf[dst];
+                rp.part = part; rp.n_parts = g.n_tiles_n; rp.bias = rgb->p.act_bias;
+                rp.prev = rgb_cur >= 0 ? rgbbuf[rgb_cur] : nullptr;
+                rp.B = B; rp.R = L.res_out;
+                memcpy(rp.kf, S->kf, sizeof(rp.kf));
+                rc = launch_rgb_combine(rp, S->sms, st);
+                if (rc) return rc;
+                if ((rc = rec(S, st, "rgb_combine"))) return rc;
+                rgb_cur = dst;
+            }
+        } else {
+            // transposed conv -> 4 polyphase planes in Tbuf (demodulated), then FIR + noise + bias + lrelu + modulate
+            const long long plane = (long long)B * (L.res_in + 1) * (L.res_in + 1) * L.p.cout;
+            for (int s = 0; s < g.nsub; ++s) g.sub[s].out_off = plane * s;
+            g.out = Tbuf;
+            rc = launch_modconv_gemm(g, L.tmA, L.tmB, S->sms, st);
+            if (rc) return rc;
+            if ((rc = rec(S, st, "gemm(up)"))) return rc;
+            SG2_REQUIRE(next_conv, SG2_ERR_BAD_ARG, "engine: up-sampling conv without a consumer");
+            UpfirParams up;
+            up.T = Tbuf; up.plane_stride = plane; up.out = act[0]; up.r = L.res_in; up.C = L.p.cout;
+            up.noise = nz; up.noise_bstride = nzs; up.noise_weight = L.p.noise_weight;
+            up.bias = L.p.act_bias; up.next_style = (const float *)(ws + next_conv->style);
+            memcpy(up.kf, S->kf, sizeof(up.kf));
+            rc = launch_upfir(up, B, st);
+            if (rc) return rc;
+            if ((rc = rec(S, st, "upfir"))) return rc;
+        }
+    }
+    return SG2_OK;
+}

@@ -166,11 +166,13 @@ modconv_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant_
                 const long long o = (long long)b * p.Cout + n0 + col;
                 sm.e_demod[i] = __ldg(p.demod + o);
                 if (p.mode == 0) {
-                    sm.e_next[i] = p.next_style ? __ldg(p.next_style + o) : 0.f;
-                    if (p.wrgb) {
+                    // lrelu gain sqrt(2) (fused_bias_act_kernel.cu:47) folded into both consumers
+                    sm.e_next[i] = p.next_style ? 1.41421356237f * __ldg(p.next_style + o) : 0.f;
+                    if (p.rgb_w) {
+                        const float rs = 1.41421356237f * __ldg(p.rgb_style + o);
 #pragma unroll
                         for (int c = 0; c < 3; ++c)
-                            sm.e_wrgb[c][i] = __ldg(p.wrgb + ((long long)b * 3 + c) * p.Cout + n0 + col);
+                            sm.e_wrgb[c][i] = rs * __ldg(p.rgb_w + (long long)c * p.Cout + n0 + col);
                     }
                 }
             }
@@ -215,7 +217,7 @@ modconv_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant_
                         v[3] = fmaf(__uint_as_float(r[j + 3]), d4.w, nz) + b4.w;
 #pragma unroll
                         for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], kSlope * v[e]);   // lrelu (gain folded downstream)
-                        if (p.wrgb) {
+                        if (p.rgb_w) {
                             const float4 w0 = *reinterpret_cast<const float4 *>(&sm.e_wrgb[0][pb + c0 + j]);
                             const float4 w1 = *reinterpret_cast<const float4 *>(&sm.e_wrgb[1][pb + c0 + j]);
                             const float4 w2 = *reinterpret_cast<const float4 *>(&sm.e_wrgb[2][pb + c0 + j]);
@@ -244,7 +246,7 @@ modconv_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant_
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm.tmem_empty[acc]);
-            if (valid && p.mode == 0 && p.wrgb) {
+            if (valid && p.mode == 0 && p.rgb_w) {
                 const long long plane = (long long)g.PH * g.PW;
                 float *rp = p.rgb_part + (((long long)t.nt * p.B + b) * 3) * plane + (long long)y * g.PW + x;
                 rp[0] = rgb0;

@@ -38,8 +38,9 @@ struct GemmParams {
     long long noise_bstride;
     const float *noise_weight;      // [1]
     const float *bias;              // [Cout]
-    const float *next_style;        // [B, Cout]  sqrt(2) * style of the consumer conv, or null (no store)
-    const float *wrgb;              // [B, 3, Cout] sqrt(2)-scaled per-sample ToRGB weights, or null
+    const float *next_style;        // [B, Cout] style of the consumer conv (sqrt(2) gain applied here), or null (no store)
+    const float *rgb_w;             // [3, Cout] ToRGB weights (1x1, scale folded), or null
+    const float *rgb_style;         // [B, Cout] ToRGB modulation
     float *rgb_part;                // [n_tiles_n, B, 3, PH, PW] fp32 partial ToRGB sums
     __nv_bfloat16 *out;             // NHWC bf16
 };

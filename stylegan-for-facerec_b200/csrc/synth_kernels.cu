@@ -1,0 +1,275 @@
+// synth_kernels.cu -- the small kernels around the tcgen05 GEMM in the bf16 synthesis engine:
+// weight packing (once per weight update), style / demodulation tables (once per forward, all
+// layers in one launch each), constant input, the polyphase FIR + noise/bias/lrelu/modulate pass of
+// the up-sampling layers and the RGB skip chain.  All HBM-bound or tiny; NHWC bf16 activations.
+#include "common.cuh"
+#include "synth_kernels.cuh"
+
+namespace sg2 {
+
+// ---- pack: W fp32 [Cout,Cin,k,k] -> Wp bf16 [k*k][Cout][Cin] (conv_scale folded), wsq fp32 [Cin][Cout]
+__global__ void __launch_bounds__(256)
+pack_conv_weight_kernel(__nv_bfloat16 *__restrict__ wp, float *__restrict__ wsq, const float *__restrict__ w,
+                        int Cin, int Cout, int kk, float scale) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;     // over (co, ci), ci fastest
+    if (i >= (int64_t)Cin * Cout) return;
+    const int co = (int)(i / Cin), ci = (int)(i - (int64_t)co * Cin);
+    float ss = 0.f;
+    for (int t = 0; t < kk; ++t) {
+        const float v = w[((int64_t)co * Cin + ci) * kk + t] * scale;
+        wp[((int64_t)t * Cout + co) * Cin + ci] = __float2bfloat16_rn(v);
+        ss += v * v;
+    }
+    if (wsq) wsq[(int64_t)ci * Cout + co] = ss;
+}
+
+// ToRGB weight fp32 [3,Cin] -> scaled fp32 [3][Cin]
+__global__ void pack_rgb_weight_kernel(float *__restrict__ out, const float *__restrict__ w, int n, float scale) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i < n) out[i] = w[i] * scale;
+}
+
+// ---- styles of every layer in one launch: s_l[b,ci] = latent[b, idx_l, :] . mod_w_l[ci,:] * scale + mod_b_l[ci]
+__global__ void __launch_bounds__(256)
+styles_kernel(StyleJobs jobs, const float *__restrict__ latent, int B, int n_latent, int style_dim) {
+    int j = 0;
+    while (j + 1 < jobs.n && (int)blockIdx.x >= jobs.job[j + 1].block_begin) ++j;
+    const StyleJob &job = jobs.job[j];
+    const int lane = threadIdx.x & 31;
+    const int ci = ((int)blockIdx.x - job.block_begin) * 8 + (threadIdx.x >> 5);
+    if (ci >= job.cin) return;
+    float wr[16];                                            // style_dim <= 512
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const int idx = lane + 32 * k;
+        wr[k] = idx < style_dim ? __ldg(job.mod_w + (int64_t)ci * style_dim + idx) : 0.f;
+    }
+    const float bv = __ldg(job.mod_b + ci);
+    const float scale = rsqrtf((float)style_dim);            // EqualLinear scale, lr_mul = 1 (model.py:144)
+    for (int b = blockIdx.y; b < B; b += gridDim.y) {
+        const float *lr = latent + ((int64_t)b * n_latent + job.latent_index) * style_dim;
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int idx = lane + 32 * k;
+            if (idx < style_dim) acc += __ldg(lr + idx) * wr[k];
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) job.out[(int64_t)b * job.cin + ci] = acc * scale + bv;
+    }
+}
+
+// ---- demod of every styled conv in one launch: d[b,co] = rsqrt(sum_ci s^2 * wsq[ci,co] + 1e-8)
+__global__ void __launch_bounds__(256)
+demod_kernel(DemodJobs jobs, int B) {
+    extern __shared__ float s_s2[];
+    const DemodJob &job = jobs.job[blockIdx.z];
+    const int b = blockIdx.y;
+    if ((int)blockIdx.x * 256 >= job.cout) return;
+    for (int i = threadIdx.x; i < job.cin; i += 256) {
+        const float s = job.style[(int64_t)b * job.cin + i];
+        s_s2[i] = s * s;
+    }
+    __syncthreads();
+    const int co = blockIdx.x * 256 + threadIdx.x;
+    if (co >= job.cout) return;
+    float acc = 0.f;
+    for (int ci = 0; ci < job.cin; ++ci) acc += s_s2[ci] * __ldg(job.wsq + (int64_t)ci * job.cout + co);
+    job.demod[(int64_t)b * job.cout + co] = rsqrtf(acc + 1e-8f);
+}
+
+// ---- constant input, pre-modulated by conv1's style: X0[b,y,x,c] = const[c,y,x] * s[b,c]   (NHWC bf16)
+__global__ void __launch_bounds__(256)
+const_input_kernel(__nv_bfloat16 *__restrict__ out, const float *__restrict__ cst, const float *__restrict__ style,
+                   int B, int C, int HW) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= (int64_t)B * HW * C) return;
+    const int c = (int)(i % C);
+    const int p = (int)((i / C) % HW);
+    const int b = (int)(i / ((int64_t)C * HW));
+    out[i] = __float2bfloat16_rn(cst[(int64_t)c * HW + p] * style[(int64_t)b * C + c]);
+}
+
+// ---- up-sampling layer tail: blur (4x4, pad (1,1)) over the 4 polyphase planes of the transposed
+// conv, + noise, + bias, lrelu, x sqrt(2) * next style, NHWC bf16 store.
+// Block: 32 cells (8 x 4, each a 2x2 output block) x 8 channel-vectors (64 channels).
+constexpr int FIR_CA = 8, FIR_CB = 4, FIR_CH = 64;
+constexpr int FIR_ROWS = 2 * FIR_CA + 3, FIR_COLS = 2 * FIR_CB + 3;
+
+__global__ void __launch_bounds__(256)
+upfir_kernel(UpfirParams p) {
+    __shared__ __align__(16) __nv_bfloat16 s_t[FIR_ROWS][FIR_COLS][FIR_CH];
+    const int tid = threadIdx.x;
+    const int tiles_b = (p.r + FIR_CB - 1) / FIR_CB;
+    const int a0 = (blockIdx.x / tiles_b) * FIR_CA, b0 = (blockIdx.x % tiles_b) * FIR_CB;
+    const int c0 = blockIdx.y * FIR_CH;
+    const int n = blockIdx.z;
+    const int P = p.r + 1;                                   // allocated plane extent
+    // stage the T window: rows t = 2*a0-1 .. 2*a0+2*CA+1, cols likewise
+    for (int i = tid; i < FIR_ROWS * FIR_COLS * 8; i += 256) {
+        const int v = i & 7, pix = i >> 3;
+        const int row = pix / FIR_COLS, col = pix - row * FIR_COLS;
+        const int t = 2 * a0 - 1 + row, u = 2 * b0 - 1 + col;
+        uint4 val = make_uint4(0, 0, 0, 0);
+        if (t >= 0 && u >= 0 && t <= 2 * p.r && u <= 2 * p.r) {
+            const int ph = ((t & 1) << 1) | (u & 1);
+            const int a = t >> 1, b = u >> 1;
+            const __nv_bfloat16 *src = p.T + (int64_t)ph * p.plane_stride +
+                                       (((int64_t)n * P + a) * P + b) * p.C + c0 + v * 8;
+            val = __ldg(reinterpret_cast<const uint4 *>(src));
+        }
+        *reinterpret_cast<uint4 *>(&s_t[row][col][v * 8]) = val;
+    }
+    __syncthreads();
+    const int v = tid & 7, cell = tid >> 3;
+    const int ca = cell / FIR_CB, cb = cell - ca * FIR_CB;
+    const int a = a0 + ca, b = b0 + cb;
+    if (a >= p.r || b >= p.r) return;
+    float acc[2][2][8];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[i][j][e] = 0.f;
+    // window rows 2*ca .. 2*ca+4 ; output (oy, ox) uses window rows oy..oy+3, cols ox..ox+3
+#pragma unroll
+    for (int wr = 0; wr < 5; ++wr) {
+#pragma unroll
+        for (int wc = 0; wc < 5; ++wc) {
+            const uint4 raw = *reinterpret_cast<const uint4 *>(&s_t[2 * ca + wr][2 * cb + wc][v * 8]);
+            const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&raw);
+            float x[8];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 f = __bfloat1622float2(h[e]);
+                x[2 * e] = f.x; x[2 * e + 1] = f.y;
+            }
+#pragma unroll
+            for (int oy = 0; oy < 2; ++oy) {
+                const int j = wr - oy;
+                if (j < 0 || j > 3) continue;
+#pragma unroll
+                for (int ox = 0; ox < 2; ++ox) {
+                    const int i = wc - ox;
+                    if (i < 0 || i > 3) continue;
+                    const float k = p.kf[j * 4 + i];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) acc[oy][ox][e] += k * x[e];
+                }
+            }
+        }
+    }
+    const int R = 2 * p.r;
+    const float nw = p.noise ? __ldg(p.noise_weight) : 0.f;
+    float bias[8], sn[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        bias[e] = __ldg(p.bias + c0 + v * 8 + e);
+        sn[e] = 1.41421356237f * __ldg(p.next_style + (int64_t)n * p.C + c0 + v * 8 + e);
+    }
+#pragma unroll
+    for (int oy = 0; oy < 2; ++oy)
+#pragma unroll
+        for (int ox = 0; ox < 2; ++ox) {
+            const int Y = 2 * a + oy, X = 2 * b + ox;
+            const float nz = p.noise ? nw * __ldg(p.noise + (int64_t)n * p.noise_bstride + (int64_t)Y * R + X) : 0.f;
+            uint32_t packed[4];
+#pragma unroll
+            for (int e = 0; e < 8; e += 2) {
+                float v0 = acc[oy][ox][e] + nz + bias[e], v1 = acc[oy][ox][e + 1] + nz + bias[e + 1];
+                v0 = fmaxf(v0, 0.2f * v0) * sn[e];
+                v1 = fmaxf(v1, 0.2f * v1) * sn[e + 1];
+                __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+                packed[e / 2] = *reinterpret_cast<uint32_t *>(&h);
+            }
+            __nv_bfloat16 *dst = p.out + (((int64_t)n * R + Y) * R + X) * p.C + c0 + v * 8;
+            *reinterpret_cast<uint4 *>(dst) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+        }
+}
+
+// ---- RGB skip chain: rgb[n,c,Y,X] = sum_nt part[nt,n,c,Y,X] + bias[c] + up2(prev)[n,c,Y,X]   (NCHW fp32)
+__host__ __device__ __forceinline__ int fdiv2(int a) { return a >= 0 ? a / 2 : -((-a + 1) / 2); }
+
+__global__ void __launch_bounds__(256)
+rgb_combine_kernel(RgbParams p) {
+    const int64_t total = (int64_t)p.B * 3 * p.R * p.R;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+        const int X = (int)(i % p.R), Y = (int)((i / p.R) % p.R);
+        const int64_t plane = i / ((int64_t)p.R * p.R);      // n*3 + c
+        const int c = (int)(plane % 3);
+        float v = __ldg(p.bias + c);
+        for (int nt = 0; nt < p.n_parts; ++nt) v += __ldg(p.part + (int64_t)nt * total + i);
+        if (p.prev) {
+            // up=2, pad (2,1), 4x4 taps: same index math as upfirdn2d_kernel.cu:112-129
+            const int S = p.R / 2;
+            const int mid_y = Y + 1 - 2, mid_x = X + 1 - 2;
+            const int iy0 = fdiv2(mid_y), ix0 = fdiv2(mid_x);
+            const int ky0 = (iy0 + 1) * 2 - mid_y - 1, kx0 = (ix0 + 1) * 2 - mid_x - 1;
+            const float *sp = p.prev + plane * S * S;
+            float acc = 0.f;
+#pragma unroll
+            for (int a = 0; a < 2; ++a) {
+                const int iy = iy0 + a;
+                if (iy < 0 || iy >= S) continue;
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    const int ix = ix0 + b;
+                    if (ix < 0 || ix >= S) continue;
+                    acc += __ldg(sp + iy * S + ix) * p.kf[(ky0 + 2 * a) * 4 + kx0 + 2 * b];
+                }
+            }
+            v += acc;
+        }
+        p.out[i] = v;
+    }
+}
+
+// ---- launch helpers --------------------------------------------------------------------------------
+int launch_pack_conv_weight(__nv_bfloat16 *wp, float *wsq, const float *w, int Cin, int Cout, int kk, float scale,
+                            cudaStream_t st) {
+    const int64_t n = (int64_t)Cin * Cout;
+    pack_conv_weight_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(wp, wsq, w, Cin, Cout, kk, scale);
+    SG2_LAUNCH_CHECK();
+    return SG2_OK;
+}
+int launch_pack_rgb_weight(float *out, const float *w, int n, float scale, cudaStream_t st) {
+    pack_rgb_weight_kernel<<<(n + 255) / 256, 256, 0, st>>>(out, w, n, scale);
+    SG2_LAUNCH_CHECK();
+    return SG2_OK;
+}
+int launch_styles(const StyleJobs &jobs, int total_blocks, const float *latent, int B, int n_latent, int style_dim,
+                  cudaStream_t st) {
+    dim3 grid(total_blocks, B < 64 ? B : 64);
+    styles_kernel<<<grid, 256, 0, st>>>(jobs, latent, B, n_latent, style_dim);
+    SG2_LAUNCH_CHECK();
+    return SG2_OK;
+}
+int launch_demod(const DemodJobs &jobs, int max_cin, int max_cout, int B, cudaStream_t st) {
+    dim3 grid((max_cout + 255) / 256, B, jobs.n);
+    demod_kernel<<<grid, 256, sizeof(float) * max_cin, st>>>(jobs, B);
+    SG2_LAUNCH_CHECK();
+    return SG2_OK;
+}
+int launch_const_input(__nv_bfloat16 *out, const float *cst, const float *style, int B, int C, int HW, cudaStream_t st) {
+    const int64_t n = (int64_t)B * C * HW;
+    const_input_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(out, cst, style, B, C, HW);
+    SG2_LAUNCH_CHECK();
+    return SG2_OK;
+}
+int launch_upfir(const UpfirParams &p, int B, cudaStream_t st) {
+    const int ta = (p.r + FIR_CA - 1) / FIR_CA, tb = (p.r + FIR_CB - 1) / FIR_CB;
+    dim3 grid(ta * tb, p.C / FIR_CH, B);
+    upfir_kernel<<<grid, 256, 0, st>>>(p);
+    SG2_LAUNCH_CHECK();
+    return SG2_OK;
+}
+int launch_rgb_combine(const RgbParams &p, int sms, cudaStream_t st) {
+    const int64_t total = (int64_t)p.B * 3 * p.R * p.R;
+    unsigned blocks = (unsigned)std::min<int64_t>(ceil_div64(total, 256), (int64_t)sms * 16);
+    rgb_combine_kernel<<<blocks, 256, 0, st>>>(p);
+    SG2_LAUNCH_CHECK();
+    return SG2_OK;
+}
+
+}  // namespace sg2

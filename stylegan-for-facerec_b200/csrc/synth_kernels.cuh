@@ -1,0 +1,54 @@
+// synth_kernels.cuh -- parameter blocks + launchers of the engine's auxiliary kernels.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sg2 {
+
+constexpr int kMaxJobs = 40;   // 17 styled convs + 9 ToRGB at 1024^2
+
+struct StyleJob {
+    const float *mod_w, *mod_b;   // [cin, style_dim], [cin]
+    float *out;                   // [B, cin]
+    int cin, latent_index, block_begin;
+};
+struct StyleJobs { int n; StyleJob job[kMaxJobs]; };
+
+struct DemodJob {
+    const float *style, *wsq;     // [B, cin], [cin, cout]
+    float *demod;                 // [B, cout]
+    int cin, cout;
+};
+struct DemodJobs { int n; DemodJob job[kMaxJobs]; };
+
+struct UpfirParams {
+    const __nv_bfloat16 *T;       // 4 planes [(py,px)][B][r+1][r+1][C], demodulated transposed-conv output
+    long long plane_stride;       // elements between planes
+    __nv_bfloat16 *out;           // [B][2r][2r][C]
+    int r, C;
+    const float *noise; long long noise_bstride; const float *noise_weight;
+    const float *bias;            // [C]
+    const float *next_style;      // [B][C]
+    float kf[16];                 // flipped 4x4 taps
+};
+
+struct RgbParams {
+    float *out;                   // [B,3,R,R]
+    const float *part;            // [n_parts][B,3,R,R]
+    int n_parts;
+    const float *bias;            // [3]
+    const float *prev;            // [B,3,R/2,R/2] or null
+    int B, R;
+    float kf[16];
+};
+
+int launch_pack_conv_weight(__nv_bfloat16 *wp, float *wsq, const float *w, int Cin, int Cout, int kk, float scale, cudaStream_t st);
+int launch_pack_rgb_weight(float *out, const float *w, int n, float scale, cudaStream_t st);
+int launch_styles(const StyleJobs &jobs, int total_blocks, const float *latent, int B, int n_latent, int style_dim, cudaStream_t st);
+int launch_demod(const DemodJobs &jobs, int max_cin, int max_cout, int B, cudaStream_t st);
+int launch_const_input(__nv_bfloat16 *out, const float *cst, const float *style, int B, int C, int HW, cudaStream_t st);
+int launch_upfir(const UpfirParams &p, int B, cudaStream_t st);
+int launch_rgb_combine(const RgbParams &p, int sms, cudaStream_t st);
+
+}  // namespace sg2

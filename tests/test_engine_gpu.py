@@ -1,0 +1,100 @@
+"""GPU parity of the bf16 tcgen05 synthesis engine (Generator.precision = 'bf16').
+
+Tolerance: the reference ops do not support bf16 (fused_bias_act_kernel.cu:79, upfirdn2d_kernel.cu:225),
+so the engine is compared with the reference's fp32 output (golden vectors / oracle).  The engine
+keeps bf16 activations and weights with fp32 accumulation; the survey measured 2.4e-2 of |ref|max
+for an all-bf16 evaluation of the reference math, so the stated tolerance is
+    max|d| <= 3e-2 * |ref|max   and   rel-L2 <= 2e-2."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+REL_MAX, REL_L2 = 3e-2, 2e-2
+
+
+def _check(img, ref, name):
+    img, ref = img.float().cpu(), ref.float()
+    assert img.shape == ref.shape, name
+    assert torch.isfinite(img).all(), name
+    rel_max = ((img - ref).abs().max() / ref.abs().max()).item()
+    rel_l2 = ((img - ref).norm() / ref.norm()).item()
+    assert rel_max <= REL_MAX and rel_l2 <= REL_L2, f"{name}: max|d|/|ref|max = {rel_max:.3e}, rel-L2 = {rel_l2:.3e}"
+    return rel_max, rel_l2
+
+
+def _gen(sg2, oracle, size, n_mlp, cm=2):
+    sd = oracle.init_state_dict(size, 512, n_mlp, cm, seed=0)
+    G = sg2.Generator(size, 512, n_mlp, channel_multiplier=cm)
+    G.load_state_dict(sd, strict=True)
+    G = G.to(DEV).eval()
+    G.precision = "bf16"
+    return G, sd
+
+
+@pytest.mark.parametrize("size", [8, 16, 32])
+def test_engine_small_vs_oracle(sg2, oracle, size):
+    G, sd = _gen(sg2, oracle, size, 2)
+    for B in (1, 3, 8):
+        z = oracle.named_randn(f"eng:z{size}:{B}", (B, 512), 4)
+        with torch.no_grad():
+            ref, _ = oracle.generator_forward(sd, size, [z], n_mlp=2, randomize_noise=False)
+            img, none = G([z.to(DEV)], randomize_noise=False)
+        assert none is None
+        _check(img, ref, f"size{size} B{B}")
+
+
+def test_engine_golden_cases(sg2, oracle, golden, cases):
+    for name, size, n_mlp, cm, batch, mode in cases.GEN_CASES:
+        if size > 256 or mode == "features":
+            continue
+        G, sd = _gen(sg2, oracle, size, n_mlp, cm)
+        styles, kw = cases.gen_inputs(name, size, n_mlp, batch, mode, sd)
+        styles = [s.to(DEV) for s in styles]
+        kw = {k: ([n.to(DEV) for n in v] if k == "noise" else (v.to(DEV) if torch.is_tensor(v) else v)) for k, v in kw.items()}
+        with torch.no_grad():
+            img, aux = G(styles, **kw)
+        _check(img, torch.from_numpy(golden["generator"][name + "/img"]), name)
+        if aux is not None:       # latents are passed through untouched
+            assert torch.allclose(aux.cpu(), torch.from_numpy(golden["generator"][name + "/aux"]), atol=1e-4)
+
+
+def test_engine_matches_exact_path_at_batch(sg2, oracle):
+    """B = 9 at 64x64 (odd batch: partially filled sample tiles), per-sample noise."""
+    G, sd = _gen(sg2, oracle, 64, 4)
+    z = oracle.named_randn("eng:z64", (9, 512), 4).to(DEV)
+    noise = [oracle.named_randn(f"eng:n{i}", (9, 1, 2 ** ((i + 5) // 2), 2 ** ((i + 5) // 2)), 4).to(DEV) for i in range(G.num_layers)]
+    with torch.no_grad():
+        img, _ = G([z], noise=noise)
+        G.precision = "exact"
+        ref, _ = G([z], noise=noise)
+    _check(img, ref.cpu(), "64 B9")
+
+
+def test_engine_randomize_noise_and_repack(sg2, oracle):
+    G, sd = _gen(sg2, oracle, 32, 2)
+    z = torch.randn(4, 512, device=DEV)
+    with torch.no_grad():
+        a, _ = G([z], randomize_noise=False)
+        b, _ = G([z], randomize_noise=False)
+        assert torch.equal(a, b)                        # deterministic
+        c, _ = G([z], randomize_noise=True)
+        assert not torch.equal(a, c)
+        # in-place weight update must be picked up (re-pack)
+        G.to_rgbs[-1].bias.data.add_(1.0)
+        d, _ = G([z], randomize_noise=False)
+        assert torch.allclose(d, a + 1.0, atol=1e-5)
+        assert "gemm" in G.engine().describe()
+
+
+def test_engine_launch_count(sg2, oracle):
+    """~3 launches per octave instead of the reference's ~250."""
+    G, sd = _gen(sg2, oracle, 256, 8)
+    z = torch.randn(2, 512, device=DEV)
+    with torch.no_grad():
+        G([z], randomize_noise=False)
+        n0 = sg2._lib.launch_count()
+        G([z], randomize_noise=False)
+        n = sg2._lib.launch_count() - n0
+    assert n <= 40, n
