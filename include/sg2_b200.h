@@ -87,10 +87,12 @@ int sg2_equal_linear_fwd(void *out, const void *x, const void *w, const void *bi
                          sg2_stream_t stream);
 
 /* Mapping network: w = MLP(pixel_norm(z)); weights[n_mlp][dim][dim], biases[n_mlp][dim] given as
- * arrays of n_mlp device pointers (host arrays).  dim must be a multiple of 32 and <= 1024.     */
+ * arrays of n_mlp device pointers (host arrays).  dim in {32, 64, 128, 256, 512}.  scratch: a
+ * [B, dim] buffer of the same dtype (layers ping-pong between it and w_out; may be NULL when
+ * n_mlp <= 1).  One launch per layer, PixelNorm fused into the first.                           */
 int sg2_mapping_fwd(void *w_out, const void *z, const void *const *weights,
                     const void *const *biases, int n_mlp, int64_t B, int dim, float lr_mul,
-                    int pixel_norm, int dtype, sg2_stream_t stream);
+                    int pixel_norm, void *scratch, int dtype, sg2_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Modulated convolution, exact fp32-accumulate path (NCHW, SIMT).  Three calls:

@@ -44,7 +44,7 @@ SIGNATURES = {
     "sg2_equal_linear_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_int,
                                      c_float, c_float, c_int, c_int, c_void_p]),
     "sg2_mapping_fwd": (c_int, [c_void_p, c_void_p, C.POINTER(c_void_p), C.POINTER(c_void_p), c_int,
-                                c_i64, c_int, c_float, c_int, c_int, c_void_p]),
+                                c_i64, c_int, c_float, c_int, c_void_p, c_int, c_void_p]),
     "sg2_modconv2d_prep": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int, c_void_p]),
     "sg2_modulation_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_void_p, c_void_p,
                                    c_i64, c_int, c_int, c_int, c_float, c_float, c_int, c_void_p]),

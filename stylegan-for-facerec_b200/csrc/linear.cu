@@ -1,7 +1,7 @@
 // linear.cu -- the small dense pieces around the convolutions (all warp-shuffle kernels):
 //   * EqualLinear (model.py:147-157)                      -> equal_linear_kernel
-//   * mapping network PixelNorm + n_mlp x EqualLinear     -> mapping_kernel, one launch
-//     (model.py:10-15, 378-387; 36 launches in the reference)
+//   * mapping network PixelNorm + n_mlp x EqualLinear     -> mapping_layer_kernel, one launch per
+//     layer with PixelNorm fused into the first (model.py:10-15, 378-387; 36 launches in the reference)
 //   * modulation affine + demodulation coefficients       -> modulation kernels
 //     (model.py:235-240), computed WITHOUT materialising per-sample weights:
 //         demod[b,co] = rsqrt( sum_ci style[b,ci]^2 * wsq[ci,co] + 1e-8 ),
@@ -188,74 +188,86 @@ extern "C" int sg2_equal_linear_fwd(void *out, const void *x, const void *w, con
 }
 
 namespace sg2 {
-// Pointer tables travel by value in the kernel's parameter bank: no device allocation, no copy.
-struct PtrTables { const void *w[32]; const void *b[32]; };
+// One mapping layer: out[b,o] = lrelu((xn[b,:] . w[o,:]) * w_scale + bias[o]*lr_mul) * sqrt(2), where
+// xn = pixel_norm(x) for the first layer (model.py:14-15 fused into the load) and x otherwise.
+// Block = 4 output features (their weight rows staged in shared memory) x up to 64 samples
+// (8 warps x 8 samples); a lane keeps its slice of the sample row in registers, so every global
+// load is a coalesced 128-byte line and the reduction is a warp shuffle.  The whole chip works on
+// every layer (dim/4 x ceil(B/64) blocks) instead of the previous one-block-per-two-samples chain.
+constexpr int MAP_ROWS = 4, MAP_SPB = 64;
 
-// Whole mapping network for TS samples per block; activations ping-pong in shared memory, every
-// warp owns output features o = warp, warp+8, ... and streams that weight row once per layer.
-template <typename T, int TS>
+template <typename T, int NJ>   // dim == 32 * NJ
 __global__ void __launch_bounds__(256)
-mapping_kernel(T *__restrict__ w_out, const T *__restrict__ z, PtrTables tabs, int n_mlp, int64_t B,
-               int dim, float w_scale, float lr_mul, int pixel_norm) {
-    extern __shared__ float s_act[];   // [2][TS][dim]
+mapping_layer_kernel(T *__restrict__ out, const T *__restrict__ x, const T *__restrict__ w,
+                     const T *__restrict__ bias, int64_t B, float w_scale, float lr_mul, int pixel_norm) {
+    constexpr int dim = 32 * NJ;
+    __shared__ float s_w[MAP_ROWS][dim];
+    __shared__ float s_b[MAP_ROWS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t b0 = (int64_t)blockIdx.x * TS;
-    float *cur = s_act, *nxt = s_act + TS * dim;
-    for (int s = warp; s < TS; s += 8) {   // load + pixel norm (model.py:14-15): one warp per sample
-        const int64_t b = b0 + s;
-        float ss = 0.f;
-        for (int j = lane; j < dim; j += 32) {
-            const float v = b < B ? Cvt<T>::to_f(z[b * dim + j]) : 0.f;
-            cur[s * dim + j] = v;
-            ss += v * v;
-        }
-        ss = warp_sum(ss);
-        if (pixel_norm) {
-            const float r = rsqrtf(ss / (float)dim + 1e-8f);
-            for (int j = lane; j < dim; j += 32) cur[s * dim + j] *= r;
-        }
+    const int o0 = blockIdx.x * MAP_ROWS;
+    for (int i = threadIdx.x; i < MAP_ROWS * dim; i += 256) {
+        const int r = i / dim, j = i - r * dim;
+        s_w[r][j] = Cvt<T>::to_f(w[(int64_t)(o0 + r) * dim + j]);
     }
+    if (threadIdx.x < MAP_ROWS) s_b[threadIdx.x] = Cvt<T>::to_f(bias[o0 + threadIdx.x]) * lr_mul;
     __syncthreads();
-    const int nj = dim / 32;   // dim is a multiple of 32, <= 1024
-    for (int l = 0; l < n_mlp; ++l) {
-        const T *W = (const T *)tabs.w[l];
-        const T *Bv = (const T *)tabs.b[l];
-        for (int o = warp; o < dim; o += 8) {
-            float acc[TS];
-#pragma unroll
-            for (int s = 0; s < TS; ++s) acc[s] = 0.f;
-            for (int j = 0; j < nj; ++j) {
-                const float wv = Cvt<T>::to_f(W[(int64_t)o * dim + lane + 32 * j]);
-#pragma unroll
-                for (int s = 0; s < TS; ++s) acc[s] += cur[s * dim + lane + 32 * j] * wv;
-            }
-            const float bv = Cvt<T>::to_f(Bv[o]) * lr_mul;
-#pragma unroll
-            for (int s = 0; s < TS; ++s) {
-                float v = warp_sum(acc[s]) * w_scale + bv;
-                v = (v > 0.f ? v : v * kLreluSlope) * kLreluGain;
-                if (lane == 0) nxt[s * dim + o] = v;
-            }
-        }
-        __syncthreads();
-        float *t = cur; cur = nxt; nxt = t;
-    }
-    for (int i = threadIdx.x; i < TS * dim; i += 256) {
-        const int s = i / dim;
+    const int64_t b0 = (int64_t)blockIdx.y * MAP_SPB;
+    for (int s = warp; s < MAP_SPB; s += 8) {
         const int64_t b = b0 + s;
-        if (b < B) w_out[b * dim + (i - s * dim)] = Cvt<T>::from_f(cur[i]);
+        if (b >= B) break;
+        float xv[NJ];
+        float ss = 0.f;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            xv[j] = Cvt<T>::to_f(x[b * dim + lane + 32 * j]);
+            ss += xv[j] * xv[j];
+        }
+        if (pixel_norm) {
+            ss = warp_sum(ss);
+            const float rn = rsqrtf(ss / (float)dim + 1e-8f);
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) xv[j] *= rn;
+        }
+        float acc[MAP_ROWS];
+#pragma unroll
+        for (int r = 0; r < MAP_ROWS; ++r) {
+            acc[r] = 0.f;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) acc[r] += xv[j] * s_w[r][lane + 32 * j];
+        }
+#pragma unroll
+        for (int r = 0; r < MAP_ROWS; ++r) acc[r] = warp_sum(acc[r]);
+        if (lane < MAP_ROWS) {
+            float v = (lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3]) * w_scale + s_b[lane];
+            v = (v > 0.f ? v : v * kLreluSlope) * kLreluGain;
+            out[b * dim + o0 + lane] = Cvt<T>::from_f(v);
+        }
     }
 }
 
-template <typename T, int TS>
-static int launch_mapping(void *w_out, const void *z, const PtrTables &tabs, int n_mlp, int64_t B,
-                          int dim, float w_scale, float lr_mul, int pixel_norm, cudaStream_t st) {
-    const size_t smem = sizeof(float) * 2 * TS * dim;
-    if (smem > 48 * 1024)
-        SG2_CUDA_OK(cudaFuncSetAttribute(mapping_kernel<T, TS>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    mapping_kernel<T, TS><<<(unsigned)ceil_div64(B, TS), 256, smem, st>>>(
-        (T *)w_out, (const T *)z, tabs, n_mlp, B, dim, w_scale, lr_mul, pixel_norm);
+template <typename T>
+__global__ void __launch_bounds__(256)
+pixel_norm_kernel(T *__restrict__ out, const T *__restrict__ x, int64_t B, int dim, int pixel_norm) {
+    const int lane = threadIdx.x & 31;
+    const int64_t b = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (b >= B) return;
+    float ss = 0.f;
+    for (int j = lane; j < dim; j += 32) { const float v = Cvt<T>::to_f(x[b * dim + j]); ss += v * v; }
+    ss = warp_sum(ss);
+    const float rn = pixel_norm ? rsqrtf(ss / (float)dim + 1e-8f) : 1.f;
+    for (int j = lane; j < dim; j += 32) out[b * dim + j] = Cvt<T>::from_f(Cvt<T>::to_f(x[b * dim + j]) * rn);
+}
+
+template <typename T>
+static int launch_mapping_layer(T *out, const T *x, const T *w, const T *bias, int64_t B, int dim,
+                                float w_scale, float lr_mul, int pixel_norm, cudaStream_t st) {
+    dim3 grid(dim / MAP_ROWS, (unsigned)ceil_div64(B, MAP_SPB));
+#define SG2_ML(NJ) case NJ: mapping_layer_kernel<T, NJ><<<grid, 256, 0, st>>>(out, x, w, bias, B, w_scale, lr_mul, pixel_norm); break
+    switch (dim / 32) {
+        SG2_ML(1); SG2_ML(2); SG2_ML(4); SG2_ML(8); SG2_ML(16);
+        default: set_error("mapping: style_dim %d not in {32,64,128,256,512}", dim); return SG2_ERR_UNSUPPORTED;
+    }
+#undef SG2_ML
     SG2_LAUNCH_CHECK();
     return SG2_OK;
 }
@@ -263,28 +275,34 @@ static int launch_mapping(void *w_out, const void *z, const PtrTables &tabs, int
 
 extern "C" int sg2_mapping_fwd(void *w_out, const void *z, const void *const *weights,
                                const void *const *biases, int n_mlp, int64_t B, int dim,
-                               float lr_mul, int pixel_norm, int dtype, sg2_stream_t stream) {
+                               float lr_mul, int pixel_norm, void *scratch, int dtype,
+                               sg2_stream_t stream) {
     SG2_REQUIRE(B >= 0 && n_mlp >= 0 && n_mlp <= 32, SG2_ERR_BAD_ARG, "mapping: bad n_mlp/B");
-    SG2_REQUIRE(dim >= 32 && dim <= 1024 && dim % 32 == 0, SG2_ERR_UNSUPPORTED,
-                "mapping: style_dim must be a multiple of 32 in [32,1024], got %d", dim);
-    SG2_REQUIRE(B <= 0x7fffffffll, SG2_ERR_UNSUPPORTED, "mapping: batch too large");
+    SG2_REQUIRE(dim == 32 || dim == 64 || dim == 128 || dim == 256 || dim == 512, SG2_ERR_UNSUPPORTED,
+                "mapping: style_dim must be one of 32, 64, 128, 256, 512, got %d", dim);
+    SG2_REQUIRE(B <= 65535ll * MAP_SPB, SG2_ERR_UNSUPPORTED, "mapping: batch too large");
     if (B == 0) return SG2_OK;
-    SG2_REQUIRE(w_out && z && (n_mlp == 0 || (weights && biases)), SG2_ERR_BAD_ARG,
-                "mapping: null pointer");
-    PtrTables tabs;
-    for (int i = 0; i < 32; ++i) {
-        tabs.w[i] = i < n_mlp ? weights[i] : nullptr;
-        tabs.b[i] = i < n_mlp ? biases[i] : nullptr;
-        SG2_REQUIRE(i >= n_mlp || (tabs.w[i] && tabs.b[i]), SG2_ERR_BAD_ARG, "mapping: null layer pointer");
-    }
+    SG2_REQUIRE(w_out && z && (n_mlp == 0 || (weights && biases)), SG2_ERR_BAD_ARG, "mapping: null pointer");
+    SG2_REQUIRE(n_mlp <= 1 || scratch, SG2_ERR_BAD_ARG, "mapping: n_mlp > 1 needs a [B, dim] scratch buffer");
+    for (int i = 0; i < n_mlp; ++i)
+        SG2_REQUIRE(weights[i] && biases[i], SG2_ERR_BAD_ARG, "mapping: null layer pointer");
     const float w_scale = lr_mul / sqrtf((float)dim);   // model.py:144
     cudaStream_t st = as_stream(stream);
-    const int sms = sm_count();
     SG2_DISPATCH_DTYPE(dtype, {
-        // few samples: 2 per block for latency; many: 8 per block to amortise the weight stream
-        if (B <= 4 * (int64_t)sms)
-            return launch_mapping<T, 2>(w_out, z, tabs, n_mlp, B, dim, w_scale, lr_mul, pixel_norm, st);
-        return launch_mapping<T, 8>(w_out, z, tabs, n_mlp, B, dim, w_scale, lr_mul, pixel_norm, st);
+        if (n_mlp == 0) {
+            pixel_norm_kernel<T><<<(unsigned)ceil_div64(B, 8), 256, 0, st>>>((T *)w_out, (const T *)z, B, dim, pixel_norm);
+            SG2_LAUNCH_CHECK();
+            return SG2_OK;
+        }
+        const T *src = (const T *)z;
+        for (int l = 0; l < n_mlp; ++l) {
+            // ping-pong so that the last layer lands in w_out
+            T *dst = ((n_mlp - 1 - l) & 1) ? (T *)scratch : (T *)w_out;
+            int rc = launch_mapping_layer<T>(dst, src, (const T *)weights[l], (const T *)biases[l], B, dim,
+                                             w_scale, lr_mul, l == 0 ? pixel_norm : 0, st);
+            if (rc) return rc;
+            src = dst;
+        }
     });
     return SG2_OK;
 }

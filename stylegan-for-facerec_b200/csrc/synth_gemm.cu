@@ -33,15 +33,19 @@ constexpr int kABytes = kBlockM * kBlockK * 2;          // 16 KiB
 constexpr int kBBytesMax = kMaxBlockN * kBlockK * 2;    // 32 KiB
 constexpr int kEpiCap = 512;                            // NB * BLOCK_N entries of per-sample epilogue params
 constexpr float kSlope = 0.2f;
+// The operand ring is one byte array cut into stages of (16 KiB A + BLOCK_N*128 B of B): narrow
+// BLOCK_N means short MMAs per stage, so more stages are needed to cover the TMA latency
+// (4 stages at N=256, 6 at N=128, 8 at N<=64).
+constexpr int kRingBytes = kStages * (kABytes + kBBytesMax);   // 192 KiB
+constexpr int kMaxStages = 8;
 
 struct __align__(1024) GemmSmem {
-    uint8_t a[kStages][kABytes];
-    uint8_t b[kStages][kBBytesMax];
+    uint8_t ring[kRingBytes];
     float e_demod[kEpiCap];
     float e_next[kEpiCap];
     float e_wrgb[3][kEpiCap];
     float e_bias[kMaxBlockN];
-    uint64_t full[kStages], empty[kStages];
+    uint64_t full[kMaxStages], empty[kMaxStages];
     uint64_t tmem_full[2], tmem_empty[2];
     uint32_t tmem_base;
 };
@@ -87,7 +91,7 @@ modconv_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant_
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA0);
         tma_prefetch_desc(&tmB);
-        for (int i = 0; i < kStages; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.empty[i], 1); }
+        for (int i = 0; i < kMaxStages; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&sm.tmem_full[i], 1); mbar_init(&sm.tmem_empty[i], 4); }
         fence_barrier_init();
     }
@@ -97,6 +101,8 @@ modconv_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant_
     tc_fence_after();
     const uint32_t tmem_base = sm.tmem_base;
     const uint32_t b_bytes = (uint32_t)p.block_n * kBlockK * 2;
+    const uint32_t stage_bytes = kABytes + b_bytes;          // multiple of 1 KiB: swizzle atoms stay aligned
+    const uint32_t nstages = min((uint32_t)kMaxStages, (uint32_t)kRingBytes / stage_bytes);
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -111,11 +117,12 @@ modconv_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant_
                     for (int tap = 0; tap < g.ntaps; ++tap) {
                         mbar_wait(&sm.empty[stage], phase ^ 1);
                         mbar_arrive_expect_tx(&sm.full[stage], a_bytes + b_bytes);
-                        tma_load_4d(sm.a[stage], tmA, &sm.full[stage], kc * kBlockK, t.x0 + g.dx[tap],
+                        uint8_t *slot = sm.ring + stage * stage_bytes;
+                        tma_load_4d(slot, tmA, &sm.full[stage], kc * kBlockK, t.x0 + g.dx[tap],
                                     t.y0 + g.dy[tap], t.b0);
-                        tma_load_3d(sm.b[stage], &tmB, &sm.full[stage], kc * kBlockK, t.nt * p.block_n,
+                        tma_load_3d(slot + kABytes, &tmB, &sm.full[stage], kc * kBlockK, t.nt * p.block_n,
                                     g.wtap[tap]);
-                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                        if (++stage == nstages) { stage = 0; phase ^= 1; }
                     }
                 }
             }
@@ -134,13 +141,14 @@ modconv_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant_
                 for (int s = 0; s < nstage; ++s) {
                     mbar_wait(&sm.full[stage], phase);
                     tc_fence_after();
-                    const uint64_t adesc = make_smem_desc(smem_u32(sm.a[stage]), 128);
-                    const uint64_t bdesc = make_smem_desc(smem_u32(sm.b[stage]), 128);
+                    const uint32_t slot = smem_u32(sm.ring) + stage * stage_bytes;
+                    const uint64_t adesc = make_smem_desc(slot, 128);
+                    const uint64_t bdesc = make_smem_desc(slot + kABytes, 128);
 #pragma unroll
                     for (int k = 0; k < kBlockK / 16; ++k)   // advance 32 bytes (>>4 = 2) inside the swizzle row
                         umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (s | k) != 0);
                     umma_commit(&sm.empty[stage]);           // frees the smem slot when these MMAs retire
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    if (++stage == nstages) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(&sm.tmem_full[acc]);             // accumulator complete -> epilogue
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }

@@ -60,22 +60,34 @@ styles_kernel(StyleJobs jobs, const float *__restrict__ latent, int B, int n_lat
 }
 
 // ---- demod of every styled conv in one launch: d[b,co] = rsqrt(sum_ci s^2 * wsq[ci,co] + 1e-8)
+// block = 256 output channels x 8 samples: each wsq element is loaded once for 8 samples
+constexpr int DEMOD_SB = 8;
 __global__ void __launch_bounds__(256)
 demod_kernel(DemodJobs jobs, int B) {
-    extern __shared__ float s_s2[];
+    extern __shared__ float s_s2[];                          // [DEMOD_SB][cin]
     const DemodJob &job = jobs.job[blockIdx.z];
-    const int b = blockIdx.y;
+    const int b0 = blockIdx.y * DEMOD_SB;
     if ((int)blockIdx.x * 256 >= job.cout) return;
-    for (int i = threadIdx.x; i < job.cin; i += 256) {
-        const float s = job.style[(int64_t)b * job.cin + i];
+    const int nb = min(DEMOD_SB, B - b0);
+    for (int i = threadIdx.x; i < DEMOD_SB * job.cin; i += 256) {
+        const int sb = i / job.cin, ci = i - sb * job.cin;
+        const float s = sb < nb ? job.style[(int64_t)(b0 + sb) * job.cin + ci] : 0.f;
         s_s2[i] = s * s;
     }
     __syncthreads();
     const int co = blockIdx.x * 256 + threadIdx.x;
     if (co >= job.cout) return;
-    float acc = 0.f;
-    for (int ci = 0; ci < job.cin; ++ci) acc += s_s2[ci] * __ldg(job.wsq + (int64_t)ci * job.cout + co);
-    job.demod[(int64_t)b * job.cout + co] = rsqrtf(acc + 1e-8f);
+    float acc[DEMOD_SB];
+#pragma unroll
+    for (int sb = 0; sb < DEMOD_SB; ++sb) acc[sb] = 0.f;
+    for (int ci = 0; ci < job.cin; ++ci) {
+        const float w = __ldg(job.wsq + (int64_t)ci * job.cout + co);
+#pragma unroll
+        for (int sb = 0; sb < DEMOD_SB; ++sb) acc[sb] += s_s2[sb * job.cin + ci] * w;
+    }
+#pragma unroll
+    for (int sb = 0; sb < DEMOD_SB; ++sb)
+        if (sb < nb) job.demod[(int64_t)(b0 + sb) * job.cout + co] = rsqrtf(acc[sb] + 1e-8f);
 }
 
 // ---- constant input, pre-modulated by conv1's style: X0[b,y,x,c] = const[c,y,x] * s[b,c]   (NHWC bf16)
@@ -240,14 +252,14 @@ int launch_pack_rgb_weight(float *out, const float *w, int n, float scale, cudaS
 }
 int launch_styles(const StyleJobs &jobs, int total_blocks, const float *latent, int B, int n_latent, int style_dim,
                   cudaStream_t st) {
-    dim3 grid(total_blocks, B < 64 ? B : 64);
+    dim3 grid(total_blocks, B < 8 ? B : 8);   // a warp keeps its weight row in registers for B/8 samples
     styles_kernel<<<grid, 256, 0, st>>>(jobs, latent, B, n_latent, style_dim);
     SG2_LAUNCH_CHECK();
     return SG2_OK;
 }
 int launch_demod(const DemodJobs &jobs, int max_cin, int max_cout, int B, cudaStream_t st) {
-    dim3 grid((max_cout + 255) / 256, B, jobs.n);
-    demod_kernel<<<grid, 256, sizeof(float) * max_cin, st>>>(jobs, B);
+    dim3 grid((max_cout + 255) / 256, (B + DEMOD_SB - 1) / DEMOD_SB, jobs.n);
+    demod_kernel<<<grid, 256, sizeof(float) * DEMOD_SB * max_cin, st>>>(jobs, B);
     SG2_LAUNCH_CHECK();
     return SG2_OK;
 }

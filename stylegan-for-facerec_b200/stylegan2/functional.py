@@ -43,10 +43,11 @@ def mapping(z, weights, biases, lr_mul, pixel_norm=True):
     wp = (C.c_void_p * max(n, 1))(*[w.data_ptr() for w in ws])
     bp = (C.c_void_p * max(n, 1))(*[b.data_ptr() for b in bs])
     out = torch.empty_like(z2)
+    scratch = torch.empty_like(z2) if n > 1 else None
     with _lib.device_of(z2):
         _lib.check(lib.sg2_mapping_fwd(out.data_ptr(), z2.data_ptr(), wp, bp, n, z2.shape[0], z2.shape[1],
-                                       float(lr_mul), 1 if pixel_norm else 0, _lib.dtype_code(z2),
-                                       _lib.stream_of(z2)), "mapping_fwd")
+                                       float(lr_mul), 1 if pixel_norm else 0, _lib.ptr(scratch),
+                                       _lib.dtype_code(z2), _lib.stream_of(z2)), "mapping_fwd")
     return out
 
 

@@ -152,7 +152,7 @@ class MappingNetwork(nn.Sequential):
                    and all(isinstance(m, EqualLinear) and m.activation and m.bias is not None
                            and m.weight.shape == (input.shape[1], input.shape[1])
                            and m.lr_mul == layers[1].lr_mul for m in layers[1:])
-                   and input.shape[1] % 32 == 0 and 32 <= input.shape[1] <= 1024 and len(layers) <= 33)
+                   and input.shape[1] in (32, 64, 128, 256, 512) and len(layers) <= 33)
         if fusable and not K.needs_grad(input, *self.parameters()):
             lr_mul = layers[1].lr_mul if len(layers) > 1 else 1.0
             return K.mapping(input, [m.weight for m in layers[1:]], [m.bias for m in layers[1:]], lr_mul, True)
