@@ -49,6 +49,7 @@ struct Layer {
     int block_n = 0;
     GemmParams gp;        // static part, pointers filled per forward
     CUtensorMap tmA[kGemmMaxSub], tmB;
+    CUtensorMap tmT[4];   // up-sampling layers: the 4 polyphase planes as the FIR kernel reads them
 };
 
 }  // namespace
@@ -58,7 +59,10 @@ struct sg2_synth {
     std::vector<Layer> layers;
     const float *const_input;
     float kf[16];                 // flipped blur taps (x4)
-    size_t off_act[2], off_T, off_rgb[2], off_part, ws_bytes;
+    size_t off_act[2], off_T, off_rgb[2], off_part, off_toeplitz, ws_bytes;
+    std::vector<uint16_t> toeplitz;   // host copy of the FIR Toeplitz matrix (bf16 bits), uploaded by pack
+    CUtensorMap tmK;
+    bool fir_simt = false;
     // descriptor cache
     void *cached_ws = nullptr;
     int cached_B = -1;
@@ -181,6 +185,27 @@ int encode_maps(sg2_synth *S, Layer &L, const __nv_bfloat16 *x, const __nv_bfloa
     return SG2_OK;
 }
 
+// TMA views of the 4 polyphase planes [(py,px)][B][r+1][r+1][C]: valid extent (r+1-py) x (r+1-px), so the
+// never-written last row/column of the odd planes reads as zero; box = 10 x 6 pixels x 64 channels
+int encode_fir_maps(Layer &L, const __nv_bfloat16 *T, int B) {
+    EncodeTiledFn enc = get_encode();
+    SG2_REQUIRE(enc, SG2_ERR_CUDA, "engine: cuTensorMapEncodeTiled entry point not available");
+    const int C = L.p.cout, r = L.res_in, P = r + 1;
+    const size_t plane = (size_t)B * P * P * C;
+    for (int s = 0; s < 4; ++s) {
+        const int py = s >> 1, px = s & 1;
+        cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)(P - px), (cuuint64_t)(P - py), (cuuint64_t)B};
+        cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)P * C * 2, (cuuint64_t)P * P * C * 2};
+        cuuint32_t box[4] = {64, 6, 10, 1};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        CUresult rc = enc(&L.tmT[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void *)(T + plane * s), dims, strides, box, es,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        SG2_REQUIRE(rc == CUDA_SUCCESS, SG2_ERR_CUDA, "engine: cuTensorMapEncodeTiled(T plane) failed with %d", (int)rc);
+    }
+    return SG2_OK;
+}
+
 // after every launch: optional timing event; with SG2_SYNTH_DEBUG=1 also a sync that names the
 // first failing kernel (debug only -- never set while capturing a CUDA graph)
 inline int rec(sg2_synth *S, cudaStream_t st, const char *what = "") {
@@ -261,7 +286,7 @@ extern "C" int sg2_synth_create(sg2_synth **plan, int size, int style_dim, int m
             if (L.p.upsample)
                 max_T = std::max(max_T, sizeof(__nv_bfloat16) * 4 * (size_t)B * (L.res_in + 1) * (L.res_in + 1) * L.p.cout);
             else
-                max_part = std::max(max_part, sizeof(float) * (size_t)L.gp.n_tiles_n * B * 3 * L.res_out * L.res_out);
+                max_part = std::max(max_part, sizeof(float) * 2 * (size_t)L.gp.n_tiles_n * B * 3 * L.res_out * L.res_out);
         }
         S->layers.push_back(L);
     }
@@ -270,6 +295,10 @@ extern "C" int sg2_synth_create(sg2_synth **plan, int size, int style_dim, int m
     S->off_rgb[0] = take(sizeof(float) * (size_t)B * 3 * size * size);
     S->off_rgb[1] = take(sizeof(float) * (size_t)B * 3 * size * size);
     S->off_part = take(max_part);
+    S->off_toeplitz = take(128 * 256 * 2);
+    S->toeplitz.resize(128 * 256);
+    build_fir_toeplitz(S->toeplitz.data(), S->kf);
+    S->fir_simt = getenv("SG2_FIR_SIMT") != nullptr;
     S->ws_bytes = off;
     // description (one line per launch of a forward pass, in launch order)
     char line[512];
@@ -340,6 +369,7 @@ extern "C" int sg2_synth_pack(sg2_synth *S, void *workspace, sg2_stream_t stream
             if (rc) return rc;
         }
     }
+    SG2_CUDA_OK(cudaMemcpyAsync(ws + S->off_toeplitz, S->toeplitz.data(), S->toeplitz.size() * 2, cudaMemcpyHostToDevice, st));
     S->cached_ws = nullptr;   // descriptors are rebuilt by the next forward
     return SG2_OK;
 }
@@ -370,6 +400,21 @@ extern "C" int sg2_synth_forward(sg2_synth *S, void *workspace, const float *lat
             (void)cur;
             int rc = encode_maps(S, L, x, (const __nv_bfloat16 *)(ws + L.wp), B);
             if (rc) return rc;
+            if (L.p.upsample) {
+                rc = encode_fir_maps(L, Tbuf, B);
+                if (rc) return rc;
+            }
+        }
+        {
+            EncodeTiledFn enc = get_encode();
+            cuuint64_t dims[2] = {256, 128};
+            cuuint64_t strides[1] = {512};
+            cuuint32_t box[2] = {64, 128};
+            cuuint32_t es[2] = {1, 1};
+            CUresult rc = enc(&S->tmK, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ws + S->off_toeplitz, dims, strides, box, es,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            SG2_REQUIRE(rc == CUDA_SUCCESS, SG2_ERR_CUDA, "engine: cuTensorMapEncodeTiled(Toeplitz) failed with %d", (int)rc);
         }
         S->cached_ws = workspace;
         S->cached_B = B;
@@ -441,7 +486,7 @@ extern "C" int sg2_synth_forward(sg2_synth *S, void *workspace, const float *lat
                 const bool last = next_conv == nullptr;
                 const int dst = rgb_cur == 0 ? 1 : 0;
                 rp.out = last ? image : rgbbuf[dst];
-                rp.part = part; rp.n_parts = g.n_tiles_n; rp.bias = rgb->p.act_bias;
+                rp.part = part; rp.n_parts = 2 * g.n_tiles_n; rp.bias = rgb->p.act_bias;
                 rp.prev = rgb_cur >= 0 ? rgbbuf[rgb_cur] : nullptr;
                 rp.B = B; rp.R = L.res_out;
                 memcpy(rp.kf, S->kf, sizeof(rp.kf));
@@ -464,7 +509,18 @@ extern "C" int sg2_synth_forward(sg2_synth *S, void *workspace, const float *lat
             up.noise = nz; up.noise_bstride = nzs; up.noise_weight = L.p.noise_weight;
             up.bias = L.p.act_bias; up.next_style = (const float *)(ws + next_conv->style);
             memcpy(up.kf, S->kf, sizeof(up.kf));
-            rc = launch_upfir(up, B, st);
+            if (S->fir_simt) {
+                rc = launch_upfir(up, B, st);
+            } else {
+                UpfirTcParams tp;
+                tp.out = act[0]; tp.r = L.res_in; tp.C = L.p.cout;
+                tp.block_n = L.p.cout % 128 == 0 ? 128 : 64;
+                tp.tiles_x = (2 * L.res_in + 7) / 8; tp.tiles_y = (2 * L.res_in + 15) / 16; tp.tiles_c = L.p.cout / tp.block_n;
+                tp.total_tiles = tp.tiles_x * tp.tiles_y * tp.tiles_c * B;
+                tp.noise = nz; tp.noise_bstride = nzs; tp.noise_weight = L.p.noise_weight;
+                tp.bias = L.p.act_bias; tp.next_style = up.next_style;
+                rc = launch_upfir_tc(tp, S->tmK, L.tmT, S->sms, st);
+            }
             if (rc) return rc;
             if ((rc = rec(S, st, "upfir"))) return rc;
         }

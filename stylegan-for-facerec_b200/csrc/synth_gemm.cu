@@ -15,11 +15,12 @@
 //   D: fp32 accumulators in TMEM, 128 lanes x BLOCK_N columns, double buffered (2 x 256 columns)
 //       so the epilogue of tile i overlaps the MMAs of tile i+1.
 //   Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) + TMEM allocator,
-//       warps 2..5 = epilogue (tcgen05.ld -> demod, +noise, +bias, lrelu, ToRGB partial dot,
-//       x next layer's style, bf16 pack, store).
+//       warps 2..9 = epilogue, two warps per TMEM lane quarter (tcgen05.ld -> demod, +noise, +bias,
+//       lrelu, ToRGB partial dot, x next layer's style, bf16 pack, store).  Eight warps because the
+//       128-channel layers have only 4.6k cycles of MMA per tile to hide the epilogue under.
 //   The transposed stride-2 convolution of the up-sampling layers runs as four polyphase
 //   sub-problems (4/2/2/1 taps) of the same kernel: no multiplies by inserted zeros.
-//   Persistent: grid = #SMs, static round-robin tile schedule.
+//   Persistent: grid = #SMs; every CTA owns a contiguous chunk of each sub-problem's tiles.
 #include "common.cuh"
 #include "synth_gemm.cuh"
 #include "tc_ptx.cuh"
@@ -28,7 +29,8 @@ namespace sg2 {
 
 using namespace tc;
 
-constexpr int kGemmThreads = 192;
+constexpr int kEpiWarps = 8;
+constexpr int kGemmThreads = 64 + 32 * kEpiWarps;   // TMA warp + MMA warp + epilogue warps
 constexpr int kABytes = kBlockM * kBlockK * 2;          // 16 KiB
 constexpr int kBBytesMax = kMaxBlockN * kBlockK * 2;    // 32 KiB
 constexpr int kEpiCap = 512;                            // NB * BLOCK_N entries of per-sample epilogue params
@@ -51,28 +53,35 @@ struct __align__(1024) GemmSmem {
 };
 
 struct TileCoord {
-    int sub, nt, x0, y0, b0;
+    int nt, x0, y0, b0;
 };
 
-__device__ __forceinline__ TileCoord decode_tile(const GemmParams &p, int tile) {
+// Tile order inside a sub-problem: x fastest, then y, then the N tile, then the sample block --
+// consecutive tiles of a CTA share (sample, N tile), so the staged epilogue parameters are reused.
+__device__ __forceinline__ TileCoord decode_tile(const GemmParams &p, const GemmSub &g, int local) {
     TileCoord t;
-    int s = 0;
-#pragma unroll
-    for (int i = 1; i < kGemmMaxSub; ++i)
-        if (i < p.nsub && tile >= p.sub[i].tile_begin) s = i;
-    const GemmSub &g = p.sub[s];
-    const int local = tile - g.tile_begin;
-    t.sub = s;
+    const int bx = local % g.tiles_x;
+    local /= g.tiles_x;
+    const int by = local % g.tiles_y;
+    local /= g.tiles_y;
     t.nt = local % p.n_tiles_n;
-    int mt = local / p.n_tiles_n;
-    const int bx = mt % g.tiles_x;
-    mt /= g.tiles_x;
-    const int by = mt % g.tiles_y;
-    const int bb = mt / g.tiles_y;
+    const int bb = local / p.n_tiles_n;
     t.x0 = bx * g.TW;
     t.y0 = by * g.TH;
     t.b0 = bb * g.NB;
     return t;
+}
+
+// Every CTA takes one contiguous chunk of EVERY sub-problem (the polyphase sub-problems of the
+// transposed conv cost 4/2/2/1 taps per tile, so chunking them separately keeps CTAs balanced).
+struct TileRange { int lo, hi; };
+__device__ __forceinline__ TileRange cta_range(const GemmParams &p, const GemmSub &g) {
+    const int count = g.tiles_x * g.tiles_y * g.tiles_b * p.n_tiles_n;
+    const int per = (count + (int)gridDim.x - 1) / (int)gridDim.x;
+    TileRange r;
+    r.lo = min(count, (int)blockIdx.x * per);
+    r.hi = min(count, r.lo + per);
+    return r;
 }
 
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
@@ -92,7 +101,7 @@ modconv_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant_
         tma_prefetch_desc(&tmA0);
         tma_prefetch_desc(&tmB);
         for (int i = 0; i < kMaxStages; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&sm.tmem_full[i], 1); mbar_init(&sm.tmem_empty[i], 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&sm.tmem_full[i], 1); mbar_init(&sm.tmem_empty[i], kEpiWarps); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(&sm.tmem_base, 512);
@@ -108,21 +117,24 @@ modconv_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant_
         // ===================== TMA producer =====================
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-                const TileCoord t = decode_tile(p, tile);
-                const GemmSub &g = p.sub[t.sub];
-                const CUtensorMap *tmA = t.sub == 0 ? &tmA0 : (t.sub == 1 ? &tmA1 : (t.sub == 2 ? &tmA2 : &tmA3));
+            for (int s = 0; s < p.nsub; ++s) {
+                const GemmSub &g = p.sub[s];
+                const CUtensorMap *tmA = s == 0 ? &tmA0 : (s == 1 ? &tmA1 : (s == 2 ? &tmA2 : &tmA3));
                 const uint32_t a_bytes = (uint32_t)(g.TH * g.TW * g.NB) * kBlockK * 2;
-                for (int kc = 0; kc < p.kchunks; ++kc) {
-                    for (int tap = 0; tap < g.ntaps; ++tap) {
-                        mbar_wait(&sm.empty[stage], phase ^ 1);
-                        mbar_arrive_expect_tx(&sm.full[stage], a_bytes + b_bytes);
-                        uint8_t *slot = sm.ring + stage * stage_bytes;
-                        tma_load_4d(slot, tmA, &sm.full[stage], kc * kBlockK, t.x0 + g.dx[tap],
-                                    t.y0 + g.dy[tap], t.b0);
-                        tma_load_3d(slot + kABytes, &tmB, &sm.full[stage], kc * kBlockK, t.nt * p.block_n,
-                                    g.wtap[tap]);
-                        if (++stage == nstages) { stage = 0; phase ^= 1; }
+                const TileRange tr = cta_range(p, g);
+                for (int local = tr.lo; local < tr.hi; ++local) {
+                    const TileCoord t = decode_tile(p, g, local);
+                    for (int kc = 0; kc < p.kchunks; ++kc) {
+                        for (int tap = 0; tap < g.ntaps; ++tap) {
+                            mbar_wait(&sm.empty[stage], phase ^ 1);
+                            mbar_arrive_expect_tx(&sm.full[stage], a_bytes + b_bytes);
+                            uint8_t *slot = sm.ring + stage * stage_bytes;
+                            tma_load_4d(slot, tmA, &sm.full[stage], kc * kBlockK, t.x0 + g.dx[tap],
+                                        t.y0 + g.dy[tap], t.b0);
+                            tma_load_3d(slot + kABytes, &tmB, &sm.full[stage], kc * kBlockK, t.nt * p.block_n,
+                                        g.wtap[tap]);
+                            if (++stage == nstages) { stage = 0; phase ^= 1; }
+                        }
                     }
                 }
             }
@@ -132,136 +144,149 @@ modconv_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant_
         if (lane == 0) {
             const uint32_t idesc = make_idesc_bf16(kBlockM, (uint32_t)p.block_n);
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-                const TileCoord t = decode_tile(p, tile);
-                const int nstage = p.kchunks * p.sub[t.sub].ntaps;
-                mbar_wait(&sm.tmem_empty[acc], acc_phase ^ 1);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * kMaxBlockN;
-                for (int s = 0; s < nstage; ++s) {
-                    mbar_wait(&sm.full[stage], phase);
+            for (int s = 0; s < p.nsub; ++s) {
+                const GemmSub &g = p.sub[s];
+                const int nstage = p.kchunks * g.ntaps;
+                const TileRange tr = cta_range(p, g);
+                for (int local = tr.lo; local < tr.hi; ++local) {
+                    mbar_wait(&sm.tmem_empty[acc], acc_phase ^ 1);
                     tc_fence_after();
-                    const uint32_t slot = smem_u32(sm.ring) + stage * stage_bytes;
-                    const uint64_t adesc = make_smem_desc(slot, 128);
-                    const uint64_t bdesc = make_smem_desc(slot + kABytes, 128);
+                    const uint32_t d_tmem = tmem_base + acc * kMaxBlockN;
+                    for (int k0 = 0; k0 < nstage; ++k0) {
+                        mbar_wait(&sm.full[stage], phase);
+                        tc_fence_after();
+                        const uint32_t slot = smem_u32(sm.ring) + stage * stage_bytes;
+                        const uint64_t adesc = make_smem_desc(slot, 128);
+                        const uint64_t bdesc = make_smem_desc(slot + kABytes, 128);
 #pragma unroll
-                    for (int k = 0; k < kBlockK / 16; ++k)   // advance 32 bytes (>>4 = 2) inside the swizzle row
-                        umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (s | k) != 0);
-                    umma_commit(&sm.empty[stage]);           // frees the smem slot when these MMAs retire
-                    if (++stage == nstages) { stage = 0; phase ^= 1; }
+                        for (int k = 0; k < kBlockK / 16; ++k)   // advance 32 bytes (>>4 = 2) inside the swizzle row
+                            umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (k0 | k) != 0);
+                        umma_commit(&sm.empty[stage]);           // frees the smem slot when these MMAs retire
+                        if (++stage == nstages) { stage = 0; phase ^= 1; }
+                    }
+                    umma_commit(&sm.tmem_full[acc]);             // accumulator complete -> epilogue
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 }
-                umma_commit(&sm.tmem_full[acc]);             // accumulator complete -> epilogue
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
     } else {
-        // ===================== epilogue (4 warps = 128 TMEM lanes) =====================
-        const int q = warp & 3;                      // TMEM lane quarter this warp may access
+        // ===================== epilogue: 8 warps, two per TMEM lane quarter =====================
+        // warp (2 + 4h + i) may access TMEM lanes 32*((2+i)&3) ..; the two warps of a quarter split the
+        // accumulator columns in alternating 32-column chunks (h = 0: even chunks, h = 1: odd chunks).
+        const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
         const int m = q * 32 + lane;                 // accumulator row = pixel of the tile
-        const int et = threadIdx.x - 64;             // 0..127 within the epilogue group
+        const int et = threadIdx.x - 64;             // 0..255 within the epilogue group
         const float nw = (p.mode == 0 && p.noise) ? __ldg(p.noise_weight) : 0.f;
+        const int N = p.block_n;
         uint32_t acc = 0, acc_phase = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-            const TileCoord t = decode_tile(p, tile);
-            const GemmSub &g = p.sub[t.sub];
-            const int n0 = t.nt * p.block_n;
-            const int N = p.block_n;
-            // ---- stage the per-(sample, channel) epilogue parameters of this tile ----
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            for (int i = et; i < g.NB * N; i += 128) {
-                const int nb = i / N, col = i - nb * N;
-                const int b = t.b0 + nb < p.B ? t.b0 + nb : p.B - 1;
-                const long long o = (long long)b * p.Cout + n0 + col;
-                sm.e_demod[i] = __ldg(p.demod + o);
-                if (p.mode == 0) {
-                    // lrelu gain sqrt(2) (fused_bias_act_kernel.cu:47) folded into both consumers
-                    sm.e_next[i] = p.next_style ? 1.41421356237f * __ldg(p.next_style + o) : 0.f;
-                    if (p.rgb_w) {
-                        const float rs = 1.41421356237f * __ldg(p.rgb_style + o);
-#pragma unroll
-                        for (int c = 0; c < 3; ++c)
-                            sm.e_wrgb[c][i] = rs * __ldg(p.rgb_w + (long long)c * p.Cout + n0 + col);
-                    }
-                }
-            }
-            if (p.mode == 0)
-                for (int i = et; i < N; i += 128) sm.e_bias[i] = __ldg(p.bias + n0 + i);
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-
-            // ---- which pixel does this lane own ----
+        int staged_key = -1;
+        for (int s = 0; s < p.nsub; ++s) {
+            const GemmSub &g = p.sub[s];
             const int per = g.TH * g.TW;
             const int nb = m / per;
             const int rem = m - nb * per;
             const int ty = rem / g.TW, tx = rem - ty * g.TW;
-            const int y = t.y0 + ty, x = t.x0 + tx, b = t.b0 + nb;
-            const bool valid = nb < g.NB && y < g.PH && x < g.PW && b < p.B;
             const int pb = (nb < g.NB ? nb : 0) * N;    // row of the staged per-sample params
-            float nz = 0.f;
-            if (valid && p.mode == 0 && p.noise)
-                nz = nw * __ldg(p.noise + (long long)b * p.noise_bstride + (long long)y * g.PW + x);
-            __nv_bfloat16 *orow = nullptr;
-            if (valid && p.out)
-                orow = p.out + g.out_off + (((long long)b * g.out_H + y) * g.out_W + x) * p.Cout + n0;
-
-            mbar_wait(&sm.tmem_full[acc], acc_phase);
-            tc_fence_after();
-            float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
-            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kMaxBlockN;
-            for (int c0 = 0; c0 < N; c0 += 32) {
-                uint32_t r[32];
-                tmem_ld32(t_row + c0, r);
-                tmem_ld_wait();
-                uint32_t packed[16];
-                if (p.mode == 0) {
+            const TileRange tr = cta_range(p, g);
+            for (int local = tr.lo; local < tr.hi; ++local) {
+                const TileCoord t = decode_tile(p, g, local);
+                const int n0 = t.nt * N;
+                const int y = t.y0 + ty, x = t.x0 + tx, b = t.b0 + nb;
+                const bool valid = nb < g.NB && y < g.PH && x < g.PW && b < p.B;
+                float nz = 0.f;
+                if (valid && p.mode == 0 && p.noise)     // issued early: overlaps the staging below
+                    nz = __ldg(p.noise + (long long)b * p.noise_bstride + (long long)y * g.PW + x);
+                // ---- stage the per-(sample, channel) epilogue parameters when they change ----
+                const int key = (t.b0 * kMaxBlockN + t.nt) * 16 + g.NB;
+                if (key != staged_key) {
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    for (int i = et; i < g.NB * N; i += 256) {
+                        const int sb = i / N, col = i - sb * N;
+                        const int bb = t.b0 + sb < p.B ? t.b0 + sb : p.B - 1;
+                        const long long o = (long long)bb * p.Cout + n0 + col;
+                        sm.e_demod[i] = __ldg(p.demod + o);
+                        if (p.mode == 0) {
+                            // lrelu gain sqrt(2) (fused_bias_act_kernel.cu:47) folded into both consumers
+                            sm.e_next[i] = p.next_style ? 1.41421356237f * __ldg(p.next_style + o) : 0.f;
+                            if (p.rgb_w) {
+                                const float rs = 1.41421356237f * __ldg(p.rgb_style + o);
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 d4 = *reinterpret_cast<const float4 *>(&sm.e_demod[pb + c0 + j]);
-                        const float4 b4 = *reinterpret_cast<const float4 *>(&sm.e_bias[c0 + j]);
-                        const float4 s4 = *reinterpret_cast<const float4 *>(&sm.e_next[pb + c0 + j]);
-                        float v[4];
-                        v[0] = fmaf(__uint_as_float(r[j + 0]), d4.x, nz) + b4.x;
-                        v[1] = fmaf(__uint_as_float(r[j + 1]), d4.y, nz) + b4.y;
-                        v[2] = fmaf(__uint_as_float(r[j + 2]), d4.z, nz) + b4.z;
-                        v[3] = fmaf(__uint_as_float(r[j + 3]), d4.w, nz) + b4.w;
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], kSlope * v[e]);   // lrelu (gain folded downstream)
-                        if (p.rgb_w) {
-                            const float4 w0 = *reinterpret_cast<const float4 *>(&sm.e_wrgb[0][pb + c0 + j]);
-                            const float4 w1 = *reinterpret_cast<const float4 *>(&sm.e_wrgb[1][pb + c0 + j]);
-                            const float4 w2 = *reinterpret_cast<const float4 *>(&sm.e_wrgb[2][pb + c0 + j]);
-                            rgb0 += v[0] * w0.x + v[1] * w0.y + v[2] * w0.z + v[3] * w0.w;
-                            rgb1 += v[0] * w1.x + v[1] * w1.y + v[2] * w1.z + v[3] * w1.w;
-                            rgb2 += v[0] * w2.x + v[1] * w2.y + v[2] * w2.z + v[3] * w2.w;
+                                for (int c = 0; c < 3; ++c)
+                                    sm.e_wrgb[c][i] = rs * __ldg(p.rgb_w + (long long)c * p.Cout + n0 + col);
+                            }
                         }
-                        packed[j / 2 + 0] = pack_bf16(v[0] * s4.x, v[1] * s4.y);
-                        packed[j / 2 + 1] = pack_bf16(v[2] * s4.z, v[3] * s4.w);
                     }
-                } else {
+                    if (p.mode == 0)
+                        for (int i = et; i < N; i += 256) sm.e_bias[i] = __ldg(p.bias + n0 + i);
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    staged_key = key;
+                }
+                nz *= nw;
+                __nv_bfloat16 *orow = nullptr;
+                if (valid && p.out)
+                    orow = p.out + g.out_off + (((long long)b * g.out_H + y) * g.out_W + x) * p.Cout + n0;
+
+                mbar_wait(&sm.tmem_full[acc], acc_phase);
+                tc_fence_after();
+                float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
+                const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kMaxBlockN;
+                for (int c0 = 32 * half; c0 < N; c0 += 64) {
+                    uint32_t r[32];
+                    tmem_ld32(t_row + c0, r);
+                    tmem_ld_wait();
+                    uint32_t packed[16];
+                    if (p.mode == 0) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 d4 = *reinterpret_cast<const float4 *>(&sm.e_demod[pb + c0 + j]);
-                        packed[j / 2 + 0] = pack_bf16(__uint_as_float(r[j + 0]) * d4.x, __uint_as_float(r[j + 1]) * d4.y);
-                        packed[j / 2 + 1] = pack_bf16(__uint_as_float(r[j + 2]) * d4.z, __uint_as_float(r[j + 3]) * d4.w);
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 d4 = *reinterpret_cast<const float4 *>(&sm.e_demod[pb + c0 + j]);
+                            const float4 b4 = *reinterpret_cast<const float4 *>(&sm.e_bias[c0 + j]);
+                            const float4 s4 = *reinterpret_cast<const float4 *>(&sm.e_next[pb + c0 + j]);
+                            float v[4];
+                            v[0] = fmaf(__uint_as_float(r[j + 0]), d4.x, nz) + b4.x;
+                            v[1] = fmaf(__uint_as_float(r[j + 1]), d4.y, nz) + b4.y;
+                            v[2] = fmaf(__uint_as_float(r[j + 2]), d4.z, nz) + b4.z;
+                            v[3] = fmaf(__uint_as_float(r[j + 3]), d4.w, nz) + b4.w;
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], kSlope * v[e]);   // lrelu (gain folded downstream)
+                            if (p.rgb_w) {
+                                const float4 w0 = *reinterpret_cast<const float4 *>(&sm.e_wrgb[0][pb + c0 + j]);
+                                const float4 w1 = *reinterpret_cast<const float4 *>(&sm.e_wrgb[1][pb + c0 + j]);
+                                const float4 w2 = *reinterpret_cast<const float4 *>(&sm.e_wrgb[2][pb + c0 + j]);
+                                rgb0 += v[0] * w0.x + v[1] * w0.y + v[2] * w0.z + v[3] * w0.w;
+                                rgb1 += v[0] * w1.x + v[1] * w1.y + v[2] * w1.z + v[3] * w1.w;
+                                rgb2 += v[0] * w2.x + v[1] * w2.y + v[2] * w2.z + v[3] * w2.w;
+                            }
+                            packed[j / 2 + 0] = pack_bf16(v[0] * s4.x, v[1] * s4.y);
+                            packed[j / 2 + 1] = pack_bf16(v[2] * s4.z, v[3] * s4.w);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 d4 = *reinterpret_cast<const float4 *>(&sm.e_demod[pb + c0 + j]);
+                            packed[j / 2 + 0] = pack_bf16(__uint_as_float(r[j + 0]) * d4.x, __uint_as_float(r[j + 1]) * d4.y);
+                            packed[j / 2 + 1] = pack_bf16(__uint_as_float(r[j + 2]) * d4.z, __uint_as_float(r[j + 3]) * d4.w);
+                        }
+                    }
+                    if (orow) {
+                        uint4 *dst = reinterpret_cast<uint4 *>(orow + c0);
+#pragma unroll
+                        for (int v4 = 0; v4 < 4; ++v4)
+                            dst[v4] = make_uint4(packed[4 * v4], packed[4 * v4 + 1], packed[4 * v4 + 2], packed[4 * v4 + 3]);
                     }
                 }
-                if (orow) {
-                    uint4 *dst = reinterpret_cast<uint4 *>(orow + c0);
-#pragma unroll
-                    for (int v4 = 0; v4 < 4; ++v4)
-                        dst[v4] = make_uint4(packed[4 * v4], packed[4 * v4 + 1], packed[4 * v4 + 2], packed[4 * v4 + 3]);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.tmem_empty[acc]);
+                if (valid && p.mode == 0 && p.rgb_w) {   // each column half writes its own partial plane
+                    const long long plane = (long long)g.PH * g.PW;
+                    float *rp = p.rgb_part + ((((long long)t.nt * 2 + half) * p.B + b) * 3) * plane + (long long)y * g.PW + x;
+                    rp[0] = rgb0;
+                    rp[plane] = rgb1;
+                    rp[2 * plane] = rgb2;
                 }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.tmem_empty[acc]);
-            if (valid && p.mode == 0 && p.rgb_w) {
-                const long long plane = (long long)g.PH * g.PW;
-                float *rp = p.rgb_part + (((long long)t.nt * p.B + b) * 3) * plane + (long long)y * g.PW + x;
-                rp[0] = rgb0;
-                rp[plane] = rgb1;
-                rp[2 * plane] = rgb2;
-            }
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
 

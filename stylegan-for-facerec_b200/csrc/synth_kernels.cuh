@@ -1,5 +1,6 @@
 // synth_kernels.cuh -- parameter blocks + launchers of the engine's auxiliary kernels.
 #pragma once
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -33,6 +34,16 @@ struct UpfirParams {
     float kf[16];                 // flipped 4x4 taps
 };
 
+// tensor-core variant (synth_fir.cu): T is read through TMA descriptors
+struct UpfirTcParams {
+    __nv_bfloat16 *out;           // [B][2r][2r][C]
+    int r, C, block_n;            // block_n = channels per tile: 128 or 64
+    int tiles_x, tiles_y, tiles_c, total_tiles;
+    const float *noise; long long noise_bstride; const float *noise_weight;
+    const float *bias;            // [C]
+    const float *next_style;      // [B][C]
+};
+
 struct RgbParams {
     float *out;                   // [B,3,R,R]
     const float *part;            // [n_parts][B,3,R,R]
@@ -50,5 +61,7 @@ int launch_demod(const DemodJobs &jobs, int max_cin, int max_cout, int B, cudaSt
 int launch_const_input(__nv_bfloat16 *out, const float *cst, const float *style, int B, int C, int HW, cudaStream_t st);
 int launch_upfir(const UpfirParams &p, int B, cudaStream_t st);
 int launch_rgb_combine(const RgbParams &p, int sms, cudaStream_t st);
+void build_fir_toeplitz(uint16_t *out /*[128][256] bf16 bits*/, const float *kf /*flipped 4x4 taps*/);
+int launch_upfir_tc(const UpfirTcParams &p, const CUtensorMap &tmK, const CUtensorMap *tmT /*[4]*/, int sms, cudaStream_t st);
 
 }  // namespace sg2
