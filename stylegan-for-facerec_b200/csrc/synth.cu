@@ -50,6 +50,7 @@ struct Layer {
     GemmParams gp;        // static part, pointers filled per forward
     CUtensorMap tmA[kGemmMaxSub], tmB;
     CUtensorMap tmT[4];   // up-sampling layers: the 4 polyphase planes as the FIR kernel reads them
+    CUtensorMap tmO;      // ... and its output [B][2r][2r][C] as the TMA store writes it (box 64 ch x 8 x 16)
 };
 
 }  // namespace
@@ -187,7 +188,7 @@ int encode_maps(sg2_synth *S, Layer &L, const __nv_bfloat16 *x, const __nv_bfloa
 
 // TMA views of the 4 polyphase planes [(py,px)][B][r+1][r+1][C]: valid extent (r+1-py) x (r+1-px), so the
 // never-written last row/column of the odd planes reads as zero; box = 10 x 6 pixels x 64 channels
-int encode_fir_maps(Layer &L, const __nv_bfloat16 *T, int B) {
+int encode_fir_maps(Layer &L, const __nv_bfloat16 *T, const __nv_bfloat16 *out, int B) {
     EncodeTiledFn enc = get_encode();
     SG2_REQUIRE(enc, SG2_ERR_CUDA, "engine: cuTensorMapEncodeTiled entry point not available");
     const int C = L.p.cout, r = L.res_in, P = r + 1;
@@ -202,6 +203,17 @@ int encode_fir_maps(Layer &L, const __nv_bfloat16 *T, int B) {
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         SG2_REQUIRE(rc == CUDA_SUCCESS, SG2_ERR_CUDA, "engine: cuTensorMapEncodeTiled(T plane) failed with %d", (int)rc);
+    }
+    {
+        const int R = 2 * r;
+        cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)R, (cuuint64_t)R, (cuuint64_t)B};
+        cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)R * C * 2, (cuuint64_t)R * R * C * 2};
+        cuuint32_t box[4] = {64, 8, 16, 1};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        CUresult rc = enc(&L.tmO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void *)out, dims, strides, box, es,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        SG2_REQUIRE(rc == CUDA_SUCCESS, SG2_ERR_CUDA, "engine: cuTensorMapEncodeTiled(FIR out) failed with %d", (int)rc);
     }
     return SG2_OK;
 }
@@ -401,7 +413,7 @@ extern "C" int sg2_synth_forward(sg2_synth *S, void *workspace, const float *lat
             int rc = encode_maps(S, L, x, (const __nv_bfloat16 *)(ws + L.wp), B);
             if (rc) return rc;
             if (L.p.upsample) {
-                rc = encode_fir_maps(L, Tbuf, B);
+                rc = encode_fir_maps(L, Tbuf, act[0], B);
                 if (rc) return rc;
             }
         }
@@ -519,7 +531,7 @@ extern "C" int sg2_synth_forward(sg2_synth *S, void *workspace, const float *lat
                 tp.total_tiles = tp.tiles_x * tp.tiles_y * tp.tiles_c * B;
                 tp.noise = nz; tp.noise_bstride = nzs; tp.noise_weight = L.p.noise_weight;
                 tp.bias = L.p.act_bias; tp.next_style = up.next_style;
-                rc = launch_upfir_tc(tp, S->tmK, L.tmT, S->sms, st);
+                rc = launch_upfir_tc(tp, S->tmK, L.tmT, L.tmO, S->sms, st);
             }
             if (rc) return rc;
             if ((rc = rec(S, st, "upfir"))) return rc;

@@ -34,6 +34,7 @@ constexpr int FT_N = 128;                        // channels per tile (two 64-ch
 constexpr int FT_CB_BYTES = FT_K * 128;          // one column block of the window: 32 KiB
 constexpr int FT_STAGE_BYTES = 2 * FT_CB_BYTES;  // 64 KiB
 constexpr int FT_STAGES = 2;
+constexpr int FT_OUT_CB_BYTES = 128 * 128;       // staged output tile, one column block: 128 pixels x 128 B
 constexpr int FT_A_BYTES = 128 * FT_K * 2;       // 64 KiB Toeplitz
 constexpr int FT_EPI_WARPS = 8;
 constexpr int FT_THREADS = 64 + 32 * FT_EPI_WARPS;
@@ -41,6 +42,7 @@ constexpr int FT_THREADS = 64 + 32 * FT_EPI_WARPS;
 struct __align__(1024) FirSmem {
     uint8_t a[FT_A_BYTES];
     uint8_t b[FT_STAGES][FT_STAGE_BYTES];
+    uint8_t o[2 * FT_OUT_CB_BYTES];                // bf16 output tile in the TMA store layout (SWIZZLE_128B)
     float e_bias[FT_N];
     float e_next[FT_N];
     uint64_t a_full;
@@ -74,7 +76,8 @@ __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t smem_addr, uint32
 __global__ void __launch_bounds__(FT_THREADS, 1)
 upfir_tc_kernel(const __grid_constant__ UpfirTcParams p, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmT0, const __grid_constant__ CUtensorMap tmT1,
-                const __grid_constant__ CUtensorMap tmT2, const __grid_constant__ CUtensorMap tmT3) {
+                const __grid_constant__ CUtensorMap tmT2, const __grid_constant__ CUtensorMap tmT3,
+                const __grid_constant__ CUtensorMap tmO) {
     extern __shared__ uint8_t smem_raw[];
     FirSmem &sm = *reinterpret_cast<FirSmem *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -101,8 +104,11 @@ upfir_tc_kernel(const __grid_constant__ UpfirTcParams p, const __grid_constant__
     const uint32_t tmem_base = sm.tmem_base;
 
     const int per = (p.total_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int tile_lo = min(p.total_tiles, (int)blockIdx.x * per);
-    const int tile_hi = min(p.total_tiles, tile_lo + per);
+    // round-robin: at any moment the 148 CTAs work on ~5 adjacent tile rows, so the halo rows a tile
+    // shares with its vertical neighbours are still in L2 when the neighbour loads them
+    const int tile_lo = (int)blockIdx.x, tile_step = (int)gridDim.x;
+    (void)per;
+    const int tile_hi = p.total_tiles;
     const int ncb = p.block_n / 64;                 // column blocks per tile (1 or 2)
 
     if (warp == 0) {
@@ -117,7 +123,7 @@ upfir_tc_kernel(const __grid_constant__ UpfirTcParams p, const __grid_constant__
                     "r"(ka * 64), "r"(0)
                     : "memory");
             uint32_t stage = 0, phase = 0;
-            for (int tile = tile_lo; tile < tile_hi; ++tile) {
+            for (int tile = tile_lo; tile < tile_hi; tile += tile_step) {
                 const FirTile t = fir_decode(p, tile);
                 const int a0 = t.y0 / 2, b0 = t.x0 / 2;     // first cell of the tile
                 mbar_wait(&sm.empty[stage], phase ^ 1);
@@ -140,7 +146,7 @@ upfir_tc_kernel(const __grid_constant__ UpfirTcParams p, const __grid_constant__
             const uint32_t idesc = make_idesc_bf16(128, (uint32_t)p.block_n) | (1u << 16);
             mbar_wait(&sm.a_full, 0);
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-            for (int tile = tile_lo; tile < tile_hi; ++tile) {
+            for (int tile = tile_lo; tile < tile_hi; tile += tile_step) {
                 mbar_wait(&sm.tmem_empty[acc], acc_phase ^ 1);
                 mbar_wait(&sm.full[stage], phase);
                 tc_fence_after();
@@ -168,7 +174,7 @@ upfir_tc_kernel(const __grid_constant__ UpfirTcParams p, const __grid_constant__
         const float nw = p.noise ? __ldg(p.noise_weight) : 0.f;
         uint32_t acc = 0, acc_phase = 0;
         int staged_key = -1;
-        for (int tile = tile_lo; tile < tile_hi; ++tile) {
+        for (int tile = tile_lo; tile < tile_hi; tile += tile_step) {
             const FirTile t = fir_decode(p, tile);
             const int Y = t.y0 + oy, X = t.x0 + ox, c0 = t.ct * N;
             const bool valid = Y < R && X < R;
@@ -185,7 +191,9 @@ upfir_tc_kernel(const __grid_constant__ UpfirTcParams p, const __grid_constant__
                 staged_key = key;
             }
             nz *= nw;
-            __nv_bfloat16 *orow = valid ? p.out + (((long long)t.n * R + Y) * R + X) * p.C + c0 : nullptr;
+            // the previous tile's TMA store must have finished reading the staging buffer
+            if (et == 0) tma_store_wait_read();
+            asm volatile("bar.sync 2, 256;" ::: "memory");
             mbar_wait(&sm.tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * FT_N;
@@ -206,19 +214,28 @@ upfir_tc_kernel(const __grid_constant__ UpfirTcParams p, const __grid_constant__
                     packed[j / 2] = *reinterpret_cast<uint32_t *>(&h0);
                     packed[j / 2 + 1] = *reinterpret_cast<uint32_t *>(&h1);
                 }
-                if (orow) {
-                    uint4 *dst = reinterpret_cast<uint4 *>(orow + cc);
+                // stage the 64 bytes of this pixel in the TMA layout: 16-byte chunk index XOR (row & 7)
+                uint8_t *orow = sm.o + (cc >> 6) * FT_OUT_CB_BYTES + m * 128;
+                const int ch0 = (cc & 63) >> 3;
 #pragma unroll
-                    for (int v4 = 0; v4 < 4; ++v4)
-                        dst[v4] = make_uint4(packed[4 * v4], packed[4 * v4 + 1], packed[4 * v4 + 2], packed[4 * v4 + 3]);
-                }
+                for (int v4 = 0; v4 < 4; ++v4)
+                    *reinterpret_cast<uint4 *>(orow + (((ch0 + v4) ^ (m & 7)) << 4)) =
+                        make_uint4(packed[4 * v4], packed[4 * v4 + 1], packed[4 * v4 + 2], packed[4 * v4 + 3]);
             }
             tc_fence_before();
+            fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm.tmem_empty[acc]);
+            asm volatile("bar.sync 3, 256;" ::: "memory");
+            if (et == 0) {      // rows/cols beyond the image are clipped by the TMA unit
+                for (int cb = 0; cb < ncb; ++cb)
+                    tma_store_4d(&tmO, sm.o + cb * FT_OUT_CB_BYTES, c0 + cb * 64, t.x0, t.y0, t.n);
+                tma_store_commit();
+            }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
+    if (threadIdx.x == 64) tma_store_wait_all();
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, 256);
@@ -243,7 +260,8 @@ void build_fir_toeplitz(uint16_t *out, const float *kf) {
     }
 }
 
-int launch_upfir_tc(const UpfirTcParams &p, const CUtensorMap &tmK, const CUtensorMap *tmT, int sms, cudaStream_t st) {
+int launch_upfir_tc(const UpfirTcParams &p, const CUtensorMap &tmK, const CUtensorMap *tmT, const CUtensorMap &tmO,
+                    int sms, cudaStream_t st) {
     static_assert(sizeof(FirSmem) + 1024 <= 227 * 1024, "FirSmem exceeds the 227 KiB CTA limit");
     const size_t smem = sizeof(FirSmem) + 1024;
     static std::atomic<int> configured{0};
@@ -254,7 +272,7 @@ int launch_upfir_tc(const UpfirTcParams &p, const CUtensorMap &tmK, const CUtens
     SG2_REQUIRE(p.block_n == 64 || p.block_n == 128, SG2_ERR_BAD_ARG, "upfir_tc: block_n must be 64 or 128");
     const int grid = p.total_tiles < sms ? p.total_tiles : sms;
     if (grid <= 0) return SG2_OK;
-    upfir_tc_kernel<<<grid, FT_THREADS, smem, st>>>(p, tmK, tmT[0], tmT[1], tmT[2], tmT[3]);
+    upfir_tc_kernel<<<grid, FT_THREADS, smem, st>>>(p, tmK, tmT[0], tmT[1], tmT[2], tmT[3], tmO);
     SG2_LAUNCH_CHECK();
     return SG2_OK;
 }

@@ -62,6 +62,7 @@ int launch_const_input(__nv_bfloat16 *out, const float *cst, const float *style,
 int launch_upfir(const UpfirParams &p, int B, cudaStream_t st);
 int launch_rgb_combine(const RgbParams &p, int sms, cudaStream_t st);
 void build_fir_toeplitz(uint16_t *out /*[128][256] bf16 bits*/, const float *kf /*flipped 4x4 taps*/);
-int launch_upfir_tc(const UpfirTcParams &p, const CUtensorMap &tmK, const CUtensorMap *tmT /*[4]*/, int sms, cudaStream_t st);
+int launch_upfir_tc(const UpfirTcParams &p, const CUtensorMap &tmK, const CUtensorMap *tmT /*[4]*/, const CUtensorMap &tmO,
+                    int sms, cudaStream_t st);
 
 }  // namespace sg2

@@ -63,6 +63,19 @@ __device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *m, uin
         : "memory");
 }
 
+// TMA store (shared -> global), bulk-group completion
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap *m, const void *src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// the issuing thread waits until the source shared memory of all its stores has been read
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// make generic-proxy shared-memory writes visible to the async proxy (TMA, tcgen05)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // ---- tcgen05 ------------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {   // whole warp
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
