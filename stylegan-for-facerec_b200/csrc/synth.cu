@@ -100,7 +100,8 @@ int plan_gemm(sg2_synth *S, Layer &L) {
     const int cin = L.p.cin, cout = L.p.cout;
     const bool up = L.p.upsample != 0;
     const int r = L.res_in;
-    g.Cin = cin; g.Cout = cout; g.kchunks = cin / kBlockK;
+    g.block_k = cin % 64 == 0 ? 64 : 32;
+    g.Cin = cin; g.Cout = cout; g.kchunks = cin / g.block_k;
     g.mode = up ? 1 : 0;
     g.nsub = up ? 4 : 1;
     // sub-problems
@@ -161,14 +162,15 @@ int encode_maps(sg2_synth *S, Layer &L, const __nv_bfloat16 *x, const __nv_bfloa
     EncodeTiledFn enc = get_encode();
     SG2_REQUIRE(enc, SG2_ERR_CUDA, "engine: cuTensorMapEncodeTiled entry point not available");
     const int C = L.p.cin, r = L.res_in;
+    const CUtensorMapSwizzle swz = L.gp.block_k == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     for (int s = 0; s < L.gp.nsub; ++s) {
         const GemmSub &q = L.gp.sub[s];
         cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)r, (cuuint64_t)r, (cuuint64_t)B};
         cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)r * C * 2, (cuuint64_t)r * r * C * 2};
-        cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)q.TW, (cuuint32_t)q.TH, (cuuint32_t)q.NB};
+        cuuint32_t box[4] = {(cuuint32_t)L.gp.block_k, (cuuint32_t)q.TW, (cuuint32_t)q.TH, (cuuint32_t)q.NB};
         cuuint32_t es[4] = {1, 1, 1, 1};
         CUresult rc = enc(&L.tmA[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void *)x, dims, strides, box, es,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         SG2_REQUIRE(rc == CUDA_SUCCESS, SG2_ERR_CUDA, "engine: cuTensorMapEncodeTiled(A) failed with %d (C=%d r=%d box %d,%d,%d)",
                     (int)rc, C, r, q.TW, q.TH, q.NB);
@@ -176,10 +178,10 @@ int encode_maps(sg2_synth *S, Layer &L, const __nv_bfloat16 *x, const __nv_bfloa
     {
         cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)L.p.cout, 9};
         cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)C * L.p.cout * 2};
-        cuuint32_t box[3] = {(cuuint32_t)kBlockK, (cuuint32_t)L.block_n, 1};
+        cuuint32_t box[3] = {(cuuint32_t)L.gp.block_k, (cuuint32_t)L.block_n, 1};
         cuuint32_t es[3] = {1, 1, 1};
         CUresult rc = enc(&L.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void *)wp, dims, strides, box, es,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         SG2_REQUIRE(rc == CUDA_SUCCESS, SG2_ERR_CUDA, "engine: cuTensorMapEncodeTiled(B) failed with %d", (int)rc);
     }
@@ -279,11 +281,10 @@ extern "C" int sg2_synth_create(sg2_synth **plan, int size, int style_dim, int m
         if (L.rgb) {
             L.rgbw = take(sizeof(float) * 3 * L.p.cin);
         } else {
-            if (L.p.cin % kBlockK || L.p.cout % 16 || (L.p.upsample && L.p.cout % 64)) {
+            if (L.p.cin % 32 || L.p.cout % 16 || (L.p.upsample && L.p.cout % 32)) {
                 delete S;
-                set_error("engine: styled conv %d with Cin %d / Cout %d needs Cin %% 64 == 0 (and Cout %% 64 == 0 for "
-                          "up-sampling layers); the 32-channel 1024^2 tail is not on the tensor-core path yet",
-                          i, L.p.cin, L.p.cout);
+                set_error("engine: styled conv %d with Cin %d / Cout %d needs Cin %% 32 == 0 and Cout %% 16 == 0 "
+                          "(Cout %% 32 == 0 for up-sampling layers)", i, L.p.cin, L.p.cout);
                 return SG2_ERR_UNSUPPORTED;
             }
             L.wp = take(sizeof(__nv_bfloat16) * 9 * L.p.cout * L.p.cin);
@@ -521,7 +522,7 @@ extern "C" int sg2_synth_forward(sg2_synth *S, void *workspace, const float *lat
             up.noise = nz; up.noise_bstride = nzs; up.noise_weight = L.p.noise_weight;
             up.bias = L.p.act_bias; up.next_style = (const float *)(ws + next_conv->style);
             memcpy(up.kf, S->kf, sizeof(up.kf));
-            if (S->fir_simt) {
+            if (S->fir_simt || L.p.cout % 64 != 0) {   // 32-channel tail: SIMT stencil (64-byte rows)
                 rc = launch_upfir(up, B, st);
             } else {
                 UpfirTcParams tp;

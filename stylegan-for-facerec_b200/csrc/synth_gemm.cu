@@ -109,8 +109,12 @@ modconv_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = sm.tmem_base;
-    const uint32_t b_bytes = (uint32_t)p.block_n * kBlockK * 2;
-    const uint32_t stage_bytes = kABytes + b_bytes;          // multiple of 1 KiB: swizzle atoms stay aligned
+    // K chunk per stage: 64 channels (128-byte rows, SWIZZLE_128B) or, for the 32-channel 1024^2 tail,
+    // 32 channels (64-byte rows, SWIZZLE_64B)
+    const uint32_t bk = (uint32_t)p.block_k, row_bytes = bk * 2;
+    const uint32_t a_stage = kBlockM * row_bytes;
+    const uint32_t b_bytes = (uint32_t)p.block_n * row_bytes;
+    const uint32_t stage_bytes = a_stage + b_bytes;          // multiple of 1 KiB: swizzle atoms stay aligned
     const uint32_t nstages = min((uint32_t)kMaxStages, (uint32_t)kRingBytes / stage_bytes);
 
     if (warp == 0) {
@@ -120,7 +124,7 @@ modconv_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant_
             for (int s = 0; s < p.nsub; ++s) {
                 const GemmSub &g = p.sub[s];
                 const CUtensorMap *tmA = s == 0 ? &tmA0 : (s == 1 ? &tmA1 : (s == 2 ? &tmA2 : &tmA3));
-                const uint32_t a_bytes = (uint32_t)(g.TH * g.TW * g.NB) * kBlockK * 2;
+                const uint32_t a_bytes = (uint32_t)(g.TH * g.TW * g.NB) * row_bytes;
                 const TileRange tr = cta_range(p, g);
                 for (int local = tr.lo; local < tr.hi; ++local) {
                     const TileCoord t = decode_tile(p, g, local);
@@ -129,9 +133,9 @@ modconv_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant_
                             mbar_wait(&sm.empty[stage], phase ^ 1);
                             mbar_arrive_expect_tx(&sm.full[stage], a_bytes + b_bytes);
                             uint8_t *slot = sm.ring + stage * stage_bytes;
-                            tma_load_4d(slot, tmA, &sm.full[stage], kc * kBlockK, t.x0 + g.dx[tap],
+                            tma_load_4d(slot, tmA, &sm.full[stage], kc * (int)bk, t.x0 + g.dx[tap],
                                         t.y0 + g.dy[tap], t.b0);
-                            tma_load_3d(slot + kABytes, &tmB, &sm.full[stage], kc * kBlockK, t.nt * p.block_n,
+                            tma_load_3d(slot + a_stage, &tmB, &sm.full[stage], kc * (int)bk, t.nt * p.block_n,
                                         g.wtap[tap]);
                             if (++stage == nstages) { stage = 0; phase ^= 1; }
                         }
@@ -156,10 +160,9 @@ modconv_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant_
                         mbar_wait(&sm.full[stage], phase);
                         tc_fence_after();
                         const uint32_t slot = smem_u32(sm.ring) + stage * stage_bytes;
-                        const uint64_t adesc = make_smem_desc(slot, 128);
-                        const uint64_t bdesc = make_smem_desc(slot + kABytes, 128);
-#pragma unroll
-                        for (int k = 0; k < kBlockK / 16; ++k)   // advance 32 bytes (>>4 = 2) inside the swizzle row
+                        const uint64_t adesc = make_smem_desc(slot, row_bytes);
+                        const uint64_t bdesc = make_smem_desc(slot + a_stage, row_bytes);
+                        for (uint32_t k = 0; k < bk / 16; ++k)   // advance 32 bytes (>>4 = 2) inside the swizzle row
                             umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (k0 | k) != 0);
                         umma_commit(&sm.empty[stage]);           // frees the smem slot when these MMAs retire
                         if (++stage == nstages) { stage = 0; phase ^= 1; }
@@ -306,8 +309,8 @@ int launch_modconv_gemm(const GemmParams &p, const CUtensorMap *tmA, const CUten
         configured.store(1, std::memory_order_release);
     }
     SG2_REQUIRE(p.block_n % 16 == 0 && p.block_n >= 16 && p.block_n <= kMaxBlockN, SG2_ERR_BAD_ARG, "gemm: bad BLOCK_N %d", p.block_n);
-    SG2_REQUIRE(p.Cin % kBlockK == 0 && p.Cout % p.block_n == 0, SG2_ERR_UNSUPPORTED,
-                "gemm: Cin %d must be a multiple of 64 and Cout %d of BLOCK_N %d", p.Cin, p.Cout, p.block_n);
+    SG2_REQUIRE((p.block_k == 64 || p.block_k == 32) && p.Cin % p.block_k == 0 && p.Cout % p.block_n == 0, SG2_ERR_UNSUPPORTED,
+                "gemm: Cin %d must be a multiple of BLOCK_K %d and Cout %d of BLOCK_N %d", p.Cin, p.block_k, p.Cout, p.block_n);
     for (int s = 0; s < p.nsub; ++s)
         SG2_REQUIRE(p.sub[s].NB * p.block_n <= kEpiCap && p.sub[s].TH * p.sub[s].TW * p.sub[s].NB <= kBlockM,
                     SG2_ERR_BAD_ARG, "gemm: tile of sub-problem %d too large", s);

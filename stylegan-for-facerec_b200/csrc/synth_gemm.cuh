@@ -30,7 +30,8 @@ struct GemmParams {
     int nsub;
     GemmSub sub[kGemmMaxSub];
     int B, Cin, Cout;
-    int block_n, n_tiles_n, total_tiles, kchunks;   // kchunks = Cin / 64
+    int block_n, n_tiles_n, total_tiles, kchunks;   // kchunks = Cin / block_k
+    int block_k;                    // channels per pipeline stage: 64 (SWIZZLE_128B rows) or 32 (SWIZZLE_64B)
     // epilogue
     int mode;                       // 0: styled conv (noise, bias, lrelu, next-style, ToRGB); 1: plain scaled store
     const float *demod;             // [B, Cout]

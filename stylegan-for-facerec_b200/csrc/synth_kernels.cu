@@ -102,25 +102,31 @@ const_input_kernel(__nv_bfloat16 *__restrict__ out, const float *__restrict__ cs
     out[i] = __float2bfloat16_rn(cst[(int64_t)c * HW + p] * style[(int64_t)b * C + c]);
 }
 
-// ---- up-sampling layer tail: blur (4x4, pad (1,1)) over the 4 polyphase planes of the transposed
-// conv, + noise, + bias, lrelu, x sqrt(2) * next style, NHWC bf16 store.
-// Block: 32 cells (8 x 4, each a 2x2 output block) x 8 channel-vectors (64 channels).
-constexpr int FIR_CA = 8, FIR_CB = 4, FIR_CH = 64;
-constexpr int FIR_ROWS = 2 * FIR_CA + 3, FIR_COLS = 2 * FIR_CB + 3;
+// ---- up-sampling layer tail, SIMT stencil (used for the 32-channel 1024^2 layer; the 64-channel
+// multiples go through the tensor-core kernel in synth_fir.cu): blur (4x4, pad (1,1)) over the 4
+// polyphase planes of the transposed conv, + noise, + bias, lrelu, x sqrt(2) * next style, NHWC bf16.
+// Block: 256 threads = (8 x CB) cells (each a 2x2 output block) x (CH/8) channel vectors.
+constexpr int FIR_CA = 8;
+template <int CH> struct FirGeo {
+    static constexpr int VEC = CH / 8, CELLS = 256 / VEC, CB = CELLS / FIR_CA;
+    static constexpr int ROWS = 2 * FIR_CA + 3, COLS = 2 * CB + 3;
+};
 
+template <int CH>
 __global__ void __launch_bounds__(256)
 upfir_kernel(UpfirParams p) {
-    __shared__ __align__(16) __nv_bfloat16 s_t[FIR_ROWS][FIR_COLS][FIR_CH];
+    using G = FirGeo<CH>;
+    __shared__ __align__(16) __nv_bfloat16 s_t[G::ROWS][G::COLS][CH];
     const int tid = threadIdx.x;
-    const int tiles_b = (p.r + FIR_CB - 1) / FIR_CB;
-    const int a0 = (blockIdx.x / tiles_b) * FIR_CA, b0 = (blockIdx.x % tiles_b) * FIR_CB;
-    const int c0 = blockIdx.y * FIR_CH;
+    const int tiles_b = (p.r + G::CB - 1) / G::CB;
+    const int a0 = (blockIdx.x / tiles_b) * FIR_CA, b0 = (blockIdx.x % tiles_b) * G::CB;
+    const int c0 = blockIdx.y * CH;
     const int n = blockIdx.z;
     const int P = p.r + 1;                                   // allocated plane extent
     // stage the T window: rows t = 2*a0-1 .. 2*a0+2*CA+1, cols likewise
-    for (int i = tid; i < FIR_ROWS * FIR_COLS * 8; i += 256) {
-        const int v = i & 7, pix = i >> 3;
-        const int row = pix / FIR_COLS, col = pix - row * FIR_COLS;
+    for (int i = tid; i < G::ROWS * G::COLS * G::VEC; i += 256) {
+        const int v = i % G::VEC, pix = i / G::VEC;
+        const int row = pix / G::COLS, col = pix - row * G::COLS;
         const int t = 2 * a0 - 1 + row, u = 2 * b0 - 1 + col;
         uint4 val = make_uint4(0, 0, 0, 0);
         if (t >= 0 && u >= 0 && t <= 2 * p.r && u <= 2 * p.r) {
@@ -133,8 +139,8 @@ upfir_kernel(UpfirParams p) {
         *reinterpret_cast<uint4 *>(&s_t[row][col][v * 8]) = val;
     }
     __syncthreads();
-    const int v = tid & 7, cell = tid >> 3;
-    const int ca = cell / FIR_CB, cb = cell - ca * FIR_CB;
+    const int v = tid % G::VEC, cell = tid / G::VEC;
+    const int ca = cell / G::CB, cb = cell - ca * G::CB;
     const int a = a0 + ca, b = b0 + cb;
     if (a >= p.r || b >= p.r) return;
     float acc[2][2][8];
@@ -270,9 +276,15 @@ int launch_const_input(__nv_bfloat16 *out, const float *cst, const float *style,
     return SG2_OK;
 }
 int launch_upfir(const UpfirParams &p, int B, cudaStream_t st) {
-    const int ta = (p.r + FIR_CA - 1) / FIR_CA, tb = (p.r + FIR_CB - 1) / FIR_CB;
-    dim3 grid(ta * tb, p.C / FIR_CH, B);
-    upfir_kernel<<<grid, 256, 0, st>>>(p);
+    const int ta = (p.r + FIR_CA - 1) / FIR_CA;
+    if (p.C % 64 == 0) {
+        const int tb = (p.r + FirGeo<64>::CB - 1) / FirGeo<64>::CB;
+        upfir_kernel<64><<<dim3(ta * tb, p.C / 64, B), 256, 0, st>>>(p);
+    } else {
+        SG2_REQUIRE(p.C % 32 == 0, SG2_ERR_UNSUPPORTED, "upfir: channel count %d is not a multiple of 32", p.C);
+        const int tb = (p.r + FirGeo<32>::CB - 1) / FirGeo<32>::CB;
+        upfir_kernel<32><<<dim3(ta * tb, p.C / 32, B), 256, 0, st>>>(p);
+    }
     SG2_LAUNCH_CHECK();
     return SG2_OK;
 }

@@ -98,3 +98,19 @@ def test_engine_launch_count(sg2, oracle):
         G([z], randomize_noise=False)
         n = sg2._lib.launch_count() - n0
     assert n <= 40, n
+
+
+def test_engine_golden_1024(sg2, oracle, golden, cases):
+    """FFHQ/ReStyle default resolution: exercises the 32-channel tail (BLOCK_K = 32 / SWIZZLE_64B GEMM,
+    32-channel FIR) against the reference's fp32 output lattice."""
+    case = [c for c in cases.GEN_CASES if c[0] == "g1024_wplus"][0]
+    name, size, n_mlp, cm, batch, mode = case
+    G, sd = _gen(sg2, oracle, size, n_mlp, cm)
+    styles, kw = cases.gen_inputs(name, size, n_mlp, batch, mode, sd)
+    with torch.no_grad():
+        img, lat = G([s.to(DEV) for s in styles], **kw)
+    assert img.shape == (1, 3, 1024, 1024) and lat.shape == (1, 18, 512)
+    ref = torch.from_numpy(golden["generator"][name + "/img_lattice8"])
+    _check(img[:, :, 3::8, 5::8], ref, name)
+    mom = golden["generator"][name + "/img_moments"]
+    assert abs(img.double().mean().item() - mom[0]) < 2e-2 and abs(img.double().std().item() - mom[1]) < 2e-2
