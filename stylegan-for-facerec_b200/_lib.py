@@ -15,7 +15,8 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libsg2_b200.so")
+# SG2_B200_LIB selects another build of the same ABI (A/B runs of kernel variants on one GPU box)
+LIB_PATH = os.environ.get("SG2_B200_LIB") or os.path.join(_HERE, "csrc", "libsg2_b200.so")
 
 SG2_F32, SG2_F16, SG2_BF16 = 0, 1, 2
 _DTYPES = {torch.float32: SG2_F32, torch.float16: SG2_F16, torch.bfloat16: SG2_BF16}
