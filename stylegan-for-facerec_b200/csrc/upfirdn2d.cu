@@ -25,11 +25,22 @@ __host__ __device__ __forceinline__ int floordiv(int a, int b) {
     return (q * b > a) ? q - 1 : q;
 }
 
+constexpr int GEN_TILE_W = 32, GEN_TILE_H = 8, GEN_MAXK = 16, GEN_MAXF = 4;
+constexpr int GEN_IN_W = ((GEN_TILE_W - 1) * GEN_MAXF + GEN_MAXK - 1) + 1;  // worst case, up = 1
+constexpr int GEN_IN_H = ((GEN_TILE_H - 1) * GEN_MAXF + GEN_MAXK - 1) + 1;
+
+struct UfdGenParams {
+    int in_h, in_w, out_h, out_w, minor;
+    int up_x, up_y, down_x, down_y, pad_x0, pad_y0, kh, kw;
+    int64_t major;
+};
+
 struct UfdParams {
     int in_h, in_w, out_h, out_w;
     int pad_x0, pad_y0;
     int kh, kw;
     int shift_x, shift_y;   // tile-grid shift so that phases are compile-time
+    int vec_store;          // rows of a thread's TX outputs are aligned for one vector store
     int64_t planes;
 };
 
@@ -80,13 +91,17 @@ upfirdn2d_poly_kernel(T *__restrict__ out, const T *__restrict__ x, const float 
     for (int64_t plane = blockIdx.z; plane < p.planes; plane += gridDim.z) {
         const T *xp = x + plane * p.in_h * p.in_w;
         __syncthreads();
-        for (int i = tid; i < G::IN_H * G::IN_W; i += 256) {
-            const int ry = i / G::IN_W, rx = i - ry * G::IN_W;
-            const int iy = iy0 + ry, ix = ix0 + rx;
-            float v = 0.f;
-            if (iy >= 0 && ix >= 0 && iy < p.in_h && ix < p.in_w)
-                v = Cvt<T>::to_f(xp[(int64_t)iy * p.in_w + ix]);
-            s_in[ry * G::IN_WP + rx] = v;
+        // one warp per tile row: coalesced, no per-element division, row validity hoisted
+        for (int ry = tid >> 5; ry < G::IN_H; ry += 8) {
+            const int iy = iy0 + ry;
+            const bool row_ok = iy >= 0 && iy < p.in_h;
+            const T *xr = xp + (int64_t)iy * p.in_w;
+            float *sr = s_in + ry * G::IN_WP;
+#pragma unroll 2
+            for (int rx = tid & 31; rx < G::IN_W; rx += 32) {
+                const int ix = ix0 + rx;
+                sr[rx] = (row_ok && ix >= 0 && ix < p.in_w) ? Cvt<T>::to_f(xr[ix]) : 0.f;
+            }
         }
         __syncthreads();
 
@@ -117,9 +132,9 @@ upfirdn2d_poly_kernel(T *__restrict__ out, const T *__restrict__ x, const float 
 #pragma unroll
         for (int j = 0; j < TY; ++j) {
             const int oy = oy0 + ty * TY + j;
+            float row[TX];
 #pragma unroll
             for (int i = 0; i < TX; ++i) {
-                const int ox = ox0 + tx * TX + i;
                 float acc = 0.f;
 #pragma unroll
                 for (int a = 0; a < G::ntap(j); ++a)
@@ -127,23 +142,28 @@ upfirdn2d_poly_kernel(T *__restrict__ out, const T *__restrict__ x, const float 
                     for (int b = 0; b < G::ntap(i); ++b)
                         acc += win[G::in_off(j) + a][G::in_off(i) + b] *
                                kreg[G::k0(j) + a * UP][G::k0(i) + b * UP];
-                if (oy >= 0 && ox >= 0 && oy < p.out_h && ox < p.out_w)
-                    op[(int64_t)oy * p.out_w + ox] = Cvt<T>::from_f(acc);
+                row[i] = acc;
+            }
+            if (oy < 0 || oy >= p.out_h) continue;
+            const int oxs = ox0 + tx * TX;
+            T *dst = op + (int64_t)oy * p.out_w + oxs;
+            if (p.vec_store && oxs >= 0 && oxs + TX <= p.out_w) {       // TX contiguous outputs in one store
+                T pk[TX];
+#pragma unroll
+                for (int i = 0; i < TX; ++i) pk[i] = Cvt<T>::from_f(row[i]);
+                if (sizeof(T) * TX == 16) *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(pk);
+                else if (sizeof(T) * TX == 8) *reinterpret_cast<uint2 *>(dst) = *reinterpret_cast<const uint2 *>(pk);
+                else *reinterpret_cast<uint32_t *>(dst) = *reinterpret_cast<const uint32_t *>(pk);
+            } else {
+#pragma unroll
+                for (int i = 0; i < TX; ++i)
+                    if (oxs + i >= 0 && oxs + i < p.out_w) dst[i] = Cvt<T>::from_f(row[i]);
             }
         }
     }
 }
 
 // ---- generic kernel (runtime up/down/taps, minor >= 1) ----------------------------------------------
-constexpr int GEN_TILE_W = 32, GEN_TILE_H = 8, GEN_MAXK = 16, GEN_MAXF = 4;
-constexpr int GEN_IN_W = ((GEN_TILE_W - 1) * GEN_MAXF + GEN_MAXK - 1) + 1;  // worst case, up = 1
-constexpr int GEN_IN_H = ((GEN_TILE_H - 1) * GEN_MAXF + GEN_MAXK - 1) + 1;
-
-struct UfdGenParams {
-    int in_h, in_w, out_h, out_w, minor;
-    int up_x, up_y, down_x, down_y, pad_x0, pad_y0, kh, kw;
-    int64_t major;
-};
 
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -192,6 +212,43 @@ upfirdn2d_generic_kernel(T *__restrict__ out, const T *__restrict__ x,
     }
 }
 
+// ---- small images (<= 16 x 16 outputs): one thread per output, planes packed into the grid ------------
+// At 4x4 ... 16x16 a 128 x 32 tile per block is >= 94 % idle; everything is cache resident, so plain
+// gather loads with the same polyphase index math (upfirdn2d_kernel.cu:112-129) win.
+template <typename T>
+__global__ void __launch_bounds__(256)
+upfirdn2d_small_kernel(T *__restrict__ out, const T *__restrict__ x, const float *__restrict__ taps,
+                       UfdGenParams p) {
+    __shared__ float s_k[GEN_MAXK * GEN_MAXK];
+    for (int i = threadIdx.x; i < p.kh * p.kw; i += 256) {
+        const int ky = i / p.kw, kx = i - ky * p.kw;
+        s_k[i] = taps[(p.kh - 1 - ky) * p.kw + (p.kw - 1 - kx)];
+    }
+    __syncthreads();
+    const int opix = p.out_h * p.out_w;
+    const int64_t total = p.major * opix;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+        const int64_t plane = i / opix;
+        const int r = (int)(i - plane * opix);
+        const int oy = r / p.out_w, ox = r - oy * p.out_w;
+        const int mid_x = ox * p.down_x + p.up_x - 1 - p.pad_x0, mid_y = oy * p.down_y + p.up_y - 1 - p.pad_y0;
+        const int in_x = floordiv(mid_x, p.up_x), in_y = floordiv(mid_y, p.up_y);
+        const int kx0 = (in_x + 1) * p.up_x - mid_x - 1, ky0 = (in_y + 1) * p.up_y - mid_y - 1;
+        const T *xp = x + plane * p.in_h * p.in_w;
+        float acc = 0.f;
+        for (int a = 0, ky = ky0; ky < p.kh; ++a, ky += p.up_y) {
+            const int iy = in_y + a;
+            if (iy < 0 || iy >= p.in_h) continue;
+            for (int b = 0, kx = kx0; kx < p.kw; ++b, kx += p.up_x) {
+                const int ix = in_x + b;
+                if (ix < 0 || ix >= p.in_w) continue;
+                acc += Cvt<T>::to_f(xp[iy * p.in_w + ix]) * s_k[ky * p.kw + kx];
+            }
+        }
+        out[i] = Cvt<T>::from_f(acc);
+    }
+}
+
 template <typename T, int UP, int DOWN, int TX, int TY>
 static int launch_poly(void *out, const void *x, const float *taps, int64_t planes, int in_h,
                        int in_w, int out_h, int out_w, int kh, int kw, int pad_x0, int pad_y0,
@@ -203,6 +260,8 @@ static int launch_poly(void *out, const void *x, const float *taps, int64_t plan
     // shift s in [0, UP) with (-s*DOWN - pad) % UP == 0  (DOWN == 1 whenever UP > 1 here)
     auto shift = [](int pad) { return UP == 1 ? 0 : ((-pad) % UP + UP) % UP; };
     p.shift_x = shift(pad_x0); p.shift_y = shift(pad_y0);
+    p.vec_store = p.shift_x == 0 && out_w % TX == 0 && (reinterpret_cast<uintptr_t>(out) % (sizeof(T) * TX)) == 0 &&
+                  ((int64_t)out_h * out_w * sizeof(T)) % (sizeof(T) * TX) == 0;
     dim3 grid((out_w + p.shift_x + G::TILE_W - 1) / G::TILE_W,
               (out_h + p.shift_y + G::TILE_H - 1) / G::TILE_H,
               (unsigned)std::min<int64_t>(planes, 32768));
@@ -239,6 +298,17 @@ extern "C" int sg2_upfirdn2d(void *out, const void *x, const float *kernel, int6
     cudaStream_t st = as_stream(stream);
     const bool sym = up_x == up_y && down_x == down_y && minor == 1 && kh <= 4 && kw <= 4;
     SG2_DISPATCH_DTYPE(dtype, {
+        if (minor == 1 && out_h * out_w <= 256) {   // up to 16 x 16 outputs per plane
+            UfdGenParams p;
+            p.in_h = in_h; p.in_w = in_w; p.out_h = out_h; p.out_w = out_w; p.minor = 1;
+            p.up_x = up_x; p.up_y = up_y; p.down_x = down_x; p.down_y = down_y;
+            p.pad_x0 = pad_x0; p.pad_y0 = pad_y0; p.kh = kh; p.kw = kw; p.major = major;
+            const int64_t total = major * out_h * out_w;
+            unsigned blocks = (unsigned)std::min<int64_t>(ceil_div64(total, 256), (int64_t)sm_count() * 32);
+            upfirdn2d_small_kernel<T><<<blocks, 256, 0, st>>>((T *)out, (const T *)x, kernel, p);
+            SG2_LAUNCH_CHECK();
+            return SG2_OK;
+        }
         if (sym && up_x == 1 && down_x == 1)
             return launch_poly<T, 1, 1, 4, 4>(out, x, kernel, major, in_h, in_w, out_h, out_w, kh, kw, pad_x0, pad_y0, st);
         if (sym && up_x == 2 && down_x == 1)
