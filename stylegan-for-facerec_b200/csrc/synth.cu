@@ -390,10 +390,11 @@ extern "C" int sg2_synth_pack(sg2_synth *S, void *workspace, sg2_stream_t stream
 extern "C" int sg2_synth_forward(sg2_synth *S, void *workspace, const float *latent, int64_t B64,
                                  const float *const *noise, const int64_t *noise_bstride, float *image,
                                  sg2_stream_t stream) {
-    SG2_REQUIRE(S && workspace && latent && image && noise && noise_bstride, SG2_ERR_BAD_ARG, "synth_forward: null pointer");
+    SG2_REQUIRE(S, SG2_ERR_BAD_ARG, "synth_forward: null plan");
     SG2_REQUIRE(B64 >= 0 && B64 <= S->max_batch, SG2_ERR_BAD_ARG, "synth_forward: batch %lld exceeds the plan's max_batch %d",
                 (long long)B64, S->max_batch);
-    if (B64 == 0) return SG2_OK;
+    if (B64 == 0) return SG2_OK;                 // empty batch: nothing to launch (tensor pointers may be null)
+    SG2_REQUIRE(workspace && latent && image && noise && noise_bstride, SG2_ERR_BAD_ARG, "synth_forward: null pointer");
     const int B = (int)B64;
     cudaStream_t st = as_stream(stream);
     uint8_t *ws = static_cast<uint8_t *>(workspace);
@@ -527,7 +528,8 @@ extern "C" int sg2_synth_forward(sg2_synth *S, void *workspace, const float *lat
             } else {
                 UpfirTcParams tp;
                 tp.out = act[0]; tp.r = L.res_in; tp.C = L.p.cout;
-                tp.block_n = L.p.cout % 128 == 0 ? 128 : 64;
+                static const bool fir64 = getenv("SG2_FIR_N64") != nullptr;
+                tp.block_n = (L.p.cout % 128 == 0 && !fir64) ? 128 : 64;
                 tp.tiles_x = (2 * L.res_in + 7) / 8; tp.tiles_y = (2 * L.res_in + 15) / 16; tp.tiles_c = L.p.cout / tp.block_n;
                 tp.total_tiles = tp.tiles_x * tp.tiles_y * tp.tiles_c * B;
                 tp.noise = nz; tp.noise_bstride = nzs; tp.noise_weight = L.p.noise_weight;

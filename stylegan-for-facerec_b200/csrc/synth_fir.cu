@@ -32,8 +32,7 @@ constexpr int FT_PLANE_ROWS = 64;                // 60 used + 4 zero pad rows
 constexpr int FT_K = 4 * FT_PLANE_ROWS;          // 256
 constexpr int FT_N = 128;                        // channels per tile (two 64-channel column blocks)
 constexpr int FT_CB_BYTES = FT_K * 128;          // one column block of the window: 32 KiB
-constexpr int FT_STAGE_BYTES = 2 * FT_CB_BYTES;  // 64 KiB
-constexpr int FT_STAGES = 2;
+constexpr int FT_RING_CBS = 4;                   // window ring: 4 column blocks = 2 stages at N=128, 4 stages at N=64
 constexpr int FT_OUT_CB_BYTES = 128 * 128;       // staged output tile, one column block: 128 pixels x 128 B
 constexpr int FT_A_BYTES = 128 * FT_K * 2;       // 64 KiB Toeplitz
 constexpr int FT_EPI_WARPS = 8;
@@ -41,12 +40,12 @@ constexpr int FT_THREADS = 64 + 32 * FT_EPI_WARPS;
 
 struct __align__(1024) FirSmem {
     uint8_t a[FT_A_BYTES];
-    uint8_t b[FT_STAGES][FT_STAGE_BYTES];
+    uint8_t b[FT_RING_CBS * FT_CB_BYTES];
     uint8_t o[2 * FT_OUT_CB_BYTES];                // bf16 output tile in the TMA store layout (SWIZZLE_128B)
     float e_bias[FT_N];
     float e_next[FT_N];
     uint64_t a_full;
-    uint64_t full[FT_STAGES], empty[FT_STAGES];
+    uint64_t full[FT_RING_CBS], empty[FT_RING_CBS];
     uint64_t tmem_full[2], tmem_empty[2];
     uint32_t tmem_base;
 };
@@ -83,16 +82,16 @@ upfir_tc_kernel(const __grid_constant__ UpfirTcParams p, const __grid_constant__
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     // zero the pad rows (60..63 of every plane region) once: TMA never writes them
-    for (int i = threadIdx.x; i < FT_STAGES * 2 * 4 * 4 * 8; i += FT_THREADS) {
-        const int v = i & 7, row = (i >> 3) & 3, plane = (i >> 5) & 3, cb = (i >> 7) & 1, st = i >> 8;
-        *reinterpret_cast<uint4 *>(&sm.b[st][cb * FT_CB_BYTES + (plane * FT_PLANE_ROWS + 60 + row) * 128 + v * 16]) =
+    for (int i = threadIdx.x; i < FT_RING_CBS * 4 * 4 * 8; i += FT_THREADS) {
+        const int v = i & 7, row = (i >> 3) & 3, plane = (i >> 5) & 3, cb = i >> 7;
+        *reinterpret_cast<uint4 *>(&sm.b[cb * FT_CB_BYTES + (plane * FT_PLANE_ROWS + 60 + row) * 128 + v * 16]) =
             make_uint4(0, 0, 0, 0);
     }
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmK);
         tma_prefetch_desc(&tmT0);
         mbar_init(&sm.a_full, 1);
-        for (int i = 0; i < FT_STAGES; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.empty[i], 1); }
+        for (int i = 0; i < FT_RING_CBS; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&sm.tmem_full[i], 1); mbar_init(&sm.tmem_empty[i], FT_EPI_WARPS); }
         fence_barrier_init();
     }
@@ -110,6 +109,7 @@ upfir_tc_kernel(const __grid_constant__ UpfirTcParams p, const __grid_constant__
     (void)per;
     const int tile_hi = p.total_tiles;
     const int ncb = p.block_n / 64;                 // column blocks per tile (1 or 2)
+    const uint32_t nstages = FT_RING_CBS / ncb, stage_bytes = ncb * FT_CB_BYTES;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -130,13 +130,13 @@ upfir_tc_kernel(const __grid_constant__ UpfirTcParams p, const __grid_constant__
                 mbar_arrive_expect_tx(&sm.full[stage], (uint32_t)(ncb * 4 * FT_RA * FT_RB * 128));
                 for (int cb = 0; cb < ncb; ++cb) {
                     const int c = t.ct * p.block_n + cb * 64;
-                    uint8_t *dst = sm.b[stage] + cb * FT_CB_BYTES;
+                    uint8_t *dst = sm.b + stage * stage_bytes + cb * FT_CB_BYTES;
                     tma_load_4d(dst + 0 * FT_PLANE_ROWS * 128, &tmT0, &sm.full[stage], c, b0 - 1, a0 - 1, t.n);
                     tma_load_4d(dst + 1 * FT_PLANE_ROWS * 128, &tmT1, &sm.full[stage], c, b0 - 1, a0 - 1, t.n);
                     tma_load_4d(dst + 2 * FT_PLANE_ROWS * 128, &tmT2, &sm.full[stage], c, b0 - 1, a0 - 1, t.n);
                     tma_load_4d(dst + 3 * FT_PLANE_ROWS * 128, &tmT3, &sm.full[stage], c, b0 - 1, a0 - 1, t.n);
                 }
-                if (++stage == FT_STAGES) { stage = 0; phase ^= 1; }
+                if (++stage == nstages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
@@ -151,7 +151,7 @@ upfir_tc_kernel(const __grid_constant__ UpfirTcParams p, const __grid_constant__
                 mbar_wait(&sm.full[stage], phase);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * FT_N;
-                const uint32_t a_base = smem_u32(sm.a), b_base = smem_u32(sm.b[stage]);
+                const uint32_t a_base = smem_u32(sm.a), b_base = smem_u32(sm.b) + stage * stage_bytes;
 #pragma unroll
                 for (int kk = 0; kk < FT_K / 16; ++kk) {
                     const uint64_t adesc = make_smem_desc(a_base + (kk >> 2) * 16384 + (kk & 3) * 32, 128);
@@ -160,7 +160,7 @@ upfir_tc_kernel(const __grid_constant__ UpfirTcParams p, const __grid_constant__
                 }
                 umma_commit(&sm.empty[stage]);
                 umma_commit(&sm.tmem_full[acc]);
-                if (++stage == FT_STAGES) { stage = 0; phase ^= 1; }
+                if (++stage == nstages) { stage = 0; phase ^= 1; }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }

@@ -114,3 +114,40 @@ def test_engine_golden_1024(sg2, oracle, golden, cases):
     _check(img[:, :, 3::8, 5::8], ref, name)
     mom = golden["generator"][name + "/img_moments"]
     assert abs(img.double().mean().item() - mom[0]) < 2e-2 and abs(img.double().std().item() - mom[1]) < 2e-2
+
+
+def test_engine_auto_precision_with_bfloat16_parameters(sg2, oracle):
+    """`G.bfloat16()` (precision 'auto') routes through the engine and returns bfloat16 images."""
+    sd = oracle.init_state_dict(32, 512, 2)
+    G = sg2.Generator(32, 512, 2)
+    G.load_state_dict(sd)
+    G = G.to(DEV).bfloat16().eval()
+    assert G.precision == "auto"
+    z = oracle.named_randn("eng:bf16:z", (3, 512), 4)
+    with torch.no_grad():
+        img, _ = G([z.to(DEV).bfloat16()], randomize_noise=False)
+        ref, _ = oracle.generator_forward(sd, 32, [z], n_mlp=2, randomize_noise=False)
+    assert img.dtype == torch.bfloat16
+    rel = ((img.float().cpu() - ref).abs().max() / ref.abs().max()).item()
+    assert rel < 6e-2, rel            # bf16 master weights + bf16 mapping network on top of the engine's own rounding
+
+
+def test_engine_batch_growth_and_empty_batch(sg2, oracle):
+    G, sd = _gen(sg2, oracle, 16, 2)
+    with torch.no_grad():
+        a, _ = G([torch.randn(2, 512, device=DEV)], randomize_noise=False)
+        b, _ = G([torch.randn(19, 512, device=DEV)], randomize_noise=False)     # outgrows the plan -> re-plan
+        e, _ = G([torch.randn(0, 512, device=DEV)], randomize_noise=False)
+    assert a.shape == (2, 3, 16, 16) and b.shape == (19, 3, 16, 16) and e.shape == (0, 3, 16, 16)
+    assert torch.isfinite(b).all()
+
+
+def test_engine_rejects_what_it_cannot_run(sg2):
+    G = sg2.Generator(16, 512, 1, blur_kernel=[1, 2, 1]).to(DEV).eval()      # 3-tap blur: exact path only
+    G.precision = "bf16"
+    with pytest.raises(RuntimeError, match="4x4 taps"), torch.no_grad():
+        G([torch.randn(1, 512, device=DEV)])
+    G.precision = "exact"
+    with torch.no_grad():
+        img, _ = G([torch.randn(1, 512, device=DEV)], randomize_noise=False)
+    assert img.shape == (1, 3, 16, 16)
