@@ -246,7 +246,7 @@ def main():
         noise = [getattr(G.noises, f"noise_{i}") for i in range(G.num_layers)]
         for _ in range(reps):
             sg2._lib.check(eng.lib.sg2_synth_set_profile_events(eng.plan, arr, len(evs)))
-            eng.synthesize(lat, noise)
+            eng.synthesize(lat, noise, graph=False)
             torch.cuda.synchronize()
             for k in range(n_k):
                 acc[k] += evs[k].elapsed_time(evs[k + 1]) * 1e-3

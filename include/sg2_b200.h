@@ -51,6 +51,8 @@ int sg2_abi_version(void);
 const char *sg2_last_error(void);
 /* number of kernel launches issued through this library by the calling process (all threads) */
 int64_t sg2_launch_count(void);
+/* a CUDA-graph replay re-launches kernels without passing through this library: the host adds them */
+void sg2_note_launches(int64_t n);
 /* CPU-only self check of the multiply-shift division used by the vector kernels: 0 if n/d matches */
 int sg2_selftest_fastdiv(uint32_t d, uint32_t n);
 

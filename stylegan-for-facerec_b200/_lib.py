@@ -37,6 +37,7 @@ SIGNATURES = {
     "sg2_abi_version": (c_int, []),
     "sg2_last_error": (C.c_char_p, []),
     "sg2_launch_count": (c_i64, []),
+    "sg2_note_launches": (None, [c_i64]),
     "sg2_selftest_fastdiv": (c_int, [C.c_uint32, C.c_uint32]),
     "sg2_fused_bias_act": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_int,
                                    c_int, c_float, c_float, c_int, c_void_p]),

@@ -35,3 +35,4 @@ int sm_count() {
 extern "C" int sg2_abi_version(void) { return SG2_ABI_VERSION; }
 extern "C" const char *sg2_last_error(void) { return sg2::t_error; }
 extern "C" int64_t sg2_launch_count(void) { return sg2::g_launches.load(std::memory_order_relaxed); }
+extern "C" void sg2_note_launches(int64_t n) { sg2::g_launches.fetch_add(n, std::memory_order_relaxed); }

@@ -46,16 +46,24 @@ styles_kernel(StyleJobs jobs, const float *__restrict__ latent, int B, int n_lat
     }
     const float bv = __ldg(job.mod_b + ci);
     const float scale = rsqrtf((float)style_dim);            // EqualLinear scale, lr_mul = 1 (model.py:144)
-    for (int b = blockIdx.y; b < B; b += gridDim.y) {
-        const float *lr = latent + ((int64_t)b * n_latent + job.latent_index) * style_dim;
-        float acc = 0.f;
+    // 4 samples per pass with independent accumulators: 64 loads in flight per lane instead of a
+    // load -> reduce -> store chain per sample
+    for (int b0 = blockIdx.y * 4; b0 < B; b0 += gridDim.y * 4) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            const int idx = lane + 32 * k;
-            if (idx < style_dim) acc += __ldg(lr + idx) * wr[k];
+        for (int u = 0; u < 4; ++u) {
+            const int b = b0 + u < B ? b0 + u : B - 1;
+            const float *lr = latent + ((int64_t)b * n_latent + job.latent_index) * style_dim;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const int idx = lane + 32 * k;
+                if (idx < style_dim) acc[u] += __ldg(lr + idx) * wr[k];
+            }
         }
-        acc = warp_sum(acc);
-        if (lane == 0) job.out[(int64_t)b * job.cin + ci] = acc * scale + bv;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc[u] = warp_sum(acc[u]);
+        if (lane < 4 && b0 + lane < B)
+            job.out[(int64_t)(b0 + lane) * job.cin + ci] = (lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3]) * scale + bv;
     }
 }
 
@@ -258,7 +266,7 @@ int launch_pack_rgb_weight(float *out, const float *w, int n, float scale, cudaS
 }
 int launch_styles(const StyleJobs &jobs, int total_blocks, const float *latent, int B, int n_latent, int style_dim,
                   cudaStream_t st) {
-    dim3 grid(total_blocks, B < 8 ? B : 8);   // a warp keeps its weight row in registers for B/8 samples
+    dim3 grid(total_blocks, (unsigned)std::max(1, std::min(64, (B + 3) / 4)));   // one pass of 4 samples per warp: latency-bound, so maximise warps
     styles_kernel<<<grid, 256, 0, st>>>(jobs, latent, B, n_latent, style_dim);
     SG2_LAUNCH_CHECK();
     return SG2_OK;

@@ -9,6 +9,7 @@ workspace (a torch uint8 tensor), hands over pointers to the fp32 master paramet
 them into the engine's bf16 layouts whenever they change.
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -24,6 +25,10 @@ class SynthesisEngine:
         self.workspace = None
         self._packed_version = None
         self._keep = []
+        # CUDA graph per (batch, noise layout): one graph launch replaces the ~30 kernel launches of a
+        # forward.  SG2_B200_GRAPH=0 switches it off.
+        self.use_graph = os.environ.get("SG2_B200_GRAPH", "1") != "0"
+        self._graphs = {}
         if generator.input.input.is_cuda:
             self._ensure(max_batch)
 
@@ -82,6 +87,7 @@ class SynthesisEngine:
         if self.plan is not None:
             self.lib.sg2_synth_destroy(self.plan)
             self.plan = None
+        self._graphs = {}          # graphs hold the old plan's pointers
         rows, const, taps, dev = self._layer_table()
         if taps.shape != (4, 4):
             raise RuntimeError("sg2_b200 engine: blur kernel must have 4x4 taps (blur_kernel=[1,3,3,1])")
@@ -106,41 +112,102 @@ class SynthesisEngine:
         return buf.value.decode()
 
     # -- forward ----------------------------------------------------------------------------------
-    @torch.no_grad()
-    def synthesize(self, latent, noise):
-        """latent [B, n_latent, style_dim]; noise: list (num_layers) of [B or 1, 1, r, r] tensors or
-        None entries (fresh N(0,1) is drawn, model.py:283-285).  Returns the image [B,3,size,size]."""
-        G = self.G
-        _lib.require_cuda(latent, "latent")
-        B = latent.shape[0]
-        self._ensure(B)
-        lat = latent.detach().float().contiguous()
-        out_dtype = G.input.input.dtype
-        n_layers = G.num_layers
+    def _noise_args(self, B, noise, device, into=None):
+        """-> (pointer array, stride array, tensors kept alive).  `into`: static buffers to fill."""
+        n_layers = self.G.num_layers
         ptrs = (C.c_void_p * n_layers)()
         strides = (C.c_int64 * n_layers)()
         keep = []
         for i in range(n_layers):
             r = 2 ** ((i + 5) // 2)
             n = noise[i] if noise is not None else None
-            if n is None:
-                n = torch.randn(B, 1, r, r, device=lat.device, dtype=torch.float32)
-            n = n.detach().float().contiguous()
-            if n.numel() == B * r * r and B > 1:
-                strides[i] = r * r
+            if into is not None:
+                buf = into[i]
+                if n is None:
+                    buf.normal_()                                  # fresh N(0,1), model.py:283-285
+                else:
+                    buf.copy_(n.detach().reshape(buf.shape))
+                n = buf
+            else:
+                if n is None:
+                    n = torch.randn(B, 1, r, r, device=device, dtype=torch.float32)
+                n = n.detach().float().contiguous()
+            if n.numel() == B * r * r:
+                strides[i] = r * r if B > 1 else 0       # one map per sample
             elif n.numel() == r * r:
-                strides[i] = 0
-            elif n.numel() == B * r * r:
-                strides[i] = r * r
+                strides[i] = 0                           # one map broadcast over the batch (model.py:417-420)
             else:
                 raise RuntimeError(f"noise[{i}] of shape {tuple(n.shape)} does not match [{B} or 1, 1, {r}, {r}]")
             keep.append(n)
             ptrs[i] = n.data_ptr()
-        image = torch.empty(B, 3, G.size, G.size, device=lat.device, dtype=torch.float32)
+        return ptrs, strides, keep
+
+    def _noise_layout(self, B, noise):
+        """per layer: number of noise maps (B or 1) the caller supplies / wants"""
+        out = []
+        for i in range(self.G.num_layers):
+            r = 2 ** ((i + 5) // 2)
+            n = noise[i] if noise is not None else None
+            if n is None:
+                out.append(B)
+            elif n.numel() == B * r * r:
+                out.append(B)
+            elif n.numel() == r * r:
+                out.append(1)
+            else:
+                raise RuntimeError(f"noise[{i}] of shape {tuple(n.shape)} does not match [{B} or 1, 1, {r}, {r}]")
+        return tuple(out)
+
+    def _call(self, lat, B, ptrs, strides, image):
         with _lib.device_of(lat):
             _lib.check(self.lib.sg2_synth_forward(self.plan, self.workspace.data_ptr(), lat.data_ptr(), B, ptrs,
                                                   strides, image.data_ptr(), _lib.stream_of(lat)), "synth_forward")
-        return image if out_dtype == torch.float32 else image.to(out_dtype)
+
+    @torch.no_grad()
+    def synthesize(self, latent, noise, graph=None):
+        """latent [B, n_latent, style_dim]; noise: list (num_layers) of [B or 1, 1, r, r] tensors or
+        None entries (fresh N(0,1) is drawn, model.py:283-285).  Returns the image [B,3,size,size]."""
+        G = self.G
+        _lib.require_cuda(latent, "latent")
+        B = latent.shape[0]
+        self._ensure(B)
+        out_dtype = G.input.input.dtype
+        dev = latent.device
+        use_graph = self.use_graph if graph is None else graph
+        if B == 0:
+            return torch.empty(0, 3, G.size, G.size, device=dev, dtype=out_dtype)
+        if not use_graph or torch.cuda.is_current_stream_capturing():
+            lat = latent.detach().float().contiguous()
+            ptrs, strides, keep = self._noise_args(B, noise, dev)
+            image = torch.empty(B, 3, G.size, G.size, device=dev, dtype=torch.float32)
+            self._call(lat, B, ptrs, strides, image)
+            return image if out_dtype == torch.float32 else image.to(out_dtype)
+
+        layout = self._noise_layout(B, noise)
+        key = (B, layout, dev.index)
+        entry = self._graphs.get(key)
+        if entry is None:
+            s_lat = torch.empty(B, G.n_latent, G.style_dim, device=dev, dtype=torch.float32)
+            s_noise = [torch.empty(nb, 1, 2 ** ((i + 5) // 2), 2 ** ((i + 5) // 2), device=dev, dtype=torch.float32)
+                       for i, nb in enumerate(layout)]
+            s_img = torch.empty(B, 3, G.size, G.size, device=dev, dtype=torch.float32)
+            s_lat.copy_(latent)
+            ptrs, strides, _ = self._noise_args(B, noise, dev, into=s_noise)
+            n0 = _lib.launch_count()
+            self._call(s_lat, B, ptrs, strides, s_img)              # warm-up outside capture (lazy attributes, descriptors)
+            n_launch = _lib.launch_count() - n0
+            torch.cuda.current_stream(dev).synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._call(s_lat, B, ptrs, strides, s_img)
+            entry = (g, s_lat, s_noise, s_img, n_launch, (ptrs, strides))
+            self._graphs[key] = entry
+        g, s_lat, s_noise, s_img, n_launch, _ = entry
+        s_lat.copy_(latent)
+        self._noise_args(B, noise, dev, into=s_noise)
+        g.replay()
+        self.lib.sg2_note_launches(n_launch)                       # kernels launched by the graph replay
+        return s_img.clone() if out_dtype == torch.float32 else s_img.to(out_dtype)
 
     def __del__(self):
         try:
