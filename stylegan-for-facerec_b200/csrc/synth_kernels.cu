@@ -30,72 +30,101 @@ __global__ void pack_rgb_weight_kernel(float *__restrict__ out, const float *__r
 }
 
 // ---- styles of every layer in one launch: s_l[b,ci] = latent[b, idx_l, :] . mod_w_l[ci,:] * scale + mod_b_l[ci]
+// Block = 8 input channels of one layer (one per warp, weight row in registers) x ALL samples; the
+// latent rows are staged through shared memory 16 samples at a time so the dot products read
+// shared memory instead of chaining global loads (the kernel is pure latency otherwise).
+constexpr int STY_SB = 16;
 __global__ void __launch_bounds__(256)
 styles_kernel(StyleJobs jobs, const float *__restrict__ latent, int B, int n_latent, int style_dim) {
+    __shared__ float s_lat[STY_SB][512];                     // style_dim <= 512
     int j = 0;
     while (j + 1 < jobs.n && (int)blockIdx.x >= jobs.job[j + 1].block_begin) ++j;
     const StyleJob &job = jobs.job[j];
-    const int lane = threadIdx.x & 31;
-    const int ci = ((int)blockIdx.x - job.block_begin) * 8 + (threadIdx.x >> 5);
-    if (ci >= job.cin) return;
-    float wr[16];                                            // style_dim <= 512
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ci = ((int)blockIdx.x - job.block_begin) * 8 + warp;
+    const bool ci_ok = ci < job.cin;
+    float wr[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
         const int idx = lane + 32 * k;
-        wr[k] = idx < style_dim ? __ldg(job.mod_w + (int64_t)ci * style_dim + idx) : 0.f;
+        wr[k] = (ci_ok && idx < style_dim) ? __ldg(job.mod_w + (int64_t)ci * style_dim + idx) : 0.f;
     }
-    const float bv = __ldg(job.mod_b + ci);
+    const float bv = ci_ok ? __ldg(job.mod_b + ci) : 0.f;
     const float scale = rsqrtf((float)style_dim);            // EqualLinear scale, lr_mul = 1 (model.py:144)
-    // 4 samples per pass with independent accumulators: 64 loads in flight per lane instead of a
-    // load -> reduce -> store chain per sample
-    for (int b0 = blockIdx.y * 4; b0 < B; b0 += gridDim.y * 4) {
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int b = b0 + u < B ? b0 + u : B - 1;
-            const float *lr = latent + ((int64_t)b * n_latent + job.latent_index) * style_dim;
-#pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                const int idx = lane + 32 * k;
-                if (idx < style_dim) acc[u] += __ldg(lr + idx) * wr[k];
-            }
+    for (int b0 = 0; b0 < B; b0 += STY_SB) {
+        const int nb = min(STY_SB, B - b0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < nb * style_dim; i += 256) {
+            const int sb = i / style_dim, k = i - sb * style_dim;
+            s_lat[sb][k] = __ldg(latent + ((int64_t)(b0 + sb) * n_latent + job.latent_index) * style_dim + k);
         }
+        __syncthreads();
+        if (!ci_ok) continue;
+        for (int sb = 0; sb < nb; sb += 4) {                 // 4 independent reductions in flight
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int u = 0; u < 4; ++u) acc[u] = warp_sum(acc[u]);
-        if (lane < 4 && b0 + lane < B)
-            job.out[(int64_t)(b0 + lane) * job.cin + ci] = (lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3]) * scale + bv;
+            for (int u = 0; u < 4; ++u) {
+                const int r = sb + u < nb ? sb + u : nb - 1;
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const int idx = lane + 32 * k;
+                    if (idx < style_dim) acc[u] += s_lat[r][idx] * wr[k];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) acc[u] = warp_sum(acc[u]);
+            if (lane < 4 && sb + lane < nb)
+                job.out[(int64_t)(b0 + sb + lane) * job.cin + ci] =
+                    (lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3]) * scale + bv;
+        }
     }
 }
 
 // ---- demod of every styled conv in one launch: d[b,co] = rsqrt(sum_ci s^2 * wsq[ci,co] + 1e-8)
-// block = 256 output channels x 8 samples: each wsq element is loaded once for 8 samples
-constexpr int DEMOD_SB = 8;
+// block = 64 output channels x 4 slices of the input channels (reduced through shared memory) x
+// DEMOD_SB samples: each wsq element is loaded once for DEMOD_SB samples, 4x more loads in flight.
+constexpr int DEMOD_SB = 4, DEMOD_CO = 64;
 __global__ void __launch_bounds__(256)
 demod_kernel(DemodJobs jobs, int B) {
-    extern __shared__ float s_s2[];                          // [DEMOD_SB][cin]
+    extern __shared__ float s_dm[];                          // [DEMOD_SB][cin] s^2, then [4][DEMOD_SB][64] partials
     const DemodJob &job = jobs.job[blockIdx.z];
     const int b0 = blockIdx.y * DEMOD_SB;
-    if ((int)blockIdx.x * 256 >= job.cout) return;
+    if ((int)blockIdx.x * DEMOD_CO >= job.cout) return;
     const int nb = min(DEMOD_SB, B - b0);
+    float *s_s2 = s_dm, *s_part = s_dm + DEMOD_SB * job.cin;
     for (int i = threadIdx.x; i < DEMOD_SB * job.cin; i += 256) {
         const int sb = i / job.cin, ci = i - sb * job.cin;
         const float s = sb < nb ? job.style[(int64_t)(b0 + sb) * job.cin + ci] : 0.f;
         s_s2[i] = s * s;
     }
     __syncthreads();
-    const int co = blockIdx.x * 256 + threadIdx.x;
-    if (co >= job.cout) return;
+    const int col = threadIdx.x & 63, slice = threadIdx.x >> 6;
+    const int co = blockIdx.x * DEMOD_CO + col;
     float acc[DEMOD_SB];
 #pragma unroll
     for (int sb = 0; sb < DEMOD_SB; ++sb) acc[sb] = 0.f;
-    for (int ci = 0; ci < job.cin; ++ci) {
-        const float w = __ldg(job.wsq + (int64_t)ci * job.cout + co);
+    if (co < job.cout) {
+        const int per = (job.cin + 3) / 4, lo = slice * per, hi = min(job.cin, lo + per);
+#pragma unroll 8
+        for (int ci = lo; ci < hi; ++ci) {
+            const float w = __ldg(job.wsq + (int64_t)ci * job.cout + co);
 #pragma unroll
-        for (int sb = 0; sb < DEMOD_SB; ++sb) acc[sb] += s_s2[sb * job.cin + ci] * w;
+            for (int sb = 0; sb < DEMOD_SB; ++sb) acc[sb] += s_s2[sb * job.cin + ci] * w;
+        }
     }
 #pragma unroll
-    for (int sb = 0; sb < DEMOD_SB; ++sb)
-        if (sb < nb) job.demod[(int64_t)(b0 + sb) * job.cout + co] = rsqrtf(acc[sb] + 1e-8f);
+    for (int sb = 0; sb < DEMOD_SB; ++sb) s_part[(slice * DEMOD_SB + sb) * DEMOD_CO + col] = acc[sb];
+    __syncthreads();
+    if (threadIdx.x < DEMOD_SB * DEMOD_CO) {
+        const int sb = threadIdx.x / DEMOD_CO, c2 = threadIdx.x - sb * DEMOD_CO;
+        const int co2 = blockIdx.x * DEMOD_CO + c2;
+        if (sb < nb && co2 < job.cout) {
+            float t = 0.f;
+#pragma unroll
+            for (int sl = 0; sl < 4; ++sl) t += s_part[(sl * DEMOD_SB + sb) * DEMOD_CO + c2];
+            job.demod[(int64_t)(b0 + sb) * job.cout + co2] = rsqrtf(t + 1e-8f);
+        }
+    }
 }
 
 // ---- constant input, pre-modulated by conv1's style: X0[b,y,x,c] = const[c,y,x] * s[b,c]   (NHWC bf16)
@@ -219,35 +248,45 @@ __host__ __device__ __forceinline__ int fdiv2(int a) { return a >= 0 ? a / 2 : -
 
 __global__ void __launch_bounds__(256)
 rgb_combine_kernel(RgbParams p) {
-    const int64_t total = (int64_t)p.B * 3 * p.R * p.R;
-    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
-        const int X = (int)(i % p.R), Y = (int)((i / p.R) % p.R);
-        const int64_t plane = i / ((int64_t)p.R * p.R);      // n*3 + c
-        const int c = (int)(plane % 3);
-        float v = __ldg(p.bias + c);
-        for (int nt = 0; nt < p.n_parts; ++nt) v += __ldg(p.part + (int64_t)nt * total + i);
-        if (p.prev) {
-            // up=2, pad (2,1), 4x4 taps: same index math as upfirdn2d_kernel.cu:112-129
-            const int S = p.R / 2;
-            const int mid_y = Y + 1 - 2, mid_x = X + 1 - 2;
-            const int iy0 = fdiv2(mid_y), ix0 = fdiv2(mid_x);
-            const int ky0 = (iy0 + 1) * 2 - mid_y - 1, kx0 = (ix0 + 1) * 2 - mid_x - 1;
-            const float *sp = p.prev + plane * S * S;
-            float acc = 0.f;
-#pragma unroll
-            for (int a = 0; a < 2; ++a) {
-                const int iy = iy0 + a;
-                if (iy < 0 || iy >= S) continue;
-#pragma unroll
-                for (int b = 0; b < 2; ++b) {
-                    const int ix = ix0 + b;
-                    if (ix < 0 || ix >= S) continue;
-                    acc += __ldg(sp + iy * S + ix) * p.kf[(ky0 + 2 * a) * 4 + kx0 + 2 * b];
-                }
+    // grid.y = plane (n*3 + c); a thread owns 4 consecutive pixels of a row: float4 traffic, 32-bit index math
+    const int R = p.R, S = R / 2, quads = R / 4;
+    const int64_t plane_px = (int64_t)R * R, total = (int64_t)p.B * 3 * plane_px;
+    for (int plane = blockIdx.y; plane < p.B * 3; plane += gridDim.y) {
+        const float bias = __ldg(p.bias + plane % 3);
+        const float *sp = p.prev ? p.prev + (int64_t)plane * S * S : nullptr;
+        for (int q = blockIdx.x * 256 + threadIdx.x; q < R * quads; q += gridDim.x * 256) {
+            const int Y = q / quads, X0 = (q - Y * quads) * 4;
+            const int64_t i = (int64_t)plane * plane_px + (int64_t)Y * R + X0;
+            float4 v = make_float4(bias, bias, bias, bias);
+            for (int nt = 0; nt < p.n_parts; ++nt) {
+                const float4 t = __ldg(reinterpret_cast<const float4 *>(p.part + (int64_t)nt * total + i));
+                v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
             }
-            v += acc;
+            if (sp) {
+                // up=2, pad (2,1), 4x4 taps: same index math as upfirdn2d_kernel.cu:112-129
+                const int mid_y = Y - 1;
+                const int iy0 = fdiv2(mid_y), ky0 = (iy0 + 1) * 2 - mid_y - 1;
+                float up[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int mid_x = X0 + e - 1;
+                    const int ix0 = fdiv2(mid_x), kx0 = (ix0 + 1) * 2 - mid_x - 1;
+#pragma unroll
+                    for (int a2 = 0; a2 < 2; ++a2) {
+                        const int iy = iy0 + a2;
+                        if (iy < 0 || iy >= S) continue;
+#pragma unroll
+                        for (int b2 = 0; b2 < 2; ++b2) {
+                            const int ix = ix0 + b2;
+                            if (ix < 0 || ix >= S) continue;
+                            up[e] += __ldg(sp + iy * S + ix) * p.kf[(ky0 + 2 * a2) * 4 + kx0 + 2 * b2];
+                        }
+                    }
+                }
+                v.x += up[0]; v.y += up[1]; v.z += up[2]; v.w += up[3];
+            }
+            *reinterpret_cast<float4 *>(p.out + i) = v;
         }
-        p.out[i] = v;
     }
 }
 
@@ -266,14 +305,14 @@ int launch_pack_rgb_weight(float *out, const float *w, int n, float scale, cudaS
 }
 int launch_styles(const StyleJobs &jobs, int total_blocks, const float *latent, int B, int n_latent, int style_dim,
                   cudaStream_t st) {
-    dim3 grid(total_blocks, (unsigned)std::max(1, std::min(64, (B + 3) / 4)));   // one pass of 4 samples per warp: latency-bound, so maximise warps
+    dim3 grid(total_blocks);
     styles_kernel<<<grid, 256, 0, st>>>(jobs, latent, B, n_latent, style_dim);
     SG2_LAUNCH_CHECK();
     return SG2_OK;
 }
 int launch_demod(const DemodJobs &jobs, int max_cin, int max_cout, int B, cudaStream_t st) {
-    dim3 grid((max_cout + 255) / 256, (B + DEMOD_SB - 1) / DEMOD_SB, jobs.n);
-    demod_kernel<<<grid, 256, sizeof(float) * DEMOD_SB * max_cin, st>>>(jobs, B);
+    dim3 grid((max_cout + DEMOD_CO - 1) / DEMOD_CO, (B + DEMOD_SB - 1) / DEMOD_SB, jobs.n);
+    demod_kernel<<<grid, 256, sizeof(float) * (DEMOD_SB * max_cin + 4 * DEMOD_SB * DEMOD_CO), st>>>(jobs, B);
     SG2_LAUNCH_CHECK();
     return SG2_OK;
 }
@@ -297,9 +336,10 @@ int launch_upfir(const UpfirParams &p, int B, cudaStream_t st) {
     return SG2_OK;
 }
 int launch_rgb_combine(const RgbParams &p, int sms, cudaStream_t st) {
-    const int64_t total = (int64_t)p.B * 3 * p.R * p.R;
-    unsigned blocks = (unsigned)std::min<int64_t>(ceil_div64(total, 256), (int64_t)sms * 16);
-    rgb_combine_kernel<<<blocks, 256, 0, st>>>(p);
+    const int quads = p.R * (p.R / 4);
+    dim3 grid((unsigned)std::min(64, (quads + 255) / 256), (unsigned)std::min(p.B * 3, 65535));
+    (void)sms;
+    rgb_combine_kernel<<<grid, 256, 0, st>>>(p);
     SG2_LAUNCH_CHECK();
     return SG2_OK;
 }
