@@ -47,6 +47,7 @@ struct Layer {
     size_t wp = 0, wsq = 0, rgbw = 0, style = 0, demod = 0;
     // GEMM tiling (styled convs)
     int block_n = 0;
+    bool two_sm = false;  // run this layer on the cta_group::2 kernel (synth_gemm2.cu)
     GemmParams gp;        // static part, pointers filled per forward
     CUtensorMap tmA[kGemmMaxSub], tmB;
     CUtensorMap tmT[4];   // up-sampling layers: the 4 polyphase planes as the FIR kernel reads them
@@ -141,6 +142,10 @@ int plan_gemm(sg2_synth *S, Layer &L) {
     SG2_REQUIRE(best_n > 0, SG2_ERR_UNSUPPORTED, "engine: no BLOCK_N for Cout=%d", cout);
     g.block_n = L.block_n = best_n;
     g.n_tiles_n = cout / best_n;
+    // cta_group::2 (CTA pairs): SG2_GEMM_2SM=0 off, 1 = layers with BLOCK_N <= 128 (default), 2 = every layer
+    static const char *env2 = getenv("SG2_GEMM_2SM");
+    const int mode2 = env2 ? atoi(env2) : 0;
+    L.two_sm = best_n >= 32 && g.block_k == 64 && (mode2 == 2 || (mode2 == 1 && best_n <= 128));
     return SG2_OK;
 }
 
@@ -178,7 +183,7 @@ int encode_maps(sg2_synth *S, Layer &L, const __nv_bfloat16 *x, const __nv_bfloa
     {
         cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)L.p.cout, 9};
         cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)C * L.p.cout * 2};
-        cuuint32_t box[3] = {(cuuint32_t)L.gp.block_k, (cuuint32_t)L.block_n, 1};
+        cuuint32_t box[3] = {(cuuint32_t)L.gp.block_k, (cuuint32_t)(L.two_sm ? L.block_n / 2 : L.block_n), 1};
         cuuint32_t es[3] = {1, 1, 1};
         CUresult rc = enc(&L.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void *)wp, dims, strides, box, es,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -492,7 +497,7 @@ extern "C" int sg2_synth_forward(sg2_synth *S, void *workspace, const float *lat
                 g.rgb_style = (const float *)(ws + rgb->style);
                 g.rgb_part = part;
             }
-            rc = launch_modconv_gemm(g, L.tmA, L.tmB, S->sms, st);
+            rc = L.two_sm ? launch_modconv_gemm2(g, L.tmA, L.tmB, S->sms, st) : launch_modconv_gemm(g, L.tmA, L.tmB, S->sms, st);
             if (rc) return rc;
             if ((rc = rec(S, st, "gemm(conv)"))) return rc;
             if (rgb) {
@@ -514,7 +519,7 @@ extern "C" int sg2_synth_forward(sg2_synth *S, void *workspace, const float *lat
             const long long plane = (long long)B * (L.res_in + 1) * (L.res_in + 1) * L.p.cout;
             for (int s = 0; s < g.nsub; ++s) g.sub[s].out_off = plane * s;
             g.out = Tbuf;
-            rc = launch_modconv_gemm(g, L.tmA, L.tmB, S->sms, st);
+            rc = L.two_sm ? launch_modconv_gemm2(g, L.tmA, L.tmB, S->sms, st) : launch_modconv_gemm(g, L.tmA, L.tmB, S->sms, st);
             if (rc) return rc;
             if ((rc = rec(S, st, "gemm(up)"))) return rc;
             SG2_REQUIRE(next_conv, SG2_ERR_BAD_ARG, "engine: up-sampling conv without a consumer");

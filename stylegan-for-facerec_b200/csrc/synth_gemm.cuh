@@ -48,5 +48,8 @@ struct GemmParams {
 
 int launch_modconv_gemm(const GemmParams &p, const CUtensorMap *tmA /*[nsub]*/, const CUtensorMap &tmB,
                         int sm_count, cudaStream_t st);
+// cta_group::2 variant (synth_gemm2.cu): tmB must have box rows = block_n / 2
+int launch_modconv_gemm2(const GemmParams &p, const CUtensorMap *tmA /*[nsub]*/, const CUtensorMap &tmB,
+                         int sm_count, cudaStream_t st);
 
 }  // namespace sg2

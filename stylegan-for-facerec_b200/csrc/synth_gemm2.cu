@@ -1,3 +1,18 @@
+// synth_gemm2.cu -- the same implicit GEMM as synth_gemm.cu, issued as tcgen05.mma.cta_group::2:
+// a pair of CTAs (one thread-block cluster = one TPC) computes TWO pixel tiles against one weight
+// tile; each CTA keeps its own activation tile and only HALF of the weight tile in shared memory,
+// the leader CTA issues M=256 MMAs for both, each CTA's TMEM receives its own 128 rows.
+// Why: a single-CTA 128x128x16 UMMA reads 8 KB of operands per 64 clk = the whole 128 B/clk shared-
+// memory bandwidth of the SM (measured: 35 % tensor-pipe utilisation on the Cout = 128 layers vs
+// 71-75 % at N = 256); with cta_group::2 each SM reads A (4 KB) + half of B (2 KB).
+// Protocol (differences from synth_gemm.cu):
+//   * both producers issue their TMA loads with .cta_group::2 and signal the LEADER's full barrier
+//     (barrier address with the CTA-rank bit cleared); the leader arms it with the bytes of both CTAs;
+//   * the leader's MMA thread frees a stage / publishes an accumulator with a MULTICAST commit that
+//     arrives on the same barrier in both CTAs;
+//   * the epilogue warps of both CTAs arrive on the leader's tmem_empty barrier (count 16).
+// Everything else (tile geometry, epilogue math) is identical.  Original header follows.
+//
 // synth_gemm.cu -- ModulatedConv2d as ONE tcgen05/TMEM implicit-GEMM kernel fed by TMA (sm_100a).
 //
 // Replaces the ~12 PyTorch ops + cuDNN grouped conv of ModulatedConv2d.forward / StyledConv.forward
@@ -29,43 +44,48 @@ namespace sg2 {
 
 using namespace tc;
 
-constexpr int kEpiWarps = 8;
-constexpr int kGemmThreads = 64 + 32 * kEpiWarps;   // TMA warp + MMA warp + epilogue warps
-constexpr int kABytes = kBlockM * kBlockK * 2;          // 16 KiB
-constexpr int kBBytesMax = kMaxBlockN * kBlockK * 2;    // 32 KiB
-constexpr int kEpiCap = 512;                            // NB * BLOCK_N entries of per-sample epilogue params
-constexpr float kSlope = 0.2f;
+constexpr int kEpiWarps2 = 8;
+constexpr int kGemmThreads2 = 64 + 32 * kEpiWarps2;   // TMA warp + MMA warp + epilogue warps
+constexpr int kABytes2 = kBlockM * kBlockK * 2;          // 16 KiB
+constexpr int kBBytesMax2 = kMaxBlockN * kBlockK * 2;    // 32 KiB
+constexpr int kEpiCap2 = 512;                            // NB * BLOCK_N entries of per-sample epilogue params
+constexpr float kSlope2 = 0.2f;
 // The operand ring is one byte array cut into stages of (16 KiB A + BLOCK_N*128 B of B): narrow
 // BLOCK_N means short MMAs per stage, so more stages are needed to cover the TMA latency
 // (4 stages at N=256, 6 at N=128, 8 at N<=64).
-constexpr int kRingBytes = kStages * (kABytes + kBBytesMax);   // 192 KiB
-constexpr int kMaxStages = 8;
+constexpr int kRingBytes2 = kStages * (kABytes2 + kBBytesMax2);   // 192 KiB
+constexpr int kMaxStages2 = 8;
 
-struct __align__(1024) GemmSmem {
-    uint8_t ring[kRingBytes];
-    float e_demod[kEpiCap];
-    float e_next[kEpiCap];
-    float e_wrgb[3][kEpiCap];
+struct __align__(1024) Gemm2Smem {
+    uint8_t ring[kRingBytes2];
+    float e_demod[kEpiCap2];
+    float e_next[kEpiCap2];
+    float e_wrgb[3][kEpiCap2];
     float e_bias[kMaxBlockN];
-    uint64_t full[kMaxStages], empty[kMaxStages];
+    uint64_t full[kMaxStages2], empty[kMaxStages2];
     uint64_t tmem_full[2], tmem_empty[2];
     uint32_t tmem_base;
 };
 
-struct TileCoord {
-    int nt, x0, y0, b0;
+struct TileCoord2 {
+    int nt, x0, y0, b0, dummy;
 };
 
 // Tile order inside a sub-problem: x fastest, then y, then the N tile, then the sample block --
 // consecutive tiles of a CTA share (sample, N tile), so the staged epilogue parameters are reused.
-__device__ __forceinline__ TileCoord decode_tile(const GemmParams &p, const GemmSub &g, int local) {
-    TileCoord t;
-    const int bx = local % g.tiles_x;
-    local /= g.tiles_x;
-    const int by = local % g.tiles_y;
-    local /= g.tiles_y;
-    t.nt = local % p.n_tiles_n;
-    const int bb = local / p.n_tiles_n;
+__device__ __forceinline__ int pair_groups(const GemmSub &g) { return (g.tiles_x * g.tiles_y * g.tiles_b + 1) / 2; }
+__device__ __forceinline__ TileCoord2 decode_tile2(const GemmParams &p, const GemmSub &g, int local, int rank) {
+    TileCoord2 t;
+    const int pg = pair_groups(g), sxyb = g.tiles_x * g.tiles_y * g.tiles_b;
+    const int q = local % pg;
+    t.nt = local / pg;                 // N tile slowest: both CTAs of the pair always share it
+    int sp = 2 * q + rank;
+    t.dummy = sp >= sxyb;             // odd tile count: the surplus CTA recomputes the last tile, stores nothing
+    if (t.dummy) sp = sxyb - 1;
+    const int bx = sp % g.tiles_x;
+    sp /= g.tiles_x;
+    const int by = sp % g.tiles_y;
+    const int bb = sp / g.tiles_y;
     t.x0 = bx * g.TW;
     t.y0 = by * g.TH;
     t.b0 = bb * g.NB;
@@ -74,71 +94,75 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams &p, const Gemm
 
 // Every CTA takes one contiguous chunk of EVERY sub-problem (the polyphase sub-problems of the
 // transposed conv cost 4/2/2/1 taps per tile, so chunking them separately keeps CTAs balanced).
-struct TileRange { int lo, hi; };
-__device__ __forceinline__ TileRange cta_range(const GemmParams &p, const GemmSub &g) {
-    const int count = g.tiles_x * g.tiles_y * g.tiles_b * p.n_tiles_n;
-    const int per = (count + (int)gridDim.x - 1) / (int)gridDim.x;
-    TileRange r;
-    r.lo = min(count, (int)blockIdx.x * per);
+struct TileRange2 { int lo, hi; };
+__device__ __forceinline__ TileRange2 cta_range2(const GemmParams &p, const GemmSub &g) {
+    const int count = pair_groups(g) * p.n_tiles_n;          // work items of a CLUSTER
+    const int ncl = (int)gridDim.x / 2, cid = (int)blockIdx.x / 2;
+    const int per = (count + ncl - 1) / ncl;
+    TileRange2 r;
+    r.lo = min(count, cid * per);
     r.hi = min(count, r.lo + per);
     return r;
 }
 
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+__device__ __forceinline__ uint32_t pack_bf162(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t *>(&v);
 }
 
-__global__ void __launch_bounds__(kGemmThreads, 1)
-modconv_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ CUtensorMap tmA0,
+__global__ void __launch_bounds__(kGemmThreads2, 1)
+modconv_gemm2_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ CUtensorMap tmA0,
                     const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                     const __grid_constant__ CUtensorMap tmA3, const __grid_constant__ CUtensorMap tmB) {
     extern __shared__ uint8_t smem_raw[];
-    GemmSmem &sm = *reinterpret_cast<GemmSmem *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    Gemm2Smem &sm = *reinterpret_cast<Gemm2Smem *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rank = (int)cluster_ctarank();
+    const bool leader = rank == 0;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA0);
         tma_prefetch_desc(&tmB);
-        for (int i = 0; i < kMaxStages; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&sm.tmem_full[i], 1); mbar_init(&sm.tmem_empty[i], kEpiWarps); }
+        for (int i = 0; i < kMaxStages2; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.empty[i], 1); }
+        // tmem_empty lives in the leader: the epilogue warps of BOTH CTAs arrive on it
+        for (int i = 0; i < 2; ++i) { mbar_init(&sm.tmem_full[i], 1); mbar_init(&sm.tmem_empty[i], 2 * kEpiWarps2); }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(&sm.tmem_base, 512);
+    if (warp == 1) tmem_alloc_2sm(&sm.tmem_base, 512);
     tc_fence_before();
     __syncthreads();
+    cluster_sync();                              // peer barriers initialised, peer TMEM allocated
     tc_fence_after();
     const uint32_t tmem_base = sm.tmem_base;
     // K chunk per stage: 64 channels (128-byte rows, SWIZZLE_128B) or, for the 32-channel 1024^2 tail,
     // 32 channels (64-byte rows, SWIZZLE_64B)
     const uint32_t bk = (uint32_t)p.block_k, row_bytes = bk * 2;
     const uint32_t a_stage = kBlockM * row_bytes;
-    const uint32_t b_bytes = (uint32_t)p.block_n * row_bytes;
+    const uint32_t b_bytes = (uint32_t)(p.block_n / 2) * row_bytes;   // this CTA's half of the weight tile
     const uint32_t stage_bytes = a_stage + b_bytes;          // multiple of 1 KiB: swizzle atoms stay aligned
-    const uint32_t nstages = min((uint32_t)kMaxStages, (uint32_t)kRingBytes / stage_bytes);
+    const uint32_t nstages = min((uint32_t)kMaxStages2, (uint32_t)kRingBytes2 / stage_bytes);
 
     if (warp == 0) {
-        // ===================== TMA producer (warp-uniform control flow, one elected lane issues) =====
-        {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
             uint32_t stage = 0, phase = 0;
             for (int s = 0; s < p.nsub; ++s) {
                 const GemmSub &g = p.sub[s];
                 const CUtensorMap *tmA = s == 0 ? &tmA0 : (s == 1 ? &tmA1 : (s == 2 ? &tmA2 : &tmA3));
                 const uint32_t a_bytes = (uint32_t)(g.TH * g.TW * g.NB) * row_bytes;
-                const TileRange tr = cta_range(p, g);
+                const TileRange2 tr = cta_range2(p, g);
                 for (int local = tr.lo; local < tr.hi; ++local) {
-                    const TileCoord t = decode_tile(p, g, local);
+                    const TileCoord2 t = decode_tile2(p, g, local, rank);
                     for (int kc = 0; kc < p.kchunks; ++kc) {
                         for (int tap = 0; tap < g.ntaps; ++tap) {
                             mbar_wait(&sm.empty[stage], phase ^ 1);
-                            uint8_t *slot = sm.ring + stage * stage_bytes;
-                            const int ax = t.x0 + g.dx[tap], ay = t.y0 + g.dy[tap], wt = g.wtap[tap];
-                            if (elect_one()) {
-                                mbar_arrive_expect_tx(&sm.full[stage], a_bytes + b_bytes);
-                                tma_load_4d(slot, tmA, &sm.full[stage], kc * (int)bk, ax, ay, t.b0);
-                                tma_load_3d(slot + a_stage, &tmB, &sm.full[stage], kc * (int)bk, t.nt * p.block_n, wt);
-                            }
-                            __syncwarp();
+                            // the leader's barrier collects the bytes of both CTAs
+                            if (leader) mbar_arrive_expect_tx(&sm.full[stage], 2 * (a_bytes + b_bytes));
+                            const uint32_t slot = smem_u32(sm.ring) + stage * stage_bytes;
+                            tma_load_4d_2sm(slot, tmA, &sm.full[stage], kc * (int)bk, t.x0 + g.dx[tap],
+                                            t.y0 + g.dy[tap], t.b0);
+                            tma_load_3d_2sm(slot + a_stage, &tmB, &sm.full[stage], kc * (int)bk,
+                                            t.nt * p.block_n + rank * (p.block_n / 2), g.wtap[tap]);
                             if (++stage == nstages) { stage = 0; phase ^= 1; }
                         }
                     }
@@ -146,14 +170,14 @@ modconv_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant_
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer (warp-uniform control flow, one elected lane issues) =======
-        {
-            const uint32_t idesc = make_idesc_bf16(kBlockM, (uint32_t)p.block_n);
+        // ===================== MMA issuer =====================
+        if (lane == 0 && leader) {
+            const uint32_t idesc = make_idesc_bf16(2 * kBlockM, (uint32_t)p.block_n);
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
             for (int s = 0; s < p.nsub; ++s) {
                 const GemmSub &g = p.sub[s];
                 const int nstage = p.kchunks * g.ntaps;
-                const TileRange tr = cta_range(p, g);
+                const TileRange2 tr = cta_range2(p, g);
                 for (int local = tr.lo; local < tr.hi; ++local) {
                     mbar_wait(&sm.tmem_empty[acc], acc_phase ^ 1);
                     tc_fence_after();
@@ -164,21 +188,12 @@ modconv_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant_
                         const uint32_t slot = smem_u32(sm.ring) + stage * stage_bytes;
                         const uint64_t adesc = make_smem_desc(slot, row_bytes);
                         const uint64_t bdesc = make_smem_desc(slot + a_stage, row_bytes);
-                        if (elect_one()) {
-                            // advance 32 bytes (>>4 = 2) inside the swizzle row per K = 16 step
-                            umma_bf16(d_tmem, adesc, bdesc, idesc, k0 != 0);
-                            umma_bf16(d_tmem, adesc + 2, bdesc + 2, idesc, 1);
-                            if (bk == 64) {
-                                umma_bf16(d_tmem, adesc + 4, bdesc + 4, idesc, 1);
-                                umma_bf16(d_tmem, adesc + 6, bdesc + 6, idesc, 1);
-                            }
-                            umma_commit(&sm.empty[stage]);       // frees the smem slot when these MMAs retire
-                        }
-                        __syncwarp();
+                        for (uint32_t k = 0; k < bk / 16; ++k)   // advance 32 bytes (>>4 = 2) inside the swizzle row
+                            umma_bf16_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (k0 | k) != 0);
+                        umma_commit_2sm_mc(&sm.empty[stage], 3);    // frees the smem slot in BOTH CTAs when these MMAs retire
                         if (++stage == nstages) { stage = 0; phase ^= 1; }
                     }
-                    if (elect_one()) umma_commit(&sm.tmem_full[acc]);   // accumulator complete -> epilogue
-                    __syncwarp();
+                    umma_commit_2sm_mc(&sm.tmem_full[acc], 3);   // accumulators complete -> epilogue of both CTAs
                     if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 }
             }
@@ -202,12 +217,12 @@ modconv_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant_
             const int rem = m - nb * per;
             const int ty = rem / g.TW, tx = rem - ty * g.TW;
             const int pb = (nb < g.NB ? nb : 0) * N;    // row of the staged per-sample params
-            const TileRange tr = cta_range(p, g);
+            const TileRange2 tr = cta_range2(p, g);
             for (int local = tr.lo; local < tr.hi; ++local) {
-                const TileCoord t = decode_tile(p, g, local);
+                const TileCoord2 t = decode_tile2(p, g, local, rank);
                 const int n0 = t.nt * N;
                 const int y = t.y0 + ty, x = t.x0 + tx, b = t.b0 + nb;
-                const bool valid = nb < g.NB && y < g.PH && x < g.PW && b < p.B;
+                const bool valid = !t.dummy && nb < g.NB && y < g.PH && x < g.PW && b < p.B;
                 float nz = 0.f;
                 if (valid && p.mode == 0 && p.noise)     // issued early: overlaps the staging below
                     nz = __ldg(p.noise + (long long)b * p.noise_bstride + (long long)y * g.PW + x);
@@ -262,7 +277,7 @@ modconv_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant_
                             v[2] = fmaf(__uint_as_float(r[j + 2]), d4.z, nz) + b4.z;
                             v[3] = fmaf(__uint_as_float(r[j + 3]), d4.w, nz) + b4.w;
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], kSlope * v[e]);   // lrelu (gain folded downstream)
+                            for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], kSlope2 * v[e]);   // lrelu (gain folded downstream)
                             if (p.rgb_w) {
                                 const float4 w0 = *reinterpret_cast<const float4 *>(&sm.e_wrgb[0][pb + c0 + j]);
                                 const float4 w1 = *reinterpret_cast<const float4 *>(&sm.e_wrgb[1][pb + c0 + j]);
@@ -271,15 +286,15 @@ modconv_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant_
                                 rgb1 += v[0] * w1.x + v[1] * w1.y + v[2] * w1.z + v[3] * w1.w;
                                 rgb2 += v[0] * w2.x + v[1] * w2.y + v[2] * w2.z + v[3] * w2.w;
                             }
-                            packed[j / 2 + 0] = pack_bf16(v[0] * s4.x, v[1] * s4.y);
-                            packed[j / 2 + 1] = pack_bf16(v[2] * s4.z, v[3] * s4.w);
+                            packed[j / 2 + 0] = pack_bf162(v[0] * s4.x, v[1] * s4.y);
+                            packed[j / 2 + 1] = pack_bf162(v[2] * s4.z, v[3] * s4.w);
                         }
                     } else {
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
                             const float4 d4 = *reinterpret_cast<const float4 *>(&sm.e_demod[pb + c0 + j]);
-                            packed[j / 2 + 0] = pack_bf16(__uint_as_float(r[j + 0]) * d4.x, __uint_as_float(r[j + 1]) * d4.y);
-                            packed[j / 2 + 1] = pack_bf16(__uint_as_float(r[j + 2]) * d4.z, __uint_as_float(r[j + 3]) * d4.w);
+                            packed[j / 2 + 0] = pack_bf162(__uint_as_float(r[j + 0]) * d4.x, __uint_as_float(r[j + 1]) * d4.y);
+                            packed[j / 2 + 1] = pack_bf162(__uint_as_float(r[j + 2]) * d4.z, __uint_as_float(r[j + 3]) * d4.w);
                         }
                     }
                     if (orow) {
@@ -291,7 +306,7 @@ modconv_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant_
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&sm.tmem_empty[acc]);
+                if (lane == 0) mbar_arrive_leader(&sm.tmem_empty[acc]);   // the leader's MMA thread waits for both CTAs
                 if (valid && p.mode == 0 && p.rgb_w) {   // each column half writes its own partial plane
                     const long long plane = (long long)g.PH * g.PW;
                     float *rp = p.rgb_part + ((((long long)t.nt * 2 + half) * p.B + b) * 3) * plane + (long long)y * g.PW + x;
@@ -306,32 +321,50 @@ modconv_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant_
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, 512);
+    cluster_sync();                              // neither CTA exits (or frees TMEM) while the pair is still working
+    if (warp == 1) tmem_dealloc_2sm(tmem_base, 512);
 }
 
-int launch_modconv_gemm(const GemmParams &p, const CUtensorMap *tmA, const CUtensorMap &tmB, int sms,
+int launch_modconv_gemm2(const GemmParams &p, const CUtensorMap *tmA, const CUtensorMap &tmB, int sms,
                         cudaStream_t st) {
-    static_assert(sizeof(GemmSmem) + 1024 <= 227 * 1024, "GemmSmem exceeds the 227 KiB CTA limit");
+    static_assert(sizeof(Gemm2Smem) + 1024 <= 227 * 1024, "GemmSmem exceeds the 227 KiB CTA limit");
     static_assert(sizeof(GemmParams) + 5 * sizeof(CUtensorMap) <= 4000, "kernel parameter space");
-    const size_t smem = sizeof(GemmSmem) + 1024;
+    const size_t smem = sizeof(Gemm2Smem) + 1024;
     static std::atomic<int> configured{0};
     if (!configured.load(std::memory_order_acquire)) {
-        SG2_CUDA_OK(cudaFuncSetAttribute(modconv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SG2_CUDA_OK(cudaFuncSetAttribute(modconv_gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured.store(1, std::memory_order_release);
     }
-    SG2_REQUIRE(p.block_n % 16 == 0 && p.block_n >= 16 && p.block_n <= kMaxBlockN, SG2_ERR_BAD_ARG, "gemm: bad BLOCK_N %d", p.block_n);
+    SG2_REQUIRE(p.block_n % 32 == 0 && p.block_n >= 32 && p.block_n <= kMaxBlockN, SG2_ERR_BAD_ARG, "gemm2: bad BLOCK_N %d", p.block_n);
     SG2_REQUIRE((p.block_k == 64 || p.block_k == 32) && p.Cin % p.block_k == 0 && p.Cout % p.block_n == 0, SG2_ERR_UNSUPPORTED,
                 "gemm: Cin %d must be a multiple of BLOCK_K %d and Cout %d of BLOCK_N %d", p.Cin, p.block_k, p.Cout, p.block_n);
     for (int s = 0; s < p.nsub; ++s)
-        SG2_REQUIRE(p.sub[s].NB * p.block_n <= kEpiCap && p.sub[s].TH * p.sub[s].TW * p.sub[s].NB <= kBlockM,
+        SG2_REQUIRE(p.sub[s].NB * p.block_n <= kEpiCap2 && p.sub[s].TH * p.sub[s].TW * p.sub[s].NB <= kBlockM,
                     SG2_ERR_BAD_ARG, "gemm: tile of sub-problem %d too large", s);
-    const int grid = p.total_tiles < sms ? p.total_tiles : sms;
-    if (grid <= 0) return SG2_OK;
+    long most = 0;
+    for (int s2 = 0; s2 < p.nsub; ++s2) {
+        const GemmSub &g = p.sub[s2];
+        most = std::max(most, ((long)g.tiles_x * g.tiles_y * g.tiles_b + 1) / 2 * p.n_tiles_n);
+    }
+    const int n_clusters = (int)std::min<long>(most, sms / 2);
+    if (n_clusters <= 0) return SG2_OK;
     const CUtensorMap &a0 = tmA[0];
     const CUtensorMap &a1 = tmA[p.nsub > 1 ? 1 : 0];
     const CUtensorMap &a2 = tmA[p.nsub > 2 ? 2 : 0];
     const CUtensorMap &a3 = tmA[p.nsub > 3 ? 3 : 0];
-    modconv_gemm_kernel<<<grid, kGemmThreads, smem, st>>>(p, a0, a1, a2, a3, tmB);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * n_clusters);
+    cfg.blockDim = dim3(kGemmThreads2);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    SG2_CUDA_OK(cudaLaunchKernelEx(&cfg, modconv_gemm2_kernel, p, a0, a1, a2, a3, tmB));
     SG2_LAUNCH_CHECK();
     return SG2_OK;
 }
