@@ -142,10 +142,13 @@ int plan_gemm(sg2_synth *S, Layer &L) {
     SG2_REQUIRE(best_n > 0, SG2_ERR_UNSUPPORTED, "engine: no BLOCK_N for Cout=%d", cout);
     g.block_n = L.block_n = best_n;
     g.n_tiles_n = cout / best_n;
+    static const char *envk = getenv("SG2_GEMM_KPACK");
+    g.kpack = (g.block_k == 64 && g.kchunks % 2 == 0 && (envk ? atoi(envk) == 2 : best_n <= 128)) ? 2 : 1;
     // cta_group::2 (CTA pairs): SG2_GEMM_2SM=0 off, 1 = layers with BLOCK_N <= 128 (default), 2 = every layer
     static const char *env2 = getenv("SG2_GEMM_2SM");
     const int mode2 = env2 ? atoi(env2) : 0;
     L.two_sm = best_n >= 32 && g.block_k == 64 && (mode2 == 2 || (mode2 == 1 && best_n <= 128));
+    if (L.two_sm) g.kpack = 1;                    // the cta_group::2 kernel packs one K chunk per stage
     return SG2_OK;
 }
 

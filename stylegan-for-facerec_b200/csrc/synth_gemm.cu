@@ -114,7 +114,10 @@ modconv_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant_
     const uint32_t bk = (uint32_t)p.block_k, row_bytes = bk * 2;
     const uint32_t a_stage = kBlockM * row_bytes;
     const uint32_t b_bytes = (uint32_t)p.block_n * row_bytes;
-    const uint32_t stage_bytes = a_stage + b_bytes;          // multiple of 1 KiB: swizzle atoms stay aligned
+    // kpack K chunks per pipeline stage: narrow N means short MMAs, so two chunks (8 MMAs) per barrier
+    // round trip keep the tensor pipe fed while the issuing lane does its per-stage bookkeeping
+    const uint32_t kpk = (uint32_t)p.kpack;
+    const uint32_t stage_bytes = kpk * (a_stage + b_bytes);   // multiple of 1 KiB: swizzle atoms stay aligned
     const uint32_t nstages = min((uint32_t)kMaxStages, (uint32_t)kRingBytes / stage_bytes);
 
     if (warp == 0) {
@@ -128,15 +131,20 @@ modconv_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant_
                 const TileRange tr = cta_range(p, g);
                 for (int local = tr.lo; local < tr.hi; ++local) {
                     const TileCoord t = decode_tile(p, g, local);
-                    for (int kc = 0; kc < p.kchunks; ++kc) {
+                    for (int kc = 0; kc < p.kchunks; kc += (int)kpk) {
                         for (int tap = 0; tap < g.ntaps; ++tap) {
                             mbar_wait(&sm.empty[stage], phase ^ 1);
                             uint8_t *slot = sm.ring + stage * stage_bytes;
                             const int ax = t.x0 + g.dx[tap], ay = t.y0 + g.dy[tap], wt = g.wtap[tap];
                             if (elect_one()) {
-                                mbar_arrive_expect_tx(&sm.full[stage], a_bytes + b_bytes);
+                                mbar_arrive_expect_tx(&sm.full[stage], kpk * (a_bytes + b_bytes));
                                 tma_load_4d(slot, tmA, &sm.full[stage], kc * (int)bk, ax, ay, t.b0);
-                                tma_load_3d(slot + a_stage, &tmB, &sm.full[stage], kc * (int)bk, t.nt * p.block_n, wt);
+                                tma_load_3d(slot + kpk * a_stage, &tmB, &sm.full[stage], kc * (int)bk, t.nt * p.block_n, wt);
+                                if (kpk == 2) {
+                                    tma_load_4d(slot + a_stage, tmA, &sm.full[stage], (kc + 1) * (int)bk, ax, ay, t.b0);
+                                    tma_load_3d(slot + 2 * a_stage + b_bytes, &tmB, &sm.full[stage], (kc + 1) * (int)bk,
+                                                t.nt * p.block_n, wt);
+                                }
                             }
                             __syncwarp();
                             if (++stage == nstages) { stage = 0; phase ^= 1; }
@@ -152,7 +160,7 @@ modconv_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant_
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
             for (int s = 0; s < p.nsub; ++s) {
                 const GemmSub &g = p.sub[s];
-                const int nstage = p.kchunks * g.ntaps;
+                const int nstage = p.kchunks / (int)kpk * g.ntaps;
                 const TileRange tr = cta_range(p, g);
                 for (int local = tr.lo; local < tr.hi; ++local) {
                     mbar_wait(&sm.tmem_empty[acc], acc_phase ^ 1);
@@ -163,7 +171,7 @@ modconv_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant_
                         tc_fence_after();
                         const uint32_t slot = smem_u32(sm.ring) + stage * stage_bytes;
                         const uint64_t adesc = make_smem_desc(slot, row_bytes);
-                        const uint64_t bdesc = make_smem_desc(slot + a_stage, row_bytes);
+                        const uint64_t bdesc = make_smem_desc(slot + kpk * a_stage, row_bytes);
                         if (elect_one()) {
                             // advance 32 bytes (>>4 = 2) inside the swizzle row per K = 16 step
                             umma_bf16(d_tmem, adesc, bdesc, idesc, k0 != 0);
@@ -171,6 +179,13 @@ modconv_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant_
                             if (bk == 64) {
                                 umma_bf16(d_tmem, adesc + 4, bdesc + 4, idesc, 1);
                                 umma_bf16(d_tmem, adesc + 6, bdesc + 6, idesc, 1);
+                            }
+                            if (kpk == 2) {      // second K chunk of the stage (bk == 64 by construction)
+                                const uint64_t a2 = adesc + (a_stage >> 4), b2 = bdesc + (b_bytes >> 4);
+                                umma_bf16(d_tmem, a2, b2, idesc, 1);
+                                umma_bf16(d_tmem, a2 + 2, b2 + 2, idesc, 1);
+                                umma_bf16(d_tmem, a2 + 4, b2 + 4, idesc, 1);
+                                umma_bf16(d_tmem, a2 + 6, b2 + 6, idesc, 1);
                             }
                             umma_commit(&sm.empty[stage]);       // frees the smem slot when these MMAs retire
                         }
@@ -320,6 +335,7 @@ int launch_modconv_gemm(const GemmParams &p, const CUtensorMap *tmA, const CUten
         configured.store(1, std::memory_order_release);
     }
     SG2_REQUIRE(p.block_n % 16 == 0 && p.block_n >= 16 && p.block_n <= kMaxBlockN, SG2_ERR_BAD_ARG, "gemm: bad BLOCK_N %d", p.block_n);
+    SG2_REQUIRE(p.kpack == 1 || (p.kpack == 2 && p.block_k == 64 && p.kchunks % 2 == 0), SG2_ERR_BAD_ARG, "gemm: bad kpack %d", p.kpack);
     SG2_REQUIRE((p.block_k == 64 || p.block_k == 32) && p.Cin % p.block_k == 0 && p.Cout % p.block_n == 0, SG2_ERR_UNSUPPORTED,
                 "gemm: Cin %d must be a multiple of BLOCK_K %d and Cout %d of BLOCK_N %d", p.Cin, p.block_k, p.Cout, p.block_n);
     for (int s = 0; s < p.nsub; ++s)

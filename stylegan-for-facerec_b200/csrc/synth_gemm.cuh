@@ -31,7 +31,8 @@ struct GemmParams {
     GemmSub sub[kGemmMaxSub];
     int B, Cin, Cout;
     int block_n, n_tiles_n, total_tiles, kchunks;   // kchunks = Cin / block_k
-    int block_k;                    // channels per pipeline stage: 64 (SWIZZLE_128B rows) or 32 (SWIZZLE_64B)
+    int block_k;                    // channels per K chunk: 64 (SWIZZLE_128B rows) or 32 (SWIZZLE_64B)
+    int kpack;                      // K chunks per pipeline stage: 1, or 2 for narrow BLOCK_N
     // epilogue
     int mode;                       // 0: styled conv (noise, bias, lrelu, next-style, ToRGB); 1: plain scaled store
     const float *demod;             // [B, Cout]
