@@ -126,6 +126,7 @@ int plan_gemm(sg2_synth *S, Layer &L) {
     // BLOCK_N: as wide as possible while the launch still has >= 2 waves of tiles, and the staged
     // per-sample epilogue parameters fit (NB * BLOCK_N <= 512)
     int best_n = 0;
+    long best_tiles = 0;
     for (int bn : {256, 128, 64, 32, 16}) {
         if (cout % bn) continue;
         bool fits = true;
@@ -137,6 +138,7 @@ int plan_gemm(sg2_synth *S, Layer &L) {
         }
         if (!fits) continue;
         best_n = bn;
+        best_tiles = tiles;
         if (tiles >= 2L * S->sms || bn <= 64) break;
     }
     SG2_REQUIRE(best_n > 0, SG2_ERR_UNSUPPORTED, "engine: no BLOCK_N for Cout=%d", cout);
@@ -144,11 +146,16 @@ int plan_gemm(sg2_synth *S, Layer &L) {
     g.n_tiles_n = cout / best_n;
     static const char *envk = getenv("SG2_GEMM_KPACK");
     g.kpack = (g.block_k == 64 && g.kchunks % 2 == 0 && (envk ? atoi(envk) == 2 : best_n <= 128)) ? 2 : 1;
-    // cta_group::2 (CTA pairs): SG2_GEMM_2SM=0 off, 1 = layers with BLOCK_N <= 128 (default), 2 = every layer
+    // cta_group::2 (CTA pairs share the weight tile, synth_gemm2.cu).  SG2_GEMM_2SM=0 off, 2 = every layer,
+    // 1 / unset = where it measured faster on B200 (profiles/experiments/README.md): plain convs with at
+    // least a wave of tiles and BLOCK_N >= 128 or a deep K (-7..-11 %), up-sampling convs only at
+    // BLOCK_N = 256 (short-K tiles lose more to the pair hand-shake than they gain: the 64-channel
+    // 512^2 layer of the 1024^2 network is 23 % slower as a pair).
     static const char *env2 = getenv("SG2_GEMM_2SM");
-    const int mode2 = env2 ? atoi(env2) : 0;
-    L.two_sm = best_n >= 32 && g.block_k == 64 && (mode2 == 2 || (mode2 == 1 && best_n <= 128));
-    if (L.two_sm) g.kpack = 1;                    // the cta_group::2 kernel packs one K chunk per stage
+    const int mode2 = env2 ? atoi(env2) : 1;
+    const bool auto2 = up ? (best_n > 128 && best_tiles >= 4L * S->sms)
+                          : (best_tiles >= (long)S->sms && (best_n >= 128 || cin >= 256));
+    L.two_sm = best_n >= 32 && g.block_k == 64 && (mode2 == 2 || (mode2 == 1 && auto2));
     return SG2_OK;
 }
 

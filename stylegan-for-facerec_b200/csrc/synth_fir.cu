@@ -113,53 +113,66 @@ upfir_tc_kernel(const __grid_constant__ UpfirTcParams p, const __grid_constant__
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0 && tile_lo < tile_hi) {
+        // warp-uniform loop, one elected lane issues (no divergent single-thread region)
+        if (tile_lo < tile_hi) {
             // Toeplitz matrix: 4 K-atoms of [128 rows][64 k] each
-            mbar_arrive_expect_tx(&sm.a_full, FT_A_BYTES);
-            for (int ka = 0; ka < 4; ++ka)
-                asm volatile(
-                    "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                    ::"r"(smem_u32(sm.a + ka * 16384)), "l"(reinterpret_cast<uint64_t>(&tmK)), "r"(smem_u32(&sm.a_full)),
-                    "r"(ka * 64), "r"(0)
-                    : "memory");
+            if (elect_one()) {
+                mbar_arrive_expect_tx(&sm.a_full, FT_A_BYTES);
+                for (int ka = 0; ka < 4; ++ka)
+                    asm volatile(
+                        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                        ::"r"(smem_u32(sm.a + ka * 16384)), "l"(reinterpret_cast<uint64_t>(&tmK)), "r"(smem_u32(&sm.a_full)),
+                        "r"(ka * 64), "r"(0)
+                        : "memory");
+            }
+            __syncwarp();
             uint32_t stage = 0, phase = 0;
             for (int tile = tile_lo; tile < tile_hi; tile += tile_step) {
                 const FirTile t = fir_decode(p, tile);
                 const int a0 = t.y0 / 2, b0 = t.x0 / 2;     // first cell of the tile
                 mbar_wait(&sm.empty[stage], phase ^ 1);
-                mbar_arrive_expect_tx(&sm.full[stage], (uint32_t)(ncb * 4 * FT_RA * FT_RB * 128));
-                for (int cb = 0; cb < ncb; ++cb) {
-                    const int c = t.ct * p.block_n + cb * 64;
-                    uint8_t *dst = sm.b + stage * stage_bytes + cb * FT_CB_BYTES;
-                    tma_load_4d(dst + 0 * FT_PLANE_ROWS * 128, &tmT0, &sm.full[stage], c, b0 - 1, a0 - 1, t.n);
-                    tma_load_4d(dst + 1 * FT_PLANE_ROWS * 128, &tmT1, &sm.full[stage], c, b0 - 1, a0 - 1, t.n);
-                    tma_load_4d(dst + 2 * FT_PLANE_ROWS * 128, &tmT2, &sm.full[stage], c, b0 - 1, a0 - 1, t.n);
-                    tma_load_4d(dst + 3 * FT_PLANE_ROWS * 128, &tmT3, &sm.full[stage], c, b0 - 1, a0 - 1, t.n);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(&sm.full[stage], (uint32_t)(ncb * 4 * FT_RA * FT_RB * 128));
+                    for (int cb = 0; cb < ncb; ++cb) {
+                        const int c = t.ct * p.block_n + cb * 64;
+                        uint8_t *dst = sm.b + stage * stage_bytes + cb * FT_CB_BYTES;
+                        tma_load_4d(dst + 0 * FT_PLANE_ROWS * 128, &tmT0, &sm.full[stage], c, b0 - 1, a0 - 1, t.n);
+                        tma_load_4d(dst + 1 * FT_PLANE_ROWS * 128, &tmT1, &sm.full[stage], c, b0 - 1, a0 - 1, t.n);
+                        tma_load_4d(dst + 2 * FT_PLANE_ROWS * 128, &tmT2, &sm.full[stage], c, b0 - 1, a0 - 1, t.n);
+                        tma_load_4d(dst + 3 * FT_PLANE_ROWS * 128, &tmT3, &sm.full[stage], c, b0 - 1, a0 - 1, t.n);
+                    }
                 }
+                __syncwarp();
                 if (++stage == nstages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0 && tile_lo < tile_hi) {
+        if (tile_lo < tile_hi) {
             // kind::f16, D=f32, A=B=bf16, A K-major, B MN-major (bit 16), M=128, N=block_n
             const uint32_t idesc = make_idesc_bf16(128, (uint32_t)p.block_n) | (1u << 16);
             mbar_wait(&sm.a_full, 0);
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+            const uint32_t a_base = smem_u32(sm.a);
             for (int tile = tile_lo; tile < tile_hi; tile += tile_step) {
                 mbar_wait(&sm.tmem_empty[acc], acc_phase ^ 1);
                 mbar_wait(&sm.full[stage], phase);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * FT_N;
-                const uint32_t a_base = smem_u32(sm.a), b_base = smem_u32(sm.b) + stage * stage_bytes;
+                const uint32_t b_base = smem_u32(sm.b) + stage * stage_bytes;
+                const uint64_t adesc0 = make_smem_desc(a_base, 128);
+                const uint64_t bdesc0 = make_smem_desc_mn(b_base, FT_CB_BYTES);
+                if (elect_one()) {
 #pragma unroll
-                for (int kk = 0; kk < FT_K / 16; ++kk) {
-                    const uint64_t adesc = make_smem_desc(a_base + (kk >> 2) * 16384 + (kk & 3) * 32, 128);
-                    const uint64_t bdesc = make_smem_desc_mn(b_base + kk * 16 * 128, FT_CB_BYTES);
-                    umma_bf16(d_tmem, adesc, bdesc, idesc, kk != 0);
+                    for (int kk = 0; kk < FT_K / 16; ++kk) {
+                        const uint64_t adesc = adesc0 + (uint64_t)(((kk >> 2) * 16384 + (kk & 3) * 32) >> 4);
+                        const uint64_t bdesc = bdesc0 + (uint64_t)((kk * 16 * 128) >> 4);
+                        umma_bf16(d_tmem, adesc, bdesc, idesc, kk != 0);
+                    }
+                    umma_commit(&sm.empty[stage]);
+                    umma_commit(&sm.tmem_full[acc]);
                 }
-                umma_commit(&sm.empty[stage]);
-                umma_commit(&sm.tmem_full[acc]);
+                __syncwarp();
                 if (++stage == nstages) { stage = 0; phase ^= 1; }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }

@@ -139,44 +139,51 @@ modconv_gemm2_kernel(const __grid_constant__ GemmParams p, const __grid_constant
     const uint32_t bk = (uint32_t)p.block_k, row_bytes = bk * 2;
     const uint32_t a_stage = kBlockM * row_bytes;
     const uint32_t b_bytes = (uint32_t)(p.block_n / 2) * row_bytes;   // this CTA's half of the weight tile
-    const uint32_t stage_bytes = a_stage + b_bytes;          // multiple of 1 KiB: swizzle atoms stay aligned
+    const uint32_t kpk = (uint32_t)p.kpack;                  // K chunks per pipeline stage (see synth_gemm.cu)
+    const uint32_t stage_bytes = kpk * (a_stage + b_bytes);  // multiple of 1 KiB: swizzle atoms stay aligned
     const uint32_t nstages = min((uint32_t)kMaxStages2, (uint32_t)kRingBytes2 / stage_bytes);
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
-            uint32_t stage = 0, phase = 0;
-            for (int s = 0; s < p.nsub; ++s) {
-                const GemmSub &g = p.sub[s];
-                const CUtensorMap *tmA = s == 0 ? &tmA0 : (s == 1 ? &tmA1 : (s == 2 ? &tmA2 : &tmA3));
-                const uint32_t a_bytes = (uint32_t)(g.TH * g.TW * g.NB) * row_bytes;
-                const TileRange2 tr = cta_range2(p, g);
-                for (int local = tr.lo; local < tr.hi; ++local) {
-                    const TileCoord2 t = decode_tile2(p, g, local, rank);
-                    for (int kc = 0; kc < p.kchunks; ++kc) {
-                        for (int tap = 0; tap < g.ntaps; ++tap) {
-                            mbar_wait(&sm.empty[stage], phase ^ 1);
+        // ===================== TMA producer (warp-uniform control flow, one elected lane issues) =====
+        uint32_t stage = 0, phase = 0;
+        for (int s = 0; s < p.nsub; ++s) {
+            const GemmSub &g = p.sub[s];
+            const CUtensorMap *tmA = s == 0 ? &tmA0 : (s == 1 ? &tmA1 : (s == 2 ? &tmA2 : &tmA3));
+            const uint32_t a_bytes = (uint32_t)(g.TH * g.TW * g.NB) * row_bytes;
+            const TileRange2 tr = cta_range2(p, g);
+            for (int local = tr.lo; local < tr.hi; ++local) {
+                const TileCoord2 t = decode_tile2(p, g, local, rank);
+                const int wrow = t.nt * p.block_n + rank * (p.block_n / 2);
+                for (int kc = 0; kc < p.kchunks; kc += (int)kpk) {
+                    for (int tap = 0; tap < g.ntaps; ++tap) {
+                        mbar_wait(&sm.empty[stage], phase ^ 1);
+                        const uint32_t slot = smem_u32(sm.ring) + stage * stage_bytes;
+                        const int ax = t.x0 + g.dx[tap], ay = t.y0 + g.dy[tap], wt = g.wtap[tap];
+                        if (elect_one()) {
                             // the leader's barrier collects the bytes of both CTAs
-                            if (leader) mbar_arrive_expect_tx(&sm.full[stage], 2 * (a_bytes + b_bytes));
-                            const uint32_t slot = smem_u32(sm.ring) + stage * stage_bytes;
-                            tma_load_4d_2sm(slot, tmA, &sm.full[stage], kc * (int)bk, t.x0 + g.dx[tap],
-                                            t.y0 + g.dy[tap], t.b0);
-                            tma_load_3d_2sm(slot + a_stage, &tmB, &sm.full[stage], kc * (int)bk,
-                                            t.nt * p.block_n + rank * (p.block_n / 2), g.wtap[tap]);
-                            if (++stage == nstages) { stage = 0; phase ^= 1; }
+                            if (leader) mbar_arrive_expect_tx(&sm.full[stage], 2 * kpk * (a_bytes + b_bytes));
+                            tma_load_4d_2sm(slot, tmA, &sm.full[stage], kc * (int)bk, ax, ay, t.b0);
+                            tma_load_3d_2sm(slot + kpk * a_stage, &tmB, &sm.full[stage], kc * (int)bk, wrow, wt);
+                            if (kpk == 2) {
+                                tma_load_4d_2sm(slot + a_stage, tmA, &sm.full[stage], (kc + 1) * (int)bk, ax, ay, t.b0);
+                                tma_load_3d_2sm(slot + 2 * a_stage + b_bytes, &tmB, &sm.full[stage], (kc + 1) * (int)bk,
+                                                wrow, wt);
+                            }
                         }
+                        __syncwarp();
+                        if (++stage == nstages) { stage = 0; phase ^= 1; }
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0 && leader) {
+        // ===================== MMA issuer: the leader CTA's warp, one elected lane issues ============
+        if (leader) {
             const uint32_t idesc = make_idesc_bf16(2 * kBlockM, (uint32_t)p.block_n);
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
             for (int s = 0; s < p.nsub; ++s) {
                 const GemmSub &g = p.sub[s];
-                const int nstage = p.kchunks * g.ntaps;
+                const int nstage = p.kchunks / (int)kpk * g.ntaps;
                 const TileRange2 tr = cta_range2(p, g);
                 for (int local = tr.lo; local < tr.hi; ++local) {
                     mbar_wait(&sm.tmem_empty[acc], acc_phase ^ 1);
@@ -187,13 +194,29 @@ modconv_gemm2_kernel(const __grid_constant__ GemmParams p, const __grid_constant
                         tc_fence_after();
                         const uint32_t slot = smem_u32(sm.ring) + stage * stage_bytes;
                         const uint64_t adesc = make_smem_desc(slot, row_bytes);
-                        const uint64_t bdesc = make_smem_desc(slot + a_stage, row_bytes);
-                        for (uint32_t k = 0; k < bk / 16; ++k)   // advance 32 bytes (>>4 = 2) inside the swizzle row
-                            umma_bf16_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (k0 | k) != 0);
-                        umma_commit_2sm_mc(&sm.empty[stage], 3);    // frees the smem slot in BOTH CTAs when these MMAs retire
+                        const uint64_t bdesc = make_smem_desc(slot + kpk * a_stage, row_bytes);
+                        if (elect_one()) {
+                            // advance 32 bytes (>>4 = 2) inside the swizzle row per K = 16 step
+                            umma_bf16_2sm(d_tmem, adesc, bdesc, idesc, k0 != 0);
+                            umma_bf16_2sm(d_tmem, adesc + 2, bdesc + 2, idesc, 1);
+                            if (bk == 64) {
+                                umma_bf16_2sm(d_tmem, adesc + 4, bdesc + 4, idesc, 1);
+                                umma_bf16_2sm(d_tmem, adesc + 6, bdesc + 6, idesc, 1);
+                            }
+                            if (kpk == 2) {
+                                const uint64_t a2 = adesc + (a_stage >> 4), b2 = bdesc + (b_bytes >> 4);
+                                umma_bf16_2sm(d_tmem, a2, b2, idesc, 1);
+                                umma_bf16_2sm(d_tmem, a2 + 2, b2 + 2, idesc, 1);
+                                umma_bf16_2sm(d_tmem, a2 + 4, b2 + 4, idesc, 1);
+                                umma_bf16_2sm(d_tmem, a2 + 6, b2 + 6, idesc, 1);
+                            }
+                            umma_commit_2sm_mc(&sm.empty[stage], 3);    // frees the smem slot in BOTH CTAs
+                        }
+                        __syncwarp();
                         if (++stage == nstages) { stage = 0; phase ^= 1; }
                     }
-                    umma_commit_2sm_mc(&sm.tmem_full[acc], 3);   // accumulators complete -> epilogue of both CTAs
+                    if (elect_one()) umma_commit_2sm_mc(&sm.tmem_full[acc], 3);   // -> epilogue of both CTAs
+                    __syncwarp();
                     if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 }
             }
