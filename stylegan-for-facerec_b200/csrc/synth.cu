@@ -156,6 +156,65 @@ int plan_gemm(sg2_synth *S, Layer &L) {
     const bool auto2 = up ? (best_n > 128 && best_tiles >= 4L * S->sms)
                           : (best_tiles >= (long)S->sms && (best_n >= 128 || cin >= 256));
     L.two_sm = best_n >= 32 && g.block_k == 64 && (mode2 == 2 || (mode2 == 1 && auto2));
+
+    // Resident weights (the narrow, high-resolution tail of the 512^2 / 1024^2 networks): when all 9*Cin*Cout
+    // bf16 weights fit in shared memory next to >= 2 activation stages, load them once per CTA and stream
+    // only activations -- one slab per distinct dx with the dy halo inside it, so a 3x3 tile costs 3 TMA
+    // loads and ONE barrier round trip per K chunk instead of 9.  SG2_GEMM_RESIDENT=0 switches it off.
+    static const char *envr = getenv("SG2_GEMM_RESIDENT");
+    bool nb1 = true;
+    for (int s = 0; s < g.nsub; ++s) nb1 = nb1 && g.sub[s].NB == 1;
+    if ((!envr || atoi(envr) != 0) && g.n_tiles_n == 1 && nb1 && r >= 16 && cin % 32 == 0) {
+        const int resb = 18 * cin * best_n;
+        int pick_bk = 0, pick_stage = 0;
+        for (int bk : {64, 32}) {
+            if (cin % bk) continue;
+            int stage = 0;
+            for (int s = 0; s < g.nsub; ++s) {
+                const GemmSub &q = g.sub[s];
+                int dxs[3], ndx = 0, dymin = 0, dymax = 0;
+                for (int t = 0; t < q.ntaps; ++t) {
+                    bool seen = false;
+                    for (int i = 0; i < ndx; ++i) seen = seen || dxs[i] == q.dx[t];
+                    if (!seen) dxs[ndx++] = q.dx[t];
+                    dymin = std::min(dymin, q.dy[t]); dymax = std::max(dymax, q.dy[t]);
+                }
+                stage = std::max(stage, ndx * (16 + dymax - dymin) * 8 * bk * 2);
+            }
+            stage = (stage + 1023) & ~1023;
+            const int nst = (kGemmRingBytes - resb) / stage;
+            if (resb < kGemmRingBytes && (nst >= 3 || (nst >= 2 && bk == 32))) { pick_bk = bk; pick_stage = stage; break; }
+        }
+        if (pick_bk) {
+            g.resident = 1; g.resb_bytes = resb; g.stage_bytes = pick_stage;
+            g.block_k = pick_bk; g.kchunks = cin / pick_bk; g.kpack = 1;
+            L.two_sm = false;
+            for (int s = 0; s < g.nsub; ++s) {
+                GemmSub &q = g.sub[s];
+                q.TH = 16; q.TW = 8; q.NB = 1;
+                int dymin = 0, dymax = 0;
+                q.nslab = 0;
+                for (int t = 0; t < q.ntaps; ++t) {
+                    bool seen = false;
+                    for (int i = 0; i < q.nslab; ++i) seen = seen || q.slab_dx[i] == q.dx[t];
+                    if (!seen) q.slab_dx[q.nslab++] = q.dx[t];
+                    dymin = std::min(dymin, q.dy[t]); dymax = std::max(dymax, q.dy[t]);
+                }
+                q.slab_dy0 = dymin;
+                q.slab_rows = q.TH + dymax - dymin;
+                const int row_bytes = pick_bk * 2, slab_bytes = q.slab_rows * q.TW * row_bytes;
+                for (int t = 0; t < q.ntaps; ++t) {
+                    int sl = 0;
+                    while (q.slab_dx[sl] != q.dx[t]) ++sl;
+                    q.tap_aoff[t] = sl * slab_bytes + (q.dy[t] - dymin) * q.TW * row_bytes;
+                }
+            }
+        }
+    }
+    static const char *enva = getenv("SG2_GEMM_EPI_ALT");
+    bool small = best_n <= 64;
+    for (int s = 0; s < g.nsub; ++s) small = small && g.sub[s].NB * best_n <= 256;
+    g.epi_alt = (!L.two_sm && small && (!enva || atoi(enva) != 0)) ? 1 : 0;
     return SG2_OK;
 }
 
@@ -182,7 +241,8 @@ int encode_maps(sg2_synth *S, Layer &L, const __nv_bfloat16 *x, const __nv_bfloa
         const GemmSub &q = L.gp.sub[s];
         cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)r, (cuuint64_t)r, (cuuint64_t)B};
         cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)r * C * 2, (cuuint64_t)r * r * C * 2};
-        cuuint32_t box[4] = {(cuuint32_t)L.gp.block_k, (cuuint32_t)q.TW, (cuuint32_t)q.TH, (cuuint32_t)q.NB};
+        cuuint32_t box[4] = {(cuuint32_t)L.gp.block_k, (cuuint32_t)q.TW, (cuuint32_t)(L.gp.resident ? q.slab_rows : q.TH),
+                             (cuuint32_t)q.NB};
         cuuint32_t es[4] = {1, 1, 1, 1};
         CUresult rc = enc(&L.tmA[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void *)x, dims, strides, box, es,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -515,7 +575,7 @@ extern "C" int sg2_synth_forward(sg2_synth *S, void *workspace, const float *lat
                 const bool last = next_conv == nullptr;
                 const int dst = rgb_cur == 0 ? 1 : 0;
                 rp.out = last ? image : rgbbuf[dst];
-                rp.part = part; rp.n_parts = 2 * g.n_tiles_n; rp.bias = rgb->p.act_bias;
+                rp.part = part; rp.n_parts = (g.epi_alt ? 1 : 2) * g.n_tiles_n; rp.bias = rgb->p.act_bias;
                 rp.prev = rgb_cur >= 0 ? rgbbuf[rgb_cur] : nullptr;
                 rp.B = B; rp.R = L.res_out;
                 memcpy(rp.kf, S->kf, sizeof(rp.kf));

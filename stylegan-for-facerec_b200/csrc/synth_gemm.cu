@@ -38,7 +38,7 @@ constexpr float kSlope = 0.2f;
 // The operand ring is one byte array cut into stages of (16 KiB A + BLOCK_N*128 B of B): narrow
 // BLOCK_N means short MMAs per stage, so more stages are needed to cover the TMA latency
 // (4 stages at N=256, 6 at N=128, 8 at N<=64).
-constexpr int kRingBytes = kStages * (kABytes + kBBytesMax);   // 192 KiB
+constexpr int kRingBytes = kGemmRingBytes;
 constexpr int kMaxStages = 8;
 
 struct __align__(1024) GemmSmem {
@@ -48,7 +48,8 @@ struct __align__(1024) GemmSmem {
     float e_wrgb[3][kEpiCap];
     float e_bias[kMaxBlockN];
     uint64_t full[kMaxStages], empty[kMaxStages];
-    uint64_t tmem_full[2], tmem_empty[2];
+    uint64_t tmem_full[4], tmem_empty[4];   // 4 accumulators of 128 columns at BLOCK_N <= 128, else 2 of 256
+    uint64_t b_full;              // resident-weights mode: the weight tensor has landed
     uint32_t tmem_base;
 };
 
@@ -72,6 +73,18 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams &p, const Gemm
     return t;
 }
 
+// A CTA walks consecutive tiles, so only the first one is decoded with divisions.
+__device__ __forceinline__ void next_tile(const GemmParams &p, const GemmSub &g, TileCoord &t) {
+    t.x0 += g.TW;
+    if (t.x0 >= g.tiles_x * g.TW) {
+        t.x0 = 0; t.y0 += g.TH;
+        if (t.y0 >= g.tiles_y * g.TH) {
+            t.y0 = 0;
+            if (++t.nt == p.n_tiles_n) { t.nt = 0; t.b0 += g.NB; }
+        }
+    }
+}
+
 // Every CTA takes one contiguous chunk of EVERY sub-problem (the polyphase sub-problems of the
 // transposed conv cost 4/2/2/1 taps per tile, so chunking them separately keeps CTAs balanced).
 struct TileRange { int lo, hi; };
@@ -88,6 +101,60 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t *>(&v);
 }
+// 16-byte shared-memory load through the shared window (the staged tables are reached through plain
+// pointers, which would otherwise compile to generic loads)
+__device__ __forceinline__ float4 lds4(const float *p) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(p)));
+    return v;
+}
+
+// staged epilogue parameters of this thread's sample (shared memory), indexed by tile column
+struct EpiTables { const float *demod, *next, *w0, *w1, *w2, *bias; };
+
+// W accumulator columns [c0, c0 + W) of one pixel row: TMEM -> registers -> epilogue math -> bf16 -> global.
+template <int W>
+__device__ __forceinline__ void epi_cols(const GemmParams &p, const EpiTables &e, uint32_t taddr, int c0, float nz,
+                                         __nv_bfloat16 *orow, float &rgb0, float &rgb1, float &rgb2) {
+    uint32_t r[W];
+    tmem_ld_cols(taddr, r);
+    tmem_ld_wait();
+    uint32_t packed[W / 2];
+    if (p.mode == 0) {
+#pragma unroll
+        for (int j = 0; j < W; j += 4) {
+            const float4 d4 = lds4(e.demod + c0 + j), b4 = lds4(e.bias + c0 + j), s4 = lds4(e.next + c0 + j);
+            float v[4];
+            v[0] = fmaf(__uint_as_float(r[j + 0]), d4.x, nz) + b4.x;
+            v[1] = fmaf(__uint_as_float(r[j + 1]), d4.y, nz) + b4.y;
+            v[2] = fmaf(__uint_as_float(r[j + 2]), d4.z, nz) + b4.z;
+            v[3] = fmaf(__uint_as_float(r[j + 3]), d4.w, nz) + b4.w;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] = fmaxf(v[k], kSlope * v[k]);   // lrelu (gain folded downstream)
+            if (p.rgb_w) {
+                const float4 w0 = lds4(e.w0 + c0 + j), w1 = lds4(e.w1 + c0 + j), w2 = lds4(e.w2 + c0 + j);
+                rgb0 += v[0] * w0.x + v[1] * w0.y + v[2] * w0.z + v[3] * w0.w;
+                rgb1 += v[0] * w1.x + v[1] * w1.y + v[2] * w1.z + v[3] * w1.w;
+                rgb2 += v[0] * w2.x + v[1] * w2.y + v[2] * w2.z + v[3] * w2.w;
+            }
+            packed[j / 2 + 0] = pack_bf16(v[0] * s4.x, v[1] * s4.y);
+            packed[j / 2 + 1] = pack_bf16(v[2] * s4.z, v[3] * s4.w);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < W; j += 4) {
+            const float4 d4 = lds4(e.demod + c0 + j);
+            packed[j / 2 + 0] = pack_bf16(__uint_as_float(r[j + 0]) * d4.x, __uint_as_float(r[j + 1]) * d4.y);
+            packed[j / 2 + 1] = pack_bf16(__uint_as_float(r[j + 2]) * d4.z, __uint_as_float(r[j + 3]) * d4.w);
+        }
+    }
+    if (orow) {
+        uint4 *dst = reinterpret_cast<uint4 *>(orow + c0);
+#pragma unroll
+        for (int v4 = 0; v4 < W / 8; ++v4)
+            dst[v4] = make_uint4(packed[4 * v4], packed[4 * v4 + 1], packed[4 * v4 + 2], packed[4 * v4 + 3]);
+    }
+}
 
 __global__ void __launch_bounds__(kGemmThreads, 1)
 modconv_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ CUtensorMap tmA0,
@@ -101,7 +168,8 @@ modconv_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant_
         tma_prefetch_desc(&tmA0);
         tma_prefetch_desc(&tmB);
         for (int i = 0; i < kMaxStages; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&sm.tmem_full[i], 1); mbar_init(&sm.tmem_empty[i], kEpiWarps); }
+        for (int i = 0; i < 4; ++i) { mbar_init(&sm.tmem_full[i], 1); mbar_init(&sm.tmem_empty[i], p.epi_alt ? kEpiWarps / 2 : kEpiWarps); }
+        mbar_init(&sm.b_full, 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(&sm.tmem_base, 512);
@@ -117,20 +185,60 @@ modconv_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant_
     // kpack K chunks per pipeline stage: narrow N means short MMAs, so two chunks (8 MMAs) per barrier
     // round trip keep the tensor pipe fed while the issuing lane does its per-stage bookkeeping
     const uint32_t kpk = (uint32_t)p.kpack;
-    const uint32_t stage_bytes = kpk * (a_stage + b_bytes);   // multiple of 1 KiB: swizzle atoms stay aligned
-    const uint32_t nstages = min((uint32_t)kMaxStages, (uint32_t)kRingBytes / stage_bytes);
+    const bool resident = p.resident != 0;
+    // accumulator ring in TMEM: short-K tiles (polyphase sub-problems, the narrow tail) need the MMA warp
+    // to run several tiles ahead of the epilogue
+    const uint32_t nacc = p.block_n <= 128 ? 4u : 2u, acc_cols = 512u / nacc;
+    // multiple of 1 KiB: swizzle atoms stay aligned
+    const uint32_t stage_bytes = resident ? (uint32_t)p.stage_bytes : kpk * (a_stage + b_bytes);
+    const uint32_t ring_off = resident ? (uint32_t)p.resb_bytes : 0u;      // resident weights sit in front of the ring
+    const uint32_t nstages = min((uint32_t)kMaxStages, ((uint32_t)kRingBytes - ring_off) / stage_bytes);
 
     if (warp == 0) {
         // ===================== TMA producer (warp-uniform control flow, one elected lane issues) =====
-        {
+        if (resident) {
+            // weights once: [tap][K chunk] tiles of BLOCK_N rows, K-major swizzled like the streamed ones
+            if (elect_one()) {
+                mbar_arrive_expect_tx(&sm.b_full, (uint32_t)p.resb_bytes);
+                for (int tap = 0; tap < kGemmMaxTaps; ++tap)
+                    for (int kc = 0; kc < p.kchunks; ++kc)
+                        tma_load_3d(sm.ring + (uint32_t)(tap * p.kchunks + kc) * b_bytes, &tmB, &sm.b_full, kc * (int)bk, 0, tap);
+            }
+            __syncwarp();
+            uint32_t stage = 0, phase = 0;
+            for (int s = 0; s < p.nsub; ++s) {
+                const GemmSub &g = p.sub[s];
+                const CUtensorMap *tmA = s == 0 ? &tmA0 : (s == 1 ? &tmA1 : (s == 2 ? &tmA2 : &tmA3));
+                const uint32_t slab_bytes = (uint32_t)(g.slab_rows * g.TW) * row_bytes;
+                const int nslab = g.nslab, sdx[3] = {g.slab_dx[0], g.slab_dx[1], g.slab_dx[2]};
+                const TileRange tr = cta_range(p, g);
+                TileCoord t = decode_tile(p, g, tr.lo);
+                for (int local = tr.lo; local < tr.hi; ++local, next_tile(p, g, t)) {
+                    const int ay = t.y0 + g.slab_dy0;
+                    for (int kc = 0; kc < p.kchunks; ++kc) {
+                        mbar_wait(&sm.empty[stage], phase ^ 1);
+                        uint8_t *slot = sm.ring + ring_off + stage * stage_bytes;
+                        if (elect_one()) {
+                            mbar_arrive_expect_tx(&sm.full[stage], (uint32_t)g.nslab * slab_bytes);
+#pragma unroll
+                            for (int sl = 0; sl < 3; ++sl)
+                                if (sl < nslab)
+                                    tma_load_4d(slot + sl * slab_bytes, tmA, &sm.full[stage], kc * (int)bk, t.x0 + sdx[sl], ay, t.b0);
+                        }
+                        __syncwarp();
+                        if (++stage == nstages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        } else {
             uint32_t stage = 0, phase = 0;
             for (int s = 0; s < p.nsub; ++s) {
                 const GemmSub &g = p.sub[s];
                 const CUtensorMap *tmA = s == 0 ? &tmA0 : (s == 1 ? &tmA1 : (s == 2 ? &tmA2 : &tmA3));
                 const uint32_t a_bytes = (uint32_t)(g.TH * g.TW * g.NB) * row_bytes;
                 const TileRange tr = cta_range(p, g);
-                for (int local = tr.lo; local < tr.hi; ++local) {
-                    const TileCoord t = decode_tile(p, g, local);
+                TileCoord t = decode_tile(p, g, tr.lo);
+                for (int local = tr.lo; local < tr.hi; ++local, next_tile(p, g, t)) {
                     for (int kc = 0; kc < p.kchunks; kc += (int)kpk) {
                         for (int tap = 0; tap < g.ntaps; ++tap) {
                             mbar_wait(&sm.empty[stage], phase ^ 1);
@@ -155,7 +263,59 @@ modconv_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant_
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (warp-uniform control flow, one elected lane issues) =======
-        {
+        if (resident) {
+            const uint32_t idesc = make_idesc_bf16(kBlockM, (uint32_t)p.block_n);
+            uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+            const uint32_t ring = smem_u32(sm.ring);
+            const uint32_t ksteps = bk / 16;
+            mbar_wait(&sm.b_full, 0);
+            for (int s = 0; s < p.nsub; ++s) {
+                const GemmSub &g = p.sub[s];
+                const TileRange tr = cta_range(p, g);
+                // per-tap descriptor offsets (16-byte units), warp-uniform and hoisted out of the tile loop so
+                // the elected lane issues the whole stage's MMAs back to back
+                uint32_t aoff[kGemmMaxTaps], boff[kGemmMaxTaps];
+#pragma unroll
+                for (int tap = 0; tap < kGemmMaxTaps; ++tap) {
+                    const bool on = tap < g.ntaps;
+                    aoff[tap] = on ? (uint32_t)g.tap_aoff[tap] >> 4 : 0u;
+                    boff[tap] = on ? ((uint32_t)(g.wtap[tap] * p.kchunks) * b_bytes) >> 4 : 0u;
+                }
+                const int ntaps = g.ntaps;
+                for (int local = tr.lo; local < tr.hi; ++local) {
+                    mbar_wait(&sm.tmem_empty[acc], acc_phase ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + acc * acc_cols;
+                    for (int kc = 0; kc < p.kchunks; ++kc) {
+                        mbar_wait(&sm.full[stage], phase);
+                        tc_fence_after();
+                        const uint64_t a0 = make_smem_desc(ring + ring_off + stage * stage_bytes, row_bytes);
+                        const uint64_t b0 = make_smem_desc(ring + (uint32_t)kc * b_bytes, row_bytes);
+                        if (elect_one()) {
+#pragma unroll
+                            for (int tap = 0; tap < kGemmMaxTaps; ++tap) {
+                                if (tap < ntaps) {
+                                    const uint64_t adesc = a0 + aoff[tap], bdesc = b0 + boff[tap];
+                                    // 32 bytes (>>4 = 2) inside the swizzle row per K = 16 step
+                                    umma_bf16(d_tmem, adesc, bdesc, idesc, (kc | tap) != 0);
+                                    umma_bf16(d_tmem, adesc + 2, bdesc + 2, idesc, 1);
+                                    if (ksteps == 4) {
+                                        umma_bf16(d_tmem, adesc + 4, bdesc + 4, idesc, 1);
+                                        umma_bf16(d_tmem, adesc + 6, bdesc + 6, idesc, 1);
+                                    }
+                                }
+                            }
+                            umma_commit(&sm.empty[stage]);
+                        }
+                        __syncwarp();
+                        if (++stage == nstages) { stage = 0; phase ^= 1; }
+                    }
+                    if (elect_one()) umma_commit(&sm.tmem_full[acc]);
+                    __syncwarp();
+                    if (++acc == nacc) { acc = 0; acc_phase ^= 1; }
+                }
+            }
+        } else {
             const uint32_t idesc = make_idesc_bf16(kBlockM, (uint32_t)p.block_n);
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
             for (int s = 0; s < p.nsub; ++s) {
@@ -165,7 +325,7 @@ modconv_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant_
                 for (int local = tr.lo; local < tr.hi; ++local) {
                     mbar_wait(&sm.tmem_empty[acc], acc_phase ^ 1);
                     tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + acc * kMaxBlockN;
+                    const uint32_t d_tmem = tmem_base + acc * acc_cols;
                     for (int k0 = 0; k0 < nstage; ++k0) {
                         mbar_wait(&sm.full[stage], phase);
                         tc_fence_after();
@@ -194,21 +354,31 @@ modconv_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant_
                     }
                     if (elect_one()) umma_commit(&sm.tmem_full[acc]);   // accumulator complete -> epilogue
                     __syncwarp();
-                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                    if (++acc == nacc) { acc = 0; acc_phase ^= 1; }
                 }
             }
         }
     } else {
         // ===================== epilogue: 8 warps, two per TMEM lane quarter =====================
-        // warp (2 + 4h + i) may access TMEM lanes 32*((2+i)&3) ..; the two warps of a quarter split the
-        // accumulator columns in alternating 32-column chunks (h = 0: even chunks, h = 1: odd chunks).
+        // warp (2 + 4h + i) may access TMEM lanes 32*((2+i)&3) ..  Two schedules:
+        //  * column split (default): the two warps of a quarter alternate 32-column chunks of every tile;
+        //  * tile split (p.epi_alt, narrow BLOCK_N): warps 2-5 take the even tiles and warps 6-9 the odd ones, so
+        //    the per-pixel work (coordinates, noise, addresses, ToRGB store) is done once per pixel.
         const int q = warp & 3;
-        const int half = (warp - 2) >> 2;
+        const int grp = (warp - 2) >> 2;
+        const bool alt = p.epi_alt != 0;
+        const int half = alt ? 0 : grp;
         const int m = q * 32 + lane;                 // accumulator row = pixel of the tile
-        const int et = threadIdx.x - 64;             // 0..255 within the epilogue group
+        const int et = alt ? ((threadIdx.x - 64) & 127) : threadIdx.x - 64;   // thread index inside the staging group
+        const int ethreads = alt ? 128 : 256, bar_id = alt ? 1 + grp : 1, step = alt ? 2 : 1;
+        // staged per-(sample, channel) parameters: one copy per group in tile-split mode
+        const int po = alt ? grp * (kEpiCap / 2) : 0;
+        float *e_demod = sm.e_demod + po, *e_next = sm.e_next + po, *e_bias = sm.e_bias + (alt ? grp * (kMaxBlockN / 2) : 0);
+        float *e_w0 = sm.e_wrgb[0] + po, *e_w1 = sm.e_wrgb[1] + po, *e_w2 = sm.e_wrgb[2] + po;
         const float nw = (p.mode == 0 && p.noise) ? __ldg(p.noise_weight) : 0.f;
+        const bool has_noise = p.mode == 0 && p.noise != nullptr;
         const int N = p.block_n;
-        uint32_t acc = 0, acc_phase = 0;
+        uint32_t it0 = 0;                            // tiles of the earlier sub-problems (= the MMA warp's count)
         int staged_key = -1;
         for (int s = 0; s < p.nsub; ++s) {
             const GemmSub &g = p.sub[s];
@@ -217,41 +387,55 @@ modconv_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant_
             const int rem = m - nb * per;
             const int ty = rem / g.TW, tx = rem - ty * g.TW;
             const int pb = (nb < g.NB ? nb : 0) * N;    // row of the staged per-sample params
+            const int PH = g.PH, PW = g.PW, NB = g.NB;
+            const long long plane = (long long)PH * PW;
             const TileRange tr = cta_range(p, g);
-            for (int local = tr.lo; local < tr.hi; ++local) {
-                const TileCoord t = decode_tile(p, g, local);
+            int local = tr.lo + (alt ? (int)((grp - it0) & 1u) : 0);
+            TileCoord t = decode_tile(p, g, local);
+            auto noise_at = [&](const TileCoord &tc) -> float {
+                const int y = tc.y0 + ty, x = tc.x0 + tx, b = tc.b0 + nb;
+                if (has_noise && nb < NB && y < PH && x < PW && b < p.B)
+                    return __ldg(p.noise + (long long)b * p.noise_bstride + (long long)y * PW + x);
+                return 0.f;
+            };
+            float nz_cur = local < tr.hi ? noise_at(t) : 0.f;
+            for (; local < tr.hi; local += step) {
+                // the noise of this group's NEXT tile is fetched now and consumed one iteration later
+                TileCoord tn = t;
+                next_tile(p, g, tn);
+                if (alt) next_tile(p, g, tn);
+                const float nz_nxt = local + step < tr.hi ? noise_at(tn) : 0.f;
+                const uint32_t it = it0 + (uint32_t)(local - tr.lo);
+                const uint32_t acc = it & (nacc - 1), acc_phase = (it / nacc) & 1u;
                 const int n0 = t.nt * N;
                 const int y = t.y0 + ty, x = t.x0 + tx, b = t.b0 + nb;
-                const bool valid = nb < g.NB && y < g.PH && x < g.PW && b < p.B;
-                float nz = 0.f;
-                if (valid && p.mode == 0 && p.noise)     // issued early: overlaps the staging below
-                    nz = __ldg(p.noise + (long long)b * p.noise_bstride + (long long)y * g.PW + x);
+                const bool valid = nb < NB && y < PH && x < PW && b < p.B;
                 // ---- stage the per-(sample, channel) epilogue parameters when they change ----
-                const int key = (t.b0 * kMaxBlockN + t.nt) * 16 + g.NB;
+                const int key = (t.b0 * kMaxBlockN + t.nt) * 16 + NB;
                 if (key != staged_key) {
-                    asm volatile("bar.sync 1, 256;" ::: "memory");
-                    for (int i = et; i < g.NB * N; i += 256) {
+                    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(ethreads) : "memory");
+                    for (int i = et; i < NB * N; i += ethreads) {
                         const int sb = i / N, col = i - sb * N;
                         const int bb = t.b0 + sb < p.B ? t.b0 + sb : p.B - 1;
                         const long long o = (long long)bb * p.Cout + n0 + col;
-                        sm.e_demod[i] = __ldg(p.demod + o);
+                        e_demod[i] = __ldg(p.demod + o);
                         if (p.mode == 0) {
                             // lrelu gain sqrt(2) (fused_bias_act_kernel.cu:47) folded into both consumers
-                            sm.e_next[i] = p.next_style ? 1.41421356237f * __ldg(p.next_style + o) : 0.f;
+                            e_next[i] = p.next_style ? 1.41421356237f * __ldg(p.next_style + o) : 0.f;
                             if (p.rgb_w) {
                                 const float rs = 1.41421356237f * __ldg(p.rgb_style + o);
-#pragma unroll
-                                for (int c = 0; c < 3; ++c)
-                                    sm.e_wrgb[c][i] = rs * __ldg(p.rgb_w + (long long)c * p.Cout + n0 + col);
+                                e_w0[i] = rs * __ldg(p.rgb_w + n0 + col);
+                                e_w1[i] = rs * __ldg(p.rgb_w + (long long)p.Cout + n0 + col);
+                                e_w2[i] = rs * __ldg(p.rgb_w + 2LL * p.Cout + n0 + col);
                             }
                         }
                     }
                     if (p.mode == 0)
-                        for (int i = et; i < N; i += 256) sm.e_bias[i] = __ldg(p.bias + n0 + i);
-                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                        for (int i = et; i < N; i += ethreads) e_bias[i] = __ldg(p.bias + n0 + i);
+                    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(ethreads) : "memory");
                     staged_key = key;
                 }
-                nz *= nw;
+                const float nz = nz_cur * nw;
                 __nv_bfloat16 *orow = nullptr;
                 if (valid && p.out)
                     orow = p.out + g.out_off + (((long long)b * g.out_H + y) * g.out_W + x) * p.Cout + n0;
@@ -259,63 +443,30 @@ modconv_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant_
                 mbar_wait(&sm.tmem_full[acc], acc_phase);
                 tc_fence_after();
                 float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
-                const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kMaxBlockN;
-                for (int c0 = 32 * half; c0 < N; c0 += 64) {
-                    uint32_t r[32];
-                    tmem_ld32(t_row + c0, r);
-                    tmem_ld_wait();
-                    uint32_t packed[16];
-                    if (p.mode == 0) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 d4 = *reinterpret_cast<const float4 *>(&sm.e_demod[pb + c0 + j]);
-                            const float4 b4 = *reinterpret_cast<const float4 *>(&sm.e_bias[c0 + j]);
-                            const float4 s4 = *reinterpret_cast<const float4 *>(&sm.e_next[pb + c0 + j]);
-                            float v[4];
-                            v[0] = fmaf(__uint_as_float(r[j + 0]), d4.x, nz) + b4.x;
-                            v[1] = fmaf(__uint_as_float(r[j + 1]), d4.y, nz) + b4.y;
-                            v[2] = fmaf(__uint_as_float(r[j + 2]), d4.z, nz) + b4.z;
-                            v[3] = fmaf(__uint_as_float(r[j + 3]), d4.w, nz) + b4.w;
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], kSlope * v[e]);   // lrelu (gain folded downstream)
-                            if (p.rgb_w) {
-                                const float4 w0 = *reinterpret_cast<const float4 *>(&sm.e_wrgb[0][pb + c0 + j]);
-                                const float4 w1 = *reinterpret_cast<const float4 *>(&sm.e_wrgb[1][pb + c0 + j]);
-                                const float4 w2 = *reinterpret_cast<const float4 *>(&sm.e_wrgb[2][pb + c0 + j]);
-                                rgb0 += v[0] * w0.x + v[1] * w0.y + v[2] * w0.z + v[3] * w0.w;
-                                rgb1 += v[0] * w1.x + v[1] * w1.y + v[2] * w1.z + v[3] * w1.w;
-                                rgb2 += v[0] * w2.x + v[1] * w2.y + v[2] * w2.z + v[3] * w2.w;
-                            }
-                            packed[j / 2 + 0] = pack_bf16(v[0] * s4.x, v[1] * s4.y);
-                            packed[j / 2 + 1] = pack_bf16(v[2] * s4.z, v[3] * s4.w);
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 d4 = *reinterpret_cast<const float4 *>(&sm.e_demod[pb + c0 + j]);
-                            packed[j / 2 + 0] = pack_bf16(__uint_as_float(r[j + 0]) * d4.x, __uint_as_float(r[j + 1]) * d4.y);
-                            packed[j / 2 + 1] = pack_bf16(__uint_as_float(r[j + 2]) * d4.z, __uint_as_float(r[j + 3]) * d4.w);
-                        }
-                    }
-                    if (orow) {
-                        uint4 *dst = reinterpret_cast<uint4 *>(orow + c0);
-#pragma unroll
-                        for (int v4 = 0; v4 < 4; ++v4)
-                            dst[v4] = make_uint4(packed[4 * v4], packed[4 * v4 + 1], packed[4 * v4 + 2], packed[4 * v4 + 3]);
-                    }
+                const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * acc_cols;
+                const EpiTables tab{e_demod + pb, e_next + pb, e_w0 + pb, e_w1 + pb, e_w2 + pb, e_bias};
+                if (alt) {            // this warp owns every column of the tile
+                    if (N == 16) epi_cols<16>(p, tab, t_row, 0, nz, orow, rgb0, rgb1, rgb2);
+                    else
+                        for (int c0 = 0; c0 < N; c0 += 32) epi_cols<32>(p, tab, t_row + c0, c0, nz, orow, rgb0, rgb1, rgb2);
+                } else if (N >= 64) {   // the two warps of a lane quarter alternate 32-column chunks
+                    for (int c0 = 32 * half; c0 < N; c0 += 64) epi_cols<32>(p, tab, t_row + c0, c0, nz, orow, rgb0, rgb1, rgb2);
+                } else if (16 * half < N) {   // N = 32 / 16 with NB * N > 256: 16 columns per warp
+                    epi_cols<16>(p, tab, t_row + 16 * half, 16 * half, nz, orow, rgb0, rgb1, rgb2);
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sm.tmem_empty[acc]);
                 if (valid && p.mode == 0 && p.rgb_w) {   // each column half writes its own partial plane
-                    const long long plane = (long long)g.PH * g.PW;
-                    float *rp = p.rgb_part + ((((long long)t.nt * 2 + half) * p.B + b) * 3) * plane + (long long)y * g.PW + x;
+                    float *rp = p.rgb_part + ((((long long)t.nt * (alt ? 1 : 2) + half) * p.B + b) * 3) * plane + (long long)y * PW + x;
                     rp[0] = rgb0;
                     rp[plane] = rgb1;
                     rp[2 * plane] = rgb2;
                 }
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                t = tn;
+                nz_cur = nz_nxt;
             }
+            it0 += (uint32_t)(tr.hi - tr.lo);
         }
     }
 
@@ -335,6 +486,15 @@ int launch_modconv_gemm(const GemmParams &p, const CUtensorMap *tmA, const CUten
         configured.store(1, std::memory_order_release);
     }
     SG2_REQUIRE(p.block_n % 16 == 0 && p.block_n >= 16 && p.block_n <= kMaxBlockN, SG2_ERR_BAD_ARG, "gemm: bad BLOCK_N %d", p.block_n);
+    if (p.resident) {
+        SG2_REQUIRE(p.n_tiles_n == 1 && p.kpack == 1 && p.resb_bytes == 9 * p.Cin * p.block_n * 2 && p.stage_bytes % 1024 == 0 &&
+                        p.resb_bytes % 1024 == 0 && p.resb_bytes + 2 * p.stage_bytes <= kRingBytes,
+                    SG2_ERR_BAD_ARG, "gemm: bad resident-weights plan (weights %d B, stage %d B)", p.resb_bytes, p.stage_bytes);
+        for (int s = 0; s < p.nsub; ++s)
+            SG2_REQUIRE(p.sub[s].NB == 1 && p.sub[s].TW % 8 == 0 && p.sub[s].nslab >= 1 && p.sub[s].nslab <= 3 &&
+                            p.sub[s].nslab * p.sub[s].slab_rows * p.sub[s].TW * p.block_k * 2 <= p.stage_bytes,
+                        SG2_ERR_BAD_ARG, "gemm: bad slab plan of sub-problem %d", s);
+    }
     SG2_REQUIRE(p.kpack == 1 || (p.kpack == 2 && p.block_k == 64 && p.kchunks % 2 == 0), SG2_ERR_BAD_ARG, "gemm: bad kpack %d", p.kpack);
     SG2_REQUIRE((p.block_k == 64 || p.block_k == 32) && p.Cin % p.block_k == 0 && p.Cout % p.block_n == 0, SG2_ERR_UNSUPPORTED,
                 "gemm: Cin %d must be a multiple of BLOCK_K %d and Cout %d of BLOCK_N %d", p.Cin, p.block_k, p.Cout, p.block_n);

@@ -12,6 +12,7 @@ constexpr int kBlockM = 128;      // pixels per tile = TMEM lanes
 constexpr int kBlockK = 64;       // bf16 channels per stage = one 128-byte swizzle row
 constexpr int kStages = 4;
 constexpr int kMaxBlockN = 256;
+constexpr int kGemmRingBytes = 208 * 1024;   // operand ring of the single-CTA kernel (4 stages of 16 + 32 KiB at N = 256)
 
 // One polyphase sub-problem: an output plane [B, PH, PW, Cout] whose pixel (y, x) is
 // sum over taps t of  W[wtap[t]] . X[y + dy[t], x + dx[t], :]   (zero outside X).
@@ -24,6 +25,11 @@ struct GemmSub {
     int dy[kGemmMaxTaps], dx[kGemmMaxTaps], wtap[kGemmMaxTaps];
     long long out_off;           // element offset of the plane inside `out`
     int out_H, out_W;            // allocated plane extent (row pitch = out_W * Cout)
+    // resident-weights mode: the activation window of a tile is loaded ONCE per K chunk as `nslab`
+    // slabs (one per distinct dx) of slab_rows x TW pixels starting at row y0 + slab_dy0; tap t reads
+    // the 128 pixel rows that start tap_aoff[t] bytes into the stage (a dy shift = TW rows, TW % 8 == 0)
+    int nslab, slab_dx[3], slab_dy0, slab_rows;
+    int tap_aoff[kGemmMaxTaps];
 };
 
 struct GemmParams {
@@ -33,6 +39,12 @@ struct GemmParams {
     int block_n, n_tiles_n, total_tiles, kchunks;   // kchunks = Cin / block_k
     int block_k;                    // channels per K chunk: 64 (SWIZZLE_128B rows) or 32 (SWIZZLE_64B)
     int kpack;                      // K chunks per pipeline stage: 1, or 2 for narrow BLOCK_N
+    // resident-weights mode (narrow layers whose 9*Cin*Cout bf16 weights fit in shared memory): the whole
+    // weight tensor is loaded once per CTA, the ring holds only activation slabs (stage_bytes each)
+    int resident, resb_bytes, stage_bytes;
+    // epilogue schedule of the single-CTA kernel: 1 = the two warp groups take alternate tiles (narrow BLOCK_N,
+    // ONE ToRGB partial plane per N tile), 0 = they split the columns of every tile (two partial planes)
+    int epi_alt;
     // epilogue
     int mode;                       // 0: styled conv (noise, bias, lrelu, next-style, ToRGB); 1: plain scaled store
     const float *demod;             // [B, Cout]
