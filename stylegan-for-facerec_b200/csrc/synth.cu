@@ -263,21 +263,28 @@ int encode_maps(sg2_synth *S, Layer &L, const __nv_bfloat16 *x, const __nv_bfloa
     return SG2_OK;
 }
 
+inline int fir_store_mode() {
+    static const char *e = getenv("SG2_FIR_STORE");
+    return e ? atoi(e) : 0;
+}
+
 // TMA views of the 4 polyphase planes [(py,px)][B][r+1][r+1][C]: valid extent (r+1-py) x (r+1-px), so the
 // never-written last row/column of the odd planes reads as zero; box = 10 x 6 pixels x 64 channels
 int encode_fir_maps(Layer &L, const __nv_bfloat16 *T, const __nv_bfloat16 *out, int B) {
     EncodeTiledFn enc = get_encode();
     SG2_REQUIRE(enc, SG2_ERR_CUDA, "engine: cuTensorMapEncodeTiled entry point not available");
     const int C = L.p.cout, r = L.res_in, P = r + 1;
+    const int cbw = C % 64 == 0 ? 64 : 32;            // column block width of the FIR kernel (synth_fir.cu)
+    const CUtensorMapSwizzle swz = cbw == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     const size_t plane = (size_t)B * P * P * C;
     for (int s = 0; s < 4; ++s) {
         const int py = s >> 1, px = s & 1;
         cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)(P - px), (cuuint64_t)(P - py), (cuuint64_t)B};
         cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)P * C * 2, (cuuint64_t)P * P * C * 2};
-        cuuint32_t box[4] = {64, 6, 10, 1};
+        cuuint32_t box[4] = {(cuuint32_t)cbw, 6, 10, 1};
         cuuint32_t es[4] = {1, 1, 1, 1};
         CUresult rc = enc(&L.tmT[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void *)(T + plane * s), dims, strides, box, es,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         SG2_REQUIRE(rc == CUDA_SUCCESS, SG2_ERR_CUDA, "engine: cuTensorMapEncodeTiled(T plane) failed with %d", (int)rc);
     }
@@ -285,10 +292,10 @@ int encode_fir_maps(Layer &L, const __nv_bfloat16 *T, const __nv_bfloat16 *out, 
         const int R = 2 * r;
         cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)R, (cuuint64_t)R, (cuuint64_t)B};
         cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)R * C * 2, (cuuint64_t)R * R * C * 2};
-        cuuint32_t box[4] = {64, 8, 16, 1};
+        cuuint32_t box[4] = {(cuuint32_t)cbw, 8, (cuuint32_t)(fir_store_mode() ? 4 : 16), 1};   // a column block of the tile / of one warp
         cuuint32_t es[4] = {1, 1, 1, 1};
         CUresult rc = enc(&L.tmO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void *)out, dims, strides, box, es,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         SG2_REQUIRE(rc == CUDA_SUCCESS, SG2_ERR_CUDA, "engine: cuTensorMapEncodeTiled(FIR out) failed with %d", (int)rc);
     }
@@ -598,15 +605,18 @@ extern "C" int sg2_synth_forward(sg2_synth *S, void *workspace, const float *lat
             up.noise = nz; up.noise_bstride = nzs; up.noise_weight = L.p.noise_weight;
             up.bias = L.p.act_bias; up.next_style = (const float *)(ws + next_conv->style);
             memcpy(up.kf, S->kf, sizeof(up.kf));
-            if (S->fir_simt || L.p.cout % 64 != 0) {   // 32-channel tail: SIMT stencil (64-byte rows)
+            if (S->fir_simt || L.p.cout % 32 != 0) {   // odd widths: SIMT stencil
                 rc = launch_upfir(up, B, st);
             } else {
                 UpfirTcParams tp;
-                tp.out = act[0]; tp.r = L.res_in; tp.C = L.p.cout;
-                static const bool fir64 = getenv("SG2_FIR_N64") != nullptr;
-                tp.block_n = (L.p.cout % 128 == 0 && !fir64) ? 128 : 64;
-                tp.tiles_x = (2 * L.res_in + 7) / 8; tp.tiles_y = (2 * L.res_in + 15) / 16; tp.tiles_c = L.p.cout / tp.block_n;
-                tp.total_tiles = tp.tiles_x * tp.tiles_y * tp.tiles_c * B;
+                tp.out = act[0]; tp.r = L.res_in; tp.C = L.p.cout; tp.B = B;
+                tp.cbw = L.p.cout % 64 == 0 ? 64 : 32;
+                tp.nsamp = L.p.cout % 128 == 0 ? 1 : 128 / L.p.cout;      // 64 channels: 2 samples per tile, 32: 4
+                tp.tiles_c = L.p.cout % 128 == 0 ? L.p.cout / 128 : 1;
+                tp.tiles_x = (2 * L.res_in + 7) / 8; tp.tiles_y = (2 * L.res_in + 15) / 16;
+                tp.total_tiles = tp.tiles_x * tp.tiles_y * tp.tiles_c * ((B + tp.nsamp - 1) / tp.nsamp);
+                static const char *envp = getenv("SG2_FIR_NZPF");
+                tp.store_mode = fir_store_mode(); tp.noise_prefetch = envp ? atoi(envp) : 1;
                 tp.noise = nz; tp.noise_bstride = nzs; tp.noise_weight = L.p.noise_weight;
                 tp.bias = L.p.act_bias; tp.next_style = up.next_style;
                 rc = launch_upfir_tc(tp, S->tmK, L.tmT, L.tmO, S->sms, st);

@@ -18,6 +18,12 @@
 //   * fp32 accumulation in TMEM; the epilogue warps only do +noise, +bias, lrelu, x style, pack.
 // The multiplications by structural zeros cost 16x more MACs than the stencil (still < 30 % of
 // the tile's HBM time on the tensor pipe) and buy an instruction stream 4x shorter.
+//
+// A tile is always 128 accumulator columns wide, cut into column blocks of `cbw` channels that each
+// map to one (sample, channel offset): C >= 128 -> two 64-channel blocks of one sample; C = 64 -> two
+// samples; C = 32 (the 1024^2 tail) -> four samples with 64-byte rows (SWIZZLE_64B operand atoms).
+// Every epilogue warp owns 32 pixels x 64 columns and stages them in shared memory in the TMA store layout;
+// the tile leaves through TMA stores (direct 16-byte register stores measured 20 % slower: profiles/experiments).
 #include "common.cuh"
 #include "synth_kernels.cuh"
 #include "tc_ptx.cuh"
@@ -30,46 +36,65 @@ constexpr int FT_TH = 16, FT_TW = 8;             // output tile (pixels)
 constexpr int FT_RA = 10, FT_RB = 6;             // window rows / cols per plane
 constexpr int FT_PLANE_ROWS = 64;                // 60 used + 4 zero pad rows
 constexpr int FT_K = 4 * FT_PLANE_ROWS;          // 256
-constexpr int FT_N = 128;                        // channels per tile (two 64-channel column blocks)
-constexpr int FT_CB_BYTES = FT_K * 128;          // one column block of the window: 32 KiB
-constexpr int FT_RING_CBS = 4;                   // window ring: 4 column blocks = 2 stages at N=128, 4 stages at N=64
-constexpr int FT_OUT_CB_BYTES = 128 * 128;       // staged output tile, one column block: 128 pixels x 128 B
+constexpr int FT_N = 128;                        // accumulator columns per tile
+constexpr int FT_STAGE_BYTES = FT_K * FT_N * 2;  // the window of one tile: 64 KiB whatever the column block width
+constexpr int FT_STAGES = 2;
 constexpr int FT_A_BYTES = 128 * FT_K * 2;       // 64 KiB Toeplitz
 constexpr int FT_EPI_WARPS = 8;
 constexpr int FT_THREADS = 64 + 32 * FT_EPI_WARPS;
 
 struct __align__(1024) FirSmem {
     uint8_t a[FT_A_BYTES];
-    uint8_t b[FT_RING_CBS * FT_CB_BYTES];
-    uint8_t o[2 * FT_OUT_CB_BYTES];                // bf16 output tile in the TMA store layout (SWIZZLE_128B)
+    uint8_t b[FT_STAGES * FT_STAGE_BYTES];
+    uint8_t o[128 * FT_N * 2];                     // bf16 output tile [column block][128 px][cbw] in the TMA store layout
     float e_bias[FT_N];
     float e_next[FT_N];
     uint64_t a_full;
-    uint64_t full[FT_RING_CBS], empty[FT_RING_CBS];
+    uint64_t full[FT_STAGES], empty[FT_STAGES];
     uint64_t tmem_full[2], tmem_empty[2];
     uint32_t tmem_base;
 };
 
-struct FirTile { int n, ct, y0, x0; };
+struct FirTile { int n0, ct, y0, x0; };
 
-__device__ __forceinline__ FirTile fir_decode(const UpfirTcParams &p, int tile) {
-    FirTile t;
-    const int bx = tile % p.tiles_x;
-    tile /= p.tiles_x;
-    const int by = tile % p.tiles_y;
-    tile /= p.tiles_y;
-    t.ct = tile % p.tiles_c;
-    t.n = tile / p.tiles_c;
-    t.x0 = bx * FT_TW;
-    t.y0 = by * FT_TH;
-    return t;
-}
+// Tiles are dealt round-robin (tile = blockIdx.x + i * gridDim.x); the walker keeps the mixed-radix digits
+// (x, y, channel group, sample group) and adds the decomposed stride with carries: no division per tile.
+struct FirWalk {
+    int bx, by, ct, ng;          // current digits
+    int sx, sy, sc, sn;          // stride digits
+    __device__ __forceinline__ void init(const UpfirTcParams &p, int tile, int step) {
+        bx = tile % p.tiles_x; tile /= p.tiles_x;
+        by = tile % p.tiles_y; tile /= p.tiles_y;
+        ct = tile % p.tiles_c; ng = tile / p.tiles_c;
+        sx = step % p.tiles_x; step /= p.tiles_x;
+        sy = step % p.tiles_y; step /= p.tiles_y;
+        sc = step % p.tiles_c; sn = step / p.tiles_c;
+    }
+    __device__ __forceinline__ void next(const UpfirTcParams &p) {
+        bx += sx;
+        int c = bx >= p.tiles_x;
+        bx -= c ? p.tiles_x : 0;
+        by += sy + c;
+        c = by >= p.tiles_y;
+        by -= c ? p.tiles_y : 0;
+        ct += sc + c;
+        c = ct >= p.tiles_c;
+        ct -= c ? p.tiles_c : 0;
+        ng += sn + c;
+    }
+    __device__ __forceinline__ FirTile tile(const UpfirTcParams &p) const {
+        FirTile t;
+        t.n0 = ng * p.nsamp; t.ct = ct; t.y0 = by * FT_TH; t.x0 = bx * FT_TW;
+        return t;
+    }
+};
 
-// MN-major SWIZZLE_128B operand: 64-element (128 B) rows along N, 8-row groups along K 1024 B apart
-// (SBO), 64-element N blocks `lbo_bytes` apart (LBO).
-__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
-    return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
-           (1ull << 46) | (2ull << 61);
+// MN-major swizzled operand (mma_traits_sm100.hpp canonical layouts): rows of `row_bytes` (128: SWIZZLE_128B,
+// 64: SWIZZLE_64B) along N, 8-row groups along K 8*row_bytes apart (SBO), N atoms `lbo_bytes` apart (LBO).
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t row_bytes) {
+    const uint64_t layout = row_bytes == 128 ? 2 : 4;
+    return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) |
+           ((uint64_t)((8 * row_bytes) >> 4) << 32) | (1ull << 46) | (layout << 61);
 }
 
 __global__ void __launch_bounds__(FT_THREADS, 1)
@@ -80,18 +105,25 @@ upfir_tc_kernel(const __grid_constant__ UpfirTcParams p, const __grid_constant__
     extern __shared__ uint8_t smem_raw[];
     FirSmem &sm = *reinterpret_cast<FirSmem *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cbw = p.cbw, ncb = FT_N / cbw;                 // column block width (channels) and count
+    const uint32_t row_bytes = (uint32_t)cbw * 2, cb_bytes = FT_K * row_bytes;
+    const int cps = ncb / p.nsamp;                           // column blocks per sample
 
-    // zero the pad rows (60..63 of every plane region) once: TMA never writes them
-    for (int i = threadIdx.x; i < FT_RING_CBS * 4 * 4 * 8; i += FT_THREADS) {
-        const int v = i & 7, row = (i >> 3) & 3, plane = (i >> 5) & 3, cb = i >> 7;
-        *reinterpret_cast<uint4 *>(&sm.b[cb * FT_CB_BYTES + (plane * FT_PLANE_ROWS + 60 + row) * 128 + v * 16]) =
-            make_uint4(0, 0, 0, 0);
+    // zero the pad rows (60..63 of every plane region of every column block) once: TMA never writes them
+    {
+        const int v16 = (int)row_bytes / 16;                 // 16-byte pieces per row
+        const int total = FT_STAGES * ncb * 4 * 4 * v16;
+        for (int i = threadIdx.x; i < total; i += FT_THREADS) {
+            const int v = i % v16, row = (i / v16) & 3, plane = (i / (v16 * 4)) & 3, cb = i / (v16 * 16);
+            *reinterpret_cast<uint4 *>(&sm.b[cb * cb_bytes + (plane * FT_PLANE_ROWS + 60 + row) * row_bytes + v * 16]) =
+                make_uint4(0, 0, 0, 0);
+        }
     }
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmK);
         tma_prefetch_desc(&tmT0);
         mbar_init(&sm.a_full, 1);
-        for (int i = 0; i < FT_RING_CBS; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.empty[i], 1); }
+        for (int i = 0; i < FT_STAGES; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&sm.tmem_full[i], 1); mbar_init(&sm.tmem_empty[i], FT_EPI_WARPS); }
         fence_barrier_init();
     }
@@ -102,21 +134,14 @@ upfir_tc_kernel(const __grid_constant__ UpfirTcParams p, const __grid_constant__
     tc_fence_after();
     const uint32_t tmem_base = sm.tmem_base;
 
-    const int per = (p.total_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
     // round-robin: at any moment the 148 CTAs work on ~5 adjacent tile rows, so the halo rows a tile
     // shares with its vertical neighbours are still in L2 when the neighbour loads them
-    const int tile_lo = (int)blockIdx.x, tile_step = (int)gridDim.x;
-    (void)per;
-    const int tile_hi = p.total_tiles;
-    const int ncb = p.block_n / 64;                 // column blocks per tile (1 or 2)
-    const uint32_t nstages = FT_RING_CBS / ncb, stage_bytes = ncb * FT_CB_BYTES;
+    const int tile_lo = (int)blockIdx.x, tile_step = (int)gridDim.x, tile_hi = p.total_tiles;
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        // warp-uniform loop, one elected lane issues (no divergent single-thread region)
+        // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
         if (tile_lo < tile_hi) {
-            // Toeplitz matrix: 4 K-atoms of [128 rows][64 k] each
-            if (elect_one()) {
+            if (elect_one()) {      // Toeplitz matrix: 4 K-atoms of [128 rows][64 k] each
                 mbar_arrive_expect_tx(&sm.a_full, FT_A_BYTES);
                 for (int ka = 0; ka < 4; ++ka)
                     asm volatile(
@@ -126,93 +151,136 @@ upfir_tc_kernel(const __grid_constant__ UpfirTcParams p, const __grid_constant__
                         : "memory");
             }
             __syncwarp();
+            const uint32_t plane_bytes = FT_PLANE_ROWS * row_bytes;
+            // per column block: channel offset inside the tile's channel group and sample offset (tile-invariant)
+            int coff[4], noff[4];
+#pragma unroll
+            for (int cb = 0; cb < 4; ++cb) { coff[cb] = (cb % cps) * cbw; noff[cb] = cb / cps; }
+            const int cgroup = cps * cbw;
             uint32_t stage = 0, phase = 0;
-            for (int tile = tile_lo; tile < tile_hi; tile += tile_step) {
-                const FirTile t = fir_decode(p, tile);
-                const int a0 = t.y0 / 2, b0 = t.x0 / 2;     // first cell of the tile
+            FirWalk w;
+            w.init(p, tile_lo, tile_step);
+            for (int tile = tile_lo; tile < tile_hi; tile += tile_step, w.next(p)) {
+                const FirTile t = w.tile(p);
+                const int a0 = t.y0 / 2 - 1, b0 = t.x0 / 2 - 1;     // first window cell of the tile
                 mbar_wait(&sm.empty[stage], phase ^ 1);
                 if (elect_one()) {
-                    mbar_arrive_expect_tx(&sm.full[stage], (uint32_t)(ncb * 4 * FT_RA * FT_RB * 128));
-                    for (int cb = 0; cb < ncb; ++cb) {
-                        const int c = t.ct * p.block_n + cb * 64;
-                        uint8_t *dst = sm.b + stage * stage_bytes + cb * FT_CB_BYTES;
-                        tma_load_4d(dst + 0 * FT_PLANE_ROWS * 128, &tmT0, &sm.full[stage], c, b0 - 1, a0 - 1, t.n);
-                        tma_load_4d(dst + 1 * FT_PLANE_ROWS * 128, &tmT1, &sm.full[stage], c, b0 - 1, a0 - 1, t.n);
-                        tma_load_4d(dst + 2 * FT_PLANE_ROWS * 128, &tmT2, &sm.full[stage], c, b0 - 1, a0 - 1, t.n);
-                        tma_load_4d(dst + 3 * FT_PLANE_ROWS * 128, &tmT3, &sm.full[stage], c, b0 - 1, a0 - 1, t.n);
+                    mbar_arrive_expect_tx(&sm.full[stage], (uint32_t)(ncb * 4 * FT_RA * FT_RB) * row_bytes);
+#pragma unroll
+                    for (int cb = 0; cb < 4; ++cb) {
+                        if (cb < ncb) {
+                            const int c = t.ct * cgroup + coff[cb], n = t.n0 + noff[cb];   // samples >= B read as zero
+                            uint8_t *dst = sm.b + stage * FT_STAGE_BYTES + cb * cb_bytes;
+                            tma_load_4d(dst + 0 * plane_bytes, &tmT0, &sm.full[stage], c, b0, a0, n);
+                            tma_load_4d(dst + 1 * plane_bytes, &tmT1, &sm.full[stage], c, b0, a0, n);
+                            tma_load_4d(dst + 2 * plane_bytes, &tmT2, &sm.full[stage], c, b0, a0, n);
+                            tma_load_4d(dst + 3 * plane_bytes, &tmT3, &sm.full[stage], c, b0, a0, n);
+                        }
                     }
                 }
                 __syncwarp();
-                if (++stage == nstages) { stage = 0; phase ^= 1; }
+                if (++stage == FT_STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (tile_lo < tile_hi) {
-            // kind::f16, D=f32, A=B=bf16, A K-major, B MN-major (bit 16), M=128, N=block_n
-            const uint32_t idesc = make_idesc_bf16(128, (uint32_t)p.block_n) | (1u << 16);
+            // kind::f16, D=f32, A=B=bf16, A K-major, B MN-major (bit 16), M=128, N=128
+            const uint32_t idesc = make_idesc_bf16(128, FT_N) | (1u << 16);
             mbar_wait(&sm.a_full, 0);
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
             const uint32_t a_base = smem_u32(sm.a);
+            const uint32_t kstep = (16 * row_bytes) >> 4;        // 16 K rows per MMA, in 16-byte units
             for (int tile = tile_lo; tile < tile_hi; tile += tile_step) {
                 mbar_wait(&sm.tmem_empty[acc], acc_phase ^ 1);
                 mbar_wait(&sm.full[stage], phase);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * FT_N;
-                const uint32_t b_base = smem_u32(sm.b) + stage * stage_bytes;
                 const uint64_t adesc0 = make_smem_desc(a_base, 128);
-                const uint64_t bdesc0 = make_smem_desc_mn(b_base, FT_CB_BYTES);
+                const uint64_t bdesc0 = make_smem_desc_mn(smem_u32(sm.b) + stage * FT_STAGE_BYTES, cb_bytes, row_bytes);
                 if (elect_one()) {
 #pragma unroll
                     for (int kk = 0; kk < FT_K / 16; ++kk) {
                         const uint64_t adesc = adesc0 + (uint64_t)(((kk >> 2) * 16384 + (kk & 3) * 32) >> 4);
-                        const uint64_t bdesc = bdesc0 + (uint64_t)((kk * 16 * 128) >> 4);
-                        umma_bf16(d_tmem, adesc, bdesc, idesc, kk != 0);
+                        umma_bf16(d_tmem, adesc, bdesc0 + (uint64_t)(kk * kstep), idesc, kk != 0);
                     }
                     umma_commit(&sm.empty[stage]);
                     umma_commit(&sm.tmem_full[acc]);
                 }
                 __syncwarp();
-                if (++stage == nstages) { stage = 0; phase ^= 1; }
+                if (++stage == FT_STAGES) { stage = 0; phase ^= 1; }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
     } else {
         // ===================== epilogue: 8 warps, two per TMEM lane quarter =====================
+        // warp (q, half) owns pixels 32q..32q+31 x columns 64*half..64*half+63 of every tile
         const int q = warp & 3, half = (warp - 2) >> 2;
         const int m = q * 32 + lane;                 // output pixel of the tile: (m / 8, m % 8)
         const int oy = m >> 3, ox = m & 7;
         const int et = threadIdx.x - 64;
-        const int R = 2 * p.r, N = p.block_n;
+        const int R = 2 * p.r;
         const float nw = p.noise ? __ldg(p.noise_weight) : 0.f;
+        // the (up to two) samples behind this warp's two 32-column chunks
+        const int cb_a = (64 * half) / cbw, cb_b = (64 * half + 32) / cbw;
+        const int ds_a = cb_a / cps, ds_b = cb_b / cps;
+        auto noise_at = [&](const FirTile &tt, int ds) -> float {
+            const int Y = tt.y0 + oy, X = tt.x0 + ox, n = tt.n0 + ds;
+            if (p.noise && Y < R && X < R && n < p.B) return __ldg(p.noise + (long long)n * p.noise_bstride + (long long)Y * R + X);
+            return 0.f;
+        };
         uint32_t acc = 0, acc_phase = 0;
         int staged_key = -1;
+        float nza = 0.f, nzb = 0.f;
+        FirWalk w;
+        w.init(p, tile_lo, tile_step);
+        if (tile_lo < tile_hi && p.noise_prefetch) {
+            const FirTile t0 = w.tile(p);
+            nza = noise_at(t0, ds_a);
+            nzb = ds_b == ds_a ? nza : noise_at(t0, ds_b);
+        }
         for (int tile = tile_lo; tile < tile_hi; tile += tile_step) {
-            const FirTile t = fir_decode(p, tile);
-            const int Y = t.y0 + oy, X = t.x0 + ox, c0 = t.ct * N;
-            const bool valid = Y < R && X < R;
-            float nz = 0.f;
-            if (valid && p.noise) nz = __ldg(p.noise + (long long)t.n * p.noise_bstride + (long long)Y * R + X);
-            const int key = t.n * 64 + t.ct;
+            const FirTile t = w.tile(p);
+            w.next(p);
+            // noise of the NEXT tile: fetched now, consumed one iteration later
+            float nza_n = 0.f, nzb_n = 0.f;
+            if (!p.noise_prefetch) {
+                nza = noise_at(t, ds_a);
+                nzb = ds_b == ds_a ? nza : noise_at(t, ds_b);
+            } else if (tile + tile_step < tile_hi) {
+                const FirTile tn = w.tile(p);
+                nza_n = noise_at(tn, ds_a);
+                nzb_n = ds_b == ds_a ? nza_n : noise_at(tn, ds_b);
+            }
+            const int key = t.n0 * 64 + t.ct;
             if (key != staged_key) {
                 asm volatile("bar.sync 1, 256;" ::: "memory");
-                for (int i = et; i < N; i += 256) {
-                    sm.e_bias[i] = __ldg(p.bias + c0 + i);
-                    sm.e_next[i] = 1.41421356237f * __ldg(p.next_style + (long long)t.n * p.C + c0 + i);
+                for (int j = et; j < FT_N; j += 256) {
+                    const int cb = j / cbw, c = t.ct * (cps * cbw) + (cb % cps) * cbw + (j - cb * cbw);
+                    const int n = min(t.n0 + cb / cps, p.B - 1);
+                    sm.e_bias[j] = __ldg(p.bias + c);
+                    sm.e_next[j] = 1.41421356237f * __ldg(p.next_style + (long long)n * p.C + c);
                 }
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 staged_key = key;
             }
-            nz *= nw;
-            // the previous tile's TMA store must have finished reading the staging buffer
-            if (et == 0) tma_store_wait_read();
-            asm volatile("bar.sync 2, 256;" ::: "memory");
+            // the previous tile's TMA stores must have finished reading the staging buffer
+            if (p.store_mode == 0) {
+                if (et == 0) tma_store_wait_read();
+                asm volatile("bar.sync 2, 256;" ::: "memory");
+            } else {
+                if (lane == 0) tma_store_wait_read();
+                __syncwarp();
+            }
             mbar_wait(&sm.tmem_full[acc], acc_phase);
             tc_fence_after();
-            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * FT_N;
-            for (int cc = 32 * half; cc < N; cc += 64) {
+            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * FT_N + 64 * half;
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+                const int cc = 64 * half + 32 * ch;              // first accumulator column of the chunk
+                const float nz = (ch == 0 ? nza : nzb) * nw;
                 uint32_t r[32];
-                tmem_ld32(t_row + cc, r);
+                tmem_ld32(t_row + 32 * ch, r);
                 tmem_ld_wait();
                 uint32_t packed[16];
 #pragma unroll
@@ -227,28 +295,49 @@ upfir_tc_kernel(const __grid_constant__ UpfirTcParams p, const __grid_constant__
                     packed[j / 2] = *reinterpret_cast<uint32_t *>(&h0);
                     packed[j / 2 + 1] = *reinterpret_cast<uint32_t *>(&h1);
                 }
-                // stage the 64 bytes of this pixel in the TMA layout: 16-byte chunk index XOR (row & 7)
-                uint8_t *orow = sm.o + (cc >> 6) * FT_OUT_CB_BYTES + m * 128;
-                const int ch0 = (cc & 63) >> 3;
+                // stage this pixel's 64 bytes in the TMA layout of the store box
+                if (cbw == 64) {      // [128 px][128 B] per column block, SWIZZLE_128B: 16-byte chunk index XOR (row & 7)
+                    uint8_t *orow = sm.o + half * (128 * 128) + m * 128;
 #pragma unroll
-                for (int v4 = 0; v4 < 4; ++v4)
-                    *reinterpret_cast<uint4 *>(orow + (((ch0 + v4) ^ (m & 7)) << 4)) =
-                        make_uint4(packed[4 * v4], packed[4 * v4 + 1], packed[4 * v4 + 2], packed[4 * v4 + 3]);
+                    for (int v4 = 0; v4 < 4; ++v4)
+                        *reinterpret_cast<uint4 *>(orow + (((4 * ch + v4) ^ (m & 7)) << 4)) =
+                            make_uint4(packed[4 * v4], packed[4 * v4 + 1], packed[4 * v4 + 2], packed[4 * v4 + 3]);
+                } else {              // [128 px][64 B] per column block, SWIZZLE_64B: chunk index XOR ((row >> 1) & 3)
+                    uint8_t *orow = sm.o + (2 * half + ch) * (128 * 64) + m * 64;
+#pragma unroll
+                    for (int v4 = 0; v4 < 4; ++v4)
+                        *reinterpret_cast<uint4 *>(orow + ((v4 ^ ((m >> 1) & 3)) << 4)) =
+                            make_uint4(packed[4 * v4], packed[4 * v4 + 1], packed[4 * v4 + 2], packed[4 * v4 + 3]);
+                }
             }
             tc_fence_before();
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm.tmem_empty[acc]);
-            asm volatile("bar.sync 3, 256;" ::: "memory");
-            if (et == 0) {      // rows/cols beyond the image are clipped by the TMA unit
-                for (int cb = 0; cb < ncb; ++cb)
-                    tma_store_4d(&tmO, sm.o + cb * FT_OUT_CB_BYTES, c0 + cb * 64, t.x0, t.y0, t.n);
+            // rows / columns / samples beyond the tensor are clipped by the TMA unit
+            if (p.store_mode == 0) {       // one thread stores whole column blocks (box cbw x 8 x 16)
+                asm volatile("bar.sync 3, 256;" ::: "memory");
+                if (et == 0) {
+                    for (int cb = 0; cb < ncb; ++cb)
+                        tma_store_4d(&tmO, sm.o + cb * (128 * (int)row_bytes), t.ct * (cps * cbw) + (cb % cps) * cbw, t.x0, t.y0,
+                                     t.n0 + cb / cps);
+                    tma_store_commit();
+                }
+            } else if (lane == 0) {        // every warp stores its own 32 pixels (box cbw x 8 x 4)
+                if (cbw == 64) {
+                    tma_store_4d(&tmO, sm.o + half * (128 * 128) + q * 4096, t.ct * (cps * 64) + (cb_a % cps) * 64, t.x0,
+                                 t.y0 + 4 * q, t.n0 + ds_a);
+                } else {
+                    tma_store_4d(&tmO, sm.o + cb_a * (128 * 64) + q * 2048, 0, t.x0, t.y0 + 4 * q, t.n0 + ds_a);
+                    tma_store_4d(&tmO, sm.o + cb_b * (128 * 64) + q * 2048, 0, t.x0, t.y0 + 4 * q, t.n0 + ds_b);
+                }
                 tma_store_commit();
             }
+            if (p.noise_prefetch) { nza = nza_n; nzb = nzb_n; }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        if (lane == 0) tma_store_wait_all();     // threads without outstanding stores return at once
     }
-    if (threadIdx.x == 64) tma_store_wait_all();
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, 256);
@@ -282,7 +371,8 @@ int launch_upfir_tc(const UpfirTcParams &p, const CUtensorMap &tmK, const CUtens
         SG2_CUDA_OK(cudaFuncSetAttribute(upfir_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured.store(1, std::memory_order_release);
     }
-    SG2_REQUIRE(p.block_n == 64 || p.block_n == 128, SG2_ERR_BAD_ARG, "upfir_tc: block_n must be 64 or 128");
+    SG2_REQUIRE((p.cbw == 64 || p.cbw == 32) && p.nsamp >= 1 && (FT_N / p.cbw) % p.nsamp == 0, SG2_ERR_BAD_ARG,
+                "upfir_tc: bad column blocking (cbw %d, %d samples per tile)", p.cbw, p.nsamp);
     const int grid = p.total_tiles < sms ? p.total_tiles : sms;
     if (grid <= 0) return SG2_OK;
     upfir_tc_kernel<<<grid, FT_THREADS, smem, st>>>(p, tmK, tmT[0], tmT[1], tmT[2], tmT[3], tmO);

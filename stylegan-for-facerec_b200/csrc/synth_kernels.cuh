@@ -37,8 +37,11 @@ struct UpfirParams {
 // tensor-core variant (synth_fir.cu): T is read through TMA descriptors
 struct UpfirTcParams {
     __nv_bfloat16 *out;           // [B][2r][2r][C]
-    int r, C, block_n;            // block_n = channels per tile: 128 or 64
-    int tiles_x, tiles_y, tiles_c, total_tiles;
+    int r, C, B;
+    int cbw, nsamp;               // a tile = 128 columns = (128 / cbw) column blocks of cbw channels over nsamp samples
+    int tiles_x, tiles_y, tiles_c, total_tiles;   // tiles_c = channel groups per sample (C / 128, or 1)
+    int store_mode;               // 0: one thread stores whole column blocks (box cbw x 8 x 16); 1: per-warp boxes cbw x 8 x 4
+    int noise_prefetch;           // fetch the next tile's noise one iteration ahead
     const float *noise; long long noise_bstride; const float *noise_weight;
     const float *bias;            // [C]
     const float *next_style;      // [B][C]
