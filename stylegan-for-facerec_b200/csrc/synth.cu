@@ -211,6 +211,8 @@ int plan_gemm(sg2_synth *S, Layer &L) {
             }
         }
     }
+    static const char *envd = getenv("SG2_GEMM_DBG");
+    g.dbg = envd ? atoi(envd) : 0;
     static const char *enva = getenv("SG2_GEMM_EPI_ALT");
     bool small = best_n <= 64;
     for (int s = 0; s < g.nsub; ++s) small = small && g.sub[s].NB * best_n <= 256;
@@ -524,7 +526,7 @@ extern "C" int sg2_synth_forward(sg2_synth *S, void *workspace, const float *lat
         StyleJob &j = sj.job[sj.n++];
         j.mod_w = L.p.mod_weight; j.mod_b = L.p.mod_bias; j.out = (float *)(ws + L.style);
         j.cin = L.p.cin; j.latent_index = L.p.latent_index; j.block_begin = blocks;
-        blocks += (L.p.cin + 7) / 8;
+        blocks += (L.p.cin + kStyleBlockCi - 1) / kStyleBlockCi;
         if (!L.rgb) {
             DemodJob &d = dj.job[dj.n++];
             d.style = (const float *)(ws + L.style); d.wsq = (const float *)(ws + L.wsq); d.demod = (float *)(ws + L.demod);
@@ -616,7 +618,9 @@ extern "C" int sg2_synth_forward(sg2_synth *S, void *workspace, const float *lat
                 tp.tiles_x = (2 * L.res_in + 7) / 8; tp.tiles_y = (2 * L.res_in + 15) / 16;
                 tp.total_tiles = tp.tiles_x * tp.tiles_y * tp.tiles_c * ((B + tp.nsamp - 1) / tp.nsamp);
                 static const char *envp = getenv("SG2_FIR_NZPF");
+                static const char *envd = getenv("SG2_FIR_DBG");
                 tp.store_mode = fir_store_mode(); tp.noise_prefetch = envp ? atoi(envp) : 1;
+                tp.dbg = envd ? atoi(envd) : 0;
                 tp.noise = nz; tp.noise_bstride = nzs; tp.noise_weight = L.p.noise_weight;
                 tp.bias = L.p.act_bias; tp.next_style = up.next_style;
                 rc = launch_upfir_tc(tp, S->tmK, L.tmT, L.tmO, S->sms, st);

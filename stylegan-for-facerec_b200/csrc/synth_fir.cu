@@ -40,8 +40,14 @@ constexpr int FT_N = 128;                        // accumulator columns per tile
 constexpr int FT_STAGE_BYTES = FT_K * FT_N * 2;  // the window of one tile: 64 KiB whatever the column block width
 constexpr int FT_STAGES = 2;
 constexpr int FT_A_BYTES = 128 * FT_K * 2;       // 64 KiB Toeplitz
-constexpr int FT_EPI_WARPS = 8;
-constexpr int FT_THREADS = 64 + 32 * FT_EPI_WARPS;
+#ifndef SG2_FIR_EPI_WARPS
+#define SG2_FIR_EPI_WARPS 16
+#endif
+constexpr int FT_EPI_WARPS = SG2_FIR_EPI_WARPS;  // 4 warps per TMEM lane quarter: a 32-column chunk each (8: two chunks each)
+constexpr int FT_EPI_THREADS = 32 * FT_EPI_WARPS;
+constexpr int FT_CPW = 16 / FT_EPI_WARPS;        // 32-column chunks per epilogue warp
+constexpr int FT_THREADS = 64 + FT_EPI_THREADS;
+static_assert(FT_EPI_WARPS == 8 || FT_EPI_WARPS == 16, "epilogue: 2 or 4 warps per TMEM lane quarter");
 
 struct __align__(1024) FirSmem {
     uint8_t a[FT_A_BYTES];
@@ -164,7 +170,9 @@ upfir_tc_kernel(const __grid_constant__ UpfirTcParams p, const __grid_constant__
                 const FirTile t = w.tile(p);
                 const int a0 = t.y0 / 2 - 1, b0 = t.x0 / 2 - 1;     // first window cell of the tile
                 mbar_wait(&sm.empty[stage], phase ^ 1);
-                if (elect_one()) {
+                if (p.dbg & 1) {
+                    if (elect_one()) mbar_arrive(&sm.full[stage]);
+                } else if (elect_one()) {
                     mbar_arrive_expect_tx(&sm.full[stage], (uint32_t)(ncb * 4 * FT_RA * FT_RB) * row_bytes);
 #pragma unroll
                     for (int cb = 0; cb < 4; ++cb) {
@@ -200,7 +208,7 @@ upfir_tc_kernel(const __grid_constant__ UpfirTcParams p, const __grid_constant__
                 const uint64_t bdesc0 = make_smem_desc_mn(smem_u32(sm.b) + stage * FT_STAGE_BYTES, cb_bytes, row_bytes);
                 if (elect_one()) {
 #pragma unroll
-                    for (int kk = 0; kk < FT_K / 16; ++kk) {
+                    for (int kk = 0; kk < ((p.dbg & 8) ? 1 : FT_K / 16); ++kk) {
                         const uint64_t adesc = adesc0 + (uint64_t)(((kk >> 2) * 16384 + (kk & 3) * 32) >> 4);
                         umma_bf16(d_tmem, adesc, bdesc0 + (uint64_t)(kk * kstep), idesc, kk != 0);
                     }
@@ -213,127 +221,151 @@ upfir_tc_kernel(const __grid_constant__ UpfirTcParams p, const __grid_constant__
             }
         }
     } else {
-        // ===================== epilogue: 8 warps, two per TMEM lane quarter =====================
-        // warp (q, half) owns pixels 32q..32q+31 x columns 64*half..64*half+63 of every tile
-        const int q = warp & 3, half = (warp - 2) >> 2;
+        // ===================== epilogue: FT_EPI_WARPS warps, FT_EPI_WARPS / 4 per TMEM lane quarter =====
+        // The knock-out analysis (profiles/experiments) showed this role, not the loads or the MMAs, paces the
+        // kernel: its per-tile chain (store-read wait, TMEM load, math, staging, fence, barrier, store) is serial.
+        // So: 16 warps (one 32-column chunk each, 4 per scheduler to hide the latencies) and packed f32x2 math.
+        // warp (q, kq) owns pixels 32q..32q+31 x chunks kq*FT_CPW .. of every tile
+        const int q = warp & 3, kq = (warp - 2) >> 2;
         const int m = q * 32 + lane;                 // output pixel of the tile: (m / 8, m % 8)
         const int oy = m >> 3, ox = m & 7;
         const int et = threadIdx.x - 64;
+        const uint32_t e_bias_s = smem_u32(sm.e_bias), e_next_s = smem_u32(sm.e_next), o_s = smem_u32(sm.o);
         const int R = 2 * p.r;
         const float nw = p.noise ? __ldg(p.noise_weight) : 0.f;
-        // the (up to two) samples behind this warp's two 32-column chunks
-        const int cb_a = (64 * half) / cbw, cb_b = (64 * half + 32) / cbw;
-        const int ds_a = cb_a / cps, ds_b = cb_b / cps;
-        auto noise_at = [&](const FirTile &tt, int ds) -> float {
-            const int Y = tt.y0 + oy, X = tt.x0 + ox, n = tt.n0 + ds;
+        // the sample behind each of this warp's chunks
+        int ds[FT_CPW];
+#pragma unroll
+        for (int ci = 0; ci < FT_CPW; ++ci) ds[ci] = ((32 * (kq * FT_CPW + ci)) / cbw) / cps;
+        auto noise_at = [&](const FirTile &tt, int d) -> float {
+            const int Y = tt.y0 + oy, X = tt.x0 + ox, n = tt.n0 + d;
             if (p.noise && Y < R && X < R && n < p.B) return __ldg(p.noise + (long long)n * p.noise_bstride + (long long)Y * R + X);
             return 0.f;
         };
         uint32_t acc = 0, acc_phase = 0;
         int staged_key = -1;
-        float nza = 0.f, nzb = 0.f;
+        float nzc[FT_CPW], nzn[FT_CPW];
+#pragma unroll
+        for (int ci = 0; ci < FT_CPW; ++ci) nzc[ci] = nzn[ci] = 0.f;
         FirWalk w;
         w.init(p, tile_lo, tile_step);
         if (tile_lo < tile_hi && p.noise_prefetch) {
             const FirTile t0 = w.tile(p);
-            nza = noise_at(t0, ds_a);
-            nzb = ds_b == ds_a ? nza : noise_at(t0, ds_b);
+#pragma unroll
+            for (int ci = 0; ci < FT_CPW; ++ci) nzc[ci] = (ci > 0 && ds[ci] == ds[0]) ? nzc[0] : noise_at(t0, ds[ci]);
         }
         for (int tile = tile_lo; tile < tile_hi; tile += tile_step) {
             const FirTile t = w.tile(p);
             w.next(p);
             // noise of the NEXT tile: fetched now, consumed one iteration later
-            float nza_n = 0.f, nzb_n = 0.f;
             if (!p.noise_prefetch) {
-                nza = noise_at(t, ds_a);
-                nzb = ds_b == ds_a ? nza : noise_at(t, ds_b);
+#pragma unroll
+                for (int ci = 0; ci < FT_CPW; ++ci) nzc[ci] = (ci > 0 && ds[ci] == ds[0]) ? nzc[0] : noise_at(t, ds[ci]);
             } else if (tile + tile_step < tile_hi) {
                 const FirTile tn = w.tile(p);
-                nza_n = noise_at(tn, ds_a);
-                nzb_n = ds_b == ds_a ? nza_n : noise_at(tn, ds_b);
+#pragma unroll
+                for (int ci = 0; ci < FT_CPW; ++ci) nzn[ci] = (ci > 0 && ds[ci] == ds[0]) ? nzn[0] : noise_at(tn, ds[ci]);
             }
             const int key = t.n0 * 64 + t.ct;
             if (key != staged_key) {
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                for (int j = et; j < FT_N; j += 256) {
+                asm volatile("bar.sync 1, %0;" ::"n"(FT_EPI_THREADS) : "memory");
+                for (int j = et; j < FT_N; j += FT_EPI_THREADS) {
                     const int cb = j / cbw, c = t.ct * (cps * cbw) + (cb % cps) * cbw + (j - cb * cbw);
                     const int n = min(t.n0 + cb / cps, p.B - 1);
                     sm.e_bias[j] = __ldg(p.bias + c);
                     sm.e_next[j] = 1.41421356237f * __ldg(p.next_style + (long long)n * p.C + c);
                 }
-                asm volatile("bar.sync 1, 256;" ::: "memory");
+                asm volatile("bar.sync 1, %0;" ::"n"(FT_EPI_THREADS) : "memory");
                 staged_key = key;
             }
+            mbar_wait(&sm.tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * FT_N;
+            // TMEM -> registers -> math first: it overlaps the previous tile's TMA store, whose read of the staging
+            // buffer only has to be over before the shared-memory writes below
+            uint32_t packed[FT_CPW][16];
+#pragma unroll
+            for (int ci = 0; ci < FT_CPW; ++ci) {
+                if (p.dbg & 4) break;
+                const int cc = 32 * (kq * FT_CPW + ci);          // first accumulator column of the chunk
+                const float2 nz2 = make_float2(nzc[ci] * nw, nzc[ci] * nw);
+                uint32_t r[32];
+                tmem_ld32(t_row + cc, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 b4 = lds128f(e_bias_s + (uint32_t)(cc + j) * 4u);
+                    const float4 s4 = lds128f(e_next_s + (uint32_t)(cc + j) * 4u);
+                    // (acc + noise + bias) -> lrelu -> x style of the consumer, two columns per instruction
+                    float2 a = __fadd2_rn(__fadd2_rn(make_float2(__uint_as_float(r[j + 0]), __uint_as_float(r[j + 1])), nz2),
+                                          make_float2(b4.x, b4.y));
+                    float2 b = __fadd2_rn(__fadd2_rn(make_float2(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])), nz2),
+                                          make_float2(b4.z, b4.w));
+                    const float2 al = __fmul2_rn(a, make_float2(0.2f, 0.2f)), bl = __fmul2_rn(b, make_float2(0.2f, 0.2f));
+                    a = __fmul2_rn(make_float2(fmaxf(a.x, al.x), fmaxf(a.y, al.y)), make_float2(s4.x, s4.y));
+                    b = __fmul2_rn(make_float2(fmaxf(b.x, bl.x), fmaxf(b.y, bl.y)), make_float2(s4.z, s4.w));
+                    __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(b.x, b.y);
+                    packed[ci][j / 2] = *reinterpret_cast<uint32_t *>(&h0);
+                    packed[ci][j / 2 + 1] = *reinterpret_cast<uint32_t *>(&h1);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.tmem_empty[acc]);     // accumulator drained: the MMA warp may reuse it
             // the previous tile's TMA stores must have finished reading the staging buffer
-            if (p.store_mode == 0) {
+            if (p.dbg & 2) {
+            } else if (p.store_mode == 0) {
                 if (et == 0) tma_store_wait_read();
-                asm volatile("bar.sync 2, 256;" ::: "memory");
+                asm volatile("bar.sync 2, %0;" ::"n"(FT_EPI_THREADS) : "memory");
             } else {
                 if (lane == 0) tma_store_wait_read();
                 __syncwarp();
             }
-            mbar_wait(&sm.tmem_full[acc], acc_phase);
-            tc_fence_after();
-            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * FT_N + 64 * half;
 #pragma unroll
-            for (int ch = 0; ch < 2; ++ch) {
-                const int cc = 64 * half + 32 * ch;              // first accumulator column of the chunk
-                const float nz = (ch == 0 ? nza : nzb) * nw;
-                uint32_t r[32];
-                tmem_ld32(t_row + 32 * ch, r);
-                tmem_ld_wait();
-                uint32_t packed[16];
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const float4 b4 = *reinterpret_cast<const float4 *>(&sm.e_bias[cc + j]);
-                    const float4 s4 = *reinterpret_cast<const float4 *>(&sm.e_next[cc + j]);
-                    float v0 = __uint_as_float(r[j + 0]) + nz + b4.x, v1 = __uint_as_float(r[j + 1]) + nz + b4.y;
-                    float v2 = __uint_as_float(r[j + 2]) + nz + b4.z, v3 = __uint_as_float(r[j + 3]) + nz + b4.w;
-                    v0 = fmaxf(v0, 0.2f * v0) * s4.x; v1 = fmaxf(v1, 0.2f * v1) * s4.y;
-                    v2 = fmaxf(v2, 0.2f * v2) * s4.z; v3 = fmaxf(v3, 0.2f * v3) * s4.w;
-                    __nv_bfloat162 h0 = __floats2bfloat162_rn(v0, v1), h1 = __floats2bfloat162_rn(v2, v3);
-                    packed[j / 2] = *reinterpret_cast<uint32_t *>(&h0);
-                    packed[j / 2 + 1] = *reinterpret_cast<uint32_t *>(&h1);
-                }
+            for (int ci = 0; ci < FT_CPW; ++ci) {
+                if (p.dbg & 4) break;
+                const int k = kq * FT_CPW + ci;                  // 32-column chunk of the tile
                 // stage this pixel's 64 bytes in the TMA layout of the store box
                 if (cbw == 64) {      // [128 px][128 B] per column block, SWIZZLE_128B: 16-byte chunk index XOR (row & 7)
-                    uint8_t *orow = sm.o + half * (128 * 128) + m * 128;
+                    const uint32_t orow = o_s + (uint32_t)((k >> 1) * (128 * 128) + m * 128);
 #pragma unroll
                     for (int v4 = 0; v4 < 4; ++v4)
-                        *reinterpret_cast<uint4 *>(orow + (((4 * ch + v4) ^ (m & 7)) << 4)) =
-                            make_uint4(packed[4 * v4], packed[4 * v4 + 1], packed[4 * v4 + 2], packed[4 * v4 + 3]);
+                        sts128(orow + (uint32_t)(((4 * (k & 1) + v4) ^ (m & 7)) << 4), packed[ci][4 * v4], packed[ci][4 * v4 + 1],
+                               packed[ci][4 * v4 + 2], packed[ci][4 * v4 + 3]);
                 } else {              // [128 px][64 B] per column block, SWIZZLE_64B: chunk index XOR ((row >> 1) & 3)
-                    uint8_t *orow = sm.o + (2 * half + ch) * (128 * 64) + m * 64;
+                    const uint32_t orow = o_s + (uint32_t)(k * (128 * 64) + m * 64);
 #pragma unroll
                     for (int v4 = 0; v4 < 4; ++v4)
-                        *reinterpret_cast<uint4 *>(orow + ((v4 ^ ((m >> 1) & 3)) << 4)) =
-                            make_uint4(packed[4 * v4], packed[4 * v4 + 1], packed[4 * v4 + 2], packed[4 * v4 + 3]);
+                        sts128(orow + (uint32_t)((v4 ^ ((m >> 1) & 3)) << 4), packed[ci][4 * v4], packed[ci][4 * v4 + 1],
+                               packed[ci][4 * v4 + 2], packed[ci][4 * v4 + 3]);
                 }
             }
-            tc_fence_before();
             fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.tmem_empty[acc]);
             // rows / columns / samples beyond the tensor are clipped by the TMA unit
-            if (p.store_mode == 0) {       // one thread stores whole column blocks (box cbw x 8 x 16)
-                asm volatile("bar.sync 3, 256;" ::: "memory");
+            if (p.dbg & 2) {
+            } else if (p.store_mode == 0) {       // one thread stores whole column blocks (box cbw x 8 x 16)
+                asm volatile("bar.sync 3, %0;" ::"n"(FT_EPI_THREADS) : "memory");
                 if (et == 0) {
                     for (int cb = 0; cb < ncb; ++cb)
                         tma_store_4d(&tmO, sm.o + cb * (128 * (int)row_bytes), t.ct * (cps * cbw) + (cb % cps) * cbw, t.x0, t.y0,
                                      t.n0 + cb / cps);
                     tma_store_commit();
                 }
-            } else if (lane == 0) {        // every warp stores its own 32 pixels (box cbw x 8 x 4)
+            } else if (FT_EPI_WARPS == 8 && lane == 0) {   // every warp stores its own 32 pixels (box cbw x 8 x 4)
+                const int cb_a = (64 * kq) / cbw, cb_b = (64 * kq + 32) / cbw;
                 if (cbw == 64) {
-                    tma_store_4d(&tmO, sm.o + half * (128 * 128) + q * 4096, t.ct * (cps * 64) + (cb_a % cps) * 64, t.x0,
-                                 t.y0 + 4 * q, t.n0 + ds_a);
+                    tma_store_4d(&tmO, sm.o + kq * (128 * 128) + q * 4096, t.ct * (cps * 64) + (cb_a % cps) * 64, t.x0,
+                                 t.y0 + 4 * q, t.n0 + cb_a / cps);
                 } else {
-                    tma_store_4d(&tmO, sm.o + cb_a * (128 * 64) + q * 2048, 0, t.x0, t.y0 + 4 * q, t.n0 + ds_a);
-                    tma_store_4d(&tmO, sm.o + cb_b * (128 * 64) + q * 2048, 0, t.x0, t.y0 + 4 * q, t.n0 + ds_b);
+                    tma_store_4d(&tmO, sm.o + cb_a * (128 * 64) + q * 2048, 0, t.x0, t.y0 + 4 * q, t.n0 + cb_a / cps);
+                    tma_store_4d(&tmO, sm.o + cb_b * (128 * 64) + q * 2048, 0, t.x0, t.y0 + 4 * q, t.n0 + cb_b / cps);
                 }
                 tma_store_commit();
             }
-            if (p.noise_prefetch) { nza = nza_n; nzb = nzb_n; }
+            if (p.noise_prefetch) {
+#pragma unroll
+                for (int ci = 0; ci < FT_CPW; ++ci) nzc[ci] = nzn[ci];
+            }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
         if (lane == 0) tma_store_wait_all();     // threads without outstanding stores return at once
@@ -373,6 +405,7 @@ int launch_upfir_tc(const UpfirTcParams &p, const CUtensorMap &tmK, const CUtens
     }
     SG2_REQUIRE((p.cbw == 64 || p.cbw == 32) && p.nsamp >= 1 && (FT_N / p.cbw) % p.nsamp == 0, SG2_ERR_BAD_ARG,
                 "upfir_tc: bad column blocking (cbw %d, %d samples per tile)", p.cbw, p.nsamp);
+    SG2_REQUIRE(p.store_mode == 0 || FT_EPI_WARPS == 8, SG2_ERR_BAD_ARG, "upfir_tc: per-warp stores need the 8-warp epilogue build");
     const int grid = p.total_tiles < sms ? p.total_tiles : sms;
     if (grid <= 0) return SG2_OK;
     upfir_tc_kernel<<<grid, FT_THREADS, smem, st>>>(p, tmK, tmT[0], tmT[1], tmT[2], tmT[3], tmO);

@@ -43,6 +43,7 @@ constexpr int kMaxStages = 8;
 
 struct __align__(1024) GemmSmem {
     uint8_t ring[kRingBytes];
+    uint8_t stg[kEpiWarps][2048];           // per-warp transposition buffers of the coalesced epilogue store
     float e_demod[kEpiCap];
     float e_next[kEpiCap];
     float e_wrgb[3][kEpiCap];
@@ -113,9 +114,10 @@ __device__ __forceinline__ float4 lds4(const float *p) {
 struct EpiTables { const float *demod, *next, *w0, *w1, *w2, *bias; };
 
 // W accumulator columns [c0, c0 + W) of one pixel row: TMEM -> registers -> epilogue math -> bf16 -> global.
+// off16: destination of this pixel's accumulator row in 16-byte units from p.out (0xFFFFFFFF: not stored)
 template <int W>
 __device__ __forceinline__ void epi_cols(const GemmParams &p, const EpiTables &e, uint32_t taddr, int c0, float nz,
-                                         __nv_bfloat16 *orow, float &rgb0, float &rgb1, float &rgb2) {
+                                         uint32_t off16, uint32_t stg, int lane, float &rgb0, float &rgb1, float &rgb2) {
     uint32_t r[W];
     tmem_ld_cols(taddr, r);
     tmem_ld_wait();
@@ -148,11 +150,17 @@ __device__ __forceinline__ void epi_cols(const GemmParams &p, const EpiTables &e
             packed[j / 2 + 1] = pack_bf16(__uint_as_float(r[j + 2]) * d4.z, __uint_as_float(r[j + 3]) * d4.w);
         }
     }
-    if (orow) {
-        uint4 *dst = reinterpret_cast<uint4 *>(orow + c0);
+    if (p.out == nullptr) return;             // last layer: only the ToRGB partial sums leave the kernel
+    const uint32_t o = off16 == 0xffffffffu ? off16 : off16 + (uint32_t)(c0 >> 3);
+    if constexpr (W == 32) {
+        store_rows64_coalesced(stg, packed, o, reinterpret_cast<uint8_t *>(p.out), lane);
+    } else {
+        if (o != 0xffffffffu) {
+            uint4 *dst = reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(p.out) + ((size_t)o << 4));
 #pragma unroll
-        for (int v4 = 0; v4 < W / 8; ++v4)
-            dst[v4] = make_uint4(packed[4 * v4], packed[4 * v4 + 1], packed[4 * v4 + 2], packed[4 * v4 + 3]);
+            for (int v4 = 0; v4 < W / 8; ++v4)
+                dst[v4] = make_uint4(packed[4 * v4], packed[4 * v4 + 1], packed[4 * v4 + 2], packed[4 * v4 + 3]);
+        }
     }
 }
 
@@ -244,7 +252,18 @@ modconv_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant_
                             mbar_wait(&sm.empty[stage], phase ^ 1);
                             uint8_t *slot = sm.ring + stage * stage_bytes;
                             const int ax = t.x0 + g.dx[tap], ay = t.y0 + g.dy[tap], wt = g.wtap[tap];
-                            if (elect_one()) {
+                            if (p.dbg & 6) {       // bottleneck analysis only
+                                if (elect_one()) {
+                                    const bool la = !(p.dbg & 2), lb = !(p.dbg & 4);
+                                    if (!la && !lb) mbar_arrive(&sm.full[stage]);
+                                    else mbar_arrive_expect_tx(&sm.full[stage], kpk * ((la ? a_bytes : 0u) + (lb ? b_bytes : 0u)));
+                                    for (uint32_t u = 0; u < kpk; ++u) {
+                                        if (la) tma_load_4d(slot + u * a_stage, tmA, &sm.full[stage], (kc + (int)u) * (int)bk, ax, ay, t.b0);
+                                        if (lb) tma_load_3d(slot + kpk * a_stage + u * b_bytes, &tmB, &sm.full[stage], (kc + (int)u) * (int)bk,
+                                                            t.nt * p.block_n, wt);
+                                    }
+                                }
+                            } else if (elect_one()) {
                                 mbar_arrive_expect_tx(&sm.full[stage], kpk * (a_bytes + b_bytes));
                                 tma_load_4d(slot, tmA, &sm.full[stage], kc * (int)bk, ax, ay, t.b0);
                                 tma_load_3d(slot + kpk * a_stage, &tmB, &sm.full[stage], kc * (int)bk, t.nt * p.block_n, wt);
@@ -335,6 +354,7 @@ modconv_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant_
                         if (elect_one()) {
                             // advance 32 bytes (>>4 = 2) inside the swizzle row per K = 16 step
                             umma_bf16(d_tmem, adesc, bdesc, idesc, k0 != 0);
+                            if (!(p.dbg & 8)) {
                             umma_bf16(d_tmem, adesc + 2, bdesc + 2, idesc, 1);
                             if (bk == 64) {
                                 umma_bf16(d_tmem, adesc + 4, bdesc + 4, idesc, 1);
@@ -346,6 +366,7 @@ modconv_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant_
                                 umma_bf16(d_tmem, a2 + 2, b2 + 2, idesc, 1);
                                 umma_bf16(d_tmem, a2 + 4, b2 + 4, idesc, 1);
                                 umma_bf16(d_tmem, a2 + 6, b2 + 6, idesc, 1);
+                            }
                             }
                             umma_commit(&sm.empty[stage]);       // frees the smem slot when these MMAs retire
                         }
@@ -369,6 +390,7 @@ modconv_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant_
         const bool alt = p.epi_alt != 0;
         const int half = alt ? 0 : grp;
         const int m = q * 32 + lane;                 // accumulator row = pixel of the tile
+        const uint32_t stg = smem_u32(sm.stg[warp - 2]);   // this warp's store staging buffer
         const int et = alt ? ((threadIdx.x - 64) & 127) : threadIdx.x - 64;   // thread index inside the staging group
         const int ethreads = alt ? 128 : 256, bar_id = alt ? 1 + grp : 1, step = alt ? 2 : 1;
         // staged per-(sample, channel) parameters: one copy per group in tile-split mode
@@ -436,9 +458,9 @@ modconv_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant_
                     staged_key = key;
                 }
                 const float nz = nz_cur * nw;
-                __nv_bfloat16 *orow = nullptr;
-                if (valid && p.out)
-                    orow = p.out + g.out_off + (((long long)b * g.out_H + y) * g.out_W + x) * p.Cout + n0;
+                uint32_t off16 = 0xffffffffu;
+                if (valid && p.out && !(p.dbg & 1))
+                    off16 = (uint32_t)((g.out_off + (((long long)b * g.out_H + y) * g.out_W + x) * p.Cout + n0) >> 3);
 
                 mbar_wait(&sm.tmem_full[acc], acc_phase);
                 tc_fence_after();
@@ -446,13 +468,13 @@ modconv_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant_
                 const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * acc_cols;
                 const EpiTables tab{e_demod + pb, e_next + pb, e_w0 + pb, e_w1 + pb, e_w2 + pb, e_bias};
                 if (alt) {            // this warp owns every column of the tile
-                    if (N == 16) epi_cols<16>(p, tab, t_row, 0, nz, orow, rgb0, rgb1, rgb2);
+                    if (N == 16) epi_cols<16>(p, tab, t_row, 0, nz, off16, stg, lane, rgb0, rgb1, rgb2);
                     else
-                        for (int c0 = 0; c0 < N; c0 += 32) epi_cols<32>(p, tab, t_row + c0, c0, nz, orow, rgb0, rgb1, rgb2);
+                        for (int c0 = 0; c0 < N; c0 += 32) epi_cols<32>(p, tab, t_row + c0, c0, nz, off16, stg, lane, rgb0, rgb1, rgb2);
                 } else if (N >= 64) {   // the two warps of a lane quarter alternate 32-column chunks
-                    for (int c0 = 32 * half; c0 < N; c0 += 64) epi_cols<32>(p, tab, t_row + c0, c0, nz, orow, rgb0, rgb1, rgb2);
+                    for (int c0 = 32 * half; c0 < N; c0 += 64) epi_cols<32>(p, tab, t_row + c0, c0, nz, off16, stg, lane, rgb0, rgb1, rgb2);
                 } else if (16 * half < N) {   // N = 32 / 16 with NB * N > 256: 16 columns per warp
-                    epi_cols<16>(p, tab, t_row + 16 * half, 16 * half, nz, orow, rgb0, rgb1, rgb2);
+                    epi_cols<16>(p, tab, t_row + 16 * half, 16 * half, nz, off16, stg, lane, rgb0, rgb1, rgb2);
                 }
                 tc_fence_before();
                 __syncwarp();

@@ -12,7 +12,8 @@ constexpr int kBlockM = 128;      // pixels per tile = TMEM lanes
 constexpr int kBlockK = 64;       // bf16 channels per stage = one 128-byte swizzle row
 constexpr int kStages = 4;
 constexpr int kMaxBlockN = 256;
-constexpr int kGemmRingBytes = 208 * 1024;   // operand ring of the single-CTA kernel (4 stages of 16 + 32 KiB at N = 256)
+constexpr int kGemmRingBytes = 196 * 1024;   // operand ring of the single-CTA kernel (4 stages of 16 + 32 KiB at N = 256; the
+                                             // 128->64 up-conv of the 1024^2 tail: 144 KiB resident weights + 3 x 17 KiB stages)
 
 // One polyphase sub-problem: an output plane [B, PH, PW, Cout] whose pixel (y, x) is
 // sum over taps t of  W[wtap[t]] . X[y + dy[t], x + dx[t], :]   (zero outside X).
@@ -45,6 +46,7 @@ struct GemmParams {
     // epilogue schedule of the single-CTA kernel: 1 = the two warp groups take alternate tiles (narrow BLOCK_N,
     // ONE ToRGB partial plane per N tile), 0 = they split the columns of every tile (two partial planes)
     int epi_alt;
+    int dbg;                        // SG2_GEMM_DBG knock-outs for bottleneck analysis (results WRONG when set): 1 no stores, 2 no A loads, 4 no B loads, 8 one MMA per stage
     // epilogue
     int mode;                       // 0: styled conv (noise, bias, lrelu, next-style, ToRGB); 1: plain scaled store
     const float *demod;             // [B, Cout]

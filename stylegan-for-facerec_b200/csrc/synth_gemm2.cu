@@ -58,6 +58,7 @@ constexpr int kMaxStages2 = 8;
 
 struct __align__(1024) Gemm2Smem {
     uint8_t ring[kRingBytes2];
+    uint8_t stg[kEpiWarps2][2048];          // per-warp transposition buffers of the coalesced epilogue store
     float e_demod[kEpiCap2];
     float e_next[kEpiCap2];
     float e_wrgb[3][kEpiCap2];
@@ -275,9 +276,9 @@ modconv_gemm2_kernel(const __grid_constant__ GemmParams p, const __grid_constant
                     staged_key = key;
                 }
                 nz *= nw;
-                __nv_bfloat16 *orow = nullptr;
+                uint32_t off16 = 0xffffffffu;     // this pixel's row in 16-byte units from p.out (0xFFFFFFFF: not stored)
                 if (valid && p.out)
-                    orow = p.out + g.out_off + (((long long)b * g.out_H + y) * g.out_W + x) * p.Cout + n0;
+                    off16 = (uint32_t)((g.out_off + (((long long)b * g.out_H + y) * g.out_W + x) * p.Cout + n0) >> 3);
 
                 mbar_wait(&sm.tmem_full[acc], acc_phase);
                 tc_fence_after();
@@ -291,9 +292,9 @@ modconv_gemm2_kernel(const __grid_constant__ GemmParams p, const __grid_constant
                     if (p.mode == 0) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
-                            const float4 d4 = *reinterpret_cast<const float4 *>(&sm.e_demod[pb + c0 + j]);
-                            const float4 b4 = *reinterpret_cast<const float4 *>(&sm.e_bias[c0 + j]);
-                            const float4 s4 = *reinterpret_cast<const float4 *>(&sm.e_next[pb + c0 + j]);
+                            const float4 d4 = lds128f(smem_u32(&sm.e_demod[pb + c0 + j]));
+                            const float4 b4 = lds128f(smem_u32(&sm.e_bias[c0 + j]));
+                            const float4 s4 = lds128f(smem_u32(&sm.e_next[pb + c0 + j]));
                             float v[4];
                             v[0] = fmaf(__uint_as_float(r[j + 0]), d4.x, nz) + b4.x;
                             v[1] = fmaf(__uint_as_float(r[j + 1]), d4.y, nz) + b4.y;
@@ -302,9 +303,9 @@ modconv_gemm2_kernel(const __grid_constant__ GemmParams p, const __grid_constant
 #pragma unroll
                             for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], kSlope2 * v[e]);   // lrelu (gain folded downstream)
                             if (p.rgb_w) {
-                                const float4 w0 = *reinterpret_cast<const float4 *>(&sm.e_wrgb[0][pb + c0 + j]);
-                                const float4 w1 = *reinterpret_cast<const float4 *>(&sm.e_wrgb[1][pb + c0 + j]);
-                                const float4 w2 = *reinterpret_cast<const float4 *>(&sm.e_wrgb[2][pb + c0 + j]);
+                                const float4 w0 = lds128f(smem_u32(&sm.e_wrgb[0][pb + c0 + j]));
+                                const float4 w1 = lds128f(smem_u32(&sm.e_wrgb[1][pb + c0 + j]));
+                                const float4 w2 = lds128f(smem_u32(&sm.e_wrgb[2][pb + c0 + j]));
                                 rgb0 += v[0] * w0.x + v[1] * w0.y + v[2] * w0.z + v[3] * w0.w;
                                 rgb1 += v[0] * w1.x + v[1] * w1.y + v[2] * w1.z + v[3] * w1.w;
                                 rgb2 += v[0] * w2.x + v[1] * w2.y + v[2] * w2.z + v[3] * w2.w;
@@ -315,17 +316,14 @@ modconv_gemm2_kernel(const __grid_constant__ GemmParams p, const __grid_constant
                     } else {
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
-                            const float4 d4 = *reinterpret_cast<const float4 *>(&sm.e_demod[pb + c0 + j]);
+                            const float4 d4 = lds128f(smem_u32(&sm.e_demod[pb + c0 + j]));
                             packed[j / 2 + 0] = pack_bf162(__uint_as_float(r[j + 0]) * d4.x, __uint_as_float(r[j + 1]) * d4.y);
                             packed[j / 2 + 1] = pack_bf162(__uint_as_float(r[j + 2]) * d4.z, __uint_as_float(r[j + 3]) * d4.w);
                         }
                     }
-                    if (orow) {
-                        uint4 *dst = reinterpret_cast<uint4 *>(orow + c0);
-#pragma unroll
-                        for (int v4 = 0; v4 < 4; ++v4)
-                            dst[v4] = make_uint4(packed[4 * v4], packed[4 * v4 + 1], packed[4 * v4 + 2], packed[4 * v4 + 3]);
-                    }
+                    if (p.out)
+                        store_rows64_coalesced(smem_u32(sm.stg[warp - 2]), packed, off16 == 0xffffffffu ? off16 : off16 + (uint32_t)(c0 >> 3),
+                                               reinterpret_cast<uint8_t *>(p.out), lane);
                 }
                 tc_fence_before();
                 __syncwarp();

@@ -30,60 +30,64 @@ __global__ void pack_rgb_weight_kernel(float *__restrict__ out, const float *__r
 }
 
 // ---- styles of every layer in one launch: s_l[b,ci] = latent[b, idx_l, :] . mod_w_l[ci,:] * scale + mod_b_l[ci]
-// Block = 8 input channels of one layer (one per warp, weight row in registers) x ALL samples; the
-// latent rows are staged through shared memory 16 samples at a time so the dot products read
-// shared memory instead of chaining global loads (the kernel is pure latency otherwise).
-constexpr int STY_SB = 16;
+// A small fp32 SGEMM per layer, [B, style_dim] x [style_dim, cin]: block = STY_CI input channels of one
+// layer x STY_SB samples, K staged through shared memory in chunks of STY_K; a thread owns one
+// channel x 8 samples, so the latent values are warp-wide broadcasts and the weight rows are read
+// conflict-free (row pitch STY_K + 4 floats).  Every weight is read from HBM once per sample tile.
+constexpr int STY_SB = 64, STY_CI = kStyleBlockCi, STY_K = 32, STY_PITCH = STY_K + 4;
+static_assert(STY_CI == 32 && STY_SB == 64, "styles_kernel: a warp spans the channel tile, 8 warps x 8 the sample tile");
 __global__ void __launch_bounds__(256)
 styles_kernel(StyleJobs jobs, const float *__restrict__ latent, int B, int n_latent, int style_dim) {
-    __shared__ float s_lat[STY_SB][512];                     // style_dim <= 512
+    __shared__ __align__(16) float s_lat[STY_SB][STY_PITCH];
+    __shared__ __align__(16) float s_w[STY_CI][STY_PITCH];
     int j = 0;
     while (j + 1 < jobs.n && (int)blockIdx.x >= jobs.job[j + 1].block_begin) ++j;
     const StyleJob &job = jobs.job[j];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int ci = ((int)blockIdx.x - job.block_begin) * 8 + warp;
-    const bool ci_ok = ci < job.cin;
-    float wr[16];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ci0 = ((int)blockIdx.x - job.block_begin) * STY_CI, b0 = (int)blockIdx.y * STY_SB;
+    const int ci = ci0 + lane;
+    float acc[8];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        const int idx = lane + 32 * k;
-        wr[k] = (ci_ok && idx < style_dim) ? __ldg(job.mod_w + (int64_t)ci * style_dim + idx) : 0.f;
-    }
-    const float bv = ci_ok ? __ldg(job.mod_b + ci) : 0.f;
-    const float scale = rsqrtf((float)style_dim);            // EqualLinear scale, lr_mul = 1 (model.py:144)
-    for (int b0 = 0; b0 < B; b0 += STY_SB) {
-        const int nb = min(STY_SB, B - b0);
+    for (int u = 0; u < 8; ++u) acc[u] = 0.f;
+    for (int k0 = 0; k0 < style_dim; k0 += STY_K) {
         __syncthreads();
-        for (int i = threadIdx.x; i < nb * style_dim; i += 256) {
-            const int sb = i / style_dim, k = i - sb * style_dim;
-            s_lat[sb][k] = __ldg(latent + ((int64_t)(b0 + sb) * n_latent + job.latent_index) * style_dim + k);
+        // stage: 64 latent rows x 32 k (8 floats per thread) and 32 weight rows x 32 k (4 per thread)
+#pragma unroll
+        for (int i = 0; i < (STY_SB * STY_K) / 256; ++i) {
+            const int e = tid + 256 * i, row = e / STY_K, k = e - row * STY_K;
+            const int b = b0 + row;
+            s_lat[row][k] = b < B ? __ldg(latent + ((int64_t)b * n_latent + job.latent_index) * style_dim + k0 + k) : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < (STY_CI * STY_K) / 256; ++i) {
+            const int e = tid + 256 * i, row = e / STY_K, k = e - row * STY_K;
+            s_w[row][k] = ci0 + row < job.cin ? __ldg(job.mod_w + (int64_t)(ci0 + row) * style_dim + k0 + k) : 0.f;
         }
         __syncthreads();
-        if (!ci_ok) continue;
-        for (int sb = 0; sb < nb; sb += 4) {                 // 4 independent reductions in flight
-            float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int r = sb + u < nb ? sb + u : nb - 1;
+        for (int k = 0; k < STY_K; k += 4) {
+            const float4 w4 = *reinterpret_cast<const float4 *>(&s_w[lane][k]);
 #pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    const int idx = lane + 32 * k;
-                    if (idx < style_dim) acc[u] += s_lat[r][idx] * wr[k];
-                }
+            for (int u = 0; u < 8; ++u) {
+                const float4 l4 = *reinterpret_cast<const float4 *>(&s_lat[warp + 8 * u][k]);
+                acc[u] = fmaf(l4.x, w4.x, fmaf(l4.y, w4.y, fmaf(l4.z, w4.z, fmaf(l4.w, w4.w, acc[u]))));
             }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) acc[u] = warp_sum(acc[u]);
-            if (lane < 4 && sb + lane < nb)
-                job.out[(int64_t)(b0 + sb + lane) * job.cin + ci] =
-                    (lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3]) * scale + bv;
         }
+    }
+    if (ci >= job.cin) return;
+    const float bv = __ldg(job.mod_b + ci);
+    const float scale = rsqrtf((float)style_dim);            // EqualLinear scale, lr_mul = 1 (model.py:144)
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const int b = b0 + warp + 8 * u;
+        if (b < B) job.out[(int64_t)b * job.cin + ci] = acc[u] * scale + bv;
     }
 }
 
 // ---- demod of every styled conv in one launch: d[b,co] = rsqrt(sum_ci s^2 * wsq[ci,co] + 1e-8)
 // block = 64 output channels x 4 slices of the input channels (reduced through shared memory) x
 // DEMOD_SB samples: each wsq element is loaded once for DEMOD_SB samples, 4x more loads in flight.
-constexpr int DEMOD_SB = 4, DEMOD_CO = 64;
+constexpr int DEMOD_SB = 8, DEMOD_CO = 64;
 __global__ void __launch_bounds__(256)
 demod_kernel(DemodJobs jobs, int B) {
     extern __shared__ float s_dm[];                          // [DEMOD_SB][cin] s^2, then [4][DEMOD_SB][64] partials
@@ -115,8 +119,8 @@ demod_kernel(DemodJobs jobs, int B) {
 #pragma unroll
     for (int sb = 0; sb < DEMOD_SB; ++sb) s_part[(slice * DEMOD_SB + sb) * DEMOD_CO + col] = acc[sb];
     __syncthreads();
-    if (threadIdx.x < DEMOD_SB * DEMOD_CO) {
-        const int sb = threadIdx.x / DEMOD_CO, c2 = threadIdx.x - sb * DEMOD_CO;
+    for (int o = threadIdx.x; o < DEMOD_SB * DEMOD_CO; o += 256) {
+        const int sb = o / DEMOD_CO, c2 = o - sb * DEMOD_CO;
         const int co2 = blockIdx.x * DEMOD_CO + c2;
         if (sb < nb && co2 < job.cout) {
             float t = 0.f;
@@ -263,27 +267,27 @@ rgb_combine_kernel(RgbParams p) {
                 v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
             }
             if (sp) {
-                // up=2, pad (2,1), 4x4 taps: same index math as upfirdn2d_kernel.cu:112-129
-                const int mid_y = Y - 1;
-                const int iy0 = fdiv2(mid_y), ky0 = (iy0 + 1) * 2 - mid_y - 1;
-                float up[4] = {0.f, 0.f, 0.f, 0.f};
+                // up=2, pad (2,1), 4x4 taps (index math of upfirdn2d_kernel.cu:112-129, specialised to a quad that
+                // starts at a multiple of 4): output row Y reads skip rows iy0, iy0+1 with tap rows ky0, ky0+2;
+                // the quad reads skip columns h-1 .. h+2 (h = X0/2) with tap columns (0,2) (1,3) (0,2) (1,3)
+                const int iy0 = fdiv2(Y - 1), ky0 = 2 * iy0 + 2 - Y, h = X0 >> 1;
+                float up0 = 0.f, up1 = 0.f, up2 = 0.f, up3 = 0.f;
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int mid_x = X0 + e - 1;
-                    const int ix0 = fdiv2(mid_x), kx0 = (ix0 + 1) * 2 - mid_x - 1;
+                for (int a2 = 0; a2 < 2; ++a2) {
+                    const int iy = iy0 + a2;
+                    if (iy < 0 || iy >= S) continue;
+                    const float *row = sp + iy * S;
+                    float k[4];             // tap row ky0 + 2*a2 (static indices: the taps stay in the constant bank)
 #pragma unroll
-                    for (int a2 = 0; a2 < 2; ++a2) {
-                        const int iy = iy0 + a2;
-                        if (iy < 0 || iy >= S) continue;
-#pragma unroll
-                        for (int b2 = 0; b2 < 2; ++b2) {
-                            const int ix = ix0 + b2;
-                            if (ix < 0 || ix >= S) continue;
-                            up[e] += __ldg(sp + iy * S + ix) * p.kf[(ky0 + 2 * a2) * 4 + kx0 + 2 * b2];
-                        }
-                    }
+                    for (int j = 0; j < 4; ++j) k[j] = ky0 ? p.kf[(1 + 2 * a2) * 4 + j] : p.kf[(2 * a2) * 4 + j];
+                    const float c0 = h >= 1 ? __ldg(row + h - 1) : 0.f, c1 = __ldg(row + h);
+                    const float c2 = h + 1 < S ? __ldg(row + h + 1) : 0.f, c3 = h + 2 < S ? __ldg(row + h + 2) : 0.f;
+                    up0 += k[0] * c0 + k[2] * c1;
+                    up1 += k[1] * c1 + k[3] * c2;
+                    up2 += k[0] * c1 + k[2] * c2;
+                    up3 += k[1] * c2 + k[3] * c3;
                 }
-                v.x += up[0]; v.y += up[1]; v.z += up[2]; v.w += up[3];
+                v.x += up0; v.y += up1; v.z += up2; v.w += up3;
             }
             *reinterpret_cast<float4 *>(p.out + i) = v;
         }
@@ -305,7 +309,8 @@ int launch_pack_rgb_weight(float *out, const float *w, int n, float scale, cudaS
 }
 int launch_styles(const StyleJobs &jobs, int total_blocks, const float *latent, int B, int n_latent, int style_dim,
                   cudaStream_t st) {
-    dim3 grid(total_blocks);
+    dim3 grid(total_blocks, (B + STY_SB - 1) / STY_SB);
+    SG2_REQUIRE(style_dim % STY_K == 0, SG2_ERR_UNSUPPORTED, "styles: style_dim %d is not a multiple of %d", style_dim, STY_K);
     styles_kernel<<<grid, 256, 0, st>>>(jobs, latent, B, n_latent, style_dim);
     SG2_LAUNCH_CHECK();
     return SG2_OK;

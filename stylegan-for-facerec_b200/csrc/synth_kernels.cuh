@@ -8,6 +8,7 @@
 namespace sg2 {
 
 constexpr int kMaxJobs = 40;   // 17 styled convs + 9 ToRGB at 1024^2
+constexpr int kStyleBlockCi = 32;   // input channels per block of styles_kernel
 
 struct StyleJob {
     const float *mod_w, *mod_b;   // [cin, style_dim], [cin]
@@ -42,6 +43,7 @@ struct UpfirTcParams {
     int tiles_x, tiles_y, tiles_c, total_tiles;   // tiles_c = channel groups per sample (C / 128, or 1)
     int store_mode;               // 0: one thread stores whole column blocks (box cbw x 8 x 16); 1: per-warp boxes cbw x 8 x 4
     int noise_prefetch;           // fetch the next tile's noise one iteration ahead
+    int dbg;                      // SG2_FIR_DBG knock-outs for bottleneck analysis (results are WRONG when set): 1 no loads, 2 no stores, 4 no epilogue math, 8 no MMA
     const float *noise; long long noise_bstride; const float *noise_weight;
     const float *bias;            // [C]
     const float *next_style;      // [B][C]

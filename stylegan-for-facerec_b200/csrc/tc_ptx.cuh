@@ -172,6 +172,48 @@ __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bu
 // make generic-proxy shared-memory writes visible to the async proxy (TMA, tcgen05)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// ---- coalesced epilogue store ------------------------------------------------------------------
+// A TMEM accumulator row lives in one lane (= one pixel), so a direct 16-byte store per lane touches
+// 32 different 128-byte lines per instruction (one LSU wavefront each, measured: up to 37 % of the
+// up-sampling GEMMs' time).  Instead every warp transposes its 32 pixels x 64 bytes through a private
+// 2 KiB staging buffer ([32 rows][64 B], 16-byte chunk index XOR ((row >> 1) & 3): conflict-free both
+// ways) and stores with 4 lanes per pixel: 8 x 64 contiguous bytes per instruction (whole sectors).
+// off16 = this lane's destination offset from out_base in 16-byte units, 0xFFFFFFFF = pixel not stored.
+// explicit shared-window accesses: pointers derived from the dynamic shared-memory base are generic to the
+// compiler (LD.E / ST.E in SASS); these keep the staging traffic on LDS / STS
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ float4 lds128f(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+
+__device__ __forceinline__ void store_rows64_coalesced(uint32_t stg /*shared-window address*/, const uint32_t (&packed)[16],
+                                                       uint32_t off16, uint8_t *out_base, int lane) {
+    const uint32_t sw = ((uint32_t)lane >> 1) & 3u;
+    const uint32_t row = stg + (uint32_t)lane * 64u;
+#pragma unroll
+    for (int v4 = 0; v4 < 4; ++v4)
+        sts128(row + ((((uint32_t)v4) ^ sw) << 4), packed[4 * v4], packed[4 * v4 + 1], packed[4 * v4 + 2], packed[4 * v4 + 3]);
+    __syncwarp();
+    const uint32_t c = (uint32_t)lane & 3u;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int px = i * 8 + (lane >> 2);
+        const uint4 val = lds128(stg + (uint32_t)px * 64u + ((c ^ (((uint32_t)px >> 1) & 3u)) << 4));
+        const uint32_t o = __shfl_sync(0xffffffffu, off16, px);
+        if (o != 0xffffffffu) *reinterpret_cast<uint4 *>(out_base + ((size_t)o << 4) + (c << 4)) = val;
+    }
+    __syncwarp();      // the next chunk overwrites the buffer
+}
+
 // ---- tcgen05 ------------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {   // whole warp
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),

@@ -10,6 +10,7 @@ them into the engine's bf16 layouts whenever they change.
 """
 import ctypes as C
 import os
+import weakref
 
 import torch
 
@@ -188,8 +189,14 @@ class SynthesisEngine:
         entry = self._graphs.get(key)
         if entry is None:
             s_lat = torch.empty(B, G.n_latent, G.style_dim, device=dev, dtype=torch.float32)
-            s_noise = [torch.empty(nb, 1, 2 ** ((i + 5) // 2), 2 ** ((i + 5) // 2), device=dev, dtype=torch.float32)
-                       for i, nb in enumerate(layout)]
+            # all static noise maps live in ONE flat buffer: a fully randomised forward refills it with one launch
+            shapes = [(nb, 1, 2 ** ((i + 5) // 2), 2 ** ((i + 5) // 2)) for i, nb in enumerate(layout)]
+            sizes = [s[0] * s[2] * s[3] for s in shapes]
+            s_flat = torch.empty(sum(sizes), device=dev, dtype=torch.float32)
+            s_noise, o = [], 0
+            for shp, n in zip(shapes, sizes):
+                s_noise.append(s_flat[o:o + n].view(shp))
+                o += n
             s_img = torch.empty(B, 3, G.size, G.size, device=dev, dtype=torch.float32)
             s_lat.copy_(latent)
             ptrs, strides, _ = self._noise_args(B, noise, dev, into=s_noise)
@@ -200,14 +207,39 @@ class SynthesisEngine:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 self._call(s_lat, B, ptrs, strides, s_img)
-            entry = (g, s_lat, s_noise, s_img, n_launch, (ptrs, strides))
+            entry = {"graph": g, "lat": s_lat, "noise": s_noise, "flat": s_flat, "img": s_img, "launches": n_launch,
+                     "args": (ptrs, strides), "src": [None] * len(s_noise)}
             self._graphs[key] = entry
-        g, s_lat, s_noise, s_img, n_launch, _ = entry
-        s_lat.copy_(latent)
-        self._noise_args(B, noise, dev, into=s_noise)
-        g.replay()
-        self.lib.sg2_note_launches(n_launch)                       # kernels launched by the graph replay
+        entry["lat"].copy_(latent)
+        self._stage_noise(entry, noise)
+        entry["graph"].replay()
+        self.lib.sg2_note_launches(entry["launches"])              # kernels launched by the graph replay
+        s_img = entry["img"]
         return s_img.clone() if out_dtype == torch.float32 else s_img.to(out_dtype)
+
+    @staticmethod
+    def _stage_noise(entry, noise):
+        """Bring the graph's static noise maps up to date: one normal_() over the flat buffer when every
+        layer draws fresh noise (model.py:283-285), no copy at all for caller tensors that have not
+        changed since they were last staged (the registered `noises` buffers of randomize_noise=False)."""
+        bufs, src = entry["noise"], entry["src"]
+        if noise is None or all(n is None for n in noise):
+            entry["flat"].normal_()
+            for i in range(len(src)):
+                src[i] = None
+            return
+        for i, buf in enumerate(bufs):
+            n = noise[i]
+            if n is None:
+                buf.normal_()
+                src[i] = None
+                continue
+            # same tensor OBJECT (weak reference: a dead source can never match, so a recycled address is
+            # not mistaken for it) at the same version -> the staged copy is still current
+            prev = src[i]
+            if prev is None or prev[0]() is not n or prev[1] != n._version:
+                buf.copy_(n.detach().reshape(buf.shape))
+                src[i] = (weakref.ref(n), n._version)
 
     def __del__(self):
         try:

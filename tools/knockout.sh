@@ -1,0 +1,16 @@
+#!/bin/bash
+# bottleneck analysis: per-kernel CUDA-event tables with parts of the FIR / GEMM kernels knocked out
+# (SG2_FIR_DBG / SG2_GEMM_DBG; results are wrong on purpose).  usage: tools/knockout.sh [size] [batch]
+SIZE=${1:-256}; BATCH=${2:-64}
+mkdir -p gpurun_out/ko
+run() { # name, env...
+  name=$1; shift
+  env "$@" timeout 200 python bench.py --size $SIZE --batch $BATCH --no-cpu-baseline --steps 5 --warmup 3 \
+      --profile-out gpurun_out/ko/$name.json > gpurun_out/ko/$name.log 2>&1 || echo "FAILED $name"
+}
+run base X=0
+for d in 1 2 4 8 3 7; do run fir$d SG2_FIR_DBG=$d; done
+run g1sm SG2_GEMM_2SM=0
+for d in 1 2 4 6 8 7 15; do run g1sm_dbg$d SG2_GEMM_2SM=0 SG2_GEMM_DBG=$d; done
+python tools/kcmp.py gpurun_out/ko/base.json gpurun_out/ko/fir*.json > gpurun_out/ko/fir_table.txt
+python tools/kcmp.py gpurun_out/ko/base.json gpurun_out/ko/g1sm*.json > gpurun_out/ko/gemm_table.txt
