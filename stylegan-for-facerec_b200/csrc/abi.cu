@@ -30,6 +30,19 @@ int sm_count() {
     return v;
 }
 
+void *tensor_map_encode_fn() {
+    static std::atomic<void *> fn{nullptr};
+    void *p = fn.load(std::memory_order_acquire);
+    if (!p) {
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        fn.store(p, std::memory_order_release);
+    }
+    return p;
+}
+
 }  // namespace sg2
 
 extern "C" int sg2_abi_version(void) { return SG2_ABI_VERSION; }

@@ -45,6 +45,8 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
 inline cudaStream_t as_stream(sg2_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 int sm_count();  // SMs of the current device (cached per device), 148 on B200
+// driver entry point of cuTensorMapEncodeTiled (cast to the driver's signature by the caller), or null
+void *tensor_map_encode_fn();
 
 // ---- dtype dispatch -----------------------------------------------------------------------------
 template <typename T> struct Cvt;

@@ -623,6 +623,7 @@ extern "C" int sg2_synth_forward(sg2_synth *S, void *workspace, const float *lat
                 tp.dbg = envd ? atoi(envd) : 0;
                 tp.noise = nz; tp.noise_bstride = nzs; tp.noise_weight = L.p.noise_weight;
                 tp.bias = L.p.act_bias; tp.next_style = up.next_style;
+                tp.toeplitz = (const __nv_bfloat16 *)(ws + S->off_toeplitz);
                 rc = launch_upfir_tc(tp, S->tmK, L.tmT, L.tmO, S->sms, st);
             }
             if (rc) return rc;

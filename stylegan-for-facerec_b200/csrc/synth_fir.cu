@@ -38,8 +38,16 @@ constexpr int FT_PLANE_ROWS = 64;                // 60 used + 4 zero pad rows
 constexpr int FT_K = 4 * FT_PLANE_ROWS;          // 256
 constexpr int FT_N = 128;                        // accumulator columns per tile
 constexpr int FT_STAGE_BYTES = FT_K * FT_N * 2;  // the window of one tile: 64 KiB whatever the column block width
-constexpr int FT_STAGES = 2;
-constexpr int FT_A_BYTES = 128 * FT_K * 2;       // 64 KiB Toeplitz
+// The Toeplitz matrix (A operand) lives in TENSOR MEMORY (128 lanes x 128 columns of packed bf16 pairs, written once
+// per CTA with tcgen05.st): the MMAs read only the window from shared memory.  The knock-out analysis showed the
+// kernel bound by the shared-memory port (per tile: 128 KiB of MMA operand reads + 61 KiB TMA fill + 32 KiB staging
+// + 32 KiB TMA-store reads at 128 B/clk); A-from-TMEM removes 64 KiB of that and frees 64 KiB for a third stage.
+#ifndef SG2_FIR_A_TMEM
+#define SG2_FIR_A_TMEM 0
+#endif
+constexpr int FT_STAGES = SG2_FIR_A_TMEM ? 3 : 2;
+constexpr int FT_A_BYTES = SG2_FIR_A_TMEM ? 16 : 128 * FT_K * 2;       // 64 KiB Toeplitz when it is a shared-memory operand
+constexpr int FT_TMEM_COLS = SG2_FIR_A_TMEM ? 512 : 256;                 // 2 accumulators (+ 128 columns of A)
 #ifndef SG2_FIR_EPI_WARPS
 #define SG2_FIR_EPI_WARPS 16
 #endif
@@ -50,9 +58,9 @@ constexpr int FT_THREADS = 64 + FT_EPI_THREADS;
 static_assert(FT_EPI_WARPS == 8 || FT_EPI_WARPS == 16, "epilogue: 2 or 4 warps per TMEM lane quarter");
 
 struct __align__(1024) FirSmem {
-    uint8_t a[FT_A_BYTES];
     uint8_t b[FT_STAGES * FT_STAGE_BYTES];
     uint8_t o[128 * FT_N * 2];                     // bf16 output tile [column block][128 px][cbw] in the TMA store layout
+    uint8_t a[FT_A_BYTES];                         // Toeplitz matrix when it is a shared-memory operand (else unused)
     float e_bias[FT_N];
     float e_next[FT_N];
     uint64_t a_full;
@@ -133,12 +141,34 @@ upfir_tc_kernel(const __grid_constant__ UpfirTcParams p, const __grid_constant__
         for (int i = 0; i < 2; ++i) { mbar_init(&sm.tmem_full[i], 1); mbar_init(&sm.tmem_empty[i], FT_EPI_WARPS); }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(&sm.tmem_base, 256);
+    if (warp == 1) tmem_alloc(&sm.tmem_base, FT_TMEM_COLS);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // pad-row zeros visible to the MMA (async proxy)
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = sm.tmem_base;
+#if SG2_FIR_A_TMEM
+    // Toeplitz matrix -> TMEM columns [256, 384): lane = output pixel m, column j = taps (2j, 2j+1) of its row.
+    // The first four epilogue warps cover the four lane quarters.
+    if (warp >= 2 && warp < 6) {
+        const int mrow = (warp & 3) * 32 + lane;
+        const uint4 *src = reinterpret_cast<const uint4 *>(p.toeplitz + (size_t)mrow * FT_K);
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+            uint32_t r[32];
+#pragma unroll
+            for (int v = 0; v < 8; ++v) {
+                const uint4 q4 = __ldg(src + ch * 8 + v);
+                r[4 * v] = q4.x; r[4 * v + 1] = q4.y; r[4 * v + 2] = q4.z; r[4 * v + 3] = q4.w;
+            }
+            tmem_st32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + 256u + 32u * ch, r);
+        }
+        tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+#endif
 
     // round-robin: at any moment the 148 CTAs work on ~5 adjacent tile rows, so the halo rows a tile
     // shares with its vertical neighbours are still in L2 when the neighbour loads them
@@ -147,7 +177,7 @@ upfir_tc_kernel(const __grid_constant__ UpfirTcParams p, const __grid_constant__
     if (warp == 0) {
         // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
         if (tile_lo < tile_hi) {
-            if (elect_one()) {      // Toeplitz matrix: 4 K-atoms of [128 rows][64 k] each
+            if (!SG2_FIR_A_TMEM && elect_one()) {      // Toeplitz matrix: 4 K-atoms of [128 rows][64 k] each
                 mbar_arrive_expect_tx(&sm.a_full, FT_A_BYTES);
                 for (int ka = 0; ka < 4; ++ka)
                     asm volatile(
@@ -195,7 +225,7 @@ upfir_tc_kernel(const __grid_constant__ UpfirTcParams p, const __grid_constant__
         if (tile_lo < tile_hi) {
             // kind::f16, D=f32, A=B=bf16, A K-major, B MN-major (bit 16), M=128, N=128
             const uint32_t idesc = make_idesc_bf16(128, FT_N) | (1u << 16);
-            mbar_wait(&sm.a_full, 0);
+            if (!SG2_FIR_A_TMEM) mbar_wait(&sm.a_full, 0);
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
             const uint32_t a_base = smem_u32(sm.a);
             const uint32_t kstep = (16 * row_bytes) >> 4;        // 16 K rows per MMA, in 16-byte units
@@ -209,8 +239,13 @@ upfir_tc_kernel(const __grid_constant__ UpfirTcParams p, const __grid_constant__
                 if (elect_one()) {
 #pragma unroll
                     for (int kk = 0; kk < ((p.dbg & 8) ? 1 : FT_K / 16); ++kk) {
+#if SG2_FIR_A_TMEM
+                        (void)adesc0;       // 16 taps = 8 TMEM columns per K step
+                        umma_bf16_ts(d_tmem, tmem_base + 256u + 8u * kk, bdesc0 + (uint64_t)(kk * kstep), idesc, kk != 0);
+#else
                         const uint64_t adesc = adesc0 + (uint64_t)(((kk >> 2) * 16384 + (kk & 3) * 32) >> 4);
                         umma_bf16(d_tmem, adesc, bdesc0 + (uint64_t)(kk * kstep), idesc, kk != 0);
+#endif
                     }
                     umma_commit(&sm.empty[stage]);
                     umma_commit(&sm.tmem_full[acc]);
@@ -372,7 +407,7 @@ upfir_tc_kernel(const __grid_constant__ UpfirTcParams p, const __grid_constant__
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, 256);
+    if (warp == 1) tmem_dealloc(tmem_base, FT_TMEM_COLS);
 }
 
 // host: Toeplitz matrix of the flipped taps kf[4][4] for the 16x8 tile, bf16 [128][256] row-major

@@ -47,6 +47,7 @@ struct UpfirTcParams {
     const float *noise; long long noise_bstride; const float *noise_weight;
     const float *bias;            // [C]
     const float *next_style;      // [B][C]
+    const __nv_bfloat16 *toeplitz; // [128][256] row-major Toeplitz matrix of the taps (copied into tensor memory)
 };
 
 struct RgbParams {

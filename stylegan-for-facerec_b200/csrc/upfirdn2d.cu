@@ -16,6 +16,8 @@
 //   * everything else (up/down <= 4, taps <= 16x16, minor > 1) goes through a generic kernel
 //     with the same staging; configurations outside that return SG2_ERR_UNSUPPORTED instead of
 //     uninitialised memory (:172-268 of the reference has no default case).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace sg2 {
@@ -270,6 +272,10 @@ static int launch_poly(void *out, const void *x, const float *taps, int64_t plan
     return SG2_OK;
 }
 
+template <typename T>
+int launch_upfirdn2d_stream(void *out, const void *x, const float *taps, int64_t planes, int in_h, int in_w, int out_h,
+                            int out_w, int kh, int kw, int up, int down, int pad_x0, int pad_y0, cudaStream_t st);
+
 }  // namespace sg2
 
 using namespace sg2;
@@ -308,6 +314,14 @@ extern "C" int sg2_upfirdn2d(void *out, const void *x, const float *kernel, int6
             upfirdn2d_small_kernel<T><<<blocks, 256, 0, st>>>((T *)out, (const T *)x, kernel, p);
             SG2_LAUNCH_CHECK();
             return SG2_OK;
+        }
+        if (sym) {   // the three model geometries: row-streaming TMA kernel (upfirdn2d_stream.cu); 1 = not applicable
+            static const char *env_tiled = getenv("SG2_UPFIRDN_TILED");     // A/B switch: force the tiled kernels
+            if (!env_tiled || atoi(env_tiled) == 0) {
+                const int rc = launch_upfirdn2d_stream<T>(out, x, kernel, major, in_h, in_w, out_h, out_w, kh, kw, up_x, down_x,
+                                                          pad_x0, pad_y0, st);
+                if (rc <= 0) return rc;
+            }
         }
         if (sym && up_x == 1 && down_x == 1)
             return launch_poly<T, 1, 1, 4, 4>(out, x, kernel, major, in_h, in_w, out_h, out_w, kh, kw, pad_x0, pad_y0, st);

@@ -1,0 +1,366 @@
+// upfirdn2d_stream.cu -- the op-API upfirdn2d (NCHW planes, minor == 1, <= 4x4 taps, the three
+// geometries the model uses: blur 1/1, skip up-sample 2/1, down-sample 1/2) as a ROW-STREAMING stencil.
+//
+// Replaces upfirdn2d_kernel (op/upfirdn2d_kernel.cu:52-137 of the reference; same definition: zero
+// insertion, pad / crop, true convolution = correlation with the flipped taps, decimation) for the
+// shapes that carry the bytes.  The first version of this op staged 2-D tiles through shared memory
+// behind block-wide barriers and sat at 12-55 % of the HBM roofline (profiles/opbench_r01.jsonl);
+// the bound is HBM, so the kernel is organised around keeping bytes in flight, not around tiles:
+//
+//   * a warp owns a vertical strip (4 output columns per lane) of one plane and walks DOWN it;
+//   * input rows are fetched with plain coalesced loads US_PF rows ahead (register prefetch ring), any
+//     row pitch / base alignment (the 257-wide blur input has neither a 16-byte pitch nor aligned rows;
+//     TMA tiles need 16-byte aligned box starts -- tools/probes/tma_probe.cu -- so they cannot express
+//     this access), converted to fp32 and staged in a per-warp line buffer from which every lane reads
+//     its window with 16-byte loads;
+//   * every input row is read from HBM once per band; it updates the <= 4 output rows it contributes
+//     to (accumulators in registers, polyphase taps resolved at compile time: no multiplies by the
+//     inserted zeros) and the finished output row leaves with one 8/16-byte store per lane;
+//   * no block-wide barrier anywhere: warps run independently (__syncwarp only).
+//
+// fp32 accumulation for every storage dtype; per output the taps are applied in the same order as
+// the reference kernel (rows, then columns), so fp32 results match it to the last bits.
+#include <stdlib.h>
+
+#include <algorithm>
+#include <type_traits>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace sg2 {
+
+using namespace tc;
+
+constexpr int US_PF = 4;         // input rows in flight per warp (registers)
+constexpr int US_WARPS = 8;
+constexpr int US_THREADS = 32 * US_WARPS;
+
+struct UfdStreamParams {
+    int in_h, in_w, out_h, out_w;
+    int pad_x0, pad_y0, kh, kw;
+    int wl_log2;          // lanes per group (3..5): a group of 1 << wl_log2 lanes owns one strip
+    int rh;               // output rows per band (even)
+    int n_strips, n_bands;
+    long long items;      // planes * n_strips * n_bands
+    int line_floats;      // shared-memory pitch of one staged row (multiple of 4)
+    int vec_store;        // output rows are aligned for one vector store per lane
+};
+
+template <int UP, int DOWN>
+struct SGeo {
+    static constexpr int LS = UP == 2 ? 2 : 4 * DOWN;               // input elements between the windows of adjacent lanes
+    static constexpr int WU = UP == 2 ? 4 : 3 * DOWN + 4;           // window elements used (7 / 10 / 4)
+    static constexpr int WR = UP == 2 ? 4 : (DOWN == 1 ? 8 : 12);   // window elements read (vector loads)
+    static constexpr int R = DOWN == 2 ? 2 : 4;                     // output rows in flight
+    static constexpr int PERIOD = UP == 2 ? 2 : 4;                  // input rows after which the slot pattern repeats
+};
+
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
+    return v;
+}
+
+// WR elements of T starting at shared address addr (aligned to ALIGN bytes) -> fp32
+template <typename T, int WR, int ALIGN>
+__device__ __forceinline__ void load_window(uint32_t addr, float (&w)[WR]) {
+    constexpr int NW = WR * (int)sizeof(T) / 4;                   // 32-bit words
+    constexpr int V = ALIGN % 16 == 0 ? 4 : (ALIGN % 8 == 0 ? 2 : 1);   // words per load
+    constexpr int FULL = NW / V, TAIL = NW % V;
+    static_assert(TAIL == 0 || TAIL == 2, "window tail");
+    uint32_t u[NW];
+#pragma unroll
+    for (int i = 0; i < FULL; ++i) {
+        if constexpr (V == 4) {
+            const uint4 q = lds128(addr + 16 * i);
+            u[4 * i] = q.x; u[4 * i + 1] = q.y; u[4 * i + 2] = q.z; u[4 * i + 3] = q.w;
+        } else if constexpr (V == 2) {
+            const uint2 q = lds64(addr + 8 * i);
+            u[2 * i] = q.x; u[2 * i + 1] = q.y;
+        } else {
+            u[i] = lds32(addr + 4 * i);
+        }
+    }
+    if constexpr (TAIL == 2) {
+        const uint2 q = lds64(addr + 4 * V * FULL);
+        u[V * FULL] = q.x; u[V * FULL + 1] = q.y;
+    }
+    if constexpr (sizeof(T) == 4) {
+#pragma unroll
+        for (int j = 0; j < WR; ++j) w[j] = __uint_as_float(u[j]);
+    } else if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+#pragma unroll
+        for (int j = 0; j < NW; ++j) {
+            w[2 * j] = __uint_as_float(u[j] << 16);
+            w[2 * j + 1] = __uint_as_float(u[j] & 0xffff0000u);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < NW; ++j) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&u[j]));
+            w[2 * j] = f.x; w[2 * j + 1] = f.y;
+        }
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ void store4(T *dst, const float (&v)[4], int n_ok, bool vec) {
+    if (vec && n_ok == 4) {
+        if constexpr (sizeof(T) == 4) {
+            *reinterpret_cast<float4 *>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+        } else {
+            T pk[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) pk[i] = Cvt<T>::from_f(v[i]);
+            *reinterpret_cast<uint2 *>(dst) = *reinterpret_cast<const uint2 *>(pk);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (i < n_ok) dst[i] = Cvt<T>::from_f(v[i]);
+    }
+}
+
+// PHX / PHY: parity of (pad_x0, pad_y0) for UP == 2 (which polyphase pattern a 4-aligned output column /
+// an even output row starts with); unused (0) otherwise.
+template <typename T, int UP, int DOWN, int PHX, int PHY>
+__global__ void __launch_bounds__(US_THREADS)
+upfirdn2d_stream_kernel(T *__restrict__ out, const T *__restrict__ x, const float *__restrict__ taps, const UfdStreamParams p) {
+    using G = SGeo<UP, DOWN>;
+    constexpr int NI = G::LS + 1;                                  // loads per lane per row: ceil(line / lanes), lanes >= 8
+    extern __shared__ __align__(16) float us_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int WL = 1 << p.wl_log2, NS = 32 >> p.wl_log2;
+    const int g = lane >> p.wl_log2, t = lane & (WL - 1);         // group of the lane, lane inside the group
+    const int line_len = (WL - 1) * G::LS + G::WR;                 // staged elements of one row
+    // per warp: two line buffers (row s is staged while the windows of row s - 1 may still be read) x NS groups
+    float *wbase = us_smem + (size_t)warp * (2 * NS * p.line_floats);
+    const uint32_t ring_s = smem_u32(wbase);
+
+    // flipped taps, zero padded to 4 x 4 (upfirdn2d_kernel.cu:71-81): kf[a][b] multiplies the sample a rows / b
+    // columns after the first one of the (up-sampled, padded) window
+    float kf[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+            kf[a][b] = (a < p.kh && b < p.kw) ? __ldg(taps + (p.kh - 1 - a) * p.kw + (p.kw - 1 - b)) : 0.f;
+
+    const long long plane_in = (long long)p.in_h * p.in_w, plane_out = (long long)p.out_h * p.out_w;
+    const long long total_groups = (long long)gridDim.x * US_WARPS * NS;
+    const long long gid0 = ((long long)blockIdx.x * US_WARPS + warp) * NS + g;
+
+    for (long long item0 = gid0 - g; item0 < p.items; item0 += total_groups) {   // warp-uniform trip count
+        const long long item = item0 + g;
+        const bool active = item < p.items;
+        // item -> (plane, band, strip), strip fastest
+        long long rest = active ? item : 0;
+        const int strip = (int)(rest % p.n_strips); rest /= p.n_strips;
+        const int band = (int)(rest % p.n_bands);
+        const long long plane = rest / p.n_bands;
+        const int xs0 = strip * (WL * 4), y0 = band * p.rh, y1 = min(p.out_h, y0 + p.rh);
+        const int nrows = y1 - y0;
+        // first input row / column of the strip and number of input rows to walk
+        int iy_first, cx0, nsteps;
+        if (UP == 1) {
+            iy_first = DOWN * y0 - p.pad_y0;
+            cx0 = DOWN * xs0 - p.pad_x0;
+            nsteps = DOWN * (nrows - 1) + 4;
+        } else {
+            iy_first = (y0 - p.pad_y0 + PHY) / 2;                  // exact: y0 - pad_y0 + PHY is even
+            cx0 = (xs0 - p.pad_x0 + PHX) / 2;
+            nsteps = (nrows + 2 - PHY) / 2 + 1;                    // rows Y = y0 + PHY + 2s <= y1 + 2
+        }
+        if (!active) nsteps = 0;
+        int nsteps_max = nsteps;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) nsteps_max = max(nsteps_max, __shfl_xor_sync(0xffffffffu, nsteps_max, o));
+
+        // this lane stages line positions t + WL*i: which of them exist / lie inside the plane (row invariant)
+        uint32_t in_line = 0, in_plane = 0;
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+            const int pos = t + WL * i, col = cx0 + pos;
+            if (pos < line_len) in_line |= 1u << i;
+            if (pos < line_len && col >= 0 && col < p.in_w) in_plane |= 1u << i;
+        }
+        const T *xp = x + plane * plane_in + cx0 + t;             // (row 0, position t); only dereferenced where valid
+
+        // ---- register prefetch ring: US_PF rows in flight ----
+        T pre[US_PF][NI];
+        auto fetch = [&](int s, T (&r)[NI]) {
+            const int iy = iy_first + s;
+            const bool row_ok = s < nsteps && iy >= 0 && iy < p.in_h;
+            const T *rp = xp + (long long)iy * p.in_w;
+#pragma unroll
+            for (int i = 0; i < NI; ++i) r[i] = (row_ok && ((in_plane >> i) & 1u)) ? __ldg(rp + WL * i) : Cvt<T>::from_f(0.f);
+        };
+#pragma unroll
+        for (int d = 0; d < US_PF; ++d) fetch(d, pre[d]);
+
+        float acc[G::R][4];
+#pragma unroll
+        for (int r = 0; r < G::R; ++r)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[r][i] = 0.f;
+        T *oplane = out + plane * plane_out;
+        const int x0 = xs0 + 4 * t;
+        const int n_ok = active ? max(0, min(4, p.out_w - x0)) : 0;
+
+        for (int sb = 0; sb < nsteps_max; sb += US_PF) {
+#pragma unroll
+            for (int u = 0; u < US_PF; ++u) {
+                const int s = sb + u;
+                if (s >= nsteps_max) break;
+                // stage row s (fp32) in line buffer s & 1, refill its register slot with row s + US_PF
+                const uint32_t line = ring_s + (uint32_t)(((u & 1) * NS + g) * p.line_floats) * 4u;
+#pragma unroll
+                for (int i = 0; i < NI; ++i)
+                    if ((in_line >> i) & 1u) wbase[((u & 1) * NS + g) * p.line_floats + t + WL * i] = Cvt<T>::to_f(pre[u][i]);
+                __syncwarp();
+                fetch(s + US_PF, pre[u]);
+                float w[G::WR];
+                load_window<float, G::WR, G::LS * 4>(line + (uint32_t)(t * G::LS * 4), w);
+
+                if constexpr (UP == 1 && DOWN == 1) {
+                    // input row s feeds tap row a of output row (s - a); ring slot (s - a) & 3 = (u - a) & 3
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) {
+                        const int r = (u - a + 4) & 3;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            float v = a == 0 ? 0.f : acc[r][i];
+#pragma unroll
+                            for (int b = 0; b < 4; ++b) v = fmaf(w[i + b], kf[a][b], v);
+                            acc[r][i] = v;
+                        }
+                    }
+                    const int ol = s - 3;                          // finished: output row y0 + s - 3
+                    if (ol >= 0 && ol < nrows && n_ok > 0)
+                        store4<T>(oplane + (long long)(y0 + ol) * p.out_w + x0, acc[(u + 1) & 3], n_ok, p.vec_store != 0);
+                } else if constexpr (UP == 1 && DOWN == 2) {
+                    // input row s feeds tap rows a = (s & 1), (s & 1) + 2 of output rows (s - a) / 2
+                    const int e = u & 1;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int a = e + 2 * h;
+                        const int r = (((u - a) / 2) + 2) & 1;     // (s - a) / 2 mod 2 with s = sb + u, sb % 4 == 0
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            float v = a == 0 ? 0.f : acc[r][i];
+#pragma unroll
+                            for (int b = 0; b < 4; ++b) v = fmaf(w[2 * i + b], kf[a][b], v);
+                            acc[r][i] = v;
+                        }
+                    }
+                    if (e == 1) {                                  // tap row 3 done: output row (s - 3) / 2 is finished
+                        const int ol = (s - 3) / 2;
+                        if (s >= 3 && ol < nrows && n_ok > 0)
+                            store4<T>(oplane + (long long)(y0 + ol) * p.out_w + x0, acc[(((u - 3) / 2) + 2) & 1], n_ok,
+                                      p.vec_store != 0);
+                    }
+                } else {
+                    // UP == 2: input row s sits at up-sampled row Y = y0 + PHY + 2s and feeds tap row a of output row
+                    // Y - a; local row index ol = 2s + 3 - a (0 = y0 + PHY - 3), ring slot ol & 3 = (2u + 3 - a) & 3.
+                    // Window element c sits at up-sampled column x0 + PHX + 2c and feeds tap b of output i = 2c + PHX - b.
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) {
+                        const int r = (2 * u + 3 - a) & 3;
+                        float v[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) v[i] = a < 2 ? 0.f : acc[r][i];   // a row starts with tap row 0 or 1
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+#pragma unroll
+                            for (int b = 0; b < 4; ++b) {
+                                const int i = 2 * c + PHX - b;
+                                if (i >= 0 && i < 4) v[i] = fmaf(w[c], kf[a][b], v[i]);
+                            }
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) acc[r][i] = v[i];
+                    }
+                    // finished: tap rows 3 and 2 -> output rows Y - 3 and Y - 2
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int oy = y0 + PHY + 2 * s - 3 + h;
+                        if (oy >= y0 && oy < y1 && n_ok > 0)
+                            store4<T>(oplane + (long long)oy * p.out_w + x0, acc[(2 * u + h) & 3], n_ok, p.vec_store != 0);
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ---- host ------------------------------------------------------------------------------------------
+template <typename T, int UP, int DOWN, int PHX, int PHY>
+static int launch_stream_t(void *out, const void *x, const float *taps, const UfdStreamParams &p, int grid, size_t smem,
+                           cudaStream_t st) {
+    upfirdn2d_stream_kernel<T, UP, DOWN, PHX, PHY><<<grid, US_THREADS, smem, st>>>((T *)out, (const T *)x, taps, p);
+    SG2_LAUNCH_CHECK();
+    return SG2_OK;
+}
+
+static bool us_debug() {
+    static const char *e = getenv("SG2_US_DEBUG");
+    return e && atoi(e);
+}
+
+// Returns SG2_OK when the launch was made, 1 when this path does not apply (the caller falls back to the
+// tiled kernels), another status on errors.
+template <typename T>
+int launch_upfirdn2d_stream(void *out, const void *x, const float *taps, int64_t planes, int in_h, int in_w, int out_h,
+                            int out_w, int kh, int kw, int up, int down, int pad_x0, int pad_y0, cudaStream_t st) {
+    if (!((up == 1 && (down == 1 || down == 2)) || (up == 2 && down == 1)) || kh > 4 || kw > 4) return 1;
+    UfdStreamParams p;
+    p.in_h = in_h; p.in_w = in_w; p.out_h = out_h; p.out_w = out_w;
+    p.pad_x0 = pad_x0; p.pad_y0 = pad_y0; p.kh = kh; p.kw = kw;
+    // lanes per strip: 4 output columns per lane (the 8-inputs-per-lane down-sampling window stays at 16 lanes: 9
+    // prefetch registers per row)
+    int wl = 3;
+    while ((4 << wl) < out_w && wl < (down == 2 ? 4 : 5)) ++wl;
+    p.wl_log2 = wl;
+    const int WL = 1 << wl, NS = 32 >> wl;
+    const int LS = up == 2 ? 2 : 4 * down, WR = up == 2 ? 4 : (down == 1 ? 8 : 12);
+    p.line_floats = ((WL - 1) * LS + WR + 3) & ~3;
+    p.n_strips = (out_w + 4 * WL - 1) / (4 * WL);
+    // band height: tall enough to amortise the vertical halo, short enough for >= 4 items per resident group
+    const int sms = sm_count();
+    const int64_t groups = (int64_t)sms * 4 * US_WARPS * NS;
+    int rh = 128;
+    while (rh > 16 && planes * p.n_strips * ((out_h + rh - 1) / rh) < 4 * groups) rh /= 2;
+    p.rh = rh;
+    p.n_bands = (out_h + rh - 1) / rh;
+    p.items = planes * p.n_strips * p.n_bands;
+    const int es = (int)sizeof(T);
+    p.vec_store = (out_w % 4 == 0 && reinterpret_cast<uintptr_t>(out) % (4 * es) == 0) ? 1 : 0;
+    const size_t smem = (size_t)US_WARPS * 2 * NS * p.line_floats * sizeof(float);
+    const int64_t want = (p.items + (int64_t)US_WARPS * NS - 1) / ((int64_t)US_WARPS * NS);
+    const int grid = (int)std::min<int64_t>(want, (int64_t)sms * 4);
+    if (grid <= 0) return SG2_OK;
+    if (us_debug())
+        fprintf(stderr, "[sg2 upfirdn2d_stream] up %d down %d, %lld planes %dx%d -> %dx%d, %d lanes per strip, bands of %d rows, "
+                        "%lld items, grid %d\n", up, down, (long long)planes, in_h, in_w, out_h, out_w, WL, p.rh, p.items, grid);
+    const int phx = up == 2 ? (pad_x0 & 1) : 0, phy = up == 2 ? (pad_y0 & 1) : 0;
+    if (up == 1 && down == 1) return launch_stream_t<T, 1, 1, 0, 0>(out, x, taps, p, grid, smem, st);
+    if (up == 1 && down == 2) return launch_stream_t<T, 1, 2, 0, 0>(out, x, taps, p, grid, smem, st);
+    if (phx == 0 && phy == 0) return launch_stream_t<T, 2, 1, 0, 0>(out, x, taps, p, grid, smem, st);
+    if (phx == 1 && phy == 0) return launch_stream_t<T, 2, 1, 1, 0>(out, x, taps, p, grid, smem, st);
+    if (phx == 0 && phy == 1) return launch_stream_t<T, 2, 1, 0, 1>(out, x, taps, p, grid, smem, st);
+    return launch_stream_t<T, 2, 1, 1, 1>(out, x, taps, p, grid, smem, st);
+}
+
+template int launch_upfirdn2d_stream<float>(void *, const void *, const float *, int64_t, int, int, int, int, int, int, int, int,
+                                            int, int, cudaStream_t);
+template int launch_upfirdn2d_stream<__half>(void *, const void *, const float *, int64_t, int, int, int, int, int, int, int, int,
+                                             int, int, cudaStream_t);
+template int launch_upfirdn2d_stream<__nv_bfloat16>(void *, const void *, const float *, int64_t, int, int, int, int, int, int,
+                                                    int, int, int, int, cudaStream_t);
+
+}  // namespace sg2

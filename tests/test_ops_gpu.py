@@ -116,6 +116,12 @@ UFD_SWEEP = [
     ((1, 3, 40, 24), 4, 2, 1, (3, 0)), ((1, 2, 31, 31), 5, 1, 1, (2, 2)), ((1, 2, 20, 20), 6, 3, 1, (3, 2)),
     ((1, 2, 20, 20), 4, 2, 2, (1, 1)), ((1, 2, 30, 30), 7, 1, 3, (3, 3)), ((2, 2, 16, 16), 4, 1, 1, (-1, -1)),
     ((1, 1, 9, 9), 1, 1, 1, (0, 0)), ((1, 2, 12, 12), 12, 1, 1, (6, 5)), ((1, 2, 16, 16), 4, 4, 1, (3, 0)),
+    # row-streaming kernel: several strips / bands / groups per warp, odd pitches (1-D TMA view), every pad parity
+    ((1, 2, 300, 300), 4, 1, 1, (1, 1)), ((3, 2, 131, 259), 4, 1, 1, (2, 2)), ((2, 3, 40, 20), 4, 1, 1, (1, 1)),
+    ((1, 2, 270, 136), 3, 1, 1, (0, 2)), ((2, 2, 150, 72), 4, 2, 1, (2, 1)), ((1, 3, 150, 72), 4, 2, 1, (1, 2)),
+    ((1, 2, 67, 67), 4, 2, 1, (3, 0)), ((1, 2, 130, 30), 2, 2, 1, (0, 1)), ((2, 2, 260, 264), 4, 1, 2, (1, 1)),
+    ((1, 3, 129, 67), 4, 1, 2, (2, 2)), ((1, 2, 64, 520), 4, 1, 2, (0, 1)), ((5, 7, 17, 17), 4, 1, 1, (1, 1)),
+    ((4, 9, 32, 32), 4, 2, 1, (2, 1)), ((4, 9, 64, 64), 4, 1, 2, (1, 1)), ((1, 1, 1030, 1030), 4, 1, 1, (1, 1)),
 ]
 
 
@@ -128,6 +134,31 @@ def test_upfirdn2d_sweep_vs_oracle(sg2, oracle, shape, k, up, down, pad):
     ref = oracle.upfirdn2d(x.double(), taps.double(), up, down, pad).float()
     assert y.shape == ref.shape
     np.testing.assert_allclose(y.numpy(), ref.numpy(), rtol=0, atol=2e-5 * k)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("shape,up,down,pad", [((2, 3, 257, 257), 1, 1, (1, 1)), ((2, 3, 128, 128), 2, 1, (2, 1)),
+                                               ((2, 3, 256, 256), 1, 2, (1, 1)), ((1, 2, 131, 70), 1, 1, (2, 2)),
+                                               ((1, 2, 37, 45), 2, 1, (1, 2)), ((1, 2, 77, 141), 1, 2, (2, 2))])
+def test_upfirdn2d_streaming_low_precision(sg2, oracle, dtype, shape, up, down, pad):
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(shape, generator=g).to(dtype)
+    taps = torch.randn(4, 4, generator=g)
+    y = sg2.upfirdn2d(x.to(DEV), taps.to(DEV), up, down, pad)
+    assert y.dtype == dtype
+    ref = oracle.upfirdn2d(x.double(), taps.double(), up, down, pad)
+    tol = _tol(dtype) * float(ref.abs().max())
+    np.testing.assert_allclose(y.float().cpu().numpy(), ref.float().numpy(), rtol=0, atol=tol)
+
+
+def test_upfirdn2d_unaligned_base_falls_back(sg2, oracle):
+    # a storage offset of one element: not 16-byte aligned -> the TMA path declines, the tiled kernel answers
+    big = torch.randn(2 * 3 * 100 * 100 + 1, device=DEV)
+    x = big[1:].view(2, 3, 100, 100)
+    taps = torch.randn(4, 4)
+    y = sg2.upfirdn2d(x, taps.to(DEV), 1, 1, (1, 1)).cpu()
+    ref = oracle.upfirdn2d(x.cpu().double(), taps.double(), 1, 1, (1, 1)).float()
+    np.testing.assert_allclose(y.numpy(), ref.numpy(), rtol=0, atol=1e-4)
 
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
