@@ -43,6 +43,22 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "which": "fallback"}
 
 
+def ncu_traffic(size, batch):
+    """DRAM bytes (read + write) per step of the dominant kernel, from the committed `ncu --set full` capture of one
+    forward at this size / batch (profiles/ncu_full_*_summary.json, written by tools/ncu_summary.py): -> (bytes, file)."""
+    import glob
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", f"ncu_full_r*_{size}_b{batch}_summary.json")), reverse=True):
+        try:
+            rows = json.load(open(path))
+        except Exception:
+            continue
+        gemm = [r for r in rows if "modconv_gemm" in r.get("kernel", "")]
+        if gemm:
+            tot = sum(r["dram__bytes_read.sum"]["value"] + r["dram__bytes_write.sum"]["value"] for r in gemm)
+            return tot, os.path.relpath(path, ROOT), len(gemm)
+    return None, None, 0
+
+
 class ClockSampler:
     """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -260,9 +276,14 @@ def main():
         fl, tt = sum(r["flops"] for r in gemm), sum(r["s"] for r in gemm)
         total = sum(r["s"] for r in table)
         peak = peaks["bf16_tflops_sustained"]
+        traffic, traffic_src, traffic_n = ncu_traffic(args.size, B)
         roofline = {"bound": "tensor", "kernel": "modconv_gemm_kernel (tcgen05 implicit GEMM, all launches of one step)",
                     "achieved": round(fl / tt / 1e12, 2), "peak": peak, "unit": "TFLOP/s", "frac": round(fl / tt / 1e12 / peak, 4),
-                    "traffic": None, "peak_source": f"{peaks['which']} bf16_tflops_sustained (kernel timed inside a long step)",
+                    "traffic": traffic, "traffic_unit": "DRAM bytes per step (read + write), all launches of the kernel",
+                    "traffic_source": traffic_src if traffic_n == len(gemm) else
+                    (f"{traffic_src}: {traffic_n} launches captured, {len(gemm)} in the plan" if traffic_src else None),
+                    "algorithmic_bytes_per_step": sum(r["bytes"] for r in gemm),
+                    "peak_source": f"{peaks['which']} bf16_tflops_sustained (kernel timed inside a long step)",
                     "share_of_step": round(tt / total, 4), "launches_per_step": len(gemm),
                     "algorithmic_flops_per_step": fl}
         fir = [r for r in table if r["kind"] == "upfir"]

@@ -61,8 +61,7 @@ struct __align__(1024) FirSmem {
     uint8_t b[FT_STAGES * FT_STAGE_BYTES];
     uint8_t o[128 * FT_N * 2];                     // bf16 output tile [column block][128 px][cbw] in the TMA store layout
     uint8_t a[FT_A_BYTES];                         // Toeplitz matrix when it is a shared-memory operand (else unused)
-    float e_bias[FT_N];
-    float e_next[FT_N];
+    float2 e_tab[2][FT_N];                         // {bias, sqrt(2) * style of the consumer} per column, double buffered by tile parity
     uint64_t a_full;
     uint64_t full[FT_STAGES], empty[FT_STAGES];
     uint64_t tmem_full[2], tmem_empty[2];
@@ -116,8 +115,11 @@ upfir_tc_kernel(const __grid_constant__ UpfirTcParams p, const __grid_constant__
                 const __grid_constant__ CUtensorMap tmT0, const __grid_constant__ CUtensorMap tmT1,
                 const __grid_constant__ CUtensorMap tmT2, const __grid_constant__ CUtensorMap tmT3,
                 const __grid_constant__ CUtensorMap tmO) {
-    extern __shared__ uint8_t smem_raw[];
-    FirSmem &sm = *reinterpret_cast<FirSmem *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // the kernel has no static shared memory: the dynamic window starts at the CTA's shared base, which satisfies the
+    // declared 1 KiB alignment (swizzle atoms); checked once, because every byte of the 227 KiB is spoken for
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    FirSmem &sm = *reinterpret_cast<FirSmem *>(smem_raw);
+    if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cbw = p.cbw, ncb = FT_N / cbw;                 // column block width (channels) and count
     const uint32_t row_bytes = (uint32_t)cbw * 2, cb_bytes = FT_K * row_bytes;
@@ -265,7 +267,7 @@ upfir_tc_kernel(const __grid_constant__ UpfirTcParams p, const __grid_constant__
         const int m = q * 32 + lane;                 // output pixel of the tile: (m / 8, m % 8)
         const int oy = m >> 3, ox = m & 7;
         const int et = threadIdx.x - 64;
-        const uint32_t e_bias_s = smem_u32(sm.e_bias), e_next_s = smem_u32(sm.e_next), o_s = smem_u32(sm.o);
+        const uint32_t e_tab_s = smem_u32(sm.e_tab), o_s = smem_u32(sm.o);
         const int R = 2 * p.r;
         const float nw = p.noise ? __ldg(p.noise_weight) : 0.f;
         // the sample behind each of this warp's chunks
@@ -277,42 +279,50 @@ upfir_tc_kernel(const __grid_constant__ UpfirTcParams p, const __grid_constant__
             if (p.noise && Y < R && X < R && n < p.B) return __ldg(p.noise + (long long)n * p.noise_bstride + (long long)Y * R + X);
             return 0.f;
         };
-        uint32_t acc = 0, acc_phase = 0;
-        int staged_key = -1;
-        float nzc[FT_CPW], nzn[FT_CPW];
+        // column et of the tile (threads et < 128): {bias, sqrt(2) * consumer style} of tile tt
+        const int tcb = (et & (FT_N - 1)) / cbw, tcol = (et & (FT_N - 1)) - tcb * cbw;
+        auto params_at = [&](const FirTile &tt) -> float2 {
+            const int c = tt.ct * (cps * cbw) + (tcb % cps) * cbw + tcol;
+            const int n = min(tt.n0 + tcb / cps, p.B - 1);
+            return make_float2(__ldg(p.bias + c), 1.41421356237f * __ldg(p.next_style + (long long)n * p.C + c));
+        };
+        // Per-thread loads (noise, epilogue parameters) queue behind the ~120 KiB of TMA loads this SM keeps in flight
+        // (ncu: they were the top two stall reasons at a distance of one tile), so both are fetched TWO tiles ahead:
+        // q0 = this tile, q1 = next tile, the loads issued in this iteration are for the tile after that.
+        uint32_t acc = 0, acc_phase = 0, it = 0;
+        float nq0[FT_CPW], nq1[FT_CPW], nqf[FT_CPW];
+        float2 pq1 = make_float2(0.f, 0.f), pqf = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int ci = 0; ci < FT_CPW; ++ci) nzc[ci] = nzn[ci] = 0.f;
-        FirWalk w;
+        for (int ci = 0; ci < FT_CPW; ++ci) nq0[ci] = nq1[ci] = nqf[ci] = 0.f;
+        FirWalk w, wp;
         w.init(p, tile_lo, tile_step);
-        if (tile_lo < tile_hi && p.noise_prefetch) {
-            const FirTile t0 = w.tile(p);
+        wp = w;
+        if (tile_lo < tile_hi) {
+            const FirTile t0 = wp.tile(p);
+            wp.next(p);
 #pragma unroll
-            for (int ci = 0; ci < FT_CPW; ++ci) nzc[ci] = (ci > 0 && ds[ci] == ds[0]) ? nzc[0] : noise_at(t0, ds[ci]);
+            for (int ci = 0; ci < FT_CPW; ++ci) nq0[ci] = (ci > 0 && ds[ci] == ds[0]) ? nq0[0] : noise_at(t0, ds[ci]);
+            if (et < FT_N) sm.e_tab[0][et] = params_at(t0);
+            if (tile_lo + tile_step < tile_hi) {
+                const FirTile t1 = wp.tile(p);
+#pragma unroll
+                for (int ci = 0; ci < FT_CPW; ++ci) nq1[ci] = (ci > 0 && ds[ci] == ds[0]) ? nq1[0] : noise_at(t1, ds[ci]);
+                if (et < FT_N) pq1 = params_at(t1);
+            }
+            wp.next(p);
+            asm volatile("bar.sync 1, %0;" ::"n"(FT_EPI_THREADS) : "memory");   // tile 0's table is staged
         }
-        for (int tile = tile_lo; tile < tile_hi; tile += tile_step) {
+        for (int tile = tile_lo; tile < tile_hi; tile += tile_step, ++it) {
             const FirTile t = w.tile(p);
             w.next(p);
-            // noise of the NEXT tile: fetched now, consumed one iteration later
-            if (!p.noise_prefetch) {
+            if (tile + 2 * tile_step < tile_hi) {                // two tiles ahead
+                const FirTile tf = wp.tile(p);
 #pragma unroll
-                for (int ci = 0; ci < FT_CPW; ++ci) nzc[ci] = (ci > 0 && ds[ci] == ds[0]) ? nzc[0] : noise_at(t, ds[ci]);
-            } else if (tile + tile_step < tile_hi) {
-                const FirTile tn = w.tile(p);
-#pragma unroll
-                for (int ci = 0; ci < FT_CPW; ++ci) nzn[ci] = (ci > 0 && ds[ci] == ds[0]) ? nzn[0] : noise_at(tn, ds[ci]);
+                for (int ci = 0; ci < FT_CPW; ++ci) nqf[ci] = (ci > 0 && ds[ci] == ds[0]) ? nqf[0] : noise_at(tf, ds[ci]);
+                if (et < FT_N) pqf = params_at(tf);
             }
-            const int key = t.n0 * 64 + t.ct;
-            if (key != staged_key) {
-                asm volatile("bar.sync 1, %0;" ::"n"(FT_EPI_THREADS) : "memory");
-                for (int j = et; j < FT_N; j += FT_EPI_THREADS) {
-                    const int cb = j / cbw, c = t.ct * (cps * cbw) + (cb % cps) * cbw + (j - cb * cbw);
-                    const int n = min(t.n0 + cb / cps, p.B - 1);
-                    sm.e_bias[j] = __ldg(p.bias + c);
-                    sm.e_next[j] = 1.41421356237f * __ldg(p.next_style + (long long)n * p.C + c);
-                }
-                asm volatile("bar.sync 1, %0;" ::"n"(FT_EPI_THREADS) : "memory");
-                staged_key = key;
-            }
+            wp.next(p);
+            const uint32_t tab_s = e_tab_s + (it & 1u) * (uint32_t)(FT_N * sizeof(float2));
             mbar_wait(&sm.tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * FT_N;
@@ -323,14 +333,15 @@ upfir_tc_kernel(const __grid_constant__ UpfirTcParams p, const __grid_constant__
             for (int ci = 0; ci < FT_CPW; ++ci) {
                 if (p.dbg & 4) break;
                 const int cc = 32 * (kq * FT_CPW + ci);          // first accumulator column of the chunk
-                const float2 nz2 = make_float2(nzc[ci] * nw, nzc[ci] * nw);
+                const float2 nz2 = make_float2(nq0[ci] * nw, nq0[ci] * nw);
                 uint32_t r[32];
                 tmem_ld32(t_row + cc, r);
                 tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
-                    const float4 b4 = lds128f(e_bias_s + (uint32_t)(cc + j) * 4u);
-                    const float4 s4 = lds128f(e_next_s + (uint32_t)(cc + j) * 4u);
+                    // {bias, style} pairs of columns cc+j .. cc+j+3
+                    const float4 t01 = lds128f(tab_s + (uint32_t)(cc + j) * 8u), t23 = lds128f(tab_s + (uint32_t)(cc + j) * 8u + 16u);
+                    const float4 b4 = make_float4(t01.x, t01.z, t23.x, t23.z), s4 = make_float4(t01.y, t01.w, t23.y, t23.w);
                     // (acc + noise + bias) -> lrelu -> x style of the consumer, two columns per instruction
                     float2 a = __fadd2_rn(__fadd2_rn(make_float2(__uint_as_float(r[j + 0]), __uint_as_float(r[j + 1])), nz2),
                                           make_float2(b4.x, b4.y));
@@ -375,10 +386,12 @@ upfir_tc_kernel(const __grid_constant__ UpfirTcParams p, const __grid_constant__
                                packed[ci][4 * v4 + 2], packed[ci][4 * v4 + 3]);
                 }
             }
+            if (et < FT_N) sm.e_tab[(it + 1) & 1u][et] = pq1;     // the next tile's table (read after this tile's last barrier)
             fence_proxy_async();
             // rows / columns / samples beyond the tensor are clipped by the TMA unit
+            if ((p.dbg & 2) || p.store_mode != 0) asm volatile("bar.sync 1, %0;" ::"n"(FT_EPI_THREADS) : "memory");   // table hand-over
             if (p.dbg & 2) {
-            } else if (p.store_mode == 0) {       // one thread stores whole column blocks (box cbw x 8 x 16)
+            } else if (p.store_mode == 0) {       // one thread stores whole column blocks (box cbw x 8 x 16); its barrier hands over the table
                 asm volatile("bar.sync 3, %0;" ::"n"(FT_EPI_THREADS) : "memory");
                 if (et == 0) {
                     for (int cb = 0; cb < ncb; ++cb)
@@ -397,10 +410,9 @@ upfir_tc_kernel(const __grid_constant__ UpfirTcParams p, const __grid_constant__
                 }
                 tma_store_commit();
             }
-            if (p.noise_prefetch) {
 #pragma unroll
-                for (int ci = 0; ci < FT_CPW; ++ci) nzc[ci] = nzn[ci];
-            }
+            for (int ci = 0; ci < FT_CPW; ++ci) { nq0[ci] = nq1[ci]; nq1[ci] = nqf[ci]; }
+            pq1 = pqf;
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
         if (lane == 0) tma_store_wait_all();     // threads without outstanding stores return at once
@@ -431,8 +443,8 @@ void build_fir_toeplitz(uint16_t *out, const float *kf) {
 
 int launch_upfir_tc(const UpfirTcParams &p, const CUtensorMap &tmK, const CUtensorMap *tmT, const CUtensorMap &tmO,
                     int sms, cudaStream_t st) {
-    static_assert(sizeof(FirSmem) + 1024 <= 227 * 1024, "FirSmem exceeds the 227 KiB CTA limit");
-    const size_t smem = sizeof(FirSmem) + 1024;
+    static_assert(sizeof(FirSmem) <= 227 * 1024, "FirSmem exceeds the 227 KiB CTA limit");
+    const size_t smem = sizeof(FirSmem);
     static std::atomic<int> configured{0};
     if (!configured.load(std::memory_order_acquire)) {
         SG2_CUDA_OK(cudaFuncSetAttribute(upfir_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

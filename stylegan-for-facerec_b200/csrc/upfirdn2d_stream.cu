@@ -32,6 +32,9 @@ namespace sg2 {
 
 using namespace tc;
 
+#ifndef SG2_US_PACKED
+#define SG2_US_PACKED 0      // blur: packed f32x2 FMAs over output pairs (measured slower: the pair-building moves eat the saved issue slots)
+#endif
 constexpr int US_PF = 4;         // input rows in flight per warp (registers)
 constexpr int US_WARPS = 8;
 constexpr int US_THREADS = 32 * US_WARPS;
@@ -40,6 +43,7 @@ struct UfdStreamParams {
     int in_h, in_w, out_h, out_w;
     int pad_x0, pad_y0, kh, kw;
     int wl_log2;          // lanes per group (3..5): a group of 1 << wl_log2 lanes owns one strip
+    long long planes;
     int rh;               // output rows per band (even)
     int n_strips, n_bands;
     long long items;      // planes * n_strips * n_bands
@@ -129,16 +133,20 @@ __device__ __forceinline__ void store4(T *dst, const float (&v)[4], int n_ok, bo
 
 // PHX / PHY: parity of (pad_x0, pad_y0) for UP == 2 (which polyphase pattern a 4-aligned output column /
 // an even output row starts with); unused (0) otherwise.
-template <typename T, int UP, int DOWN, int PHX, int PHY>
+// WLOG2: lanes per strip (log2) -- a template parameter so that the strided row loads take immediate offsets.
+template <typename T, int UP, int DOWN, int PHX, int PHY, int WLOG2>
 __global__ void __launch_bounds__(US_THREADS)
 upfirdn2d_stream_kernel(T *__restrict__ out, const T *__restrict__ x, const float *__restrict__ taps, const UfdStreamParams p) {
     using G = SGeo<UP, DOWN>;
     constexpr int NI = G::LS + 1;                                  // loads per lane per row: ceil(line / lanes), lanes >= 8
     extern __shared__ __align__(16) float us_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int WL = 1 << p.wl_log2, NS = 32 >> p.wl_log2;
-    const int g = lane >> p.wl_log2, t = lane & (WL - 1);         // group of the lane, lane inside the group
-    const int line_len = (WL - 1) * G::LS + G::WR;                 // staged elements of one row
+    constexpr int WL = 1 << WLOG2, NS = 32 >> WLOG2;
+    const int g = lane >> WLOG2, t = lane & (WL - 1);              // group of the lane, lane inside the group
+    constexpr int line_len = (WL - 1) * G::LS + G::WR;             // staged elements of one row
+    // positions t + WL*i, i < LS, always exist (WL*LS - 1 < line_len); the last one only for the first lanes
+    static_assert(G::LS - 1 < G::WR, "line layout");
+    const bool has_last = t < G::WR - G::LS;
     // per warp: two line buffers (row s is staged while the windows of row s - 1 may still be read) x NS groups
     float *wbase = us_smem + (size_t)warp * (2 * NS * p.line_floats);
     const uint32_t ring_s = smem_u32(wbase);
@@ -152,6 +160,13 @@ upfirdn2d_stream_kernel(T *__restrict__ out, const T *__restrict__ x, const floa
         for (int b = 0; b < 4; ++b)
             kf[a][b] = (a < p.kh && b < p.kw) ? __ldg(taps + (p.kh - 1 - a) * p.kw + (p.kw - 1 - b)) : 0.f;
 
+#if SG2_US_PACKED
+    float2 kf2[4][4];                                              // (tap, tap): the multiplier pair of the packed FMAs
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) kf2[a][b] = make_float2(kf[a][b], kf[a][b]);
+#endif
     const long long plane_in = (long long)p.in_h * p.in_w, plane_out = (long long)p.out_h * p.out_w;
     const long long total_groups = (long long)gridDim.x * US_WARPS * NS;
     const long long gid0 = ((long long)blockIdx.x * US_WARPS + warp) * NS + g;
@@ -182,15 +197,19 @@ upfirdn2d_stream_kernel(T *__restrict__ out, const T *__restrict__ x, const floa
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) nsteps_max = max(nsteps_max, __shfl_xor_sync(0xffffffffu, nsteps_max, o));
 
-        // this lane stages line positions t + WL*i: which of them exist / lie inside the plane (row invariant)
-        uint32_t in_line = 0, in_plane = 0;
+        // this lane stages line positions t + WL*i: which of them exist but lie OUTSIDE the plane (row invariant).
+        // Rows are fetched without per-column predicates -- a column outside the plane reads a neighbouring row's
+        // element, which a fix-up then overwrites with zero in the staged line -- except for the two rows whose
+        // over-read would leave the tensor (first row of the first plane, last row of the last plane).
+        uint32_t outside = 0;
 #pragma unroll
         for (int i = 0; i < NI; ++i) {
             const int pos = t + WL * i, col = cx0 + pos;
-            if (pos < line_len) in_line |= 1u << i;
-            if (pos < line_len && col >= 0 && col < p.in_w) in_plane |= 1u << i;
+            if ((i < G::LS || has_last) && (col < 0 || col >= p.in_w)) outside |= 1u << i;
         }
-        const T *xp = x + plane * plane_in + cx0 + t;             // (row 0, position t); only dereferenced where valid
+        const bool guard_first = plane == 0 && cx0 < 0;
+        const bool guard_last = plane == p.planes - 1 && cx0 + line_len > p.in_w;
+        const T *xp = x + plane * plane_in + cx0 + t;             // (row 0, position t)
 
         // ---- register prefetch ring: US_PF rows in flight ----
         T pre[US_PF][NI];
@@ -198,8 +217,18 @@ upfirdn2d_stream_kernel(T *__restrict__ out, const T *__restrict__ x, const floa
             const int iy = iy_first + s;
             const bool row_ok = s < nsteps && iy >= 0 && iy < p.in_h;
             const T *rp = xp + (long long)iy * p.in_w;
+            if (!row_ok) {
 #pragma unroll
-            for (int i = 0; i < NI; ++i) r[i] = (row_ok && ((in_plane >> i) & 1u)) ? __ldg(rp + WL * i) : Cvt<T>::from_f(0.f);
+                for (int i = 0; i < NI; ++i) r[i] = Cvt<T>::from_f(0.f);
+            } else if ((guard_first && iy == 0) || (guard_last && iy == p.in_h - 1)) {
+#pragma unroll
+                for (int i = 0; i < NI; ++i)
+                    r[i] = ((i < G::LS || has_last) && !((outside >> i) & 1u)) ? __ldg(rp + WL * i) : Cvt<T>::from_f(0.f);
+            } else {
+#pragma unroll
+                for (int i = 0; i < G::LS; ++i) r[i] = __ldg(rp + WL * i);
+                r[G::LS] = has_last ? __ldg(rp + WL * G::LS) : Cvt<T>::from_f(0.f);
+            }
         };
 #pragma unroll
         for (int d = 0; d < US_PF; ++d) fetch(d, pre[d]);
@@ -220,9 +249,15 @@ upfirdn2d_stream_kernel(T *__restrict__ out, const T *__restrict__ x, const floa
                 if (s >= nsteps_max) break;
                 // stage row s (fp32) in line buffer s & 1, refill its register slot with row s + US_PF
                 const uint32_t line = ring_s + (uint32_t)(((u & 1) * NS + g) * p.line_floats) * 4u;
+                float *lp = wbase + ((u & 1) * NS + g) * p.line_floats + t;
 #pragma unroll
-                for (int i = 0; i < NI; ++i)
-                    if ((in_line >> i) & 1u) wbase[((u & 1) * NS + g) * p.line_floats + t + WL * i] = Cvt<T>::to_f(pre[u][i]);
+                for (int i = 0; i < G::LS; ++i) lp[WL * i] = Cvt<T>::to_f(pre[u][i]);
+                if (has_last) lp[WL * G::LS] = Cvt<T>::to_f(pre[u][G::LS]);
+                if (outside) {                                     // zero padding: few lanes, border strips only
+#pragma unroll
+                    for (int i = 0; i < NI; ++i)
+                        if ((outside >> i) & 1u) lp[WL * i] = 0.f;
+                }
                 __syncwarp();
                 fetch(s + US_PF, pre[u]);
                 float w[G::WR];
@@ -230,6 +265,26 @@ upfirdn2d_stream_kernel(T *__restrict__ out, const T *__restrict__ x, const floa
 
                 if constexpr (UP == 1 && DOWN == 1) {
                     // input row s feeds tap row a of output row (s - a); ring slot (s - a) & 3 = (u - a) & 3
+                    // packed f32x2 FMAs over output pairs (0,1) and (2,3): half the FMA issue slots (the kernel is issue
+                    // bound: 16 FMAs per output are 73 % of the FP32 pipe at the bf16 HBM roofline); per output the taps
+                    // are still applied in ascending order, each lane of the pair is an ordinary fused multiply-add
+#if SG2_US_PACKED
+                    float2 wp[6];
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) wp[j] = make_float2(w[j], w[j + 1]);
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) {
+                        const int r = (u - a + 4) & 3;
+                        float2 v01 = a == 0 ? make_float2(0.f, 0.f) : make_float2(acc[r][0], acc[r][1]);
+                        float2 v23 = a == 0 ? make_float2(0.f, 0.f) : make_float2(acc[r][2], acc[r][3]);
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) {
+                            v01 = __ffma2_rn(wp[b], kf2[a][b], v01);
+                            v23 = __ffma2_rn(wp[b + 2], kf2[a][b], v23);
+                        }
+                        acc[r][0] = v01.x; acc[r][1] = v01.y; acc[r][2] = v23.x; acc[r][3] = v23.y;
+                    }
+#else
 #pragma unroll
                     for (int a = 0; a < 4; ++a) {
                         const int r = (u - a + 4) & 3;
@@ -241,6 +296,7 @@ upfirdn2d_stream_kernel(T *__restrict__ out, const T *__restrict__ x, const floa
                             acc[r][i] = v;
                         }
                     }
+#endif
                     const int ol = s - 3;                          // finished: output row y0 + s - 3
                     if (ol >= 0 && ol < nrows && n_ok > 0)
                         store4<T>(oplane + (long long)(y0 + ol) * p.out_w + x0, acc[(u + 1) & 3], n_ok, p.vec_store != 0);
@@ -302,7 +358,15 @@ upfirdn2d_stream_kernel(T *__restrict__ out, const T *__restrict__ x, const floa
 template <typename T, int UP, int DOWN, int PHX, int PHY>
 static int launch_stream_t(void *out, const void *x, const float *taps, const UfdStreamParams &p, int grid, size_t smem,
                            cudaStream_t st) {
-    upfirdn2d_stream_kernel<T, UP, DOWN, PHX, PHY><<<grid, US_THREADS, smem, st>>>((T *)out, (const T *)x, taps, p);
+    T *o = (T *)out;
+    const T *xi = (const T *)x;
+    switch (p.wl_log2) {
+        case 3: upfirdn2d_stream_kernel<T, UP, DOWN, PHX, PHY, 3><<<grid, US_THREADS, smem, st>>>(o, xi, taps, p); break;
+        case 4: upfirdn2d_stream_kernel<T, UP, DOWN, PHX, PHY, 4><<<grid, US_THREADS, smem, st>>>(o, xi, taps, p); break;
+        default:
+            if constexpr (DOWN == 2) { set_error("upfirdn2d_stream: bad strip width"); return SG2_ERR_BAD_ARG; }
+            else upfirdn2d_stream_kernel<T, UP, DOWN, PHX, PHY, 5><<<grid, US_THREADS, smem, st>>>(o, xi, taps, p);
+    }
     SG2_LAUNCH_CHECK();
     return SG2_OK;
 }
@@ -326,6 +390,7 @@ int launch_upfirdn2d_stream(void *out, const void *x, const float *taps, int64_t
     int wl = 3;
     while ((4 << wl) < out_w && wl < (down == 2 ? 4 : 5)) ++wl;
     p.wl_log2 = wl;
+    p.planes = planes;
     const int WL = 1 << wl, NS = 32 >> wl;
     const int LS = up == 2 ? 2 : 4 * down, WR = up == 2 ? 4 : (down == 1 ? 8 : 12);
     p.line_floats = ((WL - 1) * LS + WR + 3) & ~3;
@@ -333,8 +398,8 @@ int launch_upfirdn2d_stream(void *out, const void *x, const float *taps, int64_t
     // band height: tall enough to amortise the vertical halo, short enough for >= 4 items per resident group
     const int sms = sm_count();
     const int64_t groups = (int64_t)sms * 4 * US_WARPS * NS;
-    int rh = 128;
-    while (rh > 16 && planes * p.n_strips * ((out_h + rh - 1) / rh) < 4 * groups) rh /= 2;
+    int rh = 128;                                                   // tallest band that still gives every resident group two items
+    while (rh > 16 && planes * p.n_strips * ((out_h + rh - 1) / rh) < 2 * groups) rh /= 2;
     p.rh = rh;
     p.n_bands = (out_h + rh - 1) / rh;
     p.items = planes * p.n_strips * p.n_bands;
