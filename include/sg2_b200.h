@@ -134,6 +134,35 @@ int sg2_torgb_combine(void *out, const void *conv, const void *bias, const void 
                       int H, int W, int dtype, sg2_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * StyleGAN2-ADA variant of the decoder (restyle-encoder/models/stylegan2_ada, selected by psp.py:24-30).
+ *
+ * sg2_smooth_upsample2x  <- SmoothUpsample.forward (stylegan2_ada/utils.py:76-95): nearest x2, replication pad
+ *   (2,1,2,1), 4x4 correlation with `taps` (fp32, 16 values, row-major, NOT flipped), fused with what follows it
+ *   in SynthesisLayer2.forward (generator.py:198-204) / SynthesisBlock.forward (generator.py:134-137):
+ *     out = clamp( act( up(x) + noise * noise_strength[0] + bias[c] + addend ) * gain, -clamp, clamp )
+ *   x [B,C,H,W] -> out [B,C,2H,2W]; noise [B or 1,1,2H,2W] (noise_bstride = 4*H*W or 0), bias [C], addend
+ *   [B,C,2H,2W] may each be NULL; act: 1 linear, 3 leaky-relu(alpha); clamp <= 0 disables the clamp.
+ * sg2_ada_bias_act  <- clamp_gain(act(x + noise + bias), gain, clamp) (utils.py:6-7; generator.py:148-151,204)
+ *   for the layers without up-sampling and for ToRGBLayer2.                                          */
+int sg2_smooth_upsample2x(void *out, const void *x, const float *taps, int64_t B, int C, int H, int W,
+                          const void *noise, int64_t noise_bstride, const void *noise_strength,
+                          const void *bias, const void *addend, int act, float alpha, float gain,
+                          float clamp, int dtype, sg2_stream_t stream);
+int sg2_ada_bias_act(void *out, const void *x, const void *noise, int64_t noise_bstride,
+                     const void *noise_strength, const void *bias, int64_t B, int C, int64_t HW, int act,
+                     float alpha, float gain, float clamp, int dtype, sg2_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * The step after the decoder in ReStyle / pSp (restyle-encoder/models/psp.py:33,113-114;
+ * training/coach_restyle_psp.py:143-156): face_pool = AdaptiveAvgPool2d((256,256)) for integer ratios
+ * (x [planes, out_h*factor, out_w*factor] -> out [planes, out_h, out_w]) and
+ * F.interpolate(..., mode='bilinear', align_corners=False) (x [planes, in_h, in_w] -> [planes, out_h, out_w]). */
+int sg2_avg_pool_int(void *out, const void *x, int64_t planes, int out_h, int out_w, int factor, int dtype,
+                     sg2_stream_t stream);
+int sg2_resize_bilinear(void *out, const void *x, int64_t planes, int in_h, int in_w, int out_h, int out_w,
+                        int dtype, sg2_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Whole-network bf16 synthesis engine (NHWC activations, tcgen05/TMEM implicit GEMM fed by TMA,
  * fused epilogues).  Replaces the loop of Generator.forward, model.py:520-533.
  *

@@ -1,0 +1,93 @@
+// psp_ops.cu -- the step right after the decoder in ReStyle / pSp:
+//   * face_pool = AdaptiveAvgPool2d((256, 256)) on the decoder output   (restyle-encoder/models/psp.py:33,113-114;
+//     training/coach_restyle_psp.py:143-156; utils/inference_utils.py:36-38) -- for the integer ratios that
+//     occur (1024 -> 256: 4x4 means; 256 -> 256: identity) a box filter;
+//   * F.interpolate(y_hat, 112, mode='bilinear') before the identity / L2 losses (coach_restyle_psp.py:156),
+//     align_corners=False, no antialiasing (the PyTorch defaults the reference relies on).
+// NCHW, fp32 / fp16 / bf16 storage, fp32 math; a few MB per batch: launch-latency territory, one pass each.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace sg2 {
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+avg_pool_int_kernel(T *__restrict__ out, const T *__restrict__ x, long long total, int OH, int OW, int f) {
+    const float inv = 1.f / (float)(f * f);
+    const int IW = OW * f;
+    for (long long idx = (long long)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (long long)gridDim.x * 256) {
+        const int ox = (int)(idx % OW);
+        const long long t = idx / OW;
+        const int oy = (int)(t % OH);
+        const long long plane = t / OH;
+        const T *p = x + (plane * OH * f + (long long)oy * f) * IW + (long long)ox * f;
+        float acc = 0.f;
+        for (int a = 0; a < f; ++a)
+            for (int b = 0; b < f; ++b) acc += Cvt<T>::to_f(p[(long long)a * IW + b]);
+        out[idx] = Cvt<T>::from_f(acc * inv);
+    }
+}
+
+// same index math as ATen's area_pixel_compute_source_index(scale, dst, align_corners=false, cubic=false)
+__device__ __forceinline__ void bilinear_src(int dst, float scale, int in_size, int &i0, int &i1, float &l0, float &l1) {
+    float src = scale * ((float)dst + 0.5f) - 0.5f;
+    src = src < 0.f ? 0.f : src;
+    i0 = (int)src;
+    i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+    l1 = src - (float)i0;
+    l0 = 1.f - l1;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+resize_bilinear_kernel(T *__restrict__ out, const T *__restrict__ x, long long total, int IH, int IW, int OH, int OW,
+                       float sh, float sw) {
+    for (long long idx = (long long)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (long long)gridDim.x * 256) {
+        const int ox = (int)(idx % OW);
+        const long long t = idx / OW;
+        const int oy = (int)(t % OH);
+        const long long plane = t / OH;
+        int y0, y1, x0, x1;
+        float ly0, ly1, lx0, lx1;
+        bilinear_src(oy, sh, IH, y0, y1, ly0, ly1);
+        bilinear_src(ox, sw, IW, x0, x1, lx0, lx1);
+        const T *p = x + plane * IH * IW;
+        const float v00 = Cvt<T>::to_f(p[(long long)y0 * IW + x0]), v01 = Cvt<T>::to_f(p[(long long)y0 * IW + x1]);
+        const float v10 = Cvt<T>::to_f(p[(long long)y1 * IW + x0]), v11 = Cvt<T>::to_f(p[(long long)y1 * IW + x1]);
+        out[idx] = Cvt<T>::from_f(ly0 * (lx0 * v00 + lx1 * v01) + ly1 * (lx0 * v10 + lx1 * v11));
+    }
+}
+
+}  // namespace sg2
+
+using namespace sg2;
+
+extern "C" int sg2_avg_pool_int(void *out, const void *x, int64_t planes, int out_h, int out_w, int factor, int dtype,
+                                sg2_stream_t stream) {
+    SG2_REQUIRE(planes >= 0 && out_h >= 1 && out_w >= 1 && factor >= 1 && factor <= 64, SG2_ERR_BAD_ARG, "avg_pool_int: bad shape");
+    if (planes == 0) return SG2_OK;
+    SG2_REQUIRE(out && x, SG2_ERR_BAD_ARG, "avg_pool_int: null pointer");
+    const long long total = (long long)planes * out_h * out_w;
+    const unsigned blocks = (unsigned)std::min<long long>((total + 255) / 256, (long long)sm_count() * 32);
+    SG2_DISPATCH_DTYPE(dtype, {
+        avg_pool_int_kernel<T><<<blocks, 256, 0, as_stream(stream)>>>((T *)out, (const T *)x, total, out_h, out_w, factor);
+        SG2_LAUNCH_CHECK();
+    });
+    return SG2_OK;
+}
+
+extern "C" int sg2_resize_bilinear(void *out, const void *x, int64_t planes, int in_h, int in_w, int out_h, int out_w, int dtype,
+                                   sg2_stream_t stream) {
+    SG2_REQUIRE(planes >= 0 && in_h >= 1 && in_w >= 1 && out_h >= 1 && out_w >= 1, SG2_ERR_BAD_ARG, "resize_bilinear: bad shape");
+    if (planes == 0) return SG2_OK;
+    SG2_REQUIRE(out && x, SG2_ERR_BAD_ARG, "resize_bilinear: null pointer");
+    const long long total = (long long)planes * out_h * out_w;
+    const unsigned blocks = (unsigned)std::min<long long>((total + 255) / 256, (long long)sm_count() * 32);
+    const float sh = (float)in_h / (float)out_h, sw = (float)in_w / (float)out_w;
+    SG2_DISPATCH_DTYPE(dtype, {
+        resize_bilinear_kernel<T><<<blocks, 256, 0, as_stream(stream)>>>((T *)out, (const T *)x, total, in_h, in_w, out_h, out_w, sh, sw);
+        SG2_LAUNCH_CHECK();
+    });
+    return SG2_OK;
+}

@@ -1,0 +1,66 @@
+"""The step right after the decoder in ReStyle / pSp on the sg2_b200 kernels:
+
+    images = net.face_pool(images)                       # psp.py:33,113-114  AdaptiveAvgPool2d((256, 256))
+    y_hat = F.interpolate(y_hat, 112, mode='bilinear')   # coach_restyle_psp.py:156
+
+`FacePool` is a drop-in for the `torch.nn.AdaptiveAvgPool2d((256, 256))` the reference assigns to
+`pSp.face_pool`; `resize_bilinear` for the interpolate call.  Inference path (no autograd yet): a call that
+needs gradients raises."""
+import torch
+
+from . import _lib
+from .stylegan2.functional import needs_grad
+
+
+def _guard(x, what):
+    _lib.require_cuda(x)
+    if needs_grad(x):
+        raise RuntimeError(f"sg2_b200 {what}: inference-only kernel (no autograd yet); detach the input or use torch.no_grad()")
+
+
+def face_pool(images: torch.Tensor, size=(256, 256)) -> torch.Tensor:
+    """AdaptiveAvgPool2d(size) for integer pooling ratios (1024 -> 256, 512 -> 256, 256 -> 256)."""
+    _guard(images, "face_pool")
+    oh, ow = (size, size) if isinstance(size, int) else size
+    b, c, h, w = images.shape
+    if h % oh or w % ow or h // oh != w // ow:
+        raise RuntimeError(f"sg2_b200 face_pool: {h}x{w} -> {oh}x{ow} is not an integer, isotropic ratio")
+    f = h // oh
+    if f == 1:
+        return images
+    x = images.contiguous()
+    out = torch.empty((b, c, oh, ow), device=x.device, dtype=x.dtype)
+    with _lib.device_of(x):
+        _lib.check(_lib.load().sg2_avg_pool_int(out.data_ptr(), x.data_ptr(), b * c, oh, ow, f, _lib.dtype_code(x),
+                                                _lib.stream_of(x)), "avg_pool_int")
+    return out
+
+
+def resize_bilinear(images: torch.Tensor, size) -> torch.Tensor:
+    """F.interpolate(images, size, mode='bilinear') with the PyTorch defaults (align_corners=False, no antialias)."""
+    _guard(images, "resize_bilinear")
+    oh, ow = (size, size) if isinstance(size, int) else size
+    b, c, h, w = images.shape
+    x = images.contiguous()
+    out = torch.empty((b, c, oh, ow), device=x.device, dtype=x.dtype)
+    with _lib.device_of(x):
+        _lib.check(_lib.load().sg2_resize_bilinear(out.data_ptr(), x.data_ptr(), b * c, h, w, oh, ow, _lib.dtype_code(x),
+                                                   _lib.stream_of(x)), "resize_bilinear")
+    return out
+
+
+class FacePool(torch.nn.Module):
+    """drop-in for `self.face_pool = torch.nn.AdaptiveAvgPool2d((256, 256))` (psp.py:33)"""
+
+    def __init__(self, output_size=(256, 256)):
+        super().__init__()
+        self.output_size = output_size
+
+    def forward(self, x):
+        return face_pool(x, self.output_size)
+
+
+def decode_epilogue(images: torch.Tensor, pool=(256, 256), resize=112):
+    """decoder output -> (face-pooled image for the next refinement step, its 112x112 version for the losses)."""
+    pooled = face_pool(images, pool)
+    return pooled, resize_bilinear(pooled, resize)

@@ -1,0 +1,230 @@
+"""B200 host mirror of restyle-encoder/models/stylegan2_ada/generator.py: same class names, constructor and
+forward signatures, module tree and state_dict keys (a reference checkpoint loads with strict=True); the
+arithmetic runs on the sg2_b200 kernels.  Selected by psp.py:24-30 (`opts.generator_ada`).
+
+Per layer (SynthesisLayer2.forward, generator.py:186-204) the reference runs: affine -> per-sample weights
+[N,O,I,k,k] -> demod -> grouped conv -> SmoothUpsample (3 ops) -> + noise -> + bias -> lrelu -> gain -> clamp.
+Here: one modulation kernel (style + demod table), one shared-weight conv over the whole batch, and ONE
+epilogue kernel (SmoothUpsample fused with noise, bias, lrelu, gain, clamp; or the plain epilogue when the
+layer does not up-sample).  Only the 'stylegan2' synthesis layer is implemented (the reference's default and
+the one psp.py builds); inference only (see utils.py)."""
+import numpy as np
+import torch
+
+from ..stylegan2 import functional as K
+from .utils import (FullyConnectedLayer, SmoothUpsample, _no_grad_path, ada_bias_act, identity, normalize_2nd_moment,
+                    smooth_upsample2x)
+
+
+class Generator(torch.nn.Module):                            # generator.py:6-52
+
+    def __init__(self, z_dim, w_dim, w_num_layers, img_resolution, img_channels, synthesis_layer='stylegan2'):
+        super().__init__()
+        self.z_dim = z_dim
+        self.w_dim = w_dim
+        self.img_resolution = img_resolution
+        self.img_channels = img_channels
+        self.synthesis = SynthesisNetwork(w_dim=w_dim, img_resolution=img_resolution, img_channels=img_channels,
+                                          synthesis_layer=synthesis_layer)
+        self.num_ws = self.synthesis.num_ws
+        self.mapping = MappingNetwork(z_dim=z_dim, w_dim=w_dim, num_ws=self.num_ws, num_layers=w_num_layers)
+
+    def forward(self, z, truncation_psi=1, truncation_cutoff=None, noise_mode='random', input_is_latent=False,
+                randomize_noise=None, return_latents=False):
+        noise_mode = 'random' if randomize_noise else 'const'         # generator.py:23-26
+        z = z[0]
+        if not input_is_latent:
+            ws = self.mapping(z, truncation_psi=truncation_psi, truncation_cutoff=truncation_cutoff)
+            out_synth = self.synthesis(ws, noise_mode, return_latents=return_latents)
+        else:
+            out_synth = self.synthesis(z, noise_mode, return_latents=return_latents)
+        if return_latents:
+            return out_synth[0], z
+        return out_synth[0], None
+
+    def mean_latent(self, n_latent):
+        latent_in = torch.randn(n_latent, self.w_dim, device=self.synthesis.first_block.const.device)
+        return self.mapping(latent_in, truncation_psi=1, truncation_cutoff=None).mean(0, keepdim=True)
+
+    def get_latent(self, input):
+        return self.mapping(input, truncation_psi=1, truncation_cutoff=None)
+
+
+class SynthesisNetwork(torch.nn.Module):                     # generator.py:55-88
+
+    def __init__(self, w_dim, img_resolution, img_channels, channel_base=16384, channel_max=512, synthesis_layer='stylegan2'):
+        super().__init__()
+        self.w_dim = w_dim
+        self.img_resolution = img_resolution
+        self.img_resolution_log2 = int(np.log2(img_resolution))
+        self.img_channels = img_channels
+        self.block_resolutions = [2 ** i for i in range(2, self.img_resolution_log2 + 1)]
+        self.num_ws = 2 * (len(self.block_resolutions) + 1)
+        channels_dict = {res: min(channel_base // res, channel_max) for res in self.block_resolutions}
+        self.blocks = torch.nn.ModuleList()
+        self.first_block = SynthesisPrologue(channels_dict[self.block_resolutions[0]], w_dim=w_dim,
+                                             resolution=self.block_resolutions[0], img_channels=img_channels,
+                                             synthesis_layer=synthesis_layer)
+        for res in self.block_resolutions[1:]:
+            self.blocks.append(SynthesisBlock(channels_dict[res // 2], channels_dict[res], w_dim=w_dim, resolution=res,
+                                              img_channels=img_channels, synthesis_layer=synthesis_layer))
+
+    def forward(self, ws, noise_mode='random', return_latents=False, **kwargs):
+        split_ws = [ws[:, 0:2, :]] + [ws[:, 2 * n + 1: 2 * n + 4, :] for n in range(len(self.block_resolutions))]
+        x, img = self.first_block(split_ws[0], noise_mode)
+        for i in range(len(self.block_resolutions) - 1):
+            x, img = self.blocks[i](x, img, split_ws[i + 1], noise_mode)
+        if return_latents:
+            return img, None
+        return [img]
+
+
+def _layer_classes(synthesis_layer):
+    if synthesis_layer != 'stylegan2':
+        raise NotImplementedError("sg2_b200 stylegan2_ada: only synthesis_layer='stylegan2' is implemented "
+                                  "(the reference's default and the decoder psp.py builds)")
+    return SynthesisLayer2, ToRGBLayer2
+
+
+class SynthesisPrologue(torch.nn.Module):                    # generator.py:91-111
+
+    def __init__(self, out_channels, w_dim, resolution, img_channels, synthesis_layer):
+        super().__init__()
+        SynthesisLayer, ToRGBLayer = _layer_classes(synthesis_layer)
+        self.w_dim = w_dim
+        self.resolution = resolution
+        self.img_channels = img_channels
+        self.const = torch.nn.Parameter(torch.randn([out_channels, resolution, resolution]))
+        self.conv1 = SynthesisLayer(out_channels, out_channels, w_dim=w_dim, resolution=resolution)
+        self.torgb = ToRGBLayer(out_channels, img_channels, w_dim=w_dim)
+
+    def forward(self, ws, noise_mode):
+        w_iter = iter(ws.unbind(dim=1))
+        x = self.const.unsqueeze(0).repeat([ws.shape[0], 1, 1, 1])
+        x = self.conv1(x, next(w_iter), noise_mode=noise_mode)
+        img = self.torgb(x, next(w_iter))
+        return x, img
+
+
+class SynthesisBlock(torch.nn.Module):                       # generator.py:114-139
+
+    def __init__(self, in_channels, out_channels, w_dim, resolution, img_channels, synthesis_layer):
+        super().__init__()
+        SynthesisLayer, ToRGBLayer = _layer_classes(synthesis_layer)
+        self.in_channels = in_channels
+        self.w_dim = w_dim
+        self.resolution = resolution
+        self.img_channels = img_channels
+        self.num_conv = 0
+        self.num_torgb = 0
+        self.resampler = SmoothUpsample()
+        self.conv0 = SynthesisLayer(in_channels, out_channels, w_dim=w_dim, resolution=resolution, resampler=self.resampler)
+        self.conv1 = SynthesisLayer(out_channels, out_channels, w_dim=w_dim, resolution=resolution)
+        self.torgb = ToRGBLayer(out_channels, img_channels, w_dim=w_dim)
+
+    def forward(self, x, img, ws, noise_mode):
+        w_iter = iter(ws.unbind(dim=1))
+        x = self.conv0(x, next(w_iter), noise_mode=noise_mode)
+        x = self.conv1(x, next(w_iter), noise_mode=noise_mode)
+        y = self.torgb(x, next(w_iter))
+        # img = resampler(img); img.add_(y)  (generator.py:135-137) in one pass
+        img = smooth_upsample2x(img, self.resampler.kernel, addend=y)
+        return x, img
+
+
+class ToRGBLayer2(torch.nn.Module):                          # generator.py:142-155
+
+    def __init__(self, in_channels, out_channels, w_dim, kernel_size=1):
+        super().__init__()
+        self.affine = FullyConnectedLayer(w_dim, in_channels, bias_init=1)
+        self.weight = torch.nn.Parameter(torch.randn([out_channels, in_channels, kernel_size, kernel_size]))
+        self.bias = torch.nn.Parameter(torch.zeros([out_channels]))
+        self.weight_gain = 1 / np.sqrt(in_channels * (kernel_size ** 2))
+
+    def forward(self, x, w):
+        if not x.is_cuda:
+            raise RuntimeError("input must be a CUDA tensor")
+        _no_grad_path(x, w, self.weight, self.bias, self.affine.weight, self.affine.bias)
+        # styles * weight_gain folded into the weights; no demodulation
+        wt, _ = K.conv_prep(self.weight.to(x.dtype), self.weight_gain, want_wsq=False)
+        s, _ = K.modulation(w.to(x.dtype), self.affine.weight, self.affine.bias, None, self.weight.shape[0],
+                            self.affine.weight_gain, self.affine.bias_gain, False)
+        y = K.shared_conv(x, wt, s, None, self.weight.shape[0], self.weight.shape[-1], 0)
+        return ada_bias_act(y, None, None, self.bias, act=1, gain=1.0, clamp=256.0)
+
+
+class SynthesisLayer2(torch.nn.Module):                      # generator.py:172-204
+
+    def __init__(self, in_channels, out_channels, w_dim, resolution, kernel_size=3, resampler=identity, activation='lrelu'):
+        super().__init__()
+        if activation != 'lrelu' or kernel_size != 3:
+            raise NotImplementedError("sg2_b200 SynthesisLayer2: 3x3 / lrelu only")
+        self.resolution = resolution
+        self.resampler = resampler
+        self.activation_gain = float(np.sqrt(2))
+        self.padding = kernel_size // 2
+        self.affine = FullyConnectedLayer(w_dim, in_channels, bias_init=1)
+        self.weight = torch.nn.Parameter(torch.randn([out_channels, in_channels, kernel_size, kernel_size]))
+        self.register_buffer('noise_const', torch.randn([resolution, resolution]))
+        self.noise_strength = torch.nn.Parameter(torch.zeros([1]))
+        self.bias = torch.nn.Parameter(torch.zeros([out_channels]))
+
+    def forward(self, x, w, noise_mode, gain=1):
+        if not x.is_cuda:
+            raise RuntimeError("input must be a CUDA tensor")
+        _no_grad_path(x, w, self.weight, self.bias, self.noise_strength, self.affine.weight, self.affine.bias)
+        cout = self.weight.shape[0]
+        noise = None
+        if noise_mode == 'random':
+            noise = torch.randn([x.shape[0], 1, self.resolution, self.resolution], device=x.device, dtype=x.dtype)
+        if noise_mode == 'const':
+            noise = self.noise_const
+        wt, wsq = K.conv_prep(self.weight.to(x.dtype), 1.0, want_wsq=True)
+        s, d = K.modulation(w.to(x.dtype), self.affine.weight, self.affine.bias, wsq, cout, self.affine.weight_gain,
+                            self.affine.bias_gain, True)
+        y = K.shared_conv(x, wt, s, d, cout, 3, 0)
+        g, c = self.activation_gain * gain, 256.0 * gain
+        if isinstance(self.resampler, SmoothUpsample):
+            return smooth_upsample2x(y, self.resampler.kernel, noise, self.noise_strength, self.bias, None, act=3,
+                                     gain=g, clamp=c)
+        return ada_bias_act(y, noise, self.noise_strength, self.bias, act=3, gain=g, clamp=c)
+
+
+class MappingNetwork(torch.nn.Module):                       # generator.py:242-286
+
+    def __init__(self, z_dim, w_dim, num_ws, num_layers=8, activation='lrelu', lr_multiplier=0.01, w_avg_beta=0.995):
+        super().__init__()
+        self.z_dim = z_dim
+        self.w_dim = w_dim
+        self.num_ws = num_ws
+        self.num_layers = num_layers
+        self.w_avg_beta = w_avg_beta
+        self.lr_multiplier = lr_multiplier
+        features_list = [z_dim] + [w_dim] * num_layers
+        self.layers = torch.nn.ModuleList()
+        for idx in range(num_layers):
+            self.layers.append(FullyConnectedLayer(features_list[idx], features_list[idx + 1], activation=activation,
+                                                   lr_multiplier=lr_multiplier))
+        if num_ws is not None and w_avg_beta is not None:
+            self.register_buffer('w_avg', torch.zeros([w_dim]))
+
+    def forward(self, z, truncation_psi=1, truncation_cutoff=None, skip_w_avg_update=False):
+        if not z.is_cuda:
+            raise RuntimeError("input must be a CUDA tensor")
+        if self.z_dim == self.w_dim and self.num_layers > 0 and not K.needs_grad(z, *self.parameters()):
+            # normalize_2nd_moment + the whole MLP on the mapping kernels (one launch per layer)
+            x = K.mapping(z, [l.weight for l in self.layers], [l.bias for l in self.layers], self.lr_multiplier, True)
+        else:
+            x = normalize_2nd_moment(z)
+            for idx in range(self.num_layers):
+                x = self.layers[idx](x)
+        if self.w_avg_beta is not None and self.training and not skip_w_avg_update:
+            self.w_avg.copy_(x.detach().mean(dim=0).lerp(self.w_avg, self.w_avg_beta))
+        if self.num_ws is not None:
+            x = x.unsqueeze(1).repeat([1, self.num_ws, 1])
+        if truncation_psi != 1:
+            if self.num_ws is None or truncation_cutoff is None:
+                x = self.w_avg.lerp(x, truncation_psi)
+            else:
+                x[:, :truncation_cutoff] = self.w_avg.lerp(x[:, :truncation_cutoff], truncation_psi)
+        return x
