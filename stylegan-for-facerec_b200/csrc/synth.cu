@@ -186,6 +186,10 @@ int plan_gemm(sg2_synth *S, Layer &L) {
             if (resb < kGemmRingBytes && (nst >= 3 || (nst >= 2 && bk == 32))) { pick_bk = bk; pick_stage = stage; break; }
         }
         if (pick_bk) {
+            static const char *envm = getenv("SG2_GEMM_MMA2");
+            // opt-in (SG2_GEMM_MMA2=1): correct on the <= 256^2 networks, faults on the 32/64-channel 1024^2 tail
+            // (tile-split epilogue + SWIZZLE_64B operands) -- kept for the next round, see profiles/experiments
+            g.mma2 = (envm && atoi(envm) != 0) ? 1 : 0;
             g.resident = 1; g.resb_bytes = resb; g.stage_bytes = pick_stage;
             g.block_k = pick_bk; g.kchunks = cin / pick_bk; g.kpack = 1;
             L.two_sm = false;

@@ -30,7 +30,8 @@ namespace sg2 {
 using namespace tc;
 
 constexpr int kEpiWarps = 8;
-constexpr int kGemmThreads = 64 + 32 * kEpiWarps;   // TMA warp + MMA warp + epilogue warps
+constexpr int kMma2Warp = 2 + kEpiWarps;                // second MMA-issuing warp (resident-weights layers)
+constexpr int kGemmThreads = 64 + 32 * kEpiWarps + 32;   // TMA warp + MMA warp + epilogue warps + second MMA warp
 constexpr int kABytes = kBlockM * kBlockK * 2;          // 16 KiB
 constexpr int kBBytesMax = kMaxBlockN * kBlockK * 2;    // 32 KiB
 constexpr int kEpiCap = 512;                            // NB * BLOCK_N entries of per-sample epilogue params
@@ -280,28 +281,40 @@ modconv_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant_
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == 1 || warp == kMma2Warp) {
         // ===================== MMA issuer (warp-uniform control flow, one elected lane issues) =======
-        if (resident) {
+        // Resident-weights layers have short tiles (18 MMAs of 16 clk at Cin = Cout = 32): the ISSUING warp, not the
+        // tensor pipe, paced them (ncu: ~280 instructions and 1660 clk per tile).  With p.mma2 two warps issue
+        // alternate tiles (different accumulators, their own stages); each walks the same tile sequence and only
+        // advances the ring / accumulator counters over the other warp's tiles.
+        const bool second = warp == kMma2Warp;
+        if (second && !(resident && p.mma2)) {
+        } else if (resident) {
             const uint32_t idesc = make_idesc_bf16(kBlockM, (uint32_t)p.block_n);
-            uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+            uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0, it = 0;
+            const uint32_t my_parity = second ? 1u : 0u;
+            const bool split = p.mma2 != 0;
             const uint32_t ring = smem_u32(sm.ring);
             const uint32_t ksteps = bk / 16;
             mbar_wait(&sm.b_full, 0);
-            for (int s = 0; s < p.nsub; ++s) {
+#pragma unroll
+            for (int s = 0; s < kGemmMaxSub; ++s) {          // unrolled: p.sub[s] fields become static constant-bank reads
+                if (s >= p.nsub) break;
                 const GemmSub &g = p.sub[s];
                 const TileRange tr = cta_range(p, g);
-                // per-tap descriptor offsets (16-byte units), warp-uniform and hoisted out of the tile loop so
-                // the elected lane issues the whole stage's MMAs back to back
-                uint32_t aoff[kGemmMaxTaps], boff[kGemmMaxTaps];
-#pragma unroll
-                for (int tap = 0; tap < kGemmMaxTaps; ++tap) {
-                    const bool on = tap < g.ntaps;
-                    aoff[tap] = on ? (uint32_t)g.tap_aoff[tap] >> 4 : 0u;
-                    boff[tap] = on ? ((uint32_t)(g.wtap[tap] * p.kchunks) * b_bytes) >> 4 : 0u;
-                }
+                // per-tap descriptor offsets are read from the (constant-bank) parameter block right where they are
+                // used: they stay in UNIFORM registers.  Hoisting them into a local array put them in vector registers
+                // and cost an R2UR + IADD chain per MMA -- on the narrow 1024^2 layers (18 MMAs of 16 clk per tile)
+                // the issuing warp, not the tensor pipe, paced the kernel (ncu: ~280 instructions per tile).
+                const uint32_t wb16 = ((uint32_t)p.kchunks * b_bytes) >> 4;   // 16-byte units between the weights of two taps
                 const int ntaps = g.ntaps;
-                for (int local = tr.lo; local < tr.hi; ++local) {
+                for (int local = tr.lo; local < tr.hi; ++local, ++it) {
+                    if (split && (it & 1u) != my_parity) {      // the other issuing warp's tile
+                        for (int kc = 0; kc < p.kchunks; ++kc)
+                            if (++stage == nstages) { stage = 0; phase ^= 1; }
+                        if (++acc == nacc) { acc = 0; acc_phase ^= 1; }
+                        continue;
+                    }
                     mbar_wait(&sm.tmem_empty[acc], acc_phase ^ 1);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + acc * acc_cols;
@@ -314,7 +327,8 @@ modconv_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant_
 #pragma unroll
                             for (int tap = 0; tap < kGemmMaxTaps; ++tap) {
                                 if (tap < ntaps) {
-                                    const uint64_t adesc = a0 + aoff[tap], bdesc = b0 + boff[tap];
+                                    const uint64_t adesc = a0 + ((uint32_t)g.tap_aoff[tap] >> 4);
+                                    const uint64_t bdesc = b0 + (uint32_t)g.wtap[tap] * wb16;
                                     // 32 bytes (>>4 = 2) inside the swizzle row per K = 16 step
                                     umma_bf16(d_tmem, adesc, bdesc, idesc, (kc | tap) != 0);
                                     umma_bf16(d_tmem, adesc + 2, bdesc + 2, idesc, 1);
@@ -379,7 +393,7 @@ modconv_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant_
                 }
             }
         }
-    } else {
+    } else if (warp < kMma2Warp) {
         // ===================== epilogue: 8 warps, two per TMEM lane quarter =====================
         // warp (2 + 4h + i) may access TMEM lanes 32*((2+i)&3) ..  Two schedules:
         //  * column split (default): the two warps of a quarter alternate 32-column chunks of every tile;

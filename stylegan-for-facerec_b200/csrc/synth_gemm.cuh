@@ -43,6 +43,7 @@ struct GemmParams {
     // resident-weights mode (narrow layers whose 9*Cin*Cout bf16 weights fit in shared memory): the whole
     // weight tensor is loaded once per CTA, the ring holds only activation slabs (stage_bytes each)
     int resident, resb_bytes, stage_bytes;
+    int mma2;                       // resident mode: two warps issue the MMAs of alternate tiles
     // epilogue schedule of the single-CTA kernel: 1 = the two warp groups take alternate tiles (narrow BLOCK_N,
     // ONE ToRGB partial plane per N tile), 0 = they split the columns of every tile (two partial planes)
     int epi_alt;
