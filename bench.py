@@ -215,33 +215,46 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- e2e: host buffers, H2D of latents and D2H of images inside the timed region -----------
-    out_host = [torch.empty(B, 3, args.size, args.size, dtype=torch.float32).pin_memory() for _ in range(2)]
+    # The images leave the device the way the reference's own pipelines consume them: as uint8 (tensor2im,
+    # restyle-encoder/utils/common.py:5-11), converted on the device by the repo's public `images_to_uint8`, so a
+    # quarter of the bytes crosses PCIe.  The fp32 variant (every byte of the module's output) is timed too and reported
+    # as e2e.fp32_images: it is bound by the host link once several ranks copy at the same time.
+    psp_io = importlib.import_module("stylegan-for-facerec_b200.psp_io")
     copy_stream = torch.cuda.Stream(device=dev)
-    done = [torch.cuda.Event(), torch.cuda.Event()]
 
-    def e2e_loop(n, base):
-        for i in range(n):
-            z = z_host[base + i].to(dev, non_blocking=True)          # H2D from pinned memory
-            im = step(z)
-            ready = torch.cuda.Event()
-            ready.record()
-            slot = i & 1
-            with torch.cuda.stream(copy_stream):                      # D2H overlaps the next step's compute
-                copy_stream.wait_event(ready)
-                out_host[slot].copy_(im, non_blocking=True)
-                im.record_stream(copy_stream)
-                done[slot].record()
-        copy_stream.synchronize()
+    def make_e2e(as_uint8):
+        out_host = [torch.empty(B, 3, args.size, args.size, dtype=torch.uint8 if as_uint8 else torch.float32).pin_memory()
+                    for _ in range(2)]
 
-    e2e_loop(W, 0)
-    barrier()
-    t0 = time.perf_counter()
-    e2e_loop(K, W)
-    torch.cuda.synchronize()
-    t_e2e = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    t_e2e = float(t_e2e.item())
+        def loop(n, base):
+            for i in range(n):
+                z = z_host[base + i].to(dev, non_blocking=True)          # H2D from pinned memory
+                im = step(z)
+                if as_uint8:
+                    im = psp_io.images_to_uint8(im)
+                ready = torch.cuda.Event()
+                ready.record()
+                with torch.cuda.stream(copy_stream):                      # D2H overlaps the next step's compute
+                    copy_stream.wait_event(ready)
+                    out_host[i & 1].copy_(im, non_blocking=True)
+                    im.record_stream(copy_stream)
+            copy_stream.synchronize()
+        return loop
+
+    def time_e2e(as_uint8):
+        loop = make_e2e(as_uint8)
+        loop(W, 0)
+        barrier()
+        t0 = time.perf_counter()
+        loop(K, W)
+        torch.cuda.synchronize()
+        t = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    t_e2e = time_e2e(True)
+    t_e2e_f32 = time_e2e(False)
 
     # ---- roofline of the dominant kernel: per-launch CUDA events inside the engine --------------
     roofline, table = None, None
@@ -321,9 +334,11 @@ def main():
                          "no explicit flush: per-step activation traffic >> 126 MB L2",
                    "parallelism": f"batch-sharded x{world}, no collective in the data path"},
         "e2e": {"value": round(n_img / t_e2e, 2), "unit": "images/s", "h2d_bytes_per_step": B * STYLE_DIM * 4,
-                "d2h_bytes_per_step": B * 3 * args.size * args.size * 4,
-                "note": "pinned host latents -> Generator.forward -> fp32 images copied back to pinned host memory "
-                        "(copy stream overlaps the next step)"},
+                "d2h_bytes_per_step": B * 3 * args.size * args.size,
+                "note": "pinned host latents -> Generator.forward -> images_to_uint8 (tensor2im on the device) -> uint8 images "
+                        "copied back to pinned host memory (copy stream overlaps the next step)",
+                "fp32_images": {"value": round(n_img / t_e2e_f32, 2), "d2h_bytes_per_step": B * 3 * args.size * args.size * 4,
+                                "note": "same loop copying the module's fp32 output instead of uint8"}},
         "gpu_launches": int(launches), "clocks": clocks,
     }
     if roofline:

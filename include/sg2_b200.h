@@ -161,6 +161,9 @@ int sg2_avg_pool_int(void *out, const void *x, int64_t planes, int out_h, int ou
                      sg2_stream_t stream);
 int sg2_resize_bilinear(void *out, const void *x, int64_t planes, int in_h, int in_w, int out_h, int out_w,
                         int dtype, sg2_stream_t stream);
+/* tensor2im on the device (restyle-encoder/utils/common.py:5-11): out[i] = uint8(clip((x[i] + 1) / 2, 0, 1) * 255),
+ * same element order as x; `out` 4-byte aligned. */
+int sg2_image_to_uint8(void *out, const void *x, int64_t total, int dtype, sg2_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Whole-network bf16 synthesis engine (NHWC activations, tcgen05/TMEM implicit GEMM fed by TMA,

@@ -62,6 +62,7 @@ SIGNATURES = {
                                  c_int, c_float, c_float, c_float, c_int, c_void_p]),
     "sg2_avg_pool_int": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_int, c_int, c_int, c_void_p]),
     "sg2_resize_bilinear": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "sg2_image_to_uint8": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_void_p]),
     "sg2_synth_create": (c_int, [C.POINTER(c_void_p), c_int, c_int, c_int, C.POINTER(ConvParams), c_int,
                                  c_void_p, C.POINTER(c_float)]),
     "sg2_synth_destroy": (None, [c_void_p]),

@@ -64,3 +64,15 @@ def decode_epilogue(images: torch.Tensor, pool=(256, 256), resize=112):
     """decoder output -> (face-pooled image for the next refinement step, its 112x112 version for the losses)."""
     pooled = face_pool(images, pool)
     return pooled, resize_bilinear(pooled, resize)
+
+
+def images_to_uint8(images: torch.Tensor) -> torch.Tensor:
+    """tensor2im on the device (utils/common.py:5-11 of the reference: ((x + 1) / 2).clip(0, 1) * 255 -> uint8),
+    same NCHW layout: a quarter of the bytes to bring back to the host / write to disk."""
+    _guard(images, "images_to_uint8")
+    x = images.contiguous()
+    out = torch.empty(x.shape, device=x.device, dtype=torch.uint8)
+    with _lib.device_of(x):
+        _lib.check(_lib.load().sg2_image_to_uint8(out.data_ptr(), x.data_ptr(), x.numel(), _lib.dtype_code(x),
+                                                  _lib.stream_of(x)), "image_to_uint8")
+    return out

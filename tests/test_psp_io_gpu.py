@@ -36,3 +36,14 @@ def test_face_pool_and_resize_vs_torch(sg2):
         io.face_pool(torch.randn(1, 3, 300, 300, device=DEV))
     with pytest.raises(RuntimeError, match="CUDA"):
         io.face_pool(torch.randn(1, 3, 512, 512))
+
+
+def test_images_to_uint8(sg2):
+    io = importlib.import_module("stylegan-for-facerec_b200.psp_io")
+    x = torch.randn(3, 3, 37, 41) * 0.8
+    x[0, 0, 0, :4] = torch.tensor([-1.0, 1.0, -3.0, 5.0])
+    ref = ((x.numpy() + 1) / 2).clip(0, 1) * 255
+    y = io.images_to_uint8(x.to(DEV)).cpu().numpy()
+    assert y.dtype == np.uint8 and y.shape == x.shape
+    assert np.abs(y.astype(np.int32) - ref.astype("uint8").astype(np.int32)).max() <= 1     # fp32 rounding at bin edges
+    assert (y == ref.astype("uint8")).mean() > 0.999
