@@ -215,6 +215,12 @@ int plan_gemm(sg2_synth *S, Layer &L) {
             }
         }
     }
+    // transposed conv: optionally walk the four polyphase sub-problems segment by segment so that their common input
+    // stays in L2 (ncu: the phases re-read it from DRAM, 4x the algorithmic input bytes).  Measured: no gain at 256^2
+    // (the layer is bound by L2->SM operand delivery, not DRAM) and a loss on the 1024^2 tail -> opt-in, SG2_GEMM_SEG=n.
+    static const char *envs = getenv("SG2_GEMM_SEG");
+    g.seg_tiles = up ? (envs ? atoi(envs) : 0) : 0;
+    g.nseg = 1;
     static const char *envd = getenv("SG2_GEMM_DBG");
     g.dbg = envd ? atoi(envd) : 0;
     static const char *enva = getenv("SG2_GEMM_EPI_ALT");

@@ -21,6 +21,8 @@
 //   The transposed stride-2 convolution of the up-sampling layers runs as four polyphase
 //   sub-problems (4/2/2/1 taps) of the same kernel: no multiplies by inserted zeros.
 //   Persistent: grid = #SMs; every CTA owns a contiguous chunk of each sub-problem's tiles.
+#include <algorithm>
+
 #include "common.cuh"
 #include "synth_gemm.cuh"
 #include "tc_ptx.cuh"
@@ -90,12 +92,16 @@ __device__ __forceinline__ void next_tile(const GemmParams &p, const GemmSub &g,
 // Every CTA takes one contiguous chunk of EVERY sub-problem (the polyphase sub-problems of the
 // transposed conv cost 4/2/2/1 taps per tile, so chunking them separately keeps CTAs balanced).
 struct TileRange { int lo, hi; };
-__device__ __forceinline__ TileRange cta_range(const GemmParams &p, const GemmSub &g) {
+__device__ __forceinline__ TileRange cta_range(const GemmParams &p, const GemmSub &g, int seg) {
     const int count = g.tiles_x * g.tiles_y * g.tiles_b * p.n_tiles_n;
     const int per = (count + (int)gridDim.x - 1) / (int)gridDim.x;
     TileRange r;
     r.lo = min(count, (int)blockIdx.x * per);
     r.hi = min(count, r.lo + per);
+    if (p.seg_tiles > 0) {             // segment `seg` of the chunk
+        r.lo = min(r.hi, r.lo + seg * p.seg_tiles);
+        r.hi = min(r.hi, r.lo + p.seg_tiles);
+    }
     return r;
 }
 
@@ -215,12 +221,13 @@ modconv_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant_
             }
             __syncwarp();
             uint32_t stage = 0, phase = 0;
+            for (int seg = 0; seg < p.nseg; ++seg)
             for (int s = 0; s < p.nsub; ++s) {
                 const GemmSub &g = p.sub[s];
                 const CUtensorMap *tmA = s == 0 ? &tmA0 : (s == 1 ? &tmA1 : (s == 2 ? &tmA2 : &tmA3));
                 const uint32_t slab_bytes = (uint32_t)(g.slab_rows * g.TW) * row_bytes;
                 const int nslab = g.nslab, sdx[3] = {g.slab_dx[0], g.slab_dx[1], g.slab_dx[2]};
-                const TileRange tr = cta_range(p, g);
+                const TileRange tr = cta_range(p, g, seg);
                 TileCoord t = decode_tile(p, g, tr.lo);
                 for (int local = tr.lo; local < tr.hi; ++local, next_tile(p, g, t)) {
                     const int ay = t.y0 + g.slab_dy0;
@@ -241,11 +248,12 @@ modconv_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant_
             }
         } else {
             uint32_t stage = 0, phase = 0;
+            for (int seg = 0; seg < p.nseg; ++seg)
             for (int s = 0; s < p.nsub; ++s) {
                 const GemmSub &g = p.sub[s];
                 const CUtensorMap *tmA = s == 0 ? &tmA0 : (s == 1 ? &tmA1 : (s == 2 ? &tmA2 : &tmA3));
                 const uint32_t a_bytes = (uint32_t)(g.TH * g.TW * g.NB) * row_bytes;
-                const TileRange tr = cta_range(p, g);
+                const TileRange tr = cta_range(p, g, seg);
                 TileCoord t = decode_tile(p, g, tr.lo);
                 for (int local = tr.lo; local < tr.hi; ++local, next_tile(p, g, t)) {
                     for (int kc = 0; kc < p.kchunks; kc += (int)kpk) {
@@ -297,11 +305,12 @@ modconv_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant_
             const uint32_t ring = smem_u32(sm.ring);
             const uint32_t ksteps = bk / 16;
             mbar_wait(&sm.b_full, 0);
+            for (int seg = 0; seg < p.nseg; ++seg)
 #pragma unroll
             for (int s = 0; s < kGemmMaxSub; ++s) {          // unrolled: p.sub[s] fields become static constant-bank reads
                 if (s >= p.nsub) break;
                 const GemmSub &g = p.sub[s];
-                const TileRange tr = cta_range(p, g);
+                const TileRange tr = cta_range(p, g, seg);
                 // per-tap descriptor offsets are read from the (constant-bank) parameter block right where they are
                 // used: they stay in UNIFORM registers.  Hoisting them into a local array put them in vector registers
                 // and cost an R2UR + IADD chain per MMA -- on the narrow 1024^2 layers (18 MMAs of 16 clk per tile)
@@ -351,10 +360,11 @@ modconv_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant_
         } else {
             const uint32_t idesc = make_idesc_bf16(kBlockM, (uint32_t)p.block_n);
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+            for (int seg = 0; seg < p.nseg; ++seg)
             for (int s = 0; s < p.nsub; ++s) {
                 const GemmSub &g = p.sub[s];
                 const int nstage = p.kchunks / (int)kpk * g.ntaps;
-                const TileRange tr = cta_range(p, g);
+                const TileRange tr = cta_range(p, g, seg);
                 for (int local = tr.lo; local < tr.hi; ++local) {
                     mbar_wait(&sm.tmem_empty[acc], acc_phase ^ 1);
                     tc_fence_after();
@@ -416,6 +426,7 @@ modconv_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant_
         const int N = p.block_n;
         uint32_t it0 = 0;                            // tiles of the earlier sub-problems (= the MMA warp's count)
         int staged_key = -1;
+        for (int seg = 0; seg < p.nseg; ++seg)
         for (int s = 0; s < p.nsub; ++s) {
             const GemmSub &g = p.sub[s];
             const int per = g.TH * g.TW;
@@ -425,7 +436,7 @@ modconv_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant_
             const int pb = (nb < g.NB ? nb : 0) * N;    // row of the staged per-sample params
             const int PH = g.PH, PW = g.PW, NB = g.NB;
             const long long plane = (long long)PH * PW;
-            const TileRange tr = cta_range(p, g);
+            const TileRange tr = cta_range(p, g, seg);
             int local = tr.lo + (alt ? (int)((grp - it0) & 1u) : 0);
             TileCoord t = decode_tile(p, g, local);
             auto noise_at = [&](const TileCoord &tc) -> float {
@@ -539,11 +550,22 @@ int launch_modconv_gemm(const GemmParams &p, const CUtensorMap *tmA, const CUten
                     SG2_ERR_BAD_ARG, "gemm: tile of sub-problem %d too large", s);
     const int grid = p.total_tiles < sms ? p.total_tiles : sms;
     if (grid <= 0) return SG2_OK;
+    GemmParams q = p;                      // segments of the polyphase interleave (GemmParams::seg_tiles)
+    q.nseg = 1;
+    if (q.seg_tiles > 0) {
+        int max_per = 1;
+        for (int s = 0; s < q.nsub; ++s) {
+            const GemmSub &g = q.sub[s];
+            const int count = g.tiles_x * g.tiles_y * g.tiles_b * q.n_tiles_n;
+            max_per = std::max(max_per, (count + grid - 1) / grid);
+        }
+        q.nseg = (max_per + q.seg_tiles - 1) / q.seg_tiles;
+    }
     const CUtensorMap &a0 = tmA[0];
     const CUtensorMap &a1 = tmA[p.nsub > 1 ? 1 : 0];
     const CUtensorMap &a2 = tmA[p.nsub > 2 ? 2 : 0];
     const CUtensorMap &a3 = tmA[p.nsub > 3 ? 3 : 0];
-    modconv_gemm_kernel<<<grid, kGemmThreads, smem, st>>>(p, a0, a1, a2, a3, tmB);
+    modconv_gemm_kernel<<<grid, kGemmThreads, smem, st>>>(q, a0, a1, a2, a3, tmB);
     SG2_LAUNCH_CHECK();
     return SG2_OK;
 }

@@ -44,6 +44,11 @@ struct GemmParams {
     // weight tensor is loaded once per CTA, the ring holds only activation slabs (stage_bytes each)
     int resident, resb_bytes, stage_bytes;
     int mma2;                       // resident mode: two warps issue the MMAs of alternate tiles
+    // polyphase interleave: a CTA's chunk of every sub-problem is cut into segments of seg_tiles tiles and the
+    // sub-problems are walked segment by segment (seg outer, sub-problem inner), so the four phases of the transposed
+    // conv re-read their common input while it is still in L2 (ncu: the phases read it from DRAM 4x otherwise).
+    // seg_tiles == 0: one segment = the whole chunk (plain convolutions).
+    int seg_tiles, nseg;
     // epilogue schedule of the single-CTA kernel: 1 = the two warp groups take alternate tiles (narrow BLOCK_N,
     // ONE ToRGB partial plane per N tile), 0 = they split the columns of every tile (two partial planes)
     int epi_alt;

@@ -96,13 +96,17 @@ __device__ __forceinline__ TileCoord2 decode_tile2(const GemmParams &p, const Ge
 // Every CTA takes one contiguous chunk of EVERY sub-problem (the polyphase sub-problems of the
 // transposed conv cost 4/2/2/1 taps per tile, so chunking them separately keeps CTAs balanced).
 struct TileRange2 { int lo, hi; };
-__device__ __forceinline__ TileRange2 cta_range2(const GemmParams &p, const GemmSub &g) {
+__device__ __forceinline__ TileRange2 cta_range2(const GemmParams &p, const GemmSub &g, int seg) {
     const int count = pair_groups(g) * p.n_tiles_n;          // work items of a CLUSTER
     const int ncl = (int)gridDim.x / 2, cid = (int)blockIdx.x / 2;
     const int per = (count + ncl - 1) / ncl;
     TileRange2 r;
     r.lo = min(count, cid * per);
     r.hi = min(count, r.lo + per);
+    if (p.seg_tiles > 0) {             // segment `seg` of the chunk (see GemmParams::seg_tiles)
+        r.lo = min(r.hi, r.lo + seg * p.seg_tiles);
+        r.hi = min(r.hi, r.lo + p.seg_tiles);
+    }
     return r;
 }
 
@@ -147,11 +151,12 @@ modconv_gemm2_kernel(const __grid_constant__ GemmParams p, const __grid_constant
     if (warp == 0) {
         // ===================== TMA producer (warp-uniform control flow, one elected lane issues) =====
         uint32_t stage = 0, phase = 0;
+        for (int seg = 0; seg < p.nseg; ++seg)
         for (int s = 0; s < p.nsub; ++s) {
             const GemmSub &g = p.sub[s];
             const CUtensorMap *tmA = s == 0 ? &tmA0 : (s == 1 ? &tmA1 : (s == 2 ? &tmA2 : &tmA3));
             const uint32_t a_bytes = (uint32_t)(g.TH * g.TW * g.NB) * row_bytes;
-            const TileRange2 tr = cta_range2(p, g);
+            const TileRange2 tr = cta_range2(p, g, seg);
             for (int local = tr.lo; local < tr.hi; ++local) {
                 const TileCoord2 t = decode_tile2(p, g, local, rank);
                 const int wrow = t.nt * p.block_n + rank * (p.block_n / 2);
@@ -182,10 +187,11 @@ modconv_gemm2_kernel(const __grid_constant__ GemmParams p, const __grid_constant
         if (leader) {
             const uint32_t idesc = make_idesc_bf16(2 * kBlockM, (uint32_t)p.block_n);
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+            for (int seg = 0; seg < p.nseg; ++seg)
             for (int s = 0; s < p.nsub; ++s) {
                 const GemmSub &g = p.sub[s];
                 const int nstage = p.kchunks / (int)kpk * g.ntaps;
-                const TileRange2 tr = cta_range2(p, g);
+                const TileRange2 tr = cta_range2(p, g, seg);
                 for (int local = tr.lo; local < tr.hi; ++local) {
                     mbar_wait(&sm.tmem_empty[acc], acc_phase ^ 1);
                     tc_fence_after();
@@ -234,6 +240,7 @@ modconv_gemm2_kernel(const __grid_constant__ GemmParams p, const __grid_constant
         const int N = p.block_n;
         uint32_t acc = 0, acc_phase = 0;
         int staged_key = -1;
+        for (int seg = 0; seg < p.nseg; ++seg)
         for (int s = 0; s < p.nsub; ++s) {
             const GemmSub &g = p.sub[s];
             const int per = g.TH * g.TW;
@@ -241,7 +248,7 @@ modconv_gemm2_kernel(const __grid_constant__ GemmParams p, const __grid_constant
             const int rem = m - nb * per;
             const int ty = rem / g.TW, tx = rem - ty * g.TW;
             const int pb = (nb < g.NB ? nb : 0) * N;    // row of the staged per-sample params
-            const TileRange2 tr = cta_range2(p, g);
+            const TileRange2 tr = cta_range2(p, g, seg);
             for (int local = tr.lo; local < tr.hi; ++local) {
                 const TileCoord2 t = decode_tile2(p, g, local, rank);
                 const int n0 = t.nt * N;
@@ -369,6 +376,17 @@ int launch_modconv_gemm2(const GemmParams &p, const CUtensorMap *tmA, const CUte
     }
     const int n_clusters = (int)std::min<long>(most, sms / 2);
     if (n_clusters <= 0) return SG2_OK;
+    GemmParams q = p;                      // segments of the polyphase interleave (GemmParams::seg_tiles)
+    q.nseg = 1;
+    if (q.seg_tiles > 0) {
+        long max_per = 1;
+        for (int s2 = 0; s2 < q.nsub; ++s2) {
+            const GemmSub &g = q.sub[s2];
+            const long count = ((long)g.tiles_x * g.tiles_y * g.tiles_b + 1) / 2 * q.n_tiles_n;
+            max_per = std::max(max_per, (count + n_clusters - 1) / n_clusters);
+        }
+        q.nseg = (int)((max_per + q.seg_tiles - 1) / q.seg_tiles);
+    }
     const CUtensorMap &a0 = tmA[0];
     const CUtensorMap &a1 = tmA[p.nsub > 1 ? 1 : 0];
     const CUtensorMap &a2 = tmA[p.nsub > 2 ? 2 : 0];
@@ -385,7 +403,7 @@ int launch_modconv_gemm2(const GemmParams &p, const CUtensorMap *tmA, const CUte
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    SG2_CUDA_OK(cudaLaunchKernelEx(&cfg, modconv_gemm2_kernel, p, a0, a1, a2, a3, tmB));
+    SG2_CUDA_OK(cudaLaunchKernelEx(&cfg, modconv_gemm2_kernel, q, a0, a1, a2, a3, tmB));
     SG2_LAUNCH_CHECK();
     return SG2_OK;
 }
