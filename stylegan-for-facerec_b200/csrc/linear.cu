@@ -260,8 +260,8 @@ pixel_norm_kernel(T *__restrict__ out, const T *__restrict__ x, int64_t B, int d
     for (int j = lane; j < dim; j += 32) out[b * dim + j] = Cvt<T>::from_f(Cvt<T>::to_f(x[b * dim + j]) * rn);
 }
 
-// The same layer as a small tiled fp32 GEMM (the shuffle-reduction kernel above is latency bound at ~14 us per
-// layer for B = 64, 8 layers per forward): block = MG_F output features x MG_S samples, K in chunks of MG_K through
+// The same layer as a small tiled fp32 GEMM (an experiment against the shuffle-reduction kernel above, which is latency
+// bound at ~12 us per layer for B = 64, 8 layers per forward; this one measured slower and is opt-in): block = MG_F output features x MG_S samples, K in chunks of MG_K through
 // double-buffered shared memory with the next chunk prefetched into registers, a thread owns one feature x two
 // samples.  PixelNorm of the first layer is a per-sample scale of the result (the warp that stages a sample's row
 // also accumulates its sum of squares).
@@ -339,8 +339,10 @@ mapping_gemm_kernel(T *__restrict__ out, const T *__restrict__ x, const T *__res
 template <typename T>
 static int launch_mapping_layer(T *out, const T *x, const T *w, const T *bias, int64_t B, int dim,
                                 float w_scale, float lr_mul, int pixel_norm, cudaStream_t st) {
-    static const char *env_old = getenv("SG2_MAPPING_SHUFFLE");     // A/B switch: the shuffle-reduction kernel
-    if (!(env_old && atoi(env_old))) {
+    // A/B switch: the tiled-GEMM kernel.  Measured in the step (tools/timeline.py): 19 us per layer vs 11.6 us for the
+    // shuffle-reduction kernel at B = 64 (64 blocks x 16 synchronised K chunks is too little parallelism) -> off.
+    static const char *env_gemm = getenv("SG2_MAPPING_GEMM");
+    if (env_gemm && atoi(env_gemm)) {
         dim3 g2(dim / MG_F, (unsigned)ceil_div64(B, MG_S));
         mapping_gemm_kernel<T><<<g2, 256, 0, st>>>(out, x, w, bias, B, dim, w_scale, lr_mul, pixel_norm);
         SG2_LAUNCH_CHECK();
