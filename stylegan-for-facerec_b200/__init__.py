@@ -14,9 +14,10 @@ from .stylegan2.model import (Blur, ConstantInput, ConvLayer, Discriminator, Dow
                               EqualLinear, Generator, ModulatedConv2d, NoiseInjection, PixelNorm, ResBlock,
                               ScaledLeakyReLU, StyledConv, ToRGB, Upsample, make_kernel)
 from .stylegan2.op import FusedLeakyReLU, fused_leaky_relu, upfirdn2d
+from . import psp_io, stylegan2_ada                      # ADA decoder variant, face_pool / resize / uint8 after the decoder
 
 __all__ = ["Generator", "Discriminator", "ModulatedConv2d", "StyledConv", "ToRGB", "Blur", "Upsample",
            "Downsample", "EqualLinear", "EqualConv2d", "NoiseInjection", "ConstantInput", "PixelNorm",
            "ScaledLeakyReLU", "ConvLayer", "ResBlock", "FusedLeakyReLU", "fused_leaky_relu", "upfirdn2d",
-           "make_kernel", "model", "op", "_lib"]
+           "make_kernel", "model", "op", "psp_io", "stylegan2_ada", "_lib"]
 __version__ = "0.1.0"
