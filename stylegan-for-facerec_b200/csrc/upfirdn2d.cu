@@ -304,7 +304,7 @@ extern "C" int sg2_upfirdn2d(void *out, const void *x, const float *kernel, int6
     cudaStream_t st = as_stream(stream);
     const bool sym = up_x == up_y && down_x == down_y && minor == 1 && kh <= 4 && kw <= 4;
     SG2_DISPATCH_DTYPE(dtype, {
-        if (minor == 1 && out_h * out_w <= 256) {   // up to 16 x 16 outputs per plane
+        if (minor == 1 && out_h * out_w <= 256 && !(sym && out_w > 8 && out_h > 8)) {   // tiny planes (<= 8 x 8 ... 16 x 16 non-model geometries)
             UfdGenParams p;
             p.in_h = in_h; p.in_w = in_w; p.out_h = out_h; p.out_w = out_w; p.minor = 1;
             p.up_x = up_x; p.up_y = up_y; p.down_x = down_x; p.down_y = down_y;

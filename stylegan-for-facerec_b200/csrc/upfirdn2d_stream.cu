@@ -138,7 +138,7 @@ template <typename T, int UP, int DOWN, int PHX, int PHY, int WLOG2>
 __global__ void __launch_bounds__(US_THREADS)
 upfirdn2d_stream_kernel(T *__restrict__ out, const T *__restrict__ x, const float *__restrict__ taps, const UfdStreamParams p) {
     using G = SGeo<UP, DOWN>;
-    constexpr int NI = G::LS + 1;                                  // loads per lane per row: ceil(line / lanes), lanes >= 8
+    constexpr int NI = G::LS + 1;                                  // loads per lane per row: ceil(line / lanes), lanes >= 4
     extern __shared__ __align__(16) float us_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int WL = 1 << WLOG2, NS = 32 >> WLOG2;
@@ -361,6 +361,7 @@ static int launch_stream_t(void *out, const void *x, const float *taps, const Uf
     T *o = (T *)out;
     const T *xi = (const T *)x;
     switch (p.wl_log2) {
+        case 2: upfirdn2d_stream_kernel<T, UP, DOWN, PHX, PHY, 2><<<grid, US_THREADS, smem, st>>>(o, xi, taps, p); break;
         case 3: upfirdn2d_stream_kernel<T, UP, DOWN, PHX, PHY, 3><<<grid, US_THREADS, smem, st>>>(o, xi, taps, p); break;
         case 4: upfirdn2d_stream_kernel<T, UP, DOWN, PHX, PHY, 4><<<grid, US_THREADS, smem, st>>>(o, xi, taps, p); break;
         default:
@@ -387,7 +388,7 @@ int launch_upfirdn2d_stream(void *out, const void *x, const float *taps, int64_t
     p.pad_x0 = pad_x0; p.pad_y0 = pad_y0; p.kh = kh; p.kw = kw;
     // lanes per strip: 4 output columns per lane (the 8-inputs-per-lane down-sampling window stays at 16 lanes: 9
     // prefetch registers per row)
-    int wl = 3;
+    int wl = 2;                                                      // 4 lanes: planes up to 16 columns wide, 8 planes per warp
     while ((4 << wl) < out_w && wl < (down == 2 ? 4 : 5)) ++wl;
     p.wl_log2 = wl;
     p.planes = planes;
