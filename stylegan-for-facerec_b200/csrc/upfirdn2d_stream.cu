@@ -51,13 +51,19 @@ struct UfdStreamParams {
     int vec_store;        // output rows are aligned for one vector store per lane
 };
 
+// outputs per lane (US_TX_WIDE for blur / up-sampling: halves the per-output share of loads, stores and loop
+// control -- the kernel is issue-bound; the down-sampling window is already 8 inputs per lane at 4 outputs)
+#ifndef SG2_US_TX_WIDE
+#define SG2_US_TX_WIDE 8
+#endif
 template <int UP, int DOWN>
 struct SGeo {
-    static constexpr int LS = UP == 2 ? 2 : 4 * DOWN;               // input elements between the windows of adjacent lanes
-    static constexpr int WU = UP == 2 ? 4 : 3 * DOWN + 4;           // window elements used (7 / 10 / 4)
-    static constexpr int WR = UP == 2 ? 4 : (DOWN == 1 ? 8 : 12);   // window elements read (vector loads)
+    static constexpr int TX = DOWN == 2 ? 4 : SG2_US_TX_WIDE;       // output columns per lane
+    static constexpr int LS = TX * DOWN / UP;                       // input elements between the windows of adjacent lanes
+    static constexpr int WU = UP == 2 ? TX / 2 + 2 : DOWN * (TX - 1) + 4;   // window elements used
+    static constexpr int WR = (WU + 3) & ~3;                        // window elements read (16-byte loads)
     static constexpr int R = DOWN == 2 ? 2 : 4;                     // output rows in flight
-    static constexpr int PERIOD = UP == 2 ? 2 : 4;                  // input rows after which the slot pattern repeats
+    static_assert(TX == 4 || TX == 8, "4 or 8 outputs per lane");
 };
 
 __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
@@ -113,20 +119,24 @@ __device__ __forceinline__ void load_window(uint32_t addr, float (&w)[WR]) {
     }
 }
 
-template <typename T>
-__device__ __forceinline__ void store4(T *dst, const float (&v)[4], int n_ok, bool vec) {
-    if (vec && n_ok == 4) {
-        if constexpr (sizeof(T) == 4) {
-            *reinterpret_cast<float4 *>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-        } else {
-            T pk[4];
+template <typename T, int N>
+__device__ __forceinline__ void store_row(T *dst, const float (&v)[N], int n_ok, bool vec) {
+    if (vec && n_ok == N) {
+        T pk[N];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) pk[i] = Cvt<T>::from_f(v[i]);
+        for (int i = 0; i < N; ++i) pk[i] = Cvt<T>::from_f(v[i]);
+        constexpr int BYTES = N * (int)sizeof(T);
+        if constexpr (BYTES == 32) {
+            reinterpret_cast<uint4 *>(dst)[0] = reinterpret_cast<const uint4 *>(pk)[0];
+            reinterpret_cast<uint4 *>(dst)[1] = reinterpret_cast<const uint4 *>(pk)[1];
+        } else if constexpr (BYTES == 16) {
+            *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(pk);
+        } else {
             *reinterpret_cast<uint2 *>(dst) = *reinterpret_cast<const uint2 *>(pk);
         }
     } else {
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < N; ++i)
             if (i < n_ok) dst[i] = Cvt<T>::from_f(v[i]);
     }
 }
@@ -160,7 +170,7 @@ upfirdn2d_stream_kernel(T *__restrict__ out, const T *__restrict__ x, const floa
         for (int b = 0; b < 4; ++b)
             kf[a][b] = (a < p.kh && b < p.kw) ? __ldg(taps + (p.kh - 1 - a) * p.kw + (p.kw - 1 - b)) : 0.f;
 
-#if SG2_US_PACKED
+#if SG2_US_PACKED && SG2_US_TX_WIDE == 4
     float2 kf2[4][4];                                              // (tap, tap): the multiplier pair of the packed FMAs
 #pragma unroll
     for (int a = 0; a < 4; ++a)
@@ -179,7 +189,7 @@ upfirdn2d_stream_kernel(T *__restrict__ out, const T *__restrict__ x, const floa
         const int strip = (int)(rest % p.n_strips); rest /= p.n_strips;
         const int band = (int)(rest % p.n_bands);
         const long long plane = rest / p.n_bands;
-        const int xs0 = strip * (WL * 4), y0 = band * p.rh, y1 = min(p.out_h, y0 + p.rh);
+        const int xs0 = strip * (WL * G::TX), y0 = band * p.rh, y1 = min(p.out_h, y0 + p.rh);
         const int nrows = y1 - y0;
         // first input row / column of the strip and number of input rows to walk
         int iy_first, cx0, nsteps;
@@ -233,14 +243,14 @@ upfirdn2d_stream_kernel(T *__restrict__ out, const T *__restrict__ x, const floa
 #pragma unroll
         for (int d = 0; d < US_PF; ++d) fetch(d, pre[d]);
 
-        float acc[G::R][4];
+        float acc[G::R][G::TX];
 #pragma unroll
         for (int r = 0; r < G::R; ++r)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) acc[r][i] = 0.f;
+            for (int i = 0; i < G::TX; ++i) acc[r][i] = 0.f;
         T *oplane = out + plane * plane_out;
-        const int x0 = xs0 + 4 * t;
-        const int n_ok = active ? max(0, min(4, p.out_w - x0)) : 0;
+        const int x0 = xs0 + G::TX * t;
+        const int n_ok = active ? max(0, min(G::TX, p.out_w - x0)) : 0;
 
         for (int sb = 0; sb < nsteps_max; sb += US_PF) {
 #pragma unroll
@@ -268,7 +278,7 @@ upfirdn2d_stream_kernel(T *__restrict__ out, const T *__restrict__ x, const floa
                     // packed f32x2 FMAs over output pairs (0,1) and (2,3): half the FMA issue slots (the kernel is issue
                     // bound: 16 FMAs per output are 73 % of the FP32 pipe at the bf16 HBM roofline); per output the taps
                     // are still applied in ascending order, each lane of the pair is an ordinary fused multiply-add
-#if SG2_US_PACKED
+#if SG2_US_PACKED && SG2_US_TX_WIDE == 4
                     float2 wp[6];
 #pragma unroll
                     for (int j = 0; j < 6; ++j) wp[j] = make_float2(w[j], w[j + 1]);
@@ -289,7 +299,7 @@ upfirdn2d_stream_kernel(T *__restrict__ out, const T *__restrict__ x, const floa
                     for (int a = 0; a < 4; ++a) {
                         const int r = (u - a + 4) & 3;
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
+                        for (int i = 0; i < G::TX; ++i) {
                             float v = a == 0 ? 0.f : acc[r][i];
 #pragma unroll
                             for (int b = 0; b < 4; ++b) v = fmaf(w[i + b], kf[a][b], v);
@@ -299,7 +309,7 @@ upfirdn2d_stream_kernel(T *__restrict__ out, const T *__restrict__ x, const floa
 #endif
                     const int ol = s - 3;                          // finished: output row y0 + s - 3
                     if (ol >= 0 && ol < nrows && n_ok > 0)
-                        store4<T>(oplane + (long long)(y0 + ol) * p.out_w + x0, acc[(u + 1) & 3], n_ok, p.vec_store != 0);
+                        store_row<T, G::TX>(oplane + (long long)(y0 + ol) * p.out_w + x0, acc[(u + 1) & 3], n_ok, p.vec_store != 0);
                 } else if constexpr (UP == 1 && DOWN == 2) {
                     // input row s feeds tap rows a = (s & 1), (s & 1) + 2 of output rows (s - a) / 2
                     const int e = u & 1;
@@ -308,7 +318,7 @@ upfirdn2d_stream_kernel(T *__restrict__ out, const T *__restrict__ x, const floa
                         const int a = e + 2 * h;
                         const int r = (((u - a) / 2) + 2) & 1;     // (s - a) / 2 mod 2 with s = sb + u, sb % 4 == 0
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
+                        for (int i = 0; i < G::TX; ++i) {
                             float v = a == 0 ? 0.f : acc[r][i];
 #pragma unroll
                             for (int b = 0; b < 4; ++b) v = fmaf(w[2 * i + b], kf[a][b], v);
@@ -318,7 +328,7 @@ upfirdn2d_stream_kernel(T *__restrict__ out, const T *__restrict__ x, const floa
                     if (e == 1) {                                  // tap row 3 done: output row (s - 3) / 2 is finished
                         const int ol = (s - 3) / 2;
                         if (s >= 3 && ol < nrows && n_ok > 0)
-                            store4<T>(oplane + (long long)(y0 + ol) * p.out_w + x0, acc[(((u - 3) / 2) + 2) & 1], n_ok,
+                            store_row<T, G::TX>(oplane + (long long)(y0 + ol) * p.out_w + x0, acc[(((u - 3) / 2) + 2) & 1], n_ok,
                                       p.vec_store != 0);
                     }
                 } else {
@@ -328,25 +338,25 @@ upfirdn2d_stream_kernel(T *__restrict__ out, const T *__restrict__ x, const floa
 #pragma unroll
                     for (int a = 0; a < 4; ++a) {
                         const int r = (2 * u + 3 - a) & 3;
-                        float v[4];
+                        float v[G::TX];
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) v[i] = a < 2 ? 0.f : acc[r][i];   // a row starts with tap row 0 or 1
+                        for (int i = 0; i < G::TX; ++i) v[i] = a < 2 ? 0.f : acc[r][i];   // a row starts with tap row 0 or 1
 #pragma unroll
-                        for (int c = 0; c < 4; ++c)
+                        for (int c = 0; c < G::WU; ++c)
 #pragma unroll
                             for (int b = 0; b < 4; ++b) {
                                 const int i = 2 * c + PHX - b;
-                                if (i >= 0 && i < 4) v[i] = fmaf(w[c], kf[a][b], v[i]);
+                                if (i >= 0 && i < G::TX) v[i] = fmaf(w[c], kf[a][b], v[i]);
                             }
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) acc[r][i] = v[i];
+                        for (int i = 0; i < G::TX; ++i) acc[r][i] = v[i];
                     }
                     // finished: tap rows 3 and 2 -> output rows Y - 3 and Y - 2
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         const int oy = y0 + PHY + 2 * s - 3 + h;
                         if (oy >= y0 && oy < y1 && n_ok > 0)
-                            store4<T>(oplane + (long long)oy * p.out_w + x0, acc[(2 * u + h) & 3], n_ok, p.vec_store != 0);
+                            store_row<T, G::TX>(oplane + (long long)oy * p.out_w + x0, acc[(2 * u + h) & 3], n_ok, p.vec_store != 0);
                     }
                 }
             }
@@ -388,14 +398,15 @@ int launch_upfirdn2d_stream(void *out, const void *x, const float *taps, int64_t
     p.pad_x0 = pad_x0; p.pad_y0 = pad_y0; p.kh = kh; p.kw = kw;
     // lanes per strip: 4 output columns per lane (the 8-inputs-per-lane down-sampling window stays at 16 lanes: 9
     // prefetch registers per row)
-    int wl = 2;                                                      // 4 lanes: planes up to 16 columns wide, 8 planes per warp
-    while ((4 << wl) < out_w && wl < (down == 2 ? 4 : 5)) ++wl;
+    const int TX = down == 2 ? 4 : SG2_US_TX_WIDE;                   // SGeo<UP, DOWN>::TX
+    int wl = 2;                                                      // >= 4 lanes per plane, up to 8 planes per warp
+    while ((TX << wl) < out_w && wl < (down == 2 ? 4 : 5)) ++wl;
     p.wl_log2 = wl;
     p.planes = planes;
     const int WL = 1 << wl, NS = 32 >> wl;
-    const int LS = up == 2 ? 2 : 4 * down, WR = up == 2 ? 4 : (down == 1 ? 8 : 12);
+    const int LS = TX * down / up, WU = up == 2 ? TX / 2 + 2 : down * (TX - 1) + 4, WR = (WU + 3) & ~3;
     p.line_floats = ((WL - 1) * LS + WR + 3) & ~3;
-    p.n_strips = (out_w + 4 * WL - 1) / (4 * WL);
+    p.n_strips = (out_w + TX * WL - 1) / (TX * WL);
     // band height: tall enough to amortise the vertical halo, short enough for >= 4 items per resident group
     const int sms = sm_count();
     const int64_t groups = (int64_t)sms * 4 * US_WARPS * NS;
@@ -405,7 +416,7 @@ int launch_upfirdn2d_stream(void *out, const void *x, const float *taps, int64_t
     p.n_bands = (out_h + rh - 1) / rh;
     p.items = planes * p.n_strips * p.n_bands;
     const int es = (int)sizeof(T);
-    p.vec_store = (out_w % 4 == 0 && reinterpret_cast<uintptr_t>(out) % (4 * es) == 0) ? 1 : 0;
+    p.vec_store = (out_w % TX == 0 && reinterpret_cast<uintptr_t>(out) % std::min(16, TX * es) == 0) ? 1 : 0;
     const size_t smem = (size_t)US_WARPS * 2 * NS * p.line_floats * sizeof(float);
     const int64_t want = (p.items + (int64_t)US_WARPS * NS - 1) / ((int64_t)US_WARPS * NS);
     const int grid = (int)std::min<int64_t>(want, (int64_t)sms * 4);
