@@ -209,16 +209,15 @@ upfirdn2d_stream_kernel(T *__restrict__ out, const T *__restrict__ x, const floa
 
         // this lane stages line positions t + WL*i: which of them exist but lie OUTSIDE the plane (row invariant).
         // Rows are fetched without per-column predicates -- a column outside the plane reads a neighbouring row's
-        // element, which a fix-up then overwrites with zero in the staged line -- except for the two rows whose
-        // over-read would leave the tensor (first row of the first plane, last row of the last plane).
+        // element, which a fix-up then overwrites with zero in the staged line -- except for the rows whose
+        // over-read would leave the tensor (start of the first plane, end of the last plane).
         uint32_t outside = 0;
 #pragma unroll
         for (int i = 0; i < NI; ++i) {
             const int pos = t + WL * i, col = cx0 + pos;
             if ((i < G::LS || has_last) && (col < 0 || col >= p.in_w)) outside |= 1u << i;
         }
-        const bool guard_first = plane == 0 && cx0 < 0;
-        const bool guard_last = plane == p.planes - 1 && cx0 + line_len > p.in_w;
+        const long long item_first = plane * plane_in + cx0, total_in = p.planes * plane_in;   // element index of (row 0, position 0)
         const T *xp = x + plane * plane_in + cx0 + t;             // (row 0, position t)
 
         // ---- register prefetch ring: US_PF rows in flight ----
@@ -230,7 +229,9 @@ upfirdn2d_stream_kernel(T *__restrict__ out, const T *__restrict__ x, const floa
             if (!row_ok) {
 #pragma unroll
                 for (int i = 0; i < NI; ++i) r[i] = Cvt<T>::from_f(0.f);
-            } else if ((guard_first && iy == 0) || (guard_last && iy == p.in_h - 1)) {
+            } else if (item_first + (long long)iy * p.in_w < 0 || item_first + (long long)iy * p.in_w + line_len > total_in) {
+                // the over-read of this row would leave the tensor (first rows of the first plane, last rows of the
+                // last one; several rows when the plane is narrower than the staged line): per-column predicates
 #pragma unroll
                 for (int i = 0; i < NI; ++i)
                     r[i] = ((i < G::LS || has_last) && !((outside >> i) & 1u)) ? __ldg(rp + WL * i) : Cvt<T>::from_f(0.f);

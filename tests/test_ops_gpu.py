@@ -151,6 +151,22 @@ def test_upfirdn2d_streaming_low_precision(sg2, oracle, dtype, shape, up, down, 
     np.testing.assert_allclose(y.float().cpu().numpy(), ref.float().numpy(), rtol=0, atol=tol)
 
 
+def test_upfirdn2d_streaming_tensor_edges(sg2, oracle):
+    # planes narrower than the staged line: the unpredicated row fetch must not leave the tensor at either end
+    # (the input is the tail of an allocation, so an over-read would fault or pick up NaNs)
+    for shape, up, down, pad in (((3, 5, 8, 8), 2, 1, (2, 1)), ((2, 3, 9, 9), 1, 1, (2, 2)), ((1, 2, 17, 9), 1, 1, (1, 1)),
+                                 ((2, 2, 24, 20), 1, 2, (1, 1))):
+        n = int(np.prod(shape))
+        big = torch.full((n + 4096,), float("nan"), device=DEV)
+        x = big[2048:2048 + n].view(shape)
+        x.copy_(torch.randn(shape))
+        taps = torch.randn(4, 4)
+        y = sg2.upfirdn2d(x, taps.to(DEV), up, down, pad).cpu()
+        ref = oracle.upfirdn2d(x.cpu().double(), taps.double(), up, down, pad).float()
+        assert torch.isfinite(y).all()
+        np.testing.assert_allclose(y.numpy(), ref.numpy(), rtol=0, atol=1e-4)
+
+
 def test_upfirdn2d_unaligned_base_falls_back(sg2, oracle):
     # a storage offset of one element: not 16-byte aligned -> the TMA path declines, the tiled kernel answers
     big = torch.randn(2 * 3 * 100 * 100 + 1, device=DEV)

@@ -59,3 +59,53 @@ def test_upfirdn2d_vs_reference_extension(sg2):
         ours = sg2.upfirdn2d(x, taps, up, down, pad)
         theirs = theirs.view(b, c, ours.shape[2], ours.shape[3])
         np.testing.assert_allclose(ours.cpu().numpy(), theirs.cpu().numpy(), rtol=0, atol=1e-5)
+
+
+def _time(fn, iters=10):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+
+
+def test_not_slower_than_the_reference_extensions(sg2):
+    """Same GPU, same fp32 tensors (>= 2x L2), the reference's own CUDA kernels (compiled for sm_100a) beside ours.
+    Times land in $SG2_PERF_OUT (json) when set; the assertion is only that the replacement is not slower."""
+    import json
+    ref_up, ref_act = _load("upfirdn2d"), _load("fused")
+    taps = sg2.make_kernel([1, 3, 3, 1]).to(DEV)
+    rows = []
+    cases = [("blur 257->256", (16, 64, 257, 257), dict(up=1, down=1, pad=(1, 1)), 1.0),
+             ("up2 128->256", (16, 64, 128, 128), dict(up=2, down=1, pad=(2, 1)), 4.0),
+             ("down2 256->128", (16, 64, 256, 256), dict(up=1, down=2, pad=(1, 1)), 1.0)]
+    for name, shape, kw, kscale in cases:
+        x = torch.randn(shape, device=DEV)
+        b, c, h, w = shape
+        k = taps * kscale
+        x4 = x.reshape(-1, h, w, 1)
+        p0, p1 = kw["pad"]
+        t_ref = _time(lambda: ref_up.upfirdn2d(x4, k, kw["up"], kw["up"], kw["down"], kw["down"], p0, p1, p0, p1))
+        t_our = _time(lambda: sg2.upfirdn2d(x, k, **kw))
+        rows.append({"op": "upfirdn2d " + name, "shape": list(shape), "ref_ms": round(t_ref, 4), "ours_ms": round(t_our, 4),
+                     "speedup": round(t_ref / t_our, 2)})
+    x = torch.randn(16, 64, 256, 256, device=DEV)
+    bias = torch.randn(64, device=DEV)
+    empty = x.new_empty(0)
+    t_ref = _time(lambda: ref_act.fused_bias_act(x, bias, empty, 3, 0, 0.2, 2 ** 0.5))
+    t_our = _time(lambda: sg2.fused_leaky_relu(x, bias))
+    rows.append({"op": "fused_leaky_relu", "shape": list(x.shape), "ref_ms": round(t_ref, 4), "ours_ms": round(t_our, 4),
+                 "speedup": round(t_ref / t_our, 2)})
+    for r in rows:
+        print(r)
+    out = os.environ.get("SG2_PERF_OUT")
+    if out:
+        with open(out, "w") as f:
+            json.dump(rows, f, indent=1)
+    for r in rows:
+        assert r["ours_ms"] <= 1.1 * r["ref_ms"], r
