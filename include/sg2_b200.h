@@ -148,6 +148,9 @@ int sg2_smooth_upsample2x(void *out, const void *x, const float *taps, int64_t B
                           const void *noise, int64_t noise_bstride, const void *noise_strength,
                           const void *bias, const void *addend, int act, float alpha, float gain,
                           float clamp, int dtype, sg2_stream_t stream);
+/* adjoint of the plain SmoothUpsample: grad_out [planes, 2H, 2W] -> grad_x [planes, H, W] (autograd of utils.py:89-95) */
+int sg2_smooth_upsample2x_bwd(void *grad_x, const void *grad_out, const float *taps, int64_t planes, int H, int W,
+                              int dtype, sg2_stream_t stream);
 int sg2_ada_bias_act(void *out, const void *x, const void *noise, int64_t noise_bstride,
                      const void *noise_strength, const void *bias, int64_t B, int C, int64_t HW, int act,
                      float alpha, float gain, float clamp, int dtype, sg2_stream_t stream);
@@ -161,6 +164,12 @@ int sg2_avg_pool_int(void *out, const void *x, int64_t planes, int out_h, int ou
                      sg2_stream_t stream);
 int sg2_resize_bilinear(void *out, const void *x, int64_t planes, int in_h, int in_w, int out_h, int out_w,
                         int dtype, sg2_stream_t stream);
+/* Their adjoints (what autograd derives for the two calls above when the coaches back-propagate the image losses,
+ * coach_restyle_psp.py:86-101,143-156): grad_x from grad_out, same shape arguments as the forward call. */
+int sg2_avg_pool_int_bwd(void *grad_x, const void *grad_out, int64_t planes, int out_h, int out_w, int factor,
+                         int dtype, sg2_stream_t stream);
+int sg2_resize_bilinear_bwd(void *grad_x, const void *grad_out, int64_t planes, int in_h, int in_w, int out_h,
+                            int out_w, int dtype, sg2_stream_t stream);
 /* tensor2im on the device (restyle-encoder/utils/common.py:5-11): out[i] = uint8(clip((x[i] + 1) / 2, 0, 1) * 255),
  * same element order as x; `out` 4-byte aligned. */
 int sg2_image_to_uint8(void *out, const void *x, int64_t total, int dtype, sg2_stream_t stream);

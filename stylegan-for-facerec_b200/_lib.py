@@ -58,10 +58,13 @@ SIGNATURES = {
                                   c_int, c_i64, c_int, c_int, c_int, c_int, c_void_p]),
     "sg2_smooth_upsample2x": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_int, c_int, c_int, c_void_p, c_i64,
                                       c_void_p, c_void_p, c_void_p, c_int, c_float, c_float, c_float, c_int, c_void_p]),
+    "sg2_smooth_upsample2x_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_int, c_int, c_int, c_void_p]),
     "sg2_ada_bias_act": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_void_p, c_i64, c_int, c_i64,
                                  c_int, c_float, c_float, c_float, c_int, c_void_p]),
     "sg2_avg_pool_int": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_int, c_int, c_int, c_void_p]),
     "sg2_resize_bilinear": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "sg2_avg_pool_int_bwd": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_int, c_int, c_int, c_void_p]),
+    "sg2_resize_bilinear_bwd": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "sg2_image_to_uint8": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_void_p]),
     "sg2_synth_create": (c_int, [C.POINTER(c_void_p), c_int, c_int, c_int, C.POINTER(ConvParams), c_int,
                                  c_void_p, C.POINTER(c_float)]),

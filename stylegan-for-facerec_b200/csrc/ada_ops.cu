@@ -88,6 +88,40 @@ smooth_up2x_kernel(T *__restrict__ out, const T *__restrict__ x, const float *__
     }
 }
 
+// adjoint of the plain SmoothUpsample (no epilogue): grad_x[i][j] = sum over the outputs (Y, X) and taps (a, b) whose
+// clamped source cell is (i, j) of taps[a][b] * grad_out[Y][X].  One thread per input cell; the (few) matching
+// (output row, tap row) and (output column, tap column) pairs are enumerated with the forward's own index rule, so
+// the edge replication is transposed exactly.
+template <typename T>
+__global__ void __launch_bounds__(256)
+smooth_up2x_bwd_kernel(T *__restrict__ gx, const T *__restrict__ gy, const float *__restrict__ taps, long long planes, int H,
+                       int W) {
+    __shared__ float s_k[16];
+    if (threadIdx.x < 16) s_k[threadIdx.x] = taps[threadIdx.x];
+    __syncthreads();
+    const int j = blockIdx.x * 32 + (threadIdx.x & 31), i = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (i >= H || j >= W) return;
+    const int off[2][4] = {{-1, -1, 0, 0}, {-1, 0, 0, 1}};      // source cell of tap a relative to i' for output parity p
+    // matching (output index, tap) pairs along one axis: at most 3 cells x 2 parities x 4 taps, typically 6
+    int ry[12], ra[12], nr = 0, cx[12], cb[12], nc = 0;
+    for (int ii = max(i - 1, 0); ii <= min(i + 1, H - 1); ++ii)
+        for (int py = 0; py < 2; ++py)
+            for (int a = 0; a < 4; ++a)
+                if (min(max(ii + off[py][a], 0), H - 1) == i && nr < 12) { ry[nr] = 2 * ii + py; ra[nr] = a; ++nr; }
+    for (int jj = max(j - 1, 0); jj <= min(j + 1, W - 1); ++jj)
+        for (int px = 0; px < 2; ++px)
+            for (int b = 0; b < 4; ++b)
+                if (min(max(jj + off[px][b], 0), W - 1) == j && nc < 12) { cx[nc] = 2 * jj + px; cb[nc] = b; ++nc; }
+    const int OW = 2 * W;
+    for (long long plane = blockIdx.z; plane < planes; plane += gridDim.z) {
+        const T *gp = gy + plane * 4LL * H * W;
+        float acc = 0.f;
+        for (int r = 0; r < nr; ++r)
+            for (int c = 0; c < nc; ++c) acc = fmaf(s_k[ra[r] * 4 + cb[c]], Cvt<T>::to_f(gp[(long long)ry[r] * OW + cx[c]]), acc);
+        gx[plane * (long long)H * W + (long long)i * W + j] = Cvt<T>::from_f(acc);
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 ada_bias_act_kernel(T *__restrict__ out, const T *__restrict__ x, long long total, int C, long long HW, AdaEpilogue e) {
@@ -135,6 +169,19 @@ extern "C" int sg2_ada_bias_act(void *out, const void *x, const void *noise, int
     const unsigned blocks = (unsigned)std::min<long long>((total + 255) / 256, (long long)sm_count() * 32);
     SG2_DISPATCH_DTYPE(dtype, {
         ada_bias_act_kernel<T><<<blocks, 256, 0, as_stream(stream)>>>((T *)out, (const T *)x, total, C, (long long)HW, e);
+        SG2_LAUNCH_CHECK();
+    });
+    return SG2_OK;
+}
+
+extern "C" int sg2_smooth_upsample2x_bwd(void *grad_x, const void *grad_out, const float *taps, int64_t planes, int H, int W,
+                                         int dtype, sg2_stream_t stream) {
+    SG2_REQUIRE(planes >= 0 && H >= 1 && W >= 1, SG2_ERR_BAD_ARG, "smooth_upsample2x_bwd: bad shape");
+    if (planes == 0) return SG2_OK;
+    SG2_REQUIRE(grad_x && grad_out && taps, SG2_ERR_BAD_ARG, "smooth_upsample2x_bwd: null pointer");
+    dim3 grid((W + 31) / 32, (H + 7) / 8, (unsigned)std::min<long long>(planes, 16384));
+    SG2_DISPATCH_DTYPE(dtype, {
+        smooth_up2x_bwd_kernel<T><<<grid, 256, 0, as_stream(stream)>>>((T *)grad_x, (const T *)grad_out, taps, (long long)planes, H, W);
         SG2_LAUNCH_CHECK();
     });
     return SG2_OK;

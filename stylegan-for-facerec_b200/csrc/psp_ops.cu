@@ -59,6 +59,65 @@ resize_bilinear_kernel(T *__restrict__ out, const T *__restrict__ x, long long t
     }
 }
 
+// ---- adjoints (the ReStyle coaches back-propagate the image losses through both steps) ------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+avg_pool_int_bwd_kernel(T *__restrict__ gx, const T *__restrict__ gy, long long total, int OH, int OW, int f) {
+    const float inv = 1.f / (float)(f * f);
+    const int IW = OW * f, IH = OH * f;
+    for (long long idx = (long long)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (long long)gridDim.x * 256) {
+        const int ix = (int)(idx % IW);
+        const long long t = idx / IW;
+        const int iy = (int)(t % IH);
+        const long long plane = t / IH;
+        gx[idx] = Cvt<T>::from_f(Cvt<T>::to_f(gy[(plane * OH + iy / f) * OW + ix / f]) * inv);
+    }
+}
+
+// weight with which output index `dst` reads input index `i` (0 when it does not)
+__device__ __forceinline__ float bilinear_weight(int dst, float scale, int in_size, int i) {
+    int i0, i1;
+    float l0, l1;
+    bilinear_src(dst, scale, in_size, i0, i1, l0, l1);
+    return (i0 == i ? l0 : 0.f) + (i1 == i ? l1 : 0.f);
+}
+
+// output indices that can read input index i: src(dst) in (i - 1, i + 1), one extra on each side for rounding
+__device__ __forceinline__ void bilinear_dst_range(int i, float scale, int out_size, int &lo, int &hi) {
+    const float inv = 1.f / scale;
+    lo = i == 0 ? 0 : max(0, (int)floorf(((float)i - 0.5f) * inv - 0.5f) - 1);
+    hi = min(out_size - 1, (int)ceilf(((float)i + 1.5f) * inv - 0.5f) + 1);
+}
+
+// gather form (one thread per input cell, no atomics: deterministic)
+template <typename T>
+__global__ void __launch_bounds__(256)
+resize_bilinear_bwd_kernel(T *__restrict__ gx, const T *__restrict__ gy, long long total, int IH, int IW, int OH, int OW,
+                           float sh, float sw) {
+    for (long long idx = (long long)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (long long)gridDim.x * 256) {
+        const int ix = (int)(idx % IW);
+        const long long t = idx / IW;
+        const int iy = (int)(t % IH);
+        const long long plane = t / IH;
+        int ylo, yhi, xlo, xhi;
+        bilinear_dst_range(iy, sh, OH, ylo, yhi);
+        bilinear_dst_range(ix, sw, OW, xlo, xhi);
+        const T *g = gy + plane * OH * OW;
+        float acc = 0.f;
+        for (int oy = ylo; oy <= yhi; ++oy) {
+            const float wy = bilinear_weight(oy, sh, IH, iy);
+            if (wy == 0.f) continue;
+            float row = 0.f;
+            for (int ox = xlo; ox <= xhi; ++ox) {
+                const float wx = bilinear_weight(ox, sw, IW, ix);
+                if (wx != 0.f) row += wx * Cvt<T>::to_f(g[(long long)oy * OW + ox]);
+            }
+            acc += wy * row;
+        }
+        gx[idx] = Cvt<T>::from_f(acc);
+    }
+}
+
 // images in [-1, 1] -> uint8 (tensor2im of the reference's inference scripts, restyle-encoder/utils/common.py:5-11: ((x + 1) / 2).clip(0, 1) * 255),
 // done on the device so that only a quarter of the bytes crosses PCIe
 __device__ __forceinline__ uint32_t to_u8(float x) {
@@ -131,6 +190,36 @@ extern "C" int sg2_resize_bilinear(void *out, const void *x, int64_t planes, int
     const float sh = (float)in_h / (float)out_h, sw = (float)in_w / (float)out_w;
     SG2_DISPATCH_DTYPE(dtype, {
         resize_bilinear_kernel<T><<<blocks, 256, 0, as_stream(stream)>>>((T *)out, (const T *)x, total, in_h, in_w, out_h, out_w, sh, sw);
+        SG2_LAUNCH_CHECK();
+    });
+    return SG2_OK;
+}
+
+// adjoints of the two ops above: grad_x from grad_out (same shapes / factor as the forward call)
+extern "C" int sg2_avg_pool_int_bwd(void *grad_x, const void *grad_out, int64_t planes, int out_h, int out_w, int factor,
+                                    int dtype, sg2_stream_t stream) {
+    SG2_REQUIRE(planes >= 0 && out_h >= 1 && out_w >= 1 && factor >= 1 && factor <= 64, SG2_ERR_BAD_ARG, "avg_pool_int_bwd: bad shape");
+    if (planes == 0) return SG2_OK;
+    SG2_REQUIRE(grad_x && grad_out, SG2_ERR_BAD_ARG, "avg_pool_int_bwd: null pointer");
+    const long long total = (long long)planes * out_h * out_w * factor * factor;
+    const unsigned blocks = (unsigned)std::min<long long>((total + 255) / 256, (long long)sm_count() * 32);
+    SG2_DISPATCH_DTYPE(dtype, {
+        avg_pool_int_bwd_kernel<T><<<blocks, 256, 0, as_stream(stream)>>>((T *)grad_x, (const T *)grad_out, total, out_h, out_w, factor);
+        SG2_LAUNCH_CHECK();
+    });
+    return SG2_OK;
+}
+
+extern "C" int sg2_resize_bilinear_bwd(void *grad_x, const void *grad_out, int64_t planes, int in_h, int in_w, int out_h,
+                                       int out_w, int dtype, sg2_stream_t stream) {
+    SG2_REQUIRE(planes >= 0 && in_h >= 1 && in_w >= 1 && out_h >= 1 && out_w >= 1, SG2_ERR_BAD_ARG, "resize_bilinear_bwd: bad shape");
+    if (planes == 0) return SG2_OK;
+    SG2_REQUIRE(grad_x && grad_out, SG2_ERR_BAD_ARG, "resize_bilinear_bwd: null pointer");
+    const long long total = (long long)planes * in_h * in_w;
+    const unsigned blocks = (unsigned)std::min<long long>((total + 255) / 256, (long long)sm_count() * 32);
+    const float sh = (float)in_h / (float)out_h, sw = (float)in_w / (float)out_w;
+    SG2_DISPATCH_DTYPE(dtype, {
+        resize_bilinear_bwd_kernel<T><<<blocks, 256, 0, as_stream(stream)>>>((T *)grad_x, (const T *)grad_out, total, in_h, in_w, out_h, out_w, sh, sw);
         SG2_LAUNCH_CHECK();
     });
     return SG2_OK;

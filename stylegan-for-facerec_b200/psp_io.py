@@ -4,8 +4,9 @@
     y_hat = F.interpolate(y_hat, 112, mode='bilinear')   # coach_restyle_psp.py:156
 
 `FacePool` is a drop-in for the `torch.nn.AdaptiveAvgPool2d((256, 256))` the reference assigns to
-`pSp.face_pool`; `resize_bilinear` for the interpolate call.  Inference path (no autograd yet): a call that
-needs gradients raises."""
+`pSp.face_pool`; `resize_bilinear` for the interpolate call.  Both carry autograd (forward kernel + its exact
+adjoint kernel, csrc/psp_ops.cu) because the coaches back-propagate the image losses through them;
+`images_to_uint8` is an output conversion and has none."""
 import torch
 
 from . import _lib
@@ -18,16 +19,46 @@ def _guard(x, what):
         raise RuntimeError(f"sg2_b200 {what}: inference-only kernel (no autograd yet); detach the input or use torch.no_grad()")
 
 
-def face_pool(images: torch.Tensor, size=(256, 256)) -> torch.Tensor:
-    """AdaptiveAvgPool2d(size) for integer pooling ratios (1024 -> 256, 512 -> 256, 256 -> 256)."""
-    _guard(images, "face_pool")
-    oh, ow = (size, size) if isinstance(size, int) else size
-    b, c, h, w = images.shape
-    if h % oh or w % ow or h // oh != w // ow:
-        raise RuntimeError(f"sg2_b200 face_pool: {h}x{w} -> {oh}x{ow} is not an integer, isotropic ratio")
-    f = h // oh
-    if f == 1:
-        return images
+class _FacePoolFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, oh, ow, f):
+        ctx.geom = (oh, ow, f)
+        return _face_pool_fwd(x.detach(), oh, ow, f)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gy):
+        oh, ow, f = ctx.geom
+        gy = gy.contiguous()
+        b, c = gy.shape[:2]
+        gx = torch.empty((b, c, oh * f, ow * f), device=gy.device, dtype=gy.dtype)
+        with _lib.device_of(gy):
+            _lib.check(_lib.load().sg2_avg_pool_int_bwd(gx.data_ptr(), gy.data_ptr(), b * c, oh, ow, f, _lib.dtype_code(gy),
+                                                        _lib.stream_of(gy)), "avg_pool_int_bwd")
+        return gx, None, None, None
+
+
+class _ResizeBilinearFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, oh, ow):
+        ctx.geom = (x.shape[2], x.shape[3], oh, ow)
+        return _resize_fwd(x.detach(), oh, ow)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gy):
+        h, w, oh, ow = ctx.geom
+        gy = gy.contiguous()
+        b, c = gy.shape[:2]
+        gx = torch.empty((b, c, h, w), device=gy.device, dtype=gy.dtype)
+        with _lib.device_of(gy):
+            _lib.check(_lib.load().sg2_resize_bilinear_bwd(gx.data_ptr(), gy.data_ptr(), b * c, h, w, oh, ow,
+                                                           _lib.dtype_code(gy), _lib.stream_of(gy)), "resize_bilinear_bwd")
+        return gx, None, None
+
+
+def _face_pool_fwd(images, oh, ow, f):
+    b, c = images.shape[:2]
     x = images.contiguous()
     out = torch.empty((b, c, oh, ow), device=x.device, dtype=x.dtype)
     with _lib.device_of(x):
@@ -36,10 +67,7 @@ def face_pool(images: torch.Tensor, size=(256, 256)) -> torch.Tensor:
     return out
 
 
-def resize_bilinear(images: torch.Tensor, size) -> torch.Tensor:
-    """F.interpolate(images, size, mode='bilinear') with the PyTorch defaults (align_corners=False, no antialias)."""
-    _guard(images, "resize_bilinear")
-    oh, ow = (size, size) if isinstance(size, int) else size
+def _resize_fwd(images, oh, ow):
     b, c, h, w = images.shape
     x = images.contiguous()
     out = torch.empty((b, c, oh, ow), device=x.device, dtype=x.dtype)
@@ -47,6 +75,30 @@ def resize_bilinear(images: torch.Tensor, size) -> torch.Tensor:
         _lib.check(_lib.load().sg2_resize_bilinear(out.data_ptr(), x.data_ptr(), b * c, h, w, oh, ow, _lib.dtype_code(x),
                                                    _lib.stream_of(x)), "resize_bilinear")
     return out
+
+
+def face_pool(images: torch.Tensor, size=(256, 256)) -> torch.Tensor:
+    """AdaptiveAvgPool2d(size) for integer pooling ratios (1024 -> 256, 512 -> 256, 256 -> 256)."""
+    _lib.require_cuda(images)
+    oh, ow = (size, size) if isinstance(size, int) else size
+    b, c, h, w = images.shape
+    if h % oh or w % ow or h // oh != w // ow:
+        raise RuntimeError(f"sg2_b200 face_pool: {h}x{w} -> {oh}x{ow} is not an integer, isotropic ratio")
+    f = h // oh
+    if f == 1:
+        return images
+    if needs_grad(images):
+        return _FacePoolFunction.apply(images, oh, ow, f)
+    return _face_pool_fwd(images, oh, ow, f)
+
+
+def resize_bilinear(images: torch.Tensor, size) -> torch.Tensor:
+    """F.interpolate(images, size, mode='bilinear') with the PyTorch defaults (align_corners=False, no antialias)."""
+    _lib.require_cuda(images)
+    oh, ow = (size, size) if isinstance(size, int) else size
+    if needs_grad(images):
+        return _ResizeBilinearFunction.apply(images, oh, ow)
+    return _resize_fwd(images, oh, ow)
 
 
 class FacePool(torch.nn.Module):

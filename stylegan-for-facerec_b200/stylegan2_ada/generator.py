@@ -6,14 +6,15 @@ Per layer (SynthesisLayer2.forward, generator.py:186-204) the reference runs: af
 [N,O,I,k,k] -> demod -> grouped conv -> SmoothUpsample (3 ops) -> + noise -> + bias -> lrelu -> gain -> clamp.
 Here: one modulation kernel (style + demod table), one shared-weight conv over the whole batch, and ONE
 epilogue kernel (SmoothUpsample fused with noise, bias, lrelu, gain, clamp; or the plain epilogue when the
-layer does not up-sample).  Only the 'stylegan2' synthesis layer is implemented (the reference's default and
-the one psp.py builds); inference only (see utils.py)."""
+layer does not up-sample).  When a gradient is needed the layers compose the differentiable pieces instead
+(utils.py).  Only the 'stylegan2' synthesis layer is implemented (the reference's default and the one psp.py builds)."""
 import numpy as np
 import torch
 
 from ..stylegan2 import functional as K
-from .utils import (FullyConnectedLayer, SmoothUpsample, _no_grad_path, ada_bias_act, identity, normalize_2nd_moment,
-                    smooth_upsample2x)
+from ..stylegan2.op import fused_leaky_relu
+from .utils import (FullyConnectedLayer, SmoothUpsample, SmoothUpsampleFunction, ada_bias_act, identity, modulated_conv2d,
+                    normalize_2nd_moment, smooth_upsample2x)
 
 
 class Generator(torch.nn.Module):                            # generator.py:6-52
@@ -128,7 +129,10 @@ class SynthesisBlock(torch.nn.Module):                       # generator.py:114-
         x = self.conv1(x, next(w_iter), noise_mode=noise_mode)
         y = self.torgb(x, next(w_iter))
         # img = resampler(img); img.add_(y)  (generator.py:135-137) in one pass
-        img = smooth_upsample2x(img, self.resampler.kernel, addend=y)
+        if K.needs_grad(img, y):
+            img = SmoothUpsampleFunction.apply(img, self.resampler.kernel) + y
+        else:
+            img = smooth_upsample2x(img, self.resampler.kernel, addend=y)
         return x, img
 
 
@@ -144,7 +148,10 @@ class ToRGBLayer2(torch.nn.Module):                          # generator.py:142-
     def forward(self, x, w):
         if not x.is_cuda:
             raise RuntimeError("input must be a CUDA tensor")
-        _no_grad_path(x, w, self.weight, self.bias, self.affine.weight, self.affine.bias)
+        if K.needs_grad(x, w, self.weight, self.bias, self.affine.weight, self.affine.bias):
+            styles = self.affine(w) * self.weight_gain
+            y = modulated_conv2d(x=x, weight=self.weight, styles=styles, demodulate=False)
+            return torch.clamp(y + self.bias.to(y.dtype)[None, :, None, None], -256, 256)
         # styles * weight_gain folded into the weights; no demodulation
         wt, _ = K.conv_prep(self.weight.to(x.dtype), self.weight_gain, want_wsq=False)
         s, _ = K.modulation(w.to(x.dtype), self.affine.weight, self.affine.bias, None, self.weight.shape[0],
@@ -172,18 +179,24 @@ class SynthesisLayer2(torch.nn.Module):                      # generator.py:172-
     def forward(self, x, w, noise_mode, gain=1):
         if not x.is_cuda:
             raise RuntimeError("input must be a CUDA tensor")
-        _no_grad_path(x, w, self.weight, self.bias, self.noise_strength, self.affine.weight, self.affine.bias)
         cout = self.weight.shape[0]
         noise = None
         if noise_mode == 'random':
             noise = torch.randn([x.shape[0], 1, self.resolution, self.resolution], device=x.device, dtype=x.dtype)
         if noise_mode == 'const':
             noise = self.noise_const
+        g, c = self.activation_gain * gain, 256.0 * gain
+        if K.needs_grad(x, w, self.weight, self.bias, self.noise_strength, self.affine.weight, self.affine.bias):
+            y = modulated_conv2d(x=x, weight=self.weight, styles=self.affine(w), padding=self.padding)
+            if isinstance(self.resampler, SmoothUpsample):
+                y = SmoothUpsampleFunction.apply(y, self.resampler.kernel)
+            if noise is not None:
+                y = y + noise.to(y.dtype) * self.noise_strength.to(y.dtype)
+            return torch.clamp(fused_leaky_relu(y, self.bias.to(y.dtype), 0.2, g), -c, c)
         wt, wsq = K.conv_prep(self.weight.to(x.dtype), 1.0, want_wsq=True)
         s, d = K.modulation(w.to(x.dtype), self.affine.weight, self.affine.bias, wsq, cout, self.affine.weight_gain,
                             self.affine.bias_gain, True)
         y = K.shared_conv(x, wt, s, d, cout, 3, 0)
-        g, c = self.activation_gain * gain, 256.0 * gain
         if isinstance(self.resampler, SmoothUpsample):
             return smooth_upsample2x(y, self.resampler.kernel, noise, self.noise_strength, self.bias, None, act=3,
                                      gain=g, clamp=c)

@@ -1,8 +1,11 @@
 """B200 host mirror of restyle-encoder/models/stylegan2_ada/utils.py (same names, arguments, state_dict
 keys); the arithmetic runs on the sg2_b200 kernels (csrc/ada_ops.cu, modconv_simt.cu, linear.cu).
 
-This is the INFERENCE path of the ADA decoder: the kernels have no autograd yet,
-so a call that needs gradients raises instead of silently leaving the native path."""
+Two paths, like stylegan2/model.py: without autograd every layer is three fused kernels; when a gradient is needed
+(the ReStyle coaches back-propagate through the frozen decoder) the same arithmetic is composed from the
+differentiable pieces -- the shared-weight conv `Function` (forward and dgrad on the sg2 kernel), the
+SmoothUpsample `Function` below (forward + its exact adjoint kernel), `fused_leaky_relu` -- with torch elementwise
+ops in between."""
 import math
 
 import numpy as np
@@ -98,6 +101,30 @@ def smooth_upsample2x(x, kernel, noise=None, noise_strength=None, bias=None, add
     return out
 
 
+class SmoothUpsampleFunction(torch.autograd.Function):
+    """plain SmoothUpsample with autograd: forward sg2_smooth_upsample2x, backward its adjoint kernel"""
+
+    @staticmethod
+    def forward(ctx, x, kernel):
+        ctx.save_for_backward(kernel)
+        with torch.no_grad():
+            return smooth_upsample2x(x.detach(), kernel.detach())
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gy):
+        kernel, = ctx.saved_tensors
+        gy = gy.contiguous()
+        b, c, oh, ow = gy.shape
+        taps = kernel.detach().to(device=gy.device, dtype=torch.float32).reshape(-1).contiguous()
+        gx = torch.empty((b, c, oh // 2, ow // 2), device=gy.device, dtype=gy.dtype)
+        with _lib.device_of(gy):
+            _lib.check(_lib.load().sg2_smooth_upsample2x_bwd(gx.data_ptr(), gy.data_ptr(), taps.data_ptr(), b * c, oh // 2,
+                                                             ow // 2, _lib.dtype_code(gy), _lib.stream_of(gy)),
+                       "smooth_upsample2x_bwd")
+        return gx, None
+
+
 class FullyConnectedLayer(torch.nn.Module):                  # utils.py:34-52
     def __init__(self, in_features, out_features, bias=True, activation='linear', lr_multiplier=1, bias_init=0):
         super().__init__()
@@ -135,16 +162,25 @@ class SmoothUpsample(torch.nn.Module):                       # utils.py:76-95
         self.kernel = torch.nn.Parameter(kernel, requires_grad=False)
 
     def forward(self, x: torch.Tensor):
+        if K.needs_grad(x):
+            return SmoothUpsampleFunction.apply(x, self.kernel)
         return smooth_upsample2x(x, self.kernel)
 
 
 def modulated_conv2d(x, weight, styles, padding=0, demodulate=True):
     """utils.py:118-137 without per-sample weights: y = d[b,o] * conv(W, s[b,i] * x), d = rsqrt(sum (W s)^2 + 1e-8)."""
     _lib.require_cuda(x)
-    _no_grad_path(x, weight, styles)
     k = weight.shape[-1]
     if k not in (1, 3) or padding != k // 2:
         raise RuntimeError(f"sg2_b200 modulated_conv2d: kernel {k} / padding {padding} not supported (1x1 pad 0, 3x3 pad 1)")
+    if K.needs_grad(x, weight, styles):
+        b = x.shape[0]
+        y = K.SharedConvFunction.apply(x * styles.to(x.dtype).view(b, -1, 1, 1), weight.to(x.dtype), 0)
+        if demodulate:
+            wsq = weight.float().square().sum([2, 3])                          # [Cout, Cin]
+            d = torch.rsqrt(styles.float().square() @ wsq.t() + 1e-8)           # [B, Cout]
+            y = y * d.to(y.dtype).view(b, -1, 1, 1)
+        return y
     wt, wsq = K.conv_prep(weight.to(x.dtype), 1.0, want_wsq=demodulate)
     s = styles.detach().float().contiguous()
     d = None
