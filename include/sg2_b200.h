@@ -222,6 +222,18 @@ int sg2_synth_forward(sg2_synth *plan, void *workspace, const float *latent, int
 int sg2_synth_set_profile_events(sg2_synth *plan, void **events, int n_events);
 int sg2_synth_profile_events_used(const sg2_synth *plan);
 
+/* ---------------------------------------------------------------------------------------------
+ * One 3x3 stride-1 'same' convolution on the tensor-core kernel (tcgen05/TMEM, operands by TMA), outside the
+ * whole-network plan: the contraction inside ModulatedConv2d.forward (model.py:254-273: F.conv2d with padding 1)
+ * once modulation and demodulation are factored out, and -- called with flipped taps and swapped channel roles --
+ * what autograd derives as its input gradient.  NHWC bf16 operands, fp32 accumulation:
+ *   out[b,y,x,co] = scale[b,co] * sum_{a,c,ci} x[b, y+a-1, x+c-1, ci] * wp[a*3+c][co][ci]
+ * x [B,r,r,Cin], out [B,r,r,Cout] bf16 (16-byte aligned), scale [B,Cout] fp32, Cin % 32 == 0, Cout % 16 == 0, r >= 4.
+ * sg2_conv3x3_tc_pack: weight fp32 [Cout,Cin,3,3] -> wp bf16 [9][Cout][Cin], `scale` folded in.            */
+int sg2_conv3x3_tc_pack(void *wp, const float *weight, int cin, int cout, float scale, sg2_stream_t stream);
+int sg2_conv3x3_tc(void *out, const void *x, const void *wp, const float *scale, int64_t B, int r, int cin,
+                   int cout, sg2_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

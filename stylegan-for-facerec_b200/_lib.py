@@ -72,6 +72,8 @@ SIGNATURES = {
     "sg2_synth_workspace_bytes": (c_i64, [c_void_p]),
     "sg2_synth_describe": (c_int, [c_void_p, C.c_char_p, c_int]),
     "sg2_synth_pack": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "sg2_conv3x3_tc_pack": (c_int, [c_void_p, c_void_p, c_int, c_int, C.c_float, c_void_p]),
+    "sg2_conv3x3_tc": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_int, c_int, c_void_p]),
     "sg2_synth_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, C.POINTER(c_void_p),
                                   C.POINTER(c_i64), c_void_p, c_void_p]),
     "sg2_synth_set_profile_events": (c_int, [c_void_p, C.POINTER(c_void_p), c_int]),

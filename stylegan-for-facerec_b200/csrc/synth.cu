@@ -642,3 +642,51 @@ extern "C" int sg2_synth_forward(sg2_synth *S, void *workspace, const float *lat
     }
     return SG2_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// One 3x3 stride-1 'same' convolution on the tensor-core kernel, outside the whole-network plan: the contraction of
+// ModulatedConv2d (model.py:232-273 of the reference) once modulation / demodulation are factored out, and -- with the
+// taps flipped and the channel roles swapped by the caller -- its input gradient.  NHWC bf16 in and out, fp32
+// accumulation, out[b,y,x,co] = scale[b,co] * sum_{a,b',ci} x[b, y+a-1, x+b'-1, ci] * wp[a*3+b'][co][ci].
+// Used by the differentiable path (stylegan2/functional.py, SharedConvFunction) when bf16 operands are allowed.
+extern "C" int sg2_conv3x3_tc_pack(void *wp, const float *weight, int cin, int cout, float scale, sg2_stream_t stream) {
+    SG2_REQUIRE(wp && weight && cin >= 1 && cout >= 1, SG2_ERR_BAD_ARG, "conv3x3_tc_pack: bad argument");
+    return launch_pack_conv_weight((__nv_bfloat16 *)wp, nullptr, weight, cin, cout, 9, scale, as_stream(stream));
+}
+
+extern "C" int sg2_conv3x3_tc(void *out, const void *x, const void *wp, const float *scale, int64_t B64, int r, int cin,
+                              int cout, sg2_stream_t stream) {
+    SG2_REQUIRE(B64 >= 0 && B64 <= 65535 && r >= 4 && r <= 4096, SG2_ERR_BAD_ARG, "conv3x3_tc: bad shape (B %lld, r %d)",
+                (long long)B64, r);
+    SG2_REQUIRE(cin >= 32 && cin % 32 == 0 && cout >= 16 && cout % 16 == 0 && cout <= 4096 && cin <= 4096, SG2_ERR_UNSUPPORTED,
+                "conv3x3_tc: needs Cin %% 32 == 0 and Cout %% 16 == 0, got %d -> %d", cin, cout);
+    if (B64 == 0) return SG2_OK;
+    SG2_REQUIRE(out && x && wp && scale, SG2_ERR_BAD_ARG, "conv3x3_tc: null pointer");
+    SG2_REQUIRE(((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(wp)) & 15) == 0,
+                SG2_ERR_BAD_ARG, "conv3x3_tc: tensors must be 16-byte aligned");
+    SG2_REQUIRE((long long)B64 * r * r * cout < (1LL << 34), SG2_ERR_UNSUPPORTED, "conv3x3_tc: output too large for 32-bit row offsets");
+    int dev = 0, major = 0;
+    SG2_CUDA_OK(cudaGetDevice(&dev));
+    SG2_CUDA_OK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    SG2_REQUIRE(major == 10, SG2_ERR_NO_DEVICE, "conv3x3_tc: needs an sm_100 device (tcgen05/TMEM), found compute capability %d.x", major);
+    const int B = (int)B64;
+    sg2_synth S;                                   // only max_batch and the SM count are read by the tile planner
+    S.max_batch = B;
+    S.sms = sm_count();
+    Layer L;
+    memset(&L.p, 0, sizeof(L.p));
+    L.p.cin = cin; L.p.cout = cout; L.p.ksize = 3; L.p.upsample = 0; L.p.resolution = r;
+    L.rgb = false;
+    L.res_in = L.res_out = r;
+    int rc = plan_gemm(&S, L);
+    if (rc) return rc;
+    finalize_tiles(L.gp, B);
+    rc = encode_maps(&S, L, (const __nv_bfloat16 *)x, (const __nv_bfloat16 *)wp, B);
+    if (rc) return rc;
+    GemmParams g = L.gp;
+    g.mode = 1;                                    // plain scaled store
+    g.demod = scale;
+    g.out = (__nv_bfloat16 *)out;
+    return L.two_sm ? launch_modconv_gemm2(g, L.tmA, L.tmB, S.sms, as_stream(stream))
+                    : launch_modconv_gemm(g, L.tmA, L.tmB, S.sms, as_stream(stream));
+}

@@ -4,6 +4,8 @@ Each wrapper makes inputs contiguous, allocates outputs/workspace with torch's c
 and passes raw pointers + the current stream; the C side owns nothing.
 """
 import math
+import os
+import threading
 
 import torch
 import ctypes as C
@@ -153,17 +155,74 @@ def torgb_combine(conv, bias, skip, kernel, pad):
     return out
 
 
+# ---- tensor-core route of the differentiable path ---------------------------------------------------------------
+# With bf16 operands allowed (Generator.precision == 'bf16', SG2_B200_PRECISION=bf16, or bfloat16 tensors) the 3x3
+# stride-1 convolutions of the autograd path -- forward and input gradient, 2/3 of the decoder's training FLOPs --
+# run on the tcgen05 kernel of the engine (sg2_conv3x3_tc: NHWC bf16 operands, fp32 accumulation).
+_tc_grad = threading.local()
+
+
+def tc_grad_enabled() -> bool:
+    v = getattr(_tc_grad, "on", None)
+    return (os.environ.get("SG2_B200_PRECISION", "auto") == "bf16") if v is None else v
+
+
+class tc_grad:
+    """context manager: allow (or forbid) bf16 tensor-core convolutions inside the differentiable path"""
+
+    def __init__(self, on: bool):
+        self.on = on
+
+    def __enter__(self):
+        self.prev = getattr(_tc_grad, "on", None)
+        if self.on is not None:                 # None: leave the ambient setting (environment default)
+            _tc_grad.on = self.on
+
+    def __exit__(self, *exc):
+        _tc_grad.on = self.prev
+        return False
+
+
+def tc_conv_ok(x, weight4, mode) -> bool:
+    cout, cin, k, _ = weight4.shape
+    return (mode == 0 and k == 3 and x.dim() == 4 and x.shape[2] == x.shape[3] and x.shape[2] >= 4 and cin % 32 == 0
+            and cout % 32 == 0 and x.shape[0] >= 1 and (x.dtype == torch.bfloat16 or tc_grad_enabled()))
+
+
+def tc_conv3x3(x, weight4, scale=None):
+    """y = scale[b,co] * conv2d(x, weight4, padding=1) on the tensor-core kernel: x [B,Cin,r,r] any float dtype -> same dtype."""
+    _lib.require_cuda(x)
+    lib = _lib.load()
+    cout, cin = weight4.shape[:2]
+    B, _, r, _ = x.shape
+    xh = x.detach().permute(0, 2, 3, 1).to(torch.bfloat16).contiguous()                 # NHWC bf16
+    w = weight4.detach().float().contiguous()
+    wp = torch.empty((9, cout, cin), device=x.device, dtype=torch.bfloat16)
+    ones = torch.ones((B, cout), device=x.device, dtype=torch.float32) if scale is None else scale.detach().float().contiguous()
+    out = torch.empty((B, r, r, cout), device=x.device, dtype=torch.bfloat16)
+    with _lib.device_of(x):
+        st = _lib.stream_of(x)
+        _lib.check(lib.sg2_conv3x3_tc_pack(wp.data_ptr(), w.data_ptr(), cin, cout, 1.0, st), "conv3x3_tc_pack")
+        _lib.check(lib.sg2_conv3x3_tc(out.data_ptr(), xh.data_ptr(), wp.data_ptr(), ones.data_ptr(), B, r, cin, cout, st),
+                   "conv3x3_tc")
+    return out.permute(0, 3, 1, 2).to(x.dtype)
+
+
 class SharedConvFunction(torch.autograd.Function):
     """y = conv(x, W) with one weight tensor shared by the batch (the contraction inside
     ModulatedConv2d once modulation/demodulation are factored out).  forward and grad_x run on the
-    sg2 SIMT kernel; grad_W (only when the decoder itself is trained) uses the library wgrad."""
+    sg2 kernels (fp32 SIMT; the tcgen05 kernel for 3x3 stride-1 layers when bf16 operands are allowed,
+    see tc_grad); grad_W (only when the decoder itself is trained) uses the library wgrad."""
 
     @staticmethod
     def forward(ctx, x, weight4, mode):
         cout, cin, k, _ = weight4.shape
-        wt, _ = conv_prep(weight4, 1.0, want_wsq=False)
         ctx.save_for_backward(x, weight4)
         ctx.mode = mode
+        ctx.tc = tc_conv_ok(x, weight4, mode)
+        if ctx.tc:
+            return tc_conv3x3(x, weight4)
+        wt, _ = conv_prep(weight4, 1.0, want_wsq=False)
         return shared_conv(x, wt, None, None, cout, k, mode)
 
     @staticmethod
@@ -177,6 +236,8 @@ class SharedConvFunction(torch.autograd.Function):
             if mode == 0:      # adjoint of a stride-1 'same' correlation: swap channels, flip taps
                 wadj = weight4.detach().flip([2, 3]).transpose(0, 1)
                 amode = 0
+                if ctx.tc:
+                    return tc_conv3x3(gy, wadj), (SharedConvFunction._wgrad(ctx, x, weight4, gy) if ctx.needs_input_grad[1] else None), None
             elif mode == 1:    # adjoint of conv_transpose(stride 2) is conv(stride 2) with the same taps
                 wadj = weight4.detach().transpose(0, 1)
                 amode = 2
@@ -190,14 +251,20 @@ class SharedConvFunction(torch.autograd.Function):
                 full[:, :, :gx.shape[2], :gx.shape[3]] = gx
                 gx = full
         if ctx.needs_input_grad[1]:
-            import torch.nn.grad as G
-            xf, gf = x.detach().float(), gy.detach().float()
-            with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):   # true-fp32 wgrad
-                if mode == 0:
-                    gw = G.conv2d_weight(xf, weight4.shape, gf, padding=k // 2)
-                elif mode == 2:
-                    gw = G.conv2d_weight(xf, weight4.shape, gf, stride=2)
-                else:   # y = conv_transpose(x, W^T): dW[co,ci] = corr(gy[co], x[ci]) at stride 2
-                    gw = G.conv2d_weight(gf, (cin, cout, k, k), xf, stride=2).transpose(0, 1)
-            gw = gw.to(weight4.dtype)
+            gw = SharedConvFunction._wgrad(ctx, x, weight4, gy)
         return gx, gw, None
+
+    @staticmethod
+    def _wgrad(ctx, x, weight4, gy):
+        import torch.nn.grad as G
+        mode = ctx.mode
+        cout, cin, k, _ = weight4.shape
+        xf, gf = x.detach().float(), gy.detach().float()
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):   # true-fp32 wgrad
+            if mode == 0:
+                gw = G.conv2d_weight(xf, weight4.shape, gf, padding=k // 2)
+            elif mode == 2:
+                gw = G.conv2d_weight(xf, weight4.shape, gf, stride=2)
+            else:   # y = conv_transpose(x, W^T): dW[co,ci] = corr(gy[co], x[ci]) at stride 2
+                gw = G.conv2d_weight(gf, (cin, cout, k, k), xf, stride=2).transpose(0, 1)
+        return gw.to(weight4.dtype)

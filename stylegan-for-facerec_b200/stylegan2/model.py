@@ -400,16 +400,19 @@ class Generator(nn.Module):
             image = self.engine().synthesize(latent, noise)
             return (image, latent) if return_latents else (image, None)
 
-        out = self.input(latent)
-        out = self.conv1(out, latent[:, 0], noise=noise[0])
-        skip = self.to_rgb1(out, latent[:, 1])
-        i = 1
-        for conv1, conv2, noise1, noise2, to_rgb in zip(self.convs[::2], self.convs[1::2], noise[1::2],
-                                                        noise[2::2], self.to_rgbs):
-            out = conv1(out, latent[:, i], noise=noise1)
-            out = conv2(out, latent[:, i + 1], noise=noise2)
-            skip = to_rgb(out, latent[:, i + 2], skip)
-            i += 2
+        # precision == 'bf16' with gradients: the 3x3 stride-1 convolutions of the differentiable path (forward and
+        # input gradient) run on the tensor-core kernel with bf16 operands; everything else stays fp32
+        with K.tc_grad(True if self.precision == 'bf16' else (False if self.precision == 'exact' else None)):
+            out = self.input(latent)
+            out = self.conv1(out, latent[:, 0], noise=noise[0])
+            skip = self.to_rgb1(out, latent[:, 1])
+            i = 1
+            for conv1, conv2, noise1, noise2, to_rgb in zip(self.convs[::2], self.convs[1::2], noise[1::2],
+                                                            noise[2::2], self.to_rgbs):
+                out = conv1(out, latent[:, i], noise=noise1)
+                out = conv2(out, latent[:, i + 1], noise=noise2)
+                skip = to_rgb(out, latent[:, i + 2], skip)
+                i += 2
         image = skip
         if return_latents:
             return image, latent

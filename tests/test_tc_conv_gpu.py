@@ -1,0 +1,104 @@
+"""GPU: the stand-alone tensor-core 3x3 convolution (sg2_conv3x3_tc) and the bf16 route of the differentiable path
+vs fp64 F.conv2d on CPU (the call ModulatedConv2d.forward makes, model.py:269-273 of the reference)."""
+import importlib
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _K():
+    return importlib.import_module("stylegan-for-facerec_b200.stylegan2.functional")
+
+
+def _bf(t):
+    return t.bfloat16().float()
+
+
+@pytest.mark.parametrize("B,cin,cout,r", [(2, 64, 32, 16), (3, 512, 512, 4), (1, 32, 32, 64), (2, 128, 256, 32), (5, 64, 64, 8),
+                                          (1, 256, 256, 32), (2, 96, 160, 12), (1, 64, 64, 20), (4, 32, 64, 5)])
+def test_conv3x3_tc_vs_fp64(sg2, B, cin, cout, r):
+    K = _K()
+    g = torch.Generator().manual_seed(B * 1000 + cin + r)
+    x = _bf(torch.randn(B, cin, r, r, generator=g))
+    w = _bf(torch.randn(cout, cin, 3, 3, generator=g) / (3 * cin ** 0.5))
+    sc = torch.rand(B, cout, generator=g) + 0.5
+    ref = F.conv2d(x.double(), w.double(), padding=1) * sc.double().view(B, cout, 1, 1)
+    y = K.tc_conv3x3(x.to(DEV), w.to(DEV), sc.to(DEV))
+    assert y.shape == ref.shape and y.dtype == torch.float32
+    err = (y.cpu().double() - ref).abs().max().item()
+    assert err <= 6e-3 * ref.abs().max().item(), (err, ref.abs().max().item())     # bf16 output rounding: 2^-8 relative
+    yb = K.tc_conv3x3(x.to(DEV).bfloat16(), w.to(DEV))                            # bf16 in -> bf16 out, no scale
+    ref1 = F.conv2d(x.double(), w.double(), padding=1)
+    assert yb.dtype == torch.bfloat16 and (yb.cpu().double() - ref1).abs().max() <= 6e-3 * ref1.abs().max()
+
+
+def test_conv3x3_tc_rejects_what_it_cannot_run(sg2):
+    K = _K()
+    x = torch.randn(1, 24, 8, 8, device=DEV)
+    with pytest.raises(RuntimeError, match="Cin"):
+        K.tc_conv3x3(x, torch.randn(32, 24, 3, 3, device=DEV))
+    assert not K.tc_conv_ok(x, torch.randn(32, 24, 3, 3), 0)
+    xb = torch.randn(1, 32, 8, 8, device=DEV)
+    w = torch.randn(32, 32, 3, 3)
+    assert not K.tc_conv_ok(xb, w, 0)                                  # fp32 tensors, bf16 operands not allowed
+    with K.tc_grad(True):
+        assert K.tc_conv_ok(xb, w, 0) and not K.tc_conv_ok(xb, w, 1) and not K.tc_conv_ok(xb, w[:, :, :1, :1], 0)
+    assert K.tc_conv_ok(xb.bfloat16(), w, 0)
+    with K.tc_grad(False):
+        assert not K.tc_conv_ok(xb, w, 0)
+
+
+@pytest.mark.parametrize("B,cin,cout,r", [(2, 64, 32, 16), (3, 512, 512, 4), (1, 32, 64, 32)])
+def test_shared_conv_function_tensor_core_gradients(sg2, B, cin, cout, r):
+    K = _K()
+    g = torch.Generator().manual_seed(cin + r)
+    x = _bf(torch.randn(B, cin, r, r, generator=g))
+    w = _bf(torch.randn(cout, cin, 3, 3, generator=g) / (3 * cin ** 0.5))
+    gy = _bf(torch.randn(B, cout, r, r, generator=g))
+    x64, w64 = x.double().requires_grad_(True), w.double().requires_grad_(True)
+    ref = F.conv2d(x64, w64, padding=1)
+    ref.backward(gy.double())
+    xd, wd = x.to(DEV).requires_grad_(True), w.to(DEV).requires_grad_(True)
+    with K.tc_grad(True):
+        y = K.SharedConvFunction.apply(xd, wd, 0)
+    y.backward(gy.to(DEV))
+    for name, a, b in (("y", y.detach(), ref.detach()), ("gx", xd.grad, x64.grad), ("gw", wd.grad, w64.grad)):
+        err = (a.cpu().double() - b).abs().max().item()
+        assert err <= 6e-3 * b.abs().max().item(), (name, err, b.abs().max().item())
+    # and the fp32 route is untouched when bf16 operands are not allowed
+    xe = x.to(DEV).requires_grad_(True)
+    ye = K.SharedConvFunction.apply(xe, w.to(DEV), 0)
+    assert (ye.detach().cpu().double() - ref.detach()).abs().max() <= 1e-5 * ref.abs().max()
+
+
+def test_generator_bf16_gradients_vs_oracle(sg2, oracle):
+    """precision='bf16' with gradients: tensor-core convolutions inside the differentiable path"""
+    sd = oracle.init_state_dict(16, 512, 2)
+    G = sg2.Generator(16, 512, 2)
+    G.load_state_dict(sd)
+    G = G.to(DEV).eval()
+    G.precision = 'bf16'
+    for p in G.parameters():
+        p.requires_grad_(False)
+    lat = 0.5 * oracle.named_randn("grad:lat", (2, 6, 512), 3)
+    gy = oracle.named_randn("grad:gy", (2, 3, 16, 16), 3)
+    ld = lat.to(DEV).requires_grad_(True)
+    img, _ = G([ld], input_is_latent=True, randomize_noise=False)
+    img.backward(gy.to(DEV))
+    lo = lat.double().requires_grad_(True)
+    imgo, _ = oracle.generator_forward({k: v.double() for k, v in sd.items()}, 16, [lo], n_mlp=2, input_is_latent=True,
+                                       randomize_noise=False)
+    imgo.backward(gy.double())
+    assert (img.detach().cpu().double() - imgo.detach()).abs().max() <= 3e-2 * imgo.abs().max()
+    err = ld.grad.cpu().double() - lo.grad
+    # bf16 operand rounding (2^-9 per element) through 5 conv layers forward and back, amplified by the cancellation
+    # between the modulation and demodulation terms of d/ds: 4 % measured; a wrong tap flip or channel swap gives O(1)
+    assert err.norm() <= 8e-2 * lo.grad.norm(), (err.norm() / lo.grad.norm()).item()
+    G.precision = 'exact'
+    ld2 = lat.to(DEV).requires_grad_(True)
+    img2, _ = G([ld2], input_is_latent=True, randomize_noise=False)
+    assert (img2.detach().cpu().double() - imgo.detach()).abs().max() <= 1e-3 * max(1.0, imgo.abs().max().item())
