@@ -233,6 +233,16 @@ int sg2_synth_profile_events_used(const sg2_synth *plan);
 int sg2_conv3x3_tc_pack(void *wp, const float *weight, int cin, int cout, float scale, sg2_stream_t stream);
 int sg2_conv3x3_tc(void *out, const void *x, const void *wp, const float *scale, int64_t B, int r, int cin,
                    int cout, sg2_stream_t stream);
+/* The same kernel over a subset of the 3x3 window: taps = ntaps rows {dy, dx, w} (HOST array, dy/dx in -1..1, w in 0..8),
+ *   out[b,y,x,co] = scale[b,co] * sum_t sum_ci x[b, y+dy_t, x+dx_t, ci] * wp[w_t][co][ci]
+ * (the polyphase components of the stride-2 convolution autograd derives for the transposed conv are of this form). */
+int sg2_conv_taps_tc(void *out, const void *x, const void *wp, const float *scale, int64_t B, int r, int cin,
+                     int cout, const int *taps, int ntaps, sg2_stream_t stream);
+/* F.conv_transpose2d(x, w, stride=2, padding=0) (model.py:246-252, the up-sampling ModulatedConv2d before its blur) as
+ * four polyphase planes: planes[(py*2+px)][b][y][x][co] = scale[b,co] * T[b, 2y+py, 2x+px, co]; each plane is allocated
+ * (r+1) x (r+1), its valid extent is (r+1-py) x (r+1-px) and the rest is not written.  wp as above, Cout % 32 == 0. */
+int sg2_conv_transpose3x3_tc(void *planes, const void *x, const void *wp, const float *scale, int64_t B, int r, int cin,
+                    int cout, sg2_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -94,7 +94,8 @@ void choose_tile(int PH, int PW, int maxB, int &TH, int &TW, int &NB) {
     }
 }
 
-int plan_gemm(sg2_synth *S, Layer &L) {
+// custom_taps (plain convolutions only): n_custom rows of {dy, dx, weight tap index} instead of the 3x3 window
+int plan_gemm(sg2_synth *S, Layer &L, const int *custom_taps = nullptr, int n_custom = 0) {
     const int B = S->max_batch;
     GemmParams &g = L.gp;
     memset(&g, 0, sizeof(g));
@@ -111,8 +112,13 @@ int plan_gemm(sg2_synth *S, Layer &L) {
         if (!up) {
             q.PH = q.PW = r; q.out_H = q.out_W = r; q.out_off = 0;
             q.ntaps = 0;
-            for (int a = 0; a < 3; ++a)
-                for (int b = 0; b < 3; ++b) { q.dy[q.ntaps] = a - 1; q.dx[q.ntaps] = b - 1; q.wtap[q.ntaps] = a * 3 + b; ++q.ntaps; }
+            if (custom_taps) {
+                for (int t = 0; t < n_custom; ++t) { q.dy[t] = custom_taps[3 * t]; q.dx[t] = custom_taps[3 * t + 1]; q.wtap[t] = custom_taps[3 * t + 2]; }
+                q.ntaps = n_custom;
+            } else {
+                for (int a = 0; a < 3; ++a)
+                    for (int b = 0; b < 3; ++b) { q.dy[q.ntaps] = a - 1; q.dx[q.ntaps] = b - 1; q.wtap[q.ntaps] = a * 3 + b; ++q.ntaps; }
+            }
         } else {
             // transposed stride-2 conv: T[2i+a, 2j+b] += x[i,j] * w[a,b]; plane (py,px) holds T[2y+py, 2x+px]
             const int py = s >> 1, px = s & 1;
@@ -654,31 +660,45 @@ extern "C" int sg2_conv3x3_tc_pack(void *wp, const float *weight, int cin, int c
     return launch_pack_conv_weight((__nv_bfloat16 *)wp, nullptr, weight, cin, cout, 9, scale, as_stream(stream));
 }
 
-extern "C" int sg2_conv3x3_tc(void *out, const void *x, const void *wp, const float *scale, int64_t B64, int r, int cin,
-                              int cout, sg2_stream_t stream) {
-    SG2_REQUIRE(B64 >= 0 && B64 <= 65535 && r >= 4 && r <= 4096, SG2_ERR_BAD_ARG, "conv3x3_tc: bad shape (B %lld, r %d)",
+namespace {
+
+// shared body of the stand-alone entries: plan one layer, encode its descriptors, launch with the plain scaled store
+int run_single_conv(void *out, const void *x, const void *wp, const float *scale, int64_t B64, int r, int cin, int cout,
+                    int upsample, const int *taps, int ntaps, sg2_stream_t stream, const char *what) {
+    SG2_REQUIRE(B64 >= 0 && B64 <= 65535 && r >= 4 && r <= 4096, SG2_ERR_BAD_ARG, "%s: bad shape (B %lld, r %d)", what,
                 (long long)B64, r);
-    SG2_REQUIRE(cin >= 32 && cin % 32 == 0 && cout >= 16 && cout % 16 == 0 && cout <= 4096 && cin <= 4096, SG2_ERR_UNSUPPORTED,
-                "conv3x3_tc: needs Cin %% 32 == 0 and Cout %% 16 == 0, got %d -> %d", cin, cout);
+    SG2_REQUIRE(cin >= 32 && cin % 32 == 0 && cout >= 16 && cout % 16 == 0 && (!upsample || cout % 32 == 0) && cout <= 4096 &&
+                    cin <= 4096,
+                SG2_ERR_UNSUPPORTED, "%s: needs Cin %% 32 == 0 and Cout %% 16 == 0 (%% 32 for the transposed conv), got %d -> %d",
+                what, cin, cout);
+    if (taps) {
+        SG2_REQUIRE(ntaps >= 1 && ntaps <= kGemmMaxTaps, SG2_ERR_BAD_ARG, "%s: 1..%d taps, got %d", what, kGemmMaxTaps, ntaps);
+        for (int t = 0; t < ntaps; ++t)
+            SG2_REQUIRE(taps[3 * t] >= -1 && taps[3 * t] <= 1 && taps[3 * t + 1] >= -1 && taps[3 * t + 1] <= 1 && taps[3 * t + 2] >= 0 &&
+                            taps[3 * t + 2] < 9,
+                        SG2_ERR_BAD_ARG, "%s: tap %d (dy %d, dx %d, weight %d) outside the 3x3 window", what, t, taps[3 * t],
+                        taps[3 * t + 1], taps[3 * t + 2]);
+    }
     if (B64 == 0) return SG2_OK;
-    SG2_REQUIRE(out && x && wp && scale, SG2_ERR_BAD_ARG, "conv3x3_tc: null pointer");
+    SG2_REQUIRE(out && x && wp && scale, SG2_ERR_BAD_ARG, "%s: null pointer", what);
     SG2_REQUIRE(((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(wp)) & 15) == 0,
-                SG2_ERR_BAD_ARG, "conv3x3_tc: tensors must be 16-byte aligned");
-    SG2_REQUIRE((long long)B64 * r * r * cout < (1LL << 34), SG2_ERR_UNSUPPORTED, "conv3x3_tc: output too large for 32-bit row offsets");
+                SG2_ERR_BAD_ARG, "%s: tensors must be 16-byte aligned", what);
+    SG2_REQUIRE((long long)B64 * (r + 1) * (r + 1) * cout * (upsample ? 4 : 1) < (1LL << 34), SG2_ERR_UNSUPPORTED,
+                "%s: output too large for 32-bit row offsets", what);
     int dev = 0, major = 0;
     SG2_CUDA_OK(cudaGetDevice(&dev));
     SG2_CUDA_OK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
-    SG2_REQUIRE(major == 10, SG2_ERR_NO_DEVICE, "conv3x3_tc: needs an sm_100 device (tcgen05/TMEM), found compute capability %d.x", major);
+    SG2_REQUIRE(major == 10, SG2_ERR_NO_DEVICE, "%s: needs an sm_100 device (tcgen05/TMEM), found compute capability %d.x", what, major);
     const int B = (int)B64;
     sg2_synth S;                                   // only max_batch and the SM count are read by the tile planner
     S.max_batch = B;
     S.sms = sm_count();
     Layer L;
     memset(&L.p, 0, sizeof(L.p));
-    L.p.cin = cin; L.p.cout = cout; L.p.ksize = 3; L.p.upsample = 0; L.p.resolution = r;
+    L.p.cin = cin; L.p.cout = cout; L.p.ksize = 3; L.p.upsample = upsample; L.p.resolution = upsample ? 2 * r : r;
     L.rgb = false;
-    L.res_in = L.res_out = r;
-    int rc = plan_gemm(&S, L);
+    L.res_in = r; L.res_out = L.p.resolution;
+    int rc = plan_gemm(&S, L, taps, ntaps);
     if (rc) return rc;
     finalize_tiles(L.gp, B);
     rc = encode_maps(&S, L, (const __nv_bfloat16 *)x, (const __nv_bfloat16 *)wp, B);
@@ -687,6 +707,34 @@ extern "C" int sg2_conv3x3_tc(void *out, const void *x, const void *wp, const fl
     g.mode = 1;                                    // plain scaled store
     g.demod = scale;
     g.out = (__nv_bfloat16 *)out;
+    if (upsample) {
+        const long long plane = (long long)B * (r + 1) * (r + 1) * cout;
+        for (int s = 0; s < g.nsub; ++s) g.sub[s].out_off = plane * s;
+    }
     return L.two_sm ? launch_modconv_gemm2(g, L.tmA, L.tmB, S.sms, as_stream(stream))
                     : launch_modconv_gemm(g, L.tmA, L.tmB, S.sms, as_stream(stream));
+}
+
+}  // namespace
+
+extern "C" int sg2_conv3x3_tc(void *out, const void *x, const void *wp, const float *scale, int64_t B, int r, int cin,
+                              int cout, sg2_stream_t stream) {
+    return run_single_conv(out, x, wp, scale, B, r, cin, cout, 0, nullptr, 0, stream, "conv3x3_tc");
+}
+
+// the same kernel with an arbitrary subset of the 3x3 window: out[b,y,x,co] = scale[b,co] * sum_t sum_ci
+// x[b, y+dy_t, x+dx_t, ci] * wp[w_t][co][ci]; taps = ntaps rows of {dy, dx, w} (host array).  The polyphase
+// components of the stride-2 convolution that is the input gradient of the transposed conv are of this form.
+extern "C" int sg2_conv_taps_tc(void *out, const void *x, const void *wp, const float *scale, int64_t B, int r, int cin,
+                                int cout, const int *taps, int ntaps, sg2_stream_t stream) {
+    SG2_REQUIRE(taps, SG2_ERR_BAD_ARG, "conv_taps_tc: null tap list");
+    return run_single_conv(out, x, wp, scale, B, r, cin, cout, 0, taps, ntaps, stream, "conv_taps_tc");
+}
+
+// stride-2 transposed 3x3 convolution (F.conv_transpose2d(x, w, stride=2, padding=0), model.py:246-252) as its four
+// polyphase planes: planes[(py,px)][b][y][x][co] = scale[b,co] * T[b, 2y+py, 2x+px, co], allocated extent (r+1) x (r+1)
+// per plane, valid extent (r+1-py) x (r+1-px) (the rest is not written).
+extern "C" int sg2_conv_transpose3x3_tc(void *planes, const void *x, const void *wp, const float *scale, int64_t B, int r, int cin,
+                               int cout, sg2_stream_t stream) {
+    return run_single_conv(planes, x, wp, scale, B, r, cin, cout, 1, nullptr, 0, stream, "conv_transpose3x3_tc");
 }

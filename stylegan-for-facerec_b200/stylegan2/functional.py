@@ -185,8 +185,72 @@ class tc_grad:
 
 def tc_conv_ok(x, weight4, mode) -> bool:
     cout, cin, k, _ = weight4.shape
-    return (mode == 0 and k == 3 and x.dim() == 4 and x.shape[2] == x.shape[3] and x.shape[2] >= 4 and cin % 32 == 0
+    return (mode in (0, 1) and k == 3 and x.dim() == 4 and x.shape[2] == x.shape[3] and x.shape[2] >= 4 and cin % 32 == 0
             and cout % 32 == 0 and x.shape[0] >= 1 and (x.dtype == torch.bfloat16 or tc_grad_enabled()))
+
+
+def _tc_pack(weight4):
+    """weight fp32 [Cout,Cin,3,3] -> bf16 [9][Cout][Cin] as the tensor-core kernel reads it"""
+    cout, cin = weight4.shape[:2]
+    w = weight4.detach().float().contiguous()
+    wp = torch.empty((9, cout, cin), device=w.device, dtype=torch.bfloat16)
+    with _lib.device_of(w):
+        _lib.check(_lib.load().sg2_conv3x3_tc_pack(wp.data_ptr(), w.data_ptr(), cin, cout, 1.0, _lib.stream_of(w)),
+                   "conv3x3_tc_pack")
+    return wp
+
+
+def tc_conv_transpose3x3(x, weight4):
+    """y = conv_transpose2d(x, weight4^T, stride=2) (the up-sampling ModulatedConv2d before its blur) on the tensor-core
+    kernel: x [B,Cin,r,r], weight4 [Cout,Cin,3,3] -> [B,Cout,2r+1,2r+1] in x.dtype.  The kernel writes the four
+    polyphase planes; interleaving them into the NCHW result is four strided copies."""
+    _lib.require_cuda(x)
+    cout, cin = weight4.shape[:2]
+    B, _, r, _ = x.shape
+    P = r + 1
+    xh = x.detach().permute(0, 2, 3, 1).to(torch.bfloat16).contiguous()
+    wp = _tc_pack(weight4)
+    ones = torch.ones((B, cout), device=x.device, dtype=torch.float32)
+    planes = torch.empty((4, B, P, P, cout), device=x.device, dtype=torch.bfloat16)
+    with _lib.device_of(x):
+        _lib.check(_lib.load().sg2_conv_transpose3x3_tc(planes.data_ptr(), xh.data_ptr(), wp.data_ptr(), ones.data_ptr(), B, r, cin,
+                                               cout, _lib.stream_of(x)), "conv_transpose3x3_tc")
+    out = torch.empty((B, cout, 2 * r + 1, 2 * r + 1), device=x.device, dtype=x.dtype)
+    for s in range(4):
+        py, px = s >> 1, s & 1
+        out[:, :, py::2, px::2] = planes[s, :, :P - py, :P - px, :].permute(0, 3, 1, 2)
+    return out
+
+
+def tc_conv_transpose3x3_dgrad(gy, weight4):
+    """input gradient of tc_conv_transpose3x3: gx[i,j,ci] = sum_{a,b,co} gy[2i+a, 2j+b, co] * w[co,ci,a,b], a stride-2
+    convolution evaluated as the sum of four stride-1 convolutions (4, 2, 2, 1 taps) over the polyphase planes of gy."""
+    _lib.require_cuda(gy)
+    lib = _lib.load()
+    cout, cin = weight4.shape[:2]
+    B, _, R, _ = gy.shape
+    r = (R - 1) // 2
+    P = r + 1
+    planes = torch.zeros((4, B, P, P, cout), device=gy.device, dtype=torch.bfloat16)
+    g = gy.detach()
+    for s in range(4):
+        py, px = s >> 1, s & 1
+        planes[s, :, :P - py, :P - px, :] = g[:, :, py::2, px::2].permute(0, 2, 3, 1)
+    wp = _tc_pack(weight4.detach().transpose(0, 1))                     # contraction over Cout, output channel Cin
+    ones = torch.ones((B, cin), device=gy.device, dtype=torch.float32)
+    acc = None
+    with _lib.device_of(gy):
+        st = _lib.stream_of(gy)
+        for s in range(4):
+            py, px = s >> 1, s & 1
+            taps = [(da, db, (2 * da + py) * 3 + 2 * db + px) for da in range(2 - py) for db in range(2 - px)]
+            flat = (C.c_int * (3 * len(taps)))(*[v for t in taps for v in t])
+            part = torch.empty((B, P, P, cin), device=gy.device, dtype=torch.bfloat16)
+            _lib.check(lib.sg2_conv_taps_tc(part.data_ptr(), planes[s].data_ptr(), wp.data_ptr(), ones.data_ptr(), B, P, cout,
+                                            cin, flat, len(taps), st), "conv_taps_tc")
+            part = part[:, :r, :r, :].float()
+            acc = part if acc is None else acc + part
+    return acc.permute(0, 3, 1, 2).to(gy.dtype)
 
 
 def tc_conv3x3(x, weight4, scale=None):
@@ -196,13 +260,11 @@ def tc_conv3x3(x, weight4, scale=None):
     cout, cin = weight4.shape[:2]
     B, _, r, _ = x.shape
     xh = x.detach().permute(0, 2, 3, 1).to(torch.bfloat16).contiguous()                 # NHWC bf16
-    w = weight4.detach().float().contiguous()
-    wp = torch.empty((9, cout, cin), device=x.device, dtype=torch.bfloat16)
+    wp = _tc_pack(weight4)
     ones = torch.ones((B, cout), device=x.device, dtype=torch.float32) if scale is None else scale.detach().float().contiguous()
     out = torch.empty((B, r, r, cout), device=x.device, dtype=torch.bfloat16)
     with _lib.device_of(x):
         st = _lib.stream_of(x)
-        _lib.check(lib.sg2_conv3x3_tc_pack(wp.data_ptr(), w.data_ptr(), cin, cout, 1.0, st), "conv3x3_tc_pack")
         _lib.check(lib.sg2_conv3x3_tc(out.data_ptr(), xh.data_ptr(), wp.data_ptr(), ones.data_ptr(), B, r, cin, cout, st),
                    "conv3x3_tc")
     return out.permute(0, 3, 1, 2).to(x.dtype)
@@ -221,7 +283,7 @@ class SharedConvFunction(torch.autograd.Function):
         ctx.mode = mode
         ctx.tc = tc_conv_ok(x, weight4, mode)
         if ctx.tc:
-            return tc_conv3x3(x, weight4)
+            return tc_conv3x3(x, weight4) if mode == 0 else tc_conv_transpose3x3(x, weight4)
         wt, _ = conv_prep(weight4, 1.0, want_wsq=False)
         return shared_conv(x, wt, None, None, cout, k, mode)
 
@@ -241,6 +303,8 @@ class SharedConvFunction(torch.autograd.Function):
             elif mode == 1:    # adjoint of conv_transpose(stride 2) is conv(stride 2) with the same taps
                 wadj = weight4.detach().transpose(0, 1)
                 amode = 2
+                if ctx.tc:
+                    return tc_conv_transpose3x3_dgrad(gy, weight4), (SharedConvFunction._wgrad(ctx, x, weight4, gy) if ctx.needs_input_grad[1] else None), None
             else:              # adjoint of conv(stride 2) is conv_transpose(stride 2)
                 wadj = weight4.detach().transpose(0, 1)
                 amode = 1

@@ -8,6 +8,8 @@ Here: one modulation kernel (style + demod table), one shared-weight conv over t
 epilogue kernel (SmoothUpsample fused with noise, bias, lrelu, gain, clamp; or the plain epilogue when the
 layer does not up-sample).  When a gradient is needed the layers compose the differentiable pieces instead
 (utils.py).  Only the 'stylegan2' synthesis layer is implemented (the reference's default and the one psp.py builds)."""
+import os
+
 import numpy as np
 import torch
 
@@ -43,6 +45,14 @@ class Generator(torch.nn.Module):                            # generator.py:6-52
             return out_synth[0], z
         return out_synth[0], None
 
+    @property
+    def precision(self):
+        return self.synthesis.precision
+
+    @precision.setter
+    def precision(self, value):
+        self.synthesis.precision = value
+
     def mean_latent(self, n_latent):
         latent_in = torch.randn(n_latent, self.w_dim, device=self.synthesis.first_block.const.device)
         return self.mapping(latent_in, truncation_psi=1, truncation_cutoff=None).mean(0, keepdim=True)
@@ -62,6 +72,9 @@ class SynthesisNetwork(torch.nn.Module):                     # generator.py:55-8
         self.block_resolutions = [2 ** i for i in range(2, self.img_resolution_log2 + 1)]
         self.num_ws = 2 * (len(self.block_resolutions) + 1)
         channels_dict = {res: min(channel_base // res, channel_max) for res in self.block_resolutions}
+        # 'auto' / 'exact': fp32-accumulate SIMT convolutions; 'bf16' (or SG2_B200_PRECISION=bf16): the 3x3 convolutions
+        # -- all stride 1 in this decoder -- run on the tcgen05 kernel with bf16 operands, with and without autograd
+        self.precision = os.environ.get('SG2_B200_PRECISION', 'auto')
         self.blocks = torch.nn.ModuleList()
         self.first_block = SynthesisPrologue(channels_dict[self.block_resolutions[0]], w_dim=w_dim,
                                              resolution=self.block_resolutions[0], img_channels=img_channels,
@@ -72,9 +85,10 @@ class SynthesisNetwork(torch.nn.Module):                     # generator.py:55-8
 
     def forward(self, ws, noise_mode='random', return_latents=False, **kwargs):
         split_ws = [ws[:, 0:2, :]] + [ws[:, 2 * n + 1: 2 * n + 4, :] for n in range(len(self.block_resolutions))]
-        x, img = self.first_block(split_ws[0], noise_mode)
-        for i in range(len(self.block_resolutions) - 1):
-            x, img = self.blocks[i](x, img, split_ws[i + 1], noise_mode)
+        with K.tc_grad(True if self.precision == 'bf16' else (False if self.precision == 'exact' else None)):
+            x, img = self.first_block(split_ws[0], noise_mode)
+            for i in range(len(self.block_resolutions) - 1):
+                x, img = self.blocks[i](x, img, split_ws[i + 1], noise_mode)
         if return_latents:
             return img, None
         return [img]
@@ -196,7 +210,10 @@ class SynthesisLayer2(torch.nn.Module):                      # generator.py:172-
         wt, wsq = K.conv_prep(self.weight.to(x.dtype), 1.0, want_wsq=True)
         s, d = K.modulation(w.to(x.dtype), self.affine.weight, self.affine.bias, wsq, cout, self.affine.weight_gain,
                             self.affine.bias_gain, True)
-        y = K.shared_conv(x, wt, s, d, cout, 3, 0)
+        if K.tc_conv_ok(x, self.weight, 0):       # tensor-core conv: modulation on the way in, demodulation in its epilogue
+            y = K.tc_conv3x3(x * s.to(x.dtype).view(x.shape[0], -1, 1, 1), self.weight, scale=d)
+        else:
+            y = K.shared_conv(x, wt, s, d, cout, 3, 0)
         if isinstance(self.resampler, SmoothUpsample):
             return smooth_upsample2x(y, self.resampler.kernel, noise, self.noise_strength, self.bias, None, act=3,
                                      gain=g, clamp=c)

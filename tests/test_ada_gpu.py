@@ -232,3 +232,40 @@ def test_ada_layer_gradients_vs_oracle(sg2, cin, cout, res, up):
         for k, a, r in pairs:
             e = (a.cpu().double() - r).abs().max().item()
             assert e <= 1e-4 * r.abs().max().item() + 1e-7, (name, k, e, r.abs().max().item())
+
+
+def test_ada_generator_bf16_precision(sg2):
+    """precision='bf16': every 3x3 convolution on the tensor-core kernel (bf16 operands, fp32 accumulation), with and
+    without autograd, vs the fp64 oracle"""
+    from oracle import sg2_ada_oracle as A
+    from oracle.sg2_oracle import named_randn
+    gen, U = _ada()
+    res, b, nl = 32, 2, 2
+    sd = A.init_state_dict(res, 512, 512, nl, seed=0)
+    G = gen.Generator(512, 512, nl, res, 3)
+    G.load_state_dict(sd, strict=True)
+    G = G.to(DEV).eval()
+    for p in G.parameters():
+        p.requires_grad_(False)
+    ws0 = named_randn("ada:grad:w", (b, A.num_ws(res), 512), 5)
+    gimg = named_randn("ada:grad:gy", (b, 3, res, res), 6)
+    ws64 = ws0.double().requires_grad_(True)
+    ref = A.synthesis_network({k: v.double() for k, v in sd.items()}, res, ws64, "const")
+    ref.backward(gimg.double())
+    G.precision = 'bf16'
+    assert G.synthesis.precision == 'bf16'
+    n0 = sg2._lib.launch_count()
+    with torch.no_grad():
+        img, _ = G([ws0.to(DEV)], input_is_latent=True, randomize_noise=False)
+    assert sg2._lib.launch_count() > n0
+    assert (img.cpu().double() - ref.detach()).abs().max() <= 3e-2 * ref.abs().max()
+    ws = ws0.to(DEV).requires_grad_(True)
+    img2, _ = G([ws], input_is_latent=True, randomize_noise=False)
+    assert (img2.detach() - img).abs().max() <= 3e-2 * ref.abs().max()
+    img2.backward(gimg.to(DEV))
+    err = ws.grad.cpu().double() - ws64.grad
+    assert err.norm() <= 8e-2 * ws64.grad.norm(), (err.norm() / ws64.grad.norm()).item()
+    G.precision = 'exact'
+    with torch.no_grad():
+        img3, _ = G([ws0.to(DEV)], input_is_latent=True, randomize_noise=False)
+    assert (img3.cpu().double() - ref.detach()).abs().max() <= 2e-4 * ref.abs().max()

@@ -46,33 +46,56 @@ def test_conv3x3_tc_rejects_what_it_cannot_run(sg2):
     w = torch.randn(32, 32, 3, 3)
     assert not K.tc_conv_ok(xb, w, 0)                                  # fp32 tensors, bf16 operands not allowed
     with K.tc_grad(True):
-        assert K.tc_conv_ok(xb, w, 0) and not K.tc_conv_ok(xb, w, 1) and not K.tc_conv_ok(xb, w[:, :, :1, :1], 0)
+        assert K.tc_conv_ok(xb, w, 0) and K.tc_conv_ok(xb, w, 1) and not K.tc_conv_ok(xb, w, 2) and not K.tc_conv_ok(xb, w[:, :, :1, :1], 0)
     assert K.tc_conv_ok(xb.bfloat16(), w, 0)
     with K.tc_grad(False):
         assert not K.tc_conv_ok(xb, w, 0)
 
 
-@pytest.mark.parametrize("B,cin,cout,r", [(2, 64, 32, 16), (3, 512, 512, 4), (1, 32, 64, 32)])
-def test_shared_conv_function_tensor_core_gradients(sg2, B, cin, cout, r):
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("B,cin,cout,r", [(2, 64, 32, 16), (3, 512, 512, 4), (1, 32, 64, 32), (2, 128, 64, 7)])
+def test_shared_conv_function_tensor_core_gradients(sg2, B, cin, cout, r, mode):
+    """mode 0: F.conv2d(x, w, padding=1) (model.py:269-273); mode 1: F.conv_transpose2d(x, w^T, stride=2) (model.py:246-252)"""
     K = _K()
     g = torch.Generator().manual_seed(cin + r)
     x = _bf(torch.randn(B, cin, r, r, generator=g))
     w = _bf(torch.randn(cout, cin, 3, 3, generator=g) / (3 * cin ** 0.5))
-    gy = _bf(torch.randn(B, cout, r, r, generator=g))
+    ro = r if mode == 0 else 2 * r + 1
+    gy = _bf(torch.randn(B, cout, ro, ro, generator=g))
     x64, w64 = x.double().requires_grad_(True), w.double().requires_grad_(True)
-    ref = F.conv2d(x64, w64, padding=1)
+    ref = F.conv2d(x64, w64, padding=1) if mode == 0 else F.conv_transpose2d(x64, w64.transpose(0, 1), stride=2)
     ref.backward(gy.double())
     xd, wd = x.to(DEV).requires_grad_(True), w.to(DEV).requires_grad_(True)
     with K.tc_grad(True):
-        y = K.SharedConvFunction.apply(xd, wd, 0)
+        y = K.SharedConvFunction.apply(xd, wd, mode)
     y.backward(gy.to(DEV))
     for name, a, b in (("y", y.detach(), ref.detach()), ("gx", xd.grad, x64.grad), ("gw", wd.grad, w64.grad)):
         err = (a.cpu().double() - b).abs().max().item()
-        assert err <= 6e-3 * b.abs().max().item(), (name, err, b.abs().max().item())
+        assert a.shape == b.shape and err <= 6e-3 * b.abs().max().item(), (name, err, b.abs().max().item())
     # and the fp32 route is untouched when bf16 operands are not allowed
     xe = x.to(DEV).requires_grad_(True)
-    ye = K.SharedConvFunction.apply(xe, w.to(DEV), 0)
+    ye = K.SharedConvFunction.apply(xe, w.to(DEV), mode)
     assert (ye.detach().cpu().double() - ref.detach()).abs().max() <= 1e-5 * ref.abs().max()
+
+
+def test_conv_taps_tc_rejects_bad_taps(sg2):
+    import ctypes as C
+    lib = sg2._lib.load()
+    x = torch.zeros(1, 8, 8, 32, device=DEV, dtype=torch.bfloat16)
+    wp = torch.zeros(9, 32, 32, device=DEV, dtype=torch.bfloat16)
+    sc = torch.ones(1, 32, device=DEV)
+    out = torch.empty(1, 8, 8, 32, device=DEV, dtype=torch.bfloat16)
+    st = torch.cuda.current_stream().cuda_stream
+    for taps in ((2, 0, 0), (0, 0, 9), (0, -2, 1)):
+        arr = (C.c_int * 3)(*taps)
+        assert lib.sg2_conv_taps_tc(out.data_ptr(), x.data_ptr(), wp.data_ptr(), sc.data_ptr(), 1, 8, 32, 32, arr, 1, st) != 0
+    assert lib.sg2_conv_taps_tc(out.data_ptr(), x.data_ptr(), wp.data_ptr(), sc.data_ptr(), 1, 8, 32, 32, None, 1, st) != 0
+    arr = (C.c_int * 3)(0, 0, 4)                                       # the centre tap alone: a 1x1 convolution
+    xr = torch.randn(1, 8, 8, 32, device=DEV).bfloat16()
+    wr = torch.randn(9, 32, 32, device=DEV).bfloat16()
+    assert lib.sg2_conv_taps_tc(out.data_ptr(), xr.data_ptr(), wr.data_ptr(), sc.data_ptr(), 1, 8, 32, 32, arr, 1, st) == 0
+    ref = xr.float() @ wr[4].float().t()
+    assert (out.float() - ref).abs().max() <= 6e-3 * ref.abs().max()
 
 
 def test_generator_bf16_gradients_vs_oracle(sg2, oracle):

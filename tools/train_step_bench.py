@@ -20,13 +20,19 @@ def main():
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--ada", action="store_true", help="the stylegan2_ada decoder instead of the rosinality one")
     a = ap.parse_args()
     dev = "cuda:0"
     torch.manual_seed(0)
-    G = sg2.Generator(a.size, 512, 8).to(dev).eval()
+    if a.ada:
+        G = sg2.stylegan2_ada.Generator(512, 512, 8, a.size, 3).to(dev).eval()
+        n_latent = G.num_ws
+    else:
+        G = sg2.Generator(a.size, 512, 8).to(dev).eval()
+        n_latent = G.n_latent
     for p in G.parameters():
         p.requires_grad_(False)
-    lat = torch.randn(a.batch, G.n_latent, 512, device=dev)
+    lat = torch.randn(a.batch, n_latent, 512, device=dev)
     gy = torch.randn(a.batch, 3, a.size, a.size, device=dev)
     for mode in ("exact", "bf16"):
         G.precision = mode
@@ -43,10 +49,19 @@ def main():
             torch.cuda.synchronize()
             if it >= 3:
                 times.append((e0.elapsed_time(e1), e1.elapsed_time(e2)))
+        with torch.no_grad():                                   # the no-autograd call of the same module, for scale
+            for it in range(3):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                G([lat], input_is_latent=True, randomize_noise=False)
+                e1.record()
+                torch.cuda.synchronize()
+            infer = e0.elapsed_time(e1)
         f = sorted(t[0] for t in times)[len(times) // 2]
         b = sorted(t[1] for t in times)[len(times) // 2]
         print(json.dumps({"mode": mode, "size": a.size, "batch": a.batch, "fwd_ms": round(f, 2), "bwd_ms": round(b, 2),
-                          "img_per_s": round(a.batch / (f + b) * 1e3, 1), "grad_norm": float(ld.grad.norm())}), flush=True)
+                          "img_per_s": round(a.batch / (f + b) * 1e3, 1), "no_grad_fwd_ms": round(infer, 2), "decoder": "ada" if a.ada else "rosinality",
+                          "grad_norm": float(ld.grad.norm())}), flush=True)
 
 
 if __name__ == "__main__":
