@@ -244,6 +244,17 @@ int sg2_conv_taps_tc(void *out, const void *x, const void *wp, const float *scal
 int sg2_conv_transpose3x3_tc(void *planes, const void *x, const void *wp, const float *scale, int64_t B, int r, int cin,
                     int cout, sg2_stream_t stream);
 
+/* The two passes either side of a tensor-core convolution in the differentiable path, with the per-(sample, channel)
+ * factor of the factored ModulatedConv2d (model.py:236-240: style on the way in, demodulation on the way out) folded in,
+ * and the reduction its adjoint needs in the same pass.  `dtype` is that of the NCHW tensors; NHWC tensors are bf16.
+ *   sg2_nchw_to_nhwc_bf16: out[b,p,c] = bf16(x[b,c,p] * scale[b,c]);  if other: red[b,c] += sum_p x[b,c,p] * other[b,p,c]
+ *   sg2_nhwc_bf16_to_nchw: out[b,c,p] = scale[b,c] * h[b,p,c];        if other: red[b,c] += sum_p other[b,c,p] * h[b,p,c]
+ * scale may be NULL (1); other/red both NULL or both set (red fp32 [B,C], accumulated with atomics: zero it first). */
+int sg2_nchw_to_nhwc_bf16(void *out, const void *x, const float *scale, const void *other, float *red, int64_t B,
+                          int C, int64_t HW, int dtype, sg2_stream_t stream);
+int sg2_nhwc_bf16_to_nchw(void *out, const void *h, const float *scale, const void *other, float *red, int64_t B,
+                          int C, int64_t HW, int dtype, sg2_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,154 @@
+// layout_ops.cu -- the two passes either side of a tensor-core convolution in the differentiable path
+// (stylegan2/functional.py): NCHW (fp32 / fp16 / bf16) <-> NHWC bf16 with the per-(sample, channel) factor of the
+// modulated convolution folded in, and -- for the backward direction -- the per-(sample, channel) reduction that the
+// adjoint of that factor needs, in the same pass:
+//     modulate  : xh[b,p,c] = bf16(x[b,c,p] * s[b,c])                     (ModulatedConv2d, model.py:236-237, factored)
+//     its adjoint: gx[b,c,p] = s[b,c] * gh[b,p,c],  gs[b,c] = sum_p x[b,c,p] * gh[b,p,c]
+//     demodulate: y[b,c,p]  = d[b,c] * yh[b,p,c]                          (model.py:239-240, factored)
+//     its adjoint: gh[b,p,c] = bf16(d[b,c] * gy[b,c,p]), gd[b,c] = sum_p gy[b,c,p] * yh[b,p,c]
+// Both kernels move a 64-channel x 32-pixel tile through shared memory so that each side is read / written in 128-byte
+// rows; HBM-bound, (4 + 2) bytes per element (+ 2 or 4 for the reduction operand).
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace sg2 {
+
+constexpr int LT_C = 64, LT_P = 32;
+
+// NCHW -> NHWC bf16 (x scale); optional red[b,c] += sum_p x[b,c,p] * other[b,p,c]
+template <typename T>
+__global__ void __launch_bounds__(256)
+nchw_to_nhwc_kernel(__nv_bfloat16 *__restrict__ out, const T *__restrict__ x, const float *__restrict__ scale,
+                    const __nv_bfloat16 *__restrict__ other, float *__restrict__ red, int C, long long HW) {
+    __shared__ float tile[LT_C][LT_P + 1];
+    __shared__ float part[8][LT_C];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long p0 = (long long)blockIdx.x * LT_P;
+    const int c0 = blockIdx.y * LT_C;
+    const long long b = blockIdx.z;
+#pragma unroll
+    for (int j = 0; j < LT_C / 8; ++j) {
+        const int c = c0 + warp + 8 * j;
+        const long long p = p0 + lane;
+        tile[warp + 8 * j][lane] = (c < C && p < HW) ? Cvt<T>::to_f(x[(b * C + c) * HW + p]) : 0.f;
+    }
+    __syncthreads();
+    const int c = c0 + 2 * lane;                       // this lane's channel pair
+    const bool cok = c < C;                            // C is even
+    const float s0 = (cok && scale) ? __ldg(scale + b * C + c) : 1.f, s1 = (cok && scale) ? __ldg(scale + b * C + c + 1) : 1.f;
+    float r0 = 0.f, r1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < LT_P / 8; ++j) {
+        const int pl = warp + 8 * j;
+        const long long p = p0 + pl;
+        if (cok && p < HW) {
+            const float v0 = tile[2 * lane][pl], v1 = tile[2 * lane + 1][pl];
+            const long long o = (b * HW + p) * C + c;
+            *reinterpret_cast<__nv_bfloat162 *>(out + o) = __floats2bfloat162_rn(v0 * s0, v1 * s1);
+            if (other) {
+                const float2 q = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(other + o));
+                r0 = fmaf(v0, q.x, r0);
+                r1 = fmaf(v1, q.y, r1);
+            }
+        }
+    }
+    if (other) {                                       // block-uniform
+        part[warp][2 * lane] = r0;
+        part[warp][2 * lane + 1] = r1;
+        __syncthreads();
+        if (threadIdx.x < LT_C && c0 + threadIdx.x < C) {
+            float acc = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) acc += part[w][threadIdx.x];
+            atomicAdd(red + b * C + c0 + threadIdx.x, acc);
+        }
+    }
+}
+
+// NHWC bf16 -> NCHW (x scale); optional red[b,c] += sum_p other[b,c,p] * h[b,p,c]
+template <typename T>
+__global__ void __launch_bounds__(256)
+nhwc_to_nchw_kernel(T *__restrict__ out, const __nv_bfloat16 *__restrict__ h, const float *__restrict__ scale,
+                    const T *__restrict__ other, float *__restrict__ red, int C, long long HW) {
+    __shared__ float tile[LT_C][LT_P + 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long p0 = (long long)blockIdx.x * LT_P;
+    const int c0 = blockIdx.y * LT_C;
+    const long long b = blockIdx.z;
+    {
+        const int c = c0 + 2 * lane;
+#pragma unroll
+        for (int j = 0; j < LT_P / 8; ++j) {
+            const int pl = warp + 8 * j;
+            const long long p = p0 + pl;
+            float2 q = make_float2(0.f, 0.f);
+            if (c < C && p < HW) q = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(h + (b * HW + p) * C + c));
+            tile[2 * lane][pl] = q.x;
+            tile[2 * lane + 1][pl] = q.y;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < LT_C / 8; ++j) {
+        const int c = c0 + warp + 8 * j;               // warp-uniform
+        if (c >= C) continue;
+        const long long p = p0 + lane;
+        const float v = tile[warp + 8 * j][lane];
+        const float s = scale ? __ldg(scale + b * C + c) : 1.f;
+        float r = 0.f;
+        if (p < HW) {
+            const long long o = (b * C + c) * HW + p;
+            out[o] = Cvt<T>::from_f(v * s);
+            if (other) r = Cvt<T>::to_f(other[o]) * v;
+        }
+        if (other) {
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) r += __shfl_xor_sync(0xffffffffu, r, d);
+            if (lane == 0) atomicAdd(red + b * C + c, r);
+        }
+    }
+}
+
+}  // namespace sg2
+
+using namespace sg2;
+
+static int check_layout_args(const char *what, const void *a, const void *b, const void *other, const float *red, int64_t B,
+                             int C, int64_t HW) {
+    SG2_REQUIRE(B >= 0 && B <= 65535 && C >= 2 && C % 2 == 0 && C <= 65535 * LT_C && HW >= 1, SG2_ERR_BAD_ARG,
+                "%s: bad shape (B %lld, C %d, HW %lld; C must be even)", what, (long long)B, C, (long long)HW);
+    if (B == 0) return SG2_OK;
+    SG2_REQUIRE(a && b, SG2_ERR_BAD_ARG, "%s: null pointer", what);
+    SG2_REQUIRE((other == nullptr) == (red == nullptr), SG2_ERR_BAD_ARG, "%s: the reduction needs both its operand and its output", what);
+    return SG2_OK;
+}
+
+extern "C" int sg2_nchw_to_nhwc_bf16(void *out, const void *x, const float *scale, const void *other, float *red, int64_t B,
+                                     int C, int64_t HW, int dtype, sg2_stream_t stream) {
+    int rc = check_layout_args("nchw_to_nhwc_bf16", out, x, other, red, B, C, HW);
+    if (rc || B == 0) return rc;
+    SG2_REQUIRE((reinterpret_cast<uintptr_t>(out) & 3) == 0 && (reinterpret_cast<uintptr_t>(other) & 3) == 0, SG2_ERR_BAD_ARG,
+                "nchw_to_nhwc_bf16: NHWC tensors must be 4-byte aligned");
+    dim3 grid((unsigned)((HW + LT_P - 1) / LT_P), (unsigned)((C + LT_C - 1) / LT_C), (unsigned)B);
+    SG2_DISPATCH_DTYPE(dtype, {
+        nchw_to_nhwc_kernel<T><<<grid, 256, 0, as_stream(stream)>>>((__nv_bfloat16 *)out, (const T *)x, scale,
+                                                                     (const __nv_bfloat16 *)other, red, C, (long long)HW);
+        SG2_LAUNCH_CHECK();
+    });
+    return SG2_OK;
+}
+
+extern "C" int sg2_nhwc_bf16_to_nchw(void *out, const void *h, const float *scale, const void *other, float *red, int64_t B,
+                                     int C, int64_t HW, int dtype, sg2_stream_t stream) {
+    int rc = check_layout_args("nhwc_bf16_to_nchw", out, h, other, red, B, C, HW);
+    if (rc || B == 0) return rc;
+    SG2_REQUIRE((reinterpret_cast<uintptr_t>(h) & 3) == 0, SG2_ERR_BAD_ARG, "nhwc_bf16_to_nchw: NHWC tensors must be 4-byte aligned");
+    dim3 grid((unsigned)((HW + LT_P - 1) / LT_P), (unsigned)((C + LT_C - 1) / LT_C), (unsigned)B);
+    SG2_DISPATCH_DTYPE(dtype, {
+        nhwc_to_nchw_kernel<T><<<grid, 256, 0, as_stream(stream)>>>((T *)out, (const __nv_bfloat16 *)h, scale, (const T *)other,
+                                                                     red, C, (long long)HW);
+        SG2_LAUNCH_CHECK();
+    });
+    return SG2_OK;
+}

@@ -200,74 +200,173 @@ def _tc_pack(weight4):
     return wp
 
 
-def tc_conv_transpose3x3(x, weight4):
-    """y = conv_transpose2d(x, weight4^T, stride=2) (the up-sampling ModulatedConv2d before its blur) on the tensor-core
-    kernel: x [B,Cin,r,r], weight4 [Cout,Cin,3,3] -> [B,Cout,2r+1,2r+1] in x.dtype.  The kernel writes the four
-    polyphase planes; interleaving them into the NCHW result is four strided copies."""
+def to_nhwc(x, scale=None, other=None):
+    """xh[b,y,x,c] = bf16(x[b,c,y,x] * scale[b,c]) in one pass (csrc/layout_ops.cu); with `other` (NHWC bf16, same
+    shape as the result) also returns red[b,c] = sum_p x[b,c,p] * other[b,p,c], else None."""
     _lib.require_cuda(x)
-    cout, cin = weight4.shape[:2]
-    B, _, r, _ = x.shape
-    P = r + 1
-    xh = x.detach().permute(0, 2, 3, 1).to(torch.bfloat16).contiguous()
-    wp = _tc_pack(weight4)
-    ones = torch.ones((B, cout), device=x.device, dtype=torch.float32)
-    planes = torch.empty((4, B, P, P, cout), device=x.device, dtype=torch.bfloat16)
+    x = x.detach().contiguous()
+    B, Cn, H, W = x.shape
+    out = torch.empty((B, H, W, Cn), device=x.device, dtype=torch.bfloat16)
+    red = torch.zeros((B, Cn), device=x.device, dtype=torch.float32) if other is not None else None
+    sc = None if scale is None else scale.detach().float().contiguous()
     with _lib.device_of(x):
-        _lib.check(_lib.load().sg2_conv_transpose3x3_tc(planes.data_ptr(), xh.data_ptr(), wp.data_ptr(), ones.data_ptr(), B, r, cin,
-                                               cout, _lib.stream_of(x)), "conv_transpose3x3_tc")
-    out = torch.empty((B, cout, 2 * r + 1, 2 * r + 1), device=x.device, dtype=x.dtype)
-    for s in range(4):
-        py, px = s >> 1, s & 1
-        out[:, :, py::2, px::2] = planes[s, :, :P - py, :P - px, :].permute(0, 3, 1, 2)
+        _lib.check(_lib.load().sg2_nchw_to_nhwc_bf16(out.data_ptr(), x.data_ptr(), _lib.ptr(sc), _lib.ptr(other), _lib.ptr(red),
+                                                     B, Cn, H * W, _lib.dtype_code(x), _lib.stream_of(x)), "nchw_to_nhwc_bf16")
+    return out, red
+
+
+def to_nchw(h, scale, dtype, other=None):
+    """y[b,c,y,x] = scale[b,c] * h[b,y,x,c] (h NHWC bf16) in `dtype`; with `other` (NCHW, `dtype`) also returns
+    red[b,c] = sum_p other[b,c,p] * h[b,p,c], else None."""
+    B, H, W, Cn = h.shape
+    out = torch.empty((B, Cn, H, W), device=h.device, dtype=dtype)
+    red = torch.zeros((B, Cn), device=h.device, dtype=torch.float32) if other is not None else None
+    sc = None if scale is None else scale.detach().float().contiguous()
+    if other is not None:
+        other = other.detach().to(dtype).contiguous()
+    with _lib.device_of(h):
+        _lib.check(_lib.load().sg2_nhwc_bf16_to_nchw(out.data_ptr(), h.data_ptr(), _lib.ptr(sc), _lib.ptr(other), _lib.ptr(red),
+                                                     B, Cn, H * W, _lib.dtype_code(out), _lib.stream_of(h)), "nhwc_bf16_to_nchw")
+    return out, red
+
+
+def _ones(B, n, device):
+    return torch.ones((B, n), device=device, dtype=torch.float32)
+
+
+def tc_conv3x3_nhwc(xh, wp, scale=None):
+    """NHWC bf16 [B,r,r,Cin] -> [B,r,r,Cout]: scale[b,co] * conv3x3 'same' with packed weights wp [9,Cout,Cin]"""
+    B, r, _, cin = xh.shape
+    cout = wp.shape[1]
+    sc = _ones(B, cout, xh.device) if scale is None else scale.detach().float().contiguous()
+    out = torch.empty((B, r, r, cout), device=xh.device, dtype=torch.bfloat16)
+    with _lib.device_of(xh):
+        _lib.check(_lib.load().sg2_conv3x3_tc(out.data_ptr(), xh.data_ptr(), wp.data_ptr(), sc.data_ptr(), B, r, cin, cout,
+                                              _lib.stream_of(xh)), "conv3x3_tc")
     return out
 
 
-def tc_conv_transpose3x3_dgrad(gy, weight4):
-    """input gradient of tc_conv_transpose3x3: gx[i,j,ci] = sum_{a,b,co} gy[2i+a, 2j+b, co] * w[co,ci,a,b], a stride-2
-    convolution evaluated as the sum of four stride-1 convolutions (4, 2, 2, 1 taps) over the polyphase planes of gy."""
-    _lib.require_cuda(gy)
-    lib = _lib.load()
-    cout, cin = weight4.shape[:2]
-    B, _, R, _ = gy.shape
-    r = (R - 1) // 2
+def tc_conv_transpose3x3_nhwc(xh, wp):
+    """NHWC bf16 [B,r,r,Cin] -> [B,2r+1,2r+1,Cout]: conv_transpose2d(stride 2).  The kernel writes the four polyphase
+    planes; interleaving them is four strided bf16 copies."""
+    B, r, _, cin = xh.shape
+    cout = wp.shape[1]
     P = r + 1
-    planes = torch.zeros((4, B, P, P, cout), device=gy.device, dtype=torch.bfloat16)
-    g = gy.detach()
+    planes = torch.empty((4, B, P, P, cout), device=xh.device, dtype=torch.bfloat16)
+    with _lib.device_of(xh):
+        _lib.check(_lib.load().sg2_conv_transpose3x3_tc(planes.data_ptr(), xh.data_ptr(), wp.data_ptr(),
+                                                        _ones(B, cout, xh.device).data_ptr(), B, r, cin, cout,
+                                                        _lib.stream_of(xh)), "conv_transpose3x3_tc")
+    out = torch.empty((B, 2 * r + 1, 2 * r + 1, cout), device=xh.device, dtype=torch.bfloat16)
     for s in range(4):
         py, px = s >> 1, s & 1
-        planes[s, :, :P - py, :P - px, :] = g[:, :, py::2, px::2].permute(0, 2, 3, 1)
-    wp = _tc_pack(weight4.detach().transpose(0, 1))                     # contraction over Cout, output channel Cin
-    ones = torch.ones((B, cin), device=gy.device, dtype=torch.float32)
+        out[:, py::2, px::2, :] = planes[s, :, :P - py, :P - px, :]
+    return out
+
+
+def tc_conv_transpose3x3_dgrad_nhwc(gh, wp_t):
+    """input gradient of tc_conv_transpose3x3_nhwc: gx[i,j,ci] = sum_{a,b,co} gy[2i+a, 2j+b, co] * w[co,ci,a,b], a
+    stride-2 convolution evaluated as the sum of four stride-1 convolutions (4, 2, 2, 1 taps) over the polyphase planes
+    of gy.  gh NHWC bf16 [B,2r+1,2r+1,Cout]; wp_t = pack(w^T) [9,Cin,Cout] -> NHWC bf16 [B,r,r,Cin]."""
+    lib = _lib.load()
+    B, R, _, cout = gh.shape
+    cin = wp_t.shape[1]
+    r = (R - 1) // 2
+    P = r + 1
+    planes = torch.zeros((4, B, P, P, cout), device=gh.device, dtype=torch.bfloat16)
+    for s in range(4):
+        py, px = s >> 1, s & 1
+        planes[s, :, :P - py, :P - px, :] = gh[:, py::2, px::2, :]
+    ones = _ones(B, cin, gh.device)
     acc = None
-    with _lib.device_of(gy):
-        st = _lib.stream_of(gy)
+    with _lib.device_of(gh):
+        st = _lib.stream_of(gh)
         for s in range(4):
             py, px = s >> 1, s & 1
             taps = [(da, db, (2 * da + py) * 3 + 2 * db + px) for da in range(2 - py) for db in range(2 - px)]
             flat = (C.c_int * (3 * len(taps)))(*[v for t in taps for v in t])
-            part = torch.empty((B, P, P, cin), device=gy.device, dtype=torch.bfloat16)
-            _lib.check(lib.sg2_conv_taps_tc(part.data_ptr(), planes[s].data_ptr(), wp.data_ptr(), ones.data_ptr(), B, P, cout,
+            part = torch.empty((B, P, P, cin), device=gh.device, dtype=torch.bfloat16)
+            _lib.check(lib.sg2_conv_taps_tc(part.data_ptr(), planes[s].data_ptr(), wp_t.data_ptr(), ones.data_ptr(), B, P, cout,
                                             cin, flat, len(taps), st), "conv_taps_tc")
             part = part[:, :r, :r, :].float()
             acc = part if acc is None else acc + part
-    return acc.permute(0, 3, 1, 2).to(gy.dtype)
+    return acc.to(torch.bfloat16).contiguous()
 
 
 def tc_conv3x3(x, weight4, scale=None):
     """y = scale[b,co] * conv2d(x, weight4, padding=1) on the tensor-core kernel: x [B,Cin,r,r] any float dtype -> same dtype."""
-    _lib.require_cuda(x)
-    lib = _lib.load()
-    cout, cin = weight4.shape[:2]
-    B, _, r, _ = x.shape
-    xh = x.detach().permute(0, 2, 3, 1).to(torch.bfloat16).contiguous()                 # NHWC bf16
-    wp = _tc_pack(weight4)
-    ones = torch.ones((B, cout), device=x.device, dtype=torch.float32) if scale is None else scale.detach().float().contiguous()
-    out = torch.empty((B, r, r, cout), device=x.device, dtype=torch.bfloat16)
-    with _lib.device_of(x):
-        st = _lib.stream_of(x)
-        _lib.check(lib.sg2_conv3x3_tc(out.data_ptr(), xh.data_ptr(), wp.data_ptr(), ones.data_ptr(), B, r, cin, cout, st),
-                   "conv3x3_tc")
-    return out.permute(0, 3, 1, 2).to(x.dtype)
+    xh, _ = to_nhwc(x)
+    return to_nchw(tc_conv3x3_nhwc(xh, _tc_pack(weight4), scale), None, x.dtype)[0]
+
+
+def tc_conv_transpose3x3(x, weight4):
+    """y = conv_transpose2d(x, weight4^T, stride=2) (the up-sampling ModulatedConv2d before its blur) on the tensor-core
+    kernel: x [B,Cin,r,r], weight4 [Cout,Cin,3,3] -> [B,Cout,2r+1,2r+1] in x.dtype."""
+    xh, _ = to_nhwc(x)
+    return to_nchw(tc_conv_transpose3x3_nhwc(xh, _tc_pack(weight4)), None, x.dtype)[0]
+
+
+def tc_conv_transpose3x3_dgrad(gy, weight4):
+    gh, _ = to_nhwc(gy)
+    return to_nchw(tc_conv_transpose3x3_dgrad_nhwc(gh, _tc_pack(weight4.detach().transpose(0, 1))), None, gy.dtype)[0]
+
+
+def _wgrad(mode, x, weight4, gy):
+    """weight gradient of the shared-weight convolution (library wgrad, true fp32)"""
+    import torch.nn.grad as G
+    cout, cin, k, _ = weight4.shape
+    xf, gf = x.detach().float(), gy.detach().float()
+    with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+        if mode == 0:
+            gw = G.conv2d_weight(xf, weight4.shape, gf, padding=k // 2)
+        elif mode == 2:
+            gw = G.conv2d_weight(xf, weight4.shape, gf, stride=2)
+        else:   # y = conv_transpose(x, W^T): dW[co,ci] = corr(gy[co], x[ci]) at stride 2
+            gw = G.conv2d_weight(gf, (cin, cout, k, k), xf, stride=2).transpose(0, 1)
+    return gw.to(weight4.dtype)
+
+
+class ModulatedConvTCFunction(torch.autograd.Function):
+    """y = d[b,co] * conv(W, s[b,ci] * x) -- the factored ModulatedConv2d (model.py:232-273) -- on the tensor-core kernel,
+    mode 0 (3x3 'same') or 1 (stride-2 transposed).  Three passes forward (modulate + to NHWC bf16, conv, demodulate + to
+    NCHW) and three backward; the adjoint passes also produce grad_s and grad_d, so nothing else touches the activations.
+    x [B,Cin,r,r]; s [B,Cin], d [B,Cout] fp32 (d may be None); weight4 [Cout,Cin,3,3]."""
+
+    @staticmethod
+    def forward(ctx, x, s, d, weight4, mode):
+        xh, _ = to_nhwc(x, s)
+        wp = _tc_pack(weight4)
+        yh = tc_conv3x3_nhwc(xh, wp) if mode == 0 else tc_conv_transpose3x3_nhwc(xh, wp)
+        y, _ = to_nchw(yh, d, x.dtype)
+        ctx.save_for_backward(x, s, d, weight4, yh)
+        ctx.mode = mode
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gy):
+        x, s, d, weight4, yh = ctx.saved_tensors
+        mode = ctx.mode
+        gy = gy.contiguous()
+        need_d = d is not None and ctx.needs_input_grad[2]
+        gh, gd = to_nhwc(gy, d, other=yh if need_d else None)             # gh = bf16(d * gy), gd = sum_p gy * conv
+        gx = gs = gw = None
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            if mode == 0:
+                gxh = tc_conv3x3_nhwc(gh, _tc_pack(weight4.detach().flip([2, 3]).transpose(0, 1)))
+            else:
+                gxh = tc_conv_transpose3x3_dgrad_nhwc(gh, _tc_pack(weight4.detach().transpose(0, 1)))
+            gx, gs = to_nchw(gxh, s, x.dtype, other=x if ctx.needs_input_grad[1] else None)   # gx = s * g, gs = sum_p x * g
+            if gs is not None:
+                gs = gs.to(s.dtype)
+        if ctx.needs_input_grad[3]:
+            B = x.shape[0]
+            xm = x.detach().float() * s.detach().float().view(B, -1, 1, 1)
+            gc = gy.float() if d is None else gy.float() * d.detach().float().view(B, -1, 1, 1)
+            gw = _wgrad(mode, xm, weight4, gc)
+        if gd is not None:
+            gd = gd.to(d.dtype)
+        return gx, gs, gd, gw, None
 
 
 class SharedConvFunction(torch.autograd.Function):
@@ -299,12 +398,12 @@ class SharedConvFunction(torch.autograd.Function):
                 wadj = weight4.detach().flip([2, 3]).transpose(0, 1)
                 amode = 0
                 if ctx.tc:
-                    return tc_conv3x3(gy, wadj), (SharedConvFunction._wgrad(ctx, x, weight4, gy) if ctx.needs_input_grad[1] else None), None
+                    return tc_conv3x3(gy, wadj), (_wgrad(mode, x, weight4, gy) if ctx.needs_input_grad[1] else None), None
             elif mode == 1:    # adjoint of conv_transpose(stride 2) is conv(stride 2) with the same taps
                 wadj = weight4.detach().transpose(0, 1)
                 amode = 2
                 if ctx.tc:
-                    return tc_conv_transpose3x3_dgrad(gy, weight4), (SharedConvFunction._wgrad(ctx, x, weight4, gy) if ctx.needs_input_grad[1] else None), None
+                    return tc_conv_transpose3x3_dgrad(gy, weight4), (_wgrad(mode, x, weight4, gy) if ctx.needs_input_grad[1] else None), None
             else:              # adjoint of conv(stride 2) is conv_transpose(stride 2)
                 wadj = weight4.detach().transpose(0, 1)
                 amode = 1
@@ -315,20 +414,5 @@ class SharedConvFunction(torch.autograd.Function):
                 full[:, :, :gx.shape[2], :gx.shape[3]] = gx
                 gx = full
         if ctx.needs_input_grad[1]:
-            gw = SharedConvFunction._wgrad(ctx, x, weight4, gy)
+            gw = _wgrad(mode, x, weight4, gy)
         return gx, gw, None
-
-    @staticmethod
-    def _wgrad(ctx, x, weight4, gy):
-        import torch.nn.grad as G
-        mode = ctx.mode
-        cout, cin, k, _ = weight4.shape
-        xf, gf = x.detach().float(), gy.detach().float()
-        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):   # true-fp32 wgrad
-            if mode == 0:
-                gw = G.conv2d_weight(xf, weight4.shape, gf, padding=k // 2)
-            elif mode == 2:
-                gw = G.conv2d_weight(xf, weight4.shape, gf, stride=2)
-            else:   # y = conv_transpose(x, W^T): dW[co,ci] = corr(gy[co], x[ci]) at stride 2
-                gw = G.conv2d_weight(gf, (cin, cout, k, k), xf, stride=2).transpose(0, 1)
-        return gw.to(weight4.dtype)

@@ -213,6 +213,14 @@ class ModulatedConv2d(nn.Module):
         batch = input.shape[0]
         s = self.modulation(style)                                        # [B, Cin]
         w4 = self.weight[0] * self.scale                                   # [Cout, Cin, k, k]
+        if K.tc_conv_ok(input, w4, self._mode):
+            # tensor-core route: modulate + layout / conv / demodulate + layout, each one pass, grad_s and grad_d
+            # produced by the adjoint passes (functional.ModulatedConvTCFunction)
+            d = None
+            if self.demodulate:
+                d = torch.rsqrt(s.float().pow(2) @ w4.float().pow(2).sum([2, 3]).t() + self.eps)
+            y = K.ModulatedConvTCFunction.apply(input, s.float(), d, w4, self._mode)
+            return self.blur(y) if self.upsample else y
         x = input * s.to(input.dtype).view(batch, -1, 1, 1)
         if self.downsample:
             x = self.blur(x)

@@ -175,6 +175,11 @@ def modulated_conv2d(x, weight, styles, padding=0, demodulate=True):
         raise RuntimeError(f"sg2_b200 modulated_conv2d: kernel {k} / padding {padding} not supported (1x1 pad 0, 3x3 pad 1)")
     if K.needs_grad(x, weight, styles):
         b = x.shape[0]
+        if K.tc_conv_ok(x, weight, 0):                                          # tensor-core route, see functional.py
+            d = None
+            if demodulate:
+                d = torch.rsqrt(styles.float().square() @ weight.float().square().sum([2, 3]).t() + 1e-8)
+            return K.ModulatedConvTCFunction.apply(x, styles.float(), d, weight, 0)
         y = K.SharedConvFunction.apply(x * styles.to(x.dtype).view(b, -1, 1, 1), weight.to(x.dtype), 0)
         if demodulate:
             wsq = weight.float().square().sum([2, 3])                          # [Cout, Cin]

@@ -125,3 +125,60 @@ def test_generator_bf16_gradients_vs_oracle(sg2, oracle):
     ld2 = lat.to(DEV).requires_grad_(True)
     img2, _ = G([ld2], input_is_latent=True, randomize_noise=False)
     assert (img2.detach().cpu().double() - imgo.detach()).abs().max() <= 1e-3 * max(1.0, imgo.abs().max().item())
+
+
+@pytest.mark.parametrize("B,Cn,H,W", [(2, 32, 5, 5), (1, 96, 33, 33), (3, 160, 8, 8), (1, 64, 64, 64), (2, 34, 7, 9)])
+def test_layout_passes_vs_torch(sg2, B, Cn, H, W):
+    """NCHW <-> NHWC bf16 with the per-(sample, channel) factor and the adjoint's reduction in the same pass"""
+    K = _K()
+    g = torch.Generator().manual_seed(Cn + H)
+    x = torch.randn(B, Cn, H, W, generator=g)
+    sc = torch.rand(B, Cn, generator=g) + 0.5
+    oth = torch.randn(B, H, W, Cn, generator=g).bfloat16()
+    for dt in (torch.float32, torch.bfloat16):
+        xd = x.to(dt)
+        ref = (xd.double() * sc.double().view(B, Cn, 1, 1)).permute(0, 2, 3, 1)
+        h, red = K.to_nhwc(xd.to(DEV), sc.to(DEV), other=oth.to(DEV))
+        assert h.dtype == torch.bfloat16 and h.shape == (B, H, W, Cn)
+        assert (h.cpu().double() - ref).abs().max() <= 2 ** -8 * ref.abs().max()
+        rref = (xd.double().permute(0, 2, 3, 1) * oth.double()).sum((1, 2))
+        assert (red.cpu().double() - rref).abs().max() <= 1e-5 * rref.abs().max() + 1e-5
+        h2, none = K.to_nhwc(xd.to(DEV))
+        assert none is None and torch.equal(h2.cpu(), xd.permute(0, 2, 3, 1).bfloat16())
+        # and back
+        hb = torch.randn(B, H, W, Cn, generator=g).bfloat16()
+        y, red = K.to_nchw(hb.to(DEV), sc.to(DEV), dt, other=xd.to(DEV))
+        yref = hb.double().permute(0, 3, 1, 2) * sc.double().view(B, Cn, 1, 1)
+        assert y.dtype == dt and (y.cpu().double() - yref).abs().max() <= (2 ** -8 if dt == torch.bfloat16 else 1e-6) * yref.abs().max()
+        rref = (xd.double() * hb.double().permute(0, 3, 1, 2)).sum((2, 3))
+        assert (red.cpu().double() - rref).abs().max() <= 1e-5 * rref.abs().max() + 1e-5
+        y2, none = K.to_nchw(hb.to(DEV), None, dt)
+        assert none is None and torch.equal(y2.cpu(), hb.permute(0, 3, 1, 2).to(dt))
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("B,cin,cout,r,demod", [(2, 64, 32, 16, True), (3, 512, 512, 4, True), (2, 32, 64, 9, False)])
+def test_modulated_conv_tc_function_gradients(sg2, B, cin, cout, r, demod, mode):
+    """y = d * conv(W, s * x) in three passes each way: every gradient (x, s, d, W) vs fp64 autograd"""
+    K = _K()
+    g = torch.Generator().manual_seed(cin + r + mode)
+    x = torch.randn(B, cin, r, r, generator=g)
+    s = torch.rand(B, cin, generator=g) + 0.5
+    d = torch.rand(B, cout, generator=g) + 0.5 if demod else None
+    w = torch.randn(cout, cin, 3, 3, generator=g) / (3 * cin ** 0.5)
+    ro = r if mode == 0 else 2 * r + 1
+    gy = torch.randn(B, cout, ro, ro, generator=g)
+    leaves = [t.double().requires_grad_(True) for t in (x, s, w)] + ([d.double().requires_grad_(True)] if demod else [])
+    x64, s64, w64 = leaves[:3]
+    xm = x64 * s64.view(B, cin, 1, 1)
+    ref = F.conv2d(xm, w64, padding=1) if mode == 0 else F.conv_transpose2d(xm, w64.transpose(0, 1), stride=2)
+    if demod:
+        ref = ref * leaves[3].view(B, cout, 1, 1)
+    ref.backward(gy.double())
+    dev = [t.to(DEV).requires_grad_(True) for t in (x, s, w)] + ([d.to(DEV).requires_grad_(True)] if demod else [])
+    y = K.ModulatedConvTCFunction.apply(dev[0], dev[1], dev[3] if demod else None, dev[2], mode)
+    assert y.shape == ref.shape and (y.detach().cpu().double() - ref.detach()).abs().max() <= 1e-2 * ref.abs().max()
+    y.backward(gy.to(DEV))
+    for name, a, b in zip(("gx", "gs", "gw", "gd"), dev, leaves):
+        err = (a.grad.cpu().double() - b.grad).abs().max().item()
+        assert a.grad.shape == b.grad.shape and err <= 1.2e-2 * b.grad.abs().max().item(), (name, err, b.grad.abs().max().item())
