@@ -254,6 +254,18 @@ int sg2_nchw_to_nhwc_bf16(void *out, const void *x, const float *scale, const vo
                           int C, int64_t HW, int dtype, sg2_stream_t stream);
 int sg2_nhwc_bf16_to_nchw(void *out, const void *h, const float *scale, const void *other, float *red, int64_t B,
                           int C, int64_t HW, int dtype, sg2_stream_t stream);
+/* The second pass with the StyledConv tail (NoiseInjection + FusedLeakyReLU, model.py:282-287,331-337) applied:
+ *   out[b,c,p] = lrelu(scale[b,c] * h[b,p,c] + noise_weight[0] * noise[b or 0, p] + bias[c], alpha) * gain
+ * (noise, noise_weight, bias: tensors of `dtype`; noise / bias may be NULL; noise_bstride = HW or 0), and its adjoint:
+ *   g = gy * (y > 0 ? 1 : alpha) * gain   (fused_bias_act_kernel.cu:28-47 with grad = 1, y = the output above)
+ *   out[b,p,c] = bf16(g * scale[b,c]);  red[b,c] += sum_p g * other[b,p,c];  red_sum[b,c] += sum_p g
+ * (other/red both NULL or both set; red_sum may be NULL; both fp32 [B,C], accumulated with atomics: zero them first). */
+int sg2_nhwc_bf16_to_nchw_act(void *out, const void *h, const float *scale, const void *noise, int64_t noise_bstride,
+                              const void *noise_weight, const void *bias, float alpha, float gain, int64_t B, int C,
+                              int64_t HW, int dtype, sg2_stream_t stream);
+int sg2_nchw_to_nhwc_bf16_actgrad(void *out, const void *gy, const void *y, float alpha, float gain, const float *scale,
+                                  const void *other, float *red, float *red_sum, int64_t B, int C, int64_t HW,
+                                  int dtype, sg2_stream_t stream);
 
 #ifdef __cplusplus
 }

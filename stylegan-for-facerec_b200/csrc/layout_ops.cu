@@ -6,6 +6,10 @@
 //     its adjoint: gx[b,c,p] = s[b,c] * gh[b,p,c],  gs[b,c] = sum_p x[b,c,p] * gh[b,p,c]
 //     demodulate: y[b,c,p]  = d[b,c] * yh[b,p,c]                          (model.py:239-240, factored)
 //     its adjoint: gh[b,p,c] = bf16(d[b,c] * gy[b,c,p]), gd[b,c] = sum_p gy[b,c,p] * yh[b,p,c]
+// For the layers without a blur between convolution and activation the second pass also applies the StyledConv tail
+// (NoiseInjection + FusedLeakyReLU, model.py:282-287,331-337): y = lrelu(d * yh + w * noise + bias) * sqrt(2), and the
+// first one its adjoint: g = gy * (y > 0 ? 1 : alpha) * sqrt(2) (fused_bias_act_kernel.cu:28-47, grad = 1) before
+// everything else, with grad_bias reduced in the same pass.
 // Both kernels move a 64-channel x 32-pixel tile through shared memory so that each side is read / written in 128-byte
 // rows; HBM-bound, (4 + 2) bytes per element (+ 2 or 4 for the reduction operand).
 #include <algorithm>
@@ -20,7 +24,8 @@ constexpr int LT_C = 64, LT_P = 32;
 template <typename T>
 __global__ void __launch_bounds__(256)
 nchw_to_nhwc_kernel(__nv_bfloat16 *__restrict__ out, const T *__restrict__ x, const float *__restrict__ scale,
-                    const __nv_bfloat16 *__restrict__ other, float *__restrict__ red, int C, long long HW) {
+                    const __nv_bfloat16 *__restrict__ other, float *__restrict__ red, int C, long long HW,
+                    const T *__restrict__ act_ref, float alpha, float gain, float *__restrict__ red_sum) {
     __shared__ float tile[LT_C][LT_P + 1];
     __shared__ float part[8][LT_C];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -31,13 +36,18 @@ nchw_to_nhwc_kernel(__nv_bfloat16 *__restrict__ out, const T *__restrict__ x, co
     for (int j = 0; j < LT_C / 8; ++j) {
         const int c = c0 + warp + 8 * j;
         const long long p = p0 + lane;
-        tile[warp + 8 * j][lane] = (c < C && p < HW) ? Cvt<T>::to_f(x[(b * C + c) * HW + p]) : 0.f;
+        float v = 0.f;
+        if (c < C && p < HW) {
+            v = Cvt<T>::to_f(x[(b * C + c) * HW + p]);
+            if (act_ref) v *= (Cvt<T>::to_f(act_ref[(b * C + c) * HW + p]) > 0.f ? 1.f : alpha) * gain;   // lrelu'(y) * gain
+        }
+        tile[warp + 8 * j][lane] = v;
     }
     __syncthreads();
     const int c = c0 + 2 * lane;                       // this lane's channel pair
     const bool cok = c < C;                            // C is even
     const float s0 = (cok && scale) ? __ldg(scale + b * C + c) : 1.f, s1 = (cok && scale) ? __ldg(scale + b * C + c + 1) : 1.f;
-    float r0 = 0.f, r1 = 0.f;
+    float r0 = 0.f, r1 = 0.f, t0 = 0.f, t1 = 0.f;
 #pragma unroll
     for (int j = 0; j < LT_P / 8; ++j) {
         const int pl = warp + 8 * j;
@@ -46,6 +56,8 @@ nchw_to_nhwc_kernel(__nv_bfloat16 *__restrict__ out, const T *__restrict__ x, co
             const float v0 = tile[2 * lane][pl], v1 = tile[2 * lane + 1][pl];
             const long long o = (b * HW + p) * C + c;
             *reinterpret_cast<__nv_bfloat162 *>(out + o) = __floats2bfloat162_rn(v0 * s0, v1 * s1);
+            t0 += v0;
+            t1 += v1;
             if (other) {
                 const float2 q = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(other + o));
                 r0 = fmaf(v0, q.x, r0);
@@ -64,13 +76,27 @@ nchw_to_nhwc_kernel(__nv_bfloat16 *__restrict__ out, const T *__restrict__ x, co
             atomicAdd(red + b * C + c0 + threadIdx.x, acc);
         }
     }
+    if (red_sum) {                                     // block-uniform: sum_p of the (activation-gradient) tile
+        __syncthreads();
+        part[warp][2 * lane] = t0;
+        part[warp][2 * lane + 1] = t1;
+        __syncthreads();
+        if (threadIdx.x < LT_C && c0 + threadIdx.x < C) {
+            float acc = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) acc += part[w][threadIdx.x];
+            atomicAdd(red_sum + b * C + c0 + threadIdx.x, acc);
+        }
+    }
 }
 
 // NHWC bf16 -> NCHW (x scale); optional red[b,c] += sum_p other[b,c,p] * h[b,p,c]
 template <typename T>
 __global__ void __launch_bounds__(256)
 nhwc_to_nchw_kernel(T *__restrict__ out, const __nv_bfloat16 *__restrict__ h, const float *__restrict__ scale,
-                    const T *__restrict__ other, float *__restrict__ red, int C, long long HW) {
+                    const T *__restrict__ other, float *__restrict__ red, int C, long long HW, int act,
+                    const T *__restrict__ noise, long long noise_bstride, const T *__restrict__ noise_weight,
+                    const T *__restrict__ bias, float alpha, float gain) {
     __shared__ float tile[LT_C][LT_P + 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long p0 = (long long)blockIdx.x * LT_P;
@@ -89,6 +115,8 @@ nhwc_to_nchw_kernel(T *__restrict__ out, const __nv_bfloat16 *__restrict__ h, co
         }
     }
     __syncthreads();
+    float nz = 0.f;                                    // this lane's pixel: noise_weight * noise[b or 0, p]
+    if (act && noise && p0 + lane < HW) nz = Cvt<T>::to_f(noise_weight[0]) * Cvt<T>::to_f(noise[b * noise_bstride + p0 + lane]);
 #pragma unroll
     for (int j = 0; j < LT_C / 8; ++j) {
         const int c = c0 + warp + 8 * j;               // warp-uniform
@@ -99,7 +127,12 @@ nhwc_to_nchw_kernel(T *__restrict__ out, const __nv_bfloat16 *__restrict__ h, co
         float r = 0.f;
         if (p < HW) {
             const long long o = (b * C + c) * HW + p;
-            out[o] = Cvt<T>::from_f(v * s);
+            float y = v * s;
+            if (act) {
+                y += nz + (bias ? Cvt<T>::to_f(bias[c]) : 0.f);
+                y = (y > 0.f ? y : y * alpha) * gain;
+            }
+            out[o] = Cvt<T>::from_f(y);
             if (other) r = Cvt<T>::to_f(other[o]) * v;
         }
         if (other) {
@@ -133,7 +166,8 @@ extern "C" int sg2_nchw_to_nhwc_bf16(void *out, const void *x, const float *scal
     dim3 grid((unsigned)((HW + LT_P - 1) / LT_P), (unsigned)((C + LT_C - 1) / LT_C), (unsigned)B);
     SG2_DISPATCH_DTYPE(dtype, {
         nchw_to_nhwc_kernel<T><<<grid, 256, 0, as_stream(stream)>>>((__nv_bfloat16 *)out, (const T *)x, scale,
-                                                                     (const __nv_bfloat16 *)other, red, C, (long long)HW);
+                                                                     (const __nv_bfloat16 *)other, red, C, (long long)HW,
+                                                                     nullptr, 0.f, 1.f, nullptr);
         SG2_LAUNCH_CHECK();
     });
     return SG2_OK;
@@ -147,7 +181,49 @@ extern "C" int sg2_nhwc_bf16_to_nchw(void *out, const void *h, const float *scal
     dim3 grid((unsigned)((HW + LT_P - 1) / LT_P), (unsigned)((C + LT_C - 1) / LT_C), (unsigned)B);
     SG2_DISPATCH_DTYPE(dtype, {
         nhwc_to_nchw_kernel<T><<<grid, 256, 0, as_stream(stream)>>>((T *)out, (const __nv_bfloat16 *)h, scale, (const T *)other,
-                                                                     red, C, (long long)HW);
+                                                                     red, C, (long long)HW, 0, nullptr, 0, nullptr, nullptr, 0.f, 1.f);
+        SG2_LAUNCH_CHECK();
+    });
+    return SG2_OK;
+}
+
+// out[b,c,p] = lrelu(scale[b,c] * h[b,p,c] + noise_weight[0] * noise[b or 0, p] + bias[c], alpha) * gain: the demodulation,
+// NoiseInjection and FusedLeakyReLU (model.py:239-240,282-287,335) in the NHWC -> NCHW pass.  noise / noise_weight / bias
+// are tensors of `dtype` (noise and bias may be NULL); noise_bstride = HW for per-sample noise, 0 for one shared map.
+extern "C" int sg2_nhwc_bf16_to_nchw_act(void *out, const void *h, const float *scale, const void *noise, int64_t noise_bstride,
+                                         const void *noise_weight, const void *bias, float alpha, float gain, int64_t B, int C,
+                                         int64_t HW, int dtype, sg2_stream_t stream) {
+    int rc = check_layout_args("nhwc_bf16_to_nchw_act", out, h, nullptr, nullptr, B, C, HW);
+    if (rc || B == 0) return rc;
+    SG2_REQUIRE((reinterpret_cast<uintptr_t>(h) & 3) == 0, SG2_ERR_BAD_ARG, "nhwc_bf16_to_nchw_act: NHWC tensors must be 4-byte aligned");
+    SG2_REQUIRE(!noise || noise_weight, SG2_ERR_BAD_ARG, "nhwc_bf16_to_nchw_act: noise without its weight");
+    SG2_REQUIRE(noise_bstride == 0 || noise_bstride == HW, SG2_ERR_BAD_ARG, "nhwc_bf16_to_nchw_act: noise stride must be 0 or HW");
+    dim3 grid((unsigned)((HW + LT_P - 1) / LT_P), (unsigned)((C + LT_C - 1) / LT_C), (unsigned)B);
+    SG2_DISPATCH_DTYPE(dtype, {
+        nhwc_to_nchw_kernel<T><<<grid, 256, 0, as_stream(stream)>>>((T *)out, (const __nv_bfloat16 *)h, scale, nullptr, nullptr, C,
+                                                                     (long long)HW, 1, (const T *)noise, (long long)noise_bstride,
+                                                                     (const T *)noise_weight, (const T *)bias, alpha, gain);
+        SG2_LAUNCH_CHECK();
+    });
+    return SG2_OK;
+}
+
+// The adjoint of the pass above: g = gy * (y > 0 ? 1 : alpha) * gain (y = its output), then as sg2_nchw_to_nhwc_bf16 on g:
+// out[b,p,c] = bf16(g * scale[b,c]), red[b,c] += sum_p g * other[b,p,c] (grad of the demodulation factor; other/red may be
+// NULL), and red_sum[b,c] += sum_p g (summed over b by the caller: grad of the bias; may be NULL).
+extern "C" int sg2_nchw_to_nhwc_bf16_actgrad(void *out, const void *gy, const void *y, float alpha, float gain, const float *scale,
+                                             const void *other, float *red, float *red_sum, int64_t B, int C, int64_t HW,
+                                             int dtype, sg2_stream_t stream) {
+    int rc = check_layout_args("nchw_to_nhwc_bf16_actgrad", out, gy, other, red, B, C, HW);
+    if (rc || B == 0) return rc;
+    SG2_REQUIRE(y, SG2_ERR_BAD_ARG, "nchw_to_nhwc_bf16_actgrad: null activation output");
+    SG2_REQUIRE((reinterpret_cast<uintptr_t>(out) & 3) == 0 && (reinterpret_cast<uintptr_t>(other) & 3) == 0, SG2_ERR_BAD_ARG,
+                "nchw_to_nhwc_bf16_actgrad: NHWC tensors must be 4-byte aligned");
+    dim3 grid((unsigned)((HW + LT_P - 1) / LT_P), (unsigned)((C + LT_C - 1) / LT_C), (unsigned)B);
+    SG2_DISPATCH_DTYPE(dtype, {
+        nchw_to_nhwc_kernel<T><<<grid, 256, 0, as_stream(stream)>>>((__nv_bfloat16 *)out, (const T *)gy, scale,
+                                                                     (const __nv_bfloat16 *)other, red, C, (long long)HW,
+                                                                     (const T *)y, alpha, gain, red_sum);
         SG2_LAUNCH_CHECK();
     });
     return SG2_OK;

@@ -369,6 +369,100 @@ class ModulatedConvTCFunction(torch.autograd.Function):
         return gx, gs, gd, gw, None
 
 
+def to_nchw_act(h, scale, dtype, noise, noise_weight, bias, alpha, gain):
+    """y = lrelu(scale[b,c] * h[b,p,c] + noise_weight * noise[b or 0, p] + bias[c], alpha) * gain, NHWC bf16 -> NCHW `dtype`
+    in one pass (demodulation + NoiseInjection + FusedLeakyReLU, model.py:239-240,282-287,335)"""
+    B, H, W, Cn = h.shape
+    out = torch.empty((B, Cn, H, W), device=h.device, dtype=dtype)
+    sc = None if scale is None else scale.detach().float().contiguous()
+    nstride = 0
+    if noise is not None:
+        noise = noise.detach().to(dtype).contiguous()
+        if noise.numel() == B * H * W:
+            nstride = H * W
+        elif noise.numel() != H * W:
+            raise RuntimeError(f"noise of shape {tuple(noise.shape)} does not broadcast to [{B}, 1, {H}, {W}]")
+        noise_weight = noise_weight.detach().to(dtype).contiguous()
+    if bias is not None:
+        bias = bias.detach().to(dtype).contiguous()
+    with _lib.device_of(h):
+        _lib.check(_lib.load().sg2_nhwc_bf16_to_nchw_act(out.data_ptr(), h.data_ptr(), _lib.ptr(sc), _lib.ptr(noise), nstride,
+                                                         _lib.ptr(noise_weight) if noise is not None else None, _lib.ptr(bias),
+                                                         float(alpha), float(gain), B, Cn, H * W, _lib.dtype_code(out),
+                                                         _lib.stream_of(h)), "nhwc_bf16_to_nchw_act")
+    return out
+
+
+def to_nhwc_actgrad(gy, y, alpha, gain, scale, other=None, want_sum=False):
+    """adjoint of to_nchw_act: g = gy * (y > 0 ? 1 : alpha) * gain; returns (bf16(g * scale) as NHWC,
+    red[b,c] = sum_p g * other[b,p,c] or None, sum[b,c] = sum_p g or None)"""
+    gy = gy.detach().contiguous()
+    y = y.detach().to(gy.dtype).contiguous()
+    B, Cn, H, W = gy.shape
+    out = torch.empty((B, H, W, Cn), device=gy.device, dtype=torch.bfloat16)
+    red = torch.zeros((B, Cn), device=gy.device, dtype=torch.float32) if other is not None else None
+    tot = torch.zeros((B, Cn), device=gy.device, dtype=torch.float32) if want_sum else None
+    sc = None if scale is None else scale.detach().float().contiguous()
+    with _lib.device_of(gy):
+        _lib.check(_lib.load().sg2_nchw_to_nhwc_bf16_actgrad(out.data_ptr(), gy.data_ptr(), y.data_ptr(), float(alpha), float(gain),
+                                                             _lib.ptr(sc), _lib.ptr(other), _lib.ptr(red), _lib.ptr(tot), B, Cn,
+                                                             H * W, _lib.dtype_code(gy), _lib.stream_of(gy)),
+                   "nchw_to_nhwc_bf16_actgrad")
+    return out, red, tot
+
+
+class StyledConvTCFunction(torch.autograd.Function):
+    """out = lrelu(d * conv3x3(W, s * x) + noise_weight * noise + bias, alpha) * gain -- a whole non-resampling StyledConv
+    (model.py:331-337) in three passes each way: modulate + to NHWC bf16, tensor-core conv, demodulate + noise + bias +
+    activation + to NCHW; backward: activation gradient + demodulation (+ grad_d, grad_bias) + to NHWC, conv with the
+    adjoint weights, style (+ grad_s) + to NCHW."""
+
+    @staticmethod
+    def forward(ctx, x, s, d, weight4, noise, noise_weight, bias, alpha, gain):
+        xh, _ = to_nhwc(x, s)
+        yh = tc_conv3x3_nhwc(xh, _tc_pack(weight4))
+        out = to_nchw_act(yh, d, x.dtype, noise, noise_weight, bias, alpha, gain)
+        ctx.save_for_backward(x, s, d, weight4, yh, out, noise, noise_weight)
+        ctx.act = (alpha, gain)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gout):
+        x, s, d, weight4, yh, out, noise, noise_weight = ctx.saved_tensors
+        alpha, gain = ctx.act
+        need = ctx.needs_input_grad
+        need_d = d is not None and need[2]
+        gh, gd, tot = to_nhwc_actgrad(gout, out, alpha, gain, d, other=yh if need_d else None, want_sum=need[6])
+        gx = gs = gw = gnoise = gnw = gbias = None
+        if need[0] or need[1]:
+            gxh = tc_conv3x3_nhwc(gh, _tc_pack(weight4.detach().flip([2, 3]).transpose(0, 1)))
+            gx, gs = to_nchw(gxh, s, x.dtype, other=x if need[1] else None)
+            if gs is not None:
+                gs = gs.to(s.dtype)
+        if gd is not None:
+            gd = gd.to(d.dtype)
+        if need[6]:
+            gbias = tot.sum(0).to(out.dtype)
+        if need[3] or (noise is not None and (need[4] or need[5])):
+            # rare (the decoder itself trains): the activation gradient as a tensor, from the op kernel
+            from .op.fused_act import bias_act
+            g = bias_act(gout.contiguous(), None, out, 3, 1, alpha, gain)
+            B = x.shape[0]
+            if noise is not None and (need[4] or need[5]):
+                t = g.float().sum(1, keepdim=True)                                           # [B,1,H,W]
+                if need[4]:
+                    gn = noise_weight.detach().float().view(1, 1, 1, 1) * t
+                    gnoise = (gn if noise.shape[0] == B else gn.sum(0, keepdim=True)).reshape(noise.shape).to(noise.dtype)
+                if need[5]:
+                    gnw = (t * noise.detach().float().reshape(-1, 1, *t.shape[2:])).sum().reshape(noise_weight.shape).to(noise_weight.dtype)
+            if need[3]:
+                xm = x.detach().float() * s.detach().float().view(B, -1, 1, 1)
+                gc = g.float() if d is None else g.float() * d.detach().float().view(B, -1, 1, 1)
+                gw = _wgrad(0, xm, weight4, gc)
+        return gx, gs, gd, gw, gnoise, gnw, gbias, None, None
+
+
 class SharedConvFunction(torch.autograd.Function):
     """y = conv(x, W) with one weight tensor shared by the batch (the contraction inside
     ModulatedConv2d once modulation/demodulation are factored out).  forward and grad_x run on the

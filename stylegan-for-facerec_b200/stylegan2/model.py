@@ -274,6 +274,17 @@ class StyledConv(nn.Module):
         self.activate = FusedLeakyReLU(out_channel)
 
     def forward(self, input, style, noise=None):
+        conv = self.conv
+        if (input.is_cuda and conv._mode == 0 and conv.kernel_size == 3 and K.tc_conv_ok(input, conv.weight[0], 0)
+                and K.needs_grad(input, style, noise, *self.parameters())):
+            # differentiable tensor-core route: the whole layer in three passes each way (functional.StyledConvTCFunction)
+            if noise is None:
+                noise = input.new_empty(input.shape[0], 1, input.shape[2], input.shape[3]).normal_()
+            s = conv.modulation(style)
+            w4 = conv.weight[0] * conv.scale
+            d = torch.rsqrt(s.float().pow(2) @ w4.float().pow(2).sum([2, 3]).t() + conv.eps) if conv.demodulate else None
+            return K.StyledConvTCFunction.apply(input, s.float(), d, w4, noise, self.noise.weight, self.activate.bias,
+                                                self.activate.negative_slope, self.activate.scale)
         out = self.conv(input, style)
         if not K.needs_grad(out, noise, self.noise.weight, self.activate.bias):
             # conv -> (+ w*noise) -> (+ bias) -> lrelu*sqrt(2) in one pass over the activation

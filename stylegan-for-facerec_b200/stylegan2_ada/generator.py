@@ -201,6 +201,13 @@ class SynthesisLayer2(torch.nn.Module):                      # generator.py:172-
             noise = self.noise_const
         g, c = self.activation_gain * gain, 256.0 * gain
         if K.needs_grad(x, w, self.weight, self.bias, self.noise_strength, self.affine.weight, self.affine.bias):
+            if not isinstance(self.resampler, SmoothUpsample) and K.tc_conv_ok(x, self.weight, 0):
+                # the whole layer in three passes each way on the tensor-core route (functional.StyledConvTCFunction)
+                s = self.affine(w).float()
+                d = torch.rsqrt(s.square() @ self.weight.float().square().sum([2, 3]).t() + 1e-8)
+                nz = None if noise is None else noise.reshape(-1, 1, self.resolution, self.resolution)
+                y = K.StyledConvTCFunction.apply(x, s, d, self.weight, nz, self.noise_strength, self.bias, 0.2, g)
+                return torch.clamp(y, -c, c)
             y = modulated_conv2d(x=x, weight=self.weight, styles=self.affine(w), padding=self.padding)
             if isinstance(self.resampler, SmoothUpsample):
                 y = SmoothUpsampleFunction.apply(y, self.resampler.kernel)

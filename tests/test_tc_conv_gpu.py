@@ -182,3 +182,39 @@ def test_modulated_conv_tc_function_gradients(sg2, B, cin, cout, r, demod, mode)
     for name, a, b in zip(("gx", "gs", "gw", "gd"), dev, leaves):
         err = (a.grad.cpu().double() - b.grad).abs().max().item()
         assert a.grad.shape == b.grad.shape and err <= 1.2e-2 * b.grad.abs().max().item(), (name, err, b.grad.abs().max().item())
+
+
+@pytest.mark.parametrize("B,cin,cout,r,shared_noise", [(2, 64, 32, 16, False), (3, 512, 512, 4, True), (2, 32, 96, 9, False)])
+def test_styled_conv_tc_function_gradients(sg2, B, cin, cout, r, shared_noise):
+    """a whole non-resampling StyledConv (model.py:331-337) in three passes each way: output and every gradient vs fp64
+    autograd; the upstream gradient is zeroed where the pre-activation is within bf16 rounding of the leaky-relu kink"""
+    K = _K()
+    g = torch.Generator().manual_seed(cin + r)
+    x = torch.randn(B, cin, r, r, generator=g)
+    s = torch.rand(B, cin, generator=g) + 0.5
+    d = torch.rand(B, cout, generator=g) + 0.5
+    w = torch.randn(cout, cin, 3, 3, generator=g) / (3 * cin ** 0.5)
+    nz = torch.randn(1 if shared_noise else B, 1, r, r, generator=g)
+    nw = torch.tensor([0.3])
+    bias = 0.2 * torch.randn(cout, generator=g)
+    leaves = [t.double().requires_grad_(True) for t in (x, s, d, w, nz, nw, bias)]
+    x64, s64, d64, w64, nz64, nw64, b64 = leaves
+    pre = F.conv2d(x64 * s64.view(B, cin, 1, 1), w64, padding=1) * d64.view(B, cout, 1, 1) + nw64 * nz64 + b64.view(1, cout, 1, 1)
+    ref = F.leaky_relu(pre, 0.2) * 2 ** 0.5
+    gy = torch.randn(B, cout, r, r, generator=g) * (pre.detach().abs() > 3e-2 * pre.detach().abs().max())
+    ref.backward(gy.double())
+    dev = [t.to(DEV).requires_grad_(True) for t in (x, s, d, w, nz, nw, bias)]
+    out = K.StyledConvTCFunction.apply(*dev, 0.2, 2 ** 0.5)
+    assert out.shape == ref.shape and (out.detach().cpu().double() - ref.detach()).abs().max() <= 1e-2 * ref.abs().max()
+    out.backward(gy.to(DEV))
+    for name, a, b in zip(("gx", "gs", "gd", "gw", "gnoise", "gnw", "gbias"), dev, leaves):
+        err = (a.grad.cpu().double() - b.grad).abs().max().item()
+        assert a.grad.shape == b.grad.shape and err <= 1.2e-2 * b.grad.abs().max().item() + 1e-6, (name, err, b.grad.abs().max().item())
+    # frozen parameters (the ReStyle direction): only x, s, d receive gradients
+    dev = [t.to(DEV) for t in (x, s, d, w, nz, nw, bias)]
+    for t in dev[:3]:
+        t.requires_grad_(True)
+    K.StyledConvTCFunction.apply(*dev, 0.2, 2 ** 0.5).backward(gy.to(DEV))
+    for a, b in zip(dev[:3], leaves[:3]):
+        assert (a.grad.cpu().double() - b.grad).abs().max() <= 1.2e-2 * b.grad.abs().max()
+    assert all(t.grad is None for t in dev[3:])
