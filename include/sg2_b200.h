@@ -254,6 +254,14 @@ int sg2_nchw_to_nhwc_bf16(void *out, const void *x, const float *scale, const vo
                           int C, int64_t HW, int dtype, sg2_stream_t stream);
 int sg2_nhwc_bf16_to_nchw(void *out, const void *h, const float *scale, const void *other, float *red, int64_t B,
                           int C, int64_t HW, int dtype, sg2_stream_t stream);
+/* The same two passes with the NHWC side stored as the four polyphase planes of a W x W image (W odd):
+ * planes[(y&1)*2 + (x&1)][b][y>>1][x>>1][c], each plane (W+1)/2 squared -- the layout sg2_conv_transpose3x3_tc writes and
+ * the polyphase form of its input gradient reads (no interleaving copies).  sg2_nchw_to_polyphase_bf16 writes only
+ * the valid cells of the planes: zero them first. */
+int sg2_nchw_to_polyphase_bf16(void *planes, const void *x, const float *scale, const void *other_planes, float *red,
+                               int64_t B, int C, int W, int dtype, sg2_stream_t stream);
+int sg2_polyphase_bf16_to_nchw(void *out, const void *planes, const float *scale, const void *other, float *red,
+                               int64_t B, int C, int W, int dtype, sg2_stream_t stream);
 /* The second pass with the StyledConv tail (NoiseInjection + FusedLeakyReLU, model.py:282-287,331-337) applied:
  *   out[b,c,p] = lrelu(scale[b,c] * h[b,p,c] + noise_weight[0] * noise[b or 0, p] + bias[c], alpha) * gain
  * (noise, noise_weight, bias: tensors of `dtype`; noise / bias may be NULL; noise_bstride = HW or 0), and its adjoint:

@@ -20,12 +20,23 @@ namespace sg2 {
 
 constexpr int LT_C = 64, LT_P = 32;
 
+// element offset of pixel p of sample b on the NHWC side.  poly_w == 0: plain [B][HW][C].  poly_w = W > 0: the image is
+// W x W and stored as the four polyphase planes of the transposed convolution, [(py,px)][B][P][P][C] with P = (W+1)/2,
+// pixel (y, x) living in plane (y&1, x&1) at (y>>1, x>>1) -- what sg2_conv_transpose3x3_tc writes and what the
+// polyphase form of its input gradient reads, so no interleaving copy is needed on either side.
+__device__ __forceinline__ long long nhwc_offset(long long b, long long p, int C, long long HW, int poly_w, long long B) {
+    if (poly_w == 0) return (b * HW + p) * C;
+    const int y = (int)(p / poly_w), x = (int)(p - (long long)y * poly_w);
+    const int P = (poly_w + 1) >> 1, s = (y & 1) * 2 + (x & 1);
+    return ((((long long)s * B + b) * P + (y >> 1)) * P + (x >> 1)) * C;
+}
+
 // NCHW -> NHWC bf16 (x scale); optional red[b,c] += sum_p x[b,c,p] * other[b,p,c]
 template <typename T>
 __global__ void __launch_bounds__(256)
 nchw_to_nhwc_kernel(__nv_bfloat16 *__restrict__ out, const T *__restrict__ x, const float *__restrict__ scale,
                     const __nv_bfloat16 *__restrict__ other, float *__restrict__ red, int C, long long HW,
-                    const T *__restrict__ act_ref, float alpha, float gain, float *__restrict__ red_sum) {
+                    const T *__restrict__ act_ref, float alpha, float gain, float *__restrict__ red_sum, int poly_w) {
     __shared__ float tile[LT_C][LT_P + 1];
     __shared__ float part[8][LT_C];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -54,7 +65,7 @@ nchw_to_nhwc_kernel(__nv_bfloat16 *__restrict__ out, const T *__restrict__ x, co
         const long long p = p0 + pl;
         if (cok && p < HW) {
             const float v0 = tile[2 * lane][pl], v1 = tile[2 * lane + 1][pl];
-            const long long o = (b * HW + p) * C + c;
+            const long long o = nhwc_offset(b, p, C, HW, poly_w, gridDim.z) + c;
             *reinterpret_cast<__nv_bfloat162 *>(out + o) = __floats2bfloat162_rn(v0 * s0, v1 * s1);
             t0 += v0;
             t1 += v1;
@@ -96,8 +107,9 @@ __global__ void __launch_bounds__(256)
 nhwc_to_nchw_kernel(T *__restrict__ out, const __nv_bfloat16 *__restrict__ h, const float *__restrict__ scale,
                     const T *__restrict__ other, float *__restrict__ red, int C, long long HW, int act,
                     const T *__restrict__ noise, long long noise_bstride, const T *__restrict__ noise_weight,
-                    const T *__restrict__ bias, float alpha, float gain) {
+                    const T *__restrict__ bias, float alpha, float gain, int poly_w) {
     __shared__ float tile[LT_C][LT_P + 1];
+    __shared__ float csum[LT_C];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long p0 = (long long)blockIdx.x * LT_P;
     const int c0 = blockIdx.y * LT_C;
@@ -109,7 +121,8 @@ nhwc_to_nchw_kernel(T *__restrict__ out, const __nv_bfloat16 *__restrict__ h, co
             const int pl = warp + 8 * j;
             const long long p = p0 + pl;
             float2 q = make_float2(0.f, 0.f);
-            if (c < C && p < HW) q = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(h + (b * HW + p) * C + c));
+            if (c < C && p < HW)
+                q = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(h + nhwc_offset(b, p, C, HW, poly_w, gridDim.z) + c));
             tile[2 * lane][pl] = q.x;
             tile[2 * lane + 1][pl] = q.y;
         }
@@ -138,8 +151,12 @@ nhwc_to_nchw_kernel(T *__restrict__ out, const __nv_bfloat16 *__restrict__ h, co
         if (other) {
 #pragma unroll
             for (int d = 16; d > 0; d >>= 1) r += __shfl_xor_sync(0xffffffffu, r, d);
-            if (lane == 0) atomicAdd(red + b * C + c, r);
+            if (lane == 0) csum[warp + 8 * j] = r;
         }
+    }
+    if (other) {                                       // block-uniform: one coalesced atomic per channel of the tile
+        __syncthreads();
+        if (threadIdx.x < LT_C && c0 + threadIdx.x < C) atomicAdd(red + b * C + c0 + threadIdx.x, csum[threadIdx.x]);
     }
 }
 
@@ -157,8 +174,8 @@ static int check_layout_args(const char *what, const void *a, const void *b, con
     return SG2_OK;
 }
 
-extern "C" int sg2_nchw_to_nhwc_bf16(void *out, const void *x, const float *scale, const void *other, float *red, int64_t B,
-                                     int C, int64_t HW, int dtype, sg2_stream_t stream) {
+static int run_nchw_to_nhwc(void *out, const void *x, const float *scale, const void *other, float *red, int64_t B, int C,
+                            int64_t HW, int dtype, sg2_stream_t stream, int poly_w) {
     int rc = check_layout_args("nchw_to_nhwc_bf16", out, x, other, red, B, C, HW);
     if (rc || B == 0) return rc;
     SG2_REQUIRE((reinterpret_cast<uintptr_t>(out) & 3) == 0 && (reinterpret_cast<uintptr_t>(other) & 3) == 0, SG2_ERR_BAD_ARG,
@@ -167,21 +184,21 @@ extern "C" int sg2_nchw_to_nhwc_bf16(void *out, const void *x, const float *scal
     SG2_DISPATCH_DTYPE(dtype, {
         nchw_to_nhwc_kernel<T><<<grid, 256, 0, as_stream(stream)>>>((__nv_bfloat16 *)out, (const T *)x, scale,
                                                                      (const __nv_bfloat16 *)other, red, C, (long long)HW,
-                                                                     nullptr, 0.f, 1.f, nullptr);
+                                                                     nullptr, 0.f, 1.f, nullptr, poly_w);
         SG2_LAUNCH_CHECK();
     });
     return SG2_OK;
 }
 
-extern "C" int sg2_nhwc_bf16_to_nchw(void *out, const void *h, const float *scale, const void *other, float *red, int64_t B,
-                                     int C, int64_t HW, int dtype, sg2_stream_t stream) {
+static int run_nhwc_to_nchw(void *out, const void *h, const float *scale, const void *other, float *red, int64_t B, int C,
+                            int64_t HW, int dtype, sg2_stream_t stream, int poly_w) {
     int rc = check_layout_args("nhwc_bf16_to_nchw", out, h, other, red, B, C, HW);
     if (rc || B == 0) return rc;
     SG2_REQUIRE((reinterpret_cast<uintptr_t>(h) & 3) == 0, SG2_ERR_BAD_ARG, "nhwc_bf16_to_nchw: NHWC tensors must be 4-byte aligned");
     dim3 grid((unsigned)((HW + LT_P - 1) / LT_P), (unsigned)((C + LT_C - 1) / LT_C), (unsigned)B);
     SG2_DISPATCH_DTYPE(dtype, {
         nhwc_to_nchw_kernel<T><<<grid, 256, 0, as_stream(stream)>>>((T *)out, (const __nv_bfloat16 *)h, scale, (const T *)other,
-                                                                     red, C, (long long)HW, 0, nullptr, 0, nullptr, nullptr, 0.f, 1.f);
+                                                                     red, C, (long long)HW, 0, nullptr, 0, nullptr, nullptr, 0.f, 1.f, poly_w);
         SG2_LAUNCH_CHECK();
     });
     return SG2_OK;
@@ -202,7 +219,7 @@ extern "C" int sg2_nhwc_bf16_to_nchw_act(void *out, const void *h, const float *
     SG2_DISPATCH_DTYPE(dtype, {
         nhwc_to_nchw_kernel<T><<<grid, 256, 0, as_stream(stream)>>>((T *)out, (const __nv_bfloat16 *)h, scale, nullptr, nullptr, C,
                                                                      (long long)HW, 1, (const T *)noise, (long long)noise_bstride,
-                                                                     (const T *)noise_weight, (const T *)bias, alpha, gain);
+                                                                     (const T *)noise_weight, (const T *)bias, alpha, gain, 0);
         SG2_LAUNCH_CHECK();
     });
     return SG2_OK;
@@ -223,8 +240,31 @@ extern "C" int sg2_nchw_to_nhwc_bf16_actgrad(void *out, const void *gy, const vo
     SG2_DISPATCH_DTYPE(dtype, {
         nchw_to_nhwc_kernel<T><<<grid, 256, 0, as_stream(stream)>>>((__nv_bfloat16 *)out, (const T *)gy, scale,
                                                                      (const __nv_bfloat16 *)other, red, C, (long long)HW,
-                                                                     (const T *)y, alpha, gain, red_sum);
+                                                                     (const T *)y, alpha, gain, red_sum, 0);
         SG2_LAUNCH_CHECK();
     });
     return SG2_OK;
+}
+
+extern "C" int sg2_nchw_to_nhwc_bf16(void *out, const void *x, const float *scale, const void *other, float *red, int64_t B,
+                                     int C, int64_t HW, int dtype, sg2_stream_t stream) {
+    return run_nchw_to_nhwc(out, x, scale, other, red, B, C, HW, dtype, stream, 0);
+}
+extern "C" int sg2_nhwc_bf16_to_nchw(void *out, const void *h, const float *scale, const void *other, float *red, int64_t B,
+                                     int C, int64_t HW, int dtype, sg2_stream_t stream) {
+    return run_nhwc_to_nchw(out, h, scale, other, red, B, C, HW, dtype, stream, 0);
+}
+
+// The same two passes with the NHWC side stored as the four polyphase planes of a W x W image (W odd):
+// planes[(y&1)*2 + (x&1)][b][y>>1][x>>1][c], each plane (W+1)/2 squared -- the layout sg2_conv_transpose3x3_tc writes and
+// the polyphase input gradient reads.  sg2_nchw_to_polyphase_bf16 writes only the valid cells: zero the planes first.
+extern "C" int sg2_nchw_to_polyphase_bf16(void *planes, const void *x, const float *scale, const void *other_planes, float *red,
+                                          int64_t B, int C, int W, int dtype, sg2_stream_t stream) {
+    SG2_REQUIRE(W >= 1 && W % 2 == 1 && W <= 32767, SG2_ERR_BAD_ARG, "nchw_to_polyphase_bf16: W must be odd, got %d", W);
+    return run_nchw_to_nhwc(planes, x, scale, other_planes, red, B, C, (int64_t)W * W, dtype, stream, W);
+}
+extern "C" int sg2_polyphase_bf16_to_nchw(void *out, const void *planes, const float *scale, const void *other, float *red,
+                                          int64_t B, int C, int W, int dtype, sg2_stream_t stream) {
+    SG2_REQUIRE(W >= 1 && W % 2 == 1 && W <= 32767, SG2_ERR_BAD_ARG, "polyphase_bf16_to_nchw: W must be odd, got %d", W);
+    return run_nhwc_to_nchw(out, planes, scale, other, red, B, C, (int64_t)W * W, dtype, stream, W);
 }

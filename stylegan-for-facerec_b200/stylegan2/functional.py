@@ -246,46 +246,70 @@ def tc_conv3x3_nhwc(xh, wp, scale=None):
     return out
 
 
-def tc_conv_transpose3x3_nhwc(xh, wp):
-    """NHWC bf16 [B,r,r,Cin] -> [B,2r+1,2r+1,Cout]: conv_transpose2d(stride 2).  The kernel writes the four polyphase
-    planes; interleaving them is four strided bf16 copies."""
+def tc_conv_transpose3x3_planes(xh, wp):
+    """NHWC bf16 [B,r,r,Cin] -> conv_transpose2d(stride 2) as its four polyphase planes [4,B,r+1,r+1,Cout] bf16
+    (pixel (y, x) of the (2r+1)^2 result lives in plane (y&1)*2 + (x&1) at (y>>1, x>>1); the last row / column of the odd
+    planes is not written)."""
     B, r, _, cin = xh.shape
     cout = wp.shape[1]
-    P = r + 1
-    planes = torch.empty((4, B, P, P, cout), device=xh.device, dtype=torch.bfloat16)
+    planes = torch.empty((4, B, r + 1, r + 1, cout), device=xh.device, dtype=torch.bfloat16)
     with _lib.device_of(xh):
         _lib.check(_lib.load().sg2_conv_transpose3x3_tc(planes.data_ptr(), xh.data_ptr(), wp.data_ptr(),
                                                         _ones(B, cout, xh.device).data_ptr(), B, r, cin, cout,
                                                         _lib.stream_of(xh)), "conv_transpose3x3_tc")
-    out = torch.empty((B, 2 * r + 1, 2 * r + 1, cout), device=xh.device, dtype=torch.bfloat16)
-    for s in range(4):
-        py, px = s >> 1, s & 1
-        out[:, py::2, px::2, :] = planes[s, :, :P - py, :P - px, :]
-    return out
+    return planes
 
 
-def tc_conv_transpose3x3_dgrad_nhwc(gh, wp_t):
-    """input gradient of tc_conv_transpose3x3_nhwc: gx[i,j,ci] = sum_{a,b,co} gy[2i+a, 2j+b, co] * w[co,ci,a,b], a
-    stride-2 convolution evaluated as the sum of four stride-1 convolutions (4, 2, 2, 1 taps) over the polyphase planes
-    of gy.  gh NHWC bf16 [B,2r+1,2r+1,Cout]; wp_t = pack(w^T) [9,Cin,Cout] -> NHWC bf16 [B,r,r,Cin]."""
+def planes_to_nchw(planes, scale, dtype, other=None):
+    """polyphase planes [4,B,P,P,C] bf16 -> [B,C,2P-1,2P-1] `dtype`, times scale[b,c]; with `other` (NCHW) also
+    red[b,c] = sum_p other * planes (csrc/layout_ops.cu, polyphase addressing: no interleaving copy)"""
+    _, B, P, _, Cn = planes.shape
+    R = 2 * P - 1
+    out = torch.empty((B, Cn, R, R), device=planes.device, dtype=dtype)
+    red = torch.zeros((B, Cn), device=planes.device, dtype=torch.float32) if other is not None else None
+    sc = None if scale is None else scale.detach().float().contiguous()
+    if other is not None:
+        other = other.detach().to(dtype).contiguous()
+    with _lib.device_of(planes):
+        _lib.check(_lib.load().sg2_polyphase_bf16_to_nchw(out.data_ptr(), planes.data_ptr(), _lib.ptr(sc), _lib.ptr(other),
+                                                          _lib.ptr(red), B, Cn, R, _lib.dtype_code(out), _lib.stream_of(planes)),
+                   "polyphase_bf16_to_nchw")
+    return out, red
+
+
+def to_planes(x, scale=None, other=None):
+    """[B,C,R,R] (R odd) -> zero-padded polyphase planes [4,B,P,P,C] bf16 of x * scale[b,c]; with `other` (planes of the
+    same shape) also red[b,c] = sum_p x * other"""
+    x = x.detach().contiguous()
+    B, Cn, R, _ = x.shape
+    P = (R + 1) // 2
+    planes = torch.zeros((4, B, P, P, Cn), device=x.device, dtype=torch.bfloat16)
+    red = torch.zeros((B, Cn), device=x.device, dtype=torch.float32) if other is not None else None
+    sc = None if scale is None else scale.detach().float().contiguous()
+    with _lib.device_of(x):
+        _lib.check(_lib.load().sg2_nchw_to_polyphase_bf16(planes.data_ptr(), x.data_ptr(), _lib.ptr(sc), _lib.ptr(other),
+                                                          _lib.ptr(red), B, Cn, R, _lib.dtype_code(x), _lib.stream_of(x)),
+                   "nchw_to_polyphase_bf16")
+    return planes, red
+
+
+def tc_conv_transpose3x3_dgrad_planes(planes, wp_t):
+    """input gradient of the transposed conv: gx[i,j,ci] = sum_{a,b,co} gy[2i+a, 2j+b, co] * w[co,ci,a,b], a stride-2
+    convolution evaluated as the sum of four stride-1 convolutions (4, 2, 2, 1 taps) over the zero-padded polyphase
+    planes of gy [4,B,r+1,r+1,Cout]; wp_t = pack(w^T) [9,Cin,Cout] -> NHWC bf16 [B,r,r,Cin]."""
     lib = _lib.load()
-    B, R, _, cout = gh.shape
+    _, B, P, _, cout = planes.shape
     cin = wp_t.shape[1]
-    r = (R - 1) // 2
-    P = r + 1
-    planes = torch.zeros((4, B, P, P, cout), device=gh.device, dtype=torch.bfloat16)
-    for s in range(4):
-        py, px = s >> 1, s & 1
-        planes[s, :, :P - py, :P - px, :] = gh[:, py::2, px::2, :]
-    ones = _ones(B, cin, gh.device)
+    r = P - 1
+    ones = _ones(B, cin, planes.device)
     acc = None
-    with _lib.device_of(gh):
-        st = _lib.stream_of(gh)
+    with _lib.device_of(planes):
+        st = _lib.stream_of(planes)
         for s in range(4):
             py, px = s >> 1, s & 1
             taps = [(da, db, (2 * da + py) * 3 + 2 * db + px) for da in range(2 - py) for db in range(2 - px)]
             flat = (C.c_int * (3 * len(taps)))(*[v for t in taps for v in t])
-            part = torch.empty((B, P, P, cin), device=gh.device, dtype=torch.bfloat16)
+            part = torch.empty((B, P, P, cin), device=planes.device, dtype=torch.bfloat16)
             _lib.check(lib.sg2_conv_taps_tc(part.data_ptr(), planes[s].data_ptr(), wp_t.data_ptr(), ones.data_ptr(), B, P, cout,
                                             cin, flat, len(taps), st), "conv_taps_tc")
             part = part[:, :r, :r, :].float()
@@ -303,12 +327,12 @@ def tc_conv_transpose3x3(x, weight4):
     """y = conv_transpose2d(x, weight4^T, stride=2) (the up-sampling ModulatedConv2d before its blur) on the tensor-core
     kernel: x [B,Cin,r,r], weight4 [Cout,Cin,3,3] -> [B,Cout,2r+1,2r+1] in x.dtype."""
     xh, _ = to_nhwc(x)
-    return to_nchw(tc_conv_transpose3x3_nhwc(xh, _tc_pack(weight4)), None, x.dtype)[0]
+    return planes_to_nchw(tc_conv_transpose3x3_planes(xh, _tc_pack(weight4)), None, x.dtype)[0]
 
 
 def tc_conv_transpose3x3_dgrad(gy, weight4):
-    gh, _ = to_nhwc(gy)
-    return to_nchw(tc_conv_transpose3x3_dgrad_nhwc(gh, _tc_pack(weight4.detach().transpose(0, 1))), None, gy.dtype)[0]
+    planes, _ = to_planes(gy)
+    return to_nchw(tc_conv_transpose3x3_dgrad_planes(planes, _tc_pack(weight4.detach().transpose(0, 1))), None, gy.dtype)[0]
 
 
 def _wgrad(mode, x, weight4, gy):
@@ -336,8 +360,12 @@ class ModulatedConvTCFunction(torch.autograd.Function):
     def forward(ctx, x, s, d, weight4, mode):
         xh, _ = to_nhwc(x, s)
         wp = _tc_pack(weight4)
-        yh = tc_conv3x3_nhwc(xh, wp) if mode == 0 else tc_conv_transpose3x3_nhwc(xh, wp)
-        y, _ = to_nchw(yh, d, x.dtype)
+        if mode == 0:
+            yh = tc_conv3x3_nhwc(xh, wp)
+            y, _ = to_nchw(yh, d, x.dtype)
+        else:                                   # the conv output stays in its polyphase planes
+            yh = tc_conv_transpose3x3_planes(xh, wp)
+            y, _ = planes_to_nchw(yh, d, x.dtype)
         ctx.save_for_backward(x, s, d, weight4, yh)
         ctx.mode = mode
         return y
@@ -349,13 +377,14 @@ class ModulatedConvTCFunction(torch.autograd.Function):
         mode = ctx.mode
         gy = gy.contiguous()
         need_d = d is not None and ctx.needs_input_grad[2]
-        gh, gd = to_nhwc(gy, d, other=yh if need_d else None)             # gh = bf16(d * gy), gd = sum_p gy * conv
+        # gh = bf16(d * gy) (mode 1: straight into zero-padded polyphase planes), gd = sum_p gy * conv
+        gh, gd = (to_nhwc if mode == 0 else to_planes)(gy, d, other=yh if need_d else None)
         gx = gs = gw = None
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
             if mode == 0:
                 gxh = tc_conv3x3_nhwc(gh, _tc_pack(weight4.detach().flip([2, 3]).transpose(0, 1)))
             else:
-                gxh = tc_conv_transpose3x3_dgrad_nhwc(gh, _tc_pack(weight4.detach().transpose(0, 1)))
+                gxh = tc_conv_transpose3x3_dgrad_planes(gh, _tc_pack(weight4.detach().transpose(0, 1)))
             gx, gs = to_nchw(gxh, s, x.dtype, other=x if ctx.needs_input_grad[1] else None)   # gx = s * g, gs = sum_p x * g
             if gs is not None:
                 gs = gs.to(s.dtype)

@@ -57,18 +57,19 @@ def grad_bias_reduce(grad_input):
 
 class FusedLeakyReLUFunctionBackward(Function):
     @staticmethod
-    def forward(ctx, grad_output, out, negative_slope, scale):
+    def forward(ctx, grad_output, out, negative_slope, scale, want_bias=True):
         ctx.save_for_backward(out)
         ctx.negative_slope, ctx.scale = negative_slope, scale
         grad_input = bias_act(grad_output, None, out, 3, 1, negative_slope, scale)
-        grad_bias = grad_bias_reduce(grad_input).detach()
+        # the reduction over the whole activation is skipped when the bias is frozen (the ReStyle direction)
+        grad_bias = grad_bias_reduce(grad_input).detach() if want_bias else grad_input.new_zeros(out.shape[1])
         return grad_input, grad_bias
 
     @staticmethod
     def backward(ctx, gradgrad_input, gradgrad_bias):
         out, = ctx.saved_tensors
         gradgrad_out = bias_act(gradgrad_input, gradgrad_bias, out, 3, 1, ctx.negative_slope, ctx.scale)
-        return gradgrad_out, None, None, None
+        return gradgrad_out, None, None, None, None
 
 
 class FusedLeakyReLUFunction(Function):
@@ -83,8 +84,8 @@ class FusedLeakyReLUFunction(Function):
     def backward(ctx, grad_output):
         out, = ctx.saved_tensors
         grad_input, grad_bias = FusedLeakyReLUFunctionBackward.apply(
-            grad_output, out, ctx.negative_slope, ctx.scale)
-        return grad_input, grad_bias, None, None
+            grad_output, out, ctx.negative_slope, ctx.scale, ctx.needs_input_grad[1])
+        return grad_input, (grad_bias if ctx.needs_input_grad[1] else None), None, None
 
 
 class FusedLeakyReLU(nn.Module):

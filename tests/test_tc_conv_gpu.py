@@ -218,3 +218,33 @@ def test_styled_conv_tc_function_gradients(sg2, B, cin, cout, r, shared_noise):
     for a, b in zip(dev[:3], leaves[:3]):
         assert (a.grad.cpu().double() - b.grad).abs().max() <= 1.2e-2 * b.grad.abs().max()
     assert all(t.grad is None for t in dev[3:])
+
+
+@pytest.mark.parametrize("B,Cn,R", [(2, 32, 9), (1, 96, 33), (3, 64, 5)])
+def test_polyphase_layout_passes(sg2, B, Cn, R):
+    """NCHW <-> the four polyphase planes the transposed convolution writes (no interleaving copies)"""
+    K = _K()
+    g = torch.Generator().manual_seed(Cn + R)
+    x = torch.randn(B, Cn, R, R, generator=g)
+    sc = torch.rand(B, Cn, generator=g) + 0.5
+    P = (R + 1) // 2
+    oth = torch.randn(4, B, P, P, Cn, generator=g).bfloat16()
+    planes, red = K.to_planes(x.to(DEV), sc.to(DEV), other=oth.to(DEV))
+    xs = (x * sc.view(B, Cn, 1, 1))
+    rref = torch.zeros(B, Cn, dtype=torch.float64)
+    for s in range(4):
+        py, px = s >> 1, s & 1
+        want = xs[:, :, py::2, px::2].permute(0, 2, 3, 1)
+        got = planes[s].cpu().float()
+        assert (got[:, :P - py, :P - px] - want).abs().max() <= 2 ** -8 * want.abs().max()
+        assert got[:, P - py:].abs().sum() == 0 and got[:, :, P - px:].abs().sum() == 0       # the padding stays zero
+        rref += (x[:, :, py::2, px::2].permute(0, 2, 3, 1).double() * oth[s, :, :P - py, :P - px].double()).sum((1, 2))
+    assert (red.cpu().double() - rref).abs().max() <= 1e-5 * rref.abs().max() + 1e-5
+    y, red2 = K.planes_to_nchw(planes, sc.to(DEV), torch.float32, other=x.to(DEV))
+    yref = torch.zeros(B, Cn, R, R)
+    for s in range(4):
+        py, px = s >> 1, s & 1
+        yref[:, :, py::2, px::2] = planes[s].cpu().float()[:, :P - py, :P - px].permute(0, 3, 1, 2)
+    r2 = (yref.double() * x.double()).sum((2, 3))
+    assert (y.cpu() - yref * sc.view(B, Cn, 1, 1)).abs().max() <= 1e-6 * yref.abs().max()
+    assert (red2.cpu().double() - r2).abs().max() <= 1e-5 * r2.abs().max() + 1e-5
