@@ -222,6 +222,15 @@ int sg2_synth_forward(sg2_synth *plan, void *workspace, const float *latent, int
 int sg2_synth_set_profile_events(sg2_synth *plan, void **events, int n_events);
 int sg2_synth_profile_events_used(const sg2_synth *plan);
 
+/* The modulated 1x1 convolution of ToRGB (model.py:350-355: ModulatedConv2d(in, 3, 1, demodulate=False)) and what
+ * autograd derives for it, one HBM-bound pass over the activation each way, fp32 math:
+ *   fwd: y[b,k,p] = sum_c w[k,c] * s[b,c] * x[b,c,p]          w [K,C] fp32 (conv scale folded), s [B,C] fp32, K <= 4
+ *   bwd: gx[b,c,p] = s[b,c] * t, gs[b,c] += sum_p x[b,c,p] * t, t = sum_k w[k,c] * gy[b,k,p]   (gs fp32, zero it first) */
+int sg2_rgb_modconv_fwd(void *y, const void *x, const float *w, const float *s, int64_t B, int C, int K, int64_t HW,
+                        int dtype, sg2_stream_t stream);
+int sg2_rgb_modconv_bwd(void *gx, float *gs, const void *gy, const void *x, const float *w, const float *s, int64_t B,
+                        int C, int K, int64_t HW, int dtype, sg2_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * One 3x3 stride-1 'same' convolution on the tensor-core kernel (tcgen05/TMEM, operands by TMA), outside the
  * whole-network plan: the contraction inside ModulatedConv2d.forward (model.py:254-273: F.conv2d with padding 1)

@@ -492,6 +492,48 @@ class StyledConvTCFunction(torch.autograd.Function):
         return gx, gs, gd, gw, gnoise, gnw, gbias, None, None
 
 
+class RgbModConvFunction(torch.autograd.Function):
+    """y[b,k] = sum_c w[k,c] * s[b,c] * x[b,c]: the modulated 1x1 convolution of ToRGB (model.py:350-355, no
+    demodulation) -- one pass over the activation each way (csrc/torgb.cu), fp32 math.  x [B,C,H,W]; s [B,C];
+    w2 [K,C] with the conv scale folded in."""
+
+    @staticmethod
+    def forward(ctx, x, s, w2):
+        _lib.require_cuda(x)
+        x = x.contiguous()
+        B, Cn, H, W = x.shape
+        K_ = w2.shape[0]
+        wf, sf = w2.detach().float().contiguous(), s.detach().float().contiguous()
+        y = torch.empty((B, K_, H, W), device=x.device, dtype=x.dtype)
+        with _lib.device_of(x):
+            _lib.check(_lib.load().sg2_rgb_modconv_fwd(y.data_ptr(), x.data_ptr(), wf.data_ptr(), sf.data_ptr(), B, Cn, K_, H * W,
+                                                       _lib.dtype_code(x), _lib.stream_of(x)), "rgb_modconv_fwd")
+        ctx.save_for_backward(x, s, w2)
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gy):
+        x, s, w2 = ctx.saved_tensors
+        B, Cn, H, W = x.shape
+        K_ = w2.shape[0]
+        gy = gy.contiguous().to(x.dtype)
+        gx = gs = gw = None
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            wf, sf = w2.detach().float().contiguous(), s.detach().float().contiguous()
+            gx = torch.empty_like(x)
+            gs = torch.zeros((B, Cn), device=x.device, dtype=torch.float32)
+            with _lib.device_of(x):
+                _lib.check(_lib.load().sg2_rgb_modconv_bwd(gx.data_ptr(), gs.data_ptr(), gy.data_ptr(), x.data_ptr(), wf.data_ptr(),
+                                                           sf.data_ptr(), B, Cn, K_, H * W, _lib.dtype_code(x), _lib.stream_of(x)),
+                           "rgb_modconv_bwd")
+            gs = gs.to(s.dtype)
+        if ctx.needs_input_grad[2]:            # rare (the decoder itself trains): gw[k,c] = sum_{b,p} gy[b,k,p] * s[b,c] * x[b,c,p]
+            gw = torch.einsum("bkp,bcp->bkc", gy.float().flatten(2), x.detach().float().flatten(2))
+            gw = (gw * s.detach().float().unsqueeze(1)).sum(0).to(w2.dtype)
+        return gx, gs, gw
+
+
 class SharedConvFunction(torch.autograd.Function):
     """y = conv(x, W) with one weight tensor shared by the batch (the contraction inside
     ModulatedConv2d once modulation/demodulation are factored out).  forward and grad_x run on the

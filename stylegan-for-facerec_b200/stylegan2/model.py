@@ -213,6 +213,9 @@ class ModulatedConv2d(nn.Module):
         batch = input.shape[0]
         s = self.modulation(style)                                        # [B, Cin]
         w4 = self.weight[0] * self.scale                                   # [Cout, Cin, k, k]
+        if self.kernel_size == 1 and self._mode == 0 and not self.demodulate and self.out_channel <= 4 and self.in_channel <= 1024:
+            # ToRGB: one pass over the activation each way (functional.RgbModConvFunction), exact fp32 math
+            return K.RgbModConvFunction.apply(input, s, w4.reshape(self.out_channel, self.in_channel))
         if K.tc_conv_ok(input, w4, self._mode):
             # tensor-core route: modulate + layout / conv / demodulate + layout, each one pass, grad_s and grad_d
             # produced by the adjoint passes (functional.ModulatedConvTCFunction)

@@ -175,6 +175,8 @@ def modulated_conv2d(x, weight, styles, padding=0, demodulate=True):
         raise RuntimeError(f"sg2_b200 modulated_conv2d: kernel {k} / padding {padding} not supported (1x1 pad 0, 3x3 pad 1)")
     if K.needs_grad(x, weight, styles):
         b = x.shape[0]
+        if k == 1 and not demodulate and weight.shape[0] <= 4 and weight.shape[1] <= 1024:     # ToRGB: one pass each way
+            return K.RgbModConvFunction.apply(x, styles, weight.reshape(weight.shape[0], weight.shape[1]))
         if K.tc_conv_ok(x, weight, 0):                                          # tensor-core route, see functional.py
             d = None
             if demodulate:

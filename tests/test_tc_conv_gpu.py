@@ -248,3 +248,25 @@ def test_polyphase_layout_passes(sg2, B, Cn, R):
     r2 = (yref.double() * x.double()).sum((2, 3))
     assert (y.cpu() - yref * sc.view(B, Cn, 1, 1)).abs().max() <= 1e-6 * yref.abs().max()
     assert (red2.cpu().double() - r2).abs().max() <= 1e-5 * r2.abs().max() + 1e-5
+
+
+@pytest.mark.parametrize("B,Cn,H,W,dt", [(2, 128, 16, 16, torch.float32), (3, 512, 4, 4, torch.float32), (1, 32, 65, 67, torch.float32),
+                                        (2, 64, 32, 32, torch.bfloat16), (1, 13, 130, 70, torch.float32)])
+def test_rgb_modconv_function_vs_fp64(sg2, B, Cn, H, W, dt):
+    """the modulated 1x1 convolution of ToRGB (model.py:350-355) and every gradient vs fp64 autograd"""
+    K = _K()
+    g = torch.Generator().manual_seed(Cn + H)
+    x = torch.randn(B, Cn, H, W, generator=g).to(dt)
+    s = torch.rand(B, Cn, generator=g) + 0.5
+    w = torch.randn(3, Cn, generator=g) / Cn ** 0.5
+    gy = torch.randn(B, 3, H, W, generator=g).to(dt)
+    x64, s64, w64 = (t.double().requires_grad_(True) for t in (x, s, w))
+    ref = torch.einsum("kc,bc,bchw->bkhw", w64, s64, x64)
+    ref.backward(gy.double())
+    xd, sd, wd = (t.to(DEV).requires_grad_(True) for t in (x, s, w))
+    y = K.RgbModConvFunction.apply(xd, sd, wd)
+    y.backward(gy.to(DEV))
+    tol = 2 ** -7 if dt == torch.bfloat16 else 2e-5
+    for name, a, b in (("y", y.detach(), ref.detach()), ("gx", xd.grad, x64.grad), ("gs", sd.grad, s64.grad), ("gw", wd.grad, w64.grad)):
+        err = (a.cpu().double() - b).abs().max().item()
+        assert a.shape == b.shape and err <= tol * b.abs().max().item() + 1e-6, (name, err, b.abs().max().item())
