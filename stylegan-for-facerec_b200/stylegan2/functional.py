@@ -357,9 +357,10 @@ class ModulatedConvTCFunction(torch.autograd.Function):
     x [B,Cin,r,r]; s [B,Cin], d [B,Cout] fp32 (d may be None); weight4 [Cout,Cin,3,3]."""
 
     @staticmethod
-    def forward(ctx, x, s, d, weight4, mode):
+    def forward(ctx, x, s, d, weight4, mode, wp=None, wp_adj=None):
         xh, _ = to_nhwc(x, s)
-        wp = _tc_pack(weight4)
+        wp = _tc_pack(weight4) if wp is None else wp
+        ctx.wp_adj = wp_adj
         if mode == 0:
             yh = tc_conv3x3_nhwc(xh, wp)
             y, _ = to_nchw(yh, d, x.dtype)
@@ -382,9 +383,9 @@ class ModulatedConvTCFunction(torch.autograd.Function):
         gx = gs = gw = None
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
             if mode == 0:
-                gxh = tc_conv3x3_nhwc(gh, _tc_pack(weight4.detach().flip([2, 3]).transpose(0, 1)))
+                gxh = tc_conv3x3_nhwc(gh, ctx.wp_adj if ctx.wp_adj is not None else _tc_pack(weight4.detach().flip([2, 3]).transpose(0, 1)))
             else:
-                gxh = tc_conv_transpose3x3_dgrad_planes(gh, _tc_pack(weight4.detach().transpose(0, 1)))
+                gxh = tc_conv_transpose3x3_dgrad_planes(gh, ctx.wp_adj if ctx.wp_adj is not None else _tc_pack(weight4.detach().transpose(0, 1)))
             gx, gs = to_nchw(gxh, s, x.dtype, other=x if ctx.needs_input_grad[1] else None)   # gx = s * g, gs = sum_p x * g
             if gs is not None:
                 gs = gs.to(s.dtype)
@@ -395,7 +396,7 @@ class ModulatedConvTCFunction(torch.autograd.Function):
             gw = _wgrad(mode, xm, weight4, gc)
         if gd is not None:
             gd = gd.to(d.dtype)
-        return gx, gs, gd, gw, None
+        return gx, gs, gd, gw, None, None, None
 
 
 def to_nchw_act(h, scale, dtype, noise, noise_weight, bias, alpha, gain):
@@ -447,9 +448,10 @@ class StyledConvTCFunction(torch.autograd.Function):
     adjoint weights, style (+ grad_s) + to NCHW."""
 
     @staticmethod
-    def forward(ctx, x, s, d, weight4, noise, noise_weight, bias, alpha, gain):
+    def forward(ctx, x, s, d, weight4, noise, noise_weight, bias, alpha, gain, wp=None, wp_adj=None):
         xh, _ = to_nhwc(x, s)
-        yh = tc_conv3x3_nhwc(xh, _tc_pack(weight4))
+        yh = tc_conv3x3_nhwc(xh, _tc_pack(weight4) if wp is None else wp)
+        ctx.wp_adj = wp_adj
         out = to_nchw_act(yh, d, x.dtype, noise, noise_weight, bias, alpha, gain)
         ctx.save_for_backward(x, s, d, weight4, yh, out, noise, noise_weight)
         ctx.act = (alpha, gain)
@@ -465,7 +467,7 @@ class StyledConvTCFunction(torch.autograd.Function):
         gh, gd, tot = to_nhwc_actgrad(gout, out, alpha, gain, d, other=yh if need_d else None, want_sum=need[6])
         gx = gs = gw = gnoise = gnw = gbias = None
         if need[0] or need[1]:
-            gxh = tc_conv3x3_nhwc(gh, _tc_pack(weight4.detach().flip([2, 3]).transpose(0, 1)))
+            gxh = tc_conv3x3_nhwc(gh, ctx.wp_adj if ctx.wp_adj is not None else _tc_pack(weight4.detach().flip([2, 3]).transpose(0, 1)))
             gx, gs = to_nchw(gxh, s, x.dtype, other=x if need[1] else None)
             if gs is not None:
                 gs = gs.to(s.dtype)
@@ -489,7 +491,54 @@ class StyledConvTCFunction(torch.autograd.Function):
                 xm = x.detach().float() * s.detach().float().view(B, -1, 1, 1)
                 gc = g.float() if d is None else g.float() * d.detach().float().view(B, -1, 1, 1)
                 gw = _wgrad(0, xm, weight4, gc)
-        return gx, gs, gd, gw, gnoise, gnw, gbias, None, None
+        return gx, gs, gd, gw, gnoise, gnw, gbias, None, None, None, None
+
+
+def cached_tc_packs(owner, weight4_fn, version_key, mode):
+    """(w4, wp, wp_adj, wsq) of a FROZEN conv weight for the tensor-core route, cached on `owner` until the parameter
+    changes: w4 = weight4_fn() detached [Cout,Cin,3,3], wp / wp_adj its packed forward / adjoint forms, wsq [Cout,Cin] the
+    per-(co,ci) sum of squared taps the demodulation needs.  Saves a scale, two flips/transposes and two pack launches
+    per layer per step, forward and backward."""
+    c = owner.__dict__.get("_tc_cache")
+    if c is None or c[0] != version_key:
+        with torch.no_grad():
+            w4 = weight4_fn().detach()
+            adj = w4.flip([2, 3]).transpose(0, 1) if mode == 0 else w4.transpose(0, 1)
+            c = (version_key, w4, _tc_pack(w4), _tc_pack(adj), w4.float().pow(2).sum([2, 3]))
+        owner.__dict__["_tc_cache"] = c
+    return c[1:]
+
+
+class NoiseBiasActFunction(torch.autograd.Function):
+    """out = lrelu(x + noise_weight * noise + bias[c], alpha) * gain (NoiseInjection + FusedLeakyReLU, model.py:282-287,335)
+    as one pass each way (first-order autograd); used after the blur of the up-sampling layers on the tensor-core route."""
+
+    @staticmethod
+    def forward(ctx, x, noise, noise_weight, bias, alpha, gain):
+        out = noise_bias_act(x, noise, noise_weight, bias, act=3, alpha=alpha, act_scale=gain)
+        ctx.save_for_backward(out, noise, noise_weight)
+        ctx.act = (alpha, gain)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        from .op.fused_act import bias_act, grad_bias_reduce
+        out, noise, noise_weight = ctx.saved_tensors
+        alpha, gain = ctx.act
+        need = ctx.needs_input_grad
+        gx = bias_act(g.contiguous(), None, out, 3, 1, alpha, gain)
+        gnoise = gnw = gbias = None
+        if need[3]:
+            gbias = grad_bias_reduce(gx)
+        if noise is not None and (need[1] or need[2]):
+            t = gx.float().sum(1, keepdim=True)                                              # [B,1,H,W]
+            if need[1]:
+                gn = noise_weight.detach().float().view(1, 1, 1, 1) * t
+                gnoise = (gn if noise.shape[0] == gx.shape[0] else gn.sum(0, keepdim=True)).reshape(noise.shape).to(noise.dtype)
+            if need[2]:
+                gnw = (t * noise.detach().float().reshape(-1, 1, *t.shape[2:])).sum().reshape(noise_weight.shape).to(noise_weight.dtype)
+        return gx, gnoise, gnw, gbias, None, None
 
 
 class RgbModConvFunction(torch.autograd.Function):

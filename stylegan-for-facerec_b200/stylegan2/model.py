@@ -207,6 +207,16 @@ class ModulatedConv2d(nn.Module):
             out = self.blur(out)
         return out
 
+    def _tc_weights(self, w4=None):
+        """(w4, packed forward weights, packed adjoint weights, wsq [Cout,Cin]) for the tensor-core route; cached while the
+        weight is frozen (the ReStyle direction), recomputed -- and differentiable through w4 / wsq -- when it trains"""
+        w = self.weight
+        if not (w.requires_grad and torch.is_grad_enabled()):
+            return K.cached_tc_packs(self, lambda: w[0] * self.scale, (w.data_ptr(), w._version, str(w.device)), self._mode)
+        if w4 is None:
+            w4 = w[0] * self.scale
+        return w4, None, None, w4.float().pow(2).sum([2, 3])
+
     def _forward_autograd(self, input, style):
         """differentiable path.  Same algebra as the kernels: y = d[b,co] * conv(W*scale, s[b,ci]*x),
         d = rsqrt(sum_ci s^2 * sum_k (scale*W)^2 + eps)  ==  model.py:236-240 without per-sample weights."""
@@ -219,10 +229,9 @@ class ModulatedConv2d(nn.Module):
         if K.tc_conv_ok(input, w4, self._mode):
             # tensor-core route: modulate + layout / conv / demodulate + layout, each one pass, grad_s and grad_d
             # produced by the adjoint passes (functional.ModulatedConvTCFunction)
-            d = None
-            if self.demodulate:
-                d = torch.rsqrt(s.float().pow(2) @ w4.float().pow(2).sum([2, 3]).t() + self.eps)
-            y = K.ModulatedConvTCFunction.apply(input, s.float(), d, w4, self._mode)
+            w4, wp, wp_adj, wsq = self._tc_weights(w4)
+            d = torch.rsqrt(s.float().pow(2) @ wsq.t() + self.eps) if self.demodulate else None
+            y = K.ModulatedConvTCFunction.apply(input, s.float(), d, w4, self._mode, wp, wp_adj)
             return self.blur(y) if self.upsample else y
         x = input * s.to(input.dtype).view(batch, -1, 1, 1)
         if self.downsample:
@@ -284,11 +293,17 @@ class StyledConv(nn.Module):
             if noise is None:
                 noise = input.new_empty(input.shape[0], 1, input.shape[2], input.shape[3]).normal_()
             s = conv.modulation(style)
-            w4 = conv.weight[0] * conv.scale
-            d = torch.rsqrt(s.float().pow(2) @ w4.float().pow(2).sum([2, 3]).t() + conv.eps) if conv.demodulate else None
+            w4, wp, wp_adj, wsq = conv._tc_weights()
+            d = torch.rsqrt(s.float().pow(2) @ wsq.t() + conv.eps) if conv.demodulate else None
             return K.StyledConvTCFunction.apply(input, s.float(), d, w4, noise, self.noise.weight, self.activate.bias,
-                                                self.activate.negative_slope, self.activate.scale)
+                                                self.activate.negative_slope, self.activate.scale, wp, wp_adj)
         out = self.conv(input, style)
+        if out.is_cuda and K.tc_grad_enabled() and K.needs_grad(out, noise, self.noise.weight, self.activate.bias):
+            # tensor-core route, after the blur of an up-sampling layer: noise + bias + activation in one pass each way
+            if noise is None:
+                noise = out.new_empty(out.shape[0], 1, out.shape[2], out.shape[3]).normal_()
+            return K.NoiseBiasActFunction.apply(out, noise, self.noise.weight, self.activate.bias,
+                                                self.activate.negative_slope, self.activate.scale)
         if not K.needs_grad(out, noise, self.noise.weight, self.activate.bias):
             # conv -> (+ w*noise) -> (+ bias) -> lrelu*sqrt(2) in one pass over the activation
             if noise is None:

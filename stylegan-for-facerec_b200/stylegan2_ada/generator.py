@@ -204,9 +204,14 @@ class SynthesisLayer2(torch.nn.Module):                      # generator.py:172-
             if not isinstance(self.resampler, SmoothUpsample) and K.tc_conv_ok(x, self.weight, 0):
                 # the whole layer in three passes each way on the tensor-core route (functional.StyledConvTCFunction)
                 s = self.affine(w).float()
-                d = torch.rsqrt(s.square() @ self.weight.float().square().sum([2, 3]).t() + 1e-8)
+                wt = self.weight
+                if wt.requires_grad:
+                    w4, wp, wp_adj, wsq = wt, None, None, wt.float().square().sum([2, 3])
+                else:                             # frozen decoder: packed weights cached until the parameter changes
+                    w4, wp, wp_adj, wsq = K.cached_tc_packs(self, lambda: wt, (wt.data_ptr(), wt._version, str(wt.device)), 0)
+                d = torch.rsqrt(s.square() @ wsq.t() + 1e-8)
                 nz = None if noise is None else noise.reshape(-1, 1, self.resolution, self.resolution)
-                y = K.StyledConvTCFunction.apply(x, s, d, self.weight, nz, self.noise_strength, self.bias, 0.2, g)
+                y = K.StyledConvTCFunction.apply(x, s, d, w4, nz, self.noise_strength, self.bias, 0.2, g, wp, wp_adj)
                 return torch.clamp(y, -c, c)
             y = modulated_conv2d(x=x, weight=self.weight, styles=self.affine(w), padding=self.padding)
             if isinstance(self.resampler, SmoothUpsample):

@@ -270,3 +270,24 @@ def test_rgb_modconv_function_vs_fp64(sg2, B, Cn, H, W, dt):
     for name, a, b in (("y", y.detach(), ref.detach()), ("gx", xd.grad, x64.grad), ("gs", sd.grad, s64.grad), ("gw", wd.grad, w64.grad)):
         err = (a.cpu().double() - b).abs().max().item()
         assert a.shape == b.shape and err <= tol * b.abs().max().item() + 1e-6, (name, err, b.abs().max().item())
+
+
+def test_frozen_weight_cache_follows_the_parameter(sg2, oracle):
+    """the packed-weight cache of the tensor-core route is keyed on the parameter's version: an in-place update of a
+    frozen weight (load_state_dict, optimizer step of an outer loop) must be seen by the next forward"""
+    G = sg2.Generator(16, 512, 2).to(DEV).eval()
+    G.precision = 'bf16'
+    for p in G.parameters():
+        p.requires_grad_(False)
+    lat = torch.randn(2, G.n_latent, 512, device=DEV)
+    a, _ = G([lat.clone().requires_grad_(True)], input_is_latent=True, randomize_noise=False)
+    b, _ = G([lat.clone().requires_grad_(True)], input_is_latent=True, randomize_noise=False)
+    assert torch.equal(a, b)
+    with torch.no_grad():
+        G.convs[1].conv.weight.mul_(1.5)
+        G.convs[1].conv.weight[0, :8].add_(0.3)
+    c, _ = G([lat.clone().requires_grad_(True)], input_is_latent=True, randomize_noise=False)
+    G.precision = 'exact'
+    e, _ = G([lat.clone().requires_grad_(True)], input_is_latent=True, randomize_noise=False)
+    assert not torch.equal(a, c)
+    assert (c - e).abs().max() <= 3e-2 * e.abs().max()          # the updated weights, not the cached ones
