@@ -271,6 +271,11 @@ int sg2_nchw_to_polyphase_bf16(void *planes, const void *x, const float *scale, 
                                int64_t B, int C, int W, int dtype, sg2_stream_t stream);
 int sg2_polyphase_bf16_to_nchw(void *out, const void *planes, const float *scale, const void *other, float *red,
                                int64_t B, int C, int W, int dtype, sg2_stream_t stream);
+/* out[b,c,y,x] = scale[b,c] * sum_k parts[k][b][y][x][c] over the top-left W x W corner of n_parts (1..4) bf16 tensors
+ * [B][pitch][pitch][C], summed in fp32; other / red as above.  Turns the four polyphase components of the transposed
+ * conv's input gradient (sg2_conv_taps_tc outputs) into grad_x and grad_s in one pass. */
+int sg2_sum_parts_bf16_to_nchw(void *out, const void *parts, int n_parts, int pitch, const float *scale, const void *other,
+                               float *red, int64_t B, int C, int W, int dtype, sg2_stream_t stream);
 /* The second pass with the StyledConv tail (NoiseInjection + FusedLeakyReLU, model.py:282-287,331-337) applied:
  *   out[b,c,p] = lrelu(scale[b,c] * h[b,p,c] + noise_weight[0] * noise[b or 0, p] + bias[c], alpha) * gain
  * (noise, noise_weight, bias: tensors of `dtype`; noise / bias may be NULL; noise_bstride = HW or 0), and its adjoint:

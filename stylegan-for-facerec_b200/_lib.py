@@ -81,6 +81,8 @@ SIGNATURES = {
                                     c_void_p]),
     "sg2_nchw_to_polyphase_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_int, c_int, c_void_p]),
     "sg2_polyphase_bf16_to_nchw": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_int, c_int, c_void_p]),
+    "sg2_sum_parts_bf16_to_nchw": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_int, c_int,
+                                           c_void_p]),
     "sg2_nhwc_bf16_to_nchw_act": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_void_p, c_float, c_float,
                                           c_i64, c_int, c_i64, c_int, c_void_p]),
     "sg2_nchw_to_nhwc_bf16_actgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p, c_void_p,

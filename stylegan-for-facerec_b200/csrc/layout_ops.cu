@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(256)
 nhwc_to_nchw_kernel(T *__restrict__ out, const __nv_bfloat16 *__restrict__ h, const float *__restrict__ scale,
                     const T *__restrict__ other, float *__restrict__ red, int C, long long HW, int act,
                     const T *__restrict__ noise, long long noise_bstride, const T *__restrict__ noise_weight,
-                    const T *__restrict__ bias, float alpha, float gain, int poly_w) {
+                    const T *__restrict__ bias, float alpha, float gain, int poly_w, int n_parts, int part_pitch) {
     __shared__ float tile[LT_C][LT_P + 1];
     __shared__ float csum[LT_C];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -121,8 +121,22 @@ nhwc_to_nchw_kernel(T *__restrict__ out, const __nv_bfloat16 *__restrict__ h, co
             const int pl = warp + 8 * j;
             const long long p = p0 + pl;
             float2 q = make_float2(0.f, 0.f);
-            if (c < C && p < HW)
-                q = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(h + nhwc_offset(b, p, C, HW, poly_w, gridDim.z) + c));
+            if (c < C && p < HW) {
+                if (n_parts == 0) {
+                    q = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(h + nhwc_offset(b, p, C, HW, poly_w, gridDim.z) + c));
+                } else {
+                    // sum of n_parts tensors [B][pitch][pitch][C], of which the top-left W x W corner (W = poly_w) is read:
+                    // the polyphase components of the transposed conv's input gradient, accumulated in fp32
+                    const int y = (int)(p / poly_w), x = (int)(p - (long long)y * poly_w);
+                    const long long base = ((b * part_pitch + y) * part_pitch + x) * C + c;
+                    const long long stride = (long long)gridDim.z * part_pitch * part_pitch * C;
+                    for (int k = 0; k < n_parts; ++k) {
+                        const float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(h + k * stride + base));
+                        q.x += t.x;
+                        q.y += t.y;
+                    }
+                }
+            }
             tile[2 * lane][pl] = q.x;
             tile[2 * lane + 1][pl] = q.y;
         }
@@ -191,14 +205,14 @@ static int run_nchw_to_nhwc(void *out, const void *x, const float *scale, const 
 }
 
 static int run_nhwc_to_nchw(void *out, const void *h, const float *scale, const void *other, float *red, int64_t B, int C,
-                            int64_t HW, int dtype, sg2_stream_t stream, int poly_w) {
+                            int64_t HW, int dtype, sg2_stream_t stream, int poly_w, int n_parts = 0, int part_pitch = 0) {
     int rc = check_layout_args("nhwc_bf16_to_nchw", out, h, other, red, B, C, HW);
     if (rc || B == 0) return rc;
     SG2_REQUIRE((reinterpret_cast<uintptr_t>(h) & 3) == 0, SG2_ERR_BAD_ARG, "nhwc_bf16_to_nchw: NHWC tensors must be 4-byte aligned");
     dim3 grid((unsigned)((HW + LT_P - 1) / LT_P), (unsigned)((C + LT_C - 1) / LT_C), (unsigned)B);
     SG2_DISPATCH_DTYPE(dtype, {
         nhwc_to_nchw_kernel<T><<<grid, 256, 0, as_stream(stream)>>>((T *)out, (const __nv_bfloat16 *)h, scale, (const T *)other,
-                                                                     red, C, (long long)HW, 0, nullptr, 0, nullptr, nullptr, 0.f, 1.f, poly_w);
+                                                                     red, C, (long long)HW, 0, nullptr, 0, nullptr, nullptr, 0.f, 1.f, poly_w, n_parts, part_pitch);
         SG2_LAUNCH_CHECK();
     });
     return SG2_OK;
@@ -219,7 +233,7 @@ extern "C" int sg2_nhwc_bf16_to_nchw_act(void *out, const void *h, const float *
     SG2_DISPATCH_DTYPE(dtype, {
         nhwc_to_nchw_kernel<T><<<grid, 256, 0, as_stream(stream)>>>((T *)out, (const __nv_bfloat16 *)h, scale, nullptr, nullptr, C,
                                                                      (long long)HW, 1, (const T *)noise, (long long)noise_bstride,
-                                                                     (const T *)noise_weight, (const T *)bias, alpha, gain, 0);
+                                                                     (const T *)noise_weight, (const T *)bias, alpha, gain, 0, 0, 0);
         SG2_LAUNCH_CHECK();
     });
     return SG2_OK;
@@ -267,4 +281,14 @@ extern "C" int sg2_polyphase_bf16_to_nchw(void *out, const void *planes, const f
                                           int64_t B, int C, int W, int dtype, sg2_stream_t stream) {
     SG2_REQUIRE(W >= 1 && W % 2 == 1 && W <= 32767, SG2_ERR_BAD_ARG, "polyphase_bf16_to_nchw: W must be odd, got %d", W);
     return run_nhwc_to_nchw(out, planes, scale, other, red, B, C, (int64_t)W * W, dtype, stream, W);
+}
+
+// out[b,c,y,x] = scale[b,c] * sum_k parts[k][b][y][x][c] for the top-left W x W corner of n_parts (1..4) tensors
+// [B][pitch][pitch][C] bf16, summed in fp32; other / red as in sg2_nhwc_bf16_to_nchw.  The four polyphase components of the
+// transposed conv's input gradient (sg2_conv_taps_tc outputs) become grad_x and grad_s in this one pass.
+extern "C" int sg2_sum_parts_bf16_to_nchw(void *out, const void *parts, int n_parts, int pitch, const float *scale, const void *other,
+                                          float *red, int64_t B, int C, int W, int dtype, sg2_stream_t stream) {
+    SG2_REQUIRE(n_parts >= 1 && n_parts <= 4 && W >= 1 && pitch >= W && pitch <= 32767, SG2_ERR_BAD_ARG,
+                "sum_parts_bf16_to_nchw: bad geometry (%d parts, W %d, pitch %d)", n_parts, W, pitch);
+    return run_nhwc_to_nchw(out, parts, scale, other, red, B, C, (int64_t)W * W, dtype, stream, W, n_parts, pitch);
 }

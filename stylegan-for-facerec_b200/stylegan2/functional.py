@@ -296,25 +296,40 @@ def to_planes(x, scale=None, other=None):
 def tc_conv_transpose3x3_dgrad_planes(planes, wp_t):
     """input gradient of the transposed conv: gx[i,j,ci] = sum_{a,b,co} gy[2i+a, 2j+b, co] * w[co,ci,a,b], a stride-2
     convolution evaluated as the sum of four stride-1 convolutions (4, 2, 2, 1 taps) over the zero-padded polyphase
-    planes of gy [4,B,r+1,r+1,Cout]; wp_t = pack(w^T) [9,Cin,Cout] -> NHWC bf16 [B,r,r,Cin]."""
+    planes of gy [4,B,r+1,r+1,Cout]; wp_t = pack(w^T) [9,Cin,Cout] -> the four components [4,B,r+1,r+1,Cin] bf16, whose
+    top-left r x r corners sum to the gradient (parts_to_nchw)."""
     lib = _lib.load()
     _, B, P, _, cout = planes.shape
     cin = wp_t.shape[1]
     r = P - 1
     ones = _ones(B, cin, planes.device)
-    acc = None
+    parts = torch.empty((4, B, P, P, cin), device=planes.device, dtype=torch.bfloat16)
     with _lib.device_of(planes):
         st = _lib.stream_of(planes)
         for s in range(4):
             py, px = s >> 1, s & 1
             taps = [(da, db, (2 * da + py) * 3 + 2 * db + px) for da in range(2 - py) for db in range(2 - px)]
             flat = (C.c_int * (3 * len(taps)))(*[v for t in taps for v in t])
-            part = torch.empty((B, P, P, cin), device=planes.device, dtype=torch.bfloat16)
-            _lib.check(lib.sg2_conv_taps_tc(part.data_ptr(), planes[s].data_ptr(), wp_t.data_ptr(), ones.data_ptr(), B, P, cout,
+            _lib.check(lib.sg2_conv_taps_tc(parts[s].data_ptr(), planes[s].data_ptr(), wp_t.data_ptr(), ones.data_ptr(), B, P, cout,
                                             cin, flat, len(taps), st), "conv_taps_tc")
-            part = part[:, :r, :r, :].float()
-            acc = part if acc is None else acc + part
-    return acc.to(torch.bfloat16).contiguous()
+    return parts
+
+
+def parts_to_nchw(parts, scale, dtype, other=None):
+    """the four polyphase components [4,B,P,P,C] of the transposed conv's input gradient -> scale[b,c] * their fp32 sum
+    over the valid (P-1)^2 corner as [B,C,P-1,P-1] `dtype`; with `other` (NCHW) also red[b,c] = sum_p other * sum"""
+    n, B, P, _, Cn = parts.shape
+    r = P - 1
+    out = torch.empty((B, Cn, r, r), device=parts.device, dtype=dtype)
+    red = torch.zeros((B, Cn), device=parts.device, dtype=torch.float32) if other is not None else None
+    sc = None if scale is None else scale.detach().float().contiguous()
+    if other is not None:
+        other = other.detach().to(dtype).contiguous()
+    with _lib.device_of(parts):
+        _lib.check(_lib.load().sg2_sum_parts_bf16_to_nchw(out.data_ptr(), parts.data_ptr(), n, P, _lib.ptr(sc), _lib.ptr(other),
+                                                          _lib.ptr(red), B, Cn, r, _lib.dtype_code(out), _lib.stream_of(parts)),
+                   "sum_parts_bf16_to_nchw")
+    return out, red
 
 
 def tc_conv3x3(x, weight4, scale=None):
@@ -332,7 +347,7 @@ def tc_conv_transpose3x3(x, weight4):
 
 def tc_conv_transpose3x3_dgrad(gy, weight4):
     planes, _ = to_planes(gy)
-    return to_nchw(tc_conv_transpose3x3_dgrad_planes(planes, _tc_pack(weight4.detach().transpose(0, 1))), None, gy.dtype)[0]
+    return parts_to_nchw(tc_conv_transpose3x3_dgrad_planes(planes, _tc_pack(weight4.detach().transpose(0, 1))), None, gy.dtype)[0]
 
 
 def _wgrad(mode, x, weight4, gy):
@@ -382,11 +397,13 @@ class ModulatedConvTCFunction(torch.autograd.Function):
         gh, gd = (to_nhwc if mode == 0 else to_planes)(gy, d, other=yh if need_d else None)
         gx = gs = gw = None
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
-            if mode == 0:
+            xo = x if ctx.needs_input_grad[1] else None
+            if mode == 0:                                                          # gx = s * g, gs = sum_p x * g
                 gxh = tc_conv3x3_nhwc(gh, ctx.wp_adj if ctx.wp_adj is not None else _tc_pack(weight4.detach().flip([2, 3]).transpose(0, 1)))
+                gx, gs = to_nchw(gxh, s, x.dtype, other=xo)
             else:
-                gxh = tc_conv_transpose3x3_dgrad_planes(gh, ctx.wp_adj if ctx.wp_adj is not None else _tc_pack(weight4.detach().transpose(0, 1)))
-            gx, gs = to_nchw(gxh, s, x.dtype, other=x if ctx.needs_input_grad[1] else None)   # gx = s * g, gs = sum_p x * g
+                parts = tc_conv_transpose3x3_dgrad_planes(gh, ctx.wp_adj if ctx.wp_adj is not None else _tc_pack(weight4.detach().transpose(0, 1)))
+                gx, gs = parts_to_nchw(parts, s, x.dtype, other=xo)
             if gs is not None:
                 gs = gs.to(s.dtype)
         if ctx.needs_input_grad[3]:
