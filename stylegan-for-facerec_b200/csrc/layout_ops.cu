@@ -1,5 +1,5 @@
 // layout_ops.cu -- the two passes either side of a tensor-core convolution in the differentiable path
-// (stylegan2/functional.py): NCHW (fp32 / fp16 / bf16) <-> NHWC bf16 with the per-(sample, channel) factor of the
+// (stylegan2/tc_route.py): NCHW (fp32 / fp16 / bf16) <-> NHWC bf16 with the per-(sample, channel) factor of the
 // modulated convolution folded in, and -- for the backward direction -- the per-(sample, channel) reduction that the
 // adjoint of that factor needs, in the same pass:
 //     modulate  : xh[b,p,c] = bf16(x[b,c,p] * s[b,c])                     (ModulatedConv2d, model.py:236-237, factored)

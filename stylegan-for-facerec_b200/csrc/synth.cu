@@ -654,7 +654,7 @@ extern "C" int sg2_synth_forward(sg2_synth *S, void *workspace, const float *lat
 // ModulatedConv2d (model.py:232-273 of the reference) once modulation / demodulation are factored out, and -- with the
 // taps flipped and the channel roles swapped by the caller -- its input gradient.  NHWC bf16 in and out, fp32
 // accumulation, out[b,y,x,co] = scale[b,co] * sum_{a,b',ci} x[b, y+a-1, x+b'-1, ci] * wp[a*3+b'][co][ci].
-// Used by the differentiable path (stylegan2/functional.py, SharedConvFunction) when bf16 operands are allowed.
+// Used by the differentiable path (stylegan2/tc_route.py) when bf16 operands are allowed.
 extern "C" int sg2_conv3x3_tc_pack(void *wp, const float *weight, int cin, int cout, float scale, sg2_stream_t stream) {
     SG2_REQUIRE(wp && weight && cin >= 1 && cout >= 1, SG2_ERR_BAD_ARG, "conv3x3_tc_pack: bad argument");
     return launch_pack_conv_weight((__nv_bfloat16 *)wp, nullptr, weight, cin, cout, 9, scale, as_stream(stream));
