@@ -26,7 +26,8 @@ constexpr int LT_C = 64, LT_P = 32;
 // polyphase form of its input gradient reads, so no interleaving copy is needed on either side.
 __device__ __forceinline__ long long nhwc_offset(long long b, long long p, int C, long long HW, int poly_w, long long B) {
     if (poly_w == 0) return (b * HW + p) * C;
-    const int y = (int)(p / poly_w), x = (int)(p - (long long)y * poly_w);
+    const int pi = (int)p;                                        // W <= 32767: 32-bit division
+    const int y = pi / poly_w, x = pi - y * poly_w;
     const int P = (poly_w + 1) >> 1, s = (y & 1) * 2 + (x & 1);
     return ((((long long)s * B + b) * P + (y >> 1)) * P + (x >> 1)) * C;
 }
@@ -127,7 +128,8 @@ nhwc_to_nchw_kernel(T *__restrict__ out, const __nv_bfloat16 *__restrict__ h, co
                 } else {
                     // sum of n_parts tensors [B][pitch][pitch][C], of which the top-left W x W corner (W = poly_w) is read:
                     // the polyphase components of the transposed conv's input gradient, accumulated in fp32
-                    const int y = (int)(p / poly_w), x = (int)(p - (long long)y * poly_w);
+                    const int pi = (int)p;
+                    const int y = pi / poly_w, x = pi - y * poly_w;
                     const long long base = ((b * part_pitch + y) * part_pitch + x) * C + c;
                     const long long stride = (long long)gridDim.z * part_pitch * part_pitch * C;
                     for (int k = 0; k < n_parts; ++k) {
