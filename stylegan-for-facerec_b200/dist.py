@@ -51,3 +51,56 @@ def synthesize_sharded(generator, styles, total: Optional[int] = None, gather: b
     if gather:
         image = gather_images(image, total if total is not None else styles[0].shape[0])
     return image, aux
+
+
+# ---- the one exchange step of the fine-tuning path -------------------------------------
+# ReStyle trains the ENCODER only; the decoder is frozen and replicated, so the only collective of a training step is the
+# average of the encoder's gradients.  The reference gets it implicitly from nn.DataParallel's reduce-add onto GPU 0
+# (coach_restyle_psp.py:134-135); here every rank keeps a full replica and the gradients are averaged in place with
+# bucketed, asynchronous all-reduces (NCCL over NVLink / NVSwitch on a B200 box, gloo in the CPU tests).
+def broadcast_parameters(module: torch.nn.Module, src: int = 0) -> None:
+    """Make every rank start from rank `src`'s parameters and buffers."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return
+    for t in list(module.parameters()) + list(module.buffers()):
+        dist.broadcast(t.data, src)
+
+
+def average_gradients(params, bucket_bytes: int = 64 << 20) -> int:
+    """All-reduce (mean) the .grad of `params` across ranks, in place.  Gradients are packed into flat buckets of at most
+    `bucket_bytes` per (dtype, device) so that a 535 MB encoder costs a few dozen launches, every bucket's all-reduce is
+    issued asynchronously before the first one is waited for, and a parameter without a gradient on this rank contributes
+    zeros (the bucket layout must not depend on the rank).  Returns the number of buckets (collectives) issued."""
+    params = [p for p in params if p.requires_grad]
+    if not dist.is_initialized() or dist.get_world_size() == 1 or not params:
+        return 0
+    world = dist.get_world_size()
+    buckets, cur, cur_bytes, cur_key = [], [], 0, None
+    for p in params:
+        key = (p.dtype, p.device)
+        nbytes = p.numel() * p.element_size()
+        if cur and (key != cur_key or cur_bytes + nbytes > bucket_bytes):
+            buckets.append(cur)
+            cur, cur_bytes = [], 0
+        cur.append(p)
+        cur_bytes += nbytes
+        cur_key = key
+    if cur:
+        buckets.append(cur)
+    pending = []
+    for group in buckets:
+        flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in group])
+        pending.append((dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=True), flat, group))
+    for work, flat, group in pending:
+        work.wait()
+        flat.div_(world)
+        off = 0
+        for p in group:
+            n = p.numel()
+            g = flat[off:off + n].view_as(p)
+            if p.grad is None:
+                p.grad = g.clone()
+            else:
+                p.grad.copy_(g)
+            off += n
+    return len(buckets)

@@ -69,3 +69,65 @@ def test_shard_bounds_properties():
             assert max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         d.shard_bounds(4, 2, 2)
+
+
+def _grad_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    d = importlib.import_module("stylegan-for-facerec_b200.dist")
+    torch.manual_seed(100 + rank)                               # different initial weights per rank ...
+    enc = torch.nn.Sequential(torch.nn.Linear(6, 16), torch.nn.ReLU(), torch.nn.Linear(16, 4), torch.nn.Linear(4, 4))
+    d.broadcast_parameters(enc, src=0)                          # ... until they are broadcast
+    for p in enc[3].parameters():
+        p.requires_grad_(False)                                 # a frozen tail (the decoder's role): no gradient, skipped
+    torch.manual_seed(0)
+    x = torch.randn(8, 6)                                       # the global batch, same on every rank
+    y = torch.randn(8, 4)
+    mine, tgt = d.shard_batch(x), d.shard_batch(y)
+    loss = ((enc(mine) - tgt) ** 2).sum() / x.shape[0]          # per-rank share of the global mean loss
+    loss.backward()
+    if rank == 1:
+        enc[2].bias.grad = None                                 # a rank without a gradient for one parameter: counts as zeros
+    n_buckets = d.average_gradients(enc.parameters(), bucket_bytes=256)   # tiny buckets: several collectives
+    grads = [None if p.grad is None else (p.grad * world).clone() for p in enc.parameters()]   # mean * world == sum over ranks
+    w0 = [p.detach().clone() for p in enc.parameters()]
+    q.put((rank, n_buckets, grads, w0))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gradient_average_gloo():
+    """the one collective of the fine-tuning path: bucketed all-reduce (mean) of the trainable gradients"""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=120) for _ in procs), key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, nb0, g0, w0), (_, nb1, g1, w1) = res
+    assert nb0 == nb1 and nb0 >= 2                              # same bucket layout on both ranks, more than one bucket
+    assert all(torch.equal(a, b) for a, b in zip(w0, w1))       # broadcast made the replicas identical
+    assert all((a is None) == (b is None) and (a is None or torch.equal(a, b)) for a, b in zip(g0, g1))
+    assert g0[-1] is None and g0[-2] is None                    # frozen parameters are left alone
+    # single-process reference: the whole batch through the same weights
+    enc = torch.nn.Sequential(torch.nn.Linear(6, 16), torch.nn.ReLU(), torch.nn.Linear(16, 4), torch.nn.Linear(4, 4))
+    with torch.no_grad():
+        for p, w in zip(enc.parameters(), w0):
+            p.copy_(w)
+    torch.manual_seed(0)
+    x, y = torch.randn(8, 6), torch.randn(8, 4)
+    (((enc(x) - y) ** 2).sum() / 8).backward()
+    ref = [p.grad for p in enc.parameters()]
+    # rank 1 dropped its share of enc[2].bias (index 3): the averaged value there is rank 0's share alone
+    for i, (a, r) in enumerate(zip(g0[:4], ref[:4])):
+        if i == 3:
+            lo, hi = 0, 4
+            enc.zero_grad()
+            (((enc(x[lo:hi]) - y[lo:hi]) ** 2).sum() / 8).backward()
+            r = list(enc.parameters())[3].grad
+        assert torch.allclose(a, r, rtol=1e-5, atol=1e-6), i
