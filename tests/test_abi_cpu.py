@@ -102,3 +102,43 @@ def test_reference_init_statistics(sg2):
     assert float(G.to_rgb1.bias.abs().sum()) == 0
     assert float(G.conv1.conv.modulation.bias.mean()) == 1
     assert 80 < float(G.style[1].weight.std()) < 120                                             # randn / 0.01
+
+
+def test_binding_arity_and_types_match_the_header(sg2):
+    """every ctypes signature has as many arguments as the C prototype, pointers where the header has pointers,
+    64-bit integers where it has int64_t and floats where it has float (a mismatch corrupts the call silently)"""
+    txt = open(os.path.join(ROOT, "include", "sg2_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    protos = dict(re.findall(r"\b(sg2_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", txt, flags=re.S))
+    assert set(protos) == set(sg2._lib.SIGNATURES)
+    for name, (restype, argtypes) in sg2._lib.SIGNATURES.items():
+        params = [p.strip() for p in protos[name].replace("\n", " ").split(",")]
+        if params == ["void"] or params == [""]:
+            params = []
+        assert len(params) == len(argtypes), (name, len(params), len(argtypes))
+        for p, t in zip(params, argtypes):
+            is_ptr_c = "*" in p or "sg2_stream_t" in p
+            is_ptr_py = t is ctypes.c_void_p or t is ctypes.c_char_p or hasattr(t, "_type_") and hasattr(t, "contents")
+            assert is_ptr_c == bool(is_ptr_py), (name, p, t)
+            if not is_ptr_c:
+                if "int64_t" in p or "long long" in p:
+                    assert t is ctypes.c_int64, (name, p, t)
+                elif "float" in p:
+                    assert t is ctypes.c_float, (name, p, t)
+                elif "uint32_t" in p or "unsigned" in p:
+                    assert t in (ctypes.c_uint, ctypes.c_uint32), (name, p, t)
+                else:
+                    assert t is ctypes.c_int, (name, p, t)
+    rets = dict((n, r.strip()) for r, n in re.findall(r"^\s*((?:const\s+)?[A-Za-z_][A-Za-z0-9_]*(?:\s*\*)?)\s*(sg2_[a-z0-9_]+)\s*\(", txt, flags=re.M))
+    for name, (restype, _) in sg2._lib.SIGNATURES.items():
+        r = rets[name]
+        if "char" in r:
+            assert restype is ctypes.c_char_p, (name, r)
+        elif r == "void":
+            assert restype is None, (name, r)
+        elif "int64_t" in r:
+            assert restype is ctypes.c_int64, (name, r)
+        elif r == "int":
+            assert restype is ctypes.c_int, (name, r)
+        else:
+            raise AssertionError((name, r))
