@@ -137,3 +137,35 @@ def test_c_oracle_modconv(c_oracle, oracle, golden, cases):
         if up:
             y = oracle.upfirdn2d(y, oracle.fir_kernel_2d([1, 3, 3, 1]) * 4, pad=oracle.upconv_blur_pad())
         np.testing.assert_allclose(y.numpy(), golden["layers"][name + "/y"], rtol=0, atol=2e-5, err_msg=name)
+
+
+def test_oracle_autograd_matches_reference_gradients():
+    """whole-decoder gradients: fp64 autograd through the oracle restatements == fp64 autograd through the unmodified
+    reference modules (tests/golden/grads.npz, make_golden_grads.py) -- the `-m gpu` gradient tests compare the CUDA
+    path with the oracle's autograd, this pins that autograd to the reference"""
+    import make_golden_grads as MG
+    from oracle import sg2_ada_oracle as A
+    from oracle import sg2_oracle as O
+    g = np.load(os.path.join(GOLDEN, "grads.npz"))
+    for name, size, n_mlp, batch in MG.ROS_CASES:
+        sd = {k: v.double() for k, v in O.init_state_dict(size, 512, n_mlp, 2, seed=0).items()}
+        lat, noise, gy = MG.ros_inputs(name, size, batch)
+        ld = lat.double().requires_grad_(True)
+        nd = [n.double().requires_grad_(True) for n in noise]
+        img, _ = O.generator_forward(sd, size, [ld], n_mlp=n_mlp, input_is_latent=True, noise=nd)
+        grads = torch.autograd.grad(img, [ld] + nd, gy.double())
+        ref_img = torch.from_numpy(g[name + "/image"])
+        assert (img.detach() - ref_img).abs().max() <= 1e-10 * ref_img.abs().max(), name
+        refs = [g[name + "/g_latent"]] + [g[f"{name}/g_noise{i}"] for i in range(len(nd))]
+        for i, (a, r) in enumerate(zip(grads, refs)):
+            r = torch.from_numpy(r)
+            assert a.shape == r.shape and (a - r).abs().max() <= 1e-9 * max(1.0, r.abs().max().item()), (name, i)
+    for name, res, nl, batch in MG.ADA_CASES:
+        sd = {k: v.double() for k, v in A.init_state_dict(res, 512, 512, nl, seed=0).items()}
+        ws, gy = MG.ada_inputs(name, res, batch)
+        wd = ws.double().requires_grad_(True)
+        img = A.synthesis_network(sd, res, wd, "const")
+        (ga,) = torch.autograd.grad(img, [wd], gy.double())
+        ref_img, r = torch.from_numpy(g[name + "/image"]), torch.from_numpy(g[name + "/g_ws"])
+        assert (img.detach() - ref_img).abs().max() <= 1e-10 * ref_img.abs().max(), name
+        assert ga.shape == r.shape and (ga - r).abs().max() <= 1e-9 * max(1.0, r.abs().max().item()), name
