@@ -69,3 +69,32 @@ def test_generators_expose_the_precision_switch(sg2, monkeypatch):
     assert A.synthesis.precision == "bf16" and "precision" not in A.state_dict()
     monkeypatch.setenv("SG2_B200_PRECISION", "bf16")
     assert sg2.Generator(8, 32, 1).precision == "bf16" and sg2.stylegan2_ada.Generator(32, 32, 1, 8, 3).precision == "bf16"
+
+
+def test_frozen_pack_cache_keys_on_the_parameter_version(sg2, monkeypatch):
+    """ModulatedConv2d._tc_weights: cached while the weight is frozen and unchanged, rebuilt after an in-place update,
+    bypassed (and differentiable) while the weight trains.  The pack kernel is replaced by a CPU stand-in."""
+    T = importlib.import_module("stylegan-for-facerec_b200.stylegan2.tc_route")
+    calls = []
+    monkeypatch.setattr(T, "_tc_pack", lambda w: (calls.append(tuple(w.shape)), w.detach().clone())[1])
+    conv = sg2.ModulatedConv2d(32, 64, 3, 16)
+    conv.weight.requires_grad_(False)
+    w4, wp, wp_adj, wsq = conv._tc_weights()
+    assert len(calls) == 2 and w4.shape == (64, 32, 3, 3) and wp_adj.shape == (32, 64, 3, 3) and wsq.shape == (64, 32)
+    assert torch.allclose(w4, conv.weight[0] * conv.scale) and torch.allclose(wsq, w4.pow(2).sum([2, 3]))
+    assert torch.equal(wp_adj, w4.flip([2, 3]).transpose(0, 1))          # adjoint of the 'same' conv: taps flipped, roles swapped
+    again = conv._tc_weights()
+    assert len(calls) == 2 and all(a is b for a, b in zip(again, (w4, wp, wp_adj, wsq)))      # served from the cache
+    with torch.no_grad():
+        conv.weight.mul_(2.0)                                            # in-place update bumps the version counter
+    w4b, _, _, wsqb = conv._tc_weights()
+    assert len(calls) == 4 and torch.allclose(w4b, 2 * w4) and torch.allclose(wsqb, 4 * wsq)
+    conv.weight.requires_grad_(True)                                     # training the decoder: no cache, gradients flow
+    w4c, wpc, wpac, wsqc = conv._tc_weights()
+    assert len(calls) == 4 and wpc is None and wpac is None and w4c.requires_grad and wsqc.requires_grad
+    with torch.no_grad():                                                # ... unless autograd is off altogether
+        assert conv._tc_weights()[1] is not None
+    up = sg2.ModulatedConv2d(32, 64, 3, 16, upsample=True)
+    up.weight.requires_grad_(False)
+    w4u, _, wp_adj_u, _ = up._tc_weights()
+    assert torch.equal(wp_adj_u, w4u.transpose(0, 1))                    # adjoint of the transposed conv: same taps
