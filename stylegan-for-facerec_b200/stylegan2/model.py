@@ -460,72 +460,12 @@ class Generator(nn.Module):
 
 
 # ------------------------------------------------------------------------------------------------
-# discriminator-side consumers of the op API (model.py:545-673).  Never instantiated by the
-# reference repo itself; kept so third-party rosinality training code imports unchanged.
+# discriminator-side consumers of the op API (model.py:545-673 of the reference): discriminator.py,
+# instantiated over the building blocks above and re-exported here under the reference's names.
 # ------------------------------------------------------------------------------------------------
-class ConvLayer(nn.Sequential):
-    def __init__(self, in_channel, out_channel, kernel_size, downsample=False, blur_kernel=[1, 3, 3, 1],
-                 bias=True, activate=True):
-        layers = []
-        if downsample:
-            factor = 2
-            p = (len(blur_kernel) - factor) + (kernel_size - 1)
-            layers.append(Blur(blur_kernel, pad=((p + 1) // 2, p // 2)))
-            stride = 2
-            self.padding = 0
-        else:
-            stride = 1
-            self.padding = kernel_size // 2
-        layers.append(EqualConv2d(in_channel, out_channel, kernel_size, padding=self.padding, stride=stride,
-                                  bias=bias and not activate))
-        if activate:
-            layers.append(FusedLeakyReLU(out_channel) if bias else ScaledLeakyReLU(0.2))
-        super().__init__(*layers)
+from .discriminator import _make_classes, feature_channels, minibatch_stddev  # noqa: E402,F401
 
-
-class ResBlock(nn.Module):
-    def __init__(self, in_channel, out_channel, blur_kernel=[1, 3, 3, 1]):
-        super().__init__()
-        self.conv1 = ConvLayer(in_channel, in_channel, 3)
-        self.conv2 = ConvLayer(in_channel, out_channel, 3, downsample=True)
-        self.skip = ConvLayer(in_channel, out_channel, 1, downsample=True, activate=False, bias=False)
-
-    def forward(self, input):
-        out = self.conv2(self.conv1(input))
-        return (out + self.skip(input)) / math.sqrt(2)
-
-
-class Discriminator(nn.Module):
-    def __init__(self, size, channel_multiplier=2, blur_kernel=[1, 3, 3, 1]):
-        super().__init__()
-        channels = {4: 512, 8: 512, 16: 512, 32: 512, 64: 256 * channel_multiplier,
-                    128: 128 * channel_multiplier, 256: 64 * channel_multiplier,
-                    512: 32 * channel_multiplier, 1024: 16 * channel_multiplier}
-        convs = [ConvLayer(3, channels[size], 1)]
-        log_size = int(math.log(size, 2))
-        in_channel = channels[size]
-        for i in range(log_size, 2, -1):
-            out_channel = channels[2 ** (i - 1)]
-            convs.append(ResBlock(in_channel, out_channel, blur_kernel))
-            in_channel = out_channel
-        self.convs = nn.Sequential(*convs)
-        self.stddev_group = 4
-        self.stddev_feat = 1
-        self.final_conv = ConvLayer(in_channel + 1, channels[4], 3)
-        self.final_linear = nn.Sequential(
-            EqualLinear(channels[4] * 4 * 4, channels[4], activation='fused_lrelu'),
-            EqualLinear(channels[4], 1),
-        )
-
-    def forward(self, input):
-        out = self.convs(input)
-        batch, channel, height, width = out.shape
-        group = min(batch, self.stddev_group)
-        stddev = out.view(group, -1, self.stddev_feat, channel // self.stddev_feat, height, width)
-        stddev = torch.sqrt(stddev.var(0, unbiased=False) + 1e-8)
-        stddev = stddev.mean([2, 3, 4], keepdims=True).squeeze(2)
-        stddev = stddev.repeat(group, 1, height, width)
-        out = torch.cat([out, stddev], 1)
-        out = self.final_conv(out)
-        out = out.view(batch, -1)
-        return self.final_linear(out)
+ConvLayer, ResBlock, Discriminator = _make_classes(Blur, EqualConv2d, EqualLinear, FusedLeakyReLU, ScaledLeakyReLU)
+for _cls in (ConvLayer, ResBlock, Discriminator):      # picklable / printable under the module users import them from
+    _cls.__module__ = __name__
+    _cls.__qualname__ = _cls.__name__

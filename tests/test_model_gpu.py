@@ -201,6 +201,26 @@ def test_generator_gradients_vs_oracle(sg2, oracle):
         assert (a.cpu().double() - b).abs().max() < 1e-3 * scale
 
 
+def test_discriminator_matches_reference_golden(sg2):
+    """the Discriminator mirror on the kernels vs golden vectors of the unmodified reference class
+    (tests/golden/make_golden_disc.py); the differentiable route, library convolutions in true fp32"""
+    import os
+    import numpy as np
+    import make_golden_disc as MD
+    from conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "disc.npz"))
+    for name, size, cm, batch in MD.CASES:
+        D = sg2.Discriminator(size, channel_multiplier=cm).eval()
+        D.load_state_dict(MD.seeded_state_dict(D, name), strict=True)
+        D = D.to(DEV)
+        x = MD.images(name, batch, size).to(DEV).requires_grad_(True)
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            y = D(x)
+        ref = torch.from_numpy(g[name + "/out"])
+        err = (y.detach().cpu() - ref).abs().max().item()
+        assert y.shape == ref.shape and err <= 1e-3 * max(1.0, ref.abs().max().item()), (name, err)
+
+
 def test_discriminator_runs_on_the_op_api(sg2):
     D = sg2.Discriminator(32).to(DEV)
     x = torch.randn(4, 3, 32, 32, device=DEV, requires_grad=True)
