@@ -62,26 +62,29 @@ class Generator(torch.nn.Module):                            # generator.py:6-52
 
 
 class SynthesisNetwork(torch.nn.Module):                     # generator.py:55-88
+    """The decoder proper: a 4x4 prologue (learned constant -> conv1 -> ToRGB) and one block per octave (conv0 with the
+    2x SmoothUpsample, conv1, ToRGB added to the up-sampled running image).  ws [B, num_ws, w_dim] is cut into windows of
+    3 rows that overlap by one (the ToRGB row of an octave is also the conv0 row of the next), as in the reference.
+
+    Per call this issues 3 kernels per layer without autograd (modulation + demodulation table, shared-weight conv, fused
+    epilogue) and the differentiable composition of utils.py / tc_route.py with it; `precision` selects the fp32 SIMT
+    convolutions ('auto' / 'exact') or the tcgen05 kernel with bf16 operands ('bf16', or SG2_B200_PRECISION=bf16) --
+    every 3x3 convolution of this decoder is stride 1, so all of them qualify."""
 
     def __init__(self, w_dim, img_resolution, img_channels, channel_base=16384, channel_max=512, synthesis_layer='stylegan2'):
         super().__init__()
-        self.w_dim = w_dim
-        self.img_resolution = img_resolution
-        self.img_resolution_log2 = int(np.log2(img_resolution))
-        self.img_channels = img_channels
-        self.block_resolutions = [2 ** i for i in range(2, self.img_resolution_log2 + 1)]
-        self.num_ws = 2 * (len(self.block_resolutions) + 1)
-        channels_dict = {res: min(channel_base // res, channel_max) for res in self.block_resolutions}
-        # 'auto' / 'exact': fp32-accumulate SIMT convolutions; 'bf16' (or SG2_B200_PRECISION=bf16): the 3x3 convolutions
-        # -- all stride 1 in this decoder -- run on the tcgen05 kernel with bf16 operands, with and without autograd
+        log2 = int(np.log2(img_resolution))
+        octaves = [4 << i for i in range(log2 - 1)]                      # 4, 8, ..., img_resolution
+        width = {r: min(channel_base // r, channel_max) for r in octaves}
+        self.w_dim, self.img_channels = w_dim, img_channels
+        self.img_resolution, self.img_resolution_log2 = img_resolution, log2
+        self.block_resolutions = octaves
+        self.num_ws = 2 * len(octaves) + 2
         self.precision = os.environ.get('SG2_B200_PRECISION', 'auto')
-        self.blocks = torch.nn.ModuleList()
-        self.first_block = SynthesisPrologue(channels_dict[self.block_resolutions[0]], w_dim=w_dim,
-                                             resolution=self.block_resolutions[0], img_channels=img_channels,
-                                             synthesis_layer=synthesis_layer)
-        for res in self.block_resolutions[1:]:
-            self.blocks.append(SynthesisBlock(channels_dict[res // 2], channels_dict[res], w_dim=w_dim, resolution=res,
-                                              img_channels=img_channels, synthesis_layer=synthesis_layer))
+        common = dict(w_dim=w_dim, img_channels=img_channels, synthesis_layer=synthesis_layer)
+        self.blocks = torch.nn.ModuleList()                                # registered before first_block, like the reference
+        self.first_block = SynthesisPrologue(width[4], resolution=4, **common)
+        self.blocks.extend(SynthesisBlock(width[r // 2], width[r], resolution=r, **common) for r in octaves[1:])
 
     def forward(self, ws, noise_mode='random', return_latents=False, **kwargs):
         split_ws = [ws[:, 0:2, :]] + [ws[:, 2 * n + 1: 2 * n + 4, :] for n in range(len(self.block_resolutions))]
@@ -102,13 +105,12 @@ def _layer_classes(synthesis_layer):
 
 
 class SynthesisPrologue(torch.nn.Module):                    # generator.py:91-111
+    """learned constant [C, 4, 4] -> conv1 (rows 0 of ws) -> ToRGB (row 1): the first feature map and the first image"""
 
     def __init__(self, out_channels, w_dim, resolution, img_channels, synthesis_layer):
         super().__init__()
         SynthesisLayer, ToRGBLayer = _layer_classes(synthesis_layer)
-        self.w_dim = w_dim
-        self.resolution = resolution
-        self.img_channels = img_channels
+        self.w_dim, self.resolution, self.img_channels = w_dim, resolution, img_channels
         self.const = torch.nn.Parameter(torch.randn([out_channels, resolution, resolution]))
         self.conv1 = SynthesisLayer(out_channels, out_channels, w_dim=w_dim, resolution=resolution)
         self.torgb = ToRGBLayer(out_channels, img_channels, w_dim=w_dim)
@@ -122,16 +124,14 @@ class SynthesisPrologue(torch.nn.Module):                    # generator.py:91-1
 
 
 class SynthesisBlock(torch.nn.Module):                       # generator.py:114-139
+    """one octave: conv0 (3x3 at the input resolution, then SmoothUpsample x2 fused with its epilogue), conv1, ToRGB; the
+    running image is up-sampled by the same filter and the new ToRGB output added in the same pass"""
 
     def __init__(self, in_channels, out_channels, w_dim, resolution, img_channels, synthesis_layer):
         super().__init__()
         SynthesisLayer, ToRGBLayer = _layer_classes(synthesis_layer)
-        self.in_channels = in_channels
-        self.w_dim = w_dim
-        self.resolution = resolution
-        self.img_channels = img_channels
-        self.num_conv = 0
-        self.num_torgb = 0
+        self.in_channels, self.w_dim, self.resolution, self.img_channels = in_channels, w_dim, resolution, img_channels
+        self.num_conv = self.num_torgb = 0                                  # attributes of the reference class, unused here too
         self.resampler = SmoothUpsample()
         self.conv0 = SynthesisLayer(in_channels, out_channels, w_dim=w_dim, resolution=resolution, resampler=self.resampler)
         self.conv1 = SynthesisLayer(out_channels, out_channels, w_dim=w_dim, resolution=resolution)
