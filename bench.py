@@ -34,6 +34,12 @@ sys.path.insert(0, ROOT)
 SIZE_DEFAULT, BATCH_DEFAULT, N_MLP, STYLE_DIM = 256, 64, 8, 512
 
 
+def workload_name(size, batch):
+    """the one workload both arms report (BASELINE.json configs[1] at the defaults)"""
+    return (f"StyleGAN2 config-f {size}x{size} synthesis forward (mapping + synthesis), random-init weights, "
+            f"batch {batch} per GPU")
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -138,8 +144,9 @@ def run_reference(args):
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(1e3 * ts[len(ts) // 2], 2), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"StyleGAN2 config-f {args.size}x{args.size} generator forward, random-init weights, "
-                                   f"CPU (reference model.py math on torch-CPU ops)", "batch_per_step": sample_b},
+            "config": {"workload": workload_name(args.size, args.batch),
+                       "arm": "the reference's model.py math on torch-CPU ops (oracle port), all host threads",
+                       "batch_per_gpu": args.batch, "batch_per_step": sample_b, "precision": "fp32"},
             "cpu_baseline": {"value": round(ips, 4), "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
                              "sample": f"each step = one forward of batch {sample_b} (bounded sample of the batch-{args.batch} "
                                        f"GPU step), fp32, randomize_noise=False"},
@@ -327,8 +334,7 @@ def main():
         "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": round(1e3 * t_dev / K, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-        "config": {"workload": f"StyleGAN2 config-f {args.size}x{args.size} synthesis forward (mapping + synthesis), "
-                               f"random-init weights, batch {B} per GPU, {args.precision}",
+        "config": {"workload": workload_name(args.size, B),
                    "batch_per_gpu": B, "global_batch": B * world, "precision": args.precision,
                    "l2": f"no explicit flush: each step streams >= {act_gb:.1f} GB of activations (>> 126 MB L2)" if act_gb else
                          "no explicit flush: per-step activation traffic >> 126 MB L2",
