@@ -1,5 +1,12 @@
 // common.cuh -- shared helpers for libsg2_b200 (sm_100a only).
 #pragma once
+// Knock-out branches for bottleneck analysis (SG2_GEMM_DBG / SG2_FIR_DBG: loads, MMAs, math or stores removed one at a
+// time; results are WRONG when set) exist only in a variant build: `python build.py --tag ko -DSG2_KNOCKOUT=1`
+// (tools/knockout.sh).  The shipped library compiles them out.
+#ifndef SG2_KNOCKOUT
+#define SG2_KNOCKOUT 0
+#endif
+#define SG2_DBG(p) (SG2_KNOCKOUT ? (p).dbg : 0)
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>

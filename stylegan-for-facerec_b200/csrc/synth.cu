@@ -434,7 +434,13 @@ extern "C" int sg2_synth_create(sg2_synth **plan, int size, int style_dim, int m
         } else {
             // algorithmic FLOPs per image in the reference's formulation
             const double fl = 2.0 * 9 * L.p.cin * L.p.cout * (L.p.upsample ? px_in : px_out);
-            add("gemm", name, fl, 2.0 * (px_in * L.p.cin + px_out * L.p.cout), L.gp.total_tiles, L.block_n);
+            // algorithmic bytes: the input read once + what the kernel writes: the (2r+1)^2 intermediate of an up-sampling
+            // layer, the output plane of a plain one -- except the LAST conv, which stores no activation at all, only
+            // the three fp32 ToRGB planes
+            const bool last = i + 2 >= S->layers.size();
+            const double out_b = L.p.upsample ? 2.0 * (2 * L.res_in + 1.0) * (2 * L.res_in + 1.0) * L.p.cout
+                                              : (last ? 4.0 * 3 * px_out : 2.0 * px_out * L.p.cout);
+            add("gemm", name, fl, 2.0 * px_in * L.p.cin + out_b, L.gp.total_tiles, L.block_n);
             if (L.p.upsample) add("upfir", name, 0, 2.0 * ((2 * L.res_in + 1.0) * (2 * L.res_in + 1.0) + px_out) * L.p.cout, 0, 0);
         }
     }

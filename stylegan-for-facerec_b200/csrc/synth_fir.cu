@@ -202,7 +202,7 @@ upfir_tc_kernel(const __grid_constant__ UpfirTcParams p, const __grid_constant__
                 const FirTile t = w.tile(p);
                 const int a0 = t.y0 / 2 - 1, b0 = t.x0 / 2 - 1;     // first window cell of the tile
                 mbar_wait(&sm.empty[stage], phase ^ 1);
-                if (p.dbg & 1) {
+                if (SG2_DBG(p) & 1) {
                     if (elect_one()) mbar_arrive(&sm.full[stage]);
                 } else if (elect_one()) {
                     mbar_arrive_expect_tx(&sm.full[stage], (uint32_t)(ncb * 4 * FT_RA * FT_RB) * row_bytes);
@@ -240,7 +240,7 @@ upfir_tc_kernel(const __grid_constant__ UpfirTcParams p, const __grid_constant__
                 const uint64_t bdesc0 = make_smem_desc_mn(smem_u32(sm.b) + stage * FT_STAGE_BYTES, cb_bytes, row_bytes);
                 if (elect_one()) {
 #pragma unroll
-                    for (int kk = 0; kk < ((p.dbg & 8) ? 1 : FT_K / 16); ++kk) {
+                    for (int kk = 0; kk < ((SG2_DBG(p) & 8) ? 1 : FT_K / 16); ++kk) {
 #if SG2_FIR_A_TMEM
                         (void)adesc0;       // 16 taps = 8 TMEM columns per K step
                         umma_bf16_ts(d_tmem, tmem_base + 256u + 8u * kk, bdesc0 + (uint64_t)(kk * kstep), idesc, kk != 0);
@@ -331,7 +331,7 @@ upfir_tc_kernel(const __grid_constant__ UpfirTcParams p, const __grid_constant__
             uint32_t packed[FT_CPW][16];
 #pragma unroll
             for (int ci = 0; ci < FT_CPW; ++ci) {
-                if (p.dbg & 4) break;
+                if (SG2_DBG(p) & 4) break;
                 const int cc = 32 * (kq * FT_CPW + ci);          // first accumulator column of the chunk
                 const float2 nz2 = make_float2(nq0[ci] * nw, nq0[ci] * nw);
                 uint32_t r[32];
@@ -359,7 +359,7 @@ upfir_tc_kernel(const __grid_constant__ UpfirTcParams p, const __grid_constant__
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm.tmem_empty[acc]);     // accumulator drained: the MMA warp may reuse it
             // the previous tile's TMA stores must have finished reading the staging buffer
-            if (p.dbg & 2) {
+            if (SG2_DBG(p) & 2) {
             } else if (p.store_mode == 0) {
                 if (et == 0) tma_store_wait_read();
                 asm volatile("bar.sync 2, %0;" ::"n"(FT_EPI_THREADS) : "memory");
@@ -369,7 +369,7 @@ upfir_tc_kernel(const __grid_constant__ UpfirTcParams p, const __grid_constant__
             }
 #pragma unroll
             for (int ci = 0; ci < FT_CPW; ++ci) {
-                if (p.dbg & 4) break;
+                if (SG2_DBG(p) & 4) break;
                 const int k = kq * FT_CPW + ci;                  // 32-column chunk of the tile
                 // stage this pixel's 64 bytes in the TMA layout of the store box
                 if (cbw == 64) {      // [128 px][128 B] per column block, SWIZZLE_128B: 16-byte chunk index XOR (row & 7)
@@ -389,8 +389,8 @@ upfir_tc_kernel(const __grid_constant__ UpfirTcParams p, const __grid_constant__
             if (et < FT_N) sm.e_tab[(it + 1) & 1u][et] = pq1;     // the next tile's table (read after this tile's last barrier)
             fence_proxy_async();
             // rows / columns / samples beyond the tensor are clipped by the TMA unit
-            if ((p.dbg & 2) || p.store_mode != 0) asm volatile("bar.sync 1, %0;" ::"n"(FT_EPI_THREADS) : "memory");   // table hand-over
-            if (p.dbg & 2) {
+            if ((SG2_DBG(p) & 2) || p.store_mode != 0) asm volatile("bar.sync 1, %0;" ::"n"(FT_EPI_THREADS) : "memory");   // table hand-over
+            if (SG2_DBG(p) & 2) {
             } else if (p.store_mode == 0) {       // one thread stores whole column blocks (box cbw x 8 x 16); its barrier hands over the table
                 asm volatile("bar.sync 3, %0;" ::"n"(FT_EPI_THREADS) : "memory");
                 if (et == 0) {

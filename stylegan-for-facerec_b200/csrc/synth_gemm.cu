@@ -261,9 +261,9 @@ modconv_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant_
                             mbar_wait(&sm.empty[stage], phase ^ 1);
                             uint8_t *slot = sm.ring + stage * stage_bytes;
                             const int ax = t.x0 + g.dx[tap], ay = t.y0 + g.dy[tap], wt = g.wtap[tap];
-                            if (p.dbg & 6) {       // bottleneck analysis only
+                            if (SG2_DBG(p) & 6) {       // bottleneck analysis only
                                 if (elect_one()) {
-                                    const bool la = !(p.dbg & 2), lb = !(p.dbg & 4);
+                                    const bool la = !(SG2_DBG(p) & 2), lb = !(SG2_DBG(p) & 4);
                                     if (!la && !lb) mbar_arrive(&sm.full[stage]);
                                     else mbar_arrive_expect_tx(&sm.full[stage], kpk * ((la ? a_bytes : 0u) + (lb ? b_bytes : 0u)));
                                     for (uint32_t u = 0; u < kpk; ++u) {
@@ -378,7 +378,7 @@ modconv_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant_
                         if (elect_one()) {
                             // advance 32 bytes (>>4 = 2) inside the swizzle row per K = 16 step
                             umma_bf16(d_tmem, adesc, bdesc, idesc, k0 != 0);
-                            if (!(p.dbg & 8)) {
+                            if (!(SG2_DBG(p) & 8)) {
                             umma_bf16(d_tmem, adesc + 2, bdesc + 2, idesc, 1);
                             if (bk == 64) {
                                 umma_bf16(d_tmem, adesc + 4, bdesc + 4, idesc, 1);
@@ -484,7 +484,7 @@ modconv_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant_
                 }
                 const float nz = nz_cur * nw;
                 uint32_t off16 = 0xffffffffu;
-                if (valid && p.out && !(p.dbg & 1))
+                if (valid && p.out && !(SG2_DBG(p) & 1))
                     off16 = (uint32_t)((g.out_off + (((long long)b * g.out_H + y) * g.out_W + x) * p.Cout + n0) >> 3);
 
                 mbar_wait(&sm.tmem_full[acc], acc_phase);

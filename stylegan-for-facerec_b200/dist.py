@@ -45,11 +45,17 @@ def gather_images(local: torch.Tensor, total: int) -> torch.Tensor:
 
 
 def synthesize_sharded(generator, styles, total: Optional[int] = None, gather: bool = False, **kwargs):
-    """Run `generator(styles, **kwargs)` on this rank's shard of every style tensor."""
+    """Run `generator(styles, **kwargs)` on this rank's shard of every style tensor.  Per-sample `noise` maps
+    ([B_global, 1, r, r]) are sharded with the latents; maps broadcast over the batch ([1, 1, r, r]) pass through."""
     local = [shard_batch(s) for s in styles]
+    n_global = styles[0].shape[0]
+    noise = kwargs.get("noise")
+    if noise is not None:
+        kwargs = dict(kwargs)
+        kwargs["noise"] = [n if (n is None or n.shape[0] != n_global or n_global == 1) else shard_batch(n) for n in noise]
     image, aux = generator(local, **kwargs)
     if gather:
-        image = gather_images(image, total if total is not None else styles[0].shape[0])
+        image = gather_images(image, total if total is not None else n_global)
     return image, aux
 
 
@@ -59,22 +65,21 @@ def synthesize_sharded(generator, styles, total: Optional[int] = None, gather: b
 # (coach_restyle_psp.py:134-135); here every rank keeps a full replica and the gradients are averaged in place with
 # bucketed, asynchronous all-reduces (NCCL over NVLink / NVSwitch on a B200 box, gloo in the CPU tests).
 def broadcast_parameters(module: torch.nn.Module, src: int = 0) -> None:
-    """Make every rank start from rank `src`'s parameters and buffers."""
-    if not dist.is_initialized() or dist.get_world_size() == 1:
-        return
-    for t in list(module.parameters()) + list(module.buffers()):
-        dist.broadcast(t.data, src)
+    """Make every rank start from rank `src`'s parameters and buffers.  The broadcast writes through `t.detach()`, which
+    shares the tensor's version counter (a write through `.data` does not bump it), and then drops every packed-weight
+    cache below `module` (`invalidate_caches()`), so the bf16 engine re-packs from the new values."""
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        with torch.no_grad():
+            for t in list(module.parameters()) + list(module.buffers()):
+                dist.broadcast(t.detach(), src)
+    for m in module.modules():
+        inv = getattr(m, "invalidate_caches", None)
+        if callable(inv):
+            inv()
 
 
-def average_gradients(params, bucket_bytes: int = 64 << 20) -> int:
-    """All-reduce (mean) the .grad of `params` across ranks, in place.  Gradients are packed into flat buckets of at most
-    `bucket_bytes` per (dtype, device) so that a 535 MB encoder costs a few dozen launches, every bucket's all-reduce is
-    issued asynchronously before the first one is waited for, and a parameter without a gradient on this rank contributes
-    zeros (the bucket layout must not depend on the rank).  Returns the number of buckets (collectives) issued."""
-    params = [p for p in params if p.requires_grad]
-    if not dist.is_initialized() or dist.get_world_size() == 1 or not params:
-        return 0
-    world = dist.get_world_size()
+def _bucket_layout(params, bucket_bytes):
+    """consecutive parameters of one (dtype, device) packed into buckets of at most bucket_bytes"""
     buckets, cur, cur_bytes, cur_key = [], [], 0, None
     for p in params:
         key = (p.dtype, p.device)
@@ -87,20 +92,139 @@ def average_gradients(params, bucket_bytes: int = 64 << 20) -> int:
         cur_key = key
     if cur:
         buckets.append(cur)
+    return buckets
+
+
+class GradientAverager:
+    """Bucketed gradient all-reduce (mean) that overlaps with the backward pass which produces the gradients.
+
+    * The gradients LIVE in flat buckets: every `p.grad` is a view into its bucket (no concatenation, no copy back), the
+      buckets are laid out in REVERSE parameter order, i.e. roughly the order in which autograd finishes them.
+    * `arm()` before the last backward of a step (ReStyle accumulates `n_iters_per_batch` = 5 backward passes into the
+      same gradients, coach_restyle_psp.py:138-168; only the last one may trigger the exchange): a post-accumulate hook
+      per parameter counts its bucket down and issues the bucket's asynchronous all-reduce the moment it is complete,
+      while autograd is still working on the earlier layers -- over NCCL the collective runs on its own stream.
+    * `finish()` issues whatever was not triggered (parameters that received no gradient in the armed pass), waits, and
+      turns sums into means.  Parameters that received a gradient on NO rank during the step get `grad = None` back, so
+      an optimizer with weight decay or momentum skips them exactly like the single-process run would.
+    """
+
+    def __init__(self, params, bucket_bytes: int = 64 << 20):
+        self.params = [p for p in params if p.requires_grad]
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.buckets = []
+        self._index = {}
+        for group in _bucket_layout(list(reversed(self.params)), bucket_bytes):
+            flat = torch.zeros(sum(p.numel() for p in group), dtype=group[0].dtype, device=group[0].device)
+            views, off = [], 0
+            for p in group:
+                views.append(flat[off:off + p.numel()].view_as(p))
+                off += p.numel()
+            b = {"flat": flat, "params": group, "views": views, "pending": 0, "work": None}
+            for k, p in enumerate(group):
+                self._index[id(p)] = (len(self.buckets), k)
+            self.buckets.append(b)
+        self._pos = {id(p): i for i, p in enumerate(self.params)}
+        self._touched = torch.zeros(len(self.params), dtype=torch.float32)
+        self._armed = False
+        self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
+        self.attach()
+
+    def attach(self):
+        """(re)point every p.grad at its bucket view; the buckets are zeroed (the start of an optimizer step)"""
+        for b in self.buckets:
+            b["flat"].zero_()
+            b["work"] = None
+            for p, v in zip(b["params"], b["views"]):
+                p.grad = v
+        self._touched.zero_()
+        self._armed = False
+
+    zero_grad = attach
+
+    def arm(self):
+        self._armed = True
+        for b in self.buckets:
+            b["pending"] = len(b["params"])
+
+    def _on_grad(self, p):
+        self._touched[self._pos[id(p)]] = 1.0
+        bi, k = self._index[id(p)]
+        b = self.buckets[bi]
+        if p.grad is not b["views"][k]:                    # someone replaced .grad (e.g. zero_grad(set_to_none=True)): fold it back
+            b["views"][k].copy_(p.grad)
+            p.grad = b["views"][k]
+        if self._armed:
+            b["pending"] -= 1
+            if b["pending"] == 0 and self.world > 1 and b["work"] is None:
+                b["work"] = dist.all_reduce(b["flat"], op=dist.ReduceOp.SUM, async_op=True)
+
+    def finish(self) -> int:
+        """-> number of collectives issued for this step"""
+        n = 0
+        if self.world > 1:
+            for b in self.buckets:
+                if b["work"] is None:
+                    b["work"] = dist.all_reduce(b["flat"], op=dist.ReduceOp.SUM, async_op=True)
+            mask = self._touched.to(self.buckets[0]["flat"].device) if self.buckets else self._touched
+            mwork = dist.all_reduce(mask, op=dist.ReduceOp.MAX, async_op=True) if self.buckets else None
+            for b in self.buckets:
+                b["work"].wait()
+                b["flat"].div_(self.world)
+                b["work"] = None
+                n += 1
+            if mwork is not None:
+                mwork.wait()
+                n += 1
+                self._touched = mask.cpu()
+        for p in self.params:
+            if self._touched[self._pos[id(p)]] == 0:
+                p.grad = None
+        self._armed = False
+        return n
+
+    def close(self):
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
+
+
+def average_gradients(params, bucket_bytes: int = 64 << 20) -> int:
+    """All-reduce (mean) the .grad of `params` across ranks, in place, after the backward passes are done (the blocking
+    form; `GradientAverager` is the one that overlaps with backward).  Gradients are packed into flat buckets of at most
+    `bucket_bytes` per (dtype, device) with one fused multi-tensor copy each way, every bucket's all-reduce is issued
+    asynchronously before the first one is waited for, and a parameter without a gradient on this rank contributes zeros
+    (the bucket layout must not depend on the rank) -- unless it has a gradient on NO rank, in which case its `.grad`
+    stays None.  Returns the number of gradient buckets (collectives) issued."""
+    params = [p for p in params if p.requires_grad]
+    if not dist.is_initialized() or dist.get_world_size() == 1 or not params:
+        return 0
+    world = dist.get_world_size()
+    buckets = _bucket_layout(params, bucket_bytes)
+    has = torch.tensor([0.0 if p.grad is None else 1.0 for p in params], device=params[0].device)
+    mwork = dist.all_reduce(has, op=dist.ReduceOp.MAX, async_op=True)
     pending = []
     for group in buckets:
-        flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in group])
-        pending.append((dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=True), flat, group))
-    for work, flat, group in pending:
+        flat = torch.zeros(sum(p.numel() for p in group), dtype=group[0].dtype, device=group[0].device)
+        views, off = [], 0
+        for p in group:
+            views.append(flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
+        src = [(v, p.grad) for v, p in zip(views, group) if p.grad is not None]
+        if src:
+            torch._foreach_copy_([v for v, _ in src], [g for _, g in src])
+        pending.append((dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=True), flat, views, group))
+    mwork.wait()
+    has = has.cpu()
+    anywhere = {id(p): bool(has[i] > 0) for i, p in enumerate(params)}
+    for work, flat, views, group in pending:
         work.wait()
         flat.div_(world)
-        off = 0
-        for p in group:
-            n = p.numel()
-            g = flat[off:off + n].view_as(p)
+        for p, v in zip(group, views):
+            if not anywhere[id(p)]:
+                continue                                   # no rank produced a gradient: leave .grad = None
             if p.grad is None:
-                p.grad = g.clone()
+                p.grad = v.clone()
             else:
-                p.grad.copy_(g)
-            off += n
+                p.grad.copy_(v)
     return len(buckets)

@@ -10,6 +10,7 @@ them into the engine's bf16 layouts whenever they change.
 """
 import ctypes as C
 import os
+import threading
 import weakref
 
 import torch
@@ -18,7 +19,7 @@ from . import _lib
 
 
 class SynthesisEngine:
-    def __init__(self, generator, max_batch=8):
+    def __init__(self, generator, max_batch=8, use_graph=None):
         self.G = generator
         self.lib = _lib.load()
         self.plan = None
@@ -26,9 +27,11 @@ class SynthesisEngine:
         self.workspace = None
         self._packed_version = None
         self._keep = []
+        self.device = generator.input.input.device
         # CUDA graph per (batch, noise layout): one graph launch replaces the ~30 kernel launches of a
-        # forward.  SG2_B200_GRAPH=0 switches it off.
-        self.use_graph = os.environ.get("SG2_B200_GRAPH", "1") != "0"
+        # forward.  SG2_B200_GRAPH=0 switches it off; so does a caller that is not the main thread (stream capture is
+        # process-global by default: an nn.DataParallel replica thread must not capture while its siblings launch).
+        self.use_graph = (os.environ.get("SG2_B200_GRAPH", "1") != "0") if use_graph is None else bool(use_graph)
         self._graphs = {}
         if generator.input.input.is_cuda:
             self._ensure(max_batch)
@@ -175,6 +178,11 @@ class SynthesisEngine:
         out_dtype = G.input.input.dtype
         dev = latent.device
         use_graph = self.use_graph if graph is None else graph
+        if use_graph and threading.current_thread() is not threading.main_thread():
+            use_graph = False
+        if dev != self.device:
+            raise RuntimeError(f"sg2_b200 engine: planned for {self.device}, called with latents on {dev} "
+                               "(Generator.engine() re-plans after the module moves)")
         if B == 0:
             return torch.empty(0, 3, G.size, G.size, device=dev, dtype=out_dtype)
         if not use_graph or torch.cuda.is_current_stream_capturing():
@@ -240,6 +248,10 @@ class SynthesisEngine:
             if prev is None or prev[0]() is not n or prev[1] != n._version:
                 buf.copy_(n.detach().reshape(buf.shape))
                 src[i] = (weakref.ref(n), n._version)
+
+    def __reduce__(self):
+        raise TypeError("SynthesisEngine holds device handles and cannot be pickled; copy the Generator instead "
+                        "(its copies re-plan lazily)")
 
     def __del__(self):
         try:

@@ -376,6 +376,41 @@ class Generator(nn.Module):
         self.precision = os.environ.get('SG2_B200_PRECISION', 'auto')
         self._engine = None
 
+    # -- engine / cache lifetime ---------------------------------------------------------------
+    # The bf16 engine owns a ctypes plan handle, a device workspace and CUDA graphs: none of it may travel with a copy
+    # of the module.  deepcopy / pickle / torch.save(G) drop it (the copy re-plans lazily on its first bf16 forward), and
+    # nn.DataParallel replicas (whose parameters are fresh broadcast copies on every forward) get a transient engine
+    # without CUDA graphs on their own device instead of sharing the device-0 one.
+    @property
+    def precision(self):
+        return self.__dict__.get('_precision', 'auto')
+
+    @precision.setter
+    def precision(self, value):
+        if value not in ('auto', 'exact', 'bf16'):
+            raise ValueError(f"sg2_b200 Generator.precision must be 'auto', 'exact' or 'bf16', got {value!r}")
+        self.__dict__['_precision'] = value
+
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state['_engine'] = None
+        return state
+
+    def _replicate_for_data_parallel(self):
+        replica = super()._replicate_for_data_parallel()
+        replica.__dict__['_engine'] = None
+        replica.__dict__['_transient_engine'] = True
+        return replica
+
+    def invalidate_caches(self):
+        """Drop every packed copy of the parameters (the engine's bf16 weight pack and CUDA graphs, the frozen-weight
+        packs of the tensor-core autograd route).  Parameter updates through optimizers, `copy_`, `load_state_dict` or
+        `.to()` are detected automatically (tensor version counter / storage address); an in-place write through `.data`
+        bumps neither, so code that updates weights that way (rosinality-style EMA `accumulate()`) must call this."""
+        self._engine = None
+        for m in self.modules():
+            m.__dict__.pop('_tc_cache', None)
+
     def make_noise(self):
         device = self.input.input.device
         noises = [torch.randn(1, 1, 2 ** 2, 2 ** 2, device=device)]
@@ -403,10 +438,12 @@ class Generator(nn.Module):
         return mode == 'auto' and self.input.input.dtype == torch.bfloat16
 
     def engine(self):
-        """The whole-network bf16 tcgen05 engine bound to this module's parameters (lazy)."""
-        if self._engine is None:
+        """The whole-network bf16 tcgen05 engine bound to this module's parameters (lazy, one per device: moving the
+        module re-plans)."""
+        dev = self.input.input.device
+        if self._engine is None or self._engine.device != dev:
             from ..engine import SynthesisEngine
-            self._engine = SynthesisEngine(self)
+            self._engine = SynthesisEngine(self, use_graph=None if not self.__dict__.get('_transient_engine') else False)
         return self._engine
 
     def forward(self, styles, return_latents=False, return_features=False, inject_index=None, truncation=1,

@@ -86,6 +86,21 @@ class SynthesisNetwork(torch.nn.Module):                     # generator.py:55-8
         self.first_block = SynthesisPrologue(width[4], resolution=4, **common)
         self.blocks.extend(SynthesisBlock(width[r // 2], width[r], resolution=r, **common) for r in octaves[1:])
 
+    @property
+    def precision(self):
+        return self.__dict__.get('_precision', 'auto')
+
+    @precision.setter
+    def precision(self, value):
+        if value not in ('auto', 'exact', 'bf16'):
+            raise ValueError(f"sg2_b200 SynthesisNetwork.precision must be 'auto', 'exact' or 'bf16', got {value!r}")
+        self.__dict__['_precision'] = value
+
+    def invalidate_caches(self):
+        """drop the frozen-weight packs of the tensor-core route (needed after an in-place `.data` write to a weight)"""
+        for m in self.modules():
+            m.__dict__.pop('_tc_cache', None)
+
     def forward(self, ws, noise_mode='random', return_latents=False, **kwargs):
         split_ws = [ws[:, 0:2, :]] + [ws[:, 2 * n + 1: 2 * n + 4, :] for n in range(len(self.block_resolutions))]
         with K.tc_grad(True if self.precision == 'bf16' else (False if self.precision == 'exact' else None)):
@@ -242,6 +257,7 @@ class MappingNetwork(torch.nn.Module):                       # generator.py:242-
         self.num_layers = num_layers
         self.w_avg_beta = w_avg_beta
         self.lr_multiplier = lr_multiplier
+        self.activation = activation
         features_list = [z_dim] + [w_dim] * num_layers
         self.layers = torch.nn.ModuleList()
         for idx in range(num_layers):
@@ -253,7 +269,9 @@ class MappingNetwork(torch.nn.Module):                       # generator.py:242-
     def forward(self, z, truncation_psi=1, truncation_cutoff=None, skip_w_avg_update=False):
         if not z.is_cuda:
             raise RuntimeError("input must be a CUDA tensor")
-        if self.z_dim == self.w_dim and self.num_layers > 0 and not K.needs_grad(z, *self.parameters()):
+        fused_ok = (getattr(self, 'activation', 'lrelu') == 'lrelu' and self.z_dim == self.w_dim and 0 < self.num_layers <= 32
+                    and self.w_dim in (32, 64, 128, 256, 512) and z.dim() == 2)      # what sg2_mapping_fwd implements
+        if fused_ok and not K.needs_grad(z, *self.parameters()):
             # normalize_2nd_moment + the whole MLP on the mapping kernels (one launch per layer)
             x = K.mapping(z, [l.weight for l in self.layers], [l.bias for l in self.layers], self.lr_multiplier, True)
         else:

@@ -71,6 +71,14 @@ def test_shard_bounds_properties():
         d.shard_bounds(4, 2, 2)
 
 
+def _np(ts):
+    return [None if t is None else t.detach().numpy().copy() for t in ts]
+
+
+def _pt(ts):
+    return [None if t is None else torch.from_numpy(t) for t in ts]
+
+
 def _grad_worker(rank, world, port, q):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
@@ -92,7 +100,7 @@ def _grad_worker(rank, world, port, q):
     n_buckets = d.average_gradients(enc.parameters(), bucket_bytes=256)   # tiny buckets: several collectives
     grads = [None if p.grad is None else (p.grad * world).clone() for p in enc.parameters()]   # mean * world == sum over ranks
     w0 = [p.detach().clone() for p in enc.parameters()]
-    q.put((rank, n_buckets, grads, w0))
+    q.put((rank, n_buckets, _np(grads), _np(w0)))        # by value: shared-memory tensor handles die with the worker
     dist.barrier()
     dist.destroy_process_group()
 
@@ -110,6 +118,7 @@ def test_two_rank_gradient_average_gloo():
         p.join(timeout=60)
         assert p.exitcode == 0
     (_, nb0, g0, w0), (_, nb1, g1, w1) = res
+    g0, w0, g1, w1 = _pt(g0), _pt(w0), _pt(g1), _pt(w1)
     assert nb0 == nb1 and nb0 >= 2                              # same bucket layout on both ranks, more than one bucket
     assert all(torch.equal(a, b) for a, b in zip(w0, w1))       # broadcast made the replicas identical
     assert all((a is None) == (b is None) and (a is None or torch.equal(a, b)) for a, b in zip(g0, g1))
@@ -131,3 +140,66 @@ def test_two_rank_gradient_average_gloo():
             (((enc(x[lo:hi]) - y[lo:hi]) ** 2).sum() / 8).backward()
             r = list(enc.parameters())[3].grad
         assert torch.allclose(a, r, rtol=1e-5, atol=1e-6), i
+
+
+def _averager_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    d = importlib.import_module("stylegan-for-facerec_b200.dist")
+    torch.manual_seed(100 + rank)
+    enc = torch.nn.Sequential(torch.nn.Linear(6, 16), torch.nn.ReLU(), torch.nn.Linear(16, 4))
+    unused = torch.nn.Parameter(torch.randn(3))                 # receives a gradient on NO rank
+    d.broadcast_parameters(enc, src=0)
+    params = list(enc.parameters()) + [unused]
+    avg = d.GradientAverager(params, bucket_bytes=256)          # several buckets
+    torch.manual_seed(0)
+    x, y = torch.randn(8, 6), torch.randn(8, 4)
+    mine, tgt = d.shard_batch(x), d.shard_batch(y)
+    out = []
+    for step in range(2):                                       # second step: the buckets are re-used
+        avg.zero_grad()
+        for it in range(3):                                     # gradient accumulation over refinement iterations
+            if it == 2:
+                avg.arm()                                       # only the last backward triggers the exchange
+            loss = ((enc(mine * (it + 1)) - tgt) ** 2).sum() / x.shape[0]
+            loss.backward()
+        n = avg.finish()
+        out.append((n, [None if p.grad is None else (p.grad * world).clone() for p in params]))
+    views_ok = all(p.grad is None or p.grad.data_ptr() == v.data_ptr()
+                   for b in avg.buckets for p, v in zip(b["params"], b["views"]))
+    q.put((rank, [(n, _np(g)) for n, g in out], views_ok, len(avg.buckets)))
+    avg.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_overlapped_gradient_averager_gloo():
+    """GradientAverager: gradients live in bucket views, the exchange is issued from hooks during the armed backward,
+    accumulation over several backward passes is preserved, a parameter without a gradient anywhere keeps grad = None"""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_averager_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=120) for _ in procs), key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, out0, ok0, nb0), (_, out1, ok1, nb1) = res
+    assert ok0 and ok1 and nb0 == nb1 and nb0 >= 2
+    # single-process reference: whole batch, same three accumulated passes
+    torch.manual_seed(100)
+    enc = torch.nn.Sequential(torch.nn.Linear(6, 16), torch.nn.ReLU(), torch.nn.Linear(16, 4))
+    torch.manual_seed(0)
+    x, y = torch.randn(8, 6), torch.randn(8, 4)
+    for it in range(3):
+        (((enc(x * (it + 1)) - y) ** 2).sum() / 8).backward()
+    ref = [p.grad for p in enc.parameters()]
+    for (n0, g0), (n1, g1) in zip(out0, out1):
+        g0, g1 = _pt(g0), _pt(g1)
+        assert n0 == n1 == nb0 + 1                               # one collective per bucket + the has-gradient mask
+        assert g0[-1] is None and g1[-1] is None                 # unused parameter: no gradient invented
+        for a, b, r in zip(g0[:-1], g1[:-1], ref):
+            assert torch.equal(a, b) and torch.allclose(a, r, rtol=1e-5, atol=1e-6)

@@ -3,9 +3,13 @@
 # (SG2_FIR_DBG / SG2_GEMM_DBG; results are wrong on purpose).  usage: tools/knockout.sh [size] [batch]
 SIZE=${1:-256}; BATCH=${2:-64}
 mkdir -p gpurun_out/ko
+# the knock-out branches are compiled only into a variant build of the library (-DSG2_KNOCKOUT=1), selected by SG2_B200_LIB
+KO_LIB=stylegan-for-facerec_b200/csrc/libsg2_b200_ko.so
+[ -f $KO_LIB ] || python stylegan-for-facerec_b200/build.py --tag ko -DSG2_KNOCKOUT=1
+export SG2_B200_LIB=$PWD/$KO_LIB
 run() { # name, env...
   name=$1; shift
-  env "$@" timeout 200 python bench.py --size $SIZE --batch $BATCH --no-cpu-baseline --steps 5 --warmup 3 \
+  env "$@" timeout 200 python bench.py --size $SIZE --batch $BATCH --no-cpu-baseline --no-extra --steps 5 --warmup 3 \
       --profile-out gpurun_out/ko/$name.json > gpurun_out/ko/$name.log 2>&1 || echo "FAILED $name"
 }
 run base X=0
