@@ -38,7 +38,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 SIZE_DEFAULT, BATCH_DEFAULT, N_MLP, STYLE_DIM = 256, 64, 8, 512
-PARITY_REL_MAX = 1.4e-2          # same bound as tests/test_bench_configs_gpu.py (<= 2x the measured error)
+PARITY_REL_MAX = 1.6e-2          # same bound as tests/test_bench_configs_gpu.py (<= 2x the measured error)
 
 
 def workload_name(size, batch):
@@ -385,7 +385,7 @@ def measure(ctx, size, B, K, W, precision, profile_out=None, fp32_e2e=True):
 
     # ---- parity of the timed output: sample 0 of the last timed batch on the exact fp32 path ----
     parity = None
-    if precision == "bf16":
+    if precision == "bf16" and not os.environ.get("SG2_BENCH_NO_PARITY"):      # (off only for knock-out builds, tools/knockout.sh)
         with torch.no_grad():
             G.precision = "exact"
             ref = G([z_dev[W + K - 1][:1]], randomize_noise=False)[0]

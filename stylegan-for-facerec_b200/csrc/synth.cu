@@ -48,6 +48,8 @@ struct Layer {
     // GEMM tiling (styled convs)
     int block_n = 0;
     bool two_sm = false;  // run this layer on the cta_group::2 kernel (synth_gemm2.cu)
+    bool fused_up = false;   // up-sampling layer run as ONE 3x3 conv with N = 4*Cout composite (weights * blur) columns, no FIR pass
+    int n_gemm = 0;          // N of the GEMM: Cout, or 4*Cout for a fused up-sampling layer
     GemmParams gp;        // static part, pointers filled per forward
     CUtensorMap tmA[kGemmMaxSub], tmB;
     CUtensorMap tmT[4];   // up-sampling layers: the 4 polyphase planes as the FIR kernel reads them
@@ -99,18 +101,21 @@ int plan_gemm(sg2_synth *S, Layer &L, const int *custom_taps = nullptr, int n_cu
     const int B = S->max_batch;
     GemmParams &g = L.gp;
     memset(&g, 0, sizeof(g));
-    const int cin = L.p.cin, cout = L.p.cout;
-    const bool up = L.p.upsample != 0;
+    const bool fused = L.fused_up;
+    const int cin = L.p.cin, cout = fused ? 4 * L.p.cout : L.p.cout;
+    const bool up = L.p.upsample != 0 && !fused;
     const int r = L.res_in;
+    L.n_gemm = cout;
     g.block_k = cin % 64 == 0 ? 64 : 32;
     g.Cin = cin; g.Cout = cout; g.kchunks = cin / g.block_k;
+    g.cout_real = L.p.cout; g.up4 = fused ? 1 : 0;
     g.mode = up ? 1 : 0;
     g.nsub = up ? 4 : 1;
     // sub-problems
     for (int s = 0; s < g.nsub; ++s) {
         GemmSub &q = g.sub[s];
         if (!up) {
-            q.PH = q.PW = r; q.out_H = q.out_W = r; q.out_off = 0;
+            q.PH = q.PW = r; q.out_H = q.out_W = fused ? 2 * r : r; q.out_off = 0;
             q.ntaps = 0;
             if (custom_taps) {
                 for (int t = 0; t < n_custom; ++t) { q.dy[t] = custom_taps[3 * t]; q.dx[t] = custom_taps[3 * t + 1]; q.wtap[t] = custom_taps[3 * t + 2]; }
@@ -161,7 +166,17 @@ int plan_gemm(sg2_synth *S, Layer &L, const int *custom_taps = nullptr, int n_cu
     const int mode2 = env2 ? atoi(env2) : 1;
     const bool auto2 = up ? (best_n > 128 && best_tiles >= 4L * S->sms)
                           : (best_tiles >= (long)S->sms && (best_n >= 128 || cin >= 256));
-    L.two_sm = best_n >= 32 && g.block_k == 64 && (mode2 == 2 || (mode2 == 1 && auto2));
+    L.two_sm = best_n >= 32 && g.block_k == 64 && (mode2 == 2 || (mode2 == 1 && auto2) || fused);
+    // cta_group::2 with resident weights: each CTA of the pair keeps its half of all 9 * kchunks weight tiles in shared
+    // memory next to >= 4 activation stages.  For the fused up-sampling conv of the last octave (64 -> 4 x 32) this removes
+    // the weight stream, which is 1/3 of the layer's L2 -> SM traffic.  SG2_GEMM_RES2=0 switches it off.
+    static const char *envr2 = getenv("SG2_GEMM_RES2");
+    g.resident2 = 0;
+    if (L.two_sm && fused && g.n_tiles_n == 1 && (!envr2 || atoi(envr2) != 0)) {
+        const int half_b = 9 * g.kchunks * (best_n / 2) * g.block_k * 2;
+        const int a_stage = kBlockM * g.block_k * 2 * g.kpack;
+        if (half_b + 4 * a_stage <= kStages * (kBlockM * kBlockK * 2 + kMaxBlockN * kBlockK * 2)) g.resident2 = 1;
+    }
 
     // Resident weights (the narrow, high-resolution tail of the 512^2 / 1024^2 networks): when all 9*Cin*Cout
     // bf16 weights fit in shared memory next to >= 2 activation stages, load them once per CTA and stream
@@ -170,7 +185,7 @@ int plan_gemm(sg2_synth *S, Layer &L, const int *custom_taps = nullptr, int n_cu
     static const char *envr = getenv("SG2_GEMM_RESIDENT");
     bool nb1 = true;
     for (int s = 0; s < g.nsub; ++s) nb1 = nb1 && g.sub[s].NB == 1;
-    if ((!envr || atoi(envr) != 0) && g.n_tiles_n == 1 && nb1 && r >= 16 && cin % 32 == 0) {
+    if ((!envr || atoi(envr) != 0) && !fused && g.n_tiles_n == 1 && nb1 && r >= 16 && cin % 32 == 0) {
         const int resb = 18 * cin * best_n;
         int pick_bk = 0, pick_stage = 0;
         for (int bk : {64, 32}) {
@@ -269,8 +284,9 @@ int encode_maps(sg2_synth *S, Layer &L, const __nv_bfloat16 *x, const __nv_bfloa
                     (int)rc, C, r, q.TW, q.TH, q.NB);
     }
     {
-        cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)L.p.cout, 9};
-        cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)C * L.p.cout * 2};
+        const int n_gemm = L.n_gemm ? L.n_gemm : L.p.cout;
+        cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)n_gemm, 9};
+        cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)C * n_gemm * 2};
         cuuint32_t box[3] = {(cuuint32_t)L.gp.block_k, (cuuint32_t)(L.two_sm ? L.block_n / 2 : L.block_n), 1};
         cuuint32_t es[3] = {1, 1, 1};
         CUresult rc = enc(&L.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void *)wp, dims, strides, box, es,
@@ -387,7 +403,14 @@ extern "C" int sg2_synth_create(sg2_synth **plan, int size, int style_dim, int m
                           "(Cout %% 32 == 0 for up-sampling layers)", i, L.p.cin, L.p.cout);
                 return SG2_ERR_UNSUPPORTED;
             }
-            L.wp = take(sizeof(__nv_bfloat16) * 9 * L.p.cout * L.p.cin);
+            // Fused up-sampling conv (GemmParams::up4): where the polyphase transposed conv + FIR pass is bandwidth-bound --
+            // the narrow octaves, Cout <= 64: FLOP/byte 96..192 -- the blur is folded into the weights and
+            // the (2r+1)^2 intermediate never exists.  SG2_UPFUSED=0: never, 2: every up-sampling layer that qualifies.
+            static const char *envf = getenv("SG2_UPFUSED");
+            const int fmode = envf ? atoi(envf) : 1;
+            L.fused_up = L.p.upsample && fmode != 0 && L.p.cin % 64 == 0 && L.p.cout % 32 == 0 && L.res_out >= 32 &&
+                         (L.p.cout <= 64 || fmode == 2);
+            L.wp = take(sizeof(__nv_bfloat16) * 9 * L.p.cout * L.p.cin * (L.fused_up ? 4 : 1));
             L.wsq = take(sizeof(float) * L.p.cin * L.p.cout);
             L.demod = take(sizeof(float) * B * L.p.cout);
             int rc = plan_gemm(S, L);
@@ -396,9 +419,9 @@ extern "C" int sg2_synth_create(sg2_synth **plan, int size, int style_dim, int m
             prev_cout = L.p.cout;
             max_act = std::max(max_act, sizeof(__nv_bfloat16) * (size_t)B * L.res_in * L.res_in * L.p.cin);
             max_act = std::max(max_act, sizeof(__nv_bfloat16) * (size_t)B * L.res_out * L.res_out * L.p.cout);
-            if (L.p.upsample)
+            if (L.p.upsample && !L.fused_up)
                 max_T = std::max(max_T, sizeof(__nv_bfloat16) * 4 * (size_t)B * (L.res_in + 1) * (L.res_in + 1) * L.p.cout);
-            else
+            else if (!L.p.upsample)
                 max_part = std::max(max_part, sizeof(float) * 2 * (size_t)L.gp.n_tiles_n * B * 3 * L.res_out * L.res_out);
         }
         S->layers.push_back(L);
@@ -427,7 +450,8 @@ extern "C" int sg2_synth_create(sg2_synth **plan, int size, int style_dim, int m
     for (size_t i = 0; i < S->layers.size(); ++i) {
         const Layer &L = S->layers[i];
         char name[64];
-        snprintf(name, sizeof(name), "L%zu_%dx%d_%d->%d%s", i, L.res_out, L.res_out, L.p.cin, L.p.cout, L.p.upsample ? "_up" : "");
+        snprintf(name, sizeof(name), "L%zu_%dx%d_%d->%d%s", i, L.res_out, L.res_out, L.p.cin, L.p.cout,
+                 L.p.upsample ? (L.fused_up ? "_upfused" : "_up") : "");
         const double px_in = (double)L.res_in * L.res_in, px_out = (double)L.res_out * L.res_out;
         if (L.rgb) {
             add("rgb_combine", name, 2.0 * 3 * L.p.cin * px_out, 0, 0, 0);
@@ -438,10 +462,10 @@ extern "C" int sg2_synth_create(sg2_synth **plan, int size, int style_dim, int m
             // layer, the output plane of a plain one -- except the LAST conv, which stores no activation at all, only
             // the three fp32 ToRGB planes
             const bool last = i + 2 >= S->layers.size();
-            const double out_b = L.p.upsample ? 2.0 * (2 * L.res_in + 1.0) * (2 * L.res_in + 1.0) * L.p.cout
-                                              : (last ? 4.0 * 3 * px_out : 2.0 * px_out * L.p.cout);
+            const double out_b = (L.p.upsample && !L.fused_up) ? 2.0 * (2 * L.res_in + 1.0) * (2 * L.res_in + 1.0) * L.p.cout
+                                                               : (last ? 4.0 * 3 * px_out : 2.0 * px_out * L.p.cout);
             add("gemm", name, fl, 2.0 * px_in * L.p.cin + out_b, L.gp.total_tiles, L.block_n);
-            if (L.p.upsample) add("upfir", name, 0, 2.0 * ((2 * L.res_in + 1.0) * (2 * L.res_in + 1.0) + px_out) * L.p.cout, 0, 0);
+            if (L.p.upsample && !L.fused_up) add("upfir", name, 0, 2.0 * ((2 * L.res_in + 1.0) * (2 * L.res_in + 1.0) + px_out) * L.p.cout, 0, 0);
         }
     }
     S->description = d;
@@ -483,9 +507,15 @@ extern "C" int sg2_synth_pack(sg2_synth *S, void *workspace, sg2_stream_t stream
             int rc = launch_pack_rgb_weight((float *)(ws + L.rgbw), L.p.weight, 3 * L.p.cin, 1.0f / sqrtf((float)L.p.cin), st);
             if (rc) return rc;
         } else {
+            // (a fused up-sampling layer needs wsq from the plain weights and then its own composite pack over wp)
             int rc = launch_pack_conv_weight((__nv_bfloat16 *)(ws + L.wp), (float *)(ws + L.wsq), L.p.weight, L.p.cin,
                                              L.p.cout, 9, 1.0f / sqrtf((float)L.p.cin * 9), st);
             if (rc) return rc;
+            if (L.fused_up) {
+                rc = launch_pack_upfused_weight((__nv_bfloat16 *)(ws + L.wp), L.p.weight, L.p.cin, L.p.cout,
+                                                1.0f / sqrtf((float)L.p.cin * 9), S->kf, st);
+                if (rc) return rc;
+            }
         }
     }
     SG2_CUDA_OK(cudaMemcpyAsync(ws + S->off_toeplitz, S->toeplitz.data(), S->toeplitz.size() * 2, cudaMemcpyHostToDevice, st));
@@ -520,7 +550,7 @@ extern "C" int sg2_synth_forward(sg2_synth *S, void *workspace, const float *lat
             (void)cur;
             int rc = encode_maps(S, L, x, (const __nv_bfloat16 *)(ws + L.wp), B);
             if (rc) return rc;
-            if (L.p.upsample) {
+            if (L.p.upsample && !L.fused_up) {
                 rc = encode_fir_maps(L, Tbuf, act[0], B);
                 if (rc) return rc;
             }
@@ -588,7 +618,17 @@ extern "C" int sg2_synth_forward(sg2_synth *S, void *workspace, const float *lat
         const float *nz = noise[noise_idx];
         const int64_t nzs = noise_bstride[noise_idx];
         ++noise_idx;
-        if (!L.p.upsample) {
+        if (L.fused_up) {
+            // conv_transpose + blur + noise + bias + lrelu + next layer's modulation in ONE launch: act[1] -> act[0]
+            SG2_REQUIRE(next_conv, SG2_ERR_BAD_ARG, "engine: up-sampling conv without a consumer");
+            g.noise = nz; g.noise_bstride = nzs; g.noise_weight = L.p.noise_weight;
+            g.bias = L.p.act_bias;
+            g.next_style = (const float *)(ws + next_conv->style);
+            g.out = act[0];
+            rc = L.two_sm ? launch_modconv_gemm2(g, L.tmA, L.tmB, S->sms, st) : launch_modconv_gemm(g, L.tmA, L.tmB, S->sms, st);
+            if (rc) return rc;
+            if ((rc = rec(S, st, "gemm(upfused)"))) return rc;
+        } else if (!L.p.upsample) {
             g.noise = nz; g.noise_bstride = nzs; g.noise_weight = L.p.noise_weight;
             g.bias = L.p.act_bias;
             g.next_style = next_conv ? (const float *)(ws + next_conv->style) : nullptr;

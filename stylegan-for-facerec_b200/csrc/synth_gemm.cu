@@ -234,7 +234,9 @@ modconv_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant_
                     for (int kc = 0; kc < p.kchunks; ++kc) {
                         mbar_wait(&sm.empty[stage], phase ^ 1);
                         uint8_t *slot = sm.ring + ring_off + stage * stage_bytes;
-                        if (elect_one()) {
+                        if (SG2_DBG(p) & 2) {                 // bottleneck analysis only (variant build): no activation loads
+                            if (elect_one()) mbar_arrive(&sm.full[stage]);
+                        } else if (elect_one()) {
                             mbar_arrive_expect_tx(&sm.full[stage], (uint32_t)g.nslab * slab_bytes);
 #pragma unroll
                             for (int sl = 0; sl < 3; ++sl)
@@ -340,6 +342,7 @@ modconv_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant_
                                     const uint64_t bdesc = b0 + (uint32_t)g.wtap[tap] * wb16;
                                     // 32 bytes (>>4 = 2) inside the swizzle row per K = 16 step
                                     umma_bf16(d_tmem, adesc, bdesc, idesc, (kc | tap) != 0);
+                                    if (SG2_DBG(p) & 8) continue;          // knock-out: one MMA per tap
                                     umma_bf16(d_tmem, adesc + 2, bdesc + 2, idesc, 1);
                                     if (ksteps == 4) {
                                         umma_bf16(d_tmem, adesc + 4, bdesc + 4, idesc, 1);
@@ -492,7 +495,8 @@ modconv_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant_
                 float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
                 const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * acc_cols;
                 const EpiTables tab{e_demod + pb, e_next + pb, e_w0 + pb, e_w1 + pb, e_w2 + pb, e_bias};
-                if (alt) {            // this warp owns every column of the tile
+                if (SG2_DBG(p) & 16) {   // knock-out: no epilogue work at all
+                } else if (alt) {            // this warp owns every column of the tile
                     if (N == 16) epi_cols<16>(p, tab, t_row, 0, nz, off16, stg, lane, rgb0, rgb1, rgb2);
                     else
                         for (int c0 = 0; c0 < N; c0 += 32) epi_cols<32>(p, tab, t_row + c0, c0, nz, off16, stg, lane, rgb0, rgb1, rgb2);
@@ -533,6 +537,7 @@ int launch_modconv_gemm(const GemmParams &p, const CUtensorMap *tmA, const CUten
         configured.store(1, std::memory_order_release);
     }
     SG2_REQUIRE(p.block_n % 16 == 0 && p.block_n >= 16 && p.block_n <= kMaxBlockN, SG2_ERR_BAD_ARG, "gemm: bad BLOCK_N %d", p.block_n);
+    SG2_REQUIRE(!p.up4 && !p.resident2, SG2_ERR_UNSUPPORTED, "gemm: the fused up-sampling conv runs on the cta_group::2 kernel only");
     if (p.resident) {
         SG2_REQUIRE(p.n_tiles_n == 1 && p.kpack == 1 && p.resb_bytes == 9 * p.Cin * p.block_n * 2 && p.stage_bytes % 1024 == 0 &&
                         p.resb_bytes % 1024 == 0 && p.resb_bytes + 2 * p.stage_bytes <= kRingBytes,

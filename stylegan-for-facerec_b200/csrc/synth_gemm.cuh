@@ -43,6 +43,7 @@ struct GemmParams {
     // resident-weights mode (narrow layers whose 9*Cin*Cout bf16 weights fit in shared memory): the whole
     // weight tensor is loaded once per CTA, the ring holds only activation slabs (stage_bytes each)
     int resident, resb_bytes, stage_bytes;
+    int resident2;                  // cta_group::2 kernel: each CTA keeps its half of every weight tile resident, the ring streams A only
     int mma2;                       // resident mode: two warps issue the MMAs of alternate tiles
     // polyphase interleave: a CTA's chunk of every sub-problem is cut into segments of seg_tiles tiles and the
     // sub-problems are walked segment by segment (seg outer, sub-problem inner), so the four phases of the transposed
@@ -52,6 +53,14 @@ struct GemmParams {
     // epilogue schedule of the single-CTA kernel: 1 = the two warp groups take alternate tiles (narrow BLOCK_N,
     // ONE ToRGB partial plane per N tile), 0 = they split the columns of every tile (two partial planes)
     int epi_alt;
+    // Fused up-sampling conv (the narrow, HBM-bound octaves): conv_transpose2d(stride 2) followed by the 4x4 blur is ONE
+    // stride-2 transposed convolution with a 6x6 kernel (3x3 weights convolved with the blur taps); each of its four
+    // output phases (py, px) is a dense 3x3 convolution of the INPUT with its own weights.  The four phases are
+    // concatenated along N (column = (py*2 + px) * cout_real + co), so the layer is a plain 3x3 conv with N = 4*Cout
+    // whose epilogue writes column block (py, px) of input pixel (y, x) to output pixel (2y+py, 2x+px): no (2r+1)^2
+    // intermediate, no FIR pass.  4x the tensor FLOPs of the polyphase form -- used where the layer is bandwidth-bound.
+    int up4;
+    int cout_real;                  // channels of the output tensor (= Cout / 4 when up4, else Cout)
     int dbg;                        // SG2_GEMM_DBG knock-outs for bottleneck analysis (results WRONG when set): 1 no stores, 2 no A loads, 4 no B loads, 8 one MMA per stage
     // epilogue
     int mode;                       // 0: styled conv (noise, bias, lrelu, next-style, ToRGB); 1: plain scaled store

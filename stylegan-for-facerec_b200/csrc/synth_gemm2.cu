@@ -65,6 +65,7 @@ struct __align__(1024) Gemm2Smem {
     float e_bias[kMaxBlockN];
     uint64_t full[kMaxStages2], empty[kMaxStages2];
     uint64_t tmem_full[2], tmem_empty[2];
+    uint64_t b_full;              // resident-weights mode: both halves of the weight tensor have landed (leader's barrier)
     uint32_t tmem_base;
 };
 
@@ -131,6 +132,7 @@ modconv_gemm2_kernel(const __grid_constant__ GemmParams p, const __grid_constant
         for (int i = 0; i < kMaxStages2; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.empty[i], 1); }
         // tmem_empty lives in the leader: the epilogue warps of BOTH CTAs arrive on it
         for (int i = 0; i < 2; ++i) { mbar_init(&sm.tmem_full[i], 1); mbar_init(&sm.tmem_empty[i], 2 * kEpiWarps2); }
+        mbar_init(&sm.b_full, 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc_2sm(&sm.tmem_base, 512);
@@ -145,12 +147,27 @@ modconv_gemm2_kernel(const __grid_constant__ GemmParams p, const __grid_constant
     const uint32_t a_stage = kBlockM * row_bytes;
     const uint32_t b_bytes = (uint32_t)(p.block_n / 2) * row_bytes;   // this CTA's half of the weight tile
     const uint32_t kpk = (uint32_t)p.kpack;                  // K chunks per pipeline stage (see synth_gemm.cu)
-    const uint32_t stage_bytes = kpk * (a_stage + b_bytes);  // multiple of 1 KiB: swizzle atoms stay aligned
-    const uint32_t nstages = min((uint32_t)kMaxStages2, (uint32_t)kRingBytes2 / stage_bytes);
+    // Resident weights (p.resident2): this CTA's half of EVERY weight tile ([tap][K chunk], b_bytes each) is loaded once
+    // and stays in front of the ring; the ring then streams activation tiles only.  The layer's operand traffic from L2
+    // drops from (A + B/2) to A per tap, which is what bounds the narrow layers.
+    const bool resident = p.resident2 != 0;
+    const uint32_t ring_off = resident ? (uint32_t)(kGemmMaxTaps * p.kchunks) * b_bytes : 0u;
+    const uint32_t stage_bytes = resident ? kpk * a_stage : kpk * (a_stage + b_bytes);   // multiple of 1 KiB: swizzle atoms stay aligned
+    const uint32_t nstages = min((uint32_t)kMaxStages2, ((uint32_t)kRingBytes2 - ring_off) / stage_bytes);
 
     if (warp == 0) {
         // ===================== TMA producer (warp-uniform control flow, one elected lane issues) =====
         uint32_t stage = 0, phase = 0;
+        if (resident) {
+            if (elect_one()) {
+                if (leader) mbar_arrive_expect_tx(&sm.b_full, 2u * ring_off);
+                for (int tap = 0; tap < kGemmMaxTaps; ++tap)
+                    for (int kc = 0; kc < p.kchunks; ++kc)
+                        tma_load_3d_2sm(smem_u32(sm.ring) + (uint32_t)(tap * p.kchunks + kc) * b_bytes, &tmB, &sm.b_full, kc * (int)bk,
+                                        rank * (p.block_n / 2), tap);
+            }
+            __syncwarp();
+        }
         for (int seg = 0; seg < p.nseg; ++seg)
         for (int s = 0; s < p.nsub; ++s) {
             const GemmSub &g = p.sub[s];
@@ -163,9 +180,27 @@ modconv_gemm2_kernel(const __grid_constant__ GemmParams p, const __grid_constant
                 for (int kc = 0; kc < p.kchunks; kc += (int)kpk) {
                     for (int tap = 0; tap < g.ntaps; ++tap) {
                         mbar_wait(&sm.empty[stage], phase ^ 1);
-                        const uint32_t slot = smem_u32(sm.ring) + stage * stage_bytes;
+                        const uint32_t slot = smem_u32(sm.ring) + ring_off + stage * stage_bytes;
                         const int ax = t.x0 + g.dx[tap], ay = t.y0 + g.dy[tap], wt = g.wtap[tap];
-                        if (elect_one()) {
+                        if (SG2_DBG(p) & 6) {                 // bottleneck analysis only (variant build)
+                            if (elect_one()) {
+                                const bool la = !(SG2_DBG(p) & 2), lb = !(SG2_DBG(p) & 4) && !resident;
+                                if (leader) {
+                                    if (!la && !lb) mbar_arrive(&sm.full[stage]);
+                                    else mbar_arrive_expect_tx(&sm.full[stage], 2 * kpk * ((la ? a_bytes : 0u) + (lb ? b_bytes : 0u)));
+                                }
+                                for (uint32_t u = 0; u < kpk; ++u) {
+                                    if (la) tma_load_4d_2sm(slot + u * a_stage, tmA, &sm.full[stage], (kc + (int)u) * (int)bk, ax, ay, t.b0);
+                                    if (lb) tma_load_3d_2sm(slot + kpk * a_stage + u * b_bytes, &tmB, &sm.full[stage], (kc + (int)u) * (int)bk, wrow, wt);
+                                }
+                            }
+                        } else if (resident) {
+                            if (elect_one()) {
+                                if (leader) mbar_arrive_expect_tx(&sm.full[stage], 2 * kpk * a_bytes);
+                                tma_load_4d_2sm(slot, tmA, &sm.full[stage], kc * (int)bk, ax, ay, t.b0);
+                                if (kpk == 2) tma_load_4d_2sm(slot + a_stage, tmA, &sm.full[stage], (kc + 1) * (int)bk, ax, ay, t.b0);
+                            }
+                        } else if (elect_one()) {
                             // the leader's barrier collects the bytes of both CTAs
                             if (leader) mbar_arrive_expect_tx(&sm.full[stage], 2 * kpk * (a_bytes + b_bytes));
                             tma_load_4d_2sm(slot, tmA, &sm.full[stage], kc * (int)bk, ax, ay, t.b0);
@@ -187,6 +222,10 @@ modconv_gemm2_kernel(const __grid_constant__ GemmParams p, const __grid_constant
         if (leader) {
             const uint32_t idesc = make_idesc_bf16(2 * kBlockM, (uint32_t)p.block_n);
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+            if (resident) {
+                mbar_wait(&sm.b_full, 0);
+                tc_fence_after();
+            }
             for (int seg = 0; seg < p.nseg; ++seg)
             for (int s = 0; s < p.nsub; ++s) {
                 const GemmSub &g = p.sub[s];
@@ -196,26 +235,32 @@ modconv_gemm2_kernel(const __grid_constant__ GemmParams p, const __grid_constant
                     mbar_wait(&sm.tmem_empty[acc], acc_phase ^ 1);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + acc * kMaxBlockN;
+                    int tap = 0, kc = 0;                      // the producer's order: K chunk outer, tap inner
                     for (int k0 = 0; k0 < nstage; ++k0) {
                         mbar_wait(&sm.full[stage], phase);
                         tc_fence_after();
-                        const uint32_t slot = smem_u32(sm.ring) + stage * stage_bytes;
+                        const uint32_t slot = smem_u32(sm.ring) + ring_off + stage * stage_bytes;
                         const uint64_t adesc = make_smem_desc(slot, row_bytes);
-                        const uint64_t bdesc = make_smem_desc(slot + kpk * a_stage, row_bytes);
+                        const uint64_t bdesc = resident
+                            ? make_smem_desc(smem_u32(sm.ring) + (uint32_t)(g.wtap[tap] * p.kchunks + kc) * b_bytes, row_bytes)
+                            : make_smem_desc(slot + kpk * a_stage, row_bytes);
+                        if (++tap == g.ntaps) { tap = 0; kc += (int)kpk; }
                         if (elect_one()) {
                             // advance 32 bytes (>>4 = 2) inside the swizzle row per K = 16 step
                             umma_bf16_2sm(d_tmem, adesc, bdesc, idesc, k0 != 0);
+                            if (!(SG2_DBG(p) & 8)) {
                             umma_bf16_2sm(d_tmem, adesc + 2, bdesc + 2, idesc, 1);
                             if (bk == 64) {
                                 umma_bf16_2sm(d_tmem, adesc + 4, bdesc + 4, idesc, 1);
                                 umma_bf16_2sm(d_tmem, adesc + 6, bdesc + 6, idesc, 1);
                             }
-                            if (kpk == 2) {
+                            if (kpk == 2) {       // the next K chunk: b_bytes further in the resident layout too
                                 const uint64_t a2 = adesc + (a_stage >> 4), b2 = bdesc + (b_bytes >> 4);
                                 umma_bf16_2sm(d_tmem, a2, b2, idesc, 1);
                                 umma_bf16_2sm(d_tmem, a2 + 2, b2 + 2, idesc, 1);
                                 umma_bf16_2sm(d_tmem, a2 + 4, b2 + 4, idesc, 1);
                                 umma_bf16_2sm(d_tmem, a2 + 6, b2 + 6, idesc, 1);
+                            }
                             }
                             umma_commit_2sm_mc(&sm.empty[stage], 3);    // frees the smem slot in BOTH CTAs
                         }
@@ -238,6 +283,8 @@ modconv_gemm2_kernel(const __grid_constant__ GemmParams p, const __grid_constant
         const int et = threadIdx.x - 64;             // 0..255 within the epilogue group
         const float nw = (p.mode == 0 && p.noise) ? __ldg(p.noise_weight) : 0.f;
         const int N = p.block_n;
+        const bool up4 = p.up4 != 0;
+        const int cr = p.cout_real;                  // channels of the output tensor (N = 4 * cr column blocks when up4)
         uint32_t acc = 0, acc_phase = 0;
         int staged_key = -1;
         for (int seg = 0; seg < p.nseg; ++seg)
@@ -254,9 +301,17 @@ modconv_gemm2_kernel(const __grid_constant__ GemmParams p, const __grid_constant
                 const int n0 = t.nt * N;
                 const int y = t.y0 + ty, x = t.x0 + tx, b = t.b0 + nb;
                 const bool valid = !t.dummy && nb < g.NB && y < g.PH && x < g.PW && b < p.B;
-                float nz = 0.f;
-                if (valid && p.mode == 0 && p.noise)     // issued early: overlaps the staging below
-                    nz = __ldg(p.noise + (long long)b * p.noise_bstride + (long long)y * g.PW + x);
+                float nz = 0.f, nz1 = 0.f, nz2 = 0.f, nz3 = 0.f;      // up4: one noise value per output phase
+                if (valid && p.mode == 0 && p.noise) {   // issued early: overlaps the staging below
+                    if (up4) {
+                        const float2 *np = reinterpret_cast<const float2 *>(p.noise + (long long)b * p.noise_bstride +
+                                                                           (long long)(2 * y) * (2 * g.PW) + 2 * x);
+                        const float2 r0 = __ldg(np), r1 = __ldg(np + g.PW);
+                        nz = r0.x; nz1 = r0.y; nz2 = r1.x; nz3 = r1.y;
+                    } else {
+                        nz = __ldg(p.noise + (long long)b * p.noise_bstride + (long long)y * g.PW + x);
+                    }
+                }
                 // ---- stage the per-(sample, channel) epilogue parameters when they change ----
                 const int key = (t.b0 * kMaxBlockN + t.nt) * 16 + g.NB;
                 if (key != staged_key) {
@@ -264,7 +319,8 @@ modconv_gemm2_kernel(const __grid_constant__ GemmParams p, const __grid_constant
                     for (int i = et; i < g.NB * N; i += 256) {
                         const int sb = i / N, col = i - sb * N;
                         const int bb = t.b0 + sb < p.B ? t.b0 + sb : p.B - 1;
-                        const long long o = (long long)bb * p.Cout + n0 + col;
+                        // up4: the four phase blocks of a tile share the per-channel tables
+                        const long long o = up4 ? (long long)bb * cr + (n0 + col) % cr : (long long)bb * p.Cout + n0 + col;
                         sm.e_demod[i] = __ldg(p.demod + o);
                         if (p.mode == 0) {
                             // lrelu gain sqrt(2) (fused_bias_act_kernel.cu:47) folded into both consumers
@@ -278,24 +334,34 @@ modconv_gemm2_kernel(const __grid_constant__ GemmParams p, const __grid_constant
                         }
                     }
                     if (p.mode == 0)
-                        for (int i = et; i < N; i += 256) sm.e_bias[i] = __ldg(p.bias + n0 + i);
+                        for (int i = et; i < N; i += 256) sm.e_bias[i] = __ldg(p.bias + (up4 ? (n0 + i) % cr : n0 + i));
                     asm volatile("bar.sync 1, 256;" ::: "memory");
                     staged_key = key;
                 }
-                nz *= nw;
+                nz *= nw; nz1 *= nw; nz2 *= nw; nz3 *= nw;
                 uint32_t off16 = 0xffffffffu;     // this pixel's row in 16-byte units from p.out (0xFFFFFFFF: not stored)
-                if (valid && p.out)
-                    off16 = (uint32_t)((g.out_off + (((long long)b * g.out_H + y) * g.out_W + x) * p.Cout + n0) >> 3);
+                if (valid && p.out && !(SG2_DBG(p) & 1))
+                    off16 = up4 ? (uint32_t)(((((long long)b * g.out_H + 2 * y) * g.out_W + 2 * x) * cr) >> 3)   // pixel (2y, 2x)
+                                : (uint32_t)((g.out_off + (((long long)b * g.out_H + y) * g.out_W + x) * p.Cout + n0) >> 3);
 
                 mbar_wait(&sm.tmem_full[acc], acc_phase);
                 tc_fence_after();
                 float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
                 const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kMaxBlockN;
                 for (int c0 = 32 * half; c0 < N; c0 += 64) {
+                    if (SG2_DBG(p) & 16) break;            // knock-out: no epilogue work at all
                     uint32_t r[32];
                     tmem_ld32(t_row + c0, r);
                     tmem_ld_wait();
                     uint32_t packed[16];
+                    uint32_t o16 = off16 == 0xffffffffu ? off16 : off16 + (uint32_t)(c0 >> 3);
+                    float nzc = nz;
+                    if (up4) {            // column block (py, px) of input pixel (y, x) -> output pixel (2y+py, 2x+px)
+                        const int ph = (n0 + c0) / cr, chb = (n0 + c0) - ph * cr;
+                        nzc = ph == 0 ? nz : (ph == 1 ? nz1 : (ph == 2 ? nz2 : nz3));
+                        if (off16 != 0xffffffffu)
+                            o16 = off16 + (uint32_t)((((ph >> 1) * g.out_W + (ph & 1)) * cr + chb) >> 3);
+                    }
                     if (p.mode == 0) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
@@ -303,10 +369,10 @@ modconv_gemm2_kernel(const __grid_constant__ GemmParams p, const __grid_constant
                             const float4 b4 = lds128f(smem_u32(&sm.e_bias[c0 + j]));
                             const float4 s4 = lds128f(smem_u32(&sm.e_next[pb + c0 + j]));
                             float v[4];
-                            v[0] = fmaf(__uint_as_float(r[j + 0]), d4.x, nz) + b4.x;
-                            v[1] = fmaf(__uint_as_float(r[j + 1]), d4.y, nz) + b4.y;
-                            v[2] = fmaf(__uint_as_float(r[j + 2]), d4.z, nz) + b4.z;
-                            v[3] = fmaf(__uint_as_float(r[j + 3]), d4.w, nz) + b4.w;
+                            v[0] = fmaf(__uint_as_float(r[j + 0]), d4.x, nzc) + b4.x;
+                            v[1] = fmaf(__uint_as_float(r[j + 1]), d4.y, nzc) + b4.y;
+                            v[2] = fmaf(__uint_as_float(r[j + 2]), d4.z, nzc) + b4.z;
+                            v[3] = fmaf(__uint_as_float(r[j + 3]), d4.w, nzc) + b4.w;
 #pragma unroll
                             for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], kSlope2 * v[e]);   // lrelu (gain folded downstream)
                             if (p.rgb_w) {
@@ -329,8 +395,7 @@ modconv_gemm2_kernel(const __grid_constant__ GemmParams p, const __grid_constant
                         }
                     }
                     if (p.out)
-                        store_rows64_coalesced(smem_u32(sm.stg[warp - 2]), packed, off16 == 0xffffffffu ? off16 : off16 + (uint32_t)(c0 >> 3),
-                                               reinterpret_cast<uint8_t *>(p.out), lane);
+                        store_rows64_coalesced(smem_u32(sm.stg[warp - 2]), packed, o16, reinterpret_cast<uint8_t *>(p.out), lane);
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -369,6 +434,13 @@ int launch_modconv_gemm2(const GemmParams &p, const CUtensorMap *tmA, const CUte
     for (int s = 0; s < p.nsub; ++s)
         SG2_REQUIRE(p.sub[s].NB * p.block_n <= kEpiCap2 && p.sub[s].TH * p.sub[s].TW * p.sub[s].NB <= kBlockM,
                     SG2_ERR_BAD_ARG, "gemm: tile of sub-problem %d too large", s);
+    if (p.up4)
+        SG2_REQUIRE(p.mode == 0 && p.nsub == 1 && p.cout_real % 32 == 0 && p.Cout == 4 * p.cout_real && p.sub[0].NB == 1 &&
+                        p.sub[0].out_W == 2 * p.sub[0].PW && !p.rgb_w,
+                    SG2_ERR_BAD_ARG, "gemm2: bad fused up-sampling plan (Cout %d, channels %d)", p.Cout, p.cout_real);
+    if (p.resident2)
+        SG2_REQUIRE(p.n_tiles_n == 1 && kGemmMaxTaps * p.kchunks * (p.block_n / 2) * p.block_k * 2 + 2 * p.kpack * kBlockM * p.block_k * 2 <= kRingBytes2,
+                    SG2_ERR_BAD_ARG, "gemm2: resident weights do not fit (BLOCK_N %d, %d K chunks)", p.block_n, p.kchunks);
     long most = 0;
     for (int s2 = 0; s2 < p.nsub; ++s2) {
         const GemmSub &g = p.sub[s2];

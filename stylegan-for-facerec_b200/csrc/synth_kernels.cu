@@ -23,6 +23,39 @@ pack_conv_weight_kernel(__nv_bfloat16 *__restrict__ wp, float *__restrict__ wsq,
     if (wsq) wsq[(int64_t)ci * Cout + co] = ss;
 }
 
+// ---- pack for the fused up-sampling conv: conv_transpose2d(stride 2, 3x3) followed by the 4x4 blur (model.py:246-257) is
+// one stride-2 transposed conv with the 6x6 kernel (w * blur); output phase (py, px) of it is a dense 3x3 conv of the
+// input:   out[2y+py, 2x+px] = sum_{dy,dx in -1..1} x[y+dy, x+dx] . Wc[(dy,dx)][(py,px)]
+//          Wc[(dy,dx)][(py,px)][co][ci] = sum_{a,b in 0..3} kf[a][b] * w[co][ci][py+a-1-2dy][px+b-1-2dx]   (indices in 0..2)
+// kf = the flipped blur taps (x4 gain included) as upfirdn2d applies them with pad (1, 1).
+// Layout: bf16 [tap = (dy+1)*3 + (dx+1)][n = (py*2+px)*Cout + co][ci], conv_scale folded in.
+struct Kf16 { float v[16]; };
+__global__ void __launch_bounds__(256)
+pack_upfused_weight_kernel(__nv_bfloat16 *__restrict__ wp, const float *__restrict__ w, int Cin, int Cout, float scale, Kf16 kf) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;     // over (tap, phase, co, ci), ci fastest
+    if (i >= (int64_t)36 * Cin * Cout) return;
+    const int ci = (int)(i % Cin);
+    int64_t rest = i / Cin;
+    const int co = (int)(rest % Cout);
+    rest /= Cout;
+    const int ph = (int)(rest & 3), tap = (int)(rest >> 2);
+    const int py = ph >> 1, px = ph & 1, dy = tap / 3 - 1, dx = tap % 3 - 1;
+    const float *wk = w + ((int64_t)co * Cin + ci) * 9;
+    float acc = 0.f;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const int a2 = py + a - 1 - 2 * dy;
+        if (a2 < 0 || a2 > 2) continue;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int b2 = px + b - 1 - 2 * dx;
+            if (b2 < 0 || b2 > 2) continue;
+            acc += kf.v[a * 4 + b] * wk[a2 * 3 + b2];
+        }
+    }
+    wp[((int64_t)tap * 4 * Cout + (int64_t)ph * Cout + co) * Cin + ci] = __float2bfloat16_rn(acc * scale);
+}
+
 // ToRGB weight fp32 [3,Cin] -> scaled fp32 [3][Cin]
 __global__ void pack_rgb_weight_kernel(float *__restrict__ out, const float *__restrict__ w, int n, float scale) {
     const int i = blockIdx.x * 256 + threadIdx.x;
@@ -299,6 +332,15 @@ int launch_pack_conv_weight(__nv_bfloat16 *wp, float *wsq, const float *w, int C
                             cudaStream_t st) {
     const int64_t n = (int64_t)Cin * Cout;
     pack_conv_weight_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(wp, wsq, w, Cin, Cout, kk, scale);
+    SG2_LAUNCH_CHECK();
+    return SG2_OK;
+}
+int launch_pack_upfused_weight(__nv_bfloat16 *wp, const float *w, int Cin, int Cout, float scale, const float *kf16_host,
+                               cudaStream_t st) {
+    Kf16 kf;
+    for (int i = 0; i < 16; ++i) kf.v[i] = kf16_host[i];
+    const int64_t n = (int64_t)36 * Cin * Cout;
+    pack_upfused_weight_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(wp, w, Cin, Cout, scale, kf);
     SG2_LAUNCH_CHECK();
     return SG2_OK;
 }

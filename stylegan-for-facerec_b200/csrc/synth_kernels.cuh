@@ -61,6 +61,9 @@ struct RgbParams {
 };
 
 int launch_pack_conv_weight(__nv_bfloat16 *wp, float *wsq, const float *w, int Cin, int Cout, int kk, float scale, cudaStream_t st);
+// fused up-sampling conv: composite (3x3 weights * 4x4 blur) polyphase weights, bf16 [9][4*Cout][Cin]; kf16_host = flipped taps
+int launch_pack_upfused_weight(__nv_bfloat16 *wp, const float *w, int Cin, int Cout, float scale, const float *kf16_host,
+                               cudaStream_t st);
 int launch_pack_rgb_weight(float *out, const float *w, int n, float scale, cudaStream_t st);
 int launch_styles(const StyleJobs &jobs, int total_blocks, const float *latent, int B, int n_latent, int style_dim, cudaStream_t st);
 int launch_demod(const DemodJobs &jobs, int max_cin, int max_cout, int B, cudaStream_t st);

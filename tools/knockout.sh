@@ -9,7 +9,7 @@ KO_LIB=stylegan-for-facerec_b200/csrc/libsg2_b200_ko.so
 export SG2_B200_LIB=$PWD/$KO_LIB
 run() { # name, env...
   name=$1; shift
-  env "$@" timeout 200 python bench.py --size $SIZE --batch $BATCH --no-cpu-baseline --no-extra --steps 5 --warmup 3 \
+  env SG2_BENCH_NO_PARITY=1 "$@" timeout 200 python bench.py --size $SIZE --batch $BATCH --no-cpu-baseline --no-extra --steps 5 --warmup 3 \
       --profile-out gpurun_out/ko/$name.json > gpurun_out/ko/$name.log 2>&1 || echo "FAILED $name"
 }
 run base X=0
