@@ -107,9 +107,16 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.12)
         self.proc.terminate()
-        rows = [r for t, r in self.rows if len(r) >= 9 and (t_begin is None or t >= t_begin) and (t_end is None or t <= t_end + 0.06)]
+        return self.summary(t_begin, t_end)
+
+    def summary(self, t_begin=None, t_end=None):
+        """clock record of the samples taken in [t_begin, t_end] (perf_counter times); the sampler keeps running"""
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvidia-smi unavailable"]}
+        allrows = list(self.rows)
+        rows = [r for t, r in allrows if len(r) >= 9 and (t_begin is None or t >= t_begin) and (t_end is None or t <= t_end + 0.06)]
         if not rows:                                   # region shorter than one sampling period: nearest rows
-            rows = [r for _, r in self.rows if len(r) >= 9][-3:]
+            rows = [r for t, r in allrows if len(r) >= 9 and (t_end is None or t <= t_end + 0.2)][-2:]
         sm = sorted(int(r[1]) for r in rows if r[1].isdigit())
         reasons = set()
         for r in rows:

@@ -48,6 +48,9 @@ struct Layer {
     // GEMM tiling (styled convs)
     int block_n = 0;
     bool two_sm = false;  // run this layer on the cta_group::2 kernel (synth_gemm2.cu)
+    bool dxs = false;        // narrow plain conv on the dx-stacked kernel (synth_gemm_dxs.cu)
+    DxsParams dp;
+    CUtensorMap tmDA, tmDB;
     bool fused_up = false;   // up-sampling layer run as ONE 3x3 conv with N = 4*Cout composite (weights * blur) columns, no FIR pass
     int n_gemm = 0;          // N of the GEMM: Cout, or 4*Cout for a fused up-sampling layer
     GemmParams gp;        // static part, pointers filled per forward
@@ -175,7 +178,7 @@ int plan_gemm(sg2_synth *S, Layer &L, const int *custom_taps = nullptr, int n_cu
     if (L.two_sm && fused && g.n_tiles_n == 1 && (!envr2 || atoi(envr2) != 0)) {
         const int half_b = 9 * g.kchunks * (best_n / 2) * g.block_k * 2;
         const int a_stage = kBlockM * g.block_k * 2 * g.kpack;
-        if (half_b + 4 * a_stage <= kStages * (kBlockM * kBlockK * 2 + kMaxBlockN * kBlockK * 2)) g.resident2 = 1;
+        if (half_b + 4 * a_stage <= kGemm2RingBytes) g.resident2 = 1;
     }
 
     // Resident weights (the narrow, high-resolution tail of the 512^2 / 1024^2 networks): when all 9*Cin*Cout
@@ -236,6 +239,32 @@ int plan_gemm(sg2_synth *S, Layer &L, const int *custom_taps = nullptr, int n_cu
             }
         }
     }
+    // Merged polyphase walk (synth_gemm2p.cu): the four planes of the transposed conv share one tile walk, one activation
+    // load per K chunk and a 2-CTA weight split.  Default: the Cout = 128 layer (256 -> 128 at 128^2 -> 256^2), which the
+    // separate-planes plan holds at 50 % tensor pipe with 2x the algorithmic DRAM traffic; SG2_POLY4=0 never, 2 = every
+    // transposed conv whose shape qualifies.
+    static const char *envp4 = getenv("SG2_POLY4");
+    const int p4mode = envp4 ? atoi(envp4) : 1;
+    g.poly4 = 0;
+    if (up && p4mode != 0 && cin % 64 == 0 && r >= 16 && (cout % 128 == 0 || cout == 64) && (p4mode == 2 || cout == 128)) {
+        g.poly4 = 1;
+        g.block_k = 64; g.kchunks = cin / 64; g.kpack = 1; g.resident = 0; g.mma2 = 0; g.resident2 = 0;
+        g.block_n = L.block_n = cout % 128 == 0 ? 128 : 64;
+        g.n_tiles_n = cout / g.block_n;
+        L.two_sm = true;
+        int j = 0;
+        for (int s = 3; s >= 0; --s) {
+            GemmSub &q = g.sub[s];
+            q.TH = 16; q.TW = 8; q.NB = 1;
+            for (int t = 0; t < q.ntaps; ++t, ++j) {
+                g.m_ph[j] = s;
+                g.m_aoff[j] = (q.dx[t] == 0 ? 0 : (16 + 1) * 8 * 128) + (q.dy[t] + 1) * 8 * 128;
+                g.m_wtap[j] = q.wtap[t];
+                g.m_first[j] = t == 0;
+                g.m_last[j] = t == q.ntaps - 1;
+            }
+        }
+    }
     // transposed conv: optionally walk the four polyphase sub-problems segment by segment so that their common input
     // stays in L2 (ncu: the phases re-read it from DRAM, 4x the algorithmic input bytes).  Measured: no gain at 256^2
     // (the layer is bound by L2->SM operand delivery, not DRAM) and a loss on the 1024^2 tail -> opt-in, SG2_GEMM_SEG=n.
@@ -274,8 +303,8 @@ int encode_maps(sg2_synth *S, Layer &L, const __nv_bfloat16 *x, const __nv_bfloa
         const GemmSub &q = L.gp.sub[s];
         cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)r, (cuuint64_t)r, (cuuint64_t)B};
         cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)r * C * 2, (cuuint64_t)r * r * C * 2};
-        cuuint32_t box[4] = {(cuuint32_t)L.gp.block_k, (cuuint32_t)q.TW, (cuuint32_t)(L.gp.resident ? q.slab_rows : q.TH),
-                             (cuuint32_t)q.NB};
+        cuuint32_t box[4] = {(cuuint32_t)L.gp.block_k, (cuuint32_t)q.TW,
+                             (cuuint32_t)(L.gp.poly4 ? q.TH + 1 : (L.gp.resident ? q.slab_rows : q.TH)), (cuuint32_t)q.NB};
         cuuint32_t es[4] = {1, 1, 1, 1};
         CUresult rc = enc(&L.tmA[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void *)x, dims, strides, box, es,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -293,6 +322,31 @@ int encode_maps(sg2_synth *S, Layer &L, const __nv_bfloat16 *x, const __nv_bfloa
                           CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         SG2_REQUIRE(rc == CUDA_SUCCESS, SG2_ERR_CUDA, "engine: cuTensorMapEncodeTiled(B) failed with %d", (int)rc);
+    }
+    return SG2_OK;
+}
+
+int encode_dxs_maps(Layer &L, const __nv_bfloat16 *x, const __nv_bfloat16 *wp, int B) {
+    EncodeTiledFn enc = get_encode();
+    SG2_REQUIRE(enc, SG2_ERR_CUDA, "engine: cuTensorMapEncodeTiled entry point not available");
+    const int C = L.p.cin, r = L.res_out, N = 3 * L.p.cout;
+    const CUtensorMapSwizzle swz = C == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)r, (cuuint64_t)r, (cuuint64_t)B};
+        cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)r * C * 2, (cuuint64_t)r * r * C * 2};
+        cuuint32_t box[4] = {(cuuint32_t)C, 32, 6, 1};
+        CUresult rc = enc(&L.tmDA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void *)x, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        SG2_REQUIRE(rc == CUDA_SUCCESS, SG2_ERR_CUDA, "engine: cuTensorMapEncodeTiled(dx-stacked A) failed with %d", (int)rc);
+    }
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)N, 3};
+        cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)C * N * 2};
+        cuuint32_t box[3] = {(cuuint32_t)C, (cuuint32_t)N, 1};
+        CUresult rc = enc(&L.tmDB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void *)wp, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        SG2_REQUIRE(rc == CUDA_SUCCESS, SG2_ERR_CUDA, "engine: cuTensorMapEncodeTiled(dx-stacked B) failed with %d", (int)rc);
     }
     return SG2_OK;
 }
@@ -416,13 +470,27 @@ extern "C" int sg2_synth_create(sg2_synth **plan, int size, int style_dim, int m
             int rc = plan_gemm(S, L);
             if (rc) { delete S; return rc; }
             finalize_tiles(L.gp, B);
+            // dx-stacked kernel for the narrowest plain conv (32 -> 32 at 1024^2): N = 3 * Cout, three activation views per
+            // tile instead of nine.  Measured (round 2, B = 32): 1.83 -> 1.45 ms at Cout = 32; at Cout = 64 the three-fold
+            // accumulator read-back costs what the saved operand reads gain (0.94 -> 0.98 ms), so that layer stays on the
+            // tap-by-tap kernel.  SG2_DXS=0: never, 2: also Cout = 64.
+            static const char *envx = getenv("SG2_DXS");
+            const int xmode = envx ? atoi(envx) : 1;
+            L.dxs = !L.p.upsample && xmode != 0 && (L.p.cin == 32 || L.p.cin == 64) &&
+                    (L.p.cout == 32 || (L.p.cout == 64 && xmode == 2)) && L.res_out >= 64;
+            if (L.dxs) {
+                memset(&L.dp, 0, sizeof(L.dp));
+                L.dp.R = L.res_out; L.dp.Cin = L.p.cin; L.dp.Cout = L.p.cout;
+                L.dp.tiles_x = (L.res_out + 29) / 30; L.dp.tiles_y = L.res_out / 4;
+                L.block_n = 3 * L.p.cout;
+            }
             prev_cout = L.p.cout;
             max_act = std::max(max_act, sizeof(__nv_bfloat16) * (size_t)B * L.res_in * L.res_in * L.p.cin);
             max_act = std::max(max_act, sizeof(__nv_bfloat16) * (size_t)B * L.res_out * L.res_out * L.p.cout);
             if (L.p.upsample && !L.fused_up)
                 max_T = std::max(max_T, sizeof(__nv_bfloat16) * 4 * (size_t)B * (L.res_in + 1) * (L.res_in + 1) * L.p.cout);
             else if (!L.p.upsample)
-                max_part = std::max(max_part, sizeof(float) * 2 * (size_t)L.gp.n_tiles_n * B * 3 * L.res_out * L.res_out);
+                max_part = std::max(max_part, sizeof(float) * (L.two_sm ? kGemm2EpiGroups : 2) * (size_t)L.gp.n_tiles_n * B * 3 * L.res_out * L.res_out);
         }
         S->layers.push_back(L);
     }
@@ -451,7 +519,7 @@ extern "C" int sg2_synth_create(sg2_synth **plan, int size, int style_dim, int m
         const Layer &L = S->layers[i];
         char name[64];
         snprintf(name, sizeof(name), "L%zu_%dx%d_%d->%d%s", i, L.res_out, L.res_out, L.p.cin, L.p.cout,
-                 L.p.upsample ? (L.fused_up ? "_upfused" : "_up") : "");
+                 L.p.upsample ? (L.fused_up ? "_upfused" : "_up") : (L.dxs ? "_dxs" : ""));
         const double px_in = (double)L.res_in * L.res_in, px_out = (double)L.res_out * L.res_out;
         if (L.rgb) {
             add("rgb_combine", name, 2.0 * 3 * L.p.cin * px_out, 0, 0, 0);
@@ -464,7 +532,7 @@ extern "C" int sg2_synth_create(sg2_synth **plan, int size, int style_dim, int m
             const bool last = i + 2 >= S->layers.size();
             const double out_b = (L.p.upsample && !L.fused_up) ? 2.0 * (2 * L.res_in + 1.0) * (2 * L.res_in + 1.0) * L.p.cout
                                                                : (last ? 4.0 * 3 * px_out : 2.0 * px_out * L.p.cout);
-            add("gemm", name, fl, 2.0 * px_in * L.p.cin + out_b, L.gp.total_tiles, L.block_n);
+            add("gemm", name, fl, 2.0 * px_in * L.p.cin + out_b, L.dxs ? L.dp.tiles_x * L.dp.tiles_y * B : L.gp.total_tiles, L.block_n);
             if (L.p.upsample && !L.fused_up) add("upfir", name, 0, 2.0 * ((2 * L.res_in + 1.0) * (2 * L.res_in + 1.0) + px_out) * L.p.cout, 0, 0);
         }
     }
@@ -548,7 +616,8 @@ extern "C" int sg2_synth_forward(sg2_synth *S, void *workspace, const float *lat
             finalize_tiles(L.gp, B);
             const __nv_bfloat16 *x = L.p.upsample ? act[1] : act[0];   // conv out -> act[1]; upfir out -> act[0]
             (void)cur;
-            int rc = encode_maps(S, L, x, (const __nv_bfloat16 *)(ws + L.wp), B);
+            int rc = L.dxs ? encode_dxs_maps(L, x, (const __nv_bfloat16 *)(ws + L.wp), B)
+                           : encode_maps(S, L, x, (const __nv_bfloat16 *)(ws + L.wp), B);
             if (rc) return rc;
             if (L.p.upsample && !L.fused_up) {
                 rc = encode_fir_maps(L, Tbuf, act[0], B);
@@ -628,6 +697,36 @@ extern "C" int sg2_synth_forward(sg2_synth *S, void *workspace, const float *lat
             rc = L.two_sm ? launch_modconv_gemm2(g, L.tmA, L.tmB, S->sms, st) : launch_modconv_gemm(g, L.tmA, L.tmB, S->sms, st);
             if (rc) return rc;
             if ((rc = rec(S, st, "gemm(upfused)"))) return rc;
+        } else if (L.dxs) {
+            DxsParams d = L.dp;
+            d.B = B; d.total_tiles = d.tiles_x * d.tiles_y * B;
+            d.demod = (const float *)(ws + L.demod);
+            d.noise = nz; d.noise_bstride = nzs; d.noise_weight = L.p.noise_weight;
+            d.bias = L.p.act_bias;
+            d.next_style = next_conv ? (const float *)(ws + next_conv->style) : nullptr;
+            d.out = next_conv ? act[1] : nullptr;
+            if (rgb) {
+                d.rgb_w = (const float *)(ws + rgb->rgbw);
+                d.rgb_style = (const float *)(ws + rgb->style);
+                d.rgb_part = part;
+            }
+            rc = launch_modconv_dxs(d, L.tmDA, L.tmDB, S->sms, st);
+            if (rc) return rc;
+            if ((rc = rec(S, st, "gemm(dx-stacked)"))) return rc;
+            if (rgb) {
+                RgbParams rp;
+                const bool last = next_conv == nullptr;
+                const int dst = rgb_cur == 0 ? 1 : 0;
+                rp.out = last ? image : rgbbuf[dst];
+                rp.part = part; rp.n_parts = 3 * L.p.cout <= 128 ? 1 : 2; rp.bias = rgb->p.act_bias;
+                rp.prev = rgb_cur >= 0 ? rgbbuf[rgb_cur] : nullptr;
+                rp.B = B; rp.R = L.res_out;
+                memcpy(rp.kf, S->kf, sizeof(rp.kf));
+                rc = launch_rgb_combine(rp, S->sms, st);
+                if (rc) return rc;
+                if ((rc = rec(S, st, "rgb_combine"))) return rc;
+                rgb_cur = dst;
+            }
         } else if (!L.p.upsample) {
             g.noise = nz; g.noise_bstride = nzs; g.noise_weight = L.p.noise_weight;
             g.bias = L.p.act_bias;
@@ -646,7 +745,9 @@ extern "C" int sg2_synth_forward(sg2_synth *S, void *workspace, const float *lat
                 const bool last = next_conv == nullptr;
                 const int dst = rgb_cur == 0 ? 1 : 0;
                 rp.out = last ? image : rgbbuf[dst];
-                rp.part = part; rp.n_parts = (g.epi_alt ? 1 : 2) * g.n_tiles_n; rp.bias = rgb->p.act_bias;
+                // partial ToRGB planes per N tile: the cta_group::2 kernel has 4 column groups, the single-CTA one 2 (or 1)
+                const int parts_per_tile = L.two_sm ? std::min(kGemm2EpiGroups, g.block_n / 32) : (g.epi_alt ? 1 : 2);
+                rp.part = part; rp.n_parts = parts_per_tile * g.n_tiles_n; rp.bias = rgb->p.act_bias;
                 rp.prev = rgb_cur >= 0 ? rgbbuf[rgb_cur] : nullptr;
                 rp.B = B; rp.R = L.res_out;
                 memcpy(rp.kf, S->kf, sizeof(rp.kf));
@@ -660,7 +761,8 @@ extern "C" int sg2_synth_forward(sg2_synth *S, void *workspace, const float *lat
             const long long plane = (long long)B * (L.res_in + 1) * (L.res_in + 1) * L.p.cout;
             for (int s = 0; s < g.nsub; ++s) g.sub[s].out_off = plane * s;
             g.out = Tbuf;
-            rc = L.two_sm ? launch_modconv_gemm2(g, L.tmA, L.tmB, S->sms, st) : launch_modconv_gemm(g, L.tmA, L.tmB, S->sms, st);
+            rc = g.poly4 ? launch_modconv_gemm2_poly4(g, L.tmA[0], L.tmB, S->sms, st)
+                         : (L.two_sm ? launch_modconv_gemm2(g, L.tmA, L.tmB, S->sms, st) : launch_modconv_gemm(g, L.tmA, L.tmB, S->sms, st));
             if (rc) return rc;
             if ((rc = rec(S, st, "gemm(up)"))) return rc;
             SG2_REQUIRE(next_conv, SG2_ERR_BAD_ARG, "engine: up-sampling conv without a consumer");
@@ -757,6 +859,7 @@ int run_single_conv(void *out, const void *x, const void *wp, const float *scale
         const long long plane = (long long)B * (r + 1) * (r + 1) * cout;
         for (int s = 0; s < g.nsub; ++s) g.sub[s].out_off = plane * s;
     }
+    if (g.poly4) return launch_modconv_gemm2_poly4(g, L.tmA[0], L.tmB, S.sms, as_stream(stream));
     return L.two_sm ? launch_modconv_gemm2(g, L.tmA, L.tmB, S.sms, as_stream(stream))
                     : launch_modconv_gemm(g, L.tmA, L.tmB, S.sms, as_stream(stream));
 }

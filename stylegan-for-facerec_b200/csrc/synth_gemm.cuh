@@ -12,6 +12,9 @@ constexpr int kBlockM = 128;      // pixels per tile = TMEM lanes
 constexpr int kBlockK = 64;       // bf16 channels per stage = one 128-byte swizzle row
 constexpr int kStages = 4;
 constexpr int kMaxBlockN = 256;
+constexpr int kGemm2RingBytes = 176 * 1024;  // operand ring of the cta_group::2 kernel (5 stages of 16 + 16 KiB at N = 256)
+constexpr int kGemm2EpiGroups = 4;           // cta_group::2 kernel: column groups of the epilogue (16 warps = 4 per TMEM lane quarter);
+                                             // a tile writes min(4, BLOCK_N / 32) partial ToRGB planes
 constexpr int kGemmRingBytes = 196 * 1024;   // operand ring of the single-CTA kernel (4 stages of 16 + 32 KiB at N = 256; the
                                              // 128->64 up-conv of the 1024^2 tail: 144 KiB resident weights + 3 x 17 KiB stages)
 
@@ -60,7 +63,12 @@ struct GemmParams {
     // whose epilogue writes column block (py, px) of input pixel (y, x) to output pixel (2y+py, 2x+px): no (2r+1)^2
     // intermediate, no FIR pass.  4x the tensor FLOPs of the polyphase form -- used where the layer is bandwidth-bound.
     int up4;
-    int cout_real;                  // channels of the output tensor (= Cout / 4 when up4, else Cout)
+    int cout_real;
+    // Merged polyphase walk of the transposed conv (synth_gemm2p.cu): one tile walk serves the four planes; the nine taps
+    // in issue order (plane 3, 2, 1, 0): plane, byte offset of the tap's A operand inside the two-slab activation stage,
+    // weight tap, first / last tap of its plane
+    int poly4;
+    int m_ph[kGemmMaxTaps], m_aoff[kGemmMaxTaps], m_wtap[kGemmMaxTaps], m_first[kGemmMaxTaps], m_last[kGemmMaxTaps];                  // channels of the output tensor (= Cout / 4 when up4, else Cout)
     int dbg;                        // SG2_GEMM_DBG knock-outs for bottleneck analysis (results WRONG when set): 1 no stores, 2 no A loads, 4 no B loads, 8 one MMA per stage
     // epilogue
     int mode;                       // 0: styled conv (noise, bias, lrelu, next-style, ToRGB); 1: plain scaled store
@@ -81,5 +89,26 @@ int launch_modconv_gemm(const GemmParams &p, const CUtensorMap *tmA /*[nsub]*/, 
 // cta_group::2 variant (synth_gemm2.cu): tmB must have box rows = block_n / 2
 int launch_modconv_gemm2(const GemmParams &p, const CUtensorMap *tmA /*[nsub]*/, const CUtensorMap &tmB,
                          int sm_count, cudaStream_t st);
+
+// dx-stacked narrow styled conv (synth_gemm_dxs.cu): Cin, Cout in {32, 64}, one K chunk, N = 3 * Cout
+struct DxsParams {
+    int B, R, Cin, Cout;
+    int tiles_x, tiles_y, total_tiles;       // tiles of 4 rows x 30 output columns (32 input columns)
+    const float *demod;                      // [B, Cout]
+    const float *noise;                      // [B or 1, R*R] fp32 or null
+    long long noise_bstride;
+    const float *noise_weight;               // [1]
+    const float *bias;                       // [Cout]
+    const float *next_style;                 // [B, Cout] or null (no activation store)
+    const float *rgb_w;                      // [3, Cout] or null
+    const float *rgb_style;                  // [B, Cout]
+    float *rgb_part;                         // [col_groups][B, 3, R, R], col_groups = 1 (Cout = 32) or 2 (Cout = 64)
+    __nv_bfloat16 *out;                      // NHWC bf16 or null
+};
+// tmA: NHWC activations, box {Cin, 32, 6, 1}; tmB: weights [3][3*Cout][Cin] (= the packed [tap][Cout][Cin] layout), box {Cin, 3*Cout, 1}
+int launch_modconv_dxs(const DxsParams &p, const CUtensorMap &tmA, const CUtensorMap &tmB, int sm_count, cudaStream_t st);
+
+// merged polyphase walk on cta_group::2 (synth_gemm2p.cu): tmA box = {64, 8, 17, 1}, tmB box rows = block_n / 2
+int launch_modconv_gemm2_poly4(const GemmParams &p, const CUtensorMap &tmA, const CUtensorMap &tmB, int sm_count, cudaStream_t st);
 
 }  // namespace sg2

@@ -44,8 +44,12 @@ namespace sg2 {
 
 using namespace tc;
 
-constexpr int kEpiWarps2 = 8;
-constexpr int kGemmThreads2 = 64 + 32 * kEpiWarps2;   // TMA warp + MMA warp + epilogue warps
+// 16 epilogue warps, four per TMEM lane quarter: the epilogue is a chain of dependent latencies (tcgen05.ld -> table
+// loads -> math -> staging -> store) and with 8 warps it, not the tensor pipe, paced every layer with N <= 128 and the
+// fused up-sampling convs (knock-out runs, round 2: -10 .. -45 % with the epilogue removed)
+constexpr int kEpiWarps2 = 4 * kGemm2EpiGroups;
+constexpr int kEpiThreads2 = 32 * kEpiWarps2;
+constexpr int kGemmThreads2 = 64 + kEpiThreads2;      // TMA warp + MMA warp + epilogue warps
 constexpr int kABytes2 = kBlockM * kBlockK * 2;          // 16 KiB
 constexpr int kBBytesMax2 = kMaxBlockN * kBlockK * 2;    // 32 KiB
 constexpr int kEpiCap2 = 512;                            // NB * BLOCK_N entries of per-sample epilogue params
@@ -53,7 +57,7 @@ constexpr float kSlope2 = 0.2f;
 // The operand ring is one byte array cut into stages of (16 KiB A + BLOCK_N*128 B of B): narrow
 // BLOCK_N means short MMAs per stage, so more stages are needed to cover the TMA latency
 // (4 stages at N=256, 6 at N=128, 8 at N<=64).
-constexpr int kRingBytes2 = kStages * (kABytes2 + kBBytesMax2);   // 192 KiB
+constexpr int kRingBytes2 = kGemm2RingBytes;
 constexpr int kMaxStages2 = 8;
 
 struct __align__(1024) Gemm2Smem {
@@ -278,9 +282,9 @@ modconv_gemm2_kernel(const __grid_constant__ GemmParams p, const __grid_constant
         // warp (2 + 4h + i) may access TMEM lanes 32*((2+i)&3) ..; the two warps of a quarter split the
         // accumulator columns in alternating 32-column chunks (h = 0: even chunks, h = 1: odd chunks).
         const int q = warp & 3;
-        const int half = (warp - 2) >> 2;
+        const int half = (warp - 2) >> 2;            // column group 0..3: this warp takes the 32-column chunks half, half + 4, ...
         const int m = q * 32 + lane;                 // accumulator row = pixel of the tile
-        const int et = threadIdx.x - 64;             // 0..255 within the epilogue group
+        const int et = threadIdx.x - 64;             // 0..511 within the epilogue group
         const float nw = (p.mode == 0 && p.noise) ? __ldg(p.noise_weight) : 0.f;
         const int N = p.block_n;
         const bool up4 = p.up4 != 0;
@@ -315,8 +319,8 @@ modconv_gemm2_kernel(const __grid_constant__ GemmParams p, const __grid_constant
                 // ---- stage the per-(sample, channel) epilogue parameters when they change ----
                 const int key = (t.b0 * kMaxBlockN + t.nt) * 16 + g.NB;
                 if (key != staged_key) {
-                    asm volatile("bar.sync 1, 256;" ::: "memory");
-                    for (int i = et; i < g.NB * N; i += 256) {
+                    asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads2) : "memory");
+                    for (int i = et; i < g.NB * N; i += kEpiThreads2) {
                         const int sb = i / N, col = i - sb * N;
                         const int bb = t.b0 + sb < p.B ? t.b0 + sb : p.B - 1;
                         // up4: the four phase blocks of a tile share the per-channel tables
@@ -334,8 +338,8 @@ modconv_gemm2_kernel(const __grid_constant__ GemmParams p, const __grid_constant
                         }
                     }
                     if (p.mode == 0)
-                        for (int i = et; i < N; i += 256) sm.e_bias[i] = __ldg(p.bias + (up4 ? (n0 + i) % cr : n0 + i));
-                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                        for (int i = et; i < N; i += kEpiThreads2) sm.e_bias[i] = __ldg(p.bias + (up4 ? (n0 + i) % cr : n0 + i));
+                    asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads2) : "memory");
                     staged_key = key;
                 }
                 nz *= nw; nz1 *= nw; nz2 *= nw; nz3 *= nw;
@@ -348,11 +352,18 @@ modconv_gemm2_kernel(const __grid_constant__ GemmParams p, const __grid_constant
                 tc_fence_after();
                 float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
                 const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kMaxBlockN;
-                for (int c0 = 32 * half; c0 < N; c0 += 64) {
+                bool handed_back = false;
+                for (int c0 = 32 * half; c0 < N; c0 += 32 * kGemm2EpiGroups) {
                     if (SG2_DBG(p) & 16) break;            // knock-out: no epilogue work at all
                     uint32_t r[32];
                     tmem_ld32(t_row + c0, r);
                     tmem_ld_wait();
+                    if (c0 + 32 * kGemm2EpiGroups >= N) {   // this warp's last TMEM read of the tile: the accumulator goes back to
+                        tc_fence_before();                  // the MMA thread BEFORE the math and the stores, not after them
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_leader(&sm.tmem_empty[acc]);   // the leader's MMA thread waits for both CTAs
+                        handed_back = true;
+                    }
                     uint32_t packed[16];
                     uint32_t o16 = off16 == 0xffffffffu ? off16 : off16 + (uint32_t)(c0 >> 3);
                     float nzc = nz;
@@ -397,12 +408,15 @@ modconv_gemm2_kernel(const __grid_constant__ GemmParams p, const __grid_constant
                     if (p.out)
                         store_rows64_coalesced(smem_u32(sm.stg[warp - 2]), packed, o16, reinterpret_cast<uint8_t *>(p.out), lane);
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_leader(&sm.tmem_empty[acc]);   // the leader's MMA thread waits for both CTAs
-                if (valid && p.mode == 0 && p.rgb_w) {   // each column half writes its own partial plane
+                if (!handed_back) {                         // a warp without a chunk of this tile (N < 128)
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_leader(&sm.tmem_empty[acc]);
+                }
+                const int parts = N >= 32 * kGemm2EpiGroups ? kGemm2EpiGroups : N / 32;   // column groups that own a chunk
+                if (valid && p.mode == 0 && p.rgb_w && half < parts) {   // each column group writes its own partial plane
                     const long long plane = (long long)g.PH * g.PW;
-                    float *rp = p.rgb_part + ((((long long)t.nt * 2 + half) * p.B + b) * 3) * plane + (long long)y * g.PW + x;
+                    float *rp = p.rgb_part + ((((long long)t.nt * parts + half) * p.B + b) * 3) * plane + (long long)y * g.PW + x;
                     rp[0] = rgb0;
                     rp[plane] = rgb1;
                     rp[2 * plane] = rgb2;

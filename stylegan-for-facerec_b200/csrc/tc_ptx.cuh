@@ -131,9 +131,14 @@ __device__ __forceinline__ void tma_load_4d_2sm(uint32_t dst, const CUtensorMap 
         "r"(c3)
         : "memory");
 }
-// arrive on the barrier at this offset in the leader CTA (local arrive when executed by the leader)
+// arrive on the barrier at this offset in the leader CTA (local arrive when executed by the leader).
+// RELAXED on purpose: the default .release.cluster compiles to MEMBAR.ALL.GPU + ERRBAR, i.e. the epilogue warp waits until
+// every global store of the tile it has just written is visible GPU-wide before it may hand the accumulator back (ncu,
+// round 2: the top stall of every cta_group::2 launch, 13 % of all samples on the fused up-sampling conv).  The only
+// thing the arrive has to order is this warp's TMEM reads against the next tile's MMAs, and that is what
+// tcgen05.wait::ld + tcgen05.fence::before_thread_sync (issued by the caller) are for.
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
 }
 __device__ __forceinline__ void tmem_alloc_2sm(uint32_t *dst_smem, uint32_t ncols) {   // one warp in EACH CTA of the pair
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
