@@ -216,6 +216,20 @@ int sg2_synth_forward(sg2_synth *plan, void *workspace, const float *latent, int
                       const float *const *noise, const int64_t *noise_bstride, float *image,
                       sg2_stream_t stream);
 
+/* Training mode of the plan (the frozen decoder inside the ReStyle / pSp fine-tuning step,
+ * coach_restyle_psp.py:138-168; autograd of model.py:232-359 w.r.t. the styles).
+ * sg2_synth_enable_training: call right after sg2_synth_create, before sg2_synth_workspace_bytes / sg2_synth_pack; the
+ *   workspace grows by one kept NHWC bf16 activation per styled conv, the adjoint weight packs and reduction scratch, and
+ *   sg2_synth_forward then keeps every layer's output instead of recycling two buffers.
+ * sg2_synth_backward: dL/d(style) of every plan row from grad_image [B,3,size,size] fp32.  Must follow the
+ *   sg2_synth_forward of the same batch on the same workspace.  grad_styles (fp32, overwritten): row r of the layer table at
+ *   offset B * sum_{rows before r} cin, shape [B, cin_r]; the caller maps it to dL/d(latent) through the modulation
+ *   weights (EqualLinear, model.py:152-155).  noise / noise_bstride as given to the forward call.  Noise maps and
+ *   parameters receive no gradient (frozen-decoder direction).                                                      */
+int sg2_synth_enable_training(sg2_synth *plan);
+int sg2_synth_backward(sg2_synth *plan, void *workspace, int64_t B, const float *const *noise, const int64_t *noise_bstride,
+                       const float *grad_image, float *grad_styles, sg2_stream_t stream);
+
 /* Optional per-kernel timing: the caller passes CUDA events it created (cudaEvent_t handles);
  * every forward records events[0] before the first launch and events[k] after the k-th launch, in
  * the order sg2_synth_describe lists them.  Pass NULL / 0 to switch it off.                     */

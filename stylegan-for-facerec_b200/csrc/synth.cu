@@ -12,75 +12,12 @@
 #include <string>
 #include <vector>
 
-#include "common.cuh"
-#include "synth_gemm.cuh"
-#include "synth_kernels.cuh"
-#include "tc_ptx.cuh"
+#include "synth_plan.cuh"
 
 using namespace sg2;
+using namespace sg2plan;
 
-namespace {
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode() {
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void *p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(p);
-    }
-    return fn;
-}
-
-size_t align_up(size_t v, size_t a = 1024) { return (v + a - 1) / a * a; }
-
-struct Layer {
-    sg2_conv_params p;
-    bool rgb;
-    int res_in, res_out;
-    // workspace offsets (bytes)
-    size_t wp = 0, wsq = 0, rgbw = 0, style = 0, demod = 0;
-    // GEMM tiling (styled convs)
-    int block_n = 0;
-    bool two_sm = false;  // run this layer on the cta_group::2 kernel (synth_gemm2.cu)
-    bool dxs = false;        // narrow plain conv on the dx-stacked kernel (synth_gemm_dxs.cu)
-    DxsParams dp;
-    CUtensorMap tmDA, tmDB;
-    bool fused_up = false;   // up-sampling layer run as ONE 3x3 conv with N = 4*Cout composite (weights * blur) columns, no FIR pass
-    int n_gemm = 0;          // N of the GEMM: Cout, or 4*Cout for a fused up-sampling layer
-    GemmParams gp;        // static part, pointers filled per forward
-    CUtensorMap tmA[kGemmMaxSub], tmB;
-    CUtensorMap tmT[4];   // up-sampling layers: the 4 polyphase planes as the FIR kernel reads them
-    CUtensorMap tmO;      // ... and its output [B][2r][2r][C] as the TMA store writes it (box 64 ch x 8 x 16)
-};
-
-}  // namespace
-
-struct sg2_synth {
-    int size, style_dim, max_batch, log_size, n_latent, num_layers;
-    std::vector<Layer> layers;
-    const float *const_input;
-    float kf[16];                 // flipped blur taps (x4)
-    size_t off_act[2], off_T, off_rgb[2], off_part, off_toeplitz, ws_bytes;
-    std::vector<uint16_t> toeplitz;   // host copy of the FIR Toeplitz matrix (bf16 bits), uploaded by pack
-    CUtensorMap tmK;
-    bool fir_simt = false;
-    // descriptor cache
-    void *cached_ws = nullptr;
-    int cached_B = -1;
-    // profiling hooks
-    cudaEvent_t *events = nullptr;
-    int n_events = 0, events_used = 0;
-    std::string description;
-    int sms = 148;
-};
-
-namespace {
+namespace sg2plan {
 
 // choose the spatial tile of a PH x PW plane: TH*TW <= 128 with the fewest tiles, wide tiles preferred
 void choose_tile(int PH, int PW, int maxB, int &TH, int &TW, int &NB) {
@@ -100,7 +37,7 @@ void choose_tile(int PH, int PW, int maxB, int &TH, int &TW, int &NB) {
 }
 
 // custom_taps (plain convolutions only): n_custom rows of {dy, dx, weight tap index} instead of the 3x3 window
-int plan_gemm(sg2_synth *S, Layer &L, const int *custom_taps = nullptr, int n_custom = 0) {
+int plan_gemm(sg2_synth *S, Layer &L, const int *custom_taps, int n_custom, const int *tap_planes) {
     const int B = S->max_batch;
     GemmParams &g = L.gp;
     memset(&g, 0, sizeof(g));
@@ -121,8 +58,12 @@ int plan_gemm(sg2_synth *S, Layer &L, const int *custom_taps = nullptr, int n_cu
             q.PH = q.PW = r; q.out_H = q.out_W = fused ? 2 * r : r; q.out_off = 0;
             q.ntaps = 0;
             if (custom_taps) {
-                for (int t = 0; t < n_custom; ++t) { q.dy[t] = custom_taps[3 * t]; q.dx[t] = custom_taps[3 * t + 1]; q.wtap[t] = custom_taps[3 * t + 2]; }
+                for (int t = 0; t < n_custom; ++t) {
+                    q.dy[t] = custom_taps[3 * t]; q.dx[t] = custom_taps[3 * t + 1]; q.wtap[t] = custom_taps[3 * t + 2];
+                    q.tap_map[t] = tap_planes ? tap_planes[t] : 0;
+                }
                 q.ntaps = n_custom;
+                g.multi_map = tap_planes ? 1 : 0;
             } else {
                 for (int a = 0; a < 3; ++a)
                     for (int b = 0; b < 3; ++b) { q.dy[q.ntaps] = a - 1; q.dx[q.ntaps] = b - 1; q.wtap[q.ntaps] = a * 3 + b; ++q.ntaps; }
@@ -188,7 +129,7 @@ int plan_gemm(sg2_synth *S, Layer &L, const int *custom_taps = nullptr, int n_cu
     static const char *envr = getenv("SG2_GEMM_RESIDENT");
     bool nb1 = true;
     for (int s = 0; s < g.nsub; ++s) nb1 = nb1 && g.sub[s].NB == 1;
-    if ((!envr || atoi(envr) != 0) && !fused && g.n_tiles_n == 1 && nb1 && r >= 16 && cin % 32 == 0) {
+    if ((!envr || atoi(envr) != 0) && !fused && !tap_planes && g.n_tiles_n == 1 && nb1 && r >= 16 && cin % 32 == 0) {
         const int resb = 18 * cin * best_n;
         int pick_bk = 0, pick_stage = 0;
         for (int bk : {64, 32}) {
@@ -392,7 +333,7 @@ int encode_fir_maps(Layer &L, const __nv_bfloat16 *T, const __nv_bfloat16 *out, 
 
 // after every launch: optional timing event; with SG2_SYNTH_DEBUG=1 also a sync that names the
 // first failing kernel (debug only -- never set while capturing a CUDA graph)
-inline int rec(sg2_synth *S, cudaStream_t st, const char *what = "") {
+int rec(sg2_synth *S, cudaStream_t st, const char *what) {
     if (S->events && S->events_used < S->n_events) cudaEventRecord(S->events[S->events_used++], st);
     static const bool debug = getenv("SG2_SYNTH_DEBUG") != nullptr;
     if (debug) {
@@ -402,7 +343,7 @@ inline int rec(sg2_synth *S, cudaStream_t st, const char *what = "") {
     return SG2_OK;
 }
 
-}  // namespace
+}  // namespace sg2plan
 
 extern "C" int sg2_synth_create(sg2_synth **plan, int size, int style_dim, int max_batch,
                                 const sg2_conv_params *layers, int n_layers, const float *const_input,
@@ -587,7 +528,12 @@ extern "C" int sg2_synth_pack(sg2_synth *S, void *workspace, sg2_stream_t stream
         }
     }
     SG2_CUDA_OK(cudaMemcpyAsync(ws + S->off_toeplitz, S->toeplitz.data(), S->toeplitz.size() * 2, cudaMemcpyHostToDevice, st));
+    if (S->train) {
+        int rc = train_pack(S, ws, st);
+        if (rc) return rc;
+    }
     S->cached_ws = nullptr;   // descriptors are rebuilt by the next forward
+    S->bcached_ws = nullptr;
     return SG2_OK;
 }
 
@@ -608,19 +554,32 @@ extern "C" int sg2_synth_forward(sg2_synth *S, void *workspace, const float *lat
     float *part = (float *)(ws + S->off_part);
     S->events_used = 0;
 
+    // where every styled conv reads and writes.  Inference: two ping-pong buffers (plain conv act[0] -> act[1], up-sampling
+    // layer act[1] -> act[0]).  Training: every layer writes its own kept buffer, which the next layer reads.
+    const size_t nL = S->layers.size();
+    std::vector<__nv_bfloat16 *> inp(nL, nullptr), outp(nL, nullptr);
+    {
+        __nv_bfloat16 *prev = S->train ? (__nv_bfloat16 *)(ws + S->off_act_in) : act[0];
+        for (size_t i = 0; i < nL; ++i) {
+            Layer &L = S->layers[i];
+            if (L.rgb) continue;
+            if (S->train) { inp[i] = prev; outp[i] = (__nv_bfloat16 *)(ws + L.keep); prev = outp[i]; }
+            else { inp[i] = L.p.upsample ? act[1] : act[0]; outp[i] = L.p.upsample ? act[0] : act[1]; }
+        }
+    }
+    const float *ones = S->train ? (const float *)(ws + S->off_ones) : nullptr;
     // (re)build tile tables + TMA descriptors when the workspace or the batch changed
     if (S->cached_ws != workspace || S->cached_B != B) {
-        int cur = 0;   // buffer holding the input of the next styled conv (const -> act[0])
-        for (Layer &L : S->layers) {
+        for (size_t i = 0; i < nL; ++i) {
+            Layer &L = S->layers[i];
             if (L.rgb) continue;
             finalize_tiles(L.gp, B);
-            const __nv_bfloat16 *x = L.p.upsample ? act[1] : act[0];   // conv out -> act[1]; upfir out -> act[0]
-            (void)cur;
+            const __nv_bfloat16 *x = inp[i];
             int rc = L.dxs ? encode_dxs_maps(L, x, (const __nv_bfloat16 *)(ws + L.wp), B)
                            : encode_maps(S, L, x, (const __nv_bfloat16 *)(ws + L.wp), B);
             if (rc) return rc;
             if (L.p.upsample && !L.fused_up) {
-                rc = encode_fir_maps(L, Tbuf, act[0], B);
+                rc = encode_fir_maps(L, Tbuf, outp[i], B);
                 if (rc) return rc;
             }
         }
@@ -665,14 +624,13 @@ extern "C" int sg2_synth_forward(sg2_synth *S, void *workspace, const float *lat
     if ((rc = rec(S, st, "demod"))) return rc;
     // 2. constant input pre-modulated by conv1's style
     Layer &L0 = S->layers[0];
-    rc = launch_const_input(act[0], S->const_input, (const float *)(ws + L0.style), B, L0.p.cin, 16, st);
+    rc = launch_const_input(inp[0], S->const_input, (const float *)(ws + L0.style), B, L0.p.cin, 16, st);
     if (rc) return rc;
     if ((rc = rec(S, st, "const_input"))) return rc;
 
     // 3. the layers
     int noise_idx = 0;
     int rgb_cur = -1;      // which rgb buffer holds the running skip image (-1: none yet)
-    const size_t nL = S->layers.size();
     for (size_t i = 0; i < nL; ++i) {
         Layer &L = S->layers[i];
         if (L.rgb) continue;   // handled together with the conv that feeds it
@@ -693,7 +651,7 @@ extern "C" int sg2_synth_forward(sg2_synth *S, void *workspace, const float *lat
             g.noise = nz; g.noise_bstride = nzs; g.noise_weight = L.p.noise_weight;
             g.bias = L.p.act_bias;
             g.next_style = (const float *)(ws + next_conv->style);
-            g.out = act[0];
+            g.out = outp[i];
             rc = L.two_sm ? launch_modconv_gemm2(g, L.tmA, L.tmB, S->sms, st) : launch_modconv_gemm(g, L.tmA, L.tmB, S->sms, st);
             if (rc) return rc;
             if ((rc = rec(S, st, "gemm(upfused)"))) return rc;
@@ -703,8 +661,9 @@ extern "C" int sg2_synth_forward(sg2_synth *S, void *workspace, const float *lat
             d.demod = (const float *)(ws + L.demod);
             d.noise = nz; d.noise_bstride = nzs; d.noise_weight = L.p.noise_weight;
             d.bias = L.p.act_bias;
-            d.next_style = next_conv ? (const float *)(ws + next_conv->style) : nullptr;
-            d.out = next_conv ? act[1] : nullptr;
+            // (training keeps the last layer's activation too: stored with a unit "next style")
+            d.next_style = next_conv ? (const float *)(ws + next_conv->style) : ones;
+            d.out = (next_conv || S->train) ? outp[i] : nullptr;
             if (rgb) {
                 d.rgb_w = (const float *)(ws + rgb->rgbw);
                 d.rgb_style = (const float *)(ws + rgb->style);
@@ -730,8 +689,8 @@ extern "C" int sg2_synth_forward(sg2_synth *S, void *workspace, const float *lat
         } else if (!L.p.upsample) {
             g.noise = nz; g.noise_bstride = nzs; g.noise_weight = L.p.noise_weight;
             g.bias = L.p.act_bias;
-            g.next_style = next_conv ? (const float *)(ws + next_conv->style) : nullptr;
-            g.out = next_conv ? act[1] : nullptr;
+            g.next_style = next_conv ? (const float *)(ws + next_conv->style) : ones;
+            g.out = (next_conv || S->train) ? outp[i] : nullptr;
             if (rgb) {
                 g.rgb_w = (const float *)(ws + rgb->rgbw);
                 g.rgb_style = (const float *)(ws + rgb->style);
@@ -767,7 +726,7 @@ extern "C" int sg2_synth_forward(sg2_synth *S, void *workspace, const float *lat
             if ((rc = rec(S, st, "gemm(up)"))) return rc;
             SG2_REQUIRE(next_conv, SG2_ERR_BAD_ARG, "engine: up-sampling conv without a consumer");
             UpfirParams up;
-            up.T = Tbuf; up.plane_stride = plane; up.out = act[0]; up.r = L.res_in; up.C = L.p.cout;
+            up.T = Tbuf; up.plane_stride = plane; up.out = outp[i]; up.r = L.res_in; up.C = L.p.cout;
             up.noise = nz; up.noise_bstride = nzs; up.noise_weight = L.p.noise_weight;
             up.bias = L.p.act_bias; up.next_style = (const float *)(ws + next_conv->style);
             memcpy(up.kf, S->kf, sizeof(up.kf));
@@ -775,7 +734,7 @@ extern "C" int sg2_synth_forward(sg2_synth *S, void *workspace, const float *lat
                 rc = launch_upfir(up, B, st);
             } else {
                 UpfirTcParams tp;
-                tp.out = act[0]; tp.r = L.res_in; tp.C = L.p.cout; tp.B = B;
+                tp.out = outp[i]; tp.r = L.res_in; tp.C = L.p.cout; tp.B = B;
                 tp.cbw = L.p.cout % 64 == 0 ? 64 : 32;
                 tp.nsamp = L.p.cout % 128 == 0 ? 1 : 128 / L.p.cout;      // 64 channels: 2 samples per tile, 32: 4
                 tp.tiles_c = L.p.cout % 128 == 0 ? L.p.cout / 128 : 1;

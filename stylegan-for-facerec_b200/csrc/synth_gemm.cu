@@ -263,6 +263,10 @@ modconv_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant_
                             mbar_wait(&sm.empty[stage], phase ^ 1);
                             uint8_t *slot = sm.ring + stage * stage_bytes;
                             const int ax = t.x0 + g.dx[tap], ay = t.y0 + g.dy[tap], wt = g.wtap[tap];
+                            if (p.multi_map) {           // this tap's own activation tensor
+                                const int mi = g.tap_map[tap];
+                                tmA = mi == 0 ? &tmA0 : (mi == 1 ? &tmA1 : (mi == 2 ? &tmA2 : &tmA3));
+                            }
                             if (SG2_DBG(p) & 6) {       // bottleneck analysis only
                                 if (elect_one()) {
                                     const bool la = !(SG2_DBG(p) & 2), lb = !(SG2_DBG(p) & 4);
@@ -566,10 +570,12 @@ int launch_modconv_gemm(const GemmParams &p, const CUtensorMap *tmA, const CUten
         }
         q.nseg = (max_per + q.seg_tiles - 1) / q.seg_tiles;
     }
+    SG2_REQUIRE(!p.multi_map || (p.nsub == 1 && !p.resident), SG2_ERR_BAD_ARG, "gemm: a multi-tensor tap list needs one streamed sub-problem");
+    const int nmaps = p.multi_map ? 4 : p.nsub;
     const CUtensorMap &a0 = tmA[0];
-    const CUtensorMap &a1 = tmA[p.nsub > 1 ? 1 : 0];
-    const CUtensorMap &a2 = tmA[p.nsub > 2 ? 2 : 0];
-    const CUtensorMap &a3 = tmA[p.nsub > 3 ? 3 : 0];
+    const CUtensorMap &a1 = tmA[nmaps > 1 ? 1 : 0];
+    const CUtensorMap &a2 = tmA[nmaps > 2 ? 2 : 0];
+    const CUtensorMap &a3 = tmA[nmaps > 3 ? 3 : 0];
     modconv_gemm_kernel<<<grid, kGemmThreads, smem, st>>>(q, a0, a1, a2, a3, tmB);
     SG2_LAUNCH_CHECK();
     return SG2_OK;

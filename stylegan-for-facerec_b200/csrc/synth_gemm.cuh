@@ -27,6 +27,7 @@ struct GemmSub {
     int tile_begin;              // first global tile index of this sub-problem
     int ntaps;
     int dy[kGemmMaxTaps], dx[kGemmMaxTaps], wtap[kGemmMaxTaps];
+    int tap_map[kGemmMaxTaps];   // GemmParams::multi_map: which of the four activation tensor maps tap t reads (0..3)
     long long out_off;           // element offset of the plane inside `out`
     int out_H, out_W;            // allocated plane extent (row pitch = out_W * Cout)
     // resident-weights mode: the activation window of a tile is loaded ONCE per K chunk as `nslab`
@@ -62,6 +63,9 @@ struct GemmParams {
     // concatenated along N (column = (py*2 + px) * cout_real + co), so the layer is a plain 3x3 conv with N = 4*Cout
     // whose epilogue writes column block (py, px) of input pixel (y, x) to output pixel (2y+py, 2x+px): no (2r+1)^2
     // intermediate, no FIR pass.  4x the tensor FLOPs of the polyphase form -- used where the layer is bandwidth-bound.
+    // multi_map (nsub == 1): the taps of the one sub-problem read DIFFERENT tensors (tmA0..tmA3 chosen by GemmSub::tap_map) --
+    // the input gradient of the transposed conv, whose nine taps read the four polyphase planes of the output gradient
+    int multi_map;
     int up4;
     int cout_real;
     // Merged polyphase walk of the transposed conv (synth_gemm2p.cu): one tile walk serves the four planes; the nine taps

@@ -186,6 +186,10 @@ modconv_gemm2_kernel(const __grid_constant__ GemmParams p, const __grid_constant
                         mbar_wait(&sm.empty[stage], phase ^ 1);
                         const uint32_t slot = smem_u32(sm.ring) + ring_off + stage * stage_bytes;
                         const int ax = t.x0 + g.dx[tap], ay = t.y0 + g.dy[tap], wt = g.wtap[tap];
+                        if (p.multi_map) {                    // this tap's own activation tensor
+                            const int mi = g.tap_map[tap];
+                            tmA = mi == 0 ? &tmA0 : (mi == 1 ? &tmA1 : (mi == 2 ? &tmA2 : &tmA3));
+                        }
                         if (SG2_DBG(p) & 6) {                 // bottleneck analysis only (variant build)
                             if (elect_one()) {
                                 const bool la = !(SG2_DBG(p) & 2), lb = !(SG2_DBG(p) & 4) && !resident;
@@ -473,10 +477,12 @@ int launch_modconv_gemm2(const GemmParams &p, const CUtensorMap *tmA, const CUte
         }
         q.nseg = (int)((max_per + q.seg_tiles - 1) / q.seg_tiles);
     }
+    SG2_REQUIRE(!p.multi_map || p.nsub == 1, SG2_ERR_BAD_ARG, "gemm2: a multi-tensor tap list needs one sub-problem");
+    const int nmaps = p.multi_map ? 4 : p.nsub;
     const CUtensorMap &a0 = tmA[0];
-    const CUtensorMap &a1 = tmA[p.nsub > 1 ? 1 : 0];
-    const CUtensorMap &a2 = tmA[p.nsub > 2 ? 2 : 0];
-    const CUtensorMap &a3 = tmA[p.nsub > 3 ? 3 : 0];
+    const CUtensorMap &a1 = tmA[nmaps > 1 ? 1 : 0];
+    const CUtensorMap &a2 = tmA[nmaps > 2 ? 2 : 0];
+    const CUtensorMap &a3 = tmA[nmaps > 3 ? 3 : 0];
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * n_clusters);
     cfg.blockDim = dim3(kGemmThreads2);

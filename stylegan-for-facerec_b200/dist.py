@@ -112,6 +112,8 @@ class GradientAverager:
     def __init__(self, params, bucket_bytes: int = 64 << 20):
         self.params = [p for p in params if p.requires_grad]
         self.world = dist.get_world_size() if dist.is_initialized() else 1
+        # NCCL averages inside the collective (ReduceOp.AVG); gloo only sums
+        self._avg = self.world > 1 and dist.get_backend() == "nccl"
         self.buckets = []
         self._index = {}
         for group in _bucket_layout(list(reversed(self.params)), bucket_bytes):
@@ -157,29 +159,38 @@ class GradientAverager:
         if self._armed:
             b["pending"] -= 1
             if b["pending"] == 0 and self.world > 1 and b["work"] is None:
-                b["work"] = dist.all_reduce(b["flat"], op=dist.ReduceOp.SUM, async_op=True)
+                b["work"] = dist.all_reduce(b["flat"], op=self._op(), async_op=True)
+
+    def _op(self):
+        return dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM
 
     def finish(self) -> int:
         """-> number of collectives issued for this step"""
         n = 0
+        untouched_here = bool((self._touched == 0).any())
         if self.world > 1:
             for b in self.buckets:
                 if b["work"] is None:
-                    b["work"] = dist.all_reduce(b["flat"], op=dist.ReduceOp.SUM, async_op=True)
-            mask = self._touched.to(self.buckets[0]["flat"].device) if self.buckets else self._touched
+                    b["work"] = dist.all_reduce(b["flat"], op=self._op(), async_op=True)
+            # which parameters received a gradient on ANY rank: every rank takes part in the exchange, only a rank that
+            # has an untouched parameter itself reads the answer back (a host synchronisation the common case never pays)
+            mask = self._touched.to(self.buckets[0]["flat"].device, non_blocking=True) if self.buckets else self._touched
             mwork = dist.all_reduce(mask, op=dist.ReduceOp.MAX, async_op=True) if self.buckets else None
             for b in self.buckets:
                 b["work"].wait()
-                b["flat"].div_(self.world)
+                if not self._avg:
+                    b["flat"].div_(self.world)
                 b["work"] = None
                 n += 1
             if mwork is not None:
                 mwork.wait()
                 n += 1
-                self._touched = mask.cpu()
-        for p in self.params:
-            if self._touched[self._pos[id(p)]] == 0:
-                p.grad = None
+                if untouched_here:
+                    self._touched = mask.cpu()
+        if untouched_here:
+            for p in self.params:
+                if self._touched[self._pos[id(p)]] == 0:
+                    p.grad = None
         self._armed = False
         return n
 

@@ -19,9 +19,12 @@ from . import _lib
 
 
 class SynthesisEngine:
-    def __init__(self, generator, max_batch=8, use_graph=None):
+    def __init__(self, generator, max_batch=8, use_graph=None, training=False):
         self.G = generator
         self.lib = _lib.load()
+        self.training = bool(training)       # keep every layer's output and support `backward` (frozen decoder, dL/dlatent)
+        self._fwd_id = 0
+        self._mod = None
         self.plan = None
         self.max_batch = 0
         self.workspace = None
@@ -102,6 +105,10 @@ class SynthesisEngine:
                                              const, taps.numpy().ctypes.data_as(C.POINTER(C.c_float))),
                    "synth_create")
         self.plan, self.max_batch = plan, mb
+        if self.training:
+            _lib.check(self.lib.sg2_synth_enable_training(plan), "synth_enable_training")
+            self.use_graph = False
+        self._mod = None
         nbytes = self.lib.sg2_synth_workspace_bytes(plan)
         if self.workspace is None or self.workspace.numel() < nbytes or self.workspace.device != dev:
             self.workspace = torch.empty(nbytes, dtype=torch.uint8, device=dev)
@@ -249,6 +256,65 @@ class SynthesisEngine:
                 buf.copy_(n.detach().reshape(buf.shape))
                 src[i] = (weakref.ref(n), n._version)
 
+    # -- training: forward that keeps the activations + backward w.r.t. the latents ---------------
+    def _modulation_table(self):
+        """per plan row: (latent index, cin, W * scale [cin, style_dim]) -- the EqualLinear of every modulation
+        (model.py:152-155, 222), used to turn dL/dstyle into dL/dlatent"""
+        if self._mod is None:
+            G = self.G
+            rows = []
+
+            def add(conv, idx):
+                m = conv.modulation
+                rows.append((idx, conv.in_channel, (m.weight.detach().float() * m.scale).contiguous()))
+            add(G.conv1.conv, 0)
+            add(G.to_rgb1.conv, 1)
+            i = 1
+            for j in range(G.log_size - 2):
+                add(G.convs[2 * j].conv, i)
+                add(G.convs[2 * j + 1].conv, i + 1)
+                add(G.to_rgbs[j].conv, i + 2)
+                i += 2
+            self._mod = rows
+        return self._mod
+
+    def train_forward(self, latent, noise):
+        """-> (image fp32 [B,3,size,size], state for train_backward)"""
+        assert self.training
+        G = self.G
+        _lib.require_cuda(latent, "latent")
+        B = latent.shape[0]
+        self._ensure(B)
+        lat = latent.detach().float().contiguous()
+        ptrs, strides, keep = self._noise_args(B, noise, latent.device)
+        image = torch.empty(B, 3, G.size, G.size, device=latent.device, dtype=torch.float32)
+        self._call(lat, B, ptrs, strides, image)
+        self._fwd_id += 1
+        return image, (self._fwd_id, B, ptrs, strides, keep)
+
+    def train_backward(self, state, grad_image):
+        """dL/dlatent [B, n_latent, style_dim] fp32 from dL/dimage; the forward that produced `state` must be the last
+        one this engine ran (the kept activations are overwritten by the next forward)"""
+        fwd_id, B, ptrs, strides, keep = state
+        if fwd_id != self._fwd_id:
+            raise RuntimeError("sg2_b200 training engine: another forward pass ran on this Generator before backward(); "
+                               "the kept activations are gone.  Call backward() after each forward (as the ReStyle "
+                               "coaches do), or set SG2_B200_TRAIN_ENGINE=0 to use the autograd path")
+        G = self.G
+        g = grad_image.detach().float().contiguous()
+        mod = self._modulation_table()
+        total = B * sum(cin for _, cin, _ in mod)
+        gs = torch.empty(total, device=g.device, dtype=torch.float32)
+        with _lib.device_of(g):
+            _lib.check(self.lib.sg2_synth_backward(self.plan, self.workspace.data_ptr(), B, ptrs, strides, g.data_ptr(),
+                                                   gs.data_ptr(), _lib.stream_of(g)), "synth_backward")
+        acc = torch.zeros(G.n_latent, B, G.style_dim, device=g.device, dtype=torch.float32)
+        off = 0
+        for idx, cin, w in mod:
+            acc[idx].addmm_(gs[off:off + B * cin].view(B, cin), w)
+            off += B * cin
+        return acc.permute(1, 0, 2).contiguous()
+
     def __reduce__(self):
         raise TypeError("SynthesisEngine holds device handles and cannot be pickled; copy the Generator instead "
                         "(its copies re-plan lazily)")
@@ -259,3 +325,21 @@ class SynthesisEngine:
                 self.lib.sg2_synth_destroy(self.plan)
         except Exception:
             pass
+
+
+class SynthesisFunction(torch.autograd.Function):
+    """The frozen decoder as ONE autograd node: forward = the engine's launch plan (activations kept), backward = the
+    plan walked in reverse (csrc/synth_train.cu).  Gradient flows to `latent` only."""
+
+    @staticmethod
+    def forward(ctx, latent, engine, noise):
+        image, state = engine.train_forward(latent, noise)
+        ctx.engine, ctx.state = engine, state
+        ctx.lat_dtype = latent.dtype
+        return image
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_image):
+        g = ctx.engine.train_backward(ctx.state, grad_image)
+        return g.to(ctx.lat_dtype), None, None

@@ -394,11 +394,13 @@ class Generator(nn.Module):
     def __getstate__(self):
         state = dict(self.__dict__)
         state['_engine'] = None
+        state.pop('_train_engine', None)
         return state
 
     def _replicate_for_data_parallel(self):
         replica = super()._replicate_for_data_parallel()
         replica.__dict__['_engine'] = None
+        replica.__dict__.pop('_train_engine', None)
         replica.__dict__['_transient_engine'] = True
         return replica
 
@@ -408,6 +410,7 @@ class Generator(nn.Module):
         `.to()` are detected automatically (tensor version counter / storage address); an in-place write through `.data`
         bumps neither, so code that updates weights that way (rosinality-style EMA `accumulate()`) must call this."""
         self._engine = None
+        self.__dict__.pop('_train_engine', None)
         for m in self.modules():
             m.__dict__.pop('_tc_cache', None)
 
@@ -436,6 +439,28 @@ class Generator(nn.Module):
         if mode == 'bf16':
             return True
         return mode == 'auto' and self.input.input.dtype == torch.bfloat16
+
+    def _use_train_engine(self, latent, noise, return_features):
+        """the frozen-decoder fine-tuning direction (coach_restyle_psp.py:138-168): gradient w.r.t. the latents only"""
+        if self.precision != 'bf16' or return_features or not latent.is_cuda or not torch.is_grad_enabled():
+            return False
+        if os.environ.get('SG2_B200_TRAIN_ENGINE', '1') == '0' or not latent.requires_grad:
+            return False
+        if any(p.requires_grad for p in self.parameters()) or any(n is not None and n.requires_grad for n in noise):
+            return False
+        if self.input.input.dtype != torch.float32 or self.style_dim % 32 or self.size < 8:
+            return False
+        chans = [self.channels[2 ** i] for i in range(2, self.log_size + 1)]
+        return all(c >= 32 and c <= 512 and (c & (c - 1)) == 0 for c in chans) and list(self._blur_kernel) == [1, 3, 3, 1]
+
+    def train_engine(self):
+        dev = self.input.input.device
+        te = self.__dict__.get('_train_engine')
+        if te is None or te.device != dev:
+            from ..engine import SynthesisEngine
+            te = SynthesisEngine(self, training=True, use_graph=False)
+            self.__dict__['_train_engine'] = te
+        return te
 
     def engine(self):
         """The whole-network bf16 tcgen05 engine bound to this module's parameters (lazy, one per device: moving the
@@ -472,6 +497,10 @@ class Generator(nn.Module):
 
         if self._use_engine(latent, noise, return_features):
             image = self.engine().synthesize(latent, noise)
+            return (image, latent) if return_latents else (image, None)
+        if self._use_train_engine(latent, noise, return_features):
+            from ..engine import SynthesisFunction
+            image = SynthesisFunction.apply(latent, self.train_engine(), noise)
             return (image, latent) if return_latents else (image, None)
 
         # precision == 'bf16' with gradients: the 3x3 stride-1 convolutions of the differentiable path (forward and

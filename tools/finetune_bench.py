@@ -145,7 +145,7 @@ def main():
         t = torch.tensor([e0.elapsed_time(e1) / K, sum(s.elapsed_time(e) for s, e in tails) / K], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t[0]), float(t[1]), n, float(loss)
+        return float(t[0]), float(t[1]), n, float(loss.detach())
 
     ms_ov, tail_ov, n_coll, loss_ov = timed(True)
     ms_blk, tail_blk, _, _ = timed(False)

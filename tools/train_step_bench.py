@@ -34,8 +34,11 @@ def main():
         p.requires_grad_(False)
     lat = torch.randn(a.batch, n_latent, 512, device=dev)
     gy = torch.randn(a.batch, 3, a.size, a.size, device=dev)
-    for mode in ("exact", "bf16"):
-        G.precision = mode
+    # "bf16": the training engine (one autograd node, csrc/synth_train.cu) where it applies, else the layer-by-layer
+    # tensor-core route; "bf16-layerwise" forces the latter (SG2_B200_TRAIN_ENGINE=0)
+    for mode in ("exact", "bf16-layerwise", "bf16"):
+        G.precision = mode.split("-")[0]
+        os.environ["SG2_B200_TRAIN_ENGINE"] = "0" if mode == "bf16-layerwise" else "1"
         times = []
         for it in range(3 + a.iters):
             ld = lat.clone().requires_grad_(True)
