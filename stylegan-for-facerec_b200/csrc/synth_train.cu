@@ -74,8 +74,25 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
     return v;
 }
 
-// grid (blocks per sample, B); 256 threads; a thread owns 8 consecutive channels and walks pixels
-__global__ void __launch_bounds__(256)
+// grid (blocks per sample, B); 256 threads; a thread owns 8 consecutive channels and walks pixels.  HBM-bound by design
+// (2 x 16-byte loads + one 16-byte store per 8 elements): the loads of the NEXT pixel are issued before the math of the
+// current one; two blocks per SM (128 registers: no spills).
+struct EpassIn { uint4 st, gs; float nz, g0, g1, g2; };
+__device__ __forceinline__ EpassIn epass_load(const EpassParams &p, int b, int px, int c0, float nw) {
+    EpassIn in;
+    const long long e = ((long long)b * p.HW + px) * p.C + c0;
+    in.st = __ldg(reinterpret_cast<const uint4 *>(p.st + e));
+    in.gs = p.g_st ? __ldg(reinterpret_cast<const uint4 *>(p.g_st + e)) : make_uint4(0, 0, 0, 0);
+    in.nz = p.noise ? nw * __ldg(p.noise + (long long)b * p.noise_bstride + px) : 0.f;
+    in.g0 = in.g1 = in.g2 = 0.f;
+    if (p.g_rgb) {
+        const float *gr = p.g_rgb + (long long)b * 3 * p.HW + px;
+        in.g0 = __ldg(gr); in.g1 = __ldg(gr + p.HW); in.g2 = __ldg(gr + 2 * (long long)p.HW);
+    }
+    return in;
+}
+
+__global__ void __launch_bounds__(256, 2)
 train_epass_kernel(EpassParams p) {
     __shared__ float red[3][512];
     const int b = blockIdx.y;
@@ -85,7 +102,7 @@ train_epass_kernel(EpassParams p) {
     const int c0 = cg * 8;
     for (int i = threadIdx.x; i < 3 * 512; i += 256) (&red[0][0])[i] = 0.f;
     __syncthreads();
-    float sig[8], isig[8], dd[8], idd[8], bb[8], w0[8], w1[8], w2[8];
+    float sig[8], isig[8], dd[8], bb[8], w0[8], w1[8], w2[8];     // w_k pre-multiplied by sqrt(2) * s_rgb
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const int c = c0 + j;
@@ -93,58 +110,56 @@ train_epass_kernel(EpassParams p) {
         sig[j] = kSqrt2 * sn;
         isig[j] = fabsf(sig[j]) > 1e-20f ? 1.f / sig[j] : 0.f;
         dd[j] = __ldg(p.d + (long long)b * p.C + c);
-        idd[j] = 1.f / dd[j];
         bb[j] = __ldg(p.bias + c);
+        w0[j] = w1[j] = w2[j] = 0.f;
         if (p.g_rgb) {
-            w0[j] = __ldg(p.rgb_w + c); w1[j] = __ldg(p.rgb_w + p.C + c); w2[j] = __ldg(p.rgb_w + 2 * p.C + c);
-        } else {
-            w0[j] = w1[j] = w2[j] = 0.f;
+            const float sr = kSqrt2 * __ldg(p.s_rgb + (long long)b * p.C + c);
+            w0[j] = sr * __ldg(p.rgb_w + c); w1[j] = sr * __ldg(p.rgb_w + p.C + c); w2[j] = sr * __ldg(p.rgb_w + 2 * p.C + c);
         }
     }
-    float rsn[8], rsr[8], rd[8], srgb[8];
+    // reductions: rsn = sum g_st * a,  rsr = sum (sum_k g_rgb[k] w'_k) * a,  rd = sum g_y * (y - noise - bias); the constant
+    // factors (sqrt(2), 1 / (sqrt(2) s_rgb), 1 / d) are applied once at the end
+    float rsn[8], rsr[8], rd[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        rsn[j] = rsr[j] = rd[j] = 0.f;
-        srgb[j] = p.g_rgb ? kSqrt2 * __ldg(p.s_rgb + (long long)b * p.C + c0 + j) : 0.f;
-    }
+    for (int j = 0; j < 8; ++j) rsn[j] = rsr[j] = rd[j] = 0.f;
     const float nw = p.noise ? __ldg(p.noise_weight) : 0.f;
-    const long long base = (long long)b * p.HW;
-    for (int px = blockIdx.x * ppi + pl; px < p.HW; px += gridDim.x * ppi) {
-        const long long e = (base + px) * p.C + c0;
-        float st[8], gs[8];
-        unpack8(__ldg(reinterpret_cast<const uint4 *>(p.st + e)), st);
-        if (p.g_st) unpack8(__ldg(reinterpret_cast<const uint4 *>(p.g_st + e)), gs);
-        else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) gs[j] = 0.f;
-        }
-        const float nz = p.noise ? nw * __ldg(p.noise + (long long)b * p.noise_bstride + px) : 0.f;
-        float g0 = 0.f, g1 = 0.f, g2 = 0.f;
-        if (p.g_rgb) {
-            const float *gr = p.g_rgb + (long long)b * 3 * p.HW + px;
-            g0 = __ldg(gr); g1 = __ldg(gr + p.HW); g2 = __ldg(gr + 2 * (long long)p.HW);
-        }
-        float out[8];
+    const int stride = gridDim.x * ppi;
+    int px = blockIdx.x * ppi + pl;
+    EpassIn cur;
+    if (px < p.HW) cur = epass_load(p, b, px, c0, nw);
+    while (px < p.HW) {
+        const int pxn = px + stride;
+        EpassIn nxt;
+        if (pxn < p.HW) nxt = epass_load(p, b, pxn, c0, nw);
+        float st[8], gs[8], out[8];
+        unpack8(cur.st, st);
+        unpack8(cur.gs, gs);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const float a = st[j] * isig[j];
-            const float grw = g0 * w0[j] + g1 * w1[j] + g2 * w2[j];      // sum_k g_rgb[k] * w_rgb[k, c]
-            const float ga = gs[j] * sig[j] + grw * srgb[j];
-            rsn[j] += gs[j] * a * kSqrt2;
-            rsr[j] += grw * a * kSqrt2;
+            const float grw = cur.g0 * w0[j] + cur.g1 * w1[j] + cur.g2 * w2[j];      // sum_k g_rgb[k] * rho[k, c]
+            const float ga = fmaf(gs[j], sig[j], grw);
+            rsn[j] = fmaf(gs[j], a, rsn[j]);
+            rsr[j] = fmaf(grw, a, rsr[j]);
             const bool pos = a > 0.f;
             const float gy = pos ? ga : kSlopeT * ga;
             const float y = pos ? a : a * (1.f / kSlopeT);
-            rd[j] += gy * (y - nz - bb[j]) * idd[j];
+            rd[j] = fmaf(gy, y - cur.nz - bb[j], rd[j]);
             out[j] = gy * dd[j];
         }
-        *reinterpret_cast<uint4 *>(p.g_conv + e) = pack8(out);
+        *reinterpret_cast<uint4 *>(p.g_conv + ((long long)b * p.HW + px) * p.C + c0) = pack8(out);
+        cur = nxt;
+        px = pxn;
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        if (p.g_s_next) atomicAdd(&red[0][c0 + j], rsn[j]);
-        if (p.g_rgb) atomicAdd(&red[1][c0 + j], rsr[j]);
-        atomicAdd(&red[2][c0 + j], rd[j]);
+        if (p.g_s_next) atomicAdd(&red[0][c0 + j], rsn[j] * kSqrt2);
+        if (p.g_rgb) {
+            // rho = sqrt(2) s_rgb w: dL/ds_rgb = sum a * sqrt(2) * sum_k g_k w_k = rsr / s_rgb (a channel with s_rgb == 0 carries no rgb term)
+            const float sr = __ldg(p.s_rgb + (long long)b * p.C + c0 + j);
+            atomicAdd(&red[1][c0 + j], fabsf(sr) > 1e-20f ? rsr[j] / sr : 0.f);
+        }
+        atomicAdd(&red[2][c0 + j], rd[j] / dd[j]);
     }
     __syncthreads();
     for (int c = threadIdx.x; c < p.C; c += 256) {
@@ -156,42 +171,58 @@ train_epass_kernel(EpassParams p) {
 }
 
 // adjoint of the 4x4 blur after the transposed conv (pad (1,1)): g [B, 2r, 2r, C] -> four polyphase planes
-// gT[(py,px)][B][P][P][C], P = r + 1, gT[u, v] = sum_{a,b} kf[a][b] * g[u - a + 1, v - b + 1]   (u = 2y + py, v = 2x + px)
+// gT[(py,px)][B][P][P][C], P = r + 1, gT[u, v] = sum_{a,b} kf[a][b] * g[u - a + 1, v - b + 1]   (u = 2y + py, v = 2x + px).
+// A thread owns 8 channels of the 2 x 2 patch (u, v) in {2y, 2y+1} x {2x, 2x+1} -- one pixel of each plane: the patch reads a
+// 5 x 5 window of g (25 16-byte loads for 4 stores instead of 64).
 struct FirTParams { const __nv_bfloat16 *g; __nv_bfloat16 *planes; int B, r, C; float kf[16]; };
 __global__ void __launch_bounds__(256)
 train_firT_kernel(FirTParams p) {
     const int P = p.r + 1, R = 2 * p.r, c8n = p.C >> 3;
-    const long long total = 4LL * p.B * P * P * c8n;
+    const long long total = (long long)p.B * P * P * c8n;
+    const long long plane_elems = (long long)p.B * P * P * p.C;
     for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
         const int c8 = (int)(i % c8n);
         long long rest = i / c8n;
         const int x = (int)(rest % P);
         rest /= P;
-        const int y = (int)(rest % P);
-        rest /= P;
-        const int b = (int)(rest % p.B), ph = (int)(rest / p.B);
-        const int py = ph >> 1, px = ph & 1;
-        if (y >= P - py || x >= P - px) continue;
-        const int u = 2 * y + py, v = 2 * x + px;
-        float acc[8];
+        const int y = (int)(rest % P), b = (int)(rest / P);
+        float acc[4][8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        for (int q = 0; q < 4; ++q)
 #pragma unroll
-        for (int a = 0; a < 4; ++a) {
-            const int gy = u - a + 1;
+            for (int j = 0; j < 8; ++j) acc[q][j] = 0.f;
+        // window rows gy = 2y - 2 + wy (wy = 0..4); output row u = 2y + py takes tap a = u + 1 - gy = py + 3 - wy
+#pragma unroll
+        for (int wy = 0; wy < 5; ++wy) {
+            const int gy = 2 * y - 2 + wy;
             if (gy < 0 || gy >= R) continue;
 #pragma unroll
-            for (int bq = 0; bq < 4; ++bq) {
-                const int gx = v - bq + 1;
+            for (int wx = 0; wx < 5; ++wx) {
+                const int gx = 2 * x - 2 + wx;
                 if (gx < 0 || gx >= R) continue;
                 float f[8];
                 unpack8(__ldg(reinterpret_cast<const uint4 *>(p.g + (((long long)b * R + gy) * R + gx) * p.C + c8 * 8)), f);
-                const float k = p.kf[a * 4 + bq];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[j] = fmaf(k, f[j], acc[j]);
+                for (int py = 0; py < 2; ++py) {
+                    const int a = py + 3 - wy;
+                    if (a < 0 || a > 3) continue;
+#pragma unroll
+                    for (int px = 0; px < 2; ++px) {
+                        const int bq = px + 3 - wx;
+                        if (bq < 0 || bq > 3) continue;
+                        const float k = p.kf[a * 4 + bq];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) acc[py * 2 + px][j] = fmaf(k, f[j], acc[py * 2 + px][j]);
+                    }
+                }
             }
         }
-        *reinterpret_cast<uint4 *>(p.planes + ((((long long)ph * p.B + b) * P + y) * P + x) * p.C + c8 * 8) = pack8(acc);
+#pragma unroll
+        for (int ph = 0; ph < 4; ++ph) {
+            const int py = ph >> 1, px = ph & 1;
+            if (y >= P - py || x >= P - px) continue;       // the odd planes are one row / column shorter
+            *reinterpret_cast<uint4 *>(p.planes + ph * plane_elems + (((long long)b * P + y) * P + x) * p.C + c8 * 8) = pack8(acc[ph]);
+        }
     }
 }
 
@@ -471,7 +502,7 @@ extern "C" int sg2_synth_backward(sg2_synth *S, void *workspace, int64_t B64, co
             FirTParams f;
             f.g = Gc; f.planes = GT; f.B = B; f.r = L.res_in; f.C = L.p.cout;
             memcpy(f.kf, S->kf, sizeof(f.kf));
-            const long long total = 4LL * B * (f.r + 1) * (f.r + 1) * (f.C / 8);
+            const long long total = (long long)B * (f.r + 1) * (f.r + 1) * (f.C / 8);
             train_firT_kernel<<<(unsigned)std::min<long long>(ceil_div64(total, 256), 148 * 32), 256, 0, st>>>(f);
             SG2_LAUNCH_CHECK();
         }
