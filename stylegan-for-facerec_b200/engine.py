@@ -175,10 +175,22 @@ class SynthesisEngine:
                                                   strides, image.data_ptr(), _lib.stream_of(lat)), "synth_forward")
 
     @torch.no_grad()
-    def synthesize(self, latent, noise, graph=None):
+    def synthesize(self, latent, noise, graph=None, z=None, want_latent=True):
         """latent [B, n_latent, style_dim]; noise: list (num_layers) of [B or 1, 1, r, r] tensors or
-        None entries (fresh N(0,1) is drawn, model.py:283-285).  Returns the image [B,3,size,size]."""
+        None entries (fresh N(0,1) is drawn, model.py:283-285).  Returns the image [B,3,size,size].
+        z [B, style_dim] instead of latent (latent=None): the mapping network and the broadcast over the layers
+        (model.py:482-483,503-506) run INSIDE the CUDA graph; returns (image, latent)."""
         G = self.G
+        from_z = z is not None
+        if from_z:
+            _lib.require_cuda(z, "z")
+            if latent is None:
+                if not (self.use_graph if graph is None else graph) or torch.cuda.is_current_stream_capturing() or \
+                        threading.current_thread() is not threading.main_thread() or z.shape[0] == 0:
+                    w = G.style(z)
+                    latent = w.unsqueeze(1).repeat(1, G.n_latent, 1)
+                    return self.synthesize(latent, noise, graph=False), latent
+                latent = z                       # batch size / device below
         _lib.require_cuda(latent, "latent")
         B = latent.shape[0]
         self._ensure(B)
@@ -200,10 +212,15 @@ class SynthesisEngine:
             return image if out_dtype == torch.float32 else image.to(out_dtype)
 
         layout = self._noise_layout(B, noise)
-        key = (B, layout, dev.index)
+        key = (B, layout, dev.index, from_z)
         entry = self._graphs.get(key)
         if entry is None:
             s_lat = torch.empty(B, G.n_latent, G.style_dim, device=dev, dtype=torch.float32)
+            s_z = torch.empty(B, G.style_dim, device=dev, dtype=z.dtype) if from_z else None
+
+            def head():                      # mapping network + broadcast, part of the graph when the caller passes z
+                if from_z:
+                    s_lat.copy_(G.style(s_z).unsqueeze(1).expand(-1, G.n_latent, -1))
             # all static noise maps live in ONE flat buffer: a fully randomised forward refills it with one launch
             shapes = [(nb, 1, 2 ** ((i + 5) // 2), 2 ** ((i + 5) // 2)) for i, nb in enumerate(layout)]
             sizes = [s[0] * s[2] * s[3] for s in shapes]
@@ -213,24 +230,32 @@ class SynthesisEngine:
                 s_noise.append(s_flat[o:o + n].view(shp))
                 o += n
             s_img = torch.empty(B, 3, G.size, G.size, device=dev, dtype=torch.float32)
-            s_lat.copy_(latent)
+            (s_z if from_z else s_lat).copy_(z if from_z else latent)
             ptrs, strides, _ = self._noise_args(B, noise, dev, into=s_noise)
             n0 = _lib.launch_count()
+            head()
             self._call(s_lat, B, ptrs, strides, s_img)              # warm-up outside capture (lazy attributes, descriptors)
             n_launch = _lib.launch_count() - n0
             torch.cuda.current_stream(dev).synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
+                head()
                 self._call(s_lat, B, ptrs, strides, s_img)
-            entry = {"graph": g, "lat": s_lat, "noise": s_noise, "flat": s_flat, "img": s_img, "launches": n_launch,
+            entry = {"graph": g, "lat": s_lat, "z": s_z, "noise": s_noise, "flat": s_flat, "img": s_img, "launches": n_launch,
                      "args": (ptrs, strides), "src": [None] * len(s_noise)}
             self._graphs[key] = entry
-        entry["lat"].copy_(latent)
+        if from_z:
+            entry["z"].copy_(z)
+        else:
+            entry["lat"].copy_(latent)
         self._stage_noise(entry, noise)
         entry["graph"].replay()
         self.lib.sg2_note_launches(entry["launches"])              # kernels launched by the graph replay
         s_img = entry["img"]
-        return s_img.clone() if out_dtype == torch.float32 else s_img.to(out_dtype)
+        image = s_img.clone() if out_dtype == torch.float32 else s_img.to(out_dtype)
+        if from_z:                                                  # a copy: the static buffer is overwritten by the next call
+            return image, (entry["lat"].to(z.dtype, copy=True) if want_latent else None)
+        return image
 
     @staticmethod
     def _stage_noise(entry, noise):

@@ -473,13 +473,20 @@ class Generator(nn.Module):
 
     def forward(self, styles, return_latents=False, return_features=False, inject_index=None, truncation=1,
                 truncation_latent=None, input_is_latent=False, noise=None, randomize_noise=True):
-        if not input_is_latent:
-            styles = [self.style(s) for s in styles]
         if noise is None:
             if randomize_noise:
                 noise = [None] * self.num_layers
             else:
                 noise = [getattr(self.noises, f'noise_{i}') for i in range(self.num_layers)]
+        # one z, no truncation, bf16 engine: the mapping network and the broadcast over the layers go into the engine's CUDA
+        # graph with the synthesis (the arithmetic is the same: Generator.style on the same kernels)
+        if (not input_is_latent and len(styles) == 1 and truncation >= 1 and torch.is_tensor(styles[0]) and styles[0].ndim == 2
+                and styles[0].shape[1] == self.style_dim and self._use_engine(styles[0], noise, return_features)
+                and not K.needs_grad(styles[0])):
+            image, latent = self.engine().synthesize(None, noise, z=styles[0], want_latent=return_latents)
+            return (image, latent) if return_latents else (image, None)
+        if not input_is_latent:
+            styles = [self.style(s) for s in styles]
         if truncation < 1:
             styles = [truncation_latent + truncation * (s - truncation_latent) for s in styles]
         if len(styles) < 2:
