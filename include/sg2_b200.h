@@ -201,6 +201,15 @@ typedef struct sg2_synth sg2_synth; /* opaque launch plan */
 int sg2_synth_create(sg2_synth **plan, int size, int style_dim, int max_batch,
                      const sg2_conv_params *layers, int n_layers, const float *const_input,
                      const float *blur_taps_host);
+/* The same plan for the stylegan2_ada decoder variant (restyle-encoder/models/stylegan2_ada/generator.py:55-204, the
+ * decoder psp.py:24-30 builds with opts.generator_ada): same layer table order (first_block.conv1, first_block.torgb, then
+ * per block conv0 with upsample = 1, conv1, torgb; mod_weight / mod_bias = the affine FullyConnectedLayer, noise_weight =
+ * noise_strength), w_dim in place of style_dim, resample_taps_host = the 4x4 SmoothUpsample kernel (utils.py:76-83).
+ * Differences handled by the plan: no equalised-lr conv scale, conv -> SmoothUpsample ordering in the up-sampling layers,
+ * clamp_gain(x, sqrt(2), 256) after every activation, ToRGB clamp, SmoothUpsample of the running image.              */
+int sg2_synth_create_ada(sg2_synth **plan, int size, int w_dim, int max_batch,
+                         const sg2_conv_params *layers, int n_layers, const float *const_input,
+                         const float *resample_taps_host);
 void sg2_synth_destroy(sg2_synth *plan);
 /* bytes of device workspace the caller must provide (packed weights + activations + scratch) */
 int64_t sg2_synth_workspace_bytes(const sg2_synth *plan);

@@ -68,6 +68,8 @@ SIGNATURES = {
     "sg2_image_to_uint8": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_void_p]),
     "sg2_synth_create": (c_int, [C.POINTER(c_void_p), c_int, c_int, c_int, C.POINTER(ConvParams), c_int,
                                  c_void_p, C.POINTER(c_float)]),
+    "sg2_synth_create_ada": (c_int, [C.POINTER(c_void_p), c_int, c_int, c_int, C.POINTER(ConvParams), c_int,
+                                     c_void_p, C.POINTER(c_float)]),
     "sg2_synth_enable_training": (c_int, [c_void_p]),
     "sg2_synth_backward": (c_int, [c_void_p, c_void_p, c_i64, C.POINTER(c_void_p), C.POINTER(c_i64), c_void_p, c_void_p, c_void_p]),
     "sg2_synth_destroy": (None, [c_void_p]),

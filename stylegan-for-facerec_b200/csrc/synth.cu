@@ -43,7 +43,7 @@ int plan_gemm(sg2_synth *S, Layer &L, const int *custom_taps, int n_custom, cons
     memset(&g, 0, sizeof(g));
     const bool fused = L.fused_up;
     const int cin = L.p.cin, cout = fused ? 4 * L.p.cout : L.p.cout;
-    const bool up = L.p.upsample != 0 && !fused;
+    const bool up = L.p.upsample != 0 && !fused && !L.ada_up;
     const int r = L.res_in;
     L.n_gemm = cout;
     g.block_k = cin % 64 == 0 ? 64 : 32;
@@ -345,9 +345,9 @@ int rec(sg2_synth *S, cudaStream_t st, const char *what) {
 
 }  // namespace sg2plan
 
-extern "C" int sg2_synth_create(sg2_synth **plan, int size, int style_dim, int max_batch,
-                                const sg2_conv_params *layers, int n_layers, const float *const_input,
-                                const float *blur_taps_host) {
+static int synth_create_impl(sg2_synth **plan, int size, int style_dim, int max_batch,
+                             const sg2_conv_params *layers, int n_layers, const float *const_input,
+                             const float *blur_taps_host, bool ada) {
     SG2_REQUIRE(plan, SG2_ERR_BAD_ARG, "synth_create: null plan pointer");
     *plan = nullptr;
     int log_size = 0;
@@ -365,8 +365,17 @@ extern "C" int sg2_synth_create(sg2_synth **plan, int size, int style_dim, int m
     S->n_latent = 2 * log_size - 2; S->num_layers = 2 * (log_size - 2) + 1;
     S->const_input = const_input;
     S->sms = 148;
+    S->ada = ada;
     for (int a = 0; a < 4; ++a)
-        for (int b = 0; b < 4; ++b) S->kf[a * 4 + b] = blur_taps_host[(3 - a) * 4 + (3 - b)];
+        for (int b = 0; b < 4; ++b) { S->kf[a * 4 + b] = blur_taps_host[(3 - a) * 4 + (3 - b)]; S->kf_raw[a * 4 + b] = blur_taps_host[a * 4 + b]; }
+    {   // SmoothUpsample: tap a of output parity p reads input cell i + off[p][a] (clamped): fold the 16 taps onto the 3x3 cells
+        const int sel[2][4] = {{0, 0, 1, 1}, {0, 1, 1, 2}};
+        for (int ph = 0; ph < 4; ++ph) {
+            for (int t = 0; t < 9; ++t) S->wp_ada[ph][t] = 0.f;
+            for (int a = 0; a < 4; ++a)
+                for (int b = 0; b < 4; ++b) S->wp_ada[ph][sel[ph >> 1][a] * 3 + sel[ph & 1][b]] += blur_taps_host[a * 4 + b];
+        }
+    }
     const int B = max_batch;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes); return o; };
@@ -392,7 +401,7 @@ extern "C" int sg2_synth_create(sg2_synth **plan, int size, int style_dim, int m
         if (L.rgb) {
             L.rgbw = take(sizeof(float) * 3 * L.p.cin);
         } else {
-            if (L.p.cin % 32 || L.p.cout % 16 || (L.p.upsample && L.p.cout % 32)) {
+            if (L.p.cin % 32 || L.p.cout % 16 || (L.p.upsample && !ada && L.p.cout % 32)) {
                 delete S;
                 set_error("engine: styled conv %d with Cin %d / Cout %d needs Cin %% 32 == 0 and Cout %% 16 == 0 "
                           "(Cout %% 32 == 0 for up-sampling layers)", i, L.p.cin, L.p.cout);
@@ -403,8 +412,9 @@ extern "C" int sg2_synth_create(sg2_synth **plan, int size, int style_dim, int m
             // the (2r+1)^2 intermediate never exists.  SG2_UPFUSED=0: never, 2: every up-sampling layer that qualifies.
             static const char *envf = getenv("SG2_UPFUSED");
             const int fmode = envf ? atoi(envf) : 1;
-            L.fused_up = L.p.upsample && fmode != 0 && L.p.cin % 64 == 0 && L.p.cout % 32 == 0 && L.res_out >= 32 &&
+            L.fused_up = !ada && L.p.upsample && fmode != 0 && L.p.cin % 64 == 0 && L.p.cout % 32 == 0 && L.res_out >= 32 &&
                          (L.p.cout <= 64 || fmode == 2);
+            L.ada_up = ada && L.p.upsample;
             L.wp = take(sizeof(__nv_bfloat16) * 9 * L.p.cout * L.p.cin * (L.fused_up ? 4 : 1));
             L.wsq = take(sizeof(float) * L.p.cin * L.p.cout);
             L.demod = take(sizeof(float) * B * L.p.cout);
@@ -428,7 +438,9 @@ extern "C" int sg2_synth_create(sg2_synth **plan, int size, int style_dim, int m
             prev_cout = L.p.cout;
             max_act = std::max(max_act, sizeof(__nv_bfloat16) * (size_t)B * L.res_in * L.res_in * L.p.cin);
             max_act = std::max(max_act, sizeof(__nv_bfloat16) * (size_t)B * L.res_out * L.res_out * L.p.cout);
-            if (L.p.upsample && !L.fused_up)
+            if (L.ada_up)
+                max_T = std::max(max_T, sizeof(__nv_bfloat16) * (size_t)B * L.res_in * L.res_in * L.p.cout);
+            else if (L.p.upsample && !L.fused_up)
                 max_T = std::max(max_T, sizeof(__nv_bfloat16) * 4 * (size_t)B * (L.res_in + 1) * (L.res_in + 1) * L.p.cout);
             else if (!L.p.upsample)
                 max_part = std::max(max_part, sizeof(float) * (L.two_sm ? kGemm2EpiGroups : 2) * (size_t)L.gp.n_tiles_n * B * 3 * L.res_out * L.res_out);
@@ -471,15 +483,31 @@ extern "C" int sg2_synth_create(sg2_synth **plan, int size, int style_dim, int m
             // layer, the output plane of a plain one -- except the LAST conv, which stores no activation at all, only
             // the three fp32 ToRGB planes
             const bool last = i + 2 >= S->layers.size();
-            const double out_b = (L.p.upsample && !L.fused_up) ? 2.0 * (2 * L.res_in + 1.0) * (2 * L.res_in + 1.0) * L.p.cout
-                                                               : (last ? 4.0 * 3 * px_out : 2.0 * px_out * L.p.cout);
+            const double out_b = L.ada_up ? 2.0 * px_in * L.p.cout
+                                 : (L.p.upsample && !L.fused_up) ? 2.0 * (2 * L.res_in + 1.0) * (2 * L.res_in + 1.0) * L.p.cout
+                                                                 : (last ? 4.0 * 3 * px_out : 2.0 * px_out * L.p.cout);
             add("gemm", name, fl, 2.0 * px_in * L.p.cin + out_b, L.dxs ? L.dp.tiles_x * L.dp.tiles_y * B : L.gp.total_tiles, L.block_n);
-            if (L.p.upsample && !L.fused_up) add("upfir", name, 0, 2.0 * ((2 * L.res_in + 1.0) * (2 * L.res_in + 1.0) + px_out) * L.p.cout, 0, 0);
+            if (L.ada_up) add("smoothup", name, 0, 2.0 * (px_in + px_out) * L.p.cout, 0, 0);
+            else if (L.p.upsample && !L.fused_up) add("upfir", name, 0, 2.0 * ((2 * L.res_in + 1.0) * (2 * L.res_in + 1.0) + px_out) * L.p.cout, 0, 0);
         }
     }
     S->description = d;
     *plan = S;
     return SG2_OK;
+}
+
+extern "C" int sg2_synth_create(sg2_synth **plan, int size, int style_dim, int max_batch,
+                                const sg2_conv_params *layers, int n_layers, const float *const_input,
+                                const float *blur_taps_host) {
+    return synth_create_impl(plan, size, style_dim, max_batch, layers, n_layers, const_input, blur_taps_host, false);
+}
+// The stylegan2_ada decoder (restyle-encoder/models/stylegan2_ada/generator.py:55-204) on the same plan: same layer table
+// (first_block.conv1, first_block.torgb, then per block conv0 (upsample = 1), conv1, torgb), resample_taps_host = the 4x4
+// SmoothUpsample kernel (utils.py:76-83, sum 1).
+extern "C" int sg2_synth_create_ada(sg2_synth **plan, int size, int w_dim, int max_batch,
+                                    const sg2_conv_params *layers, int n_layers, const float *const_input,
+                                    const float *resample_taps_host) {
+    return synth_create_impl(plan, size, w_dim, max_batch, layers, n_layers, const_input, resample_taps_host, true);
 }
 
 extern "C" void sg2_synth_destroy(sg2_synth *p) { delete p; }
@@ -517,8 +545,9 @@ extern "C" int sg2_synth_pack(sg2_synth *S, void *workspace, sg2_stream_t stream
             if (rc) return rc;
         } else {
             // (a fused up-sampling layer needs wsq from the plain weights and then its own composite pack over wp)
+            // (stylegan2_ada: no equalised-lr scale on the conv weights -- the demodulation normalises them, utils.py:120-137)
             int rc = launch_pack_conv_weight((__nv_bfloat16 *)(ws + L.wp), (float *)(ws + L.wsq), L.p.weight, L.p.cin,
-                                             L.p.cout, 9, 1.0f / sqrtf((float)L.p.cin * 9), st);
+                                             L.p.cout, 9, S->ada ? 1.0f : 1.0f / sqrtf((float)L.p.cin * 9), st);
             if (rc) return rc;
             if (L.fused_up) {
                 rc = launch_pack_upfused_weight((__nv_bfloat16 *)(ws + L.wp), L.p.weight, L.p.cin, L.p.cout,
@@ -642,10 +671,30 @@ extern "C" int sg2_synth_forward(sg2_synth *S, void *workspace, const float *lat
         }
         GemmParams g = L.gp;
         g.demod = (const float *)(ws + L.demod);
+        const float act_clamp = S->ada ? 256.0f / 1.41421356237f : 0.f;     // clamp_gain(x, sqrt(2), 256) before the folded gain
+        g.clamp = act_clamp;
         const float *nz = noise[noise_idx];
         const int64_t nzs = noise_bstride[noise_idx];
         ++noise_idx;
-        if (L.fused_up) {
+        if (L.ada_up) {
+            // stylegan2_ada: 3x3 conv at the input resolution (x demod) -> Tbuf, then SmoothUpsample + noise + bias + lrelu +
+            // clamp + next layer's modulation in one pass (generator.py:198-204)
+            SG2_REQUIRE(next_conv, SG2_ERR_BAD_ARG, "engine: up-sampling conv without a consumer");
+            g.mode = 1;
+            g.out = Tbuf;
+            rc = L.two_sm ? launch_modconv_gemm2(g, L.tmA, L.tmB, S->sms, st) : launch_modconv_gemm(g, L.tmA, L.tmB, S->sms, st);
+            if (rc) return rc;
+            if ((rc = rec(S, st, "gemm(ada up)"))) return rc;
+            SmoothUpParams sp;
+            sp.T = Tbuf; sp.out = outp[i]; sp.B = B; sp.r = L.res_in; sp.C = L.p.cout;
+            sp.noise = nz; sp.noise_bstride = nzs; sp.noise_weight = L.p.noise_weight;
+            sp.bias = L.p.act_bias; sp.next_style = (const float *)(ws + next_conv->style);
+            sp.clamp = act_clamp;
+            memcpy(sp.wp, S->wp_ada, sizeof(sp.wp));
+            rc = launch_smooth_up(sp, st);
+            if (rc) return rc;
+            if ((rc = rec(S, st, "smoothup"))) return rc;
+        } else if (L.fused_up) {
             // conv_transpose + blur + noise + bias + lrelu + next layer's modulation in ONE launch: act[1] -> act[0]
             SG2_REQUIRE(next_conv, SG2_ERR_BAD_ARG, "engine: up-sampling conv without a consumer");
             g.noise = nz; g.noise_bstride = nzs; g.noise_weight = L.p.noise_weight;
@@ -658,6 +707,7 @@ extern "C" int sg2_synth_forward(sg2_synth *S, void *workspace, const float *lat
         } else if (L.dxs) {
             DxsParams d = L.dp;
             d.B = B; d.total_tiles = d.tiles_x * d.tiles_y * B;
+            d.clamp = act_clamp;
             d.demod = (const float *)(ws + L.demod);
             d.noise = nz; d.noise_bstride = nzs; d.noise_weight = L.p.noise_weight;
             d.bias = L.p.act_bias;
@@ -680,7 +730,8 @@ extern "C" int sg2_synth_forward(sg2_synth *S, void *workspace, const float *lat
                 rp.part = part; rp.n_parts = 3 * L.p.cout <= 128 ? 1 : 2; rp.bias = rgb->p.act_bias;
                 rp.prev = rgb_cur >= 0 ? rgbbuf[rgb_cur] : nullptr;
                 rp.B = B; rp.R = L.res_out;
-                memcpy(rp.kf, S->kf, sizeof(rp.kf));
+                rp.clamp = S->ada ? 256.0f : 0.f; rp.smooth = S->ada ? 1 : 0;
+                memcpy(rp.kf, S->ada ? S->kf_raw : S->kf, sizeof(rp.kf));
                 rc = launch_rgb_combine(rp, S->sms, st);
                 if (rc) return rc;
                 if ((rc = rec(S, st, "rgb_combine"))) return rc;
@@ -709,7 +760,8 @@ extern "C" int sg2_synth_forward(sg2_synth *S, void *workspace, const float *lat
                 rp.part = part; rp.n_parts = parts_per_tile * g.n_tiles_n; rp.bias = rgb->p.act_bias;
                 rp.prev = rgb_cur >= 0 ? rgbbuf[rgb_cur] : nullptr;
                 rp.B = B; rp.R = L.res_out;
-                memcpy(rp.kf, S->kf, sizeof(rp.kf));
+                rp.clamp = S->ada ? 256.0f : 0.f; rp.smooth = S->ada ? 1 : 0;
+                memcpy(rp.kf, S->ada ? S->kf_raw : S->kf, sizeof(rp.kf));
                 rc = launch_rgb_combine(rp, S->sms, st);
                 if (rc) return rc;
                 if ((rc = rec(S, st, "rgb_combine"))) return rc;

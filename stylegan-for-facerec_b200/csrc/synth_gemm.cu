@@ -140,6 +140,10 @@ __device__ __forceinline__ void epi_cols(const GemmParams &p, const EpiTables &e
             v[3] = fmaf(__uint_as_float(r[j + 3]), d4.w, nz) + b4.w;
 #pragma unroll
             for (int k = 0; k < 4; ++k) v[k] = fmaxf(v[k], kSlope * v[k]);   // lrelu (gain folded downstream)
+            if (p.clamp > 0.f) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) v[k] = fminf(fmaxf(v[k], -p.clamp), p.clamp);
+            }
             if (p.rgb_w) {
                 const float4 w0 = lds4(e.w0 + c0 + j), w1 = lds4(e.w1 + c0 + j), w2 = lds4(e.w2 + c0 + j);
                 rgb0 += v[0] * w0.x + v[1] * w0.y + v[2] * w0.z + v[3] * w0.w;

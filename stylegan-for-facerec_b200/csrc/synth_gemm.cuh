@@ -76,6 +76,8 @@ struct GemmParams {
     int dbg;                        // SG2_GEMM_DBG knock-outs for bottleneck analysis (results WRONG when set): 1 no stores, 2 no A loads, 4 no B loads, 8 one MMA per stage
     // epilogue
     int mode;                       // 0: styled conv (noise, bias, lrelu, next-style, ToRGB); 1: plain scaled store
+    float clamp;                    // mode 0: clamp the activation to +-clamp after the leaky ReLU (before the folded sqrt(2) gain); 0 = none
+                                    // (stylegan2_ada clamp_gain(x, sqrt(2), 256), utils.py:6-7: clamp = 256 / sqrt(2))
     const float *demod;             // [B, Cout]
     const float *noise;             // [B or 1, PH*PW] fp32 or null
     long long noise_bstride;
@@ -106,6 +108,7 @@ struct DxsParams {
     const float *next_style;                 // [B, Cout] or null (no activation store)
     const float *rgb_w;                      // [3, Cout] or null
     const float *rgb_style;                  // [B, Cout]
+    float clamp;                             // as GemmParams::clamp
     float *rgb_part;                         // [col_groups][B, 3, R, R], col_groups = 1 (Cout = 32) or 2 (Cout = 64)
     __nv_bfloat16 *out;                      // NHWC bf16 or null
 };

@@ -390,6 +390,10 @@ modconv_gemm2_kernel(const __grid_constant__ GemmParams p, const __grid_constant
                             v[3] = fmaf(__uint_as_float(r[j + 3]), d4.w, nzc) + b4.w;
 #pragma unroll
                             for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], kSlope2 * v[e]);   // lrelu (gain folded downstream)
+                            if (p.clamp > 0.f) {
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) v[e] = fminf(fmaxf(v[e], -p.clamp), p.clamp);
+                            }
                             if (p.rgb_w) {
                                 const float4 w0 = lds128f(smem_u32(&sm.e_wrgb[0][pb + c0 + j]));
                                 const float4 w1 = lds128f(smem_u32(&sm.e_wrgb[1][pb + c0 + j]));

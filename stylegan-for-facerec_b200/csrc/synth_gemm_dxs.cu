@@ -218,6 +218,7 @@ modconv_dxs_kernel(const __grid_constant__ DxsParams p, const __grid_constant__ 
                         const float s = a + __uint_as_float(f0[j + e]) + c;
                         v[e] = fmaf(s, dd[e], nz) + bb[e];
                         v[e] = fmaxf(v[e], kDxSlope * v[e]);             // lrelu (gain folded downstream)
+                        if (p.clamp > 0.f) v[e] = fminf(fmaxf(v[e], -p.clamp), p.clamp);
                     }
                     if (p.rgb_w) {
                         const float4 w0 = lds128f(smem_u32(e_w0 + c0 + j)), w1 = lds128f(smem_u32(e_w1 + c0 + j));

@@ -299,7 +299,31 @@ rgb_combine_kernel(RgbParams p) {
                 const float4 t = __ldg(reinterpret_cast<const float4 *>(p.part + (int64_t)nt * total + i));
                 v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
             }
-            if (sp) {
+            if (p.clamp > 0.f) {             // stylegan2_ada: clamp(y + bias) before the skip is added
+                v.x = fminf(fmaxf(v.x, -p.clamp), p.clamp); v.y = fminf(fmaxf(v.y, -p.clamp), p.clamp);
+                v.z = fminf(fmaxf(v.z, -p.clamp), p.clamp); v.w = fminf(fmaxf(v.w, -p.clamp), p.clamp);
+            }
+            if (sp && p.smooth) {
+                // SmoothUpsample (stylegan2_ada/utils.py:76-95): output (2i+py, 2j+px) = sum_{a,b} kf[a][b] *
+                // skip[clamp(i + off[py][a])][clamp(j + off[px][b])], off = {{-1,-1,0,0},{-1,0,0,1}}
+                const int i0 = Y >> 1, py = Y & 1;
+                float up[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    const int oy = py ? (a == 0 ? -1 : (a == 3 ? 1 : 0)) : (a < 2 ? -1 : 0);
+                    const float *row = sp + min(max(i0 + oy, 0), S - 1) * S;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int X = X0 + e, j0 = X >> 1, px = X & 1;
+#pragma unroll
+                        for (int bq = 0; bq < 4; ++bq) {
+                            const int ox = px ? (bq == 0 ? -1 : (bq == 3 ? 1 : 0)) : (bq < 2 ? -1 : 0);
+                            up[e] = fmaf(p.kf[a * 4 + bq], __ldg(row + min(max(j0 + ox, 0), S - 1)), up[e]);
+                        }
+                    }
+                }
+                v.x += up[0]; v.y += up[1]; v.z += up[2]; v.w += up[3];
+            } else if (sp) {
                 // up=2, pad (2,1), 4x4 taps (index math of upfirdn2d_kernel.cu:112-129, specialised to a quad that
                 // starts at a multiple of 4): output row Y reads skip rows iy0, iy0+1 with tap rows ky0, ky0+2;
                 // the quad reads skip columns h-1 .. h+2 (h = X0/2) with tap columns (0,2) (1,3) (0,2) (1,3)
@@ -325,6 +349,71 @@ rgb_combine_kernel(RgbParams p) {
             *reinterpret_cast<float4 *>(p.out + i) = v;
         }
     }
+}
+
+// ---- stylegan2_ada up-sampling layer: SmoothUpsample + noise + bias + lrelu + clamp + next style, NHWC bf16 -------------
+// a thread owns 8 channels of one INPUT cell (i, j) = the 2x2 output block (2i.., 2j..): 9 clamped 16-byte loads, 4 stores
+__global__ void __launch_bounds__(256)
+smooth_up_nhwc_kernel(SmoothUpParams p) {
+    const int r = p.r, R = 2 * r, c8n = p.C >> 3;
+    const long long total = (long long)p.B * r * r * c8n;
+    const float nw = p.noise ? __ldg(p.noise_weight) : 0.f;
+    for (long long idx = (long long)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (long long)gridDim.x * 256) {
+        const int c8 = (int)(idx % c8n);
+        long long rest = idx / c8n;
+        const int j = (int)(rest % r);
+        rest /= r;
+        const int i = (int)(rest % r), b = (int)(rest / r);
+        const int rr[3] = {max(i - 1, 0), i, min(i + 1, r - 1)}, cc[3] = {max(j - 1, 0), j, min(j + 1, r - 1)};
+        float w[9][8];
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p.T + (((long long)b * r + rr[a]) * r + cc[q]) * p.C + c8 * 8));
+                const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&v);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float2 t = __bfloat1622float2(h[e]);
+                    w[a * 3 + q][2 * e] = t.x; w[a * 3 + q][2 * e + 1] = t.y;
+                }
+            }
+        float bias[8], sn[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            bias[e] = __ldg(p.bias + c8 * 8 + e);
+            sn[e] = 1.41421356237f * __ldg(p.next_style + (long long)b * p.C + c8 * 8 + e);
+        }
+#pragma unroll
+        for (int ph = 0; ph < 4; ++ph) {
+            const int Y = 2 * i + (ph >> 1), X = 2 * j + (ph & 1);
+            const float nz = p.noise ? nw * __ldg(p.noise + (long long)b * p.noise_bstride + (long long)Y * R + X) : 0.f;
+            uint4 o;
+            __nv_bfloat162 *oh = reinterpret_cast<__nv_bfloat162 *>(&o);
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                float acc = 0.f;
+#pragma unroll
+                for (int t = 0; t < 9; ++t) acc = fmaf(p.wp[ph][t], w[t][e], acc);
+                acc += nz + bias[e];
+                acc = fmaxf(acc, 0.2f * acc);
+                if (p.clamp > 0.f) acc = fminf(fmaxf(acc, -p.clamp), p.clamp);
+                v[e] = acc * sn[e];
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) oh[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+            *reinterpret_cast<uint4 *>(p.out + (((long long)b * R + Y) * R + X) * p.C + c8 * 8) = o;
+        }
+    }
+}
+
+int launch_smooth_up(const SmoothUpParams &p, cudaStream_t st) {
+    SG2_REQUIRE(p.C % 8 == 0 && p.r >= 1, SG2_ERR_BAD_ARG, "smooth_up: bad shape");
+    const long long total = (long long)p.B * p.r * p.r * (p.C / 8);
+    smooth_up_nhwc_kernel<<<(unsigned)std::min<long long>(ceil_div64(total, 256), 148 * 32), 256, 0, st>>>(p);
+    SG2_LAUNCH_CHECK();
+    return SG2_OK;
 }
 
 // ---- launch helpers --------------------------------------------------------------------------------

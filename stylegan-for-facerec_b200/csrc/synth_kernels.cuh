@@ -58,7 +58,25 @@ struct RgbParams {
     const float *prev;            // [B,3,R/2,R/2] or null
     int B, R;
     float kf[16];
+    // stylegan2_ada (generator.py:134-137,148-151): the ToRGB output is clamped to +-clamp before the skip is added, and the
+    // running image is up-sampled by SmoothUpsample (nearest x2, edge replication, 4x4 correlation with kf as given)
+    float clamp;                  // 0: none
+    int smooth;                   // 0: zero-insertion up-sampling, pad (2,1), flipped taps (rosinality Upsample)
 };
+
+// stylegan2_ada up-sampling layer after its convolution (generator.py:198-204, utils.py:76-95): SmoothUpsample of the
+// demodulated conv output + noise + bias + leaky ReLU + clamp, times the consumer's style; NHWC bf16
+struct SmoothUpParams {
+    const __nv_bfloat16 *T;       // [B, r, r, C]
+    __nv_bfloat16 *out;           // [B, 2r, 2r, C]
+    int B, r, C;
+    const float *noise; long long noise_bstride; const float *noise_weight;   // [B or 1, 2r*2r]
+    const float *bias;            // [C]
+    const float *next_style;      // [B, C]
+    float clamp;                  // on the activation before the sqrt(2) gain; 0: none
+    float wp[4][9];               // per output phase (py*2+px): the 16 taps folded onto the clamped 3x3 input neighbourhood
+};
+int launch_smooth_up(const SmoothUpParams &p, cudaStream_t st);
 
 int launch_pack_conv_weight(__nv_bfloat16 *wp, float *wsq, const float *w, int Cin, int Cout, int kk, float scale, cudaStream_t st);
 // fused up-sampling conv: composite (3x3 weights * 4x4 blur) polyphase weights, bf16 [9][4*Cout][Cin]; kf16_host = flipped taps

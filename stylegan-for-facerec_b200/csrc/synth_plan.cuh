@@ -46,6 +46,7 @@ struct Layer {
     size_t wadj = 0;         // training: adjoint weights bf16 [9][Cin][Cout] (taps flipped for the plain conv)
     size_t gd = 0;           // training: dL/d demod [B, Cout] fp32
     int conv_index = -1;     // ordinal among the styled convs
+    bool ada_up = false;     // stylegan2_ada up-sampling layer: 3x3 conv at the INPUT resolution, then SmoothUpsample + epilogue
     bool fused_up = false;   // up-sampling layer run as ONE 3x3 conv with N = 4*Cout composite (weights * blur) columns, no FIR pass
     int n_gemm = 0;          // N of the GEMM: Cout, or 4*Cout for a fused up-sampling layer
     GemmParams gp;        // static part, pointers filled per forward
@@ -69,6 +70,11 @@ struct sg2_synth {
     // descriptor cache
     void *cached_ws = nullptr;
     int cached_B = -1;
+    // stylegan2_ada decoder variant (generator.py:55-204 of restyle-encoder/models/stylegan2_ada): no equalised-lr scale on
+    // the conv weights, conv -> SmoothUpsample ordering in the up-sampling layers, clamp_gain(..., 256), ToRGB clamp
+    bool ada = false;
+    float kf_raw[16];             // the resampling taps as given (SmoothUpsample correlates, it does not flip)
+    float wp_ada[4][9];           // per output phase: the 16 taps folded onto the clamped 3x3 input neighbourhood
     // training mode (synth_train.cu): forward keeps every layer's output, sg2_synth_backward walks the plan in reverse
     bool train = false;
     std::vector<sg2plan::Layer> blayers;      // one input-gradient GEMM per styled conv (channel roles swapped)

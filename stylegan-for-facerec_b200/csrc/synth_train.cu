@@ -335,6 +335,7 @@ int train_pack(sg2_synth *S, uint8_t *ws, cudaStream_t st) {
 extern "C" int sg2_synth_enable_training(sg2_synth *S) {
     SG2_REQUIRE(S, SG2_ERR_BAD_ARG, "synth_enable_training: null plan");
     if (S->train) return SG2_OK;
+    SG2_REQUIRE(!S->ada, SG2_ERR_UNSUPPORTED, "synth_enable_training: the stylegan2_ada plan has no backward walk (use the autograd route)");
     const int B = S->max_batch;
     size_t off = S->ws_bytes;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes); return o; };

@@ -101,8 +101,8 @@ class SynthesisEngine:
         arr = (_lib.ConvParams * len(rows))(*rows)
         plan = C.c_void_p()
         mb = max(batch, self.max_batch, 1)
-        _lib.check(self.lib.sg2_synth_create(C.byref(plan), self.G.size, self.G.style_dim, mb, arr, len(rows),
-                                             const, taps.numpy().ctypes.data_as(C.POINTER(C.c_float))),
+        _lib.check(self._create_fn()(C.byref(plan), self.G.size, self.G.style_dim, mb, arr, len(rows),
+                                     const, taps.numpy().ctypes.data_as(C.POINTER(C.c_float))),
                    "synth_create")
         self.plan, self.max_batch = plan, mb
         if self.training:
@@ -116,6 +116,9 @@ class SynthesisEngine:
             _lib.check(self.lib.sg2_synth_pack(self.plan, self.workspace.data_ptr(),
                                                _lib.stream_of(self.workspace)), "synth_pack")
         self._packed_version = v
+
+    def _create_fn(self):
+        return self.lib.sg2_synth_create
 
     def describe(self):
         buf = C.create_string_buffer(1 << 16)
@@ -368,3 +371,68 @@ class SynthesisFunction(torch.autograd.Function):
     def backward(ctx, grad_image):
         g = ctx.engine.train_backward(ctx.state, grad_image)
         return g.to(ctx.lat_dtype), None, None
+
+
+class _AdaView:
+    """what SynthesisEngine reads from a Generator, answered by a stylegan2_ada SynthesisNetwork"""
+
+    def __init__(self, syn):
+        import types
+        self.syn = syn
+        self.size, self.style_dim = syn.img_resolution, syn.w_dim
+        self.log_size = syn.img_resolution_log2
+        self.n_latent = 2 * self.log_size - 2            # rows of ws the layers read (the reference allocates two more)
+        self.num_layers = 2 * (self.log_size - 2) + 1
+        self.input = types.SimpleNamespace(input=syn.first_block.const)
+
+    def parameters(self):
+        return self.syn.parameters()
+
+
+class AdaSynthesisEngine(SynthesisEngine):
+    """The same launch plan for the stylegan2_ada decoder (`sg2_synth_create_ada`): conv -> SmoothUpsample ordering,
+    clamps, no equalised-lr conv scale.  Inference only (the differentiable composition stays in stylegan2_ada/)."""
+
+    def __init__(self, synthesis, max_batch=8, use_graph=None):
+        super().__init__(_AdaView(synthesis), max_batch=max_batch, use_graph=use_graph)
+
+    def _create_fn(self):
+        return self.lib.sg2_synth_create_ada
+
+    def _layer_table(self):
+        syn = self.G.syn
+        dev = syn.first_block.const.device
+        keep = []
+
+        def f32(t):
+            t = t.detach()
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                t = t.float().contiguous()
+            keep.append(t)
+            return t.data_ptr()
+
+        rows = []
+
+        def styled(m, latent_index, res, up):
+            cout, cin = m.weight.shape[:2]
+            rows.append(_lib.ConvParams(f32(m.weight), f32(m.affine.weight), f32(m.affine.bias), f32(m.noise_strength),
+                                        f32(m.bias), cin, cout, 3, 1 if up else 0, latent_index, res))
+
+        def rgb(m, latent_index, res):
+            cout, cin = m.weight.shape[:2]
+            rows.append(_lib.ConvParams(f32(m.weight), f32(m.affine.weight), f32(m.affine.bias), None, f32(m.bias), cin, cout,
+                                        1, 0, latent_index, res))
+
+        fb = syn.first_block
+        styled(fb.conv1, 0, 4, False)
+        rgb(fb.torgb, 1, 4)
+        for n, blk in enumerate(syn.blocks):
+            res = 8 << n
+            styled(blk.conv0, 2 * n + 1, res, True)
+            styled(blk.conv1, 2 * n + 2, res, False)
+            rgb(blk.torgb, 2 * n + 3, res)
+        const = f32(fb.const)
+        taps = (syn.blocks[0].resampler.kernel.detach().float().cpu().reshape(4, 4).contiguous() if len(syn.blocks)
+                else torch.zeros(4, 4))
+        self._keep = keep + [taps]
+        return rows, const, taps, dev

@@ -101,7 +101,45 @@ class SynthesisNetwork(torch.nn.Module):                     # generator.py:55-8
         for m in self.modules():
             m.__dict__.pop('_tc_cache', None)
 
+    # -- whole-network bf16 engine (csrc/synth.cu, sg2_synth_create_ada): the same launch plan as the rosinality decoder's --
+    def _use_engine(self, ws, noise_mode):
+        if self.precision != 'bf16' or not ws.is_cuda or noise_mode not in ('const', 'random'):
+            return False
+        if K.needs_grad(ws, *self.parameters()) or os.environ.get('SG2_B200_ADA_ENGINE', '1') == '0':
+            return False
+        widths = [self.first_block.conv1.weight.shape[0]] + [b.conv1.weight.shape[0] for b in self.blocks]
+        return (self.img_channels == 3 and self.w_dim % 32 == 0 and self.w_dim <= 512 and self.img_resolution >= 8
+                and all(c % 32 == 0 and c <= 512 for c in widths) and self.first_block.const.dtype == torch.float32)
+
+    def engine(self):
+        dev = self.first_block.const.device
+        eng = self.__dict__.get('_engine')
+        if eng is None or eng.device != dev:
+            from ..engine import AdaSynthesisEngine
+            eng = AdaSynthesisEngine(self)
+            self.__dict__['_engine'] = eng
+        return eng
+
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state.pop('_engine', None)
+        return state
+
+    def _replicate_for_data_parallel(self):
+        replica = super()._replicate_for_data_parallel()
+        replica.__dict__.pop('_engine', None)
+        return replica
+
     def forward(self, ws, noise_mode='random', return_latents=False, **kwargs):
+        if self._use_engine(ws, noise_mode):
+            eng = self.engine()
+            noise = [None] * eng.G.num_layers
+            if noise_mode == 'const':
+                noise = [self.first_block.conv1.noise_const]
+                for b in self.blocks:
+                    noise += [b.conv0.noise_const, b.conv1.noise_const]
+            img = eng.synthesize(ws[:, :eng.G.n_latent], noise)
+            return (img, None) if return_latents else [img]
         split_ws = [ws[:, 0:2, :]] + [ws[:, 2 * n + 1: 2 * n + 4, :] for n in range(len(self.block_resolutions))]
         with K.tc_grad(True if self.precision == 'bf16' else (False if self.precision == 'exact' else None)):
             x, img = self.first_block(split_ws[0], noise_mode)

@@ -269,3 +269,35 @@ def test_ada_generator_bf16_precision(sg2):
     with torch.no_grad():
         img3, _ = G([ws0.to(DEV)], input_is_latent=True, randomize_noise=False)
     assert (img3.cpu().double() - ref.detach()).abs().max() <= 2e-4 * ref.abs().max()
+
+
+@pytest.mark.parametrize("res,b", [(16, 3), (64, 3), (256, 8)])
+def test_ada_engine_vs_exact(sg2, res, b):
+    """the ADA decoder on the whole-network bf16 engine (sg2_synth_create_ada: conv -> SmoothUpsample ordering, clamps,
+    SmoothUpsample of the running image) against the exact fp32 path, itself pinned to the golden vectors of the
+    unmodified reference module (test_ada_generator_golden) -- full images, per-sample worst case"""
+    from oracle import sg2_ada_oracle as A
+    from oracle.sg2_oracle import named_randn
+    gen, U = _ada()
+    nl = 2 if res < 256 else 8
+    sd = A.init_state_dict(res, 512, 512, nl, seed=0)
+    G = gen.Generator(512, 512, nl, res, 3)
+    G.load_state_dict(sd, strict=True)
+    G = G.to(DEV).eval()
+    z = named_randn(f"ada:eng:z{res}", (b, 512), 7).to(DEV)
+    with torch.no_grad():
+        G.precision = 'exact'
+        ref, _ = G([z], randomize_noise=False)
+        G.precision = 'bf16'
+        assert G.synthesis._use_engine(torch.zeros(1, 4, 512, device=DEV), 'const')
+        n0 = sg2._lib.launch_count()
+        img, _ = G([z], randomize_noise=False)
+        img2, _ = G([z], randomize_noise=False)
+        assert "smoothup" in G.synthesis.engine().describe() and sg2._lib.launch_count() > n0
+        rnd, _ = G([z], randomize_noise=True)
+    assert img.shape == ref.shape and torch.equal(img, img2) and torch.isfinite(rnd).all() and not torch.equal(rnd, img)
+    d = img.float() - ref.float()
+    rel_max = (d.abs().amax(dim=(1, 2, 3)) / ref.abs().max()).max().item()
+    rel_l2 = (d.flatten(1).norm(dim=1) / ref.float().flatten(1).norm(dim=1)).max().item()
+    print(f"[parity] ADA engine {res}^2 B={b}: max|d|/|ref|max = {rel_max:.3e}, worst per-sample rel-L2 = {rel_l2:.3e}")
+    assert rel_max <= 1.6e-2 and rel_l2 <= 2.4e-2, (rel_max, rel_l2)
