@@ -65,7 +65,7 @@ def ncu_traffic(size, batch):
             rows = json.load(open(path))
         except Exception:
             continue
-        gemm = [r for r in rows if "modconv_gemm" in r.get("kernel", "")]
+        gemm = [r for r in rows if "modconv_" in r.get("kernel", "")]       # modconv_gemm / _gemm2 / _gemm2_poly4 / _dxs
         if gemm:
             tot = sum(r["dram__bytes_read.sum"]["value"] + r["dram__bytes_write.sum"]["value"] for r in gemm)
             return tot, os.path.relpath(path, ROOT), len(gemm)
@@ -333,7 +333,7 @@ def roofline_of(ctx, table, size, B):
     peak = peaks["bf16_tflops_sustained"]
     traffic, traffic_src, traffic_n = ncu_traffic(size, B)
     by = sum(r["bytes"] for r in gemm)
-    roofline = {"bound": "tensor", "kernel": "modconv_gemm_kernel (tcgen05 implicit GEMM, all launches of one step)",
+    roofline = {"bound": "tensor", "kernel": "modconv_gemm* / modconv_dxs (tcgen05 implicit GEMM family, all launches of one step)",
                 "achieved": round(fl / tt / 1e12, 2), "peak": peak, "unit": "TFLOP/s", "frac": round(fl / tt / 1e12 / peak, 4),
                 "traffic": traffic, "traffic_unit": "DRAM bytes per step (read + write), all launches of the kernel",
                 "traffic_source": traffic_src if traffic_n == len(gemm) else

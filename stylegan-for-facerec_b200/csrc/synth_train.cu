@@ -78,6 +78,7 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 // (2 x 16-byte loads + one 16-byte store per 8 elements): the loads of the NEXT pixel are issued before the math of the
 // current one; two blocks per SM (128 registers: no spills).
 struct EpassIn { uint4 st, gs; float nz, g0, g1, g2; };
+template <bool RGB>
 __device__ __forceinline__ EpassIn epass_load(const EpassParams &p, int b, int px, int c0, float nw) {
     EpassIn in;
     const long long e = ((long long)b * p.HW + px) * p.C + c0;
@@ -85,13 +86,14 @@ __device__ __forceinline__ EpassIn epass_load(const EpassParams &p, int b, int p
     in.gs = p.g_st ? __ldg(reinterpret_cast<const uint4 *>(p.g_st + e)) : make_uint4(0, 0, 0, 0);
     in.nz = p.noise ? nw * __ldg(p.noise + (long long)b * p.noise_bstride + px) : 0.f;
     in.g0 = in.g1 = in.g2 = 0.f;
-    if (p.g_rgb) {
+    if (RGB) {
         const float *gr = p.g_rgb + (long long)b * 3 * p.HW + px;
         in.g0 = __ldg(gr); in.g1 = __ldg(gr + p.HW); in.g2 = __ldg(gr + 2 * (long long)p.HW);
     }
     return in;
 }
 
+template <bool RGB>      // RGB: this conv feeds a ToRGB (every non-up-sampling layer); the up-sampling layers carry 32 registers less
 __global__ void __launch_bounds__(256, 2)
 train_epass_kernel(EpassParams p) {
     __shared__ float red[3][512];
@@ -112,7 +114,7 @@ train_epass_kernel(EpassParams p) {
         dd[j] = __ldg(p.d + (long long)b * p.C + c);
         bb[j] = __ldg(p.bias + c);
         w0[j] = w1[j] = w2[j] = 0.f;
-        if (p.g_rgb) {
+        if (RGB) {
             const float sr = kSqrt2 * __ldg(p.s_rgb + (long long)b * p.C + c);
             w0[j] = sr * __ldg(p.rgb_w + c); w1[j] = sr * __ldg(p.rgb_w + p.C + c); w2[j] = sr * __ldg(p.rgb_w + 2 * p.C + c);
         }
@@ -126,21 +128,21 @@ train_epass_kernel(EpassParams p) {
     const int stride = gridDim.x * ppi;
     int px = blockIdx.x * ppi + pl;
     EpassIn cur;
-    if (px < p.HW) cur = epass_load(p, b, px, c0, nw);
+    if (px < p.HW) cur = epass_load<RGB>(p, b, px, c0, nw);
     while (px < p.HW) {
         const int pxn = px + stride;
         EpassIn nxt;
-        if (pxn < p.HW) nxt = epass_load(p, b, pxn, c0, nw);
+        if (pxn < p.HW) nxt = epass_load<RGB>(p, b, pxn, c0, nw);
         float st[8], gs[8], out[8];
         unpack8(cur.st, st);
         unpack8(cur.gs, gs);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const float a = st[j] * isig[j];
-            const float grw = cur.g0 * w0[j] + cur.g1 * w1[j] + cur.g2 * w2[j];      // sum_k g_rgb[k] * rho[k, c]
+            const float grw = RGB ? cur.g0 * w0[j] + cur.g1 * w1[j] + cur.g2 * w2[j] : 0.f;      // sum_k g_rgb[k] * rho[k, c]
             const float ga = fmaf(gs[j], sig[j], grw);
             rsn[j] = fmaf(gs[j], a, rsn[j]);
-            rsr[j] = fmaf(grw, a, rsr[j]);
+            if (RGB) rsr[j] = fmaf(grw, a, rsr[j]);
             const bool pos = a > 0.f;
             const float gy = pos ? ga : kSlopeT * ga;
             const float y = pos ? a : a * (1.f / kSlopeT);
@@ -154,7 +156,7 @@ train_epass_kernel(EpassParams p) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         if (p.g_s_next) atomicAdd(&red[0][c0 + j], rsn[j] * kSqrt2);
-        if (p.g_rgb) {
+        if (RGB) {
             // rho = sqrt(2) s_rgb w: dL/ds_rgb = sum a * sqrt(2) * sum_k g_k w_k = rsr / s_rgb (a channel with s_rgb == 0 carries no rgb term)
             const float sr = __ldg(p.s_rgb + (long long)b * p.C + c0 + j);
             atomicAdd(&red[1][c0 + j], fabsf(sr) > 1e-20f ? rsr[j] / sr : 0.f);
@@ -165,7 +167,7 @@ train_epass_kernel(EpassParams p) {
     for (int c = threadIdx.x; c < p.C; c += 256) {
         const long long o = (long long)b * p.C + c;
         if (p.g_s_next) atomicAdd(p.g_s_next + o, red[0][c]);
-        if (p.g_rgb) atomicAdd(p.g_s_rgb + o, red[1][c]);
+        if (RGB) atomicAdd(p.g_s_rgb + o, red[1][c]);
         atomicAdd(p.g_d + o, red[2][c]);
     }
 }
@@ -178,14 +180,19 @@ struct FirTParams { const __nv_bfloat16 *g; __nv_bfloat16 *planes; int B, r, C; 
 __global__ void __launch_bounds__(256)
 train_firT_kernel(FirTParams p) {
     const int P = p.r + 1, R = 2 * p.r, c8n = p.C >> 3;
-    const long long total = (long long)p.B * P * P * c8n;
     const long long plane_elems = (long long)p.B * P * P * p.C;
-    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
-        const int c8 = (int)(i % c8n);
-        long long rest = i / c8n;
-        const int x = (int)(rest % P);
-        rest /= P;
-        const int y = (int)(rest % P), b = (int)(rest / P);
+    // a block = a tw x th patch of plane pixels x all channel groups, so that the overlapping 5 x 5 windows of neighbouring
+    // pixels are served by L1 (one g pixel is read by ~6 threads): 256 threads = c8n channel groups x tw x th
+    const int ppb = 256 / c8n, tw = ppb >= 64 ? 8 : (ppb >= 16 ? 4 : (ppb >= 4 ? 2 : 1)), th = ppb / tw;
+    const int tiles_x = (P + tw - 1) / tw, tiles_y = (P + th - 1) / th;
+    const long long n_tiles = (long long)p.B * tiles_x * tiles_y;
+    const int c8 = threadIdx.x % c8n, lp = threadIdx.x / c8n, lx = lp % tw, ly = lp / tw;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int bx = (int)(tile % tiles_x);
+        const long long rest = tile / tiles_x;
+        const int by = (int)(rest % tiles_y), b = (int)(rest / tiles_y);
+        const int x = bx * tw + lx, y = by * th + ly;
+        if (x >= P || y >= P) continue;
         float acc[4][8];
 #pragma unroll
         for (int q = 0; q < 4; ++q)
@@ -264,24 +271,46 @@ const_grad_kernel(float *__restrict__ g_s0, const __nv_bfloat16 *__restrict__ g_
 }
 
 // d = rsqrt(sum_ci s^2 wsq + eps):  dL/ds[b, ci] -= s[b, ci] * sum_co dL/dd[b, co] * d[b, co]^3 * wsq[ci, co]
+// grid (ceil(cin / 8), ceil(B / 8), layers); a warp owns one ci, its lanes walk co (coalesced wsq rows), 8 samples at a time
 struct DemodGradJob { const float *style, *wsq, *demod, *g_d; float *g_s; int cin, cout; };
 struct DemodGradJobs { DemodGradJob job[kMaxJobs]; int n; };
 __global__ void __launch_bounds__(256)
 demod_grad_kernel(DemodGradJobs jobs, int B) {
-    __shared__ float t[512];
+    __shared__ float t[8][512];
     const DemodGradJob &j = jobs.job[blockIdx.z];
-    const int b = blockIdx.y;
-    if (b >= B) return;
-    for (int co = threadIdx.x; co < j.cout; co += 256) {
-        const float dv = __ldg(j.demod + (long long)b * j.cout + co);
-        t[co] = __ldg(j.g_d + (long long)b * j.cout + co) * dv * dv * dv;
+    const int b0 = blockIdx.y * 8, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < 8 * j.cout; i += 256) {
+        const int bb = i / j.cout, co = i - bb * j.cout, b = b0 + bb;
+        float v = 0.f;
+        if (b < B) {
+            const float dv = __ldg(j.demod + (long long)b * j.cout + co);
+            v = __ldg(j.g_d + (long long)b * j.cout + co) * dv * dv * dv;
+        }
+        t[bb][co] = v;
     }
     __syncthreads();
-    for (int ci = blockIdx.x * 256 + threadIdx.x; ci < j.cin; ci += gridDim.x * 256) {
-        const float *wr = j.wsq + (long long)ci * j.cout;
-        float acc = 0.f;
-        for (int co = 0; co < j.cout; ++co) acc = fmaf(t[co], __ldg(wr + co), acc);
-        j.g_s[(long long)b * j.cin + ci] -= __ldg(j.style + (long long)b * j.cin + ci) * acc;
+    const int ci = blockIdx.x * 8 + warp;
+    if (ci >= j.cin) return;
+    float acc[8];
+#pragma unroll
+    for (int bb = 0; bb < 8; ++bb) acc[bb] = 0.f;
+    const float *wr = j.wsq + (long long)ci * j.cout;
+    for (int co = lane; co < j.cout; co += 32) {
+        const float w = __ldg(wr + co);
+#pragma unroll
+        for (int bb = 0; bb < 8; ++bb) acc[bb] = fmaf(w, t[bb][co], acc[bb]);
+    }
+#pragma unroll
+    for (int bb = 0; bb < 8; ++bb) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[bb] += __shfl_xor_sync(0xffffffffu, acc[bb], o);
+    }
+    if (lane < 8 && b0 + lane < B) {
+        float a = acc[0];
+#pragma unroll
+        for (int bb = 1; bb < 8; ++bb) a = lane == bb ? acc[bb] : a;
+        const long long o = (long long)(b0 + lane) * j.cin + ci;
+        j.g_s[o] -= __ldg(j.style + o) * a;
     }
 }
 
@@ -495,7 +524,8 @@ extern "C" int sg2_synth_backward(sg2_synth *S, void *workspace, int64_t B64, co
         {
             const int ppi = 256 / (e.C / 8);
             const int nblk = std::max(1, std::min((e.HW + ppi * 8 - 1) / (ppi * 8), 2048));
-            train_epass_kernel<<<dim3(nblk, B), 256, 0, st>>>(e);
+            if (e.g_rgb) train_epass_kernel<true><<<dim3(nblk, B), 256, 0, st>>>(e);
+            else train_epass_kernel<false><<<dim3(nblk, B), 256, 0, st>>>(e);
             SG2_LAUNCH_CHECK();
         }
         Layer &BL = S->blayers[L.conv_index];
@@ -503,8 +533,9 @@ extern "C" int sg2_synth_backward(sg2_synth *S, void *workspace, int64_t B64, co
             FirTParams f;
             f.g = Gc; f.planes = GT; f.B = B; f.r = L.res_in; f.C = L.p.cout;
             memcpy(f.kf, S->kf, sizeof(f.kf));
-            const long long total = (long long)B * (f.r + 1) * (f.r + 1) * (f.C / 8);
-            train_firT_kernel<<<(unsigned)std::min<long long>(ceil_div64(total, 256), 148 * 32), 256, 0, st>>>(f);
+            const int c8n = f.C / 8, ppb = 256 / c8n, tw = ppb >= 64 ? 8 : (ppb >= 16 ? 4 : (ppb >= 4 ? 2 : 1)), th = ppb / tw;
+            const long long n_tiles = (long long)B * ((f.r + tw) / tw) * ((f.r + th) / th);       // ceil((r + 1) / t)
+            train_firT_kernel<<<(unsigned)std::min<long long>(n_tiles, 148 * 16), 256, 0, st>>>(f);
             SG2_LAUNCH_CHECK();
         }
         GemmParams g = BL.gp;
@@ -530,7 +561,9 @@ extern "C" int sg2_synth_backward(sg2_synth *S, void *workspace, int64_t B64, co
             j.style = (const float *)(ws + L.style); j.wsq = (const float *)(ws + L.wsq); j.demod = (const float *)(ws + L.demod);
             j.g_d = (const float *)(ws + L.gd); j.g_s = grad_styles + goff[i]; j.cin = L.p.cin; j.cout = L.p.cout;
         }
-        demod_grad_kernel<<<dim3(2, B, dj.n), 256, 0, st>>>(dj, B);
+        int max_cin = 0;
+        for (int q = 0; q < dj.n; ++q) max_cin = std::max(max_cin, dj.job[q].cin);
+        demod_grad_kernel<<<dim3((max_cin + 7) / 8, (B + 7) / 8, dj.n), 256, 0, st>>>(dj, B);
         SG2_LAUNCH_CHECK();
     }
     return SG2_OK;
