@@ -181,18 +181,13 @@ __global__ void __launch_bounds__(256)
 train_firT_kernel(FirTParams p) {
     const int P = p.r + 1, R = 2 * p.r, c8n = p.C >> 3;
     const long long plane_elems = (long long)p.B * P * P * p.C;
-    // a block = a tw x th patch of plane pixels x all channel groups, so that the overlapping 5 x 5 windows of neighbouring
-    // pixels are served by L1 (one g pixel is read by ~6 threads): 256 threads = c8n channel groups x tw x th
-    const int ppb = 256 / c8n, tw = ppb >= 64 ? 8 : (ppb >= 16 ? 4 : (ppb >= 4 ? 2 : 1)), th = ppb / tw;
-    const int tiles_x = (P + tw - 1) / tw, tiles_y = (P + th - 1) / th;
-    const long long n_tiles = (long long)p.B * tiles_x * tiles_y;
-    const int c8 = threadIdx.x % c8n, lp = threadIdx.x / c8n, lx = lp % tw, ly = lp / tw;
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int bx = (int)(tile % tiles_x);
-        const long long rest = tile / tiles_x;
-        const int by = (int)(rest % tiles_y), b = (int)(rest / tiles_y);
-        const int x = bx * tw + lx, y = by * th + ly;
-        if (x >= P || y >= P) continue;
+    const long long total = (long long)p.B * P * P * c8n;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        const int c8 = (int)(i % c8n);
+        long long rest = i / c8n;
+        const int x = (int)(rest % P);
+        rest /= P;
+        const int y = (int)(rest % P), b = (int)(rest / P);
         float acc[4][8];
 #pragma unroll
         for (int q = 0; q < 4; ++q)
@@ -523,7 +518,11 @@ extern "C" int sg2_synth_backward(sg2_synth *S, void *workspace, int64_t B64, co
         SG2_REQUIRE(g_cur || rgb, SG2_ERR_BAD_ARG, "synth_backward: layer %d receives no gradient", i);
         {
             const int ppi = 256 / (e.C / 8);
-            const int nblk = std::max(1, std::min((e.HW + ppi * 8 - 1) / (ppi * 8), 2048));
+            // >= 32 pixels per thread where the plane allows it (per-block set-up: 8 x 7 constants, 24 shared-memory atomics),
+            // while keeping at least ~4 blocks per SM over the batch
+            int per = 32;
+            while (per > 4 && (long long)((e.HW + ppi * per - 1) / (ppi * per)) * B < 4 * 148) per >>= 1;
+            const int nblk = std::max(1, std::min((e.HW + ppi * per - 1) / (ppi * per), 2048));
             if (e.g_rgb) train_epass_kernel<true><<<dim3(nblk, B), 256, 0, st>>>(e);
             else train_epass_kernel<false><<<dim3(nblk, B), 256, 0, st>>>(e);
             SG2_LAUNCH_CHECK();
@@ -533,9 +532,9 @@ extern "C" int sg2_synth_backward(sg2_synth *S, void *workspace, int64_t B64, co
             FirTParams f;
             f.g = Gc; f.planes = GT; f.B = B; f.r = L.res_in; f.C = L.p.cout;
             memcpy(f.kf, S->kf, sizeof(f.kf));
-            const int c8n = f.C / 8, ppb = 256 / c8n, tw = ppb >= 64 ? 8 : (ppb >= 16 ? 4 : (ppb >= 4 ? 2 : 1)), th = ppb / tw;
-            const long long n_tiles = (long long)B * ((f.r + tw) / tw) * ((f.r + th) / th);       // ceil((r + 1) / t)
-            train_firT_kernel<<<(unsigned)std::min<long long>(n_tiles, 148 * 16), 256, 0, st>>>(f);
+            // (row-major thread order: a 2-D thread tile for L1 reuse of the windows measured slower, 1.14 -> 1.48 ms at B = 32)
+            const long long total = (long long)B * (f.r + 1) * (f.r + 1) * (f.C / 8);
+            train_firT_kernel<<<(unsigned)std::min<long long>(ceil_div64(total, 256), 148 * 32), 256, 0, st>>>(f);
             SG2_LAUNCH_CHECK();
         }
         GemmParams g = BL.gp;
