@@ -116,7 +116,7 @@ int plan_gemm(sg2_synth *S, Layer &L, const int *custom_taps, int n_custom, cons
     // the weight stream, which is 1/3 of the layer's L2 -> SM traffic.  SG2_GEMM_RES2=0 switches it off.
     static const char *envr2 = getenv("SG2_GEMM_RES2");
     g.resident2 = 0;
-    if (L.two_sm && fused && g.n_tiles_n == 1 && (!envr2 || atoi(envr2) != 0)) {
+    if (L.two_sm && !up && !custom_taps && g.n_tiles_n == 1 && (envr2 ? atoi(envr2) != 0 : fused)) {     // SG2_GEMM_RES2=1: every pair layer that fits
         const int half_b = 9 * g.kchunks * (best_n / 2) * g.block_k * 2;
         const int a_stage = kBlockM * g.block_k * 2 * g.kpack;
         if (half_b + 4 * a_stage <= kGemm2RingBytes) g.resident2 = 1;
@@ -156,6 +156,7 @@ int plan_gemm(sg2_synth *S, Layer &L, const int *custom_taps, int n_custom, cons
             // (tile-split epilogue + SWIZZLE_64B operands) -- kept for the next round, see profiles/experiments
             g.mma2 = (envm && atoi(envm) != 0) ? 1 : 0;
             g.resident = 1; g.resb_bytes = resb; g.stage_bytes = pick_stage;
+            g.resident2 = 0;
             g.block_k = pick_bk; g.kchunks = cin / pick_bk; g.kpack = 1;
             L.two_sm = false;
             for (int s = 0; s < g.nsub; ++s) {
@@ -719,10 +720,21 @@ extern "C" int sg2_synth_forward(sg2_synth *S, void *workspace, const float *lat
                 d.rgb_style = (const float *)(ws + rgb->style);
                 d.rgb_part = part;
             }
+            // the network's last layer can write the final image from its epilogue (no partial plane, no rgb_combine pass).
+            // Measured at 1024^2, B = 32: the conv grows by 0.34 ms (its epilogue is the paced role: every instruction added per
+            // pixel shows), rgb_combine saves 0.26 ms -> opt-in only, SG2_DXS_IMAGE=1.
+            static const char *envfi = getenv("SG2_DXS_IMAGE");
+            const bool fuse_image = rgb && !next_conv && !S->ada && L.p.cout == 32 && envfi && atoi(envfi) != 0;
+            if (fuse_image) {
+                d.image = image; d.rgb_bias = rgb->p.act_bias; d.prev = rgb_cur >= 0 ? rgbbuf[rgb_cur] : nullptr;
+                memcpy(d.kf, S->kf, sizeof(d.kf));
+            }
             rc = launch_modconv_dxs(d, L.tmDA, L.tmDB, S->sms, st);
             if (rc) return rc;
             if ((rc = rec(S, st, "gemm(dx-stacked)"))) return rc;
-            if (rgb) {
+            if (fuse_image) {
+                if ((rc = rec(S, st, "rgb_combine (fused into the conv)"))) return rc;
+            } else if (rgb) {
                 RgbParams rp;
                 const bool last = next_conv == nullptr;
                 const int dst = rgb_cur == 0 ? 1 : 0;

@@ -111,6 +111,12 @@ struct DxsParams {
     float clamp;                             // as GemmParams::clamp
     float *rgb_part;                         // [col_groups][B, 3, R, R], col_groups = 1 (Cout = 32) or 2 (Cout = 64)
     __nv_bfloat16 *out;                      // NHWC bf16 or null
+    // last layer of the network (Cout = 32: one column group holds a pixel's whole ToRGB sum): write the final image
+    // directly -- rgb + bias + Upsample(skip) (model.py:350-359) -- instead of a partial plane for rgb_combine_kernel
+    float *image;                            // [B, 3, R, R] fp32 or null
+    const float *rgb_bias;                   // [3]
+    const float *prev;                       // [B, 3, R/2, R/2] running skip image, or null
+    float kf[16];                            // flipped 4x4 taps (x4) of the skip Upsample
 };
 // tmA: NHWC activations, box {Cin, 32, 6, 1}; tmB: weights [3][3*Cout][Cin] (= the packed [tap][Cout][Cin] layout), box {Cin, 3*Cout, 1}
 int launch_modconv_dxs(const DxsParams &p, const CUtensorMap &tmA, const CUtensorMap &tmB, int sm_count, cudaStream_t st);

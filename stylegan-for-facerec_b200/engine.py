@@ -412,16 +412,34 @@ class AdaSynthesisEngine(SynthesisEngine):
             return t.data_ptr()
 
         rows = []
+        PAD = 32      # narrowest channel count of the tensor-core kernels (one 64-byte swizzle row)
+
+        # Layers narrower than 32 channels (the 1024^2 block of the ADA decoder has 16) run zero-padded to 32: padded input
+        # channels get a zero style (affine weight and bias rows = 0) and zero weights, padded output channels zero weights, a
+        # zero bias and -- through the consumer's zero style -- are stored as exact zeros, so the arithmetic of the real
+        # channels is untouched; it costs 2x the bytes on those layers only.
+        def padded(t, shape):
+            t = t.detach().float()
+            if tuple(t.shape) == tuple(shape):
+                return t
+            out = torch.zeros(shape, device=t.device, dtype=torch.float32)
+            out[tuple(slice(0, n) for n in t.shape)] = t
+            return out
 
         def styled(m, latent_index, res, up):
             cout, cin = m.weight.shape[:2]
-            rows.append(_lib.ConvParams(f32(m.weight), f32(m.affine.weight), f32(m.affine.bias), f32(m.noise_strength),
-                                        f32(m.bias), cin, cout, 3, 1 if up else 0, latent_index, res))
+            co, ci = max(cout, PAD), max(cin, PAD)
+            rows.append(_lib.ConvParams(f32(padded(m.weight, (co, ci, 3, 3))), f32(padded(m.affine.weight, (ci, m.affine.weight.shape[1]))),
+                                        f32(padded(m.affine.bias, (ci,))), f32(m.noise_strength), f32(padded(m.bias, (co,))),
+                                        ci, co, 3, 1 if up else 0, latent_index, res))
 
         def rgb(m, latent_index, res):
             cout, cin = m.weight.shape[:2]
-            rows.append(_lib.ConvParams(f32(m.weight), f32(m.affine.weight), f32(m.affine.bias), None, f32(m.bias), cin, cout,
-                                        1, 0, latent_index, res))
+            ci = max(cin, PAD)
+            # the ToRGB weight gain 1 / sqrt(cin) is applied by the engine from the PADDED width: pre-compensate
+            w = padded(m.weight, (cout, ci, 1, 1)) * float((ci / cin) ** 0.5)
+            rows.append(_lib.ConvParams(f32(w), f32(padded(m.affine.weight, (ci, m.affine.weight.shape[1]))),
+                                        f32(padded(m.affine.bias, (ci,))), None, f32(m.bias), ci, cout, 1, 0, latent_index, res))
 
         fb = syn.first_block
         styled(fb.conv1, 0, 4, False)

@@ -109,7 +109,7 @@ class SynthesisNetwork(torch.nn.Module):                     # generator.py:55-8
             return False
         widths = [self.first_block.conv1.weight.shape[0]] + [b.conv1.weight.shape[0] for b in self.blocks]
         return (self.img_channels == 3 and self.w_dim % 32 == 0 and self.w_dim <= 512 and self.img_resolution >= 8
-                and all(c % 32 == 0 and c <= 512 for c in widths) and self.first_block.const.dtype == torch.float32)
+                and all(c % 16 == 0 and 16 <= c <= 512 for c in widths) and self.first_block.const.dtype == torch.float32)
 
     def engine(self):
         dev = self.first_block.const.device
