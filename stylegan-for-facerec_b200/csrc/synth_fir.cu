@@ -42,26 +42,37 @@ constexpr int FT_STAGE_BYTES = FT_K * FT_N * 2;  // the window of one tile: 64 K
 // per CTA with tcgen05.st): the MMAs read only the window from shared memory.  The knock-out analysis showed the
 // kernel bound by the shared-memory port (per tile: 128 KiB of MMA operand reads + 61 KiB TMA fill + 32 KiB staging
 // + 32 KiB TMA-store reads at 128 B/clk); A-from-TMEM removes 64 KiB of that and frees 64 KiB for a third stage.
-#ifndef SG2_FIR_A_TMEM
-#define SG2_FIR_A_TMEM 0
+// SG2_FIR_GROUPS = 2: the epilogue warps form TWO groups that take alternate tiles (group g owns accumulator g, its own
+// staging buffer, parameter table and named barriers), so the serial per-tile chain of one group (accumulator wait, TMEM
+// load, math, staging, fence, barrier, TMA store) overlaps the other group's.  The second 32 KiB staging buffer takes the
+// place of the Toeplitz matrix, which then has to live in tensor memory.
+#ifndef SG2_FIR_GROUPS
+#define SG2_FIR_GROUPS 1
 #endif
-constexpr int FT_STAGES = SG2_FIR_A_TMEM ? 3 : 2;
+#ifndef SG2_FIR_A_TMEM
+#define SG2_FIR_A_TMEM (SG2_FIR_GROUPS == 2 ? 1 : 0)
+#endif
+static_assert(SG2_FIR_GROUPS == 1 || (SG2_FIR_GROUPS == 2 && SG2_FIR_A_TMEM), "two epilogue groups need the Toeplitz matrix in TMEM");
+constexpr int FT_GROUPS = SG2_FIR_GROUPS;
+constexpr int FT_STAGES = (SG2_FIR_A_TMEM && FT_GROUPS == 1) ? 3 : 2;
 constexpr int FT_A_BYTES = SG2_FIR_A_TMEM ? 16 : 128 * FT_K * 2;       // 64 KiB Toeplitz when it is a shared-memory operand
 constexpr int FT_TMEM_COLS = SG2_FIR_A_TMEM ? 512 : 256;                 // 2 accumulators (+ 128 columns of A)
 #ifndef SG2_FIR_EPI_WARPS
 #define SG2_FIR_EPI_WARPS 16
 #endif
-constexpr int FT_EPI_WARPS = SG2_FIR_EPI_WARPS;  // 4 warps per TMEM lane quarter: a 32-column chunk each (8: two chunks each)
+constexpr int FT_EPI_WARPS = SG2_FIR_EPI_WARPS;  // all epilogue warps of the CTA
+constexpr int FT_GW = FT_EPI_WARPS / FT_GROUPS;  // warps per group: 4 (2) per TMEM lane quarter, a 32-column chunk (two chunks) each
+constexpr int FT_GT = 32 * FT_GW;                // threads per group
 constexpr int FT_EPI_THREADS = 32 * FT_EPI_WARPS;
-constexpr int FT_CPW = 16 / FT_EPI_WARPS;        // 32-column chunks per epilogue warp
+constexpr int FT_CPW = 16 / FT_GW;               // 32-column chunks per epilogue warp
 constexpr int FT_THREADS = 64 + FT_EPI_THREADS;
-static_assert(FT_EPI_WARPS == 8 || FT_EPI_WARPS == 16, "epilogue: 2 or 4 warps per TMEM lane quarter");
+static_assert(FT_GW == 8 || FT_GW == 16, "epilogue: 2 or 4 warps per TMEM lane quarter and group");
 
 struct __align__(1024) FirSmem {
     uint8_t b[FT_STAGES * FT_STAGE_BYTES];
-    uint8_t o[128 * FT_N * 2];                     // bf16 output tile [column block][128 px][cbw] in the TMA store layout
+    uint8_t o[FT_GROUPS][128 * FT_N * 2];          // bf16 output tile [column block][128 px][cbw] in the TMA store layout, per group
     uint8_t a[FT_A_BYTES];                         // Toeplitz matrix when it is a shared-memory operand (else unused)
-    float2 e_tab[2][FT_N];                         // {bias, sqrt(2) * style of the consumer} per column, double buffered by tile parity
+    float2 e_tab[FT_GROUPS][2][FT_N];              // {bias, sqrt(2) * style of the consumer} per column, double buffered by the group's tile parity
     uint64_t a_full;
     uint64_t full[FT_STAGES], empty[FT_STAGES];
     uint64_t tmem_full[2], tmem_empty[2];
@@ -140,7 +151,7 @@ upfir_tc_kernel(const __grid_constant__ UpfirTcParams p, const __grid_constant__
         tma_prefetch_desc(&tmT0);
         mbar_init(&sm.a_full, 1);
         for (int i = 0; i < FT_STAGES; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&sm.tmem_full[i], 1); mbar_init(&sm.tmem_empty[i], FT_EPI_WARPS); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&sm.tmem_full[i], 1); mbar_init(&sm.tmem_empty[i], FT_GW); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(&sm.tmem_base, FT_TMEM_COLS);
@@ -263,11 +274,17 @@ upfir_tc_kernel(const __grid_constant__ UpfirTcParams p, const __grid_constant__
         // kernel: its per-tile chain (store-read wait, TMEM load, math, staging, fence, barrier, store) is serial.
         // So: 16 warps (one 32-column chunk each, 4 per scheduler to hide the latencies) and packed f32x2 math.
         // warp (q, kq) owns pixels 32q..32q+31 x chunks kq*FT_CPW .. of every tile
-        const int q = warp & 3, kq = (warp - 2) >> 2;
+        const int grp = (warp - 2) / FT_GW, wg = (warp - 2) % FT_GW;   // group, warp inside the group
+        const int q = warp & 3, kq = wg >> 2;        // TMEM lane quarter (fixed by the warp id), chunk set of the warp
         const int m = q * 32 + lane;                 // output pixel of the tile: (m / 8, m % 8)
         const int oy = m >> 3, ox = m & 7;
-        const int et = threadIdx.x - 64;
-        const uint32_t e_tab_s = smem_u32(sm.e_tab), o_s = smem_u32(sm.o);
+        const int et = threadIdx.x - 64 - grp * FT_GT;       // thread inside the group
+        const uint32_t e_tab_s = smem_u32(sm.e_tab[grp]), o_s = smem_u32(sm.o[grp]);
+        uint8_t *const o_p = sm.o[grp];
+        float2 (*const e_tab)[FT_N] = sm.e_tab[grp];
+        const int bar_a = 1 + 3 * grp, bar_b = 2 + 3 * grp, bar_c = 3 + 3 * grp;   // named barriers of the group
+        // the group's tiles: every FT_GROUPS-th tile of the CTA, starting at its grp-th
+        const int g_lo = tile_lo + grp * tile_step, g_step = FT_GROUPS * tile_step;
         const int R = 2 * p.r;
         const float nw = p.noise ? __ldg(p.noise_weight) : 0.f;
         // the sample behind each of this warp's chunks
@@ -289,33 +306,36 @@ upfir_tc_kernel(const __grid_constant__ UpfirTcParams p, const __grid_constant__
         // Per-thread loads (noise, epilogue parameters) queue behind the ~120 KiB of TMA loads this SM keeps in flight
         // (ncu: they were the top two stall reasons at a distance of one tile), so both are fetched TWO tiles ahead:
         // q0 = this tile, q1 = next tile, the loads issued in this iteration are for the tile after that.
-        uint32_t acc = 0, acc_phase = 0, it = 0;
+        uint32_t it = 0;
         float nq0[FT_CPW], nq1[FT_CPW], nqf[FT_CPW];
         float2 pq1 = make_float2(0.f, 0.f), pqf = make_float2(0.f, 0.f);
 #pragma unroll
         for (int ci = 0; ci < FT_CPW; ++ci) nq0[ci] = nq1[ci] = nqf[ci] = 0.f;
         FirWalk w, wp;
-        w.init(p, tile_lo, tile_step);
+        w.init(p, g_lo < tile_hi ? g_lo : tile_lo, g_step);
         wp = w;
-        if (tile_lo < tile_hi) {
+        if (g_lo < tile_hi) {
             const FirTile t0 = wp.tile(p);
             wp.next(p);
 #pragma unroll
             for (int ci = 0; ci < FT_CPW; ++ci) nq0[ci] = (ci > 0 && ds[ci] == ds[0]) ? nq0[0] : noise_at(t0, ds[ci]);
-            if (et < FT_N) sm.e_tab[0][et] = params_at(t0);
-            if (tile_lo + tile_step < tile_hi) {
+            if (et < FT_N) e_tab[0][et] = params_at(t0);
+            if (g_lo + g_step < tile_hi) {
                 const FirTile t1 = wp.tile(p);
 #pragma unroll
                 for (int ci = 0; ci < FT_CPW; ++ci) nq1[ci] = (ci > 0 && ds[ci] == ds[0]) ? nq1[0] : noise_at(t1, ds[ci]);
                 if (et < FT_N) pq1 = params_at(t1);
             }
             wp.next(p);
-            asm volatile("bar.sync 1, %0;" ::"n"(FT_EPI_THREADS) : "memory");   // tile 0's table is staged
+            asm volatile("bar.sync %0, %1;" ::"r"(bar_a), "n"(FT_GT) : "memory");   // tile 0's table is staged
         }
-        for (int tile = tile_lo; tile < tile_hi; tile += tile_step, ++it) {
+        for (int tile = g_lo; tile < tile_hi; tile += g_step, ++it) {
             const FirTile t = w.tile(p);
             w.next(p);
-            if (tile + 2 * tile_step < tile_hi) {                // two tiles ahead
+            // accumulator of this tile: the MMA warp alternates over the CTA's tiles, i.e. group g of two always drains
+            // accumulator g
+            const uint32_t ti = (uint32_t)grp + it * FT_GROUPS, acc = ti & 1u, acc_phase = (ti >> 1) & 1u;
+            if (tile + 2 * g_step < tile_hi) {                   // two tiles ahead
                 const FirTile tf = wp.tile(p);
 #pragma unroll
                 for (int ci = 0; ci < FT_CPW; ++ci) nqf[ci] = (ci > 0 && ds[ci] == ds[0]) ? nqf[0] : noise_at(tf, ds[ci]);
@@ -362,7 +382,7 @@ upfir_tc_kernel(const __grid_constant__ UpfirTcParams p, const __grid_constant__
             if (SG2_DBG(p) & 2) {
             } else if (p.store_mode == 0) {
                 if (et == 0) tma_store_wait_read();
-                asm volatile("bar.sync 2, %0;" ::"n"(FT_EPI_THREADS) : "memory");
+                asm volatile("bar.sync %0, %1;" ::"r"(bar_b), "n"(FT_GT) : "memory");
             } else {
                 if (lane == 0) tma_store_wait_read();
                 __syncwarp();
@@ -386,34 +406,33 @@ upfir_tc_kernel(const __grid_constant__ UpfirTcParams p, const __grid_constant__
                                packed[ci][4 * v4 + 2], packed[ci][4 * v4 + 3]);
                 }
             }
-            if (et < FT_N) sm.e_tab[(it + 1) & 1u][et] = pq1;     // the next tile's table (read after this tile's last barrier)
+            if (et < FT_N) e_tab[(it + 1) & 1u][et] = pq1;     // the next tile's table (read after this tile's last barrier)
             fence_proxy_async();
             // rows / columns / samples beyond the tensor are clipped by the TMA unit
-            if ((SG2_DBG(p) & 2) || p.store_mode != 0) asm volatile("bar.sync 1, %0;" ::"n"(FT_EPI_THREADS) : "memory");   // table hand-over
+            if ((SG2_DBG(p) & 2) || p.store_mode != 0) asm volatile("bar.sync %0, %1;" ::"r"(bar_a), "n"(FT_GT) : "memory");   // table hand-over
             if (SG2_DBG(p) & 2) {
             } else if (p.store_mode == 0) {       // one thread stores whole column blocks (box cbw x 8 x 16); its barrier hands over the table
-                asm volatile("bar.sync 3, %0;" ::"n"(FT_EPI_THREADS) : "memory");
+                asm volatile("bar.sync %0, %1;" ::"r"(bar_c), "n"(FT_GT) : "memory");
                 if (et == 0) {
                     for (int cb = 0; cb < ncb; ++cb)
-                        tma_store_4d(&tmO, sm.o + cb * (128 * (int)row_bytes), t.ct * (cps * cbw) + (cb % cps) * cbw, t.x0, t.y0,
+                        tma_store_4d(&tmO, o_p + cb * (128 * (int)row_bytes), t.ct * (cps * cbw) + (cb % cps) * cbw, t.x0, t.y0,
                                      t.n0 + cb / cps);
                     tma_store_commit();
                 }
-            } else if (FT_EPI_WARPS == 8 && lane == 0) {   // every warp stores its own 32 pixels (box cbw x 8 x 4)
+            } else if (FT_GW == 8 && lane == 0) {   // every warp stores its own 32 pixels (box cbw x 8 x 4)
                 const int cb_a = (64 * kq) / cbw, cb_b = (64 * kq + 32) / cbw;
                 if (cbw == 64) {
-                    tma_store_4d(&tmO, sm.o + kq * (128 * 128) + q * 4096, t.ct * (cps * 64) + (cb_a % cps) * 64, t.x0,
+                    tma_store_4d(&tmO, o_p + kq * (128 * 128) + q * 4096, t.ct * (cps * 64) + (cb_a % cps) * 64, t.x0,
                                  t.y0 + 4 * q, t.n0 + cb_a / cps);
                 } else {
-                    tma_store_4d(&tmO, sm.o + cb_a * (128 * 64) + q * 2048, 0, t.x0, t.y0 + 4 * q, t.n0 + cb_a / cps);
-                    tma_store_4d(&tmO, sm.o + cb_b * (128 * 64) + q * 2048, 0, t.x0, t.y0 + 4 * q, t.n0 + cb_b / cps);
+                    tma_store_4d(&tmO, o_p + cb_a * (128 * 64) + q * 2048, 0, t.x0, t.y0 + 4 * q, t.n0 + cb_a / cps);
+                    tma_store_4d(&tmO, o_p + cb_b * (128 * 64) + q * 2048, 0, t.x0, t.y0 + 4 * q, t.n0 + cb_b / cps);
                 }
                 tma_store_commit();
             }
 #pragma unroll
             for (int ci = 0; ci < FT_CPW; ++ci) { nq0[ci] = nq1[ci]; nq1[ci] = nqf[ci]; }
             pq1 = pqf;
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
         if (lane == 0) tma_store_wait_all();     // threads without outstanding stores return at once
     }
@@ -452,7 +471,7 @@ int launch_upfir_tc(const UpfirTcParams &p, const CUtensorMap &tmK, const CUtens
     }
     SG2_REQUIRE((p.cbw == 64 || p.cbw == 32) && p.nsamp >= 1 && (FT_N / p.cbw) % p.nsamp == 0, SG2_ERR_BAD_ARG,
                 "upfir_tc: bad column blocking (cbw %d, %d samples per tile)", p.cbw, p.nsamp);
-    SG2_REQUIRE(p.store_mode == 0 || FT_EPI_WARPS == 8, SG2_ERR_BAD_ARG, "upfir_tc: per-warp stores need the 8-warp epilogue build");
+    SG2_REQUIRE(p.store_mode == 0 || FT_GW == 8, SG2_ERR_BAD_ARG, "upfir_tc: per-warp stores need the 8-warp epilogue build");
     const int grid = p.total_tiles < sms ? p.total_tiles : sms;
     if (grid <= 0) return SG2_OK;
     upfir_tc_kernel<<<grid, FT_THREADS, smem, st>>>(p, tmK, tmT[0], tmT[1], tmT[2], tmT[3], tmO);

@@ -215,8 +215,7 @@ modconv_dxs_kernel(const __grid_constant__ DxsParams p, const __grid_constant__ 
             mbar_wait(&sm.tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * acc_cols;
-            float2 r0 = make_float2(0.f, 0.f), r1 = r0, r2 = r0;        // ToRGB partial sums over (even, odd) channels
-            const float2 nz2 = make_float2(nz, nz), slope2 = make_float2(kDxSlope, kDxSlope);
+            float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
             uint32_t packed[16];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
@@ -231,50 +230,35 @@ modconv_dxs_kernel(const __grid_constant__ DxsParams p, const __grid_constant__ 
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&sm.tmem_empty[acc]);
                 }
-                // packed f32x2 math over channel pairs (FFMA2 / FADD2 / FMUL2, sm_100): this role paces the kernel -- one
-                // instruction per two channels wherever the ISA has one (no packed max, no packed shuffle)
-                const bool store = p.out != nullptr;
+                // (scalar fp32 math: a packed f32x2 version of this loop -- FFMA2 / FADD2 / FMUL2 over channel pairs -- spills
+                //  at the 96 registers 576 threads leave and measured 1.52 -> 1.87 ms; kept out)
 #pragma unroll
                 for (int j = 0; j < 16; j += 4) {
                     const float4 d4 = lds128f(smem_u32(e_demod + c0 + j)), b4 = lds128f(smem_u32(e_bias + c0 + j));
-                    float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f), w0 = s4, w1 = s4, w2 = s4;
-                    if (store) s4 = lds128f(smem_u32(e_next + c0 + j));
-                    if (p.rgb_w) {
-                        w0 = lds128f(smem_u32(e_w0 + c0 + j)); w1 = lds128f(smem_u32(e_w1 + c0 + j)); w2 = lds128f(smem_u32(e_w2 + c0 + j));
-                    }
-                    const float2 dd[2] = {make_float2(d4.x, d4.y), make_float2(d4.z, d4.w)};
-                    const float2 bb[2] = {make_float2(b4.x, b4.y), make_float2(b4.z, b4.w)};
-                    const float2 ss[2] = {make_float2(s4.x, s4.y), make_float2(s4.z, s4.w)};
-                    const float2 q0[2] = {make_float2(w0.x, w0.y), make_float2(w0.z, w0.w)};
-                    const float2 q1[2] = {make_float2(w1.x, w1.y), make_float2(w1.z, w1.w)};
-                    const float2 q2[2] = {make_float2(w2.x, w2.y), make_float2(w2.z, w2.w)};
+                    const float4 s4 = lds128f(smem_u32(e_next + c0 + j));
+                    const float dd[4] = {d4.x, d4.y, d4.z, d4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w}, ss[4] = {s4.x, s4.y, s4.z, s4.w};
+                    float v[4];
 #pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int k = j + 2 * e;
+                    for (int e = 0; e < 4; ++e) {
                         // out[x] = F_{-1}[x-1] + F_0[x] + F_{+1}[x+1]: the neighbours' blocks come by shuffle
-                        const float2 a = make_float2(__shfl_up_sync(0xffffffffu, __uint_as_float(fm[k]), 1),
-                                                     __shfl_up_sync(0xffffffffu, __uint_as_float(fm[k + 1]), 1));
-                        const float2 c = make_float2(__shfl_down_sync(0xffffffffu, __uint_as_float(fp[k]), 1),
-                                                     __shfl_down_sync(0xffffffffu, __uint_as_float(fp[k + 1]), 1));
-                        const float2 mid = make_float2(__uint_as_float(f0[k]), __uint_as_float(f0[k + 1]));
-                        float2 v = __fadd2_rn(__fadd2_rn(a, mid), c);
-                        v = __fadd2_rn(__ffma2_rn(v, dd[e], nz2), bb[e]);
-                        const float2 lo = __fmul2_rn(v, slope2);
-                        v.x = fmaxf(v.x, lo.x); v.y = fmaxf(v.y, lo.y);          // lrelu (gain folded downstream)
-                        if (p.clamp > 0.f) {
-                            v.x = fminf(fmaxf(v.x, -p.clamp), p.clamp); v.y = fminf(fmaxf(v.y, -p.clamp), p.clamp);
-                        }
-                        r0 = __ffma2_rn(v, q0[e], r0);
-                        r1 = __ffma2_rn(v, q1[e], r1);
-                        r2 = __ffma2_rn(v, q2[e], r2);
-                        if (store) {
-                            const float2 o = __fmul2_rn(v, ss[e]);
-                            packed[8 * h + k / 2] = dx_pack(o.x, o.y);
-                        }
+                        const float a = __shfl_up_sync(0xffffffffu, __uint_as_float(fm[j + e]), 1);
+                        const float c = __shfl_down_sync(0xffffffffu, __uint_as_float(fp[j + e]), 1);
+                        const float sum = a + __uint_as_float(f0[j + e]) + c;
+                        v[e] = fmaf(sum, dd[e], nz) + bb[e];
+                        v[e] = fmaxf(v[e], kDxSlope * v[e]);             // lrelu (gain folded downstream)
+                        if (p.clamp > 0.f) v[e] = fminf(fmaxf(v[e], -p.clamp), p.clamp);
                     }
+                    if (p.rgb_w) {
+                        const float4 w0 = lds128f(smem_u32(e_w0 + c0 + j)), w1 = lds128f(smem_u32(e_w1 + c0 + j));
+                        const float4 w2 = lds128f(smem_u32(e_w2 + c0 + j));
+                        rgb0 += v[0] * w0.x + v[1] * w0.y + v[2] * w0.z + v[3] * w0.w;
+                        rgb1 += v[0] * w1.x + v[1] * w1.y + v[2] * w1.z + v[3] * w1.w;
+                        rgb2 += v[0] * w2.x + v[1] * w2.y + v[2] * w2.z + v[3] * w2.w;
+                    }
+                    packed[8 * h + j / 2 + 0] = dx_pack(v[0] * ss[0], v[1] * ss[1]);
+                    packed[8 * h + j / 2 + 1] = dx_pack(v[2] * ss[2], v[3] * ss[3]);
                 }
             }
-            const float rgb0 = r0.x + r0.y, rgb1 = r1.x + r1.y, rgb2 = r2.x + r2.y;
             if (p.out) {
                 uint32_t off16 = 0xffffffffu;     // this pixel's 64 bytes in 16-byte units from p.out (0xFFFFFFFF: not stored)
                 if (valid) off16 = (uint32_t)(((((long long)t.b * p.R + y) * p.R + x) * Cout + cbase) >> 3);

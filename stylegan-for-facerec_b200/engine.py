@@ -9,6 +9,7 @@ workspace (a torch uint8 tensor), hands over pointers to the fp32 master paramet
 them into the engine's bf16 layouts whenever they change.
 """
 import ctypes as C
+import gc
 import os
 import threading
 import weakref
@@ -20,6 +21,9 @@ from . import _lib
 
 class SynthesisEngine:
     def __init__(self, generator, max_batch=8, use_graph=None, training=False):
+        # the module owns its engine, the engine only looks back through a weak reference: no reference cycle, so an
+        # engine (plan, workspace, CUDA graphs) is torn down the moment its module dies and never by a cyclic-GC pass
+        # that happens to run while some stream is capturing (destroying a graph is illegal during a global capture)
         self.G = generator
         self.lib = _lib.load()
         self.training = bool(training)       # keep every layer's output and support `backward` (frozen decoder, dL/dlatent)
@@ -38,6 +42,19 @@ class SynthesisEngine:
         self._graphs = {}
         if generator.input.input.is_cuda:
             self._ensure(max_batch)
+
+    @property
+    def G(self):
+        g = self._G()
+        if g is None:
+            raise RuntimeError("sg2_b200 engine: its Generator no longer exists")
+        return g
+
+    @G.setter
+    def G(self, generator):
+        if isinstance(generator, _AdaView):
+            self._view = generator           # the view has no other owner
+        self._G = weakref.ref(generator)
 
     # -- plan -------------------------------------------------------------------------------------
     def _layer_table(self):
@@ -241,9 +258,19 @@ class SynthesisEngine:
             n_launch = _lib.launch_count() - n0
             torch.cuda.current_stream(dev).synchronize()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                head()
-                self._call(s_lat, B, ptrs, strides, s_img)
+            # Nothing may free device objects while the stream captures: collect garbage now, keep the collector off for
+            # the few milliseconds of the capture (a cyclic-GC pass that finalises somebody's old CUDA graph inside it
+            # invalidates the capture), and let other threads go on using CUDA (thread-local error mode).
+            gc.collect()
+            gc_was_on = gc.isenabled()
+            gc.disable()
+            try:
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                    head()
+                    self._call(s_lat, B, ptrs, strides, s_img)
+            finally:
+                if gc_was_on:
+                    gc.enable()
             entry = {"graph": g, "lat": s_lat, "z": s_z, "noise": s_noise, "flat": s_flat, "img": s_img, "launches": n_launch,
                      "args": (ptrs, strides), "src": [None] * len(s_noise)}
             self._graphs[key] = entry
@@ -378,12 +405,19 @@ class _AdaView:
 
     def __init__(self, syn):
         import types
-        self.syn = syn
+        self._syn = weakref.ref(syn)          # the network owns the engine, the engine owns this view: no cycle
         self.size, self.style_dim = syn.img_resolution, syn.w_dim
         self.log_size = syn.img_resolution_log2
         self.n_latent = 2 * self.log_size - 2            # rows of ws the layers read (the reference allocates two more)
         self.num_layers = 2 * (self.log_size - 2) + 1
         self.input = types.SimpleNamespace(input=syn.first_block.const)
+
+    @property
+    def syn(self):
+        s = self._syn()
+        if s is None:
+            raise RuntimeError("sg2_b200 engine: its SynthesisNetwork no longer exists")
+        return s
 
     def parameters(self):
         return self.syn.parameters()
@@ -394,7 +428,8 @@ class AdaSynthesisEngine(SynthesisEngine):
     clamps, no equalised-lr conv scale.  Inference only (the differentiable composition stays in stylegan2_ada/)."""
 
     def __init__(self, synthesis, max_batch=8, use_graph=None):
-        super().__init__(_AdaView(synthesis), max_batch=max_batch, use_graph=use_graph)
+        self._view = _AdaView(synthesis)
+        super().__init__(self._view, max_batch=max_batch, use_graph=use_graph)
 
     def _create_fn(self):
         return self.lib.sg2_synth_create_ada

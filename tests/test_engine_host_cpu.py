@@ -111,3 +111,27 @@ def test_engine_routes_need_cuda_tensors(sg2):
     assert not G._use_engine(lat.detach(), [None] * G.num_layers, False)
     with pytest.raises(RuntimeError, match="CUDA"):                       # ... and the module path refuses them (no CPU fallback)
         G([lat], input_is_latent=True, randomize_noise=False)
+
+
+def test_engine_holds_its_module_weakly(sg2):
+    """module -> engine is the only strong edge: an engine (plan, workspace, CUDA graphs) dies with its module by reference
+    counting, never in a cyclic-GC pass that might run inside somebody's stream capture"""
+    import gc
+    E = importlib.import_module("stylegan-for-facerec_b200.engine")
+    G = sg2.Generator(16, 32, 2)
+    eng = E.SynthesisEngine.__new__(E.SynthesisEngine)
+    eng.plan = None
+    eng.G = G
+    assert eng.G is G
+    assert not any(r is eng or r is getattr(eng, "__dict__", None) for r in gc.get_referrers(G) if isinstance(r, (dict, E.SynthesisEngine)))
+    del G
+    with pytest.raises(RuntimeError, match="no longer exists"):
+        eng.G
+    A = sg2.stylegan2_ada.Generator(32, 32, 2, 16, 3)
+    aeng = E.AdaSynthesisEngine.__new__(E.AdaSynthesisEngine)
+    aeng.plan = None
+    aeng.G = E._AdaView(A.synthesis)
+    assert aeng.G.syn is A.synthesis
+    del A
+    with pytest.raises(RuntimeError, match="no longer exists"):
+        aeng.G.syn
