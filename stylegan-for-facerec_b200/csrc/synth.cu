@@ -613,17 +613,6 @@ extern "C" int sg2_synth_forward(sg2_synth *S, void *workspace, const float *lat
                 if (rc) return rc;
             }
         }
-        {
-            EncodeTiledFn enc = get_encode();
-            cuuint64_t dims[2] = {256, 128};
-            cuuint64_t strides[1] = {512};
-            cuuint32_t box[2] = {64, 128};
-            cuuint32_t es[2] = {1, 1};
-            CUresult rc = enc(&S->tmK, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ws + S->off_toeplitz, dims, strides, box, es,
-                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            SG2_REQUIRE(rc == CUDA_SUCCESS, SG2_ERR_CUDA, "engine: cuTensorMapEncodeTiled(Toeplitz) failed with %d", (int)rc);
-        }
         S->cached_ws = workspace;
         S->cached_B = B;
     }
@@ -804,14 +793,31 @@ extern "C" int sg2_synth_forward(sg2_synth *S, void *workspace, const float *lat
                 tp.tiles_c = L.p.cout % 128 == 0 ? L.p.cout / 128 : 1;
                 tp.tiles_x = (2 * L.res_in + 7) / 8; tp.tiles_y = (2 * L.res_in + 15) / 16;
                 tp.total_tiles = tp.tiles_x * tp.tiles_y * tp.tiles_c * ((B + tp.nsamp - 1) / tp.nsamp);
-                static const char *envp = getenv("SG2_FIR_NZPF");
                 static const char *envd = getenv("SG2_FIR_DBG");
-                tp.store_mode = fir_store_mode(); tp.noise_prefetch = envp ? atoi(envp) : 1;
+                tp.store_mode = fir_store_mode();
                 tp.dbg = envd ? atoi(envd) : 0;
                 tp.noise = nz; tp.noise_bstride = nzs; tp.noise_weight = L.p.noise_weight;
                 tp.bias = L.p.act_bias; tp.next_style = up.next_style;
                 tp.toeplitz = (const __nv_bfloat16 *)(ws + S->off_toeplitz);
-                rc = launch_upfir_tc(tp, S->tmK, L.tmT, L.tmO, S->sms, st);
+                // the noise maps are the caller's tensors: their tensor map (tile = 8 x 16 pixels x the samples of a tile) is
+                // encoded per launch (host only, ~1 us) and travels as a kernel parameter
+                CUtensorMap tmN;
+                memset(&tmN, 0, sizeof(tmN));
+                if (nz) {
+                    EncodeTiledFn enc = get_encode();
+                    const int R = 2 * L.res_in;
+                    SG2_REQUIRE((reinterpret_cast<uintptr_t>(nz) & 15) == 0 && (nzs == 0 || nzs == (long long)R * R), SG2_ERR_BAD_ARG,
+                                "engine: noise maps must be 16-byte aligned and densely packed per sample (layer %d)", i);
+                    const cuuint64_t nmaps = nzs ? (cuuint64_t)B : 1;
+                    cuuint64_t dims[3] = {(cuuint64_t)R, (cuuint64_t)R, nmaps};
+                    cuuint64_t strides[2] = {(cuuint64_t)R * 4, (cuuint64_t)R * R * 4};
+                    cuuint32_t box[3] = {8, 16, (cuuint32_t)(nzs ? tp.nsamp : 1)};
+                    cuuint32_t es[3] = {1, 1, 1};
+                    CUresult crc = enc(&tmN, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)nz, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    SG2_REQUIRE(crc == CUDA_SUCCESS, SG2_ERR_CUDA, "engine: cuTensorMapEncodeTiled(noise) failed with %d", (int)crc);
+                }
+                rc = launch_upfir_tc(tp, tmN, L.tmT, L.tmO, S->sms, st);
             }
             if (rc) return rc;
             if ((rc = rec(S, st, "upfir"))) return rc;

@@ -14,16 +14,17 @@
 //     TMA straight from the planes (out-of-range rows/cols zero-filled) and used AS IT LANDS as the
 //     MN-major B operand (pixels = K dimension, 64 channels = one 128-byte swizzle row).
 //   * K = the banded Toeplitz matrix of the 4x4 taps (values {1,3,9}/16: exact in bf16), built on
-//     the host per plan, resident in shared memory for the whole kernel (A operand, K-major).
-//   * fp32 accumulation in TMEM; the epilogue warps only do +noise, +bias, lrelu, x style, pack.
+//     the host per plan, resident in TENSOR MEMORY for the whole kernel (A operand of tcgen05.mma).
+//   * fp32 accumulation in TMEM; the epilogue warps only do +noise, +bias, lrelu, x style, pack -- and
+//     read the noise tile / bias / style from shared memory, where the TMA producer put them (FirAux).
 // The multiplications by structural zeros cost 16x more MACs than the stencil (still < 30 % of
 // the tile's HBM time on the tensor pipe) and buy an instruction stream 4x shorter.
 //
 // A tile is always 128 accumulator columns wide, cut into column blocks of `cbw` channels that each
 // map to one (sample, channel offset): C >= 128 -> two 64-channel blocks of one sample; C = 64 -> two
 // samples; C = 32 (the 1024^2 tail) -> four samples with 64-byte rows (SWIZZLE_64B operand atoms).
-// Every epilogue warp owns 32 pixels x 64 columns and stages them in shared memory in the TMA store layout;
-// the tile leaves through TMA stores (direct 16-byte register stores measured 20 % slower: profiles/experiments).
+// Every epilogue warp owns 32 pixels x 32 columns and stages them in shared memory in the TMA store layout
+// (double buffered); the tile leaves through TMA stores (direct 16-byte register stores measured 20 % slower: profiles/experiments).
 #include "common.cuh"
 #include "synth_kernels.cuh"
 #include "tc_ptx.cuh"
@@ -39,42 +40,38 @@ constexpr int FT_K = 4 * FT_PLANE_ROWS;          // 256
 constexpr int FT_N = 128;                        // accumulator columns per tile
 constexpr int FT_STAGE_BYTES = FT_K * FT_N * 2;  // the window of one tile: 64 KiB whatever the column block width
 // The Toeplitz matrix (A operand) lives in TENSOR MEMORY (128 lanes x 128 columns of packed bf16 pairs, written once
-// per CTA with tcgen05.st): the MMAs read only the window from shared memory.  The knock-out analysis showed the
-// kernel bound by the shared-memory port (per tile: 128 KiB of MMA operand reads + 61 KiB TMA fill + 32 KiB staging
-// + 32 KiB TMA-store reads at 128 B/clk); A-from-TMEM removes 64 KiB of that and frees 64 KiB for a third stage.
-// SG2_FIR_GROUPS = 2: the epilogue warps form TWO groups that take alternate tiles (group g owns accumulator g, its own
-// staging buffer, parameter table and named barriers), so the serial per-tile chain of one group (accumulator wait, TMEM
-// load, math, staging, fence, barrier, TMA store) overlaps the other group's.  The second 32 KiB staging buffer takes the
-// place of the Toeplitz matrix, which then has to live in tensor memory.
-#ifndef SG2_FIR_GROUPS
-#define SG2_FIR_GROUPS 1
-#endif
-#ifndef SG2_FIR_A_TMEM
-#define SG2_FIR_A_TMEM (SG2_FIR_GROUPS == 2 ? 1 : 0)
-#endif
-static_assert(SG2_FIR_GROUPS == 1 || (SG2_FIR_GROUPS == 2 && SG2_FIR_A_TMEM), "two epilogue groups need the Toeplitz matrix in TMEM");
-constexpr int FT_GROUPS = SG2_FIR_GROUPS;
-constexpr int FT_STAGES = (SG2_FIR_A_TMEM && FT_GROUPS == 1) ? 3 : 2;
-constexpr int FT_A_BYTES = SG2_FIR_A_TMEM ? 16 : 128 * FT_K * 2;       // 64 KiB Toeplitz when it is a shared-memory operand
-constexpr int FT_TMEM_COLS = SG2_FIR_A_TMEM ? 512 : 256;                 // 2 accumulators (+ 128 columns of A)
+// per CTA with tcgen05.st): the MMAs read only the window from shared memory, and the 64 KiB it would take there hold
+// the second output staging buffer and the ring of per-tile epilogue inputs instead.
+constexpr int FT_STAGES = 2;
+constexpr int FT_OBUF = 2;                       // output staging buffers: tile i is staged while tile i - 1 is still being stored
+constexpr int FT_AUX = FT_STAGES + 2;            // ring of per-tile epilogue inputs (see FirAux)
+constexpr int FT_TMEM_COLS = 512;                // 2 accumulators (2 x 128 columns) + 128 columns of A
 #ifndef SG2_FIR_EPI_WARPS
 #define SG2_FIR_EPI_WARPS 16
 #endif
-constexpr int FT_EPI_WARPS = SG2_FIR_EPI_WARPS;  // all epilogue warps of the CTA
-constexpr int FT_GW = FT_EPI_WARPS / FT_GROUPS;  // warps per group: 4 (2) per TMEM lane quarter, a 32-column chunk (two chunks) each
-constexpr int FT_GT = 32 * FT_GW;                // threads per group
+constexpr int FT_EPI_WARPS = SG2_FIR_EPI_WARPS;  // 4 warps per TMEM lane quarter: a 32-column chunk each (8: two chunks each)
 constexpr int FT_EPI_THREADS = 32 * FT_EPI_WARPS;
-constexpr int FT_CPW = 16 / FT_GW;               // 32-column chunks per epilogue warp
+constexpr int FT_CPW = 16 / FT_EPI_WARPS;        // 32-column chunks per epilogue warp
 constexpr int FT_THREADS = 64 + FT_EPI_THREADS;
-static_assert(FT_GW == 8 || FT_GW == 16, "epilogue: 2 or 4 warps per TMEM lane quarter and group");
+static_assert(FT_EPI_WARPS == 8 || FT_EPI_WARPS == 16, "epilogue: 2 or 4 warps per TMEM lane quarter");
+
+// Everything the epilogue needs for one tile besides the accumulator: the tile's noise (16 x 8 pixels per sample), the bias and
+// the consumer's style of its 128 columns.  The TMA producer fetches it together with the tile's window (one tensor load + bulk
+// copies on their own mbarrier), FT_AUX tiles deep.  The epilogue warps issue NO global loads: an ordinary load queues behind the
+// ~120 KiB of tensor loads this SM keeps in flight (Little's law: 148 SMs x 120 KiB / 3.7 TB/s ~ 5 us), and with the noise / the
+// parameter table fetched by the epilogue threads themselves -- even two tiles ahead -- that wait was 22 % of the kernel's time
+// (knock-out: 0.555 -> 0.435 ms on the 256^2 layer with those loads removed).
+struct __align__(128) FirAux {
+    float noise[4][FT_TH * FT_TW];                 // [sample of the tile][pixel]; one map when the noise is broadcast over the batch
+    float bias[FT_N];
+    float style[FT_N];                             // style of the consumer (without the sqrt(2) gain)
+};
 
 struct __align__(1024) FirSmem {
     uint8_t b[FT_STAGES * FT_STAGE_BYTES];
-    uint8_t o[FT_GROUPS][128 * FT_N * 2];          // bf16 output tile [column block][128 px][cbw] in the TMA store layout, per group
-    uint8_t a[FT_A_BYTES];                         // Toeplitz matrix when it is a shared-memory operand (else unused)
-    float2 e_tab[FT_GROUPS][2][FT_N];              // {bias, sqrt(2) * style of the consumer} per column, double buffered by the group's tile parity
-    uint64_t a_full;
-    uint64_t full[FT_STAGES], empty[FT_STAGES];
+    uint8_t o[FT_OBUF][128 * FT_N * 2];            // bf16 output tile [column block][128 px][cbw] in the TMA store layout
+    FirAux aux[FT_AUX];
+    uint64_t full[FT_STAGES], empty[FT_STAGES], aux_full[FT_AUX];
     uint64_t tmem_full[2], tmem_empty[2];
     uint32_t tmem_base;
 };
@@ -121,13 +118,20 @@ __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t smem_addr, uint32
            ((uint64_t)((8 * row_bytes) >> 4) << 32) | (1ull << 46) | (layout << 61);
 }
 
+// plain (non-tensor) bulk copy global -> shared, completing on an mbarrier; 16-byte aligned addresses and size
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
 __global__ void __launch_bounds__(FT_THREADS, 1)
-upfir_tc_kernel(const __grid_constant__ UpfirTcParams p, const __grid_constant__ CUtensorMap tmK,
+upfir_tc_kernel(const __grid_constant__ UpfirTcParams p, const __grid_constant__ CUtensorMap tmN,
                 const __grid_constant__ CUtensorMap tmT0, const __grid_constant__ CUtensorMap tmT1,
                 const __grid_constant__ CUtensorMap tmT2, const __grid_constant__ CUtensorMap tmT3,
                 const __grid_constant__ CUtensorMap tmO) {
     // the kernel has no static shared memory: the dynamic window starts at the CTA's shared base, which satisfies the
-    // declared 1 KiB alignment (swizzle atoms); checked once, because every byte of the 227 KiB is spoken for
+    // declared 1 KiB alignment (swizzle atoms)
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     FirSmem &sm = *reinterpret_cast<FirSmem *>(smem_raw);
     if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
@@ -147,11 +151,11 @@ upfir_tc_kernel(const __grid_constant__ UpfirTcParams p, const __grid_constant__
         }
     }
     if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmK);
         tma_prefetch_desc(&tmT0);
-        mbar_init(&sm.a_full, 1);
+        tma_prefetch_desc(&tmO);
         for (int i = 0; i < FT_STAGES; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&sm.tmem_full[i], 1); mbar_init(&sm.tmem_empty[i], FT_GW); }
+        for (int i = 0; i < FT_AUX; ++i) mbar_init(&sm.aux_full[i], 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&sm.tmem_full[i], 1); mbar_init(&sm.tmem_empty[i], FT_EPI_WARPS); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(&sm.tmem_base, FT_TMEM_COLS);
@@ -160,7 +164,6 @@ upfir_tc_kernel(const __grid_constant__ UpfirTcParams p, const __grid_constant__
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = sm.tmem_base;
-#if SG2_FIR_A_TMEM
     // Toeplitz matrix -> TMEM columns [256, 384): lane = output pixel m, column j = taps (2j, 2j+1) of its row.
     // The first four epilogue warps cover the four lane quarters.
     if (warp >= 2 && warp < 6) {
@@ -181,85 +184,83 @@ upfir_tc_kernel(const __grid_constant__ UpfirTcParams p, const __grid_constant__
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-#endif
 
     // round-robin: at any moment the 148 CTAs work on ~5 adjacent tile rows, so the halo rows a tile
     // shares with its vertical neighbours are still in L2 when the neighbour loads them
     const int tile_lo = (int)blockIdx.x, tile_step = (int)gridDim.x, tile_hi = p.total_tiles;
+    const int noise_maps = p.noise ? (p.noise_bstride ? p.nsamp : 1) : 0;    // noise maps per tile
 
     if (warp == 0) {
         // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
         if (tile_lo < tile_hi) {
-            if (!SG2_FIR_A_TMEM && elect_one()) {      // Toeplitz matrix: 4 K-atoms of [128 rows][64 k] each
-                mbar_arrive_expect_tx(&sm.a_full, FT_A_BYTES);
-                for (int ka = 0; ka < 4; ++ka)
-                    asm volatile(
-                        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                        ::"r"(smem_u32(sm.a + ka * 16384)), "l"(reinterpret_cast<uint64_t>(&tmK)), "r"(smem_u32(&sm.a_full)),
-                        "r"(ka * 64), "r"(0)
-                        : "memory");
-            }
-            __syncwarp();
             const uint32_t plane_bytes = FT_PLANE_ROWS * row_bytes;
             // per column block: channel offset inside the tile's channel group and sample offset (tile-invariant)
             int coff[4], noff[4];
 #pragma unroll
             for (int cb = 0; cb < 4; ++cb) { coff[cb] = (cb % cps) * cbw; noff[cb] = cb / cps; }
             const int cgroup = cps * cbw;
-            uint32_t stage = 0, phase = 0;
+            const uint32_t aux_bytes = (uint32_t)(2 * FT_N * 4 + noise_maps * FT_TH * FT_TW * 4);
+            uint32_t stage = 0, phase = 0, slot = 0;
             FirWalk w;
             w.init(p, tile_lo, tile_step);
             for (int tile = tile_lo; tile < tile_hi; tile += tile_step, w.next(p)) {
                 const FirTile t = w.tile(p);
                 const int a0 = t.y0 / 2 - 1, b0 = t.x0 / 2 - 1;     // first window cell of the tile
+                // stage free <=> the MMAs of tile i - 2 are done <=> (accumulator hand-back) the epilogue of tile i - 4 has read
+                // its aux slot, which is the one this tile overwrites (FT_AUX = FT_STAGES + 2)
                 mbar_wait(&sm.empty[stage], phase ^ 1);
-                if (SG2_DBG(p) & 1) {
-                    if (elect_one()) mbar_arrive(&sm.full[stage]);
-                } else if (elect_one()) {
-                    mbar_arrive_expect_tx(&sm.full[stage], (uint32_t)(ncb * 4 * FT_RA * FT_RB) * row_bytes);
+                if (elect_one()) {
+                    if (SG2_DBG(p) & 1) {
+                        mbar_arrive(&sm.full[stage]);
+                    } else {
+                        mbar_arrive_expect_tx(&sm.full[stage], (uint32_t)(ncb * 4 * FT_RA * FT_RB) * row_bytes);
+#pragma unroll
+                        for (int cb = 0; cb < 4; ++cb) {
+                            if (cb < ncb) {
+                                const int c = t.ct * cgroup + coff[cb], n = t.n0 + noff[cb];   // samples >= B read as zero
+                                uint8_t *dst = sm.b + stage * FT_STAGE_BYTES + cb * cb_bytes;
+                                tma_load_4d(dst + 0 * plane_bytes, &tmT0, &sm.full[stage], c, b0, a0, n);
+                                tma_load_4d(dst + 1 * plane_bytes, &tmT1, &sm.full[stage], c, b0, a0, n);
+                                tma_load_4d(dst + 2 * plane_bytes, &tmT2, &sm.full[stage], c, b0, a0, n);
+                                tma_load_4d(dst + 3 * plane_bytes, &tmT3, &sm.full[stage], c, b0, a0, n);
+                            }
+                        }
+                    }
+                    FirAux &ax = sm.aux[slot];
+                    mbar_arrive_expect_tx(&sm.aux_full[slot], aux_bytes);
+                    // pixels / samples beyond the tensor arrive as zeros; they are clipped by the store anyway
+                    if (noise_maps) tma_load_3d(ax.noise, &tmN, &sm.aux_full[slot], t.x0, t.y0, p.noise_bstride ? t.n0 : 0);
 #pragma unroll
                     for (int cb = 0; cb < 4; ++cb) {
                         if (cb < ncb) {
-                            const int c = t.ct * cgroup + coff[cb], n = t.n0 + noff[cb];   // samples >= B read as zero
-                            uint8_t *dst = sm.b + stage * FT_STAGE_BYTES + cb * cb_bytes;
-                            tma_load_4d(dst + 0 * plane_bytes, &tmT0, &sm.full[stage], c, b0, a0, n);
-                            tma_load_4d(dst + 1 * plane_bytes, &tmT1, &sm.full[stage], c, b0, a0, n);
-                            tma_load_4d(dst + 2 * plane_bytes, &tmT2, &sm.full[stage], c, b0, a0, n);
-                            tma_load_4d(dst + 3 * plane_bytes, &tmT3, &sm.full[stage], c, b0, a0, n);
+                            const int c = t.ct * cgroup + coff[cb], n = min(t.n0 + noff[cb], p.B - 1);
+                            bulk_load(ax.bias + cb * cbw, p.bias + c, (uint32_t)cbw * 4u, &sm.aux_full[slot]);
+                            bulk_load(ax.style + cb * cbw, p.next_style + (long long)n * p.C + c, (uint32_t)cbw * 4u, &sm.aux_full[slot]);
                         }
                     }
                 }
                 __syncwarp();
                 if (++stage == FT_STAGES) { stage = 0; phase ^= 1; }
+                slot = (slot + 1) & (FT_AUX - 1);
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (tile_lo < tile_hi) {
-            // kind::f16, D=f32, A=B=bf16, A K-major, B MN-major (bit 16), M=128, N=128
+            // kind::f16, D=f32, A=B=bf16, A from tensor memory (K-major), B MN-major (bit 16), M=128, N=128
             const uint32_t idesc = make_idesc_bf16(128, FT_N) | (1u << 16);
-            if (!SG2_FIR_A_TMEM) mbar_wait(&sm.a_full, 0);
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-            const uint32_t a_base = smem_u32(sm.a);
             const uint32_t kstep = (16 * row_bytes) >> 4;        // 16 K rows per MMA, in 16-byte units
             for (int tile = tile_lo; tile < tile_hi; tile += tile_step) {
                 mbar_wait(&sm.tmem_empty[acc], acc_phase ^ 1);
                 mbar_wait(&sm.full[stage], phase);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * FT_N;
-                const uint64_t adesc0 = make_smem_desc(a_base, 128);
                 const uint64_t bdesc0 = make_smem_desc_mn(smem_u32(sm.b) + stage * FT_STAGE_BYTES, cb_bytes, row_bytes);
                 if (elect_one()) {
 #pragma unroll
-                    for (int kk = 0; kk < ((SG2_DBG(p) & 8) ? 1 : FT_K / 16); ++kk) {
-#if SG2_FIR_A_TMEM
-                        (void)adesc0;       // 16 taps = 8 TMEM columns per K step
+                    for (int kk = 0; kk < ((SG2_DBG(p) & 8) ? 1 : FT_K / 16); ++kk)      // 16 taps = 8 TMEM columns per K step
                         umma_bf16_ts(d_tmem, tmem_base + 256u + 8u * kk, bdesc0 + (uint64_t)(kk * kstep), idesc, kk != 0);
-#else
-                        const uint64_t adesc = adesc0 + (uint64_t)(((kk >> 2) * 16384 + (kk & 3) * 32) >> 4);
-                        umma_bf16(d_tmem, adesc, bdesc0 + (uint64_t)(kk * kstep), idesc, kk != 0);
-#endif
-                    }
                     umma_commit(&sm.empty[stage]);
                     umma_commit(&sm.tmem_full[acc]);
                 }
@@ -271,105 +272,54 @@ upfir_tc_kernel(const __grid_constant__ UpfirTcParams p, const __grid_constant__
     } else {
         // ===================== epilogue: FT_EPI_WARPS warps, FT_EPI_WARPS / 4 per TMEM lane quarter =====
         // The knock-out analysis (profiles/experiments) showed this role, not the loads or the MMAs, paces the
-        // kernel: its per-tile chain (store-read wait, TMEM load, math, staging, fence, barrier, store) is serial.
-        // So: 16 warps (one 32-column chunk each, 4 per scheduler to hide the latencies) and packed f32x2 math.
+        // kernel: 16 warps (one 32-column chunk each, 4 per scheduler to hide the latencies), packed f32x2 math, every
+        // input of the tile already in shared memory when the accumulator completes, one block-wide barrier per tile.
         // warp (q, kq) owns pixels 32q..32q+31 x chunks kq*FT_CPW .. of every tile
-        const int grp = (warp - 2) / FT_GW, wg = (warp - 2) % FT_GW;   // group, warp inside the group
-        const int q = warp & 3, kq = wg >> 2;        // TMEM lane quarter (fixed by the warp id), chunk set of the warp
+        const int q = warp & 3, kq = (warp - 2) >> 2;
         const int m = q * 32 + lane;                 // output pixel of the tile: (m / 8, m % 8)
-        const int oy = m >> 3, ox = m & 7;
-        const int et = threadIdx.x - 64 - grp * FT_GT;       // thread inside the group
-        const uint32_t e_tab_s = smem_u32(sm.e_tab[grp]), o_s = smem_u32(sm.o[grp]);
-        uint8_t *const o_p = sm.o[grp];
-        float2 (*const e_tab)[FT_N] = sm.e_tab[grp];
-        const int bar_a = 1 + 3 * grp, bar_b = 2 + 3 * grp, bar_c = 3 + 3 * grp;   // named barriers of the group
-        // the group's tiles: every FT_GROUPS-th tile of the CTA, starting at its grp-th
-        const int g_lo = tile_lo + grp * tile_step, g_step = FT_GROUPS * tile_step;
-        const int R = 2 * p.r;
+        const int et = threadIdx.x - 64;
         const float nw = p.noise ? __ldg(p.noise_weight) : 0.f;
-        // the sample behind each of this warp's chunks
+        // the noise map behind each of this warp's chunks (the sample of the chunk's column block, or the one broadcast map)
         int ds[FT_CPW];
 #pragma unroll
-        for (int ci = 0; ci < FT_CPW; ++ci) ds[ci] = ((32 * (kq * FT_CPW + ci)) / cbw) / cps;
-        auto noise_at = [&](const FirTile &tt, int d) -> float {
-            const int Y = tt.y0 + oy, X = tt.x0 + ox, n = tt.n0 + d;
-            if (p.noise && Y < R && X < R && n < p.B) return __ldg(p.noise + (long long)n * p.noise_bstride + (long long)Y * R + X);
-            return 0.f;
-        };
-        // column et of the tile (threads et < 128): {bias, sqrt(2) * consumer style} of tile tt
-        const int tcb = (et & (FT_N - 1)) / cbw, tcol = (et & (FT_N - 1)) - tcb * cbw;
-        auto params_at = [&](const FirTile &tt) -> float2 {
-            const int c = tt.ct * (cps * cbw) + (tcb % cps) * cbw + tcol;
-            const int n = min(tt.n0 + tcb / cps, p.B - 1);
-            return make_float2(__ldg(p.bias + c), 1.41421356237f * __ldg(p.next_style + (long long)n * p.C + c));
-        };
-        // Per-thread loads (noise, epilogue parameters) queue behind the ~120 KiB of TMA loads this SM keeps in flight
-        // (ncu: they were the top two stall reasons at a distance of one tile), so both are fetched TWO tiles ahead:
-        // q0 = this tile, q1 = next tile, the loads issued in this iteration are for the tile after that.
-        uint32_t it = 0;
-        float nq0[FT_CPW], nq1[FT_CPW], nqf[FT_CPW];
-        float2 pq1 = make_float2(0.f, 0.f), pqf = make_float2(0.f, 0.f);
-#pragma unroll
-        for (int ci = 0; ci < FT_CPW; ++ci) nq0[ci] = nq1[ci] = nqf[ci] = 0.f;
-        FirWalk w, wp;
-        w.init(p, g_lo < tile_hi ? g_lo : tile_lo, g_step);
-        wp = w;
-        if (g_lo < tile_hi) {
-            const FirTile t0 = wp.tile(p);
-            wp.next(p);
-#pragma unroll
-            for (int ci = 0; ci < FT_CPW; ++ci) nq0[ci] = (ci > 0 && ds[ci] == ds[0]) ? nq0[0] : noise_at(t0, ds[ci]);
-            if (et < FT_N) e_tab[0][et] = params_at(t0);
-            if (g_lo + g_step < tile_hi) {
-                const FirTile t1 = wp.tile(p);
-#pragma unroll
-                for (int ci = 0; ci < FT_CPW; ++ci) nq1[ci] = (ci > 0 && ds[ci] == ds[0]) ? nq1[0] : noise_at(t1, ds[ci]);
-                if (et < FT_N) pq1 = params_at(t1);
-            }
-            wp.next(p);
-            asm volatile("bar.sync %0, %1;" ::"r"(bar_a), "n"(FT_GT) : "memory");   // tile 0's table is staged
-        }
-        for (int tile = g_lo; tile < tile_hi; tile += g_step, ++it) {
+        for (int ci = 0; ci < FT_CPW; ++ci) ds[ci] = (p.noise && p.noise_bstride) ? ((32 * (kq * FT_CPW + ci)) / cbw) / cps : 0;
+        const float2 gain2 = make_float2(1.41421356237f, 1.41421356237f), slope2 = make_float2(0.2f, 0.2f);
+        uint32_t acc = 0, acc_phase = 0, it = 0;
+        FirWalk w;
+        w.init(p, tile_lo, tile_step);
+        for (int tile = tile_lo; tile < tile_hi; tile += tile_step, ++it) {
             const FirTile t = w.tile(p);
             w.next(p);
-            // accumulator of this tile: the MMA warp alternates over the CTA's tiles, i.e. group g of two always drains
-            // accumulator g
-            const uint32_t ti = (uint32_t)grp + it * FT_GROUPS, acc = ti & 1u, acc_phase = (ti >> 1) & 1u;
-            if (tile + 2 * g_step < tile_hi) {                   // two tiles ahead
-                const FirTile tf = wp.tile(p);
-#pragma unroll
-                for (int ci = 0; ci < FT_CPW; ++ci) nqf[ci] = (ci > 0 && ds[ci] == ds[0]) ? nqf[0] : noise_at(tf, ds[ci]);
-                if (et < FT_N) pqf = params_at(tf);
-            }
-            wp.next(p);
-            const uint32_t tab_s = e_tab_s + (it & 1u) * (uint32_t)(FT_N * sizeof(float2));
+            const uint32_t slot = it & (FT_AUX - 1);
+            const FirAux &ax = sm.aux[slot];
+            const uint32_t bias_s = smem_u32(ax.bias), style_s = smem_u32(ax.style);
+            const uint32_t o_s = smem_u32(sm.o[it & 1u]);
+            mbar_wait(&sm.aux_full[slot], (it / FT_AUX) & 1u);
             mbar_wait(&sm.tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * FT_N;
-            // TMEM -> registers -> math first: it overlaps the previous tile's TMA store, whose read of the staging
-            // buffer only has to be over before the shared-memory writes below
             uint32_t packed[FT_CPW][16];
 #pragma unroll
             for (int ci = 0; ci < FT_CPW; ++ci) {
                 if (SG2_DBG(p) & 4) break;
                 const int cc = 32 * (kq * FT_CPW + ci);          // first accumulator column of the chunk
-                const float2 nz2 = make_float2(nq0[ci] * nw, nq0[ci] * nw);
+                const float nz = noise_maps ? nw * ax.noise[ds[ci]][m] : 0.f;
+                const float2 nz2 = make_float2(nz, nz);
                 uint32_t r[32];
                 tmem_ld32(t_row + cc, r);
                 tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
-                    // {bias, style} pairs of columns cc+j .. cc+j+3
-                    const float4 t01 = lds128f(tab_s + (uint32_t)(cc + j) * 8u), t23 = lds128f(tab_s + (uint32_t)(cc + j) * 8u + 16u);
-                    const float4 b4 = make_float4(t01.x, t01.z, t23.x, t23.z), s4 = make_float4(t01.y, t01.w, t23.y, t23.w);
-                    // (acc + noise + bias) -> lrelu -> x style of the consumer, two columns per instruction
+                    const float4 b4 = lds128f(bias_s + (uint32_t)(cc + j) * 4u), s4 = lds128f(style_s + (uint32_t)(cc + j) * 4u);
+                    // (acc + noise + bias) -> lrelu -> x sqrt(2) * style of the consumer, two columns per instruction
                     float2 a = __fadd2_rn(__fadd2_rn(make_float2(__uint_as_float(r[j + 0]), __uint_as_float(r[j + 1])), nz2),
                                           make_float2(b4.x, b4.y));
                     float2 b = __fadd2_rn(__fadd2_rn(make_float2(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])), nz2),
                                           make_float2(b4.z, b4.w));
-                    const float2 al = __fmul2_rn(a, make_float2(0.2f, 0.2f)), bl = __fmul2_rn(b, make_float2(0.2f, 0.2f));
-                    a = __fmul2_rn(make_float2(fmaxf(a.x, al.x), fmaxf(a.y, al.y)), make_float2(s4.x, s4.y));
-                    b = __fmul2_rn(make_float2(fmaxf(b.x, bl.x), fmaxf(b.y, bl.y)), make_float2(s4.z, s4.w));
+                    const float2 al = __fmul2_rn(a, slope2), bl = __fmul2_rn(b, slope2);
+                    const float2 sa = __fmul2_rn(make_float2(s4.x, s4.y), gain2), sb = __fmul2_rn(make_float2(s4.z, s4.w), gain2);
+                    a = __fmul2_rn(make_float2(fmaxf(a.x, al.x), fmaxf(a.y, al.y)), sa);
+                    b = __fmul2_rn(make_float2(fmaxf(b.x, bl.x), fmaxf(b.y, bl.y)), sb);
                     __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(b.x, b.y);
                     packed[ci][j / 2] = *reinterpret_cast<uint32_t *>(&h0);
                     packed[ci][j / 2 + 1] = *reinterpret_cast<uint32_t *>(&h1);
@@ -377,16 +327,9 @@ upfir_tc_kernel(const __grid_constant__ UpfirTcParams p, const __grid_constant__
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.tmem_empty[acc]);     // accumulator drained: the MMA warp may reuse it
-            // the previous tile's TMA stores must have finished reading the staging buffer
-            if (SG2_DBG(p) & 2) {
-            } else if (p.store_mode == 0) {
-                if (et == 0) tma_store_wait_read();
-                asm volatile("bar.sync %0, %1;" ::"r"(bar_b), "n"(FT_GT) : "memory");
-            } else {
-                if (lane == 0) tma_store_wait_read();
-                __syncwarp();
-            }
+            if (lane == 0) mbar_arrive(&sm.tmem_empty[acc]);     // accumulator drained, aux slot read: the MMA warp may go on
+            // staging buffer it & 1 is free: before the barrier of the previous tile, thread 0 waited for the store of tile
+            // it - 2 to finish reading it
 #pragma unroll
             for (int ci = 0; ci < FT_CPW; ++ci) {
                 if (SG2_DBG(p) & 4) break;
@@ -406,35 +349,21 @@ upfir_tc_kernel(const __grid_constant__ UpfirTcParams p, const __grid_constant__
                                packed[ci][4 * v4 + 2], packed[ci][4 * v4 + 3]);
                 }
             }
-            if (et < FT_N) e_tab[(it + 1) & 1u][et] = pq1;     // the next tile's table (read after this tile's last barrier)
-            fence_proxy_async();
-            // rows / columns / samples beyond the tensor are clipped by the TMA unit
-            if ((SG2_DBG(p) & 2) || p.store_mode != 0) asm volatile("bar.sync %0, %1;" ::"r"(bar_a), "n"(FT_GT) : "memory");   // table hand-over
-            if (SG2_DBG(p) & 2) {
-            } else if (p.store_mode == 0) {       // one thread stores whole column blocks (box cbw x 8 x 16); its barrier hands over the table
-                asm volatile("bar.sync %0, %1;" ::"r"(bar_c), "n"(FT_GT) : "memory");
-                if (et == 0) {
+            if (!(SG2_DBG(p) & 2)) {
+                fence_proxy_async();
+                // the store of the previous tile must have read ITS buffer before the next tile is staged there
+                if (et == 0) tma_store_wait_read();
+                asm volatile("bar.sync 1, %0;" ::"n"(FT_EPI_THREADS) : "memory");
+                if (et == 0) {          // rows / columns / samples beyond the tensor are clipped by the TMA unit
                     for (int cb = 0; cb < ncb; ++cb)
-                        tma_store_4d(&tmO, o_p + cb * (128 * (int)row_bytes), t.ct * (cps * cbw) + (cb % cps) * cbw, t.x0, t.y0,
-                                     t.n0 + cb / cps);
+                        tma_store_4d(&tmO, sm.o[it & 1u] + cb * (128 * (int)row_bytes), t.ct * (cps * cbw) + (cb % cps) * cbw, t.x0,
+                                     t.y0, t.n0 + cb / cps);
                     tma_store_commit();
                 }
-            } else if (FT_GW == 8 && lane == 0) {   // every warp stores its own 32 pixels (box cbw x 8 x 4)
-                const int cb_a = (64 * kq) / cbw, cb_b = (64 * kq + 32) / cbw;
-                if (cbw == 64) {
-                    tma_store_4d(&tmO, o_p + kq * (128 * 128) + q * 4096, t.ct * (cps * 64) + (cb_a % cps) * 64, t.x0,
-                                 t.y0 + 4 * q, t.n0 + cb_a / cps);
-                } else {
-                    tma_store_4d(&tmO, o_p + cb_a * (128 * 64) + q * 2048, 0, t.x0, t.y0 + 4 * q, t.n0 + cb_a / cps);
-                    tma_store_4d(&tmO, o_p + cb_b * (128 * 64) + q * 2048, 0, t.x0, t.y0 + 4 * q, t.n0 + cb_b / cps);
-                }
-                tma_store_commit();
             }
-#pragma unroll
-            for (int ci = 0; ci < FT_CPW; ++ci) { nq0[ci] = nq1[ci]; nq1[ci] = nqf[ci]; }
-            pq1 = pqf;
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-        if (lane == 0) tma_store_wait_all();     // threads without outstanding stores return at once
+        if (et == 0) tma_store_wait_all();
     }
     tc_fence_before();
     __syncthreads();
@@ -460,7 +389,7 @@ void build_fir_toeplitz(uint16_t *out, const float *kf) {
     }
 }
 
-int launch_upfir_tc(const UpfirTcParams &p, const CUtensorMap &tmK, const CUtensorMap *tmT, const CUtensorMap &tmO,
+int launch_upfir_tc(const UpfirTcParams &p, const CUtensorMap &tmN, const CUtensorMap *tmT, const CUtensorMap &tmO,
                     int sms, cudaStream_t st) {
     static_assert(sizeof(FirSmem) <= 227 * 1024, "FirSmem exceeds the 227 KiB CTA limit");
     const size_t smem = sizeof(FirSmem);
@@ -471,10 +400,12 @@ int launch_upfir_tc(const UpfirTcParams &p, const CUtensorMap &tmK, const CUtens
     }
     SG2_REQUIRE((p.cbw == 64 || p.cbw == 32) && p.nsamp >= 1 && (FT_N / p.cbw) % p.nsamp == 0, SG2_ERR_BAD_ARG,
                 "upfir_tc: bad column blocking (cbw %d, %d samples per tile)", p.cbw, p.nsamp);
-    SG2_REQUIRE(p.store_mode == 0 || FT_GW == 8, SG2_ERR_BAD_ARG, "upfir_tc: per-warp stores need the 8-warp epilogue build");
+    SG2_REQUIRE(p.nsamp <= 4 && p.B >= 1, SG2_ERR_BAD_ARG, "upfir_tc: at most 4 samples per tile");
+    SG2_REQUIRE((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.next_style) & 15) == 0 && p.C % 4 == 0,
+                SG2_ERR_BAD_ARG, "upfir_tc: the bias / style rows are fetched with 16-byte bulk copies and must be 16-byte aligned");
     const int grid = p.total_tiles < sms ? p.total_tiles : sms;
     if (grid <= 0) return SG2_OK;
-    upfir_tc_kernel<<<grid, FT_THREADS, smem, st>>>(p, tmK, tmT[0], tmT[1], tmT[2], tmT[3], tmO);
+    upfir_tc_kernel<<<grid, FT_THREADS, smem, st>>>(p, tmN, tmT[0], tmT[1], tmT[2], tmT[3], tmO);
     SG2_LAUNCH_CHECK();
     return SG2_OK;
 }

@@ -29,9 +29,9 @@ struct UpfirParams {
     long long plane_stride;       // elements between planes
     __nv_bfloat16 *out;           // [B][2r][2r][C]
     int r, C;
-    const float *noise; long long noise_bstride; const float *noise_weight;
-    const float *bias;            // [C]
-    const float *next_style;      // [B][C]
+    const float *noise; long long noise_bstride; const float *noise_weight;   // noise itself is read through the tensor map tmN
+    const float *bias;            // [C], 16-byte aligned
+    const float *next_style;      // [B][C], 16-byte aligned
     float kf[16];                 // flipped 4x4 taps
 };
 
@@ -41,12 +41,11 @@ struct UpfirTcParams {
     int r, C, B;
     int cbw, nsamp;               // a tile = 128 columns = (128 / cbw) column blocks of cbw channels over nsamp samples
     int tiles_x, tiles_y, tiles_c, total_tiles;   // tiles_c = channel groups per sample (C / 128, or 1)
-    int store_mode;               // 0: one thread stores whole column blocks (box cbw x 8 x 16); 1: per-warp boxes cbw x 8 x 4
-    int noise_prefetch;           // fetch the next tile's noise one iteration ahead
+    int store_mode;               // 0: one thread stores whole column blocks (box cbw x 8 x 16)
     int dbg;                      // SG2_FIR_DBG knock-outs for bottleneck analysis (results are WRONG when set): 1 no loads, 2 no stores, 4 no epilogue math, 8 no MMA
-    const float *noise; long long noise_bstride; const float *noise_weight;
-    const float *bias;            // [C]
-    const float *next_style;      // [B][C]
+    const float *noise; long long noise_bstride; const float *noise_weight;   // noise itself is read through the tensor map tmN
+    const float *bias;            // [C], 16-byte aligned
+    const float *next_style;      // [B][C], 16-byte aligned
     const __nv_bfloat16 *toeplitz; // [128][256] row-major Toeplitz matrix of the taps (copied into tensor memory)
 };
 
@@ -89,7 +88,7 @@ int launch_const_input(__nv_bfloat16 *out, const float *cst, const float *style,
 int launch_upfir(const UpfirParams &p, int B, cudaStream_t st);
 int launch_rgb_combine(const RgbParams &p, int sms, cudaStream_t st);
 void build_fir_toeplitz(uint16_t *out /*[128][256] bf16 bits*/, const float *kf /*flipped 4x4 taps*/);
-int launch_upfir_tc(const UpfirTcParams &p, const CUtensorMap &tmK, const CUtensorMap *tmT /*[4]*/, const CUtensorMap &tmO,
+int launch_upfir_tc(const UpfirTcParams &p, const CUtensorMap &tmN /* noise [B or 1][2r][2r] fp32, box 8 x 16 x maps per tile */, const CUtensorMap *tmT /*[4]*/, const CUtensorMap &tmO,
                     int sms, cudaStream_t st);
 
 }  // namespace sg2

@@ -65,7 +65,6 @@ struct sg2_synth {
     float kf[16];                 // flipped blur taps (x4)
     size_t off_act[2], off_T, off_rgb[2], off_part, off_toeplitz, ws_bytes;
     std::vector<uint16_t> toeplitz;   // host copy of the FIR Toeplitz matrix (bf16 bits), uploaded by pack
-    CUtensorMap tmK;
     bool fir_simt = false;
     // descriptor cache
     void *cached_ws = nullptr;

@@ -163,6 +163,8 @@ class SynthesisEngine:
                 if n is None:
                     n = torch.randn(B, 1, r, r, device=device, dtype=torch.float32)
                 n = n.detach().float().contiguous()
+                if n.data_ptr() % 16:              # the FIR kernel reads the maps through a tensor map (TMA: 16-byte aligned base)
+                    n = n.clone()
             if n.numel() == B * r * r:
                 strides[i] = r * r if B > 1 else 0       # one map per sample
             elif n.numel() == r * r:
