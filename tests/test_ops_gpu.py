@@ -151,6 +151,32 @@ def test_upfirdn2d_streaming_low_precision(sg2, oracle, dtype, shape, up, down, 
     np.testing.assert_allclose(y.float().cpu().numpy(), ref.float().numpy(), rtol=0, atol=tol)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape,down,pad", [((2, 3, 257, 257), 1, (1, 1)), ((1, 2, 300, 131), 1, (2, 2)), ((3, 4, 17, 17), 1, (1, 1)),
+                                            ((2, 3, 256, 256), 2, (1, 1)), ((1, 2, 129, 67), 2, (2, 2)), ((2, 2, 24, 20), 2, (1, 1))])
+def test_upfirdn2d_separable_taps(sg2, oracle, dtype, shape, down, pad):
+    """outer-product taps (what make_kernel builds, model.py:39-48) take the separable instantiation of the streaming kernel
+    (horizontal pass + vertical accumulation, decided on the device from the taps); asymmetric factors so that a flipped or
+    transposed factor would show; 3-tap and 4-tap factors; and a rank-2 kernel one ulp-scale away from separable stays on the
+    general path with the same result"""
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(shape, generator=g).to(dtype)
+    for ky, kx in ((torch.tensor([1.0, -2.0, 3.5, 0.25]), torch.tensor([0.5, 4.0, -1.0, 2.0])),
+                   (torch.tensor([1.0, 3.0, 3.0, 1.0]) / 8, torch.tensor([1.0, 3.0, 3.0, 1.0]) / 8),
+                   (torch.tensor([0.3, -1.0, 2.0]), torch.tensor([1.5, 0.0, -0.7]))):
+        taps = torch.outer(ky, kx)
+        y = sg2.upfirdn2d(x.to(DEV), taps.to(DEV), 1, down, pad)
+        ref = oracle.upfirdn2d(x.double(), taps.double(), 1, down, pad)
+        assert y.dtype == dtype and y.shape == ref.shape
+        tol = (_tol(dtype) if dtype != torch.float32 else 2e-6) * float(ref.abs().max())
+        np.testing.assert_allclose(y.float().cpu().numpy(), ref.float().numpy(), rtol=0, atol=tol)
+        bumped = taps.clone()
+        bumped[1, 2] += 1e-3 * float(taps.abs().max())      # no longer an outer product
+        y2 = sg2.upfirdn2d(x.to(DEV), bumped.to(DEV), 1, down, pad)
+        ref2 = oracle.upfirdn2d(x.double(), bumped.double(), 1, down, pad)
+        np.testing.assert_allclose(y2.float().cpu().numpy(), ref2.float().numpy(), rtol=0, atol=tol)
+
+
 def test_upfirdn2d_streaming_tensor_edges(sg2, oracle):
     # planes narrower than the staged line: the unpredicated row fetch must not leave the tensor at either end
     # (the input is the tail of an allocation, so an over-read would fault or pick up NaNs)
