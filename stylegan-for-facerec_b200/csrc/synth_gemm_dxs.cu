@@ -160,39 +160,14 @@ modconv_dxs_kernel(const __grid_constant__ DxsParams p, const __grid_constant__ 
         const uint32_t stg = smem_u32(sm.stg[warp - 2]);
         const long long plane = (long long)p.R * p.R;
         int staged_b = -1;
-        // The group's tiles are lo + tg, lo + tg + nacc, ...: their (column, row, sample) digits are advanced with carries (one
-        // division per kernel, not three per tile), and the pixel's noise is fetched ONE GROUP-ITERATION AHEAD: the epilogue paces
-        // this kernel, so the accumulator is ready when an iteration starts and a load issued in it sat on the critical path
-        // (ncu: 13 % of all stall samples on its first use).
-        int bx, by, bb;
-        {
-            int tl = min(lo + tg, max(p.total_tiles - 1, 0));
-            bx = tl % p.tiles_x; tl /= p.tiles_x;
-            by = tl % p.tiles_y; bb = tl / p.tiles_y;
-        }
-        auto advance = [&](int &x_, int &y_, int &b_) {
-            x_ += (int)nacc;
-            while (x_ >= p.tiles_x) {                // at most once when a row has >= nacc tiles (R >= 128)
-                x_ -= p.tiles_x;
-                if (++y_ >= p.tiles_y) { y_ = 0; ++b_; }
-            }
-        };
-        auto noise_at = [&](int x_, int y_, int b_) -> float {
-            const int xx = x_ * kDxStep - 1 + lane;
-            if (!p.noise || !(lane >= 1 && lane <= kDxStep && xx < p.R)) return 0.f;
-            return __ldg(p.noise + (long long)b_ * p.noise_bstride + (long long)(y_ * kDxTH + q) * p.R + xx);
-        };
-        float nz_cur = lo + tg < hi ? noise_at(bx, by, bb) : 0.f;
         for (int tile = lo + tg; tile < hi; tile += (int)nacc) {
             const uint32_t it = (uint32_t)(tile - lo);
             const uint32_t acc = it % nacc, acc_phase = (it / nacc) & 1u;
-            DxTile t;
-            t.b = bb; t.x0 = bx * kDxStep - 1; t.y0 = by * kDxTH;
-            advance(bx, by, bb);
-            const float nz_nxt = tile + (int)nacc < hi ? noise_at(bx, by, bb) : 0.f;
+            const DxTile t = dx_decode(p, tile);
             const int y = t.y0 + q, x = t.x0 + lane;
             const bool valid = lane >= 1 && lane <= kDxStep && x < p.R;
-            const float nz = nw * nz_cur;
+            float nz = 0.f;
+            if (valid && p.noise) nz = nw * __ldg(p.noise + (long long)t.b * p.noise_bstride + (long long)y * p.R + x);
             // last layer: bias + Upsample(skip) of this pixel (up 2, pad (2,1), 4x4 taps: a 2 x 2 neighbourhood of the skip image);
             // the loads are issued here so that they fly while the warp waits for its accumulator
             float up0 = 0.f, up1 = 0.f, up2 = 0.f;
@@ -260,7 +235,8 @@ modconv_dxs_kernel(const __grid_constant__ DxsParams p, const __grid_constant__ 
 #pragma unroll
                 for (int j = 0; j < 16; j += 4) {
                     const float4 d4 = lds128f(smem_u32(e_demod + c0 + j)), b4 = lds128f(smem_u32(e_bias + c0 + j));
-                    const float dd[4] = {d4.x, d4.y, d4.z, d4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+                    const float4 s4 = lds128f(smem_u32(e_next + c0 + j));
+                    const float dd[4] = {d4.x, d4.y, d4.z, d4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w}, ss[4] = {s4.x, s4.y, s4.z, s4.w};
                     float v[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
@@ -268,7 +244,7 @@ modconv_dxs_kernel(const __grid_constant__ DxsParams p, const __grid_constant__ 
                         const float a = __shfl_up_sync(0xffffffffu, __uint_as_float(fm[j + e]), 1);
                         const float c = __shfl_down_sync(0xffffffffu, __uint_as_float(fp[j + e]), 1);
                         const float sum = a + __uint_as_float(f0[j + e]) + c;
-                        v[e] = fmaf(sum, dd[e], nz) + bv[e];
+                        v[e] = fmaf(sum, dd[e], nz) + bb[e];
                         v[e] = fmaxf(v[e], kDxSlope * v[e]);             // lrelu (gain folded downstream)
                         if (p.clamp > 0.f) v[e] = fminf(fmaxf(v[e], -p.clamp), p.clamp);
                     }
@@ -279,11 +255,8 @@ modconv_dxs_kernel(const __grid_constant__ DxsParams p, const __grid_constant__ 
                         rgb1 += v[0] * w1.x + v[1] * w1.y + v[2] * w1.z + v[3] * w1.w;
                         rgb2 += v[0] * w2.x + v[1] * w2.y + v[2] * w2.z + v[3] * w2.w;
                     }
-                    if (p.out) {         // (the last layer of the network stores only its ToRGB planes)
-                        const float4 s4 = lds128f(smem_u32(e_next + c0 + j));
-                        packed[8 * h + j / 2 + 0] = dx_pack(v[0] * s4.x, v[1] * s4.y);
-                        packed[8 * h + j / 2 + 1] = dx_pack(v[2] * s4.z, v[3] * s4.w);
-                    }
+                    packed[8 * h + j / 2 + 0] = dx_pack(v[0] * ss[0], v[1] * ss[1]);
+                    packed[8 * h + j / 2 + 1] = dx_pack(v[2] * ss[2], v[3] * ss[3]);
                 }
             }
             if (p.out) {
@@ -302,7 +275,6 @@ modconv_dxs_kernel(const __grid_constant__ DxsParams p, const __grid_constant__ 
                 rp[plane] = rgb1;
                 rp[2 * plane] = rgb2;
             }
-            nz_cur = nz_nxt;
         }
     }
 
