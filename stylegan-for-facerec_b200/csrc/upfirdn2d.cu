@@ -275,6 +275,9 @@ static int launch_poly(void *out, const void *x, const float *taps, int64_t plan
 template <typename T>
 int launch_upfirdn2d_stream(void *out, const void *x, const float *taps, int64_t planes, int in_h, int in_w, int out_h,
                             int out_w, int kh, int kw, int up, int down, int pad_x0, int pad_y0, cudaStream_t st);
+template <typename T>
+int launch_upfirdn2d_planes(void *out, const void *x, const float *taps, int64_t planes, int in_h, int in_w, int out_h,
+                            int out_w, int kh, int kw, int up, int down, int pad_x0, int pad_y0, cudaStream_t st);
 
 }  // namespace sg2
 
@@ -304,6 +307,14 @@ extern "C" int sg2_upfirdn2d(void *out, const void *x, const float *kernel, int6
     cudaStream_t st = as_stream(stream);
     const bool sym = up_x == up_y && down_x == down_y && minor == 1 && kh <= 4 && kw <= 4;
     SG2_DISPATCH_DTYPE(dtype, {
+        if (sym) {   // many small planes (the 4^2 .. 32^2 octaves): batches of whole planes per CTA (upfirdn2d_planes.cu); 1 = not applicable
+            const char *env_pl = getenv("SG2_UPFIRDN_PLANES");            // A/B switch (read per call): 0 = off
+            if (!env_pl || atoi(env_pl) != 0) {
+                const int rc = launch_upfirdn2d_planes<T>(out, x, kernel, major, in_h, in_w, out_h, out_w, kh, kw, up_x, down_x,
+                                                          pad_x0, pad_y0, st);
+                if (rc <= 0) return rc;
+            }
+        }
         if (minor == 1 && out_h * out_w <= 256 && !(sym && out_w > 8 && out_h > 8)) {   // tiny planes (<= 8 x 8 ... 16 x 16 non-model geometries)
             UfdGenParams p;
             p.in_h = in_h; p.in_w = in_w; p.out_h = out_h; p.out_w = out_w; p.minor = 1;

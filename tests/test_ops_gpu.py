@@ -177,6 +177,38 @@ def test_upfirdn2d_separable_taps(sg2, oracle, dtype, shape, down, pad):
         np.testing.assert_allclose(y2.float().cpu().numpy(), ref2.float().numpy(), rtol=0, atol=tol)
 
 
+UFD_PLANES = [
+    # (planes as N, C), h, w, k, up, down, pad -- many small planes: the batched-planes kernel (upfirdn2d_planes.cu)
+    ((8, 16), 4, 4, 4, 1, 1, (1, 1)), ((8, 16), 4, 4, 4, 2, 1, (2, 1)), ((6, 7), 5, 5, 4, 1, 1, (2, 2)), ((8, 8), 8, 8, 4, 1, 2, (1, 1)),
+    ((3, 50), 9, 9, 4, 1, 1, (1, 1)), ((4, 40), 8, 8, 4, 2, 1, (2, 1)), ((4, 33), 16, 16, 4, 2, 1, (1, 2)), ((2, 64), 17, 17, 4, 1, 1, (1, 1)),
+    ((2, 64), 16, 16, 4, 1, 2, (1, 1)), ((3, 21), 33, 33, 4, 1, 1, (1, 1)), ((3, 21), 32, 32, 4, 2, 1, (2, 1)), ((3, 21), 32, 32, 4, 1, 2, (1, 1)),
+    ((2, 19), 40, 37, 3, 1, 1, (1, 1)), ((2, 19), 31, 40, 2, 2, 1, (1, 0)), ((2, 19), 24, 30, 4, 1, 2, (2, 2)), ((2, 19), 13, 6, 4, 2, 1, (3, 0)),
+    ((2, 19), 12, 12, 4, 1, 1, (-1, -1)), ((2, 19), 10, 14, 4, 1, 1, (3, 0)), ((2, 19), 10, 14, 4, 2, 1, (3, 3)), ((1, 16), 7, 7, 1, 1, 1, (0, 0)),
+    ((5, 7), 6, 6, 4, 1, 1, (4, 4)), ((5, 7), 6, 6, 4, 1, 1, (5, 5)),      # pad 5 leaves the bordered tile: falls through to the other kernels
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("nc,h,w,k,up,down,pad", UFD_PLANES)
+def test_upfirdn2d_small_planes(sg2, oracle, dtype, nc, h, w, k, up, down, pad):
+    g = torch.Generator().manual_seed(17)
+    x = torch.randn(nc + (h, w), generator=g).to(dtype)
+    taps = torch.randn(k, k, generator=g)             # asymmetric: flips / transposes would show
+    y = sg2.upfirdn2d(x.to(DEV), taps.to(DEV), up, down, pad)
+    ref = oracle.upfirdn2d(x.double(), taps.double(), up, down, pad)
+    assert y.dtype == dtype and y.shape == ref.shape
+    tol = (_tol(dtype) if dtype != torch.float32 else 4e-6) * max(float(ref.abs().max()), 1.0)
+    np.testing.assert_allclose(y.float().cpu().numpy(), ref.float().numpy(), rtol=0, atol=tol)
+    if dtype == torch.float32:                         # same results as the kernels it replaces on these shapes
+        import os
+        os.environ["SG2_UPFIRDN_PLANES"] = "0"
+        try:
+            y0 = sg2.upfirdn2d(x.to(DEV), taps.to(DEV), up, down, pad)
+        finally:
+            del os.environ["SG2_UPFIRDN_PLANES"]
+        np.testing.assert_allclose(y.cpu().numpy(), y0.cpu().numpy(), rtol=0, atol=4e-6 * max(float(ref.abs().max()), 1.0))
+
+
 def test_upfirdn2d_streaming_tensor_edges(sg2, oracle):
     # planes narrower than the staged line: the unpredicated row fetch must not leave the tensor at either end
     # (the input is the tail of an allocation, so an over-read would fault or pick up NaNs)

@@ -62,6 +62,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--no-ref", action="store_true", help="do not time the reference's own CUDA extensions beside ours")
+    ap.add_argument("--res", type=int, nargs="*", default=None, help="only these resolutions")
+    ap.add_argument("--dtypes", nargs="*", default=None, help="only these dtypes (float32 bfloat16 float16)")
     args = ap.parse_args()
     import time
     from bench import ClockSampler
@@ -74,9 +76,13 @@ def main():
     taps = (sg2.make_kernel([1, 3, 3, 1])).to(dev)
     res_list = [4, 16, 64, 256, 1024] if args.quick else [4, 8, 16, 32, 64, 128, 256, 512, 1024]
     ch_list = [3, 64, 512] if args.quick else [3, 32, 64, 128, 256, 512]
+    if args.res:
+        res_list = list(args.res)
     target_elems = 1 << 28 if not args.quick else 1 << 26     # ~256 Mi elements per tensor
     for dtype in (torch.float32, torch.bfloat16, torch.float16):
-        if dtype == torch.float16 and ref is None:
+        if args.dtypes and str(dtype).split(".")[1] not in args.dtypes:
+            continue
+        if dtype == torch.float16 and ref is None and not args.dtypes:
             continue                          # fp16 only as the 2-byte comparison against the reference kernels
         s = torch.finfo(dtype).bits // 8
         with_ref = ref is not None and dtype in (torch.float32, torch.float16)
