@@ -219,7 +219,8 @@ int sg2_synth_describe(const sg2_synth *plan, char *buf, int buflen);
  * create and again whenever the parameters change.                                              */
 int sg2_synth_pack(sg2_synth *plan, void *workspace, sg2_stream_t stream);
 /* latent [B, n_latent, style_dim] fp32; noise[l] fp32 [B or 1, 1, r, r] for each styled conv
- * (n_noise = 2*log2(size)-3 pointers, host array), noise_bstride[l] = r*r or 0;
+ * (n_noise = 2*log2(size)-3 pointers, host array), noise_bstride[l] = r*r or 0; every noise map densely packed and
+ * 16-byte aligned (the up-sampling layers read their tile of it through a TMA tensor map);
  * image [B,3,size,size] fp32 (NCHW, as the reference returns it).                               */
 int sg2_synth_forward(sg2_synth *plan, void *workspace, const float *latent, int64_t B,
                       const float *const *noise, const int64_t *noise_bstride, float *image,

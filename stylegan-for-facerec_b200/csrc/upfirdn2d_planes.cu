@@ -12,13 +12,15 @@
 // vector where the row length allows.  Index decompositions (element -> plane, row, column) use an exact float-reciprocal
 // division (indices < 2^15), not integer division.  fp32 accumulation for every storage dtype, taps applied per output in
 // the reference's order (rows, then columns).
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "common.cuh"
 
 namespace sg2 {
 
-constexpr int PL_BR = 4;              // zero border (pixels) around every staged plane
+constexpr int PL_BR = 4;              // widest zero border (pixels) around a staged plane; the launch uses what the geometry needs
 constexpr int PL_THREADS = 256;
 constexpr int PL_MAX_IN = 40;         // largest input extent handled here
 constexpr int PL_TILE_FLOATS = 8192;  // shared-memory budget of one batch (32 KiB): 5 CTAs per SM
@@ -29,6 +31,7 @@ struct UfdPlanesParams {
     long long planes;
     int G;                 // planes per batch
     int sp, tile;          // pitch and size (floats) of one bordered plane tile
+    int bl, bt;            // border to the left of / above the plane (the right / bottom border is in sp / tile)
     int quads;             // ceil(out_w / 4)
     float r_in_plane, r_in_w, r_quads, r_items;   // reciprocals for the exact float division below
     int vec_store;
@@ -66,7 +69,7 @@ upfirdn2d_planes_kernel(T *__restrict__ out, const T *__restrict__ x, const floa
         for (int i = threadIdx.x; i < n_in; i += PL_THREADS) {
             const int g = fdiv(i, p.r_in_plane), rem = i - g * in_plane;
             const int iy = fdiv(rem, p.r_in_w), ix = rem - iy * p.in_w;
-            pl_smem[g * p.tile + (iy + PL_BR) * p.sp + ix + PL_BR] = Cvt<T>::to_f(__ldg(src + i));
+            pl_smem[g * p.tile + (iy + p.bt) * p.sp + ix + p.bl] = Cvt<T>::to_f(__ldg(src + i));
         }
         __syncthreads();
         // ---- compute: runs of four outputs ----
@@ -76,7 +79,7 @@ upfirdn2d_planes_kernel(T *__restrict__ out, const T *__restrict__ x, const floa
             const int g = fdiv(it, p.r_items);
             const int rem = it - g * items_per_plane;
             const int oy = fdiv(rem, p.r_quads), ox0 = (rem - oy * p.quads) * 4;
-            const float *tile = pl_smem + g * p.tile + PL_BR * p.sp + PL_BR;    // pixel (0, 0) of plane g
+            const float *tile = pl_smem + g * p.tile + p.bt * p.sp + p.bl;      // pixel (0, 0) of plane g
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
             if constexpr (UP == 2) {
                 // row Y = oy + a - pad_y0 of the up-sampled signal is an inserted zero row unless it is even: tap rows a = par, par + 2
@@ -136,21 +139,32 @@ int launch_upfirdn2d_planes(void *out, const void *x, const float *taps, int64_t
                             int out_w, int kh, int kw, int up, int down, int pad_x0, int pad_y0, cudaStream_t st) {
     if (!((up == 1 && (down == 1 || down == 2)) || (up == 2 && down == 1)) || kh > 4 || kw > 4) return 1;
     if (in_h > PL_MAX_IN || in_w > PL_MAX_IN || planes < 16) return 1;
-    // every tap of every output must fall inside the bordered tile (taps are zero padded to 4 x 4)
-    auto inside = [&](int pad0, int n_out, int n_in) {
-        const int lo = -pad0, hi = (n_out - 1) * down + 3 - pad0;           // first / last row of the up-sampled signal touched
+    // where it measured faster than the streaming kernel (profiles/opbench_r02_planes.jsonl); SG2_UPFIRDN_PLANES=2 lifts the limits
+    {
+        const char *env = getenv("SG2_UPFIRDN_PLANES");
+        const int big = std::max(in_h, in_w);
+        const bool all = env && atoi(env) == 2;
+        const int lim = up == 2 ? 8 : (down == 2 ? 24 : 20);
+        if (!all && (big > lim || (down == 2 && big < 12))) return 1;
+    }
+    // every tap of every output (taps zero padded to 4 x 4, rows of four outputs) must fall inside the bordered tile: the border
+    // each side needs, from the first / last row of the up-sampled signal that is touched
+    auto border = [&](int pad0, int n_out, int n_in, int &lo_b, int &hi_b) {
+        const int lo = -pad0, hi = (n_out - 1) * down + 3 - pad0;
         const int ilo = up == 2 ? (lo >> 1) : lo, ihi = up == 2 ? (hi >> 1) : hi;
-        return ilo >= -PL_BR && ihi <= n_in - 1 + PL_BR;
+        lo_b = std::max(0, -ilo);
+        hi_b = std::max(0, ihi - (n_in - 1));
+        return lo_b <= PL_BR && hi_b <= PL_BR + 4;
     };
-    // the run of four outputs starts PL_BR-safe only if its leftmost window column does: same bound, plus the three outputs to
-    // the right of the last quad's first one
     const int quads = (out_w + 3) / 4;
-    if (!inside(pad_y0, out_h, in_h) || !inside(pad_x0, quads * 4, in_w)) return 1;
+    int bt, bb, bl, br;
+    if (!border(pad_y0, out_h, in_h, bt, bb) || !border(pad_x0, quads * 4, in_w, bl, br)) return 1;
     UfdPlanesParams p;
     p.in_h = in_h; p.in_w = in_w; p.out_h = out_h; p.out_w = out_w;
     p.pad_x0 = pad_x0; p.pad_y0 = pad_y0; p.kh = kh; p.kw = kw; p.planes = planes;
-    p.sp = in_w + 2 * PL_BR;
-    p.tile = (in_h + 2 * PL_BR) * p.sp;
+    p.bl = bl; p.bt = bt;
+    p.sp = in_w + bl + br;
+    p.tile = (in_h + bt + bb) * p.sp;
     const int sms = sm_count();
     int G = std::max(1, PL_TILE_FLOATS / p.tile);
     // enough batches for every SM to hold several CTAs' worth

@@ -191,22 +191,29 @@ UFD_PLANES = [
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("nc,h,w,k,up,down,pad", UFD_PLANES)
 def test_upfirdn2d_small_planes(sg2, oracle, dtype, nc, h, w, k, up, down, pad):
+    """SG2_UPFIRDN_PLANES=2 sends every shape the batched-planes kernel can express through it (the default keeps it to the sizes
+    where it measured faster), =0 switches it off: both against the oracle, and against each other"""
+    import os
     g = torch.Generator().manual_seed(17)
     x = torch.randn(nc + (h, w), generator=g).to(dtype)
     taps = torch.randn(k, k, generator=g)             # asymmetric: flips / transposes would show
-    y = sg2.upfirdn2d(x.to(DEV), taps.to(DEV), up, down, pad)
     ref = oracle.upfirdn2d(x.double(), taps.double(), up, down, pad)
-    assert y.dtype == dtype and y.shape == ref.shape
     tol = (_tol(dtype) if dtype != torch.float32 else 4e-6) * max(float(ref.abs().max()), 1.0)
-    np.testing.assert_allclose(y.float().cpu().numpy(), ref.float().numpy(), rtol=0, atol=tol)
-    if dtype == torch.float32:                         # same results as the kernels it replaces on these shapes
-        import os
-        os.environ["SG2_UPFIRDN_PLANES"] = "0"
+    ys = {}
+    for mode in ("2", "0", None):
+        if mode is None:
+            os.environ.pop("SG2_UPFIRDN_PLANES", None)
+        else:
+            os.environ["SG2_UPFIRDN_PLANES"] = mode
         try:
-            y0 = sg2.upfirdn2d(x.to(DEV), taps.to(DEV), up, down, pad)
+            y = sg2.upfirdn2d(x.to(DEV), taps.to(DEV), up, down, pad)
         finally:
-            del os.environ["SG2_UPFIRDN_PLANES"]
-        np.testing.assert_allclose(y.cpu().numpy(), y0.cpu().numpy(), rtol=0, atol=4e-6 * max(float(ref.abs().max()), 1.0))
+            os.environ.pop("SG2_UPFIRDN_PLANES", None)
+        assert y.dtype == dtype and y.shape == ref.shape
+        np.testing.assert_allclose(y.float().cpu().numpy(), ref.float().numpy(), rtol=0, atol=tol, err_msg=f"mode {mode}")
+        ys[mode] = y.float().cpu().numpy()
+    if dtype == torch.float32:                         # same results as the kernels it replaces on these shapes
+        np.testing.assert_allclose(ys["2"], ys["0"], rtol=0, atol=4e-6 * max(float(ref.abs().max()), 1.0))
 
 
 def test_upfirdn2d_streaming_tensor_edges(sg2, oracle):
