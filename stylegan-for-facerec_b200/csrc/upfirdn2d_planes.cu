@@ -145,7 +145,7 @@ int launch_upfirdn2d_planes(void *out, const void *x, const float *taps, int64_t
         const int big = std::max(in_h, in_w);
         const bool all = env && atoi(env) == 2;
         const int lim = up == 2 ? 8 : (down == 2 ? 24 : 20);
-        if (!all && (big > lim || (down == 2 && big < 12))) return 1;
+        if (!all && (big > lim || (down == 2 && big < 8))) return 1;
     }
     // every tap of every output (taps zero padded to 4 x 4, rows of four outputs) must fall inside the bordered tile: the border
     // each side needs, from the first / last row of the up-sampled signal that is touched
