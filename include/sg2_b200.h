@@ -226,6 +226,12 @@ int sg2_synth_forward(sg2_synth *plan, void *workspace, const float *latent, int
                       const float *const *noise, const int64_t *noise_bstride, float *image,
                       sg2_stream_t stream);
 
+/* face_pool folded into the forward (psp.py:33,113-114 AdaptiveAvgPool2d((256,256)) after the decoder):
+ * with factor 2 or 4 every following sg2_synth_forward also writes the image average-pooled by `factor` to
+ * pooled [B,3,size/factor,size/factor] fp32 from inside its last launch; keep_full = 0 skips the full-resolution
+ * image altogether (sg2_synth_forward's `image` may then be null).  factor 0 switches it off.  Inference plans only. */
+int sg2_synth_set_pooled_output(sg2_synth *plan, float *pooled, int factor, int keep_full);
+
 /* Training mode of the plan (the frozen decoder inside the ReStyle / pSp fine-tuning step,
  * coach_restyle_psp.py:138-168; autograd of model.py:232-359 w.r.t. the styles).
  * sg2_synth_enable_training: call right after sg2_synth_create, before sg2_synth_workspace_bytes / sg2_synth_pack; the

@@ -96,6 +96,7 @@ SIGNATURES = {
     "sg2_conv_transpose3x3_tc": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_int, c_int, c_void_p]),
     "sg2_synth_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, C.POINTER(c_void_p),
                                   C.POINTER(c_i64), c_void_p, c_void_p]),
+    "sg2_synth_set_pooled_output": (c_int, [c_void_p, c_void_p, c_int, c_int]),
     "sg2_synth_set_profile_events": (c_int, [c_void_p, C.POINTER(c_void_p), c_int]),
     "sg2_synth_profile_events_used": (c_int, [c_void_p]),
 }

@@ -12,6 +12,10 @@
 // 4x4 / 8x8 layers still fill tiles, K = Cin x taps.  The three geometries (stride-1 "same" conv,
 // stride-2 transposed conv as four polyphase sub-convolutions that never multiply inserted zeros,
 // stride-2 conv) differ only in a small tap table.
+#include <stdlib.h>
+
+#include <atomic>
+
 #include "common.cuh"
 
 namespace sg2 {
@@ -114,6 +118,158 @@ modconv_simt_kernel(T *__restrict__ out, const T *__restrict__ x, const float *_
     }
 }
 
+
+// ---- the same implicit GEMM with a 128-wide register-blocked tile (every layer with Cout a multiple of 32) -----------------
+// 256 threads as (BM / 8) x (BN / 8), an 8 x 8 block of outputs per thread (two 4-wide halves BM/2 resp. BN/2 apart: 16-byte
+// conflict-free operand reads), BM x BN = 128 x 128, 64 x 256 or 32 x 512 so that narrow layers keep every thread busy.
+// Per K chunk (KC input channels x taps) a thread runs 64 FMAs per 4 LDS.128, against 16 per 2 in the 64 x 64 kernel above, and
+// the staging gathers one (sample, pixel) column per thread with its tap geometry resolved once per tap, not once per
+// element.  Same summation order inside a chunk (channel-major, then taps) as the small kernel: results agree to rounding.
+template <int BM_, int BN_, int KC_>
+struct BigTile {
+    static constexpr int BM = BM_, BN = BN_, KC = KC_;
+    static constexpr int TM = BM / 8, TN = BN / 8;                  // threads along M / N
+    static_assert(TM * TN == 256, "256 threads");
+    static constexpr int CPT = BN > 256 ? BN / 256 : 1;             // columns staged per thread
+    static constexpr int CS = BN < 256 ? 256 / BN : 1;              // threads that share a column (they split the chunk's channels)
+    static constexpr size_t smem = (size_t)KC * MAXT * (BM + BN) * sizeof(float);
+};
+
+template <typename T, typename CFG>
+__global__ void __launch_bounds__(256, 2)
+modconv_simt_big_kernel(T *__restrict__ out, const T *__restrict__ x, const float *__restrict__ wt,
+                        const float *__restrict__ style, const float *__restrict__ demod, ConvGeo g) {
+    constexpr int BM = CFG::BM, BN = CFG::BN, KC = CFG::KC, CPT = CFG::CPT, CS = CFG::CS;
+    extern __shared__ __align__(16) float big_smem[];
+    float (*Ws)[BM] = reinterpret_cast<float (*)[BM]>(big_smem);                       // [KC * ntaps][BM]
+    float (*Xs)[BN] = reinterpret_cast<float (*)[BN]>(big_smem + KC * MAXT * BM);      // [KC * ntaps][BN]
+    __shared__ int s_dy[MAXT], s_dx[MAXT], s_wi[MAXT];
+    __shared__ int s_woff[KC * MAXT];     // weight offset of k-row kk = cil * ntaps + t inside a chunk: (cil * kk_total + widx[t]) * Cout
+
+    const int tid = threadIdx.x;
+    if (tid < g.ntaps) { s_dy[tid] = g.dy[tid]; s_dx[tid] = g.dx[tid]; s_wi[tid] = g.widx[tid]; }
+    if (tid < KC * g.ntaps) {
+        const int cil = tid / g.ntaps, t = tid - cil * g.ntaps;
+        s_woff[tid] = (cil * g.kk + g.widx[t]) * g.Cout;
+    }
+    const int tx = tid % CFG::TN, ty = tid / CFG::TN;
+    const int co0 = blockIdx.y * BM;
+    const int64_t n0 = (int64_t)blockIdx.x * BN;
+    const int P = g.PH * g.PW;
+    const int64_t Ntot = (int64_t)g.B * P;
+    const int ntaps = g.ntaps, nk = KC * ntaps;
+    const int64_t HW = (int64_t)g.H * g.W;
+
+    // staging role: CPT columns of Xs per thread, channels cs, cs + CS, ... of the chunk
+    const int cs = CS > 1 ? tid / BN : 0;
+    int iy_base[CPT], ix_base[CPT];
+    const T *xb[CPT];
+    const float *sty[CPT];
+    bool n_ok[CPT];
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) {
+        const int64_t n_st = n0 + (tid % BN) + j * 256;
+        n_ok[j] = n_st < Ntot;
+        int sb = 0, soy = 0, sox = 0;
+        if (n_ok[j]) {
+            sb = (int)(n_st / P);
+            const int r = (int)(n_st - (int64_t)sb * P);
+            soy = r / g.PW;
+            sox = r - soy * g.PW;
+        }
+        iy_base[j] = soy * g.in_sy; ix_base[j] = sox * g.in_sx;
+        xb[j] = x + (int64_t)sb * g.Cin * HW;
+        sty[j] = style ? style + (int64_t)sb * g.Cin : nullptr;
+    }
+
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    __syncthreads();                       // tap table
+
+    for (int ci0 = 0; ci0 < g.Cin; ci0 += KC) {
+        __syncthreads();                   // the previous chunk has been consumed
+        // weights: rows kk = cil * ntaps + t, BM consecutive output channels each (coalesced)
+        {
+            // (the launcher guarantees Cin % KC == 0 and Cout % BM == 0: no bounds checks; 32-bit offsets: the tensor is < 2^31 elements)
+            const float *wc = wt + (int64_t)ci0 * g.kk * g.Cout + co0 + (tid % BM);
+#pragma unroll 4
+            for (int kk = tid / BM; kk < nk; kk += 256 / BM) Ws[kk][tid % BM] = __ldg(wc + s_woff[kk]);
+        }
+        // activations: one (sample, pixel) column per thread; the tap's input position is resolved once, then the chunk's channels
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) {
+            const int col = (tid % BN) + j * 256;
+            float sv[KC];
+#pragma unroll
+            for (int c = 0; c < KC; ++c) sv[c] = 1.f;
+            if (sty[j]) {
+#pragma unroll
+                for (int c = cs; c < KC; c += CS) sv[c] = ci0 + c < g.Cin ? __ldg(sty[j] + ci0 + c) : 0.f;
+            }
+            for (int t = 0; t < ntaps; ++t) {
+                const int iy = iy_base[j] + s_dy[t], ix = ix_base[j] + s_dx[t];
+                const bool ok = n_ok[j] && iy >= 0 && ix >= 0 && iy < g.H && ix < g.W;
+                const T *src = xb[j] + ((int64_t)ci0 * g.H + iy) * g.W + ix;
+#pragma unroll
+                for (int c = cs; c < KC; c += CS) {
+                    float v = 0.f;
+                    if (ok && ci0 + c < g.Cin) v = Cvt<T>::to_f(src[c * HW]) * sv[c];
+                    Xs[c * ntaps + t][col] = v;
+                }
+            }
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int kk = 0; kk < nk; ++kk) {
+            const float4 a0 = *reinterpret_cast<const float4 *>(&Ws[kk][ty * 4]);
+            const float4 a1 = *reinterpret_cast<const float4 *>(&Ws[kk][BM / 2 + ty * 4]);
+            const float4 b0 = *reinterpret_cast<const float4 *>(&Xs[kk][tx * 4]);
+            const float4 b1 = *reinterpret_cast<const float4 *>(&Xs[kk][BN / 2 + tx * 4]);
+            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+    }
+
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int64_t n = n0 + (j < 4 ? tx * 4 + j : BN / 2 + tx * 4 + (j - 4));
+        if (n >= Ntot) continue;
+        const int b = (int)(n / P);
+        const int r = (int)(n - (int64_t)b * P);
+        const int ly = r / g.PW, lx = r - ly * g.PW;
+        const int oy = ly * g.out_sy + g.out_oy, ox = lx * g.out_sx + g.out_ox;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int co = co0 + (i < 4 ? ty * 4 + i : BM / 2 + ty * 4 + (i - 4));
+            if (co >= g.Cout) continue;
+            float v = acc[i][j];
+            if (demod) v *= __ldg(demod + (int64_t)b * g.Cout + co);
+            out[(((int64_t)b * g.Cout + co) * g.OH + oy) * g.OW + ox] = Cvt<T>::from_f(v);
+        }
+    }
+}
+
+template <typename T, typename CFG>
+static int launch_big(T *out, const T *x, const float *wt, const float *style, const float *demod, const ConvGeo &g, int64_t Ntot,
+                      cudaStream_t st) {
+    static std::atomic<int> configured{0};
+    if (!configured.load(std::memory_order_acquire)) {
+        SG2_CUDA_OK(cudaFuncSetAttribute(modconv_simt_big_kernel<T, CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CFG::smem));
+        configured.store(1, std::memory_order_release);
+    }
+    dim3 grid((unsigned)ceil_div64(Ntot, CFG::BN), (g.Cout + CFG::BM - 1) / CFG::BM);
+    modconv_simt_big_kernel<T, CFG><<<grid, 256, CFG::smem, st>>>(out, x, wt, style, demod, g);
+    SG2_LAUNCH_CHECK();
+    return SG2_OK;
+}
+
 }  // namespace sg2
 
 using namespace sg2;
@@ -167,9 +323,20 @@ extern "C" int sg2_modconv2d_fwd(void *out, const void *x, const float *wt, cons
         const int64_t Ntot = B * (int64_t)g.PH * g.PW;
         SG2_REQUIRE(ceil_div64(Ntot, BN) <= 0x7fffffffll, SG2_ERR_UNSUPPORTED, "modconv2d: too many pixels");
         dim3 grid((unsigned)ceil_div64(Ntot, BN), (Cout + BM - 1) / BM);
+        // register-blocked big tiles where they fill: Cout a multiple of 32 and enough (sample, pixel) columns for a few waves
+        static const char *env_big = getenv("SG2_MODCONV_BIG");       // A/B switch: 0 = the 64 x 64 kernel everywhere
+        const bool big_ok = (!env_big || atoi(env_big) != 0) && Cout % 32 == 0 && Cin % 8 == 0 && k == 3 &&
+                            (int64_t)Cin * 9 * Cout < (1ll << 31);
         SG2_DISPATCH_DTYPE(dtype, {
-            modconv_simt_kernel<T><<<grid, 256, 0, st>>>((T *)out, (const T *)x, wt, style, demod, g);
-            SG2_LAUNCH_CHECK();
+            int rc = 1;
+            if (big_ok && Cout % 128 == 0 && Ntot >= 128 * 8) rc = launch_big<T, BigTile<128, 128, 8>>((T *)out, (const T *)x, wt, style, demod, g, Ntot, st);
+            else if (big_ok && Cout % 64 == 0 && Cout < 128 && Ntot >= 256 * 8) rc = launch_big<T, BigTile<64, 256, 8>>((T *)out, (const T *)x, wt, style, demod, g, Ntot, st);
+            else if (big_ok && Cout == 32 && Ntot >= 512 * 8) rc = launch_big<T, BigTile<32, 512, 4>>((T *)out, (const T *)x, wt, style, demod, g, Ntot, st);
+            if (rc < 0 || rc > 1) return rc;
+            if (rc == 1) {
+                modconv_simt_kernel<T><<<grid, 256, 0, st>>>((T *)out, (const T *)x, wt, style, demod, g);
+                SG2_LAUNCH_CHECK();
+            }
         });
     }
     return SG2_OK;

@@ -521,6 +521,17 @@ extern "C" int sg2_synth_describe(const sg2_synth *p, char *buf, int buflen) {
     return n;
 }
 
+extern "C" int sg2_synth_set_pooled_output(sg2_synth *p, float *pooled, int factor, int keep_full) {
+    SG2_REQUIRE(p, SG2_ERR_BAD_ARG, "synth_set_pooled_output: null plan");
+    SG2_REQUIRE(factor == 0 || ((factor == 2 || factor == 4) && pooled && p->size % (4 * factor) == 0), SG2_ERR_BAD_ARG,
+                "synth_set_pooled_output: factor must be 0 (off), 2 or 4 with a buffer, and divide the image size (%d)", p->size);
+    SG2_REQUIRE(!p->train || factor == 0, SG2_ERR_UNSUPPORTED, "synth_set_pooled_output: not in training mode (the backward expects the full image gradient)");
+    p->pool = factor;
+    p->pool_out = factor ? pooled : nullptr;
+    p->pool_keep_full = factor == 0 || keep_full != 0;
+    return SG2_OK;
+}
+
 extern "C" int sg2_synth_set_profile_events(sg2_synth *p, void **events, int n_events) {
     SG2_REQUIRE(p, SG2_ERR_BAD_ARG, "synth_set_profile_events: null plan");
     p->events = reinterpret_cast<cudaEvent_t *>(events);
@@ -574,7 +585,8 @@ extern "C" int sg2_synth_forward(sg2_synth *S, void *workspace, const float *lat
     SG2_REQUIRE(B64 >= 0 && B64 <= S->max_batch, SG2_ERR_BAD_ARG, "synth_forward: batch %lld exceeds the plan's max_batch %d",
                 (long long)B64, S->max_batch);
     if (B64 == 0) return SG2_OK;                 // empty batch: nothing to launch (tensor pointers may be null)
-    SG2_REQUIRE(workspace && latent && image && noise && noise_bstride, SG2_ERR_BAD_ARG, "synth_forward: null pointer");
+    SG2_REQUIRE(workspace && latent && noise && noise_bstride, SG2_ERR_BAD_ARG, "synth_forward: null pointer");
+    SG2_REQUIRE(image || (S->pool && !S->pool_keep_full), SG2_ERR_BAD_ARG, "synth_forward: null image (allowed only with a pooled-only output)");
     const int B = (int)B64;
     cudaStream_t st = as_stream(stream);
     uint8_t *ws = static_cast<uint8_t *>(workspace);
@@ -713,7 +725,7 @@ extern "C" int sg2_synth_forward(sg2_synth *S, void *workspace, const float *lat
             // Measured at 1024^2, B = 32: the conv grows by 0.34 ms (its epilogue is the paced role: every instruction added per
             // pixel shows), rgb_combine saves 0.26 ms -> opt-in only, SG2_DXS_IMAGE=1.
             static const char *envfi = getenv("SG2_DXS_IMAGE");
-            const bool fuse_image = rgb && !next_conv && !S->ada && L.p.cout == 32 && envfi && atoi(envfi) != 0;
+            const bool fuse_image = rgb && !next_conv && !S->ada && !S->pool && L.p.cout == 32 && envfi && atoi(envfi) != 0;
             if (fuse_image) {
                 d.image = image; d.rgb_bias = rgb->p.act_bias; d.prev = rgb_cur >= 0 ? rgbbuf[rgb_cur] : nullptr;
                 memcpy(d.kf, S->kf, sizeof(d.kf));
@@ -728,6 +740,11 @@ extern "C" int sg2_synth_forward(sg2_synth *S, void *workspace, const float *lat
                 const bool last = next_conv == nullptr;
                 const int dst = rgb_cur == 0 ? 1 : 0;
                 rp.out = last ? image : rgbbuf[dst];
+                rp.pool = 0; rp.pool_out = nullptr;
+                if (last && S->pool) {          // face_pool folded into the last launch (sg2_synth_set_pooled_output)
+                    rp.pool = S->pool; rp.pool_out = S->pool_out;
+                    if (!S->pool_keep_full) rp.out = nullptr;
+                }
                 rp.part = part; rp.n_parts = 3 * L.p.cout <= 128 ? 1 : 2; rp.bias = rgb->p.act_bias;
                 rp.prev = rgb_cur >= 0 ? rgbbuf[rgb_cur] : nullptr;
                 rp.B = B; rp.R = L.res_out;
@@ -756,6 +773,11 @@ extern "C" int sg2_synth_forward(sg2_synth *S, void *workspace, const float *lat
                 const bool last = next_conv == nullptr;
                 const int dst = rgb_cur == 0 ? 1 : 0;
                 rp.out = last ? image : rgbbuf[dst];
+                rp.pool = 0; rp.pool_out = nullptr;
+                if (last && S->pool) {          // face_pool folded into the last launch (sg2_synth_set_pooled_output)
+                    rp.pool = S->pool; rp.pool_out = S->pool_out;
+                    if (!S->pool_keep_full) rp.out = nullptr;
+                }
                 // partial ToRGB planes per N tile: the cta_group::2 kernel has 4 column groups, the single-CTA one 2 (or 1)
                 const int parts_per_tile = L.two_sm ? std::min(kGemm2EpiGroups, g.block_n / 32) : (g.epi_alt ? 1 : 2);
                 rp.part = part; rp.n_parts = parts_per_tile * g.n_tiles_n; rp.bias = rgb->p.act_bias;

@@ -283,70 +283,93 @@ upfir_kernel(UpfirParams p) {
 // ---- RGB skip chain: rgb[n,c,Y,X] = sum_nt part[nt,n,c,Y,X] + bias[c] + up2(prev)[n,c,Y,X]   (NCHW fp32)
 __host__ __device__ __forceinline__ int fdiv2(int a) { return a >= 0 ? a / 2 : -((-a + 1) / 2); }
 
+// one quad (four consecutive pixels of row Y starting at X0, a multiple of 4) of plane `plane`: sum of the partial ToRGB planes
+// + bias (+ clamp) + the up-sampled skip image
+__device__ __forceinline__ float4 rgb_quad(const RgbParams &p, const float *sp, float bias, int64_t total, int64_t i, int Y, int X0,
+                                           int R, int S) {
+    float4 v = make_float4(bias, bias, bias, bias);
+    for (int nt = 0; nt < p.n_parts; ++nt) {
+        const float4 t = __ldg(reinterpret_cast<const float4 *>(p.part + (int64_t)nt * total + i));
+        v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+    }
+    if (p.clamp > 0.f) {             // stylegan2_ada: clamp(y + bias) before the skip is added
+        v.x = fminf(fmaxf(v.x, -p.clamp), p.clamp); v.y = fminf(fmaxf(v.y, -p.clamp), p.clamp);
+        v.z = fminf(fmaxf(v.z, -p.clamp), p.clamp); v.w = fminf(fmaxf(v.w, -p.clamp), p.clamp);
+    }
+    if (sp && p.smooth) {
+        // SmoothUpsample (stylegan2_ada/utils.py:76-95): output (2i+py, 2j+px) = sum_{a,b} kf[a][b] *
+        // skip[clamp(i + off[py][a])][clamp(j + off[px][b])], off = {{-1,-1,0,0},{-1,0,0,1}}
+        const int i0 = Y >> 1, py = Y & 1;
+        float up[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int oy = py ? (a == 0 ? -1 : (a == 3 ? 1 : 0)) : (a < 2 ? -1 : 0);
+            const float *row = sp + min(max(i0 + oy, 0), S - 1) * S;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int X = X0 + e, j0 = X >> 1, px = X & 1;
+#pragma unroll
+                for (int bq = 0; bq < 4; ++bq) {
+                    const int ox = px ? (bq == 0 ? -1 : (bq == 3 ? 1 : 0)) : (bq < 2 ? -1 : 0);
+                    up[e] = fmaf(p.kf[a * 4 + bq], __ldg(row + min(max(j0 + ox, 0), S - 1)), up[e]);
+                }
+            }
+        }
+        v.x += up[0]; v.y += up[1]; v.z += up[2]; v.w += up[3];
+    } else if (sp) {
+        // up=2, pad (2,1), 4x4 taps (index math of upfirdn2d_kernel.cu:112-129, specialised to a quad that
+        // starts at a multiple of 4): output row Y reads skip rows iy0, iy0+1 with tap rows ky0, ky0+2;
+        // the quad reads skip columns h-1 .. h+2 (h = X0/2) with tap columns (0,2) (1,3) (0,2) (1,3)
+        const int iy0 = fdiv2(Y - 1), ky0 = 2 * iy0 + 2 - Y, h = X0 >> 1;
+        float up0 = 0.f, up1 = 0.f, up2 = 0.f, up3 = 0.f;
+#pragma unroll
+        for (int a2 = 0; a2 < 2; ++a2) {
+            const int iy = iy0 + a2;
+            if (iy < 0 || iy >= S) continue;
+            const float *row = sp + iy * S;
+            float k[4];             // tap row ky0 + 2*a2 (static indices: the taps stay in the constant bank)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) k[j] = ky0 ? p.kf[(1 + 2 * a2) * 4 + j] : p.kf[(2 * a2) * 4 + j];
+            const float c0 = h >= 1 ? __ldg(row + h - 1) : 0.f, c1 = __ldg(row + h);
+            const float c2 = h + 1 < S ? __ldg(row + h + 1) : 0.f, c3 = h + 2 < S ? __ldg(row + h + 2) : 0.f;
+            up0 += k[0] * c0 + k[2] * c1;
+            up1 += k[1] * c1 + k[3] * c2;
+            up2 += k[0] * c1 + k[2] * c2;
+            up3 += k[1] * c2 + k[3] * c3;
+        }
+        v.x += up0; v.y += up1; v.z += up2; v.w += up3;
+    }
+    return v;
+}
+
 __global__ void __launch_bounds__(256)
 rgb_combine_kernel(RgbParams p) {
-    // grid.y = plane (n*3 + c); a thread owns 4 consecutive pixels of a row: float4 traffic, 32-bit index math
+    // grid.y = plane (n*3 + c); a thread owns 4 consecutive pixels of a row: float4 traffic, 32-bit index math.
+    // p.pool = 2 / 4 (the LAST launch of a forward): the thread walks the `pool` rows of its quad column and also
+    // emits their average -- AdaptiveAvgPool2d((R / pool, R / pool)), pSp's face_pool (psp.py:33,113-114) -- so the pooled image
+    // costs no second pass over the full-resolution one; p.out may then be null (pooled image only).
     const int R = p.R, S = R / 2, quads = R / 4;
+    const int prow = p.pool > 1 ? p.pool : 1, nrows = R / prow;
     const int64_t plane_px = (int64_t)R * R, total = (int64_t)p.B * 3 * plane_px;
     for (int plane = blockIdx.y; plane < p.B * 3; plane += gridDim.y) {
         const float bias = __ldg(p.bias + plane % 3);
         const float *sp = p.prev ? p.prev + (int64_t)plane * S * S : nullptr;
-        for (int q = blockIdx.x * 256 + threadIdx.x; q < R * quads; q += gridDim.x * 256) {
-            const int Y = q / quads, X0 = (q - Y * quads) * 4;
-            const int64_t i = (int64_t)plane * plane_px + (int64_t)Y * R + X0;
-            float4 v = make_float4(bias, bias, bias, bias);
-            for (int nt = 0; nt < p.n_parts; ++nt) {
-                const float4 t = __ldg(reinterpret_cast<const float4 *>(p.part + (int64_t)nt * total + i));
-                v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+        for (int q = blockIdx.x * 256 + threadIdx.x; q < nrows * quads; q += gridDim.x * 256) {
+            const int Yp = q / quads, X0 = (q - Yp * quads) * 4;
+            float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int r = 0; r < prow; ++r) {
+                const int Y = Yp * prow + r;
+                const int64_t i = (int64_t)plane * plane_px + (int64_t)Y * R + X0;
+                const float4 v = rgb_quad(p, sp, bias, total, i, Y, X0, R, S);
+                if (p.out) *reinterpret_cast<float4 *>(p.out + i) = v;
+                sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
             }
-            if (p.clamp > 0.f) {             // stylegan2_ada: clamp(y + bias) before the skip is added
-                v.x = fminf(fmaxf(v.x, -p.clamp), p.clamp); v.y = fminf(fmaxf(v.y, -p.clamp), p.clamp);
-                v.z = fminf(fmaxf(v.z, -p.clamp), p.clamp); v.w = fminf(fmaxf(v.w, -p.clamp), p.clamp);
+            if (p.pool == 4) {
+                p.pool_out[(int64_t)plane * (plane_px / 16) + (int64_t)Yp * (R / 4) + (X0 >> 2)] = (sum.x + sum.y + sum.z + sum.w) * (1.f / 16.f);
+            } else if (p.pool == 2) {
+                *reinterpret_cast<float2 *>(p.pool_out + (int64_t)plane * (plane_px / 4) + (int64_t)Yp * (R / 2) + (X0 >> 1)) =
+                    make_float2((sum.x + sum.y) * 0.25f, (sum.z + sum.w) * 0.25f);
             }
-            if (sp && p.smooth) {
-                // SmoothUpsample (stylegan2_ada/utils.py:76-95): output (2i+py, 2j+px) = sum_{a,b} kf[a][b] *
-                // skip[clamp(i + off[py][a])][clamp(j + off[px][b])], off = {{-1,-1,0,0},{-1,0,0,1}}
-                const int i0 = Y >> 1, py = Y & 1;
-                float up[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                for (int a = 0; a < 4; ++a) {
-                    const int oy = py ? (a == 0 ? -1 : (a == 3 ? 1 : 0)) : (a < 2 ? -1 : 0);
-                    const float *row = sp + min(max(i0 + oy, 0), S - 1) * S;
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int X = X0 + e, j0 = X >> 1, px = X & 1;
-#pragma unroll
-                        for (int bq = 0; bq < 4; ++bq) {
-                            const int ox = px ? (bq == 0 ? -1 : (bq == 3 ? 1 : 0)) : (bq < 2 ? -1 : 0);
-                            up[e] = fmaf(p.kf[a * 4 + bq], __ldg(row + min(max(j0 + ox, 0), S - 1)), up[e]);
-                        }
-                    }
-                }
-                v.x += up[0]; v.y += up[1]; v.z += up[2]; v.w += up[3];
-            } else if (sp) {
-                // up=2, pad (2,1), 4x4 taps (index math of upfirdn2d_kernel.cu:112-129, specialised to a quad that
-                // starts at a multiple of 4): output row Y reads skip rows iy0, iy0+1 with tap rows ky0, ky0+2;
-                // the quad reads skip columns h-1 .. h+2 (h = X0/2) with tap columns (0,2) (1,3) (0,2) (1,3)
-                const int iy0 = fdiv2(Y - 1), ky0 = 2 * iy0 + 2 - Y, h = X0 >> 1;
-                float up0 = 0.f, up1 = 0.f, up2 = 0.f, up3 = 0.f;
-#pragma unroll
-                for (int a2 = 0; a2 < 2; ++a2) {
-                    const int iy = iy0 + a2;
-                    if (iy < 0 || iy >= S) continue;
-                    const float *row = sp + iy * S;
-                    float k[4];             // tap row ky0 + 2*a2 (static indices: the taps stay in the constant bank)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) k[j] = ky0 ? p.kf[(1 + 2 * a2) * 4 + j] : p.kf[(2 * a2) * 4 + j];
-                    const float c0 = h >= 1 ? __ldg(row + h - 1) : 0.f, c1 = __ldg(row + h);
-                    const float c2 = h + 1 < S ? __ldg(row + h + 1) : 0.f, c3 = h + 2 < S ? __ldg(row + h + 2) : 0.f;
-                    up0 += k[0] * c0 + k[2] * c1;
-                    up1 += k[1] * c1 + k[3] * c2;
-                    up2 += k[0] * c1 + k[2] * c2;
-                    up3 += k[1] * c2 + k[3] * c3;
-                }
-                v.x += up0; v.y += up1; v.z += up2; v.w += up3;
-            }
-            *reinterpret_cast<float4 *>(p.out + i) = v;
         }
     }
 }
@@ -472,7 +495,10 @@ int launch_upfir(const UpfirParams &p, int B, cudaStream_t st) {
     return SG2_OK;
 }
 int launch_rgb_combine(const RgbParams &p, int sms, cudaStream_t st) {
-    const int quads = p.R * (p.R / 4);
+    SG2_REQUIRE(p.pool == 0 || ((p.pool == 2 || p.pool == 4) && p.pool_out && p.R % (4 * p.pool / (p.pool == 4 ? 4 : 2)) == 0 && p.R >= 4 * p.pool),
+                SG2_ERR_BAD_ARG, "rgb_combine: pooled output needs factor 2 or 4 and a buffer (R %d, pool %d)", p.R, p.pool);
+    SG2_REQUIRE(p.out || p.pool, SG2_ERR_BAD_ARG, "rgb_combine: no output");
+    const int quads = (p.R / (p.pool > 1 ? p.pool : 1)) * (p.R / 4);
     // enough blocks to keep the loads of a whole plane in flight (a cap of 64 left every thread 16 dependent-looking
     // iterations at 1024^2: 2.7 TB/s)
     dim3 grid((unsigned)std::min(512, (quads + 255) / 256), (unsigned)std::min(p.B * 3, 65535));

@@ -61,6 +61,10 @@ struct RgbParams {
     // running image is up-sampled by SmoothUpsample (nearest x2, edge replication, 4x4 correlation with kf as given)
     float clamp;                  // 0: none
     int smooth;                   // 0: zero-insertion up-sampling, pad (2,1), flipped taps (rosinality Upsample)
+    // last launch of a forward only: also write the image average-pooled by `pool` (2 or 4; 0 = off) to pool_out
+    // [B,3,R/pool,R/pool]; `out` may then be null
+    int pool;
+    float *pool_out;
 };
 
 // stylegan2_ada up-sampling layer after its convolution (generator.py:198-204, utils.py:76-95): SmoothUpsample of the

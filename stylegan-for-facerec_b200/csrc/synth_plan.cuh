@@ -82,6 +82,10 @@ struct sg2_synth {
     void *bcached_ws = nullptr;
     int bcached_B = -1;
     // profiling hooks
+    // pooled output of the last rgb_combine launch (sg2_synth_set_pooled_output): factor 0 = off
+    int pool = 0;
+    bool pool_keep_full = true;
+    float *pool_out = nullptr;
     cudaEvent_t *events = nullptr;
     int n_events = 0, events_used = 0;
     std::string description;

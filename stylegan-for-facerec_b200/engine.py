@@ -191,10 +191,27 @@ class SynthesisEngine:
                 raise RuntimeError(f"noise[{i}] of shape {tuple(n.shape)} does not match [{B} or 1, 1, {r}, {r}]")
         return tuple(out)
 
-    def _call(self, lat, B, ptrs, strides, image):
+    def _call(self, lat, B, ptrs, strides, image, pooled=None, pool=0):
+        """one sg2_synth_forward; with `pooled` ([B,3,size/pool,size/pool] fp32) the last launch also writes the face-pooled
+        image (sg2_synth_set_pooled_output) and `image` may be None (pooled image only)"""
         with _lib.device_of(lat):
-            _lib.check(self.lib.sg2_synth_forward(self.plan, self.workspace.data_ptr(), lat.data_ptr(), B, ptrs,
-                                                  strides, image.data_ptr(), _lib.stream_of(lat)), "synth_forward")
+            if pool:
+                _lib.check(self.lib.sg2_synth_set_pooled_output(self.plan, pooled.data_ptr(), pool, 0 if image is None else 1),
+                           "synth_set_pooled_output")
+            try:
+                _lib.check(self.lib.sg2_synth_forward(self.plan, self.workspace.data_ptr(), lat.data_ptr(), B, ptrs, strides,
+                                                      None if image is None else image.data_ptr(), _lib.stream_of(lat)),
+                           "synth_forward")
+            finally:
+                if pool:
+                    self.lib.sg2_synth_set_pooled_output(self.plan, None, 0, 1)
+
+    def _pool_request(self, B, dev):
+        """face_pool folded into the forward (psp_io.decode_pooled sets Generator._pool_request = factor): -> factor or 0"""
+        f = getattr(self._G(), "_pool_request", None) if not self.training else None
+        if f in (2, 4) and self.G.size % (4 * f) == 0:
+            return f
+        return 0
 
     @torch.no_grad()
     def synthesize(self, latent, noise, graph=None, z=None, want_latent=True):
@@ -226,15 +243,20 @@ class SynthesisEngine:
                                "(Generator.engine() re-plans after the module moves)")
         if B == 0:
             return torch.empty(0, 3, G.size, G.size, device=dev, dtype=out_dtype)
+        pool = self._pool_request(B, dev)
         if not use_graph or torch.cuda.is_current_stream_capturing():
             lat = latent.detach().float().contiguous()
             ptrs, strides, keep = self._noise_args(B, noise, dev)
-            image = torch.empty(B, 3, G.size, G.size, device=dev, dtype=torch.float32)
-            self._call(lat, B, ptrs, strides, image)
+            if pool:                             # pooled image only: the full-resolution one is never written
+                image = torch.empty(B, 3, G.size // pool, G.size // pool, device=dev, dtype=torch.float32)
+                self._call(lat, B, ptrs, strides, None, pooled=image, pool=pool)
+            else:
+                image = torch.empty(B, 3, G.size, G.size, device=dev, dtype=torch.float32)
+                self._call(lat, B, ptrs, strides, image)
             return image if out_dtype == torch.float32 else image.to(out_dtype)
 
         layout = self._noise_layout(B, noise)
-        key = (B, layout, dev.index, from_z)
+        key = (B, layout, dev.index, from_z, pool)
         entry = self._graphs.get(key)
         if entry is None:
             s_lat = torch.empty(B, G.n_latent, G.style_dim, device=dev, dtype=torch.float32)
@@ -251,12 +273,18 @@ class SynthesisEngine:
             for shp, n in zip(shapes, sizes):
                 s_noise.append(s_flat[o:o + n].view(shp))
                 o += n
-            s_img = torch.empty(B, 3, G.size, G.size, device=dev, dtype=torch.float32)
+            s_img = torch.empty(B, 3, G.size // (pool or 1), G.size // (pool or 1), device=dev, dtype=torch.float32)
             (s_z if from_z else s_lat).copy_(z if from_z else latent)
             ptrs, strides, _ = self._noise_args(B, noise, dev, into=s_noise)
             n0 = _lib.launch_count()
             head()
-            self._call(s_lat, B, ptrs, strides, s_img)              # warm-up outside capture (lazy attributes, descriptors)
+
+            def run():
+                if pool:
+                    self._call(s_lat, B, ptrs, strides, None, pooled=s_img, pool=pool)
+                else:
+                    self._call(s_lat, B, ptrs, strides, s_img)
+            run()                                                   # warm-up outside capture (lazy attributes, descriptors)
             n_launch = _lib.launch_count() - n0
             torch.cuda.current_stream(dev).synchronize()
             g = torch.cuda.CUDAGraph()
@@ -269,7 +297,7 @@ class SynthesisEngine:
             try:
                 with torch.cuda.graph(g, capture_error_mode="thread_local"):
                     head()
-                    self._call(s_lat, B, ptrs, strides, s_img)
+                    run()
             finally:
                 if gc_was_on:
                     gc.enable()

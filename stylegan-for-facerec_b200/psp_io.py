@@ -112,6 +112,25 @@ class FacePool(torch.nn.Module):
         return face_pool(x, self.output_size)
 
 
+def decode_pooled(generator, styles, size=(256, 256), **forward_kwargs):
+    """`images, latent = decoder(styles, **kw); images = face_pool(images)` (psp.py:104-114) as one call: when the decoder runs
+    on the whole-network engine (bf16, nothing requires grad) and the pooling ratio is 2 or 4, the LAST launch of the forward
+    writes the pooled image itself and the full-resolution image is never stored; otherwise the two steps run one
+    after the other (`face_pool` carries autograd).  -> (pooled images, latent or None)"""
+    oh, ow = (size, size) if isinstance(size, int) else size
+    full = getattr(generator, "size", None)
+    factor = full // oh if (full and oh == ow and full % oh == 0) else 0
+    if factor in (2, 4):
+        generator.__dict__["_pool_request"] = factor
+    try:
+        images, latent = generator(styles, **forward_kwargs)
+    finally:
+        generator.__dict__.pop("_pool_request", None)
+    if images.shape[-2:] != (oh, ow):            # the engine did not take the request (autograd, exact path, other ratios)
+        images = face_pool(images, (oh, ow))
+    return images, latent
+
+
 def decode_epilogue(images: torch.Tensor, pool=(256, 256), resize=112):
     """decoder output -> (face-pooled image for the next refinement step, its 112x112 version for the losses)."""
     pooled = face_pool(images, pool)

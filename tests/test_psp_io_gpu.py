@@ -84,3 +84,38 @@ def test_face_pool_and_resize_gradients_vs_torch(sg2):
     assert (xd.grad.float().cpu() - xr.grad).abs().max() <= 2e-2 * xr.grad.abs().max()
     with pytest.raises(RuntimeError, match="inference-only"):
         io.images_to_uint8(xd)
+
+
+@pytest.mark.parametrize("size,pooled,b", [(64, 16, 3), (64, 32, 3), (1024, 256, 2), (512, 256, 2)])
+def test_decode_pooled_matches_decoder_then_face_pool(sg2, size, pooled, b):
+    """psp.py:104-114 as one call: the engine's last launch writes the face-pooled image itself (no full-resolution image is
+    stored) -- equal to the same engine's image pooled by the op kernel, through the CUDA graph and without it, from z and
+    from w+; on the exact path (no engine) the two steps simply run one after the other"""
+    io = importlib.import_module("stylegan-for-facerec_b200.psp_io")
+    torch.manual_seed(0)
+    G = sg2.Generator(size, 512, 2).to(DEV).eval()
+    z = torch.randn(b, 512, device=DEV)
+    with torch.no_grad():
+        G.precision = "bf16"
+        full, lat = G([z], randomize_noise=False, return_latents=True)
+        ref = io.face_pool(full, pooled)
+        n0 = sg2._lib.launch_count()
+        y, lat2 = io.decode_pooled(G, [z], pooled, randomize_noise=False, return_latents=True)          # from z, graph
+        assert sg2._lib.launch_count() > n0
+        assert y.shape == (b, 3, pooled, pooled) and torch.equal(lat, lat2)
+        scale = float(ref.abs().max())
+        assert float((y - ref).abs().max()) <= 2e-6 * max(scale, 1.0)
+        y2, _ = io.decode_pooled(G, [lat], pooled, input_is_latent=True, randomize_noise=False)         # from w+, graph
+        assert float((y2 - ref).abs().max()) <= 2e-6 * max(scale, 1.0)
+        eng = G.engine()
+        eng.use_graph = False
+        y3, _ = io.decode_pooled(G, [lat], pooled, input_is_latent=True, randomize_noise=False)         # plain launches
+        eng.use_graph = True
+        assert float((y3 - ref).abs().max()) <= 2e-6 * max(scale, 1.0)
+        full_again, _ = G([z], randomize_noise=False)                # the request does not leak into ordinary forwards
+        assert full_again.shape[-1] == size and torch.equal(full_again, full)
+        if size <= 64:
+            G.precision = "exact"
+            fe, _ = G([z], randomize_noise=False)
+            ye, _ = io.decode_pooled(G, [z], pooled, randomize_noise=False)
+            assert torch.equal(ye, io.face_pool(fe, pooled))
