@@ -256,6 +256,159 @@ modconv_simt_big_kernel(T *__restrict__ out, const T *__restrict__ x, const floa
     }
 }
 
+// ---- the big tile, software-pipelined (fp32 storage; tiles that lie inside one sample) -------------------------------------
+// ncu of the kernel above: 35 % of the stall samples sit on the first use of the staged loads (every warp loads, waits, then
+// computes; 16 warps per SM do not cover it).  Here chunk c + 1 travels by cp.async (no registers held by loads in flight)
+// into the other half of a double buffer while chunk c is multiplied: weights as 16-byte copies of four consecutive output
+// channels, activations as 4-byte copies whose zero-fill form IS the convolution's zero padding.  cp.async cannot modulate
+// on the way, so the style is multiplied into the WEIGHT tile once it has landed (one pass over Ws per chunk) -- legal when
+// all BN columns of the tile belong to one sample (P a multiple of BN: every layer from 16 x 16 up).
+__device__ __forceinline__ void cpa16(void *dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cpa4_zfill(void *dst, const void *src, bool valid) {
+    const int n = valid ? 4 : 0;           // src-size 0: four zero bytes are written, the source is not read
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "r"(n) : "memory");
+}
+
+template <typename CFG>
+__global__ void __launch_bounds__(256, 2)
+modconv_simt_pipe_kernel(float *__restrict__ out, const float *__restrict__ x, const float *__restrict__ wt,
+                         const float *__restrict__ style, const float *__restrict__ demod, ConvGeo g) {
+    constexpr int BM = CFG::BM, BN = CFG::BN, KC = CFG::KC, CPT = CFG::CPT, CS = CFG::CS;
+    constexpr int BUF = KC * MAXT * (BM + BN);                                      // floats per stage
+    extern __shared__ __align__(16) float big_smem[];
+    __shared__ int s_dy[MAXT], s_dx[MAXT];
+    __shared__ int s_woff[KC * MAXT];
+    __shared__ int s_kcil[KC * MAXT];      // channel (inside the chunk) of k-row kk
+
+    const int tid = threadIdx.x;
+    const int ntaps = g.ntaps, nk = KC * ntaps;
+    if (tid < ntaps) { s_dy[tid] = g.dy[tid]; s_dx[tid] = g.dx[tid]; }
+    if (tid < nk) {
+        const int cil = tid / ntaps, t = tid - cil * ntaps;
+        s_woff[tid] = (cil * g.kk + g.widx[t]) * g.Cout;
+        s_kcil[tid] = cil;
+    }
+    const int tx = tid % CFG::TN, ty = tid / CFG::TN;
+    const int co0 = blockIdx.y * BM;
+    const int64_t n0 = (int64_t)blockIdx.x * BN;
+    const int P = g.PH * g.PW;
+    const int64_t HW = (int64_t)g.H * g.W;
+    const int sb = (int)(n0 / P);                          // the tile's sample
+    const int p0 = (int)(n0 - (int64_t)sb * P);
+    const float *xs = x + (int64_t)sb * g.Cin * HW;
+    const float *sty = style ? style + (int64_t)sb * g.Cin : nullptr;
+
+    // staging role: CPT columns of Xs per thread, channels cs, cs + CS, ... of the chunk
+    const int cs = CS > 1 ? tid / BN : 0;
+    int iy_base[CPT], ix_base[CPT];
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) {
+        const int r = p0 + (tid % BN) + j * 256;
+        const int soy = r / g.PW, sox = r - soy * g.PW;
+        iy_base[j] = soy * g.in_sy; ix_base[j] = sox * g.in_sx;
+    }
+    __syncthreads();                       // tables
+
+    auto issue = [&](int ci0, int buf) {
+        float (*Ws)[BM] = reinterpret_cast<float (*)[BM]>(big_smem + buf * BUF);
+        float (*Xs)[BN] = reinterpret_cast<float (*)[BN]>(big_smem + buf * BUF + KC * MAXT * BM);
+        // weights: four consecutive output channels per copy
+        const float *wc = wt + (int64_t)ci0 * g.kk * g.Cout + co0;
+        for (int i = tid; i < nk * (BM / 4); i += 256) {
+            const int kk = i / (BM / 4), c4 = (i - kk * (BM / 4)) * 4;
+            cpa16(&Ws[kk][c4], wc + s_woff[kk] + c4);
+        }
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) {
+            const int col = (tid % BN) + j * 256;
+            for (int t = 0; t < ntaps; ++t) {
+                const int iy = iy_base[j] + s_dy[t], ix = ix_base[j] + s_dx[t];
+                const bool ok = iy >= 0 && ix >= 0 && iy < g.H && ix < g.W;
+                const float *src = xs + ((int64_t)ci0 * g.H + (ok ? iy : 0)) * g.W + (ok ? ix : 0);
+#pragma unroll
+                for (int c = cs; c < KC; c += CS) cpa4_zfill(&Xs[c * ntaps + t][col], src + c * HW, ok);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+    const int nchunks = g.Cin / KC;
+    issue(0, 0);
+    for (int c = 0; c < nchunks; ++c) {
+        const int buf = c & 1;
+        if (c + 1 < nchunks) {
+            issue((c + 1) * KC, buf ^ 1);                 // (its previous contents were consumed before the barrier that ended chunk c - 1)
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();                                   // every thread's copies of chunk c are visible
+        float (*Ws)[BM] = reinterpret_cast<float (*)[BM]>(big_smem + buf * BUF);
+        float (*Xs)[BN] = reinterpret_cast<float (*)[BN]>(big_smem + buf * BUF + KC * MAXT * BM);
+        if (sty) {                                         // modulation, applied to the weight rows of this chunk
+            for (int i = tid; i < nk * (BM / 4); i += 256) {
+                const int kk = i / (BM / 4), c4 = (i - kk * (BM / 4)) * 4;
+                const float sv = __ldg(sty + c * KC + s_kcil[kk]);
+                float4 w4 = *reinterpret_cast<float4 *>(&Ws[kk][c4]);
+                w4.x *= sv; w4.y *= sv; w4.z *= sv; w4.w *= sv;
+                *reinterpret_cast<float4 *>(&Ws[kk][c4]) = w4;
+            }
+            __syncthreads();
+        }
+#pragma unroll 4
+        for (int kk = 0; kk < nk; ++kk) {
+            const float4 a0 = *reinterpret_cast<const float4 *>(&Ws[kk][ty * 4]);
+            const float4 a1 = *reinterpret_cast<const float4 *>(&Ws[kk][BM / 2 + ty * 4]);
+            const float4 b0 = *reinterpret_cast<const float4 *>(&Xs[kk][tx * 4]);
+            const float4 b1 = *reinterpret_cast<const float4 *>(&Xs[kk][BN / 2 + tx * 4]);
+            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();                                   // chunk c consumed: its buffer may be refilled
+    }
+
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int r = p0 + (j < 4 ? tx * 4 + j : BN / 2 + tx * 4 + (j - 4));
+        const int ly = r / g.PW, lx = r - ly * g.PW;
+        const int oy = ly * g.out_sy + g.out_oy, ox = lx * g.out_sx + g.out_ox;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int co = co0 + (i < 4 ? ty * 4 + i : BM / 2 + ty * 4 + (i - 4));
+            float v = acc[i][j];
+            if (demod) v *= __ldg(demod + (int64_t)sb * g.Cout + co);
+            out[(((int64_t)sb * g.Cout + co) * g.OH + oy) * g.OW + ox] = v;
+        }
+    }
+}
+
+template <typename CFG>
+static int launch_pipe(float *out, const float *x, const float *wt, const float *style, const float *demod, const ConvGeo &g,
+                       int64_t Ntot, cudaStream_t st) {
+    constexpr size_t smem = 2 * CFG::smem;
+    static std::atomic<int> configured{0};
+    if (!configured.load(std::memory_order_acquire)) {
+        SG2_CUDA_OK(cudaFuncSetAttribute(modconv_simt_pipe_kernel<CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured.store(1, std::memory_order_release);
+    }
+    dim3 grid((unsigned)(Ntot / CFG::BN), g.Cout / CFG::BM);
+    modconv_simt_pipe_kernel<CFG><<<grid, 256, smem, st>>>(out, x, wt, style, demod, g);
+    SG2_LAUNCH_CHECK();
+    return SG2_OK;
+}
+
 template <typename T, typename CFG>
 static int launch_big(T *out, const T *x, const float *wt, const float *style, const float *demod, const ConvGeo &g, int64_t Ntot,
                       cudaStream_t st) {
@@ -327,6 +480,17 @@ extern "C" int sg2_modconv2d_fwd(void *out, const void *x, const float *wt, cons
         static const char *env_big = getenv("SG2_MODCONV_BIG");       // A/B switch: 0 = the 64 x 64 kernel everywhere
         const bool big_ok = (!env_big || atoi(env_big) != 0) && Cout % 32 == 0 && Cin % 8 == 0 && k == 3 &&
                             (int64_t)Cin * 9 * Cout < (1ll << 31);
+        // fp32 storage, tiles inside one sample, 16-byte aligned weight rows: the pipelined form (KC = 4 per stage)
+        static const char *env_pipe = getenv("SG2_MODCONV_PIPE");     // A/B switch: 0 = off
+        const int P = g.PH * g.PW;
+        if (big_ok && (!env_pipe || atoi(env_pipe) != 0) && dtype == SG2_F32 && (reinterpret_cast<uintptr_t>(wt) & 15) == 0 &&
+            Cin % 4 == 0) {
+            int rc = 1;
+            if (Cout % 128 == 0 && P % 128 == 0) rc = launch_pipe<BigTile<128, 128, 4>>((float *)out, (const float *)x, wt, style, demod, g, Ntot, st);
+            else if (Cout % 64 == 0 && Cout < 128 && P % 256 == 0) rc = launch_pipe<BigTile<64, 256, 4>>((float *)out, (const float *)x, wt, style, demod, g, Ntot, st);
+            if (rc < 0 || rc > 1) return rc;
+            if (rc == 0) continue;
+        }
         SG2_DISPATCH_DTYPE(dtype, {
             int rc = 1;
             if (big_ok && Cout % 128 == 0 && Ntot >= 128 * 8) rc = launch_big<T, BigTile<128, 128, 8>>((T *)out, (const T *)x, wt, style, demod, g, Ntot, st);
