@@ -342,14 +342,15 @@ __device__ __forceinline__ float4 rgb_quad(const RgbParams &p, const float *sp, 
     return v;
 }
 
+template <int POOL>      // 0: the plain launch; 2 / 4: the last launch of a forward with the face-pooled image written on the way
 __global__ void __launch_bounds__(256)
 rgb_combine_kernel(RgbParams p) {
     // grid.y = plane (n*3 + c); a thread owns 4 consecutive pixels of a row: float4 traffic, 32-bit index math.
-    // p.pool = 2 / 4 (the LAST launch of a forward): the thread walks the `pool` rows of its quad column and also
-    // emits their average -- AdaptiveAvgPool2d((R / pool, R / pool)), pSp's face_pool (psp.py:33,113-114) -- so the pooled image
-    // costs no second pass over the full-resolution one; p.out may then be null (pooled image only).
-    const int R = p.R, S = R / 2, quads = R / 4;
-    const int prow = p.pool > 1 ? p.pool : 1, nrows = R / prow;
+    // POOL = 2 / 4: the thread walks the POOL rows of its quad column and also emits their average --
+    // AdaptiveAvgPool2d((R / POOL, R / POOL)), pSp's face_pool (psp.py:33,113-114) -- so the pooled image costs no second pass
+    // over the full-resolution one; p.out may then be null (pooled image only).
+    constexpr int PROW = POOL > 1 ? POOL : 1;
+    const int R = p.R, S = R / 2, quads = R / 4, nrows = R / PROW;
     const int64_t plane_px = (int64_t)R * R, total = (int64_t)p.B * 3 * plane_px;
     for (int plane = blockIdx.y; plane < p.B * 3; plane += gridDim.y) {
         const float bias = __ldg(p.bias + plane % 3);
@@ -357,16 +358,17 @@ rgb_combine_kernel(RgbParams p) {
         for (int q = blockIdx.x * 256 + threadIdx.x; q < nrows * quads; q += gridDim.x * 256) {
             const int Yp = q / quads, X0 = (q - Yp * quads) * 4;
             float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int r = 0; r < prow; ++r) {
-                const int Y = Yp * prow + r;
+#pragma unroll
+            for (int r = 0; r < PROW; ++r) {
+                const int Y = Yp * PROW + r;
                 const int64_t i = (int64_t)plane * plane_px + (int64_t)Y * R + X0;
                 const float4 v = rgb_quad(p, sp, bias, total, i, Y, X0, R, S);
-                if (p.out) *reinterpret_cast<float4 *>(p.out + i) = v;
-                sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+                if (POOL == 0 || p.out) *reinterpret_cast<float4 *>(p.out + i) = v;
+                if (POOL) { sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w; }
             }
-            if (p.pool == 4) {
+            if (POOL == 4) {
                 p.pool_out[(int64_t)plane * (plane_px / 16) + (int64_t)Yp * (R / 4) + (X0 >> 2)] = (sum.x + sum.y + sum.z + sum.w) * (1.f / 16.f);
-            } else if (p.pool == 2) {
+            } else if (POOL == 2) {
                 *reinterpret_cast<float2 *>(p.pool_out + (int64_t)plane * (plane_px / 4) + (int64_t)Yp * (R / 2) + (X0 >> 1)) =
                     make_float2((sum.x + sum.y) * 0.25f, (sum.z + sum.w) * 0.25f);
             }
@@ -503,7 +505,9 @@ int launch_rgb_combine(const RgbParams &p, int sms, cudaStream_t st) {
     // iterations at 1024^2: 2.7 TB/s)
     dim3 grid((unsigned)std::min(512, (quads + 255) / 256), (unsigned)std::min(p.B * 3, 65535));
     (void)sms;
-    rgb_combine_kernel<<<grid, 256, 0, st>>>(p);
+    if (p.pool == 4) rgb_combine_kernel<4><<<grid, 256, 0, st>>>(p);
+    else if (p.pool == 2) rgb_combine_kernel<2><<<grid, 256, 0, st>>>(p);
+    else rgb_combine_kernel<0><<<grid, 256, 0, st>>>(p);
     SG2_LAUNCH_CHECK();
     return SG2_OK;
 }
