@@ -363,6 +363,77 @@ class SynthesisEngine:
             self._mod = rows
         return self._mod
 
+    def _train_graphs(self, latent, noise):
+        """CUDA graphs of the training forward and of the backward (+ the dL/dstyle -> dL/dlatent products) for this batch size
+        and noise layout, or None when capture is not possible here.  At B = 8 (the ReStyle batch) a decoder pass is ~30 + ~60
+        short launches: replayed as two graphs they run back to back (forward 1.40 -> 1.15 ms)."""
+        if os.environ.get("SG2_B200_TRAIN_GRAPH", "1") == "0" or torch.cuda.is_current_stream_capturing():
+            return None
+        G = self.G
+        B, dev = latent.shape[0], latent.device
+        layout = self._noise_layout(B, noise)
+        key = ("train", B, layout, dev.index)
+        e = self._graphs.get(key)
+        if e is not None:
+            return e
+        if threading.current_thread() is not threading.main_thread():
+            return None                          # capture only from the main thread (replay is fine anywhere)
+        mod = self._modulation_table()
+        total = B * sum(cin for _, cin, _ in mod)
+        s_lat = torch.empty(B, G.n_latent, G.style_dim, device=dev, dtype=torch.float32)
+        shapes = [(nb, 1, 2 ** ((i + 5) // 2), 2 ** ((i + 5) // 2)) for i, nb in enumerate(layout)]
+        sizes = [sh[0] * sh[2] * sh[3] for sh in shapes]
+        s_flat = torch.empty(sum(sizes), device=dev, dtype=torch.float32)
+        s_noise, o = [], 0
+        for shp, n in zip(shapes, sizes):
+            s_noise.append(s_flat[o:o + n].view(shp))
+            o += n
+        s_img = torch.empty(B, 3, G.size, G.size, device=dev, dtype=torch.float32)
+        s_gimg = torch.zeros(B, 3, G.size, G.size, device=dev, dtype=torch.float32)
+        s_gs = torch.empty(total, device=dev, dtype=torch.float32)
+        s_acc = torch.empty(G.n_latent, B, G.style_dim, device=dev, dtype=torch.float32)
+        s_out = torch.empty(B, G.n_latent, G.style_dim, device=dev, dtype=torch.float32)
+        s_lat.copy_(latent.detach())
+        ptrs, strides, _ = self._noise_args(B, noise, dev, into=s_noise)
+
+        def fwd():
+            self._call(s_lat, B, ptrs, strides, s_img)
+
+        def bwd():
+            with _lib.device_of(s_gimg):
+                _lib.check(self.lib.sg2_synth_backward(self.plan, self.workspace.data_ptr(), B, ptrs, strides, s_gimg.data_ptr(),
+                                                       s_gs.data_ptr(), _lib.stream_of(s_gimg)), "synth_backward")
+            s_acc.zero_()
+            off = 0
+            for idx, cin, w in mod:
+                s_acc[idx].addmm_(s_gs[off:off + B * cin].view(B, cin), w)
+                off += B * cin
+            s_out.copy_(s_acc.permute(1, 0, 2))
+
+        n0 = _lib.launch_count()
+        fwd()                                    # warm-up outside capture (descriptors, lazy attributes, library handles)
+        n1 = _lib.launch_count()
+        bwd()
+        n2 = _lib.launch_count()
+        torch.cuda.current_stream(dev).synchronize()
+        gf, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        gc.collect()
+        gc_was_on = gc.isenabled()
+        gc.disable()
+        try:
+            with torch.cuda.graph(gf, capture_error_mode="thread_local"):
+                fwd()
+            with torch.cuda.graph(gb, capture_error_mode="thread_local"):
+                bwd()
+        finally:
+            if gc_was_on:
+                gc.enable()
+        e = {"fwd": gf, "bwd": gb, "lat": s_lat, "noise": s_noise, "flat": s_flat, "img": s_img, "gimg": s_gimg, "gs": s_gs,
+             "acc": s_acc, "out": s_out, "args": (ptrs, strides), "src": [None] * len(s_noise),
+             "launches_fwd": n1 - n0, "launches_bwd": n2 - n1}
+        self._graphs[key] = e
+        return e
+
     def train_forward(self, latent, noise):
         """-> (image fp32 [B,3,size,size], state for train_backward)"""
         assert self.training
@@ -370,6 +441,14 @@ class SynthesisEngine:
         _lib.require_cuda(latent, "latent")
         B = latent.shape[0]
         self._ensure(B)
+        e = self._train_graphs(latent, noise) if B > 0 else None
+        if e is not None:
+            e["lat"].copy_(latent.detach())
+            self._stage_noise(e, noise)
+            e["fwd"].replay()
+            self.lib.sg2_note_launches(e["launches_fwd"])
+            self._fwd_id += 1
+            return e["img"].clone(), (self._fwd_id, B, e, None, None)
         lat = latent.detach().float().contiguous()
         ptrs, strides, keep = self._noise_args(B, noise, latent.device)
         image = torch.empty(B, 3, G.size, G.size, device=latent.device, dtype=torch.float32)
@@ -385,6 +464,12 @@ class SynthesisEngine:
             raise RuntimeError("sg2_b200 training engine: another forward pass ran on this Generator before backward(); "
                                "the kept activations are gone.  Call backward() after each forward (as the ReStyle "
                                "coaches do), or set SG2_B200_TRAIN_ENGINE=0 to use the autograd path")
+        if isinstance(ptrs, dict):               # graph entry of _train_graphs
+            e = ptrs
+            e["gimg"].copy_(grad_image.detach())
+            e["bwd"].replay()
+            self.lib.sg2_note_launches(e["launches_bwd"])
+            return e["out"].clone()
         G = self.G
         g = grad_image.detach().float().contiguous()
         mod = self._modulation_table()
