@@ -261,8 +261,9 @@ modconv_simt_big_kernel(T *__restrict__ out, const T *__restrict__ x, const floa
 // computes; 16 warps per SM do not cover it).  Here chunk c + 1 travels by cp.async (no registers held by loads in flight)
 // into the other half of a double buffer while chunk c is multiplied: weights as 16-byte copies of four consecutive output
 // channels, activations as 4-byte copies whose zero-fill form IS the convolution's zero padding.  cp.async cannot modulate
-// on the way, so the style is multiplied into the WEIGHT tile once it has landed (one pass over Ws per chunk) -- legal when
-// all BN columns of the tile belong to one sample (P a multiple of BN: every layer from 16 x 16 up).
+// on the way, so the style is multiplied into the WEIGHT tile once it has landed (one pass over Ws per chunk) -- legal because
+// all BN columns of a tile belong to one sample (tiles are dealt per sample; planes of at least BN pixels: every layer from
+// 16 x 16 up, including the (r+1)^2 polyphase planes of the transposed conv).
 __device__ __forceinline__ void cpa16(void *dst, const void *src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
 }
@@ -292,23 +293,30 @@ modconv_simt_pipe_kernel(float *__restrict__ out, const float *__restrict__ x, c
     }
     const int tx = tid % CFG::TN, ty = tid / CFG::TN;
     const int co0 = blockIdx.y * BM;
-    const int64_t n0 = (int64_t)blockIdx.x * BN;
     const int P = g.PH * g.PW;
     const int64_t HW = (int64_t)g.H * g.W;
-    const int sb = (int)(n0 / P);                          // the tile's sample
-    const int p0 = (int)(n0 - (int64_t)sb * P);
+    // tiles never straddle samples: ceil(P / BN) tiles per sample, the last one partly empty (columns >= P are zero-filled
+    // and not stored) -- this is what lets the modulation sit on the weight tile
+    const int tps = (P + BN - 1) / BN;
+    const int sb = (int)blockIdx.x / tps;                  // the tile's sample
+    const int p0 = ((int)blockIdx.x - sb * tps) * BN;
     const float *xs = x + (int64_t)sb * g.Cin * HW;
     const float *sty = style ? style + (int64_t)sb * g.Cin : nullptr;
 
     // staging role: CPT columns of Xs per thread, channels cs, cs + CS, ... of the chunk
     const int cs = CS > 1 ? tid / BN : 0;
     int iy_base[CPT], ix_base[CPT];
+    bool col_ok[CPT];
 #pragma unroll
     for (int j = 0; j < CPT; ++j) {
         const int r = p0 + (tid % BN) + j * 256;
+        col_ok[j] = r < P;
         const int soy = r / g.PW, sox = r - soy * g.PW;
         iy_base[j] = soy * g.in_sy; ix_base[j] = sox * g.in_sx;
     }
+    float *s_sty = big_smem + 2 * BUF;     // the tile's style vector (one sample per tile), staged once
+    if (sty)
+        for (int i = tid; i < g.Cin; i += 256) s_sty[i] = __ldg(sty + i);
     __syncthreads();                       // tables
 
     auto issue = [&](int ci0, int buf) {
@@ -325,7 +333,7 @@ modconv_simt_pipe_kernel(float *__restrict__ out, const float *__restrict__ x, c
             const int col = (tid % BN) + j * 256;
             for (int t = 0; t < ntaps; ++t) {
                 const int iy = iy_base[j] + s_dy[t], ix = ix_base[j] + s_dx[t];
-                const bool ok = iy >= 0 && ix >= 0 && iy < g.H && ix < g.W;
+                const bool ok = col_ok[j] && iy >= 0 && ix >= 0 && iy < g.H && ix < g.W;
                 const float *src = xs + ((int64_t)ci0 * g.H + (ok ? iy : 0)) * g.W + (ok ? ix : 0);
 #pragma unroll
                 for (int c = cs; c < KC; c += CS) cpa4_zfill(&Xs[c * ntaps + t][col], src + c * HW, ok);
@@ -356,7 +364,7 @@ modconv_simt_pipe_kernel(float *__restrict__ out, const float *__restrict__ x, c
         if (sty) {                                         // modulation, applied to the weight rows of this chunk
             for (int i = tid; i < nk * (BM / 4); i += 256) {
                 const int kk = i / (BM / 4), c4 = (i - kk * (BM / 4)) * 4;
-                const float sv = __ldg(sty + c * KC + s_kcil[kk]);
+                const float sv = s_sty[c * KC + s_kcil[kk]];
                 float4 w4 = *reinterpret_cast<float4 *>(&Ws[kk][c4]);
                 w4.x *= sv; w4.y *= sv; w4.z *= sv; w4.w *= sv;
                 *reinterpret_cast<float4 *>(&Ws[kk][c4]) = w4;
@@ -382,6 +390,7 @@ modconv_simt_pipe_kernel(float *__restrict__ out, const float *__restrict__ x, c
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const int r = p0 + (j < 4 ? tx * 4 + j : BN / 2 + tx * 4 + (j - 4));
+        if (r >= P) continue;
         const int ly = r / g.PW, lx = r - ly * g.PW;
         const int oy = ly * g.out_sy + g.out_oy, ox = lx * g.out_sx + g.out_ox;
 #pragma unroll
@@ -397,13 +406,17 @@ modconv_simt_pipe_kernel(float *__restrict__ out, const float *__restrict__ x, c
 template <typename CFG>
 static int launch_pipe(float *out, const float *x, const float *wt, const float *style, const float *demod, const ConvGeo &g,
                        int64_t Ntot, cudaStream_t st) {
-    constexpr size_t smem = 2 * CFG::smem;
+    constexpr int kMaxCin = 2048;                                    // style vector staged in shared memory
+    if (g.Cin > kMaxCin) return 1;
+    const size_t smem = 2 * CFG::smem + (size_t)g.Cin * sizeof(float);
     static std::atomic<int> configured{0};
     if (!configured.load(std::memory_order_acquire)) {
-        SG2_CUDA_OK(cudaFuncSetAttribute(modconv_simt_pipe_kernel<CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SG2_CUDA_OK(cudaFuncSetAttribute(modconv_simt_pipe_kernel<CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(2 * CFG::smem + kMaxCin * sizeof(float))));
         configured.store(1, std::memory_order_release);
     }
-    dim3 grid((unsigned)(Ntot / CFG::BN), g.Cout / CFG::BM);
+    const int P = g.PH * g.PW;
+    dim3 grid((unsigned)(g.B * ((P + CFG::BN - 1) / CFG::BN)), g.Cout / CFG::BM);
     modconv_simt_pipe_kernel<CFG><<<grid, 256, smem, st>>>(out, x, wt, style, demod, g);
     SG2_LAUNCH_CHECK();
     return SG2_OK;
@@ -486,8 +499,8 @@ extern "C" int sg2_modconv2d_fwd(void *out, const void *x, const float *wt, cons
         if (big_ok && (!env_pipe || atoi(env_pipe) != 0) && dtype == SG2_F32 && (reinterpret_cast<uintptr_t>(wt) & 15) == 0 &&
             Cin % 4 == 0) {
             int rc = 1;
-            if (Cout % 128 == 0 && P % 128 == 0) rc = launch_pipe<BigTile<128, 128, 4>>((float *)out, (const float *)x, wt, style, demod, g, Ntot, st);
-            else if (Cout % 64 == 0 && Cout < 128 && P % 256 == 0) rc = launch_pipe<BigTile<64, 256, 4>>((float *)out, (const float *)x, wt, style, demod, g, Ntot, st);
+            if (Cout % 128 == 0 && P >= 128) rc = launch_pipe<BigTile<128, 128, 4>>((float *)out, (const float *)x, wt, style, demod, g, Ntot, st);
+            else if (Cout % 64 == 0 && Cout < 128 && P >= 256) rc = launch_pipe<BigTile<64, 256, 4>>((float *)out, (const float *)x, wt, style, demod, g, Ntot, st);
             if (rc < 0 || rc > 1) return rc;
             if (rc == 0) continue;
         }
