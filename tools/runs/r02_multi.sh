@@ -8,5 +8,5 @@ echo "finetune N=$N rc=$?"; cat gpurun_out/r02m/finetune_n$N.json; grep -v Warni
 timeout 900 $TR --master-port 29512 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/r02m/bench_n$N.json 2> gpurun_out/r02m/bench_n$N.err
 echo "bench N=$N rc=$?"; python -c "
 import json
-d=json.load(open('gpurun_out/r02m/bench_n$N.json')); print(d['n_gpus'], d['value'], d['ms_per_step'], d['e2e']['value'], d['ranks'], d['configs']['1024_b32']['value'], d['configs']['1024_b32']['ranks'])"
+d=json.loads([l for l in open('gpurun_out/r02m/bench_n$N.json') if l.startswith('{')][-1]); print(d['n_gpus'], d['value'], d['ms_per_step'], d['e2e']['value'], d['ranks'], d['configs']['1024_b32']['value'], d['configs']['1024_b32']['ranks'])"
 grep -v Warning gpurun_out/r02m/bench_n$N.err | tail -3
