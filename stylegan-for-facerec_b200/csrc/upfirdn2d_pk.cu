@@ -1,0 +1,467 @@
+// upfirdn2d_pk.cu -- upfirdn2d for 2-BYTE storage (bf16 / fp16, NCHW planes, minor == 1, <= 4x4 taps), blur (up 1 / down 1)
+// and down-sampling (up 1 / down 2), on packed fp32 math.
+//
+// Same definition as upfirdn2d_kernel (op/upfirdn2d_kernel.cu:52-137 of the reference: pad / crop, correlation with the
+// flipped taps, decimation), fp32 accumulation, taps applied per output in the reference's order (tap rows ascending,
+// columns inside), every multiply-add an IEEE fused multiply-add: results are those of upfirdn2d_stream.cu bit for bit.
+//
+// Why a second kernel.  In 2-byte storage the blur moves 4 bytes per output and spends 16 multiply-adds on it: at the
+// HBM roofline (6.55 TB/s measured) that is 26e12 FMA/s, 85 % of what the FP32 pipe delivers (tools/probes/ffma_probe.cu:
+// 31e12 FMA/s with three register operands, the same through fma.rn.f32x2).  The row-streaming kernel issued 34
+// instructions per output (scalar FFMA + scalar 2-byte loads + fp32 staging) and stopped at 0.46 (blur) / 0.34 (down-2)
+// of the roofline, issue-bound.  Here
+//   * the multiply-adds are fma.rn.f32x2 over pairs of adjacent outputs (SASS FFMA2 with the tap as a broadcast scalar
+//     operand): 8 issue slots per output instead of 16, which leaves room for everything else beside a busy FMA pipe;
+//   * rows travel HBM -> shared memory as aligned 16-byte cp.async chunks, whatever the row pitch (a 257-wide bf16 row is
+//     514 bytes: no TMA tile, no vector load can start on it): the chunk grid is anchored at the 16-byte boundary below
+//     the row segment, so the segment starts q = 0..7 elements into its first chunk; q is warp-uniform, advances by
+//     in_w mod 8 per row, and a switch on it picks one of eight fully unrolled unpack sequences (register renaming, no
+//     shifts): two 16-byte shared loads + 20 conversions per lane and row, no staging stores at all;
+//   * copies run PK_D - 1 rows ahead per warp and the prefetch cursor walks across work items, so a warp that finishes a
+//     band already has the first rows of its next one in flight;
+//   * zero padding: rows outside the plane are zero-filled by the copy itself (src-size 0), columns outside the plane
+//     are zeroed in shared memory by the one or two lanes that own them; over-reads never leave the tensor (chunks
+//     that would are clamped / zero-filled -- the last 2..14 bytes of a tensor included).
+//
+// Work split: a group of WL = 4..32 lanes owns a strip of WL * TX output columns (TX = 8 blur, 4 down-2: 8 input
+// elements = one chunk per lane and row either way) and walks down a band of rh rows; the 32 / WL groups of a warp take
+// consecutive bands of the SAME plane and strip, rh a multiple of 8, so that every group sees the same q.
+#include <stdlib.h>
+
+#include <algorithm>
+#include <type_traits>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace sg2 {
+
+using namespace tc;
+
+#ifndef PK_KO
+#define PK_KO 0                  // knock-out bits for bottleneck analysis (variant builds only; results are WRONG when set):
+#endif                           // 1 no FMAs, 2 no global stores, 4 no global -> shared copies, 8 unpack case 0 only
+constexpr int PK_WARPS = 4;      // small CTAs: five of them fit the register file (<= 96 registers per thread) = 20 warps per SM
+constexpr int PK_THREADS = 32 * PK_WARPS;
+constexpr int PK_CTAS = 5;
+constexpr int PK_D = 10;         // ring slots per warp: PK_D - 1 rows in flight, PK_D - 3 of them beyond the row being fixed up
+
+struct UfdPkParams {
+    int in_h, in_w, out_h, out_w;
+    int pad_x0, pad_y0, kh, kw;
+    int rh;                   // output rows per band, multiple of 8
+    int n_strips, n_sbands;   // super-band = the 32 / WL bands one warp walks side by side
+    long long planes, items;  // items = planes * n_sbands * n_strips (strip fastest)
+    unsigned long long xb, xe;   // first byte of the input tensor (16-byte aligned) / one past its last byte
+    int vec_store;
+};
+
+// One conversion per pair half, written straight into the half of the 64-bit register pair the packed FMA reads.  An
+// element that sits in two pairs is converted twice, by two DIFFERENT instructions (V = 0 / 1): ptxas merges identical
+// conversions and then MOVES the value into its second pair, and both its moves and its shift-as-IMAD issue on the FMA
+// pipe, the one this kernel saturates; PRMT / LOP3 run on the ALU pipe.  (fp16: cvt either way, HADD2.F32.)
+template <typename T, int V> __device__ __forceinline__ float pk_lo(uint32_t w) {
+    float f;
+    if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+        if constexpr (V == 0) asm volatile("prmt.b32 %0, %1, 0, 0x1044;" : "=f"(f) : "r"(w));    // bytes {0, 0, w.b0, w.b1} = w << 16
+        else asm volatile("prmt.b32 %0, 0, %1, 0x5400;" : "=f"(f) : "r"(w));
+    } else {
+        asm volatile("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %1;\n\tcvt.f32.f16 %0, l;\n\t}" : "=f"(f) : "r"(w));
+    }
+    return f;
+}
+template <typename T, int V> __device__ __forceinline__ float pk_hi(uint32_t w) {
+    float f;
+    if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+        if constexpr (V == 0) asm volatile("and.b32 %0, %1, 0xffff0000;" : "=f"(f) : "r"(w));
+        else asm volatile("prmt.b32 %0, %1, 0, 0x3244;" : "=f"(f) : "r"(w));                      // bytes {0, 0, w.b2, w.b3}
+    } else {
+        asm volatile("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %1;\n\tcvt.f32.f16 %0, h;\n\t}" : "=f"(f) : "r"(w));
+    }
+    return f;
+}
+
+// element e (static after unrolling) of the lane's three chunks
+template <typename T, int V>
+__device__ __forceinline__ float pk_elem(const uint32_t (&c)[9], int e) {
+    return (e & 1) ? pk_hi<T, V>(c[e >> 1]) : pk_lo<T, V>(c[e >> 1]);
+}
+
+// NP pairs (window[j], window[j + STEP]) for a window that starts Q elements into the chunks; EVEN / ODD starts
+// blur: E[n] = (w[2n], w[2n+1]), O[n] = (w[2n+1], w[2n+2]); down-2: D[j] = (w[j], w[j+2])
+template <typename T, int DOWN, int Q>
+__device__ __forceinline__ void pk_unpack(const uint32_t (&c)[9], float2 (&P)[DOWN == 1 ? 10 : 8]) {
+    if constexpr (DOWN == 1) {
+#pragma unroll
+        for (int n = 0; n < 5; ++n) {
+            P[n] = make_float2(pk_elem<T, 0>(c, Q + 2 * n), pk_elem<T, 0>(c, Q + 2 * n + 1));
+            P[5 + n] = make_float2(pk_elem<T, 1>(c, Q + 2 * n + 1), pk_elem<T, 1>(c, Q + 2 * n + 2));
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) P[j] = make_float2(pk_elem<T, 0>(c, Q + j), pk_elem<T, 1>(c, Q + j + 2));
+    }
+}
+
+__device__ __forceinline__ void pk_cp16(uint32_t dst, unsigned long long src, int bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void pk_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void pk_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ uint32_t pk_lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void pk_sts16_zero(uint32_t addr) {
+    asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"((unsigned short)0) : "memory");
+}
+
+// predicated forms (no branch around a single instruction)
+__device__ __forceinline__ void pk_cp16_if(uint32_t dst, unsigned long long src, bool on) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p cp.async.cg.shared.global [%0], [%1], 16;\n\t}" ::"r"(dst), "l"(src), "r"((int)on) : "memory");
+}
+__device__ __forceinline__ void pk_sts128_zero_if(uint32_t addr, bool on) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %1, 0;\n\t@p st.shared.v4.b32 [%0], {%2, %2, %2, %2};\n\t}" ::"r"(addr), "r"((int)on), "r"(0) : "memory");
+}
+__device__ __forceinline__ void pk_sts16_zero_if(uint32_t addr, bool on) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %1, 0;\n\t@p st.shared.b16 [%0], %2;\n\t}" ::"r"(addr), "r"((int)on), "h"((unsigned short)0) : "memory");
+}
+
+template <typename T>
+__device__ __forceinline__ uint32_t pk_pack2(float2 v) {
+    if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(v.x, v.y);
+        return *reinterpret_cast<const uint32_t *>(&h);
+    } else {
+        const __half2 h = __floats2half2_rn(v.x, v.y);
+        return *reinterpret_cast<const uint32_t *>(&h);
+    }
+}
+// one finished row of N outputs per lane: a predicated vector store when the whole row of the lane is valid and aligned
+// (vec), element by element otherwise (n_ok of them: right edge of the plane, unaligned rows -- a rarely taken branch)
+template <typename T, int N>
+__device__ __forceinline__ void pk_store_row(T *dst, const float2 (&v)[N / 2], bool vec, int n_ok) {
+    uint32_t pk[N / 2];
+#pragma unroll
+    for (int i = 0; i < N / 2; ++i) pk[i] = pk_pack2<T>(v[i]);
+    if constexpr (N == 8)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\t@p st.global.v4.b32 [%0], {%1, %2, %3, %4};\n\t}" ::"l"(dst), "r"(pk[0]), "r"(pk[1]),
+                     "r"(pk[2]), "r"(pk[3]), "r"((int)vec) : "memory");
+    else
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %3, 0;\n\t@p st.global.v2.b32 [%0], {%1, %2};\n\t}" ::"l"(dst), "r"(pk[0]), "r"(pk[1]), "r"((int)vec)
+                     : "memory");
+    if (n_ok > 0) {
+#pragma unroll
+        for (int i = 0; i < N / 2; ++i) {
+            if (2 * i < n_ok) dst[2 * i] = Cvt<T>::from_f(v[i].x);
+            if (2 * i + 1 < n_ok) dst[2 * i + 1] = Cvt<T>::from_f(v[i].y);
+        }
+    }
+}
+
+// WLOG2: lanes per group (log2, >= 3).  TX outputs per lane; every lane consumes 8 input elements (one chunk) per row.
+template <typename T, int DOWN, int WLOG2>
+__global__ void __launch_bounds__(PK_THREADS, PK_CTAS)
+upfirdn2d_pk_kernel(T *__restrict__ out, const float *__restrict__ taps, const UfdPkParams p) {
+    constexpr int TX = DOWN == 1 ? 8 : 4;
+    constexpr int WU = DOWN == 1 ? 11 : 10;                        // window elements a lane uses
+    constexpr int WL = 1 << WLOG2, NS = 32 >> WLOG2;
+    constexpr int GB = (WL + 2) * 16;                              // bytes of one group's staged row: WL + 2 chunks
+    constexpr int SLOT = NS * GB;
+    constexpr int NP = DOWN == 1 ? 10 : 8;
+    constexpr int R = DOWN == 1 ? 4 : 2;                           // output rows in flight
+    extern __shared__ __align__(16) unsigned char pk_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> WLOG2, t = lane & (WL - 1);
+    const uint32_t ring = smem_u32(pk_smem) + (uint32_t)warp * (PK_D * SLOT) + (uint32_t)g * GB;   // this group's part of slot 0
+    const uint32_t ring_end = ring + PK_D * SLOT;
+
+    // flipped taps, zero padded to 4 x 4: kf[a][b] multiplies the sample a rows / b columns after the window's first
+    float kf[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+            kf[a][b] = (a < p.kh && b < p.kw) ? __ldg(taps + (p.kh - 1 - a) * p.kw + (p.kw - 1 - b)) : 0.f;
+
+    const long long stride = (long long)gridDim.x * PK_WARPS;
+    const long long item0 = (long long)blockIdx.x * PK_WARPS + warp;
+    const unsigned long long pitch = 2ull * (unsigned long long)p.in_w;
+
+    // item -> first output row of this lane's band, strip origin, first input row; steps = input rows the band needs
+    // (warp-uniform: taken from group 0), walked in multiples of four (the tail rows are staged as zeros and feed
+    // output rows that are never stored)
+    struct Item { long long plane; int y0, xs0, iy0, cx0, need, nsteps; };
+    auto decode = [&](long long item) {
+        Item it;
+        const int strip = (int)(item % p.n_strips);
+        const long long rest = item / p.n_strips;
+        const int sband = (int)(rest % p.n_sbands);
+        it.plane = rest / p.n_sbands;
+        const int y00 = sband * NS * p.rh;                         // group 0
+        it.y0 = y00 + g * p.rh;
+        it.xs0 = strip * (WL * TX);
+        it.iy0 = DOWN * it.y0 - p.pad_y0;
+        it.cx0 = DOWN * it.xs0 - p.pad_x0;
+        it.need = DOWN * (min(p.rh, p.out_h - y00) - 1) + 4;
+        it.nsteps = (it.need + 3) & ~3;
+        return it;
+    };
+
+    // ---- prefetch cursor: (item, step) PK_D - 1 rows ahead of the consumer, across items ----
+    long long pf_item = item0;
+    bool pf_live = pf_item < p.items, pf_safe = false;
+    int pf_left = 0, pf_tail = 0, pf_iy = 0;                       // rows left in the item (the last pf_tail are zeros), input row
+    uint32_t pf_dst = ring + 16u * t;                              // this lane's chunk of the slot the next row goes to
+    unsigned long long pf_a = 0;                                   // byte address of (row pf_iy, column cx0) of this group, + 16 t
+    auto pf_open = [&]() {
+        const Item it = decode(pf_item);
+        pf_left = it.nsteps; pf_tail = it.nsteps - it.need; pf_iy = it.iy0;
+        const unsigned long long a0 = p.xb + 2ull * (unsigned long long)((it.plane * p.in_h + it.iy0) * (long long)p.in_w + it.cx0);
+        const unsigned long long first = a0 & ~15ull, last = (a0 + (unsigned long long)(it.need - 1) * pitch) & ~15ull;
+        pf_safe = first >= p.xb && last + GB <= p.xe;             // every chunk of every row of the band lies inside the tensor
+        pf_a = a0 + 16ull * t;
+    };
+    if (pf_live) pf_open();
+    auto pf_issue = [&]() {
+        const bool row_ok = (unsigned)pf_iy < (unsigned)p.in_h && pf_left > pf_tail;
+        const unsigned long long src = pf_a & ~15ull;              // chunk t of the row (16 t is folded into pf_a)
+        const bool fast = pf_live && pf_safe;
+        // rows outside the plane (and the tail rows): zeros written by the lane itself
+        pk_cp16_if(pf_dst, src, fast && row_ok && !(PK_KO & 4));
+        pk_sts128_zero_if(pf_dst, fast && !row_ok);
+        pk_cp16_if(pf_dst + 16u * WL, src + 16ull * WL, fast && row_ok && t < 2 && !(PK_KO & 4));
+        pk_sts128_zero_if(pf_dst + 16u * WL, fast && !row_ok && t < 2);
+        if (pf_live && !pf_safe) {                                 // first / last band of the tensor: clamp every chunk
+            auto copy = [&](uint32_t dst, unsigned long long ca) {
+                const long long rem = (long long)(p.xe - ca);
+                const int bytes = (!row_ok || ca < p.xb || rem <= 0) ? 0 : (rem < 16 ? (int)rem : 16);
+                pk_cp16(dst, bytes ? ca : p.xb, bytes);
+            };
+            copy(pf_dst, src);
+            if (t < 2) copy(pf_dst + 16u * WL, src + 16ull * WL);
+        }
+        pk_commit();
+        pf_a += pitch; ++pf_iy;
+        pf_dst += SLOT;
+        if (pf_dst >= ring_end) pf_dst -= PK_D * SLOT;
+        if (--pf_left == 0 && pf_live) {
+            pf_item += stride;
+            pf_live = pf_item < p.items;
+            if (pf_live) pf_open();
+        }
+    };
+#pragma unroll 1
+    for (int d = 0; d < PK_D - 1; ++d) pf_issue();
+    pk_wait<PK_D - 2>();                                           // the very first row (every later one: see the step's wait)
+    __syncwarp();
+
+    uint32_t line = ring;                                          // this group's part of the slot the consumer reads next
+    for (long long item = item0; item < p.items; item += stride) {
+        const Item it = decode(item);
+        const int nrows = max(0, min(p.rh, p.out_h - it.y0));
+        const int x0 = it.xs0 + TX * t;
+        const int n_out = nrows > 0 ? max(0, min(TX, p.out_w - x0)) : 0;
+        const bool vec_ok = p.vec_store != 0 && n_out == TX;
+        const int n_part = vec_ok ? 0 : n_out;                     // outputs of a row stored element by element
+        // row the first store step points at (blur: s = 0 -> row -3, down-2: s = 1 -> row -1; never dereferenced)
+        T *orow = out + (it.plane * p.out_h + it.y0 - (DOWN == 1 ? 3 : 1)) * (long long)p.out_w + x0;
+        // alignment of the row segment inside its first chunk, in elements (the same for every group of the warp)
+        int q = (int)((p.xb + 2ull * (unsigned long long)((it.plane * p.in_h + it.iy0) * (long long)p.in_w + it.cx0)) >> 1) & 7;
+        // zero padding left / right of the plane: the staged positions that lie outside the plane AND inside the window of a
+        // lane that has outputs -- at most 3 on the left, 12 on the right (host check) -- are zeroed in shared memory once
+        // the row has landed (one step ahead of its use), position j of that list by lane j % WL of the group
+        const int t_last = (min(WL * TX, p.out_w - it.xs0) - 1) / TX;              // last lane with outputs
+        const int n_left = max(0, -it.cx0), pos_r = max(n_left, p.in_w - it.cx0);
+        const int n_right = max(0, 8 * t_last + WU - pos_r);
+        int fix0 = -1, fix1 = -1;                                  // byte offsets of this lane's positions
+        if (t < n_left) fix0 = 2 * t;
+        else if (t - n_left < n_right) fix0 = 2 * (pos_r + t - n_left);
+        if (t + WL - n_left < n_right) fix1 = 2 * (pos_r + t + WL - n_left);       // WL >= 8 > n_left
+        // row 0 of the item has landed and is visible (the previous step waited for it); the stores become visible to
+        // the other lanes at the first step's barrier
+        pk_sts16_zero_if(line + (uint32_t)(2 * q + fix0), fix0 >= 0);
+        pk_sts16_zero_if(line + (uint32_t)(2 * q + fix1), fix1 >= 0);
+
+        float2 acc[R][TX / 2];
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int i = 0; i < TX / 2; ++i) acc[r][i] = make_float2(0.f, 0.f);
+
+        for (int sb = 0; sb < it.nsteps; sb += 4) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int s = sb + u;
+                pk_wait<PK_D - 3>();                               // this lane's copies of rows <= s + 1 have landed
+                __syncwarp();                                      // ... and everybody's; row s is fixed up; every lane is done with row s - 1
+                uint32_t line_next = line + SLOT;
+                if (line_next >= ring_end) line_next -= PK_D * SLOT;
+                const int q_next = (q + p.in_w) & 7;
+                {   // fix up row s + 1 (unless it belongs to the next item, which does it itself)
+                    const bool mine = u < 3 || sb + 4 < it.nsteps;
+                    pk_sts16_zero_if(line_next + (uint32_t)(2 * q_next + fix0), mine && fix0 >= 0);
+                    pk_sts16_zero_if(line_next + (uint32_t)(2 * q_next + fix1), mine && fix1 >= 0);
+                }
+                pf_issue();                                        // refill the slot of row s - 1
+                uint32_t c[9];
+                {
+                    const uint4 c0 = lds128(line + 16u * t), c1 = lds128(line + 16u * t + 16u);
+                    c[0] = c0.x; c[1] = c0.y; c[2] = c0.z; c[3] = c0.w;
+                    c[4] = c1.x; c[5] = c1.y; c[6] = c1.z; c[7] = c1.w;
+                    c[8] = q + WU > 16 ? pk_lds32(line + 16u * t + 32u) : 0u;
+                }
+                float2 P[NP];
+                switch ((PK_KO & 8) ? 0 : q) {
+                    case 0: pk_unpack<T, DOWN, 0>(c, P); break;
+                    case 1: pk_unpack<T, DOWN, 1>(c, P); break;
+                    case 2: pk_unpack<T, DOWN, 2>(c, P); break;
+                    case 3: pk_unpack<T, DOWN, 3>(c, P); break;
+                    case 4: pk_unpack<T, DOWN, 4>(c, P); break;
+                    case 5: pk_unpack<T, DOWN, 5>(c, P); break;
+                    case 6: pk_unpack<T, DOWN, 6>(c, P); break;
+                    default: pk_unpack<T, DOWN, 7>(c, P); break;
+                }
+                q = q_next;
+                line = line_next;
+
+                if constexpr (DOWN == 1) {
+                    // input row s is tap row a of output row s - a (ring slot (u - a) & 3); output pair ip = columns
+                    // (2 ip, 2 ip + 1) takes the window pair that starts at 2 ip + b: E[ip + b/2] or O[ip + (b-1)/2]
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) {
+                        const int r = (u - a + 4) & 3;
+#pragma unroll
+                        for (int ip = 0; ip < 4; ++ip) {
+                            float2 v = a == 0 ? make_float2(0.f, 0.f) : acc[r][ip];
+#pragma unroll
+                            for (int b = 0; b < 4; ++b) {
+                                if ((PK_KO & 1) && (a | b)) continue;
+                                v = __ffma2_rn((b & 1) ? P[5 + ip + (b >> 1)] : P[ip + (b >> 1)], make_float2(kf[a][b], kf[a][b]), v);
+                            }
+                            acc[r][ip] = v;
+                        }
+                    }
+                    // finished: output row y0 + s - 3
+                    const bool in_band = (unsigned)(s - 3) < (unsigned)nrows;
+                    pk_store_row<T, 8>(orow, acc[(u + 1) & 3], in_band && vec_ok && !(PK_KO & 2), in_band && !(PK_KO & 2) ? n_part : 0);
+                    orow += p.out_w;
+                } else {
+                    // input row s is tap row a = (s & 1), (s & 1) + 2 of output row (s - a) / 2; output pair ip = columns
+                    // (2 ip, 2 ip + 1) takes (w[4 ip + b], w[4 ip + b + 2]) = D[4 ip + b]
+                    const int e = u & 1;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int a = e + 2 * h;
+                        const int r = (((u - a) / 2) + 2) & 1;     // (s - a) / 2 mod 2, sb a multiple of 4
+#pragma unroll
+                        for (int ip = 0; ip < 2; ++ip) {
+                            float2 v = a == 0 ? make_float2(0.f, 0.f) : acc[r][ip];
+#pragma unroll
+                            for (int b = 0; b < 4; ++b) {
+                                if ((PK_KO & 1) && (a | b)) continue;
+                                v = __ffma2_rn(P[4 * ip + b], make_float2(kf[a][b], kf[a][b]), v);
+                            }
+                            acc[r][ip] = v;
+                        }
+                    }
+                    if (e == 1) {                                  // tap row 3 done: output row (s - 3) / 2 is finished
+                        const bool in_band = (unsigned)((s - 3) >> 1) < (unsigned)nrows;   // s = 1: -1 -> out of range
+                        pk_store_row<T, 4>(orow, acc[(((u - 3) / 2) + 2) & 1], in_band && vec_ok && !(PK_KO & 2), in_band && !(PK_KO & 2) ? n_part : 0);
+                        orow += p.out_w;
+                    }
+                }
+            }
+        }
+    }
+    pk_wait<0>();
+}
+
+// ---- host ------------------------------------------------------------------------------------------
+static bool pk_debug() {
+    static const char *e = getenv("SG2_US_DEBUG");
+    return e && atoi(e);
+}
+
+template <typename T, int DOWN, int WLOG2>
+static int pk_launch_t(void *out, const float *taps, const UfdPkParams &p, int grid, cudaStream_t st) {
+    constexpr int WL = 1 << WLOG2, NS = 32 >> WLOG2;
+    constexpr size_t smem = (size_t)PK_WARPS * PK_D * NS * (WL + 2) * 16;
+    static bool attr_done = false;                                  // > 48 KiB never happens (NS = 8: exactly 48 KiB), kept for safety
+    if (smem > 48 * 1024 && !attr_done) {
+        SG2_CUDA_OK(cudaFuncSetAttribute(upfirdn2d_pk_kernel<T, DOWN, WLOG2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    upfirdn2d_pk_kernel<T, DOWN, WLOG2><<<grid, PK_THREADS, smem, st>>>((T *)out, taps, p);
+    SG2_LAUNCH_CHECK();
+    return SG2_OK;
+}
+
+// Returns SG2_OK when the launch was made, 1 when this path does not apply (the caller goes on to the row-streaming
+// kernel), another status on errors.
+template <typename T>
+int launch_upfirdn2d_pk(void *out, const void *x, const float *taps, int64_t planes, int in_h, int in_w, int out_h, int out_w,
+                        int kh, int kw, int up, int down, int pad_x0, int pad_y0, cudaStream_t st) {
+    if constexpr (sizeof(T) != 2) {
+        return 1;
+    } else {
+        if (up != 1 || (down != 1 && down != 2) || kh > 4 || kw > 4) return 1;
+        if (reinterpret_cast<uintptr_t>(x) % 16 != 0) return 1;
+        const int TX = down == 1 ? 8 : 4, WU = down == 1 ? 11 : 10;
+        if (out_w <= 4 * TX || out_h < 8 || pad_x0 > 3) return 1;     // small planes: upfirdn2d_planes.cu / the streaming kernel
+        int wl = 3;
+        while ((TX << wl) < out_w && wl < 5) ++wl;
+        const int WL = 1 << wl, NS = 32 >> wl;
+        // the kernel zeroes at most 3 + 12 staged positions per row and group (see there): every strip must fit
+        for (int xs0 = 0; xs0 < out_w; xs0 += WL * TX) {
+            const int cx0 = down * xs0 - pad_x0, t_last = (std::min(WL * TX, out_w - xs0) - 1) / TX;
+            const int n_left = std::max(0, -cx0), pos_r = std::max(n_left, in_w - cx0);
+            if (n_left > 3 || 8 * t_last + WU - pos_r > 12) return 1;
+        }
+        UfdPkParams p;
+        p.in_h = in_h; p.in_w = in_w; p.out_h = out_h; p.out_w = out_w;
+        p.pad_x0 = pad_x0; p.pad_y0 = pad_y0; p.kh = kh; p.kw = kw;
+        p.planes = planes;
+        p.n_strips = (out_w + TX * WL - 1) / (TX * WL);
+        // band height (multiple of 8): one super-band per plane if that still gives every resident warp ~4 items,
+        // otherwise shorter bands, down to 16 rows (8 when the groups of a warp already split the plane)
+        const int sms = sm_count();
+        const int64_t want_items = (int64_t)sms * PK_CTAS * PK_WARPS * 4;
+        auto up8 = [](int v) { return (v + 7) & ~7; };
+        int rh = up8((out_h + NS - 1) / NS);
+        const int rh_min = NS > 1 ? 8 : 16;
+        while (rh > rh_min && planes * p.n_strips * ((out_h + NS * rh - 1) / (NS * rh)) < want_items) rh = std::max(rh_min, up8(rh / 2));
+        p.rh = rh;
+        p.n_sbands = (out_h + NS * rh - 1) / (NS * rh);
+        p.items = planes * p.n_strips * p.n_sbands;
+        p.xb = reinterpret_cast<uintptr_t>(x);
+        p.xe = p.xb + 2ull * (unsigned long long)planes * in_h * in_w;
+        const int es = 2;
+        p.vec_store = (out_w % TX == 0 && reinterpret_cast<uintptr_t>(out) % (TX * es) == 0) ? 1 : 0;
+        const int64_t want = (p.items + PK_WARPS - 1) / PK_WARPS;
+        const int grid = (int)std::min<int64_t>(want, (int64_t)sms * PK_CTAS);
+        if (grid <= 0) return SG2_OK;
+        if (pk_debug())
+            fprintf(stderr, "[sg2 upfirdn2d_pk] down %d, %lld planes %dx%d -> %dx%d, %d lanes per strip, bands of %d rows, %d super-bands, "
+                            "%lld items, grid %d\n", down, (long long)planes, in_h, in_w, out_h, out_w, WL, p.rh, p.n_sbands, p.items, grid);
+#define SG2_PK_CASE(D, W) case W: return pk_launch_t<T, D, W>(out, taps, p, grid, st);
+        if (down == 1) {
+            switch (wl) { SG2_PK_CASE(1, 3) SG2_PK_CASE(1, 4) SG2_PK_CASE(1, 5) }
+        } else {
+            switch (wl) { SG2_PK_CASE(2, 3) SG2_PK_CASE(2, 4) SG2_PK_CASE(2, 5) }
+        }
+#undef SG2_PK_CASE
+        return 1;
+    }
+}
+
+template int launch_upfirdn2d_pk<float>(void *, const void *, const float *, int64_t, int, int, int, int, int, int, int, int, int, int,
+                                        cudaStream_t);
+template int launch_upfirdn2d_pk<__half>(void *, const void *, const float *, int64_t, int, int, int, int, int, int, int, int, int, int,
+                                         cudaStream_t);
+template int launch_upfirdn2d_pk<__nv_bfloat16>(void *, const void *, const float *, int64_t, int, int, int, int, int, int, int, int,
+                                                int, int, cudaStream_t);
+
+}  // namespace sg2
