@@ -44,7 +44,7 @@ using namespace tc;
 constexpr int PK_WARPS = 4;      // small CTAs: five of them fit the register file (<= 96 registers per thread) = 20 warps per SM
 constexpr int PK_THREADS = 32 * PK_WARPS;
 constexpr int PK_CTAS = 5;
-constexpr int PK_D = 10;         // ring slots per warp: PK_D - 1 rows in flight, PK_D - 3 of them beyond the row being fixed up
+
 
 struct UfdPkParams {
     int in_h, in_w, out_h, out_w;
@@ -161,8 +161,16 @@ __device__ __forceinline__ void pk_store_row(T *dst, const float2 (&v)[N / 2], b
     }
 }
 
+// QS: how the alignment q of a row is known.
+//   -1      read per row, eight-way switch (any geometry); batches of 4 rows
+//   0 .. 7  the same constant for every row of the launch (in_w a multiple of 8: the 2^k-wide down-sampling inputs)
+//   8       q = position of the row in a batch of 8 (in_w = 1 mod 8: the 2^k + 1 wide blur inputs; the first batch of a
+//           band starts q0 slots in, so that the row with alignment q sits at position q)
+// In the static modes the unpack code is straight-line and the compiler interleaves it with the FMAs.
+template <int QS> struct PkMode { static constexpr int BATCH = QS == 8 ? 8 : 4, RB = QS == 8 ? 2 : 3; };
+
 // WLOG2: lanes per group (log2, >= 3).  TX outputs per lane; every lane consumes 8 input elements (one chunk) per row.
-template <typename T, int DOWN, int WLOG2>
+template <typename T, int DOWN, int WLOG2, int QS>
 __global__ void __launch_bounds__(PK_THREADS, PK_CTAS)
 upfirdn2d_pk_kernel(T *__restrict__ out, const float *__restrict__ taps, const UfdPkParams p) {
     constexpr int TX = DOWN == 1 ? 8 : 4;
@@ -172,11 +180,13 @@ upfirdn2d_pk_kernel(T *__restrict__ out, const float *__restrict__ taps, const U
     constexpr int SLOT = NS * GB;
     constexpr int NP = DOWN == 1 ? 10 : 8;
     constexpr int R = DOWN == 1 ? 4 : 2;                           // output rows in flight
+    constexpr int BATCH = PkMode<QS>::BATCH, RB = PkMode<QS>::RB;  // rows per barrier / prefetch round, rounds in the ring
+    constexpr int RING = RB * BATCH * SLOT;
     extern __shared__ __align__(16) unsigned char pk_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> WLOG2, t = lane & (WL - 1);
-    const uint32_t ring = smem_u32(pk_smem) + (uint32_t)warp * (PK_D * SLOT) + (uint32_t)g * GB;   // this group's part of slot 0
-    const uint32_t ring_end = ring + PK_D * SLOT;
+    uint32_t ring = smem_u32(pk_smem) + (uint32_t)warp * RING + (uint32_t)g * GB;   // this group's part of slot 0
+    asm volatile("" : "+r"(ring));                                 // keep it in a register (ptxas re-derives it from S2R otherwise)
 
     // flipped taps, zero padded to 4 x 4: kf[a][b] multiplies the sample a rows / b columns after the window's first
     float kf[4][4];
@@ -190,89 +200,103 @@ upfirdn2d_pk_kernel(T *__restrict__ out, const float *__restrict__ taps, const U
     const long long item0 = (long long)blockIdx.x * PK_WARPS + warp;
     const unsigned long long pitch = 2ull * (unsigned long long)p.in_w;
 
-    // item -> first output row of this lane's band, strip origin, first input row; steps = input rows the band needs
-    // (warp-uniform: taken from group 0), walked in multiples of four (the tail rows are staged as zeros and feed
-    // output rows that are never stored)
-    struct Item { long long plane; int y0, xs0, iy0, cx0, need, nsteps; };
+    // item -> first output row of this lane's band, strip origin, first input row; need = input rows the bands of the
+    // warp walk (warp-uniform: group 0 has the tallest band); the walk covers steps s = -u0 .. in whole batches, steps
+    // outside [0, need) are skipped (u0 = alignment of the band's first row in mode 8, else 0)
+    struct Item { long long plane; int y0, xs0, iy0, cx0, need, u0; };
     auto decode = [&](long long item) {
         Item it;
         const int strip = (int)(item % p.n_strips);
         const long long rest = item / p.n_strips;
         const int sband = (int)(rest % p.n_sbands);
         it.plane = rest / p.n_sbands;
+        it.xs0 = strip * (WL * TX);
+        it.cx0 = DOWN * it.xs0 - p.pad_x0;
         const int y00 = sband * NS * p.rh;                         // group 0
         it.y0 = y00 + g * p.rh;
-        it.xs0 = strip * (WL * TX);
         it.iy0 = DOWN * it.y0 - p.pad_y0;
-        it.cx0 = DOWN * it.xs0 - p.pad_x0;
         it.need = DOWN * (min(p.rh, p.out_h - y00) - 1) + 4;
-        it.nsteps = (it.need + 3) & ~3;
+        it.u0 = 0;
+        if constexpr (QS == 8)   // alignment of the first row (the same for every group: rh is a multiple of 8)
+            it.u0 = (int)(((p.xb >> 1) + (unsigned long long)((it.plane * p.in_h + DOWN * y00 - p.pad_y0) * (long long)p.in_w + it.cx0)) & 7);
         return it;
     };
 
-    // ---- prefetch cursor: (item, step) PK_D - 1 rows ahead of the consumer, across items ----
+    // ---- prefetch cursor: whole batches, RB - 1 of them ahead of the consumer, across items ----
     long long pf_item = item0;
     bool pf_live = pf_item < p.items, pf_safe = false;
-    int pf_left = 0, pf_tail = 0, pf_iy = 0;                       // rows left in the item (the last pf_tail are zeros), input row
-    uint32_t pf_dst = ring + 16u * t;                              // this lane's chunk of the slot the next row goes to
+    int pf_s = 0, pf_need = 0, pf_iy = 0;                          // step / input row of the batch's first slot, steps of the item
+    uint32_t pf_off = 0;                                           // ring offset of the slot the next row goes to
     unsigned long long pf_a = 0;                                   // byte address of (row pf_iy, column cx0) of this group, + 16 t
     auto pf_open = [&]() {
         const Item it = decode(pf_item);
-        pf_left = it.nsteps; pf_tail = it.nsteps - it.need; pf_iy = it.iy0;
+        pf_s = -it.u0; pf_need = it.need; pf_iy = it.iy0 - it.u0;
         const unsigned long long a0 = p.xb + 2ull * (unsigned long long)((it.plane * p.in_h + it.iy0) * (long long)p.in_w + it.cx0);
         const unsigned long long first = a0 & ~15ull, last = (a0 + (unsigned long long)(it.need - 1) * pitch) & ~15ull;
-        pf_safe = first >= p.xb && last + GB <= p.xe;             // every chunk of every row of the band lies inside the tensor
-        pf_a = a0 + 16ull * t;
+        pf_safe = first >= p.xb && first <= last && last + GB <= p.xe;   // every chunk of every row of the band lies inside the tensor
+        pf_a = a0 - it.u0 * pitch + 16ull * t;
     };
     if (pf_live) pf_open();
-    auto pf_issue = [&]() {
-        const bool row_ok = (unsigned)pf_iy < (unsigned)p.in_h && pf_left > pf_tail;
-        const unsigned long long src = pf_a & ~15ull;              // chunk t of the row (16 t is folded into pf_a)
-        const bool fast = pf_live && pf_safe;
-        // rows outside the plane (and the tail rows): zeros written by the lane itself
-        pk_cp16_if(pf_dst, src, fast && row_ok && !(PK_KO & 4));
-        pk_sts128_zero_if(pf_dst, fast && !row_ok);
-        pk_cp16_if(pf_dst + 16u * WL, src + 16ull * WL, fast && row_ok && t < 2 && !(PK_KO & 4));
-        pk_sts128_zero_if(pf_dst + 16u * WL, fast && !row_ok && t < 2);
-        if (pf_live && !pf_safe) {                                 // first / last band of the tensor: clamp every chunk
-            auto copy = [&](uint32_t dst, unsigned long long ca) {
-                const long long rem = (long long)(p.xe - ca);
-                const int bytes = (!row_ok || ca < p.xb || rem <= 0) ? 0 : (rem < 16 ? (int)rem : 16);
-                pk_cp16(dst, bytes ? ca : p.xb, bytes);
-            };
-            copy(pf_dst, src);
-            if (t < 2) copy(pf_dst + 16u * WL, src + 16ull * WL);
+    auto pf_batch = [&]() {                                        // one batch of rows (never straddles items), one commit group
+        if (pf_live) {
+            const uint32_t dst0 = ring + pf_off + 16u * t;
+            if (pf_safe) {
+#pragma unroll
+                for (int j = 0; j < BATCH; ++j) {
+                    const bool in_item = (unsigned)(pf_s + j) < (unsigned)pf_need;
+                    const bool row_ok = in_item && (unsigned)(pf_iy + j) < (unsigned)p.in_h;
+                    const unsigned long long src = (pf_a + j * pitch) & ~15ull;   // chunk t of the row (16 t is folded into pf_a)
+                    const uint32_t dst = dst0 + j * SLOT;
+                    // rows outside the plane: zeros written by the lane itself (slots outside the item are never read)
+                    pk_cp16_if(dst, src, row_ok && !(PK_KO & 4));
+                    pk_sts128_zero_if(dst, in_item && !row_ok);
+                    pk_cp16_if(dst + 16u * WL, src + 16ull * WL, row_ok && t < 2 && !(PK_KO & 4));
+                    pk_sts128_zero_if(dst + 16u * WL, in_item && !row_ok && t < 2);
+                }
+            } else {                                               // first / last band of the tensor: clamp every chunk
+#pragma unroll 1
+                for (int j = 0; j < BATCH; ++j) {
+                    const bool row_ok = (unsigned)(pf_s + j) < (unsigned)pf_need && (unsigned)(pf_iy + j) < (unsigned)p.in_h;
+                    const unsigned long long src = (pf_a + j * pitch) & ~15ull;
+                    auto copy = [&](uint32_t dst, unsigned long long ca) {
+                        const long long rem = (long long)(p.xe - ca);
+                        const int bytes = (!row_ok || ca < p.xb || rem <= 0) ? 0 : (rem < 16 ? (int)rem : 16);
+                        pk_cp16(dst, bytes ? ca : p.xb, bytes);
+                    };
+                    copy(dst0 + j * SLOT, src);
+                    if (t < 2) copy(dst0 + j * SLOT + 16u * WL, src + 16ull * WL);
+                }
+            }
+            pf_a += BATCH * pitch; pf_iy += BATCH; pf_s += BATCH;
+            if (pf_s >= pf_need) {
+                pf_item += stride;
+                pf_live = pf_item < p.items;
+                if (pf_live) pf_open();
+            }
         }
         pk_commit();
-        pf_a += pitch; ++pf_iy;
-        pf_dst += SLOT;
-        if (pf_dst >= ring_end) pf_dst -= PK_D * SLOT;
-        if (--pf_left == 0 && pf_live) {
-            pf_item += stride;
-            pf_live = pf_item < p.items;
-            if (pf_live) pf_open();
-        }
+        pf_off += BATCH * SLOT;
+        if (pf_off == RING) pf_off = 0;
     };
 #pragma unroll 1
-    for (int d = 0; d < PK_D - 1; ++d) pf_issue();
-    pk_wait<PK_D - 2>();                                           // the very first row (every later one: see the step's wait)
-    __syncwarp();
+    for (int d = 0; d < RB - 1; ++d) pf_batch();
 
-    uint32_t line = ring;                                          // this group's part of the slot the consumer reads next
+    uint32_t cs_off = 0;                                           // ring offset of the batch the consumer reads next
     for (long long item = item0; item < p.items; item += stride) {
         const Item it = decode(item);
-        const int nrows = max(0, min(p.rh, p.out_h - it.y0));
+        const int nrows = max(0, min(p.rh, p.out_h - it.y0));      // output rows of this lane's band
         const int x0 = it.xs0 + TX * t;
         const int n_out = nrows > 0 ? max(0, min(TX, p.out_w - x0)) : 0;
         const bool vec_ok = p.vec_store != 0 && n_out == TX;
         const int n_part = vec_ok ? 0 : n_out;                     // outputs of a row stored element by element
         // row the first store step points at (blur: s = 0 -> row -3, down-2: s = 1 -> row -1; never dereferenced)
         T *orow = out + (it.plane * p.out_h + it.y0 - (DOWN == 1 ? 3 : 1)) * (long long)p.out_w + x0;
+        const int need = it.need;
         // alignment of the row segment inside its first chunk, in elements (the same for every group of the warp)
         int q = (int)((p.xb + 2ull * (unsigned long long)((it.plane * p.in_h + it.iy0) * (long long)p.in_w + it.cx0)) >> 1) & 7;
         // zero padding left / right of the plane: the staged positions that lie outside the plane AND inside the window of a
         // lane that has outputs -- at most 3 on the left, 12 on the right (host check) -- are zeroed in shared memory once
-        // the row has landed (one step ahead of its use), position j of that list by lane j % WL of the group
+        // the batch has landed, position j of that list by lane j % WL of the group
         const int t_last = (min(WL * TX, p.out_w - it.xs0) - 1) / TX;              // last lane with outputs
         const int n_left = max(0, -it.cx0), pos_r = max(n_left, p.in_w - it.cx0);
         const int n_right = max(0, 8 * t_last + WU - pos_r);
@@ -280,10 +304,7 @@ upfirdn2d_pk_kernel(T *__restrict__ out, const float *__restrict__ taps, const U
         if (t < n_left) fix0 = 2 * t;
         else if (t - n_left < n_right) fix0 = 2 * (pos_r + t - n_left);
         if (t + WL - n_left < n_right) fix1 = 2 * (pos_r + t + WL - n_left);       // WL >= 8 > n_left
-        // row 0 of the item has landed and is visible (the previous step waited for it); the stores become visible to
-        // the other lanes at the first step's barrier
-        pk_sts16_zero_if(line + (uint32_t)(2 * q + fix0), fix0 >= 0);
-        pk_sts16_zero_if(line + (uint32_t)(2 * q + fix1), fix1 >= 0);
+        const bool any_fix = n_left + n_right > 0;                 // warp-uniform
 
         float2 acc[R][TX / 2];
 #pragma unroll
@@ -291,30 +312,37 @@ upfirdn2d_pk_kernel(T *__restrict__ out, const float *__restrict__ taps, const U
 #pragma unroll
             for (int i = 0; i < TX / 2; ++i) acc[r][i] = make_float2(0.f, 0.f);
 
-        for (int sb = 0; sb < it.nsteps; sb += 4) {
+        for (int sb = -it.u0; sb < need; sb += BATCH) {
+            pk_wait<RB - 2>();                                     // this lane's copies of the batch have landed
+            __syncwarp();                                          // ... and everybody's; every lane is done with the previous batch
+            const uint32_t line0 = ring + cs_off;
+            if (any_fix) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int s = sb + u;
-                pk_wait<PK_D - 3>();                               // this lane's copies of rows <= s + 1 have landed
-                __syncwarp();                                      // ... and everybody's; row s is fixed up; every lane is done with row s - 1
-                uint32_t line_next = line + SLOT;
-                if (line_next >= ring_end) line_next -= PK_D * SLOT;
-                const int q_next = (q + p.in_w) & 7;
-                {   // fix up row s + 1 (unless it belongs to the next item, which does it itself)
-                    const bool mine = u < 3 || sb + 4 < it.nsteps;
-                    pk_sts16_zero_if(line_next + (uint32_t)(2 * q_next + fix0), mine && fix0 >= 0);
-                    pk_sts16_zero_if(line_next + (uint32_t)(2 * q_next + fix1), mine && fix1 >= 0);
+                for (int j = 0; j < BATCH; ++j) {
+                    const int qj = QS == 8 ? j : (QS >= 0 ? QS : ((q + j * p.in_w) & 7));
+                    pk_sts16_zero_if(line0 + j * SLOT + (uint32_t)(2 * qj + fix0), fix0 >= 0);
+                    pk_sts16_zero_if(line0 + j * SLOT + (uint32_t)(2 * qj + fix1), fix1 >= 0);
                 }
-                pf_issue();                                        // refill the slot of row s - 1
+                __syncwarp();
+            }
+            pf_batch();                                            // refill the slots of the previous batch
+            cs_off += BATCH * SLOT;
+            if (cs_off == RING) cs_off = 0;
+#pragma unroll
+            for (int u = 0; u < BATCH; ++u) {
+                const int s = sb + u;
+                if ((unsigned)s >= (unsigned)need) continue;       // slots before the band's first row (mode 8) / after its last
+                const uint32_t line = line0 + u * SLOT + 16u * t;
+                const int qs = QS == 8 ? u : (QS >= 0 ? QS : q);   // static in the modes 0 .. 8
                 uint32_t c[9];
                 {
-                    const uint4 c0 = lds128(line + 16u * t), c1 = lds128(line + 16u * t + 16u);
+                    const uint4 c0 = lds128(line), c1 = lds128(line + 16u);
                     c[0] = c0.x; c[1] = c0.y; c[2] = c0.z; c[3] = c0.w;
                     c[4] = c1.x; c[5] = c1.y; c[6] = c1.z; c[7] = c1.w;
-                    c[8] = q + WU > 16 ? pk_lds32(line + 16u * t + 32u) : 0u;
+                    c[8] = qs + WU > 16 ? pk_lds32(line + 32u) : 0u;
                 }
                 float2 P[NP];
-                switch ((PK_KO & 8) ? 0 : q) {
+                switch ((PK_KO & 8) ? 0 : qs) {
                     case 0: pk_unpack<T, DOWN, 0>(c, P); break;
                     case 1: pk_unpack<T, DOWN, 1>(c, P); break;
                     case 2: pk_unpack<T, DOWN, 2>(c, P); break;
@@ -324,15 +352,14 @@ upfirdn2d_pk_kernel(T *__restrict__ out, const float *__restrict__ taps, const U
                     case 6: pk_unpack<T, DOWN, 6>(c, P); break;
                     default: pk_unpack<T, DOWN, 7>(c, P); break;
                 }
-                q = q_next;
-                line = line_next;
+                if constexpr (QS < 0) q = (q + p.in_w) & 7;
 
                 if constexpr (DOWN == 1) {
                     // input row s is tap row a of output row s - a (ring slot (u - a) & 3); output pair ip = columns
                     // (2 ip, 2 ip + 1) takes the window pair that starts at 2 ip + b: E[ip + b/2] or O[ip + (b-1)/2]
 #pragma unroll
                     for (int a = 0; a < 4; ++a) {
-                        const int r = (u - a + 4) & 3;
+                        const int r = (u - a + 8) & 3;
 #pragma unroll
                         for (int ip = 0; ip < 4; ++ip) {
                             float2 v = a == 0 ? make_float2(0.f, 0.f) : acc[r][ip];
@@ -355,7 +382,7 @@ upfirdn2d_pk_kernel(T *__restrict__ out, const float *__restrict__ taps, const U
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         const int a = e + 2 * h;
-                        const int r = (((u - a) / 2) + 2) & 1;     // (s - a) / 2 mod 2, sb a multiple of 4
+                        const int r = (((u - a + 8) / 2)) & 1;     // (s - a) / 2 mod 2, sb a multiple of 4
 #pragma unroll
                         for (int ip = 0; ip < 2; ++ip) {
                             float2 v = a == 0 ? make_float2(0.f, 0.f) : acc[r][ip];
@@ -369,7 +396,7 @@ upfirdn2d_pk_kernel(T *__restrict__ out, const float *__restrict__ taps, const U
                     }
                     if (e == 1) {                                  // tap row 3 done: output row (s - 3) / 2 is finished
                         const bool in_band = (unsigned)((s - 3) >> 1) < (unsigned)nrows;   // s = 1: -1 -> out of range
-                        pk_store_row<T, 4>(orow, acc[(((u - 3) / 2) + 2) & 1], in_band && vec_ok && !(PK_KO & 2), in_band && !(PK_KO & 2) ? n_part : 0);
+                        pk_store_row<T, 4>(orow, acc[((u - 3 + 8) / 2) & 1], in_band && vec_ok && !(PK_KO & 2), in_band && !(PK_KO & 2) ? n_part : 0);
                         orow += p.out_w;
                     }
                 }
@@ -385,18 +412,23 @@ static bool pk_debug() {
     return e && atoi(e);
 }
 
-template <typename T, int DOWN, int WLOG2>
+template <typename T, int DOWN, int WLOG2, int QS>
 static int pk_launch_t(void *out, const float *taps, const UfdPkParams &p, int grid, cudaStream_t st) {
     constexpr int WL = 1 << WLOG2, NS = 32 >> WLOG2;
-    constexpr size_t smem = (size_t)PK_WARPS * PK_D * NS * (WL + 2) * 16;
-    static bool attr_done = false;                                  // > 48 KiB never happens (NS = 8: exactly 48 KiB), kept for safety
-    if (smem > 48 * 1024 && !attr_done) {
-        SG2_CUDA_OK(cudaFuncSetAttribute(upfirdn2d_pk_kernel<T, DOWN, WLOG2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
-    }
-    upfirdn2d_pk_kernel<T, DOWN, WLOG2><<<grid, PK_THREADS, smem, st>>>((T *)out, taps, p);
+    constexpr size_t smem = (size_t)PK_WARPS * PkMode<QS>::RB * PkMode<QS>::BATCH * NS * (WL + 2) * 16;
+    static_assert(smem <= 48 * 1024, "dynamic shared memory without the opt-in attribute");
+    upfirdn2d_pk_kernel<T, DOWN, WLOG2, QS><<<grid, PK_THREADS, smem, st>>>((T *)out, taps, p);
     SG2_LAUNCH_CHECK();
     return SG2_OK;
+}
+
+template <typename T, int DOWN, int QS>
+static int pk_launch_w(int wl, void *out, const float *taps, const UfdPkParams &p, int grid, cudaStream_t st) {
+    switch (wl) {
+        case 3: return pk_launch_t<T, DOWN, 3, QS>(out, taps, p, grid, st);
+        case 4: return pk_launch_t<T, DOWN, 4, QS>(out, taps, p, grid, st);
+        default: return pk_launch_t<T, DOWN, 5, QS>(out, taps, p, grid, st);
+    }
 }
 
 // Returns SG2_OK when the launch was made, 1 when this path does not apply (the caller goes on to the row-streaming
@@ -420,40 +452,49 @@ int launch_upfirdn2d_pk(void *out, const void *x, const float *taps, int64_t pla
             const int n_left = std::max(0, -cx0), pos_r = std::max(n_left, in_w - cx0);
             if (n_left > 3 || 8 * t_last + WU - pos_r > 12) return 1;
         }
+        // how the kernel knows the alignment q of a row (see PkMode): a constant of the launch, the row's position in a
+        // batch of 8, or read per row
+        int qs = -1;
+        if (in_w % 8 == 0 && pad_x0 >= 0) qs = (-pad_x0) & 7;        // 0, 7, 6, 5
+        else if (down == 1 && in_w % 8 == 1) qs = 8;
+        {
+            const char *e = getenv("SG2_UPFIRDN_PK_QS");              // A/B switch (read per call): -1 = always the per-row switch
+            if (e && atoi(e) < 0) qs = -1;
+        }
         UfdPkParams p;
         p.in_h = in_h; p.in_w = in_w; p.out_h = out_h; p.out_w = out_w;
         p.pad_x0 = pad_x0; p.pad_y0 = pad_y0; p.kh = kh; p.kw = kw;
         p.planes = planes;
         p.n_strips = (out_w + TX * WL - 1) / (TX * WL);
-        // band height (multiple of 8): one super-band per plane if that still gives every resident warp ~4 items,
-        // otherwise shorter bands, down to 16 rows (8 when the groups of a warp already split the plane)
+        // band height: one super-band per plane if that still gives every resident warp ~3 items, otherwise shorter bands
+        // (a multiple of 8 when a warp walks several bands side by side: its groups must see the same alignment)
         const int sms = sm_count();
-        const int64_t want_items = (int64_t)sms * PK_CTAS * PK_WARPS * 4;
-        auto up8 = [](int v) { return (v + 7) & ~7; };
-        int rh = up8((out_h + NS - 1) / NS);
+        const int64_t want_items = (int64_t)sms * PK_CTAS * PK_WARPS * 3;
+        auto fit = [&](int v) { return NS > 1 ? (v + 7) & ~7 : v; };
+        auto sbands = [&](int rh) { return (out_h + NS * rh - 1) / (NS * rh); };
+        int rh = fit((out_h + NS - 1) / NS);
         const int rh_min = NS > 1 ? 8 : 16;
-        while (rh > rh_min && planes * p.n_strips * ((out_h + NS * rh - 1) / (NS * rh)) < want_items) rh = std::max(rh_min, up8(rh / 2));
+        while (rh > rh_min && planes * p.n_strips * sbands(rh) < want_items) rh = std::max(rh_min, fit((rh + 1) / 2));
         p.rh = rh;
-        p.n_sbands = (out_h + NS * rh - 1) / (NS * rh);
+        p.n_sbands = sbands(rh);
         p.items = planes * p.n_strips * p.n_sbands;
         p.xb = reinterpret_cast<uintptr_t>(x);
         p.xe = p.xb + 2ull * (unsigned long long)planes * in_h * in_w;
-        const int es = 2;
-        p.vec_store = (out_w % TX == 0 && reinterpret_cast<uintptr_t>(out) % (TX * es) == 0) ? 1 : 0;
+        p.vec_store = (out_w % TX == 0 && reinterpret_cast<uintptr_t>(out) % (TX * 2) == 0) ? 1 : 0;
         const int64_t want = (p.items + PK_WARPS - 1) / PK_WARPS;
         const int grid = (int)std::min<int64_t>(want, (int64_t)sms * PK_CTAS);
         if (grid <= 0) return SG2_OK;
         if (pk_debug())
             fprintf(stderr, "[sg2 upfirdn2d_pk] down %d, %lld planes %dx%d -> %dx%d, %d lanes per strip, bands of %d rows, %d super-bands, "
-                            "%lld items, grid %d\n", down, (long long)planes, in_h, in_w, out_h, out_w, WL, p.rh, p.n_sbands, p.items, grid);
-#define SG2_PK_CASE(D, W) case W: return pk_launch_t<T, D, W>(out, taps, p, grid, st);
+                            "%lld items, grid %d, q mode %d\n", down, (long long)planes, in_h, in_w, out_h, out_w, WL, p.rh, p.n_sbands,
+                    p.items, grid, qs);
+#define SG2_PK_Q(D, Q) case Q: return pk_launch_w<T, D, Q>(wl, out, taps, p, grid, st);
         if (down == 1) {
-            switch (wl) { SG2_PK_CASE(1, 3) SG2_PK_CASE(1, 4) SG2_PK_CASE(1, 5) }
+            switch (qs) { SG2_PK_Q(1, 0) SG2_PK_Q(1, 5) SG2_PK_Q(1, 6) SG2_PK_Q(1, 7) SG2_PK_Q(1, 8) default: return pk_launch_w<T, 1, -1>(wl, out, taps, p, grid, st); }
         } else {
-            switch (wl) { SG2_PK_CASE(2, 3) SG2_PK_CASE(2, 4) SG2_PK_CASE(2, 5) }
+            switch (qs) { SG2_PK_Q(2, 0) SG2_PK_Q(2, 5) SG2_PK_Q(2, 6) SG2_PK_Q(2, 7) default: return pk_launch_w<T, 2, -1>(wl, out, taps, p, grid, st); }
         }
-#undef SG2_PK_CASE
-        return 1;
+#undef SG2_PK_Q
     }
 }
 
