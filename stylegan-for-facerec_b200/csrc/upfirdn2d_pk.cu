@@ -43,7 +43,10 @@ using namespace tc;
 #endif                           // 1 no FMAs, 2 no global stores, 4 no global -> shared copies, 8 unpack case 0 only
 constexpr int PK_WARPS = 4;      // small CTAs: five of them fit the register file (<= 96 registers per thread) = 20 warps per SM
 constexpr int PK_THREADS = 32 * PK_WARPS;
-constexpr int PK_CTAS = 5;
+#ifndef PK_CTAS_N
+#define PK_CTAS_N 5
+#endif
+constexpr int PK_CTAS = PK_CTAS_N;
 
 
 struct UfdPkParams {
@@ -54,6 +57,8 @@ struct UfdPkParams {
     long long planes, items;  // items = planes * n_sbands * n_strips (strip fastest)
     unsigned long long xb, xe;   // first byte of the input tensor (16-byte aligned) / one past its last byte
     int vec_store;
+    int by_planes;            // NS > 1: the groups of a warp are planes 8 apart (else consecutive bands of one plane)
+    int no_sep;               // never take the separable blur (A/B switch, tests of the 16-tap path)
 };
 
 // One conversion per pair half, written straight into the half of the 64-bit register pair the packed FMA reads.  An
@@ -129,6 +134,11 @@ __device__ __forceinline__ void pk_sts16_zero_if(uint32_t addr, bool on) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %1, 0;\n\t@p st.shared.b16 [%0], %2;\n\t}" ::"r"(addr), "r"((int)on), "h"((unsigned short)0) : "memory");
 }
 
+// 16-byte copy, or 16 zero bytes when `zero` is set (cp.async's ignore-src operand: one LDGSTS.ZFILL, no branch)
+__device__ __forceinline__ void pk_cp16_or_zero(uint32_t dst, unsigned long long src, bool zero) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\tcp.async.cg.shared.global [%0], [%1], 16, p;\n\t}" ::"r"(dst), "l"(src), "r"((int)zero) : "memory");
+}
+
 template <typename T>
 __device__ __forceinline__ uint32_t pk_pack2(float2 v) {
     if constexpr (std::is_same<T, __nv_bfloat16>::value) {
@@ -185,7 +195,8 @@ upfirdn2d_pk_kernel(T *__restrict__ out, const float *__restrict__ taps, const U
     extern __shared__ __align__(16) unsigned char pk_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> WLOG2, t = lane & (WL - 1);
-    uint32_t ring = smem_u32(pk_smem) + (uint32_t)warp * RING + (uint32_t)g * GB;   // this group's part of slot 0
+    uint32_t ring = smem_u32(pk_smem) + (uint32_t)warp * (RING + 512) + (uint32_t)g * GB;   // this group's part of slot 0
+    const uint32_t scratch = smem_u32(pk_smem) + (uint32_t)warp * (RING + 512) + RING + 16u * lane;   // see pf_batch
     asm volatile("" : "+r"(ring));                                 // keep it in a register (ptxas re-derives it from S2R otherwise)
 
     // flipped taps, zero padded to 4 x 4: kf[a][b] multiplies the sample a rows / b columns after the window's first
@@ -196,6 +207,37 @@ upfirdn2d_pk_kernel(T *__restrict__ out, const float *__restrict__ taps, const U
         for (int b = 0; b < 4; ++b)
             kf[a][b] = (a < p.kh && b < p.kw) ? __ldg(taps + (p.kh - 1 - a) * p.kw + (p.kw - 1 - b)) : 0.f;
 
+    // Outer-product taps (what make_kernel builds, model.py:39-48 of the reference -- every caller of the op): the blur
+    // runs as a horizontal 4-tap pass on the new row + 4 vertical accumulations, 32 packed FMAs per row instead of 64.
+    // Decided here from the taps themselves: kf[a][b] == ca[a] * rb[b] to 4 ulp of the largest tap (ca = its column,
+    // rb = its row / the tap); fp32 rounding differs from the 16-tap order by ~1e-7 relative, far below the storage type's.
+    bool sep = false;
+    float ca[4] = {0.f, 0.f, 0.f, 0.f}, rb[4] = {0.f, 0.f, 0.f, 0.f};
+    if constexpr (DOWN == 1) {
+        float pv = 0.f;
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+                if (fabsf(kf[a][b]) > fabsf(pv)) {
+                    pv = kf[a][b];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { ca[i] = kf[i][b]; rb[i] = kf[a][i]; }
+                }
+        if (pv != 0.f) {
+            sep = true;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) rb[i] = rb[i] / pv;
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) sep = sep && fabsf(kf[a][b] - ca[a] * rb[b]) <= 4.8e-7f * fabsf(pv);
+        }
+        if (p.no_sep) sep = false;
+    }
+
+    auto body = [&](auto sep_tag) {
+    constexpr bool SEP = decltype(sep_tag)::value;
     const long long stride = (long long)gridDim.x * PK_WARPS;
     const long long item0 = (long long)blockIdx.x * PK_WARPS + warp;
     const unsigned long long pitch = 2ull * (unsigned long long)p.in_w;
@@ -203,21 +245,32 @@ upfirdn2d_pk_kernel(T *__restrict__ out, const float *__restrict__ taps, const U
     // item -> first output row of this lane's band, strip origin, first input row; need = input rows the bands of the
     // warp walk (warp-uniform: group 0 has the tallest band); the walk covers steps s = -u0 .. in whole batches, steps
     // outside [0, need) are skipped (u0 = alignment of the band's first row in mode 8, else 0)
-    struct Item { long long plane; int y0, xs0, iy0, cx0, need, u0; };
+    // The groups of a warp (NS > 1: planes narrower than 32 lanes) take either consecutive bands of one plane (rh a
+    // multiple of 8) or, when there are planes enough (p.by_planes), the same band of the planes P, P + 8, P + 16, ...:
+    // eight planes apart the alignment is the same whatever the plane size, and whole-plane bands have the smallest halo.
+    struct Item { long long plane; int y0, xs0, iy0, cx0, need, u0; bool live; };
     auto decode = [&](long long item) {
         Item it;
         const int strip = (int)(item % p.n_strips);
         const long long rest = item / p.n_strips;
         const int sband = (int)(rest % p.n_sbands);
         it.plane = rest / p.n_sbands;
+        int y00;                                                   // group 0
+        if (p.by_planes) {
+            it.plane = (it.plane >> 3) * (8 * NS) + (it.plane & 7) + 8 * g;
+            y00 = sband * p.rh;
+            it.y0 = y00;
+        } else {
+            y00 = sband * NS * p.rh;
+            it.y0 = y00 + g * p.rh;
+        }
+        it.live = it.plane < p.planes;
         it.xs0 = strip * (WL * TX);
         it.cx0 = DOWN * it.xs0 - p.pad_x0;
-        const int y00 = sband * NS * p.rh;                         // group 0
-        it.y0 = y00 + g * p.rh;
         it.iy0 = DOWN * it.y0 - p.pad_y0;
         it.need = DOWN * (min(p.rh, p.out_h - y00) - 1) + 4;
         it.u0 = 0;
-        if constexpr (QS == 8)   // alignment of the first row (the same for every group: rh is a multiple of 8)
+        if constexpr (QS == 8)   // alignment of the first row (the same for every group of the warp)
             it.u0 = (int)(((p.xb >> 1) + (unsigned long long)((it.plane * p.in_h + DOWN * y00 - p.pad_y0) * (long long)p.in_w + it.cx0)) & 7);
         return it;
     };
@@ -234,6 +287,7 @@ upfirdn2d_pk_kernel(T *__restrict__ out, const float *__restrict__ taps, const U
         const unsigned long long a0 = p.xb + 2ull * (unsigned long long)((it.plane * p.in_h + it.iy0) * (long long)p.in_w + it.cx0);
         const unsigned long long first = a0 & ~15ull, last = (a0 + (unsigned long long)(it.need - 1) * pitch) & ~15ull;
         pf_safe = first >= p.xb && first <= last && last + GB <= p.xe;   // every chunk of every row of the band lies inside the tensor
+        if (!it.live) { pf_safe = true; pf_iy = -0x40000000; }      // a group beyond the last plane stages zeros
         pf_a = a0 - it.u0 * pitch + 16ull * t;
     };
     if (pf_live) pf_open();
@@ -247,11 +301,12 @@ upfirdn2d_pk_kernel(T *__restrict__ out, const float *__restrict__ taps, const U
                     const bool row_ok = in_item && (unsigned)(pf_iy + j) < (unsigned)p.in_h;
                     const unsigned long long src = (pf_a + j * pitch) & ~15ull;   // chunk t of the row (16 t is folded into pf_a)
                     const uint32_t dst = dst0 + j * SLOT;
-                    // rows outside the plane: zeros written by the lane itself (slots outside the item are never read)
-                    pk_cp16_if(dst, src, row_ok && !(PK_KO & 4));
-                    pk_sts128_zero_if(dst, in_item && !row_ok);
-                    pk_cp16_if(dst + 16u * WL, src + 16ull * WL, row_ok && t < 2 && !(PK_KO & 4));
-                    pk_sts128_zero_if(dst + 16u * WL, in_item && !row_ok && t < 2);
+                    // rows outside the plane: zero-filled by the copy itself.  Chunks WL and WL + 1 of the row are copied by
+                    // lanes 0 and 1; the other lanes zero-fill a 16-byte scratch slot of their own (no global traffic) so
+                    // that the instruction needs neither a predicate nor the branch ptxas builds around one
+                    const bool zero = !row_ok || (PK_KO & 4);
+                    pk_cp16_or_zero(dst, zero ? p.xb : src, zero);
+                    pk_cp16_or_zero(t < 2 ? dst + 16u * WL : scratch, zero || t >= 2 ? p.xb : src + 16ull * WL, zero || t >= 2);
                 }
             } else {                                               // first / last band of the tensor: clamp every chunk
 #pragma unroll 1
@@ -284,7 +339,7 @@ upfirdn2d_pk_kernel(T *__restrict__ out, const float *__restrict__ taps, const U
     uint32_t cs_off = 0;                                           // ring offset of the batch the consumer reads next
     for (long long item = item0; item < p.items; item += stride) {
         const Item it = decode(item);
-        const int nrows = max(0, min(p.rh, p.out_h - it.y0));      // output rows of this lane's band
+        const int nrows = it.live ? max(0, min(p.rh, p.out_h - it.y0)) : 0;   // output rows of this lane's band
         const int x0 = it.xs0 + TX * t;
         const int n_out = nrows > 0 ? max(0, min(TX, p.out_w - x0)) : 0;
         const bool vec_ok = p.vec_store != 0 && n_out == TX;
@@ -357,6 +412,24 @@ upfirdn2d_pk_kernel(T *__restrict__ out, const float *__restrict__ taps, const U
                 if constexpr (DOWN == 1) {
                     // input row s is tap row a of output row s - a (ring slot (u - a) & 3); output pair ip = columns
                     // (2 ip, 2 ip + 1) takes the window pair that starts at 2 ip + b: E[ip + b/2] or O[ip + (b-1)/2]
+                    if constexpr (SEP) {
+                        float2 h[4];                               // the row filtered horizontally, per output pair
+#pragma unroll
+                        for (int ip = 0; ip < 4; ++ip) {
+                            float2 v = make_float2(0.f, 0.f);
+#pragma unroll
+                            for (int b = 0; b < 4; ++b)
+                                v = __ffma2_rn((b & 1) ? P[5 + ip + (b >> 1)] : P[ip + (b >> 1)], make_float2(rb[b], rb[b]), v);
+                            h[ip] = v;
+                        }
+#pragma unroll
+                        for (int a = 0; a < 4; ++a) {
+                            const int r = (u - a + 8) & 3;
+#pragma unroll
+                            for (int ip = 0; ip < 4; ++ip)
+                                acc[r][ip] = __ffma2_rn(h[ip], make_float2(ca[a], ca[a]), a == 0 ? make_float2(0.f, 0.f) : acc[r][ip]);
+                        }
+                    } else {
 #pragma unroll
                     for (int a = 0; a < 4; ++a) {
                         const int r = (u - a + 8) & 3;
@@ -370,6 +443,7 @@ upfirdn2d_pk_kernel(T *__restrict__ out, const float *__restrict__ taps, const U
                             }
                             acc[r][ip] = v;
                         }
+                    }
                     }
                     // finished: output row y0 + s - 3
                     const bool in_band = (unsigned)(s - 3) < (unsigned)nrows;
@@ -404,6 +478,12 @@ upfirdn2d_pk_kernel(T *__restrict__ out, const float *__restrict__ taps, const U
         }
     }
     pk_wait<0>();
+    };
+    if constexpr (DOWN == 1) {
+        if (sep) body(std::true_type{}); else body(std::false_type{});
+    } else {
+        body(std::false_type{});
+    }
 }
 
 // ---- host ------------------------------------------------------------------------------------------
@@ -415,7 +495,7 @@ static bool pk_debug() {
 template <typename T, int DOWN, int WLOG2, int QS>
 static int pk_launch_t(void *out, const float *taps, const UfdPkParams &p, int grid, cudaStream_t st) {
     constexpr int WL = 1 << WLOG2, NS = 32 >> WLOG2;
-    constexpr size_t smem = (size_t)PK_WARPS * PkMode<QS>::RB * PkMode<QS>::BATCH * NS * (WL + 2) * 16;
+    constexpr size_t smem = (size_t)PK_WARPS * (PkMode<QS>::RB * PkMode<QS>::BATCH * NS * (WL + 2) * 16 + 512);
     static_assert(smem <= 48 * 1024, "dynamic shared memory without the opt-in attribute");
     upfirdn2d_pk_kernel<T, DOWN, WLOG2, QS><<<grid, PK_THREADS, smem, st>>>((T *)out, taps, p);
     SG2_LAUNCH_CHECK();
@@ -469,17 +549,32 @@ int launch_upfirdn2d_pk(void *out, const void *x, const float *taps, int64_t pla
         // band height: one super-band per plane if that still gives every resident warp ~3 items, otherwise shorter bands
         // (a multiple of 8 when a warp walks several bands side by side: its groups must see the same alignment)
         const int sms = sm_count();
-        const int64_t want_items = (int64_t)sms * PK_CTAS * PK_WARPS * 3;
-        auto fit = [&](int v) { return NS > 1 ? (v + 7) & ~7 : v; };
-        auto sbands = [&](int rh) { return (out_h + NS * rh - 1) / (NS * rh); };
-        int rh = fit((out_h + NS - 1) / NS);
-        const int rh_min = NS > 1 ? 8 : 16;
-        while (rh > rh_min && planes * p.n_strips * sbands(rh) < want_items) rh = std::max(rh_min, fit((rh + 1) / 2));
+        int per_warp = 3;
+        if (const char *e = getenv("SG2_PK_ITEMS")) per_warp = std::max(1, atoi(e));   // experiment knob (read per call)
+        const int64_t want_items = (int64_t)sms * PK_CTAS * PK_WARPS * per_warp;
+        // narrow planes, many of them: the groups of a warp take planes 8 apart (see the kernel); the item count then
+        // runs over blocks of 8 NS planes
+        p.by_planes = NS > 1 && planes >= (int64_t)8 * NS * sms;
+        {
+            const char *e = getenv("SG2_UPFIRDN_PK_BYPLANES");        // A/B switch (read per call)
+            if (e) p.by_planes = NS > 1 && atoi(e) != 0;
+        }
+        const int64_t plane_slots = p.by_planes ? (planes + 8 * NS - 1) / (8 * NS) * 8 : planes;
+        const int gb = p.by_planes ? 1 : NS;                         // bands of one plane walked side by side
+        auto fit = [&](int v) { return gb > 1 ? (v + 7) & ~7 : v; };
+        auto sbands = [&](int rh) { return (out_h + gb * rh - 1) / (gb * rh); };
+        int rh = fit((out_h + gb - 1) / gb);
+        const int rh_min = gb > 1 ? 8 : 16;
+        while (rh > rh_min && plane_slots * p.n_strips * sbands(rh) < want_items) rh = std::max(rh_min, fit((rh + 1) / 2));
         p.rh = rh;
         p.n_sbands = sbands(rh);
-        p.items = planes * p.n_strips * p.n_sbands;
+        p.items = plane_slots * p.n_strips * p.n_sbands;
         p.xb = reinterpret_cast<uintptr_t>(x);
         p.xe = p.xb + 2ull * (unsigned long long)planes * in_h * in_w;
+        {
+            const char *e = getenv("SG2_UPFIRDN_PK_SEP");             // A/B switch (read per call): 0 = always the 16-tap blur
+            p.no_sep = e && atoi(e) == 0;
+        }
         p.vec_store = (out_w % TX == 0 && reinterpret_cast<uintptr_t>(out) % (TX * 2) == 0) ? 1 : 0;
         const int64_t want = (p.items + PK_WARPS - 1) / PK_WARPS;
         const int grid = (int)std::min<int64_t>(want, (int64_t)sms * PK_CTAS);

@@ -155,10 +155,10 @@ def test_upfirdn2d_streaming_low_precision(sg2, oracle, dtype, shape, up, down, 
 @pytest.mark.parametrize("shape,down,pad", [((2, 3, 257, 257), 1, (1, 1)), ((1, 2, 300, 131), 1, (2, 2)), ((3, 4, 17, 17), 1, (1, 1)),
                                             ((2, 3, 256, 256), 2, (1, 1)), ((1, 2, 129, 67), 2, (2, 2)), ((2, 2, 24, 20), 2, (1, 1))])
 def test_upfirdn2d_separable_taps(sg2, oracle, dtype, shape, down, pad):
-    """outer-product taps (what make_kernel builds, model.py:39-48) take the separable instantiation of the streaming kernel
-    (horizontal pass + vertical accumulation, decided on the device from the taps); asymmetric factors so that a flipped or
-    transposed factor would show; 3-tap and 4-tap factors; and a rank-2 kernel one ulp-scale away from separable stays on the
-    general path with the same result"""
+    """outer-product taps (what make_kernel builds, model.py:39-48): in 2-byte storage the packed kernel (upfirdn2d_pk.cu) runs the
+    blur as a horizontal pass + vertical accumulation, decided on the device from the taps; asymmetric factors so that a flipped
+    or transposed factor would show; 3-tap and 4-tap factors; and a rank-2 kernel close to separable stays on the 16-tap path
+    with the same result"""
     g = torch.Generator().manual_seed(11)
     x = torch.randn(shape, generator=g).to(dtype)
     for ky, kx in ((torch.tensor([1.0, -2.0, 3.5, 0.25]), torch.tensor([0.5, 4.0, -1.0, 2.0])),
@@ -175,6 +175,64 @@ def test_upfirdn2d_separable_taps(sg2, oracle, dtype, shape, down, pad):
         y2 = sg2.upfirdn2d(x.to(DEV), bumped.to(DEV), 1, down, pad)
         ref2 = oracle.upfirdn2d(x.double(), bumped.double(), 1, down, pad)
         np.testing.assert_allclose(y2.float().cpu().numpy(), ref2.float().numpy(), rtol=0, atol=tol)
+
+
+PK_SHAPES = [
+    # planes, h, w: every alignment of the row segment (odd pitches), 8 / 16 / 32 lanes per strip, several strips and bands
+    (3, 40, 65), (2, 65, 66), (3, 17, 67), (2, 130, 69), (3, 40, 71), (5, 129, 129), (2, 65, 131), (3, 40, 200), (2, 257, 257),
+    (3, 65, 258), (2, 40, 261), (1, 130, 300), (1, 513, 513), (2, 64, 520), (1, 70, 1025), (4, 256, 256), (37, 64, 64), (13, 33, 129),
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("planes,h,w", PK_SHAPES)
+def test_upfirdn2d_packed_kernel_bit_identical_to_streaming(sg2, oracle, monkeypatch, dtype, planes, h, w):
+    """upfirdn2d_pk.cu (2-byte storage, blur and down-2: packed fp32 FMAs, 16-byte cp.async rows at any pitch) applies the taps in
+    the order of the row-streaming kernel (= the reference kernel's, upfirdn2d_kernel.cu:104-117) with fused multiply-adds: with
+    taps that are not an outer product the two kernels must agree BIT FOR BIT, whatever the alignment mode, the grouping of
+    planes / bands inside a warp, or the position of the tensor in its allocation (over-reads would pick up the NaNs around it);
+    and both agree with the fp64 oracle to the storage precision"""
+    g = torch.Generator().manual_seed(h * 1000 + w)
+    for down, pad, k in ((1, (1, 1), 4), (1, (2, 2), 4), (1, (0, 2), 3), (1, (3, 0), 4), (2, (1, 1), 4), (2, (2, 2), 4), (2, (0, 1), 4)):
+        taps = torch.randn(k, k, generator=g)
+        n = planes * h * w
+        big = torch.full((n + 4096 + 8,), float("nan"), device=DEV, dtype=dtype)
+        off = big.numel() - n
+        off -= off % 8                                   # 16-byte aligned, at most 7 NaN elements behind the tensor
+        x = big[off:off + n].view(1, planes, h, w)
+        x.copy_(torch.randn(1, planes, h, w, generator=g).to(dtype))
+        outs = {}
+        for name, env in (("packed", {"SG2_UPFIRDN_PK": "1"}), ("packed, per-row alignment switch", {"SG2_UPFIRDN_PK": "1", "SG2_UPFIRDN_PK_QS": "-1"}),
+                          ("packed, planes 8 apart", {"SG2_UPFIRDN_PK": "1", "SG2_UPFIRDN_PK_BYPLANES": "1"}), ("streaming", {"SG2_UPFIRDN_PK": "0"})):
+            with monkeypatch.context() as m:
+                for key, val in env.items():
+                    m.setenv(key, val)
+                outs[name] = sg2.upfirdn2d(x, taps.to(DEV), 1, down, pad)
+        ref = oracle.upfirdn2d(x.cpu().double(), taps.double(), 1, down, pad)
+        for name, y in outs.items():
+            assert y.dtype == dtype and y.shape == ref.shape
+            assert torch.equal(y.view(torch.int16), outs["streaming"].view(torch.int16)), (name, down, pad, k)
+        tol = _tol(dtype) * float(ref.abs().max())
+        np.testing.assert_allclose(outs["packed"].float().cpu().numpy(), ref.float().numpy(), rtol=0, atol=tol)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_upfirdn2d_packed_kernel_separable_blur(sg2, oracle, monkeypatch, dtype):
+    """make_kernel taps (an exact outer product) on the model's blur geometry: the separable blur of the packed kernel against its
+    own 16-tap path -- at most one unit in the last place of the storage type apart -- and against the fp64 oracle"""
+    g = torch.Generator().manual_seed(9)
+    taps = (sg2.make_kernel([1, 3, 3, 1]) * 4).to(DEV)
+    for shape, pad in (((2, 16, 257, 257), (1, 1)), ((3, 7, 129, 129), (1, 1)), ((2, 5, 65, 65), (1, 1)), ((1, 3, 256, 256), (2, 2))):
+        x = torch.randn(shape, generator=g).to(dtype).to(DEV)
+        y = sg2.upfirdn2d(x, taps, 1, 1, pad)
+        with monkeypatch.context() as m:
+            m.setenv("SG2_UPFIRDN_PK_SEP", "0")
+            y16 = sg2.upfirdn2d(x, taps, 1, 1, pad)
+        ref = oracle.upfirdn2d(x.cpu().double(), taps.cpu().double(), 1, 1, pad)
+        eps = 2.0 ** -7 if dtype == torch.bfloat16 else 2.0 ** -10
+        lim = eps * torch.maximum(y.float().abs(), y16.float().abs()) + 4e-6 * float(ref.abs().max())
+        assert bool(((y.float() - y16.float()).abs() <= lim).all())
+        np.testing.assert_allclose(y.float().cpu().numpy(), ref.float().numpy(), rtol=0, atol=_tol(dtype) * float(ref.abs().max()))
 
 
 UFD_PLANES = [

@@ -34,7 +34,7 @@ def main():
     sg2 = importlib.import_module("stylegan-for-facerec_b200")
     g = torch.Generator().manual_seed(11)
     bad = 0
-    n = 0
+    n = nsep = ndiff = ntot = 0
     shapes = []
     for w in (33, 40, 47, 64, 65, 66, 67, 68, 69, 70, 71, 72, 100, 128, 129, 131, 200, 255, 256, 257, 258, 259, 260, 261, 263, 300, 513, 520, 1025):
         for h in (9, 17, 40, 65, 130):
@@ -63,6 +63,35 @@ def main():
                 y1 = run(sg2, x, taps, down, pad, True)
                 y0 = run(sg2, x, taps, down, pad, False)
                 n += 1
+                if ow <= 128 * (8 // (4 * down)) // 2 + 0 and w <= 140:
+                    # narrow planes: the groups of a warp as planes 8 apart (chosen by itself only for thousands of planes)
+                    os.environ["SG2_UPFIRDN_PK_BYPLANES"] = "1"
+                    for npl in (1, 13, 37):
+                        xs = torch.randn(1, npl, h, w, generator=g).to(dtype).to(DEV)
+                        yb = run(sg2, xs, taps, down, pad, True)
+                        yr = run(sg2, xs, taps, down, pad, False)
+                        n += 1
+                        if not torch.equal(yb.view(torch.int16), yr.view(torch.int16)):
+                            bad += 1
+                            print(f"BY-PLANES MISMATCH {dtype} planes {npl} {h}x{w} down {down} pad {pad} k {k}", flush=True)
+                    del os.environ["SG2_UPFIRDN_PK_BYPLANES"]
+                if down == 1:
+                    # outer-product taps: the packed kernel takes its separable blur (fp32 rounding order differs): the
+                    # outputs may differ from the 16-tap order by one unit in the last place of the storage type
+                    ts = torch.outer(torch.randn(k, generator=g), torch.randn(k, generator=g)).to(DEV)
+                    z1 = run(sg2, x, ts, down, pad, True).float()
+                    z0 = run(sg2, x, ts, down, pad, False).float()
+                    eps = 2.0 ** -7 if dtype == torch.bfloat16 else 2.0 ** -10
+                    lim = eps * torch.maximum(z0.abs(), z1.abs()) + 4e-6 * float(z0.abs().max())   # floor: outputs that cancel to ~0
+                    nsep += 1
+                    if not bool(((z1 - z0).abs() <= lim).all()) or not torch.isfinite(z1).all():
+                        bad += 1
+                        d = (z1 - z0).abs() - lim
+                        i = int(d.argmax())
+                        print(f"SEPARABLE MISMATCH {dtype} planes {pl} {h}x{w} pad {pad} k {k}: max {float((z1 - z0).abs().max()):.4g}; worst: "
+                              f"16-tap {float(z0.flatten()[i])!r} separable {float(z1.flatten()[i])!r} at {i}, taps {ts.flatten().tolist()}", flush=True)
+                    ndiff += int((z1 != z0).sum())
+                    ntot += z1.numel()
                 same = torch.equal(y1.view(torch.int16), y0.view(torch.int16))
                 if not same or not torch.isfinite(y1.float()).all():
                     bad += 1
@@ -70,7 +99,7 @@ def main():
                     idx = torch.nonzero(d > 0)
                     print(f"MISMATCH {dtype} planes {pl} {h}x{w} down {down} pad {pad} k {k}: max {float(d.max()):.4g}, {idx.shape[0]} elements, first {idx[:4].tolist()}",
                           flush=True)
-    print(f"checked {n} cases, {bad} mismatches", flush=True)
+    print(f"checked {n} cases bit for bit + {nsep} with outer-product taps ({ndiff} of {ntot} outputs one ulp away), {bad} mismatches", flush=True)
 
     if args.perf or args.perf_only:
         peak = 6550.0
