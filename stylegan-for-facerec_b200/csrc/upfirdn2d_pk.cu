@@ -179,7 +179,7 @@ __device__ __forceinline__ void pk_store_row(T *dst, const float2 (&v)[N / 2], b
 // In the static modes the unpack code is straight-line and the compiler interleaves it with the FMAs.
 template <int QS> struct PkMode { static constexpr int BATCH = QS == 8 ? 8 : 4, RB = QS == 8 ? 2 : 3; };
 
-// WLOG2: lanes per group (log2, >= 3).  TX outputs per lane; every lane consumes 8 input elements (one chunk) per row.
+// WLOG2: lanes per group (log2, >= 2).  TX outputs per lane; every lane consumes 8 input elements (one chunk) per row.
 template <typename T, int DOWN, int WLOG2, int QS>
 __global__ void __launch_bounds__(PK_THREADS, PK_CTAS)
 upfirdn2d_pk_kernel(T *__restrict__ out, const float *__restrict__ taps, const UfdPkParams p) {
@@ -238,6 +238,7 @@ upfirdn2d_pk_kernel(T *__restrict__ out, const float *__restrict__ taps, const U
 
     auto body = [&](auto sep_tag) {
     constexpr bool SEP = decltype(sep_tag)::value;
+    (void)SEP;
     const long long stride = (long long)gridDim.x * PK_WARPS;
     const long long item0 = (long long)blockIdx.x * PK_WARPS + warp;
     const unsigned long long pitch = 2ull * (unsigned long long)p.in_w;
@@ -358,7 +359,7 @@ upfirdn2d_pk_kernel(T *__restrict__ out, const float *__restrict__ taps, const U
         int fix0 = -1, fix1 = -1;                                  // byte offsets of this lane's positions
         if (t < n_left) fix0 = 2 * t;
         else if (t - n_left < n_right) fix0 = 2 * (pos_r + t - n_left);
-        if (t + WL - n_left < n_right) fix1 = 2 * (pos_r + t + WL - n_left);       // WL >= 8 > n_left
+        if (t + WL - n_left < n_right) fix1 = 2 * (pos_r + t + WL - n_left);       // WL >= 4 > n_left
         const bool any_fix = n_left + n_right > 0;                 // warp-uniform
 
         float2 acc[R][TX / 2];
@@ -505,6 +506,9 @@ static int pk_launch_t(void *out, const float *taps, const UfdPkParams &p, int g
 template <typename T, int DOWN, int QS>
 static int pk_launch_w(int wl, void *out, const float *taps, const UfdPkParams &p, int grid, cudaStream_t st) {
     switch (wl) {
+        case 2:
+            if constexpr (QS != 8) return pk_launch_t<T, DOWN, 2, QS>(out, taps, p, grid, st);
+            else return 1;
         case 3: return pk_launch_t<T, DOWN, 3, QS>(out, taps, p, grid, st);
         case 4: return pk_launch_t<T, DOWN, 4, QS>(out, taps, p, grid, st);
         default: return pk_launch_t<T, DOWN, 5, QS>(out, taps, p, grid, st);
@@ -522,21 +526,23 @@ int launch_upfirdn2d_pk(void *out, const void *x, const float *taps, int64_t pla
         if (up != 1 || (down != 1 && down != 2) || kh > 4 || kw > 4) return 1;
         if (reinterpret_cast<uintptr_t>(x) % 16 != 0) return 1;
         const int TX = down == 1 ? 8 : 4, WU = down == 1 ? 11 : 10;
-        if (out_w <= 4 * TX || out_h < 8 || pad_x0 > 3) return 1;     // small planes: upfirdn2d_planes.cu / the streaming kernel
-        int wl = 3;
+        if (out_w <= 2 * TX || out_h < 8 || pad_x0 > 3) return 1;     // small planes: upfirdn2d_planes.cu / the streaming kernel
+        int wl = 2;
         while ((TX << wl) < out_w && wl < 5) ++wl;
         const int WL = 1 << wl, NS = 32 >> wl;
+        // 4 lanes per strip (planes up to 32 / 16 outputs wide): only as 8 planes per warp, many planes
+        if (wl == 2 && planes < (int64_t)8 * NS * sm_count()) return 1;
         // the kernel zeroes at most 3 + 12 staged positions per row and group (see there): every strip must fit
         for (int xs0 = 0; xs0 < out_w; xs0 += WL * TX) {
             const int cx0 = down * xs0 - pad_x0, t_last = (std::min(WL * TX, out_w - xs0) - 1) / TX;
             const int n_left = std::max(0, -cx0), pos_r = std::max(n_left, in_w - cx0);
-            if (n_left > 3 || 8 * t_last + WU - pos_r > 12) return 1;
+            if (n_left > 3 || 8 * t_last + WU - pos_r > 12 || n_left + std::max(0, 8 * t_last + WU - pos_r) > 2 * WL) return 1;
         }
         // how the kernel knows the alignment q of a row (see PkMode): a constant of the launch, the row's position in a
         // batch of 8, or read per row
         int qs = -1;
         if (in_w % 8 == 0 && pad_x0 >= 0) qs = (-pad_x0) & 7;        // 0, 7, 6, 5
-        else if (down == 1 && in_w % 8 == 1) qs = 8;
+        else if (down == 1 && in_w % 8 == 1 && wl > 2) qs = 8;      // (8 groups per warp: the ring of mode 8 would not fit)
         {
             const char *e = getenv("SG2_UPFIRDN_PK_QS");              // A/B switch (read per call): -1 = always the per-row switch
             if (e && atoi(e) < 0) qs = -1;
@@ -557,7 +563,7 @@ int launch_upfirdn2d_pk(void *out, const void *x, const float *taps, int64_t pla
         p.by_planes = NS > 1 && planes >= (int64_t)8 * NS * sms;
         {
             const char *e = getenv("SG2_UPFIRDN_PK_BYPLANES");        // A/B switch (read per call)
-            if (e) p.by_planes = NS > 1 && atoi(e) != 0;
+            if (e) p.by_planes = NS > 1 && (atoi(e) != 0 || wl == 2);
         }
         const int64_t plane_slots = p.by_planes ? (planes + 8 * NS - 1) / (8 * NS) * 8 : planes;
         const int gb = p.by_planes ? 1 : NS;                         // bands of one plane walked side by side
