@@ -144,19 +144,29 @@ __device__ __forceinline__ void store_row(T *dst, const float (&v)[N], int n_ok,
 // PHX / PHY: parity of (pad_x0, pad_y0) for UP == 2 (which polyphase pattern a 4-aligned output column /
 // an even output row starts with); unused (0) otherwise.
 // WLOG2: lanes per strip (log2) -- a template parameter so that the strided row loads take immediate offsets.
-template <typename T, int UP, int DOWN, int PHX, int PHY, int WLOG2>
+// VD: -1 = rows fetched element by element (any pitch / alignment); 0..3 = fp32 rows whose pitch and base are multiples of 16
+// bytes (the 2^k-wide planes of the down- and up-sampling passes): the staged line starts VD elements before the strip's first
+// column, on a 16-byte boundary, and rows travel as 16-byte loads / shared stores (the scalar form keeps the L1/LSU pipe 91 %
+// busy on the fp32 down-sampling pass: 21 memory instructions per row and lane, 8 here); a vector lies entirely inside or
+// entirely outside the plane, so the zero padding is a predicate on the load and nothing is ever read outside the tensor.
+template <typename T, int UP, int DOWN, int PHX, int PHY, int WLOG2, int VD = -1>
 __global__ void __launch_bounds__(US_THREADS)
 upfirdn2d_stream_kernel(T *__restrict__ out, const T *__restrict__ x, const float *__restrict__ taps, const UfdStreamParams p) {
     using G = SGeo<UP, DOWN>;
-    constexpr int NI = G::LS + 1;                                  // loads per lane per row: ceil(line / lanes), lanes >= 4
+    constexpr bool VEC = VD >= 0;
+    static_assert(!VEC || sizeof(T) == 4, "vector rows: fp32 only");
+    constexpr int D = VEC ? VD : 0;                                // window elements before the strip's first column
+    constexpr int WRD = VEC ? (D + G::WU + 3) & ~3 : G::WR;        // window elements read
+    constexpr int NI = VEC ? 1 : G::LS + 1;                        // loads per lane per row: ceil(line / lanes), lanes >= 4
+    constexpr int NVF = G::LS / 4, NVX = (WRD - G::LS) / 4;        // vector rows: full vectors per lane, extra vectors (first lanes)
     extern __shared__ __align__(16) float us_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int WL = 1 << WLOG2, NS = 32 >> WLOG2;
     const int g = lane >> WLOG2, t = lane & (WL - 1);              // group of the lane, lane inside the group
-    constexpr int line_len = (WL - 1) * G::LS + G::WR;             // staged elements of one row
+    constexpr int line_len = (WL - 1) * G::LS + WRD;               // staged elements of one row
     // positions t + WL*i, i < LS, always exist (WL*LS - 1 < line_len); the last one only for the first lanes
     static_assert(G::LS - 1 < G::WR, "line layout");
-    const bool has_last = t < G::WR - G::LS;
+    const bool has_last = t < (VEC ? NVX : G::WR - G::LS);
     // per warp: two line buffers (row s is staged while the windows of row s - 1 may still be read) x NS groups
     float *wbase = us_smem + (size_t)warp * (2 * NS * p.line_floats);
     const uint32_t ring_s = smem_u32(wbase);
@@ -202,6 +212,7 @@ upfirdn2d_stream_kernel(T *__restrict__ out, const T *__restrict__ x, const floa
             cx0 = (xs0 - p.pad_x0 + PHX) / 2;
             nsteps = (nrows + 2 - PHY) / 2 + 1;                    // rows Y = y0 + PHY + 2s <= y1 + 2
         }
+        cx0 -= D;                                                  // (vector rows: a multiple of 4 now)
         if (!active) nsteps = 0;
         int nsteps_max = nsteps;
 #pragma unroll
@@ -213,7 +224,7 @@ upfirdn2d_stream_kernel(T *__restrict__ out, const T *__restrict__ x, const floa
         // over-read would leave the tensor (start of the first plane, end of the last plane).
         uint32_t outside = 0;
 #pragma unroll
-        for (int i = 0; i < NI; ++i) {
+        for (int i = 0; i < (VEC ? 0 : NI); ++i) {
             const int pos = t + WL * i, col = cx0 + pos;
             if ((i < G::LS || has_last) && (col < 0 || col >= p.in_w)) outside |= 1u << i;
         }
@@ -222,7 +233,26 @@ upfirdn2d_stream_kernel(T *__restrict__ out, const T *__restrict__ x, const floa
 
         // ---- register prefetch ring: US_PF rows in flight ----
         T pre[US_PF][NI];
+        float4 prev[VEC ? US_PF : 1][VEC ? NVF + 1 : 1];
+        // vector rows: this lane's vectors sit at line positions 4 (t + WL i); which of them lie inside the plane (row invariant)
+        uint32_t vin = 0;
+        if constexpr (VEC) {
+#pragma unroll
+            for (int i = 0; i <= NVF; ++i) {
+                const int col = cx0 + 4 * (t + WL * i);
+                if ((i < NVF || has_last) && col >= 0 && col + 4 <= p.in_w) vin |= 1u << i;
+            }
+        }
+        auto fetch_vec = [&](int s, float4 (&r)[VEC ? NVF + 1 : 1]) {
+            const int iy = iy_first + s;
+            const bool row_ok = s < nsteps && iy >= 0 && iy < p.in_h;
+            const float4 *rp = reinterpret_cast<const float4 *>(x + plane * plane_in + (long long)iy * p.in_w + cx0) + t;
+#pragma unroll
+            for (int i = 0; i <= NVF; ++i) r[i] = (row_ok && ((vin >> i) & 1u)) ? __ldg(rp + WL * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
         auto fetch = [&](int s, T (&r)[NI]) {
+            if constexpr (VEC) return;
+            else {
             const int iy = iy_first + s;
             const bool row_ok = s < nsteps && iy >= 0 && iy < p.in_h;
             const T *rp = xp + (long long)iy * p.in_w;
@@ -240,9 +270,12 @@ upfirdn2d_stream_kernel(T *__restrict__ out, const T *__restrict__ x, const floa
                 for (int i = 0; i < G::LS; ++i) r[i] = __ldg(rp + WL * i);
                 r[G::LS] = has_last ? __ldg(rp + WL * G::LS) : Cvt<T>::from_f(0.f);
             }
+            }
         };
 #pragma unroll
-        for (int d = 0; d < US_PF; ++d) fetch(d, pre[d]);
+        for (int d = 0; d < US_PF; ++d) {
+            if constexpr (VEC) fetch_vec(d, prev[d]); else fetch(d, pre[d]);
+        }
 
         float acc[G::R][G::TX];
 #pragma unroll
@@ -261,18 +294,28 @@ upfirdn2d_stream_kernel(T *__restrict__ out, const T *__restrict__ x, const floa
                 // stage row s (fp32) in line buffer s & 1, refill its register slot with row s + US_PF
                 const uint32_t line = ring_s + (uint32_t)(((u & 1) * NS + g) * p.line_floats) * 4u;
                 float *lp = wbase + ((u & 1) * NS + g) * p.line_floats + t;
+                if constexpr (VEC) {
+                    float4 *lv = reinterpret_cast<float4 *>(wbase + ((u & 1) * NS + g) * p.line_floats) + t;
 #pragma unroll
-                for (int i = 0; i < G::LS; ++i) lp[WL * i] = Cvt<T>::to_f(pre[u][i]);
-                if (has_last) lp[WL * G::LS] = Cvt<T>::to_f(pre[u][G::LS]);
-                if (outside) {                                     // zero padding: few lanes, border strips only
+                    for (int i = 0; i < NVF; ++i) lv[WL * i] = prev[u][i];
+                    if (has_last) lv[WL * NVF] = prev[u][NVF];
+                    __syncwarp();
+                    fetch_vec(s + US_PF, prev[u]);
+                } else {
 #pragma unroll
-                    for (int i = 0; i < NI; ++i)
-                        if ((outside >> i) & 1u) lp[WL * i] = 0.f;
+                    for (int i = 0; i < G::LS; ++i) lp[WL * i] = Cvt<T>::to_f(pre[u][i]);
+                    if (has_last) lp[WL * G::LS] = Cvt<T>::to_f(pre[u][G::LS]);
+                    if (outside) {                                 // zero padding: few lanes, border strips only
+#pragma unroll
+                        for (int i = 0; i < NI; ++i)
+                            if ((outside >> i) & 1u) lp[WL * i] = 0.f;
+                    }
+                    __syncwarp();
+                    fetch(s + US_PF, pre[u]);
                 }
-                __syncwarp();
-                fetch(s + US_PF, pre[u]);
-                float w[G::WR];
-                load_window<float, G::WR, G::LS * 4>(line + (uint32_t)(t * G::LS * 4), w);
+                float wfull[WRD];
+                load_window<float, WRD, 16>(line + (uint32_t)(t * G::LS * 4), wfull);
+                const float *w = wfull + D;                        // w[j]: the window element j columns after the strip's first
 
                 if constexpr (UP == 1 && DOWN == 1) {
                     // input row s feeds tap row a of output row (s - a); ring slot (s - a) & 3 = (u - a) & 3
@@ -366,6 +409,19 @@ upfirdn2d_stream_kernel(T *__restrict__ out, const T *__restrict__ x, const floa
 }
 
 // ---- host ------------------------------------------------------------------------------------------
+template <int VD>
+static int launch_stream_vec(void *out, const void *x, const float *taps, const UfdStreamParams &p, int grid, size_t smem, cudaStream_t st) {
+    float *o = (float *)out;
+    const float *xi = (const float *)x;
+    switch (p.wl_log2) {
+        case 2: upfirdn2d_stream_kernel<float, 1, 2, 0, 0, 2, VD><<<grid, US_THREADS, smem, st>>>(o, xi, taps, p); break;
+        case 3: upfirdn2d_stream_kernel<float, 1, 2, 0, 0, 3, VD><<<grid, US_THREADS, smem, st>>>(o, xi, taps, p); break;
+        default: upfirdn2d_stream_kernel<float, 1, 2, 0, 0, 4, VD><<<grid, US_THREADS, smem, st>>>(o, xi, taps, p); break;
+    }
+    SG2_LAUNCH_CHECK();
+    return SG2_OK;
+}
+
 template <typename T, int UP, int DOWN, int PHX, int PHY>
 static int launch_stream_t(void *out, const void *x, const float *taps, const UfdStreamParams &p, int grid, size_t smem,
                            cudaStream_t st) {
@@ -406,7 +462,14 @@ int launch_upfirdn2d_stream(void *out, const void *x, const float *taps, int64_t
     p.planes = planes;
     const int WL = 1 << wl, NS = 32 >> wl;
     const int LS = TX * down / up, WU = up == 2 ? TX / 2 + 2 : down * (TX - 1) + 4, WR = (WU + 3) & ~3;
-    p.line_floats = ((WL - 1) * LS + WR + 3) & ~3;
+    // fp32 down-sampling of planes whose rows start on 16-byte boundaries (the 2^k-wide planes): rows as 16-byte vectors,
+    // the staged line starts vd elements before the strip's first column (see the kernel)
+    int vd = -1;
+    if (std::is_same<T, float>::value && up == 1 && down == 2 && in_w % 4 == 0 && reinterpret_cast<uintptr_t>(x) % 16 == 0) {
+        static const char *env_vec = getenv("SG2_UPFIRDN_VEC");         // A/B switch: 0 = element-wise rows
+        if (!env_vec || atoi(env_vec) != 0) vd = ((-pad_x0) % 4 + 4) % 4;
+    }
+    p.line_floats = ((WL - 1) * LS + (vd >= 0 ? ((vd + WU + 3) & ~3) : WR) + 3) & ~3;
     p.n_strips = (out_w + TX * WL - 1) / (TX * WL);
     // band height: tall enough to amortise the vertical halo, short enough for >= 4 items per resident group
     const int sms = sm_count();
@@ -426,6 +489,15 @@ int launch_upfirdn2d_stream(void *out, const void *x, const float *taps, int64_t
         fprintf(stderr, "[sg2 upfirdn2d_stream] up %d down %d, %lld planes %dx%d -> %dx%d, %d lanes per strip, bands of %d rows, "
                         "%lld items, grid %d\n", up, down, (long long)planes, in_h, in_w, out_h, out_w, WL, p.rh, p.items, grid);
     const int phx = up == 2 ? (pad_x0 & 1) : 0, phy = up == 2 ? (pad_y0 & 1) : 0;
+    if constexpr (std::is_same<T, float>::value) {
+        switch (vd) {
+            case 0: return launch_stream_vec<0>(out, x, taps, p, grid, smem, st);
+            case 1: return launch_stream_vec<1>(out, x, taps, p, grid, smem, st);
+            case 2: return launch_stream_vec<2>(out, x, taps, p, grid, smem, st);
+            case 3: return launch_stream_vec<3>(out, x, taps, p, grid, smem, st);
+            default: break;
+        }
+    }
     if (up == 1 && down == 1) return launch_stream_t<T, 1, 1, 0, 0>(out, x, taps, p, grid, smem, st);
     if (up == 1 && down == 2) return launch_stream_t<T, 1, 2, 0, 0>(out, x, taps, p, grid, smem, st);
     if (phx == 0 && phy == 0) return launch_stream_t<T, 2, 1, 0, 0>(out, x, taps, p, grid, smem, st);

@@ -122,6 +122,9 @@ UFD_SWEEP = [
     ((1, 2, 67, 67), 4, 2, 1, (3, 0)), ((1, 2, 130, 30), 2, 2, 1, (0, 1)), ((2, 2, 260, 264), 4, 1, 2, (1, 1)),
     ((1, 3, 129, 67), 4, 1, 2, (2, 2)), ((1, 2, 64, 520), 4, 1, 2, (0, 1)), ((5, 7, 17, 17), 4, 1, 1, (1, 1)),
     ((4, 9, 32, 32), 4, 2, 1, (2, 1)), ((4, 9, 64, 64), 4, 1, 2, (1, 1)), ((1, 1, 1030, 1030), 4, 1, 1, (1, 1)),
+    # fp32 down-sampling with 16-byte rows (vector loads): every offset of the staged line, several strips, a plane narrower than a strip
+    ((2, 3, 128, 136), 4, 1, 2, (2, 2)), ((1, 2, 96, 72), 4, 1, 2, (3, 1)), ((3, 2, 40, 24), 3, 1, 2, (0, 0)), ((1, 2, 70, 300), 4, 1, 2, (1, 1)),
+    ((2, 2, 33, 16), 2, 1, 2, (0, 0)),
 ]
 
 
