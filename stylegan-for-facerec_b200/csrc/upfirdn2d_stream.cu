@@ -154,7 +154,11 @@ __global__ void __launch_bounds__(US_THREADS)
 upfirdn2d_stream_kernel(T *__restrict__ out, const T *__restrict__ x, const float *__restrict__ taps, const UfdStreamParams p) {
     using G = SGeo<UP, DOWN>;
     constexpr bool VEC = VD >= 0;
-    static_assert(!VEC || sizeof(T) == 4, "vector rows: fp32 only");
+    // vector rows: 4 elements per load (16 bytes of fp32, 8 bytes of bf16 / fp16); the 2-byte up-sampling pass, whose rows
+    // are short (4 + 1 elements per lane) and whose time went to waiting for them (ncu: long_scoreboard + wait), also keeps
+    // 6 rows in flight instead of 4 -- a vector per row and lane costs fewer registers than 5 scalars did
+    using VecT = typename std::conditional<sizeof(T) == 4, float4, uint2>::type;
+    constexpr int PF = (VEC && UP == 2 && sizeof(T) == 2) ? 6 : US_PF;
     constexpr int D = VEC ? VD : 0;                                // window elements before the strip's first column
     constexpr int WRD = VEC ? (D + G::WU + 3) & ~3 : G::WR;        // window elements read
     constexpr int NI = VEC ? 1 : G::LS + 1;                        // loads per lane per row: ceil(line / lanes), lanes >= 4
@@ -232,8 +236,8 @@ upfirdn2d_stream_kernel(T *__restrict__ out, const T *__restrict__ x, const floa
         const T *xp = x + plane * plane_in + cx0 + t;             // (row 0, position t)
 
         // ---- register prefetch ring: US_PF rows in flight ----
-        T pre[US_PF][NI];
-        float4 prev[VEC ? US_PF : 1][VEC ? NVF + 1 : 1];
+        T pre[VEC ? 1 : PF][NI];
+        VecT prev[VEC ? PF : 1][VEC ? NVF + 1 : 1];
         // vector rows: this lane's vectors sit at line positions 4 (t + WL i); which of them lie inside the plane (row invariant)
         uint32_t vin = 0;
         if constexpr (VEC) {
@@ -243,12 +247,27 @@ upfirdn2d_stream_kernel(T *__restrict__ out, const T *__restrict__ x, const floa
                 if ((i < NVF || has_last) && col >= 0 && col + 4 <= p.in_w) vin |= 1u << i;
             }
         }
-        auto fetch_vec = [&](int s, float4 (&r)[VEC ? NVF + 1 : 1]) {
+        auto fetch_vec = [&](int s, VecT (&r)[VEC ? NVF + 1 : 1]) {
             const int iy = iy_first + s;
             const bool row_ok = s < nsteps && iy >= 0 && iy < p.in_h;
-            const float4 *rp = reinterpret_cast<const float4 *>(x + plane * plane_in + (long long)iy * p.in_w + cx0) + t;
+            const VecT *rp = reinterpret_cast<const VecT *>(x + plane * plane_in + (long long)iy * p.in_w + cx0) + t;
 #pragma unroll
-            for (int i = 0; i <= NVF; ++i) r[i] = (row_ok && ((vin >> i) & 1u)) ? __ldg(rp + WL * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = 0; i <= NVF; ++i) {
+                if (row_ok && ((vin >> i) & 1u)) r[i] = __ldg(rp + WL * i);
+                else if constexpr (sizeof(T) == 4) r[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                else r[i] = make_uint2(0u, 0u);
+            }
+        };
+        auto vec_to_f4 = [](const VecT &v) {
+            if constexpr (sizeof(T) == 4) {
+                return v;
+            } else if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+                return make_float4(__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xffff0000u), __uint_as_float(v.y << 16),
+                                   __uint_as_float(v.y & 0xffff0000u));
+            } else {
+                const float2 a = __half22float2(*reinterpret_cast<const __half2 *>(&v.x)), b = __half22float2(*reinterpret_cast<const __half2 *>(&v.y));
+                return make_float4(a.x, a.y, b.x, b.y);
+            }
         };
         auto fetch = [&](int s, T (&r)[NI]) {
             if constexpr (VEC) return;
@@ -273,22 +292,27 @@ upfirdn2d_stream_kernel(T *__restrict__ out, const T *__restrict__ x, const floa
             }
         };
 #pragma unroll
-        for (int d = 0; d < US_PF; ++d) {
+        for (int d = 0; d < PF; ++d) {
             if constexpr (VEC) fetch_vec(d, prev[d]); else fetch(d, pre[d]);
         }
 
-        float acc[G::R][G::TX];
+        float acc[UP == 2 ? 1 : G::R][G::TX];                      // (up-sampling keeps its rows as pairs, below)
 #pragma unroll
-        for (int r = 0; r < G::R; ++r)
+        for (int r = 0; r < (UP == 2 ? 1 : G::R); ++r)
 #pragma unroll
             for (int i = 0; i < G::TX; ++i) acc[r][i] = 0.f;
+        float2 acc2[2][G::TX];
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int i = 0; i < G::TX; ++i) acc2[r][i] = make_float2(0.f, 0.f);
         T *oplane = out + plane * plane_out;
         const int x0 = xs0 + G::TX * t;
         const int n_ok = active ? max(0, min(G::TX, p.out_w - x0)) : 0;
 
-        for (int sb = 0; sb < nsteps_max; sb += US_PF) {
+        for (int sb = 0; sb < nsteps_max; sb += PF) {
 #pragma unroll
-            for (int u = 0; u < US_PF; ++u) {
+            for (int u = 0; u < PF; ++u) {
                 const int s = sb + u;
                 if (s >= nsteps_max) break;
                 // stage row s (fp32) in line buffer s & 1, refill its register slot with row s + US_PF
@@ -297,10 +321,10 @@ upfirdn2d_stream_kernel(T *__restrict__ out, const T *__restrict__ x, const floa
                 if constexpr (VEC) {
                     float4 *lv = reinterpret_cast<float4 *>(wbase + ((u & 1) * NS + g) * p.line_floats) + t;
 #pragma unroll
-                    for (int i = 0; i < NVF; ++i) lv[WL * i] = prev[u][i];
-                    if (has_last) lv[WL * NVF] = prev[u][NVF];
+                    for (int i = 0; i < NVF; ++i) lv[WL * i] = vec_to_f4(prev[u][i]);
+                    if (has_last) lv[WL * NVF] = vec_to_f4(prev[u][NVF]);
                     __syncwarp();
-                    fetch_vec(s + US_PF, prev[u]);
+                    fetch_vec(s + PF, prev[u]);
                 } else {
 #pragma unroll
                     for (int i = 0; i < G::LS; ++i) lp[WL * i] = Cvt<T>::to_f(pre[u][i]);
@@ -311,7 +335,7 @@ upfirdn2d_stream_kernel(T *__restrict__ out, const T *__restrict__ x, const floa
                             if ((outside >> i) & 1u) lp[WL * i] = 0.f;
                     }
                     __syncwarp();
-                    fetch(s + US_PF, pre[u]);
+                    fetch(s + PF, pre[u]);
                 }
                 float wfull[WRD];
                 load_window<float, WRD, 16>(line + (uint32_t)(t * G::LS * 4), wfull);
@@ -377,30 +401,37 @@ upfirdn2d_stream_kernel(T *__restrict__ out, const T *__restrict__ x, const floa
                     }
                 } else {
                     // UP == 2: input row s sits at up-sampled row Y = y0 + PHY + 2s and feeds tap row a of output row
-                    // Y - a; local row index ol = 2s + 3 - a (0 = y0 + PHY - 3), ring slot ol & 3 = (2u + 3 - a) & 3.
+                    // Y - a: the rows (Y - 1, Y) start here with tap rows (1, 0), the rows (Y - 3, Y - 2) finish with tap rows
+                    // (3, 2) -- and the next input row sees the same two pairs one step older.  The accumulators are kept as
+                    // those ROW PAIRS, so that one packed fma.rn.f32x2 (window value as the broadcast scalar, a pair of taps)
+                    // does the work of two FFMAs: 32 instead of 64 per input row and lane.  Per output the products arrive
+                    // in the order of the scalar form (window columns ascending, taps inside): bit-identical results.
                     // Window element c sits at up-sampled column x0 + PHX + 2c and feeds tap b of output i = 2c + PHX - b.
+                    const int pn = u & 1;                          // pair that starts with this row; pn ^ 1 finishes
+                    float2 vn[G::TX], vo[G::TX];
 #pragma unroll
-                    for (int a = 0; a < 4; ++a) {
-                        const int r = (2 * u + 3 - a) & 3;
-                        float v[G::TX];
+                    for (int i = 0; i < G::TX; ++i) { vn[i] = make_float2(0.f, 0.f); vo[i] = acc2[pn ^ 1][i]; }
 #pragma unroll
-                        for (int i = 0; i < G::TX; ++i) v[i] = a < 2 ? 0.f : acc[r][i];   // a row starts with tap row 0 or 1
+                    for (int c = 0; c < G::WU; ++c)
 #pragma unroll
-                        for (int c = 0; c < G::WU; ++c)
-#pragma unroll
-                            for (int b = 0; b < 4; ++b) {
-                                const int i = 2 * c + PHX - b;
-                                if (i >= 0 && i < G::TX) v[i] = fmaf(w[c], kf[a][b], v[i]);
+                        for (int b = 0; b < 4; ++b) {
+                            const int i = 2 * c + PHX - b;
+                            if (i >= 0 && i < G::TX) {
+                                vn[i] = __ffma2_rn(make_float2(w[c], w[c]), make_float2(kf[1][b], kf[0][b]), vn[i]);
+                                vo[i] = __ffma2_rn(make_float2(w[c], w[c]), make_float2(kf[3][b], kf[2][b]), vo[i]);
                             }
+                        }
 #pragma unroll
-                        for (int i = 0; i < G::TX; ++i) acc[r][i] = v[i];
-                    }
+                    for (int i = 0; i < G::TX; ++i) acc2[pn][i] = vn[i];
                     // finished: tap rows 3 and 2 -> output rows Y - 3 and Y - 2
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         const int oy = y0 + PHY + 2 * s - 3 + h;
+                        float row[G::TX];
+#pragma unroll
+                        for (int i = 0; i < G::TX; ++i) row[i] = h == 0 ? vo[i].x : vo[i].y;
                         if (oy >= y0 && oy < y1 && n_ok > 0)
-                            store_row<T, G::TX>(oplane + (long long)oy * p.out_w + x0, acc[(2 * u + h) & 3], n_ok, p.vec_store != 0);
+                            store_row<T, G::TX>(oplane + (long long)oy * p.out_w + x0, row, n_ok, p.vec_store != 0);
                     }
                 }
             }
@@ -417,6 +448,21 @@ static int launch_stream_vec(void *out, const void *x, const float *taps, const 
         case 2: upfirdn2d_stream_kernel<float, 1, 2, 0, 0, 2, VD><<<grid, US_THREADS, smem, st>>>(o, xi, taps, p); break;
         case 3: upfirdn2d_stream_kernel<float, 1, 2, 0, 0, 3, VD><<<grid, US_THREADS, smem, st>>>(o, xi, taps, p); break;
         default: upfirdn2d_stream_kernel<float, 1, 2, 0, 0, 4, VD><<<grid, US_THREADS, smem, st>>>(o, xi, taps, p); break;
+    }
+    SG2_LAUNCH_CHECK();
+    return SG2_OK;
+}
+
+// 2-byte up-sampling with 8-byte rows, the model's geometry (pad_x0 = 2: the staged line starts 3 elements early)
+template <typename T, int PHY>
+static int launch_stream_vec_up(void *out, const void *x, const float *taps, const UfdStreamParams &p, int grid, size_t smem, cudaStream_t st) {
+    T *o = (T *)out;
+    const T *xi = (const T *)x;
+    switch (p.wl_log2) {
+        case 2: upfirdn2d_stream_kernel<T, 2, 1, 0, PHY, 2, 3><<<grid, US_THREADS, smem, st>>>(o, xi, taps, p); break;
+        case 3: upfirdn2d_stream_kernel<T, 2, 1, 0, PHY, 3, 3><<<grid, US_THREADS, smem, st>>>(o, xi, taps, p); break;
+        case 4: upfirdn2d_stream_kernel<T, 2, 1, 0, PHY, 4, 3><<<grid, US_THREADS, smem, st>>>(o, xi, taps, p); break;
+        default: upfirdn2d_stream_kernel<T, 2, 1, 0, PHY, 5, 3><<<grid, US_THREADS, smem, st>>>(o, xi, taps, p); break;
     }
     SG2_LAUNCH_CHECK();
     return SG2_OK;
@@ -469,6 +515,10 @@ int launch_upfirdn2d_stream(void *out, const void *x, const float *taps, int64_t
         static const char *env_vec = getenv("SG2_UPFIRDN_VEC");         // A/B switch: 0 = element-wise rows
         if (!env_vec || atoi(env_vec) != 0) vd = ((-pad_x0) % 4 + 4) % 4;
     }
+    if (sizeof(T) == 2 && up == 2 && down == 1 && pad_x0 == 2 && in_w % 4 == 0 && reinterpret_cast<uintptr_t>(x) % 16 == 0) {
+        static const char *env_vec = getenv("SG2_UPFIRDN_VEC");
+        if (!env_vec || atoi(env_vec) != 0) vd = 3;                     // cx0 = (0 - 2) / 2 = -1: 3 elements after a multiple of 4
+    }
     p.line_floats = ((WL - 1) * LS + (vd >= 0 ? ((vd + WU + 3) & ~3) : WR) + 3) & ~3;
     p.n_strips = (out_w + TX * WL - 1) / (TX * WL);
     // band height: tall enough to amortise the vertical halo, short enough for >= 4 items per resident group
@@ -497,6 +547,9 @@ int launch_upfirdn2d_stream(void *out, const void *x, const float *taps, int64_t
             case 3: return launch_stream_vec<3>(out, x, taps, p, grid, smem, st);
             default: break;
         }
+    }
+    if constexpr (sizeof(T) == 2) {
+        if (vd == 3) return phy == 0 ? launch_stream_vec_up<T, 0>(out, x, taps, p, grid, smem, st) : launch_stream_vec_up<T, 1>(out, x, taps, p, grid, smem, st);
     }
     if (up == 1 && down == 1) return launch_stream_t<T, 1, 1, 0, 0>(out, x, taps, p, grid, smem, st);
     if (up == 1 && down == 2) return launch_stream_t<T, 1, 2, 0, 0>(out, x, taps, p, grid, smem, st);

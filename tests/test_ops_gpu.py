@@ -154,6 +154,27 @@ def test_upfirdn2d_streaming_low_precision(sg2, oracle, dtype, shape, up, down, 
     np.testing.assert_allclose(y.float().cpu().numpy(), ref.float().numpy(), rtol=0, atol=tol)
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("shape,pad", [((2, 3, 40, 72), (2, 1)), ((1, 2, 33, 256), (2, 2)), ((3, 5, 20, 8), (2, 1)), ((1, 2, 65, 300), (2, 1)),
+                                       ((2, 2, 128, 128), (2, 3)), ((1, 3, 17, 16), (2, 0))])
+def test_upfirdn2d_up2_vector_rows_low_precision(sg2, oracle, dtype, shape, pad):
+    """up-sampling in 2-byte storage with pad_x0 = 2 on planes whose rows are multiples of 8 bytes: rows fetched as 8-byte vectors,
+    6 of them in flight, the staged line starting 3 elements before the strip.  The input is the very end of an allocation that
+    is NaN everywhere else: nothing outside the tensor may be read; both row parities of the padding."""
+    g = torch.Generator().manual_seed(21)
+    n = int(np.prod(shape))
+    big = torch.full((n + 4096 + 8,), float("nan"), device=DEV, dtype=dtype)
+    off = big.numel() - n
+    off -= off % 8
+    x = big[off:off + n].view(shape)
+    x.copy_(torch.randn(shape, generator=g).to(dtype))
+    taps = torch.randn(4, 4, generator=g)
+    y = sg2.upfirdn2d(x, taps.to(DEV), 2, 1, pad)
+    ref = oracle.upfirdn2d(x.cpu().double(), taps.double(), 2, 1, pad)
+    assert y.dtype == dtype and y.shape == ref.shape and torch.isfinite(y.float()).all()
+    np.testing.assert_allclose(y.float().cpu().numpy(), ref.float().numpy(), rtol=0, atol=_tol(dtype) * float(ref.abs().max()))
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("shape,down,pad", [((2, 3, 257, 257), 1, (1, 1)), ((1, 2, 300, 131), 1, (2, 2)), ((3, 4, 17, 17), 1, (1, 1)),
                                             ((2, 3, 256, 256), 2, (1, 1)), ((1, 2, 129, 67), 2, (2, 2)), ((2, 2, 24, 20), 2, (1, 1))])
