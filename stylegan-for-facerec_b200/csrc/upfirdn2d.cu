@@ -310,6 +310,14 @@ extern "C" int sg2_upfirdn2d(void *out, const void *x, const float *kernel, int6
     cudaStream_t st = as_stream(stream);
     const bool sym = up_x == up_y && down_x == down_y && minor == 1 && kh <= 4 && kw <= 4;
     SG2_DISPATCH_DTYPE(dtype, {
+        if (sym && sizeof(T) == 2) {   // 2-byte storage, blur / down-2 (planes from 16 outputs wide when there are thousands): packed-math kernel (upfirdn2d_pk.cu); 1 = not applicable
+            const char *env_pk = getenv("SG2_UPFIRDN_PK");                // A/B switch (read per call): 0 = off
+            if (!env_pk || atoi(env_pk) != 0) {
+                const int rc = launch_upfirdn2d_pk<T>(out, x, kernel, major, in_h, in_w, out_h, out_w, kh, kw, up_x, down_x,
+                                                      pad_x0, pad_y0, st);
+                if (rc <= 0) return rc;
+            }
+        }
         if (sym) {   // many small planes (the 4^2 .. 32^2 octaves): batches of whole planes per CTA (upfirdn2d_planes.cu); 1 = not applicable
             const char *env_pl = getenv("SG2_UPFIRDN_PLANES");            // A/B switch (read per call): 0 = off
             if (!env_pl || atoi(env_pl) != 0) {
@@ -328,14 +336,6 @@ extern "C" int sg2_upfirdn2d(void *out, const void *x, const float *kernel, int6
             upfirdn2d_small_kernel<T><<<blocks, 256, 0, st>>>((T *)out, (const T *)x, kernel, p);
             SG2_LAUNCH_CHECK();
             return SG2_OK;
-        }
-        if (sym && sizeof(T) == 2) {   // 2-byte storage, blur / down-2: packed-math kernel (upfirdn2d_pk.cu); 1 = not applicable
-            const char *env_pk = getenv("SG2_UPFIRDN_PK");                // A/B switch (read per call): 0 = off
-            if (!env_pk || atoi(env_pk) != 0) {
-                const int rc = launch_upfirdn2d_pk<T>(out, x, kernel, major, in_h, in_w, out_h, out_w, kh, kw, up_x, down_x,
-                                                      pad_x0, pad_y0, st);
-                if (rc <= 0) return rc;
-            }
         }
         if (sym) {   // the three model geometries: row-streaming TMA kernel (upfirdn2d_stream.cu); 1 = not applicable
             static const char *env_tiled = getenv("SG2_UPFIRDN_TILED");     // A/B switch: force the tiled kernels

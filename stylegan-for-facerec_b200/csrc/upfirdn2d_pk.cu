@@ -177,9 +177,9 @@ __device__ __forceinline__ void pk_store_row(T *dst, const float2 (&v)[N / 2], b
 //   8       q = position of the row in a batch of 8 (in_w = 1 mod 8: the 2^k + 1 wide blur inputs; the first batch of a
 //           band starts q0 slots in, so that the row with alignment q sits at position q)
 // In the static modes the unpack code is straight-line and the compiler interleaves it with the FMAs.
-template <int QS> struct PkMode { static constexpr int BATCH = QS == 8 ? 8 : 4, RB = QS == 8 ? 2 : 3; };
+template <int QS, int NS> struct PkMode { static constexpr int BATCH = QS == 8 ? 8 : 4, RB = (QS == 8 || NS >= 16) ? 2 : 3; };   // (16 groups per warp: a shorter ring fits 48 KiB)
 
-// WLOG2: lanes per group (log2, >= 2).  TX outputs per lane; every lane consumes 8 input elements (one chunk) per row.
+// WLOG2: lanes per group (log2, >= 1).  TX outputs per lane; every lane consumes 8 input elements (one chunk) per row.
 template <typename T, int DOWN, int WLOG2, int QS>
 __global__ void __launch_bounds__(PK_THREADS, PK_CTAS)
 upfirdn2d_pk_kernel(T *__restrict__ out, const float *__restrict__ taps, const UfdPkParams p) {
@@ -190,7 +190,7 @@ upfirdn2d_pk_kernel(T *__restrict__ out, const float *__restrict__ taps, const U
     constexpr int SLOT = NS * GB;
     constexpr int NP = DOWN == 1 ? 10 : 8;
     constexpr int R = DOWN == 1 ? 4 : 2;                           // output rows in flight
-    constexpr int BATCH = PkMode<QS>::BATCH, RB = PkMode<QS>::RB;  // rows per barrier / prefetch round, rounds in the ring
+    constexpr int BATCH = PkMode<QS, NS>::BATCH, RB = PkMode<QS, NS>::RB;  // rows per barrier / prefetch round, rounds in the ring
     constexpr int RING = RB * BATCH * SLOT;
     extern __shared__ __align__(16) unsigned char pk_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -356,10 +356,8 @@ upfirdn2d_pk_kernel(T *__restrict__ out, const float *__restrict__ taps, const U
         const int t_last = (min(WL * TX, p.out_w - it.xs0) - 1) / TX;              // last lane with outputs
         const int n_left = max(0, -it.cx0), pos_r = max(n_left, p.in_w - it.cx0);
         const int n_right = max(0, 8 * t_last + WU - pos_r);
-        int fix0 = -1, fix1 = -1;                                  // byte offsets of this lane's positions
-        if (t < n_left) fix0 = 2 * t;
-        else if (t - n_left < n_right) fix0 = 2 * (pos_r + t - n_left);
-        if (t + WL - n_left < n_right) fix1 = 2 * (pos_r + t + WL - n_left);       // WL >= 4 > n_left
+        auto fixpos = [&](int j) { return j < n_left ? 2 * j : (j - n_left < n_right ? 2 * (pos_r + j - n_left) : -1); };
+        const int fix0 = fixpos(t), fix1 = fixpos(t + WL);         // byte offsets of this lane's positions; 2 WL >= n_left + n_right (host check)
         const bool any_fix = n_left + n_right > 0;                 // warp-uniform
 
         float2 acc[R][TX / 2];
@@ -496,7 +494,7 @@ static bool pk_debug() {
 template <typename T, int DOWN, int WLOG2, int QS>
 static int pk_launch_t(void *out, const float *taps, const UfdPkParams &p, int grid, cudaStream_t st) {
     constexpr int WL = 1 << WLOG2, NS = 32 >> WLOG2;
-    constexpr size_t smem = (size_t)PK_WARPS * (PkMode<QS>::RB * PkMode<QS>::BATCH * NS * (WL + 2) * 16 + 512);
+    constexpr size_t smem = (size_t)PK_WARPS * (PkMode<QS, NS>::RB * PkMode<QS, NS>::BATCH * NS * (WL + 2) * 16 + 512);
     static_assert(smem <= 48 * 1024, "dynamic shared memory without the opt-in attribute");
     upfirdn2d_pk_kernel<T, DOWN, WLOG2, QS><<<grid, PK_THREADS, smem, st>>>((T *)out, taps, p);
     SG2_LAUNCH_CHECK();
@@ -506,6 +504,9 @@ static int pk_launch_t(void *out, const float *taps, const UfdPkParams &p, int g
 template <typename T, int DOWN, int QS>
 static int pk_launch_w(int wl, void *out, const float *taps, const UfdPkParams &p, int grid, cudaStream_t st) {
     switch (wl) {
+        case 1:
+            if constexpr (QS != 8) return pk_launch_t<T, DOWN, 1, QS>(out, taps, p, grid, st);
+            else return 1;
         case 2:
             if constexpr (QS != 8) return pk_launch_t<T, DOWN, 2, QS>(out, taps, p, grid, st);
             else return 1;
@@ -526,12 +527,12 @@ int launch_upfirdn2d_pk(void *out, const void *x, const float *taps, int64_t pla
         if (up != 1 || (down != 1 && down != 2) || kh > 4 || kw > 4) return 1;
         if (reinterpret_cast<uintptr_t>(x) % 16 != 0) return 1;
         const int TX = down == 1 ? 8 : 4, WU = down == 1 ? 11 : 10;
-        if (out_w <= 2 * TX || out_h < 8 || pad_x0 > 3) return 1;     // small planes: upfirdn2d_planes.cu / the streaming kernel
-        int wl = 2;
+        if (out_w <= TX || out_h < 8 || pad_x0 > 3) return 1;         // small planes: upfirdn2d_planes.cu / the streaming kernel
+        int wl = 1;
         while ((TX << wl) < out_w && wl < 5) ++wl;
         const int WL = 1 << wl, NS = 32 >> wl;
-        // 4 lanes per strip (planes up to 32 / 16 outputs wide): only as 8 planes per warp, many planes
-        if (wl == 2 && planes < (int64_t)8 * NS * sm_count()) return 1;
+        // 2 / 4 lanes per strip (planes up to 16 / 32 outputs wide; half that for down-2): only as 16 / 8 planes per warp, many planes
+        if (wl <= 2 && planes < (int64_t)8 * NS * sm_count()) return 1;
         // the kernel zeroes at most 3 + 12 staged positions per row and group (see there): every strip must fit
         for (int xs0 = 0; xs0 < out_w; xs0 += WL * TX) {
             const int cx0 = down * xs0 - pad_x0, t_last = (std::min(WL * TX, out_w - xs0) - 1) / TX;
@@ -563,7 +564,7 @@ int launch_upfirdn2d_pk(void *out, const void *x, const float *taps, int64_t pla
         p.by_planes = NS > 1 && planes >= (int64_t)8 * NS * sms;
         {
             const char *e = getenv("SG2_UPFIRDN_PK_BYPLANES");        // A/B switch (read per call)
-            if (e) p.by_planes = NS > 1 && (atoi(e) != 0 || wl == 2);
+            if (e) p.by_planes = NS > 1 && (atoi(e) != 0 || wl <= 2);
         }
         const int64_t plane_slots = p.by_planes ? (planes + 8 * NS - 1) / (8 * NS) * 8 : planes;
         const int gb = p.by_planes ? 1 : NS;                         // bands of one plane walked side by side

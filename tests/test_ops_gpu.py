@@ -206,6 +206,7 @@ PK_SHAPES = [
     (3, 40, 65), (2, 65, 66), (3, 17, 67), (2, 130, 69), (3, 40, 71), (5, 129, 129), (2, 65, 131), (3, 40, 200), (2, 257, 257),
     (3, 65, 258), (2, 40, 261), (1, 130, 300), (1, 513, 513), (2, 64, 520), (1, 70, 1025), (4, 256, 256), (37, 64, 64), (13, 33, 129),
     (9500, 33, 33), (9473, 17, 40),         # 4 lanes per strip: only with thousands of planes (8 planes per warp)
+    (19000, 17, 17), (18950, 9, 20),        # 2 lanes per strip (16 planes per warp)
 ]
 
 

@@ -43,7 +43,7 @@ def main():
             shapes.append((3, h, w))
     if args.quick:
         shapes = [(2, 17, 65), (1, 40, 131), (2, 65, 259)]
-    shapes += [(9500, 33, 33), (9473, 17, 40), (2, 257, 257), (1, 513, 513), (1, 1025, 1025), (5, 129, 129), (4, 300, 131), (1, 1030, 70), (2, 64, 520)]
+    shapes += [(19000, 17, 17), (18950, 9, 20), (9500, 33, 33), (9473, 17, 40), (2, 257, 257), (1, 513, 513), (1, 1025, 1025), (5, 129, 129), (4, 300, 131), (1, 1030, 70), (2, 64, 520)]
     for dtype in (() if args.perf_only else (torch.bfloat16, torch.float16)):
         for (pl, h, w) in shapes:
             for down, pad, k in ((1, (1, 1), 4), (1, (2, 2), 4), (1, (0, 2), 3), (1, (3, 0), 4), (1, (-1, 1), 4), (2, (1, 1), 4), (2, (2, 2), 4), (2, (0, 1), 4),
@@ -109,7 +109,7 @@ def main():
         taps = (sg2.make_kernel([1, 3, 3, 1]) * 4).to(DEV)
         flush = torch.zeros(256 << 20, dtype=torch.uint8, device=DEV)
         for dtype in ((torch.bfloat16,) if args.perf_only else (torch.bfloat16, torch.float16)):
-            for r, c in (((256, 128),) if args.perf_only else ((32, 512), (64, 512), (128, 256), (256, 128), (512, 64), (1024, 32))):
+            for r, c in (((256, 128),) if args.perf_only else ((16, 512), (32, 512), (64, 512), (128, 256), (256, 128), (512, 64), (1024, 32))):
                 B = max(1, (1 << 28) // (c * r * r))
                 for op, down, pad, shape in (("blur", 1, (1, 1), (B, c, r + 1, r + 1)), ("down2", 2, (1, 1), (B, c, r, r))):
                     x = torch.randn(shape, device=DEV, dtype=dtype)
