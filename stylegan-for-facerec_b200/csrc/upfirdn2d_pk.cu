@@ -43,6 +43,9 @@ using namespace tc;
 #endif                           // 1 no FMAs, 2 no global stores, 4 no global -> shared copies, 8 unpack case 0 only
 constexpr int PK_WARPS = 4;      // small CTAs: five of them fit the register file (<= 96 registers per thread) = 20 warps per SM
 constexpr int PK_THREADS = 32 * PK_WARPS;
+#ifndef PK_RB_N
+#define PK_RB_N 3                // batches in the ring (modes with 4-row batches, up to 4 groups per warp)
+#endif
 #ifndef PK_CTAS_N
 #define PK_CTAS_N 5
 #endif
@@ -177,7 +180,7 @@ __device__ __forceinline__ void pk_store_row(T *dst, const float2 (&v)[N / 2], b
 //   8       q = position of the row in a batch of 8 (in_w = 1 mod 8: the 2^k + 1 wide blur inputs; the first batch of a
 //           band starts q0 slots in, so that the row with alignment q sits at position q)
 // In the static modes the unpack code is straight-line and the compiler interleaves it with the FMAs.
-template <int QS, int NS> struct PkMode { static constexpr int BATCH = QS == 8 ? 8 : 4, RB = (QS == 8 || NS >= 16) ? 2 : 3; };   // (16 groups per warp: a shorter ring fits 48 KiB)
+template <int QS, int NS> struct PkMode { static constexpr int BATCH = QS == 8 ? 8 : 4, RB = (QS == 8 || NS >= 16) ? 2 : (NS <= 4 ? PK_RB_N : 3); };   // (16 groups per warp: a shorter ring fits 48 KiB)
 
 // WLOG2: lanes per group (log2, >= 1).  TX outputs per lane; every lane consumes 8 input elements (one chunk) per row.
 template <typename T, int DOWN, int WLOG2, int QS>
