@@ -77,10 +77,53 @@ class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
+    NVML_REASONS = (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown"), ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown"),
+                    ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown"), ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap"),
+                    ("hw_power_brake_slowdown", "nvmlClocksEventReasonHwPowerBrakeSlowdown"), ("gpu_idle", "nvmlClocksEventReasonGpuIdle"),
+                    ("applications_clocks_setting", "nvmlClocksEventReasonApplicationsClocksSetting"), ("sync_boost", "nvmlClocksEventReasonSyncBoost"))
+
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.extra, self.source, self._stop = set(), "nvidia-smi -lms 50", False
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:                       # the CUDA ordinal is not the NVML index under CUDA_VISIBLE_DEVICES: go by PCI address
+            pr = torch.cuda.get_device_properties(self.index)
+            return pynvml, pynvml.nvmlDeviceGetHandleByPciBusId(f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0")
+        except Exception:
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.index)
+
+    def _nvml_loop(self, nv, h):
+        """the same quantities as the nvidia-smi query, read through NVML every ~2 ms: a 0.1 s timed region gets tens of
+        samples instead of two or three, and every active clock-event reason is seen, not only the ones sampled by chance"""
+        mx = str(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        reasons = [(name, getattr(nv, attr)) for name, attr in self.NVML_REASONS if hasattr(nv, attr)]
+        while not self._stop:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+            except Exception:
+                break
+            act = {name for name, bit in reasons if mask & bit}
+            flag = lambda n: "Active" if n in act else "Not Active"
+            self.rows.append((time.perf_counter(), [str(self.index), str(sm), mx, f"{pw:.2f}", hex(mask), flag("hw_slowdown"),
+                                                    flag("hw_thermal_slowdown"), flag("sw_thermal_slowdown"), flag("sw_power_cap"),
+                                                    ",".join(sorted(act - {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"}))]))
+            time.sleep(0.002)
 
     def start(self):
+        if os.environ.get("SG2_BENCH_CLOCKS", "nvml") == "nvml":
+            try:
+                nv, h = self._nvml_handle()
+                nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                self.proc, self.source = "nvml", "NVML, 2 ms period"
+                threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True).start()
+                return self
+            except Exception:
+                self.proc = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
@@ -105,8 +148,12 @@ class ClockSampler:
     def stop(self, t_begin=None, t_end=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.12)
-        self.proc.terminate()
+        if self.proc == "nvml":
+            time.sleep(0.01)
+            self._stop = True
+        else:
+            time.sleep(0.12)
+            self.proc.terminate()
         return self.summary(t_begin, t_end)
 
     def summary(self, t_begin=None, t_end=None):
@@ -123,10 +170,13 @@ class ClockSampler:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
                 if v.lower() == "active":
                     reasons.add(name)
+            if len(r) > 9 and r[9]:                    # NVML sampler: the other clock-event reasons that were active
+                reasons.update(r[9].split(","))
         mx = [int(r[2]) for r in rows if r[2].isdigit()]
         pw = [float(r[3]) for r in rows if r[3].replace(".", "").isdigit()]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "sm_mhz_min": sm[0] if sm else None, "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons),
+                "source": self.source}
 
 
 def make_generator(sg2, size, device, precision):
