@@ -182,11 +182,14 @@ modconv_simt_big_kernel(T *__restrict__ out, const T *__restrict__ x, const floa
         sty[j] = style ? style + (int64_t)sb * g.Cin : nullptr;
     }
 
-    float acc[8][8];
+    // accumulators as pairs of adjacent columns: one fma.rn.f32x2 (weight value as the broadcast scalar, a pair of
+    // activations straight out of the 16-byte shared load) does the work of two FFMAs -- half the issue slots for the same
+    // fused multiply-adds in the same order (the kernel issued 72 instructions per 64 FMAs: issue-bound before the FP32 pipe)
+    float2 acc[8][4];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+        for (int j = 0; j < 4; ++j) acc[i][j] = make_float2(0.f, 0.f);
     __syncthreads();                       // tap table
 
     for (int ci0 = 0; ci0 < g.Cin; ci0 += KC) {
@@ -233,7 +236,7 @@ modconv_simt_big_kernel(T *__restrict__ out, const T *__restrict__ x, const floa
 #pragma unroll
             for (int i = 0; i < 8; ++i)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+                for (int j = 0; j < 4; ++j) acc[i][j] = __ffma2_rn(make_float2(a[i], a[i]), make_float2(b[2 * j], b[2 * j + 1]), acc[i][j]);
         }
     }
 
@@ -249,7 +252,7 @@ modconv_simt_big_kernel(T *__restrict__ out, const T *__restrict__ x, const floa
         for (int i = 0; i < 8; ++i) {
             const int co = co0 + (i < 4 ? ty * 4 + i : BM / 2 + ty * 4 + (i - 4));
             if (co >= g.Cout) continue;
-            float v = acc[i][j];
+            float v = (j & 1) ? acc[i][j >> 1].y : acc[i][j >> 1].x;
             if (demod) v *= __ldg(demod + (int64_t)b * g.Cout + co);
             out[(((int64_t)b * g.Cout + co) * g.OH + oy) * g.OW + ox] = Cvt<T>::from_f(v);
         }
@@ -342,11 +345,14 @@ modconv_simt_pipe_kernel(float *__restrict__ out, const float *__restrict__ x, c
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
-    float acc[8][8];
+    // accumulators as pairs of adjacent columns: one fma.rn.f32x2 (weight value as the broadcast scalar, a pair of
+    // activations straight out of the 16-byte shared load) does the work of two FFMAs -- half the issue slots for the same
+    // fused multiply-adds in the same order (the kernel issued 72 instructions per 64 FMAs: issue-bound before the FP32 pipe)
+    float2 acc[8][4];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+        for (int j = 0; j < 4; ++j) acc[i][j] = make_float2(0.f, 0.f);
 
     const int nchunks = g.Cin / KC;
     issue(0, 0);
@@ -382,7 +388,7 @@ modconv_simt_pipe_kernel(float *__restrict__ out, const float *__restrict__ x, c
 #pragma unroll
             for (int i = 0; i < 8; ++i)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+                for (int j = 0; j < 4; ++j) acc[i][j] = __ffma2_rn(make_float2(a[i], a[i]), make_float2(b[2 * j], b[2 * j + 1]), acc[i][j]);
         }
         __syncthreads();                                   // chunk c consumed: its buffer may be refilled
     }
@@ -396,7 +402,7 @@ modconv_simt_pipe_kernel(float *__restrict__ out, const float *__restrict__ x, c
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int co = co0 + (i < 4 ? ty * 4 + i : BM / 2 + ty * 4 + (i - 4));
-            float v = acc[i][j];
+            float v = (j & 1) ? acc[i][j >> 1].y : acc[i][j >> 1].x;
             if (demod) v *= __ldg(demod + (int64_t)sb * g.Cout + co);
             out[(((int64_t)sb * g.Cout + co) * g.OH + oy) * g.OW + ox] = v;
         }
