@@ -83,6 +83,21 @@ def modulation(latent, mod_weight, mod_bias, wsq, cout, mod_scale, lr_mul, demod
     return style, demod
 
 
+def rgb_modconv(x, style, w2):
+    """ToRGB's modulated 1x1 convolution without demodulation (model.py:350-355), no autograd: y[b,k] = sum_c w2[k,c] *
+    style[b,c] * x[b,c] in one pass over the activation (csrc/torgb.cu, fp32 math); w2 [K,C] with the conv scale folded in."""
+    _lib.require_cuda(x)
+    x = x.contiguous()
+    B, C, H, W = x.shape
+    Kn = w2.shape[0]
+    wf, sf = w2.detach().float().contiguous(), style.detach().float().contiguous()
+    y = torch.empty((B, Kn, H, W), device=x.device, dtype=x.dtype)
+    with _lib.device_of(x):
+        _lib.check(_lib.load().sg2_rgb_modconv_fwd(y.data_ptr(), x.data_ptr(), wf.data_ptr(), sf.data_ptr(), B, C, Kn, H * W,
+                                                   _lib.dtype_code(x), _lib.stream_of(x)), "rgb_modconv_fwd")
+    return y
+
+
 def conv_out_hw(h, w, k, mode):
     if mode == 0:
         return h, w

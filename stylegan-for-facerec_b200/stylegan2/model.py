@@ -196,8 +196,12 @@ class ModulatedConv2d(nn.Module):
         if self.kernel_size not in (1, 3):
             raise RuntimeError(f"sg2_b200 ModulatedConv2d: kernel_size {self.kernel_size} not in (1, 3)")
         w4 = self.weight[0]
-        wt, wsq = K.conv_prep(w4.to(input.dtype), self.scale, want_wsq=self.demodulate)
         mod = self.modulation
+        if self.kernel_size == 1 and self._mode == 0 and not self.demodulate and self.out_channel <= 4 and self.in_channel <= 1024:
+            # ToRGB: one HBM-bound pass over the activation (the implicit-GEMM tile would be 3 rows of 64 tall)
+            s, _ = K.modulation(style.to(input.dtype), mod.weight, mod.bias, None, self.out_channel, mod.scale, mod.lr_mul, False)
+            return K.rgb_modconv(input, s, w4.reshape(self.out_channel, self.in_channel).float() * self.scale)
+        wt, wsq = K.conv_prep(w4.to(input.dtype), self.scale, want_wsq=self.demodulate)
         s, d = K.modulation(style.to(input.dtype), mod.weight, mod.bias, wsq, self.out_channel, mod.scale,
                             mod.lr_mul, self.demodulate)
         if self.downsample:
