@@ -449,7 +449,7 @@ upfirdn2d_pk_kernel(T *__restrict__ out, const float *__restrict__ taps, const U
                     }
                     // finished: output row y0 + s - 3
                     const bool in_band = (unsigned)(s - 3) < (unsigned)nrows;
-                    pk_store_row<T, 8>(orow, acc[(u + 1) & 3], in_band && vec_ok && !(PK_KO & 2), in_band && !(PK_KO & 2) ? n_part : 0);
+                    pk_store_row<T, 8>(orow, acc[(u + 1) & 3], in_band && vec_ok && !((PK_KO & 2) && p.out_h > 0), in_band && !((PK_KO & 2) && p.out_h > 0) ? n_part : 0);
                     orow += p.out_w;
                 } else {
                     // input row s is tap row a = (s & 1), (s & 1) + 2 of output row (s - a) / 2; output pair ip = columns
@@ -472,7 +472,7 @@ upfirdn2d_pk_kernel(T *__restrict__ out, const float *__restrict__ taps, const U
                     }
                     if (e == 1) {                                  // tap row 3 done: output row (s - 3) / 2 is finished
                         const bool in_band = (unsigned)((s - 3) >> 1) < (unsigned)nrows;   // s = 1: -1 -> out of range
-                        pk_store_row<T, 4>(orow, acc[((u - 3 + 8) / 2) & 1], in_band && vec_ok && !(PK_KO & 2), in_band && !(PK_KO & 2) ? n_part : 0);
+                        pk_store_row<T, 4>(orow, acc[((u - 3 + 8) / 2) & 1], in_band && vec_ok && !((PK_KO & 2) && p.out_h > 0), in_band && !((PK_KO & 2) && p.out_h > 0) ? n_part : 0);
                         orow += p.out_w;
                     }
                 }
