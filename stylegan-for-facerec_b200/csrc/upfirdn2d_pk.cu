@@ -7,25 +7,28 @@
 //
 // Why a second kernel.  In 2-byte storage the blur moves 4 bytes per output and spends 16 multiply-adds on it: at the
 // HBM roofline (6.55 TB/s measured) that is 26e12 FMA/s, 85 % of what the FP32 pipe delivers (tools/probes/ffma_probe.cu:
-// 31e12 FMA/s with three register operands, the same through fma.rn.f32x2).  The row-streaming kernel issued 34
-// instructions per output (scalar FFMA + scalar 2-byte loads + fp32 staging) and stopped at 0.46 (blur) / 0.34 (down-2)
-// of the roofline, issue-bound.  Here
-//   * the multiply-adds are fma.rn.f32x2 over pairs of adjacent outputs (SASS FFMA2 with the tap as a broadcast scalar
-//     operand): 8 issue slots per output instead of 16, which leaves room for everything else beside a busy FMA pipe;
+// 30-35e12 FMA/s through FFMA and through fma.rn.f32x2 alike).  The row-streaming kernel issued 34 instructions per
+// output (scalar FFMA + scalar 2-byte loads + fp32 staging) and stopped at 0.46 (blur) / 0.34 (down-2) of the roofline.  Here
+//   * the multiply-adds are fma.rn.f32x2 over pairs of adjacent outputs (SASS FFMA2, the tap as a broadcast scalar operand
+//     out of a uniform register): 8 issue slots per output instead of 16; outer-product taps (what make_kernel builds; decided
+//     on the device) take a separable blur -- 4 issue slots per output, within one ulp of the storage type of the 16-tap order;
 //   * rows travel HBM -> shared memory as aligned 16-byte cp.async chunks, whatever the row pitch (a 257-wide bf16 row is
 //     514 bytes: no TMA tile, no vector load can start on it): the chunk grid is anchored at the 16-byte boundary below
-//     the row segment, so the segment starts q = 0..7 elements into its first chunk; q is warp-uniform, advances by
-//     in_w mod 8 per row, and a switch on it picks one of eight fully unrolled unpack sequences (register renaming, no
-//     shifts): two 16-byte shared loads + 20 conversions per lane and row, no staging stores at all;
-//   * copies run PK_D - 1 rows ahead per warp and the prefetch cursor walks across work items, so a warp that finishes a
-//     band already has the first rows of its next one in flight;
-//   * zero padding: rows outside the plane are zero-filled by the copy itself (src-size 0), columns outside the plane
-//     are zeroed in shared memory by the one or two lanes that own them; over-reads never leave the tensor (chunks
-//     that would are clamped / zero-filled -- the last 2..14 bytes of a tensor included).
+//     the row segment, so the segment starts q = 0..7 elements into its first chunk; q is warp-uniform and advances by
+//     in_w mod 8 per row.  A lane reads its window with two 16-byte shared loads and unpacks it with one conversion per
+//     pair half; which of the eight unpack sequences applies is known statically where the geometry allows (template
+//     parameter QS below), else an eight-way switch per row;
+//   * copies, the zero-padding fix-up and the warp barrier happen once per BATCH of 4 or 8 rows, a ring of 2-3 batches per
+//     warp; the prefetch cursor walks across work items, so a warp that finishes a band already has the first rows of its
+//     next one in flight;
+//   * zero padding: rows outside the plane are zero-filled by the copy itself (cp.async ignore-src), columns outside the
+//     plane are zeroed in shared memory by the lanes of the group (at most 15 staged positions); over-reads never leave
+//     the tensor (chunks that would are clamped / zero-filled -- the last 2..14 bytes of a tensor included).
 //
-// Work split: a group of WL = 4..32 lanes owns a strip of WL * TX output columns (TX = 8 blur, 4 down-2: 8 input
-// elements = one chunk per lane and row either way) and walks down a band of rh rows; the 32 / WL groups of a warp take
-// consecutive bands of the SAME plane and strip, rh a multiple of 8, so that every group sees the same q.
+// Work split: a group of WL = 2..32 lanes owns a strip of WL * TX output columns (TX = 8 blur, 4 down-2: 8 input elements
+// = one chunk per lane and row either way) and walks down a band of rh rows; the 32 / WL groups of a warp take consecutive
+// bands of the SAME plane and strip (rh a multiple of 8, so that every group sees the same q) or, with thousands of narrow
+// planes, the same band of the planes P, P + 8, P + 16, ... (eight planes apart the alignment is the same again).
 #include <stdlib.h>
 
 #include <algorithm>
@@ -51,11 +54,10 @@ constexpr int PK_THREADS = 32 * PK_WARPS;
 #endif
 constexpr int PK_CTAS = PK_CTAS_N;
 
-
 struct UfdPkParams {
     int in_h, in_w, out_h, out_w;
     int pad_x0, pad_y0, kh, kw;
-    int rh;                   // output rows per band, multiple of 8
+    int rh;                   // output rows per band (a multiple of 8 when the groups of a warp are bands of one plane)
     int n_strips, n_sbands;   // super-band = the 32 / WL bands one warp walks side by side
     long long planes, items;  // items = planes * n_sbands * n_strips (strip fastest)
     unsigned long long xb, xe;   // first byte of the input tensor (16-byte aligned) / one past its last byte
