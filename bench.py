@@ -401,17 +401,23 @@ def roofline_of(ctx, table, size, B):
     return roofline
 
 
+def make_latents(n_batches, B, rank, size):
+    """[n_batches, B, STYLE_DIM] synthetic latents of one rank: every rank gets its own shard ...
+    ... except sample 0 of every batch, which is the same on every rank: the parity check recomputes sample 0 of the last timed
+    batch on the exact path and ABORTS above a tolerance set from its measured error (tests/test_bench_configs_gpu.py); the bf16
+    error of a random latent spreads over 0.5 - 1.9e-2 of |ref|max (median 0.9e-2, profiles/engine_error_spread_r02.json), so a
+    rank-dependent sample made the abort a lottery at N = 8.  Sample 1 (rank-specific) is reported beside it, not judged."""
+    gen = torch.Generator().manual_seed(1234 + rank + 7919 * size)
+    z = torch.randn(n_batches, B, STYLE_DIM, generator=gen)
+    z[:, 0] = torch.randn(n_batches, STYLE_DIM, generator=torch.Generator().manual_seed(1234 + 7919 * size))
+    return z
+
+
 def measure(ctx, size, B, K, W, precision, profile_out=None, fp32_e2e=True):
     """value / e2e / roofline / clocks / parity / per-rank step times of ONE configuration"""
     sg2, dev, world, rank = ctx.sg2, ctx.dev, ctx.world, ctx.rank
     G = make_generator(sg2, size, dev, precision)
-    gen = torch.Generator().manual_seed(1234 + rank + 7919 * size)          # every rank gets its own shard of latents
-    z_host = torch.randn(K + W, B, STYLE_DIM, generator=gen)
-    # ... except sample 0 of every batch, which is the same on every rank: the parity check below recomputes sample 0 of the last
-    # timed batch on the exact path and ABORTS above a tolerance set from its measured error (tests/test_bench_configs_gpu.py);
-    # the bf16 error of a random latent spreads over 0.5 - 1.9e-2 of |ref|max (median 0.9e-2) (profiles/engine_error_spread_r02.json), so a
-    # rank-dependent sample made the abort a lottery at N = 8.  Sample 1 (rank-specific) is reported beside it, not judged.
-    z_host[:, 0] = torch.randn(K + W, STYLE_DIM, generator=torch.Generator().manual_seed(1234 + 7919 * size))
+    z_host = make_latents(K + W, B, rank, size)
     z_host = z_host.pin_memory()
     z_dev = z_host.to(dev)
 

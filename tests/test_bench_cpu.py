@@ -42,3 +42,15 @@ def test_reference_arm_under_torchrun_prints_once():
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0
+
+
+def test_parity_sample_is_the_same_on_every_rank():
+    """bench.py judges sample 0 of the last timed batch against the exact path with a tolerance set from that sample's measured
+    error: it has to be the same latent on every rank (a rank-specific one aborted the 8-GPU run), the rest of the batch must not be"""
+    import torch
+    import bench
+    z0, z5 = bench.make_latents(6, 4, 0, 256), bench.make_latents(6, 4, 5, 256)
+    assert z0.shape == (6, 4, bench.STYLE_DIM)
+    assert torch.equal(z0[:, 0], z5[:, 0])
+    assert not torch.equal(z0[:, 1:], z5[:, 1:])
+    assert not torch.equal(bench.make_latents(6, 4, 0, 1024)[:, 0], z0[:, 0])
