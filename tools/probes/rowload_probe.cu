@@ -12,8 +12,8 @@ constexpr int WARPS = 4, BATCH = 8, RB = 2, ROWB = 34 * 16;   // 34 chunks cover
 
 __device__ __forceinline__ uint32_t s32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-template <int MODE>
-__global__ void __launch_bounds__(32 * WARPS, 5) k_rows(const uint16_t *x, long long planes, int in_h, int in_w, unsigned *sink) {
+template <int MODE, int WR = 0>      // WR: the store pattern beside the loads -- 0 none, 1 down-2 (8 bytes per lane every second row), 2 blur (16 bytes per lane and row)
+__global__ void __launch_bounds__(32 * WARPS, 5) k_rows(const uint16_t *x, long long planes, int in_h, int in_w, unsigned *sink, uint16_t *y = nullptr) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char *ring = smem + warp * (RB * BATCH * ROWB + 64);
@@ -74,6 +74,17 @@ __global__ void __launch_bounds__(32 * WARPS, 5) k_rows(const uint16_t *x, long 
                 phase ^= 1 << slot;
             }
             acc += *reinterpret_cast<const unsigned *>(ring + (slot * BATCH + (b & 7)) * ROWB + 16 * lane);   // touch the batch
+            if (WR == 1) {          // output plane 128 x 128: rows 4 b .. 4 b + 3 of it from this batch of 8 input rows
+                for (int j = 0; j < 4; ++j) {
+                    const int oy = 4 * b + j;
+                    if (oy < 128) *reinterpret_cast<uint2 *>(y + (plane * 128 + oy) * 128 + 4 * lane) = make_uint2(acc, acc + j);
+                }
+            } else if (WR == 2) {   // output plane 256 x 256: rows 8 b .. 8 b + 7
+                for (int j = 0; j < 8; ++j) {
+                    const int oy = 8 * b + j;
+                    if (oy < 256) *reinterpret_cast<uint4 *>(y + (plane * 256 + oy) * 256 + 8 * lane) = make_uint4(acc, acc + j, acc, acc);
+                }
+            }
             __syncwarp();
             slot = nslot;
         }
@@ -81,21 +92,21 @@ __global__ void __launch_bounds__(32 * WARPS, 5) k_rows(const uint16_t *x, long 
     if (acc == 0x12345678u) *sink = acc;
 }
 
-template <int MODE>
-static void run(const char *name, const uint16_t *x, long long planes, int h, int w, unsigned *sink) {
+template <int MODE, int WR = 0>
+static void run(const char *name, const uint16_t *x, long long planes, int h, int w, unsigned *sink, uint16_t *y = nullptr) {
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
     const size_t smem = WARPS * (RB * BATCH * ROWB + 64);
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
-    for (int i = 0; i < 2; ++i) k_rows<MODE><<<sms * 5, 32 * WARPS, smem>>>(x, planes, h, w, sink);
+    for (int i = 0; i < 2; ++i) k_rows<MODE, WR><<<sms * 5, 32 * WARPS, smem>>>(x, planes, h, w, sink, y);
     cudaEventRecord(e0);
-    for (int i = 0; i < 5; ++i) k_rows<MODE><<<sms * 5, 32 * WARPS, smem>>>(x, planes, h, w, sink);
+    for (int i = 0; i < 5; ++i) k_rows<MODE, WR><<<sms * 5, 32 * WARPS, smem>>>(x, planes, h, w, sink, y);
     cudaEventRecord(e1);
     cudaEventSynchronize(e1);
     float ms;
     cudaEventElapsedTime(&ms, e0, e1);
-    const double bytes = 2.0 * planes * h * w * 5;
+    const double bytes = (2.0 * planes * h * w + (WR == 1 ? 2.0 * planes * 128 * 128 : WR == 2 ? 2.0 * planes * 256 * 256 : 0.0)) * 5;
     printf("%-28s %.3f ms per pass, %.2f TB/s (%s)\n", name, ms / 5, bytes / (ms * 1e-3) * 1e-12, cudaGetErrorString(cudaGetLastError()));
 }
 
@@ -112,5 +123,12 @@ int main() {
     run<2>("ld.global 16 B per lane", x, planes, h, w, sink);
     run<0>("cp.async 16 B per lane", x, planes, h, w, sink);
     run<1>("cp.async.bulk per row", x, planes, h, w, sink);
+    // the same walk with the store pattern of the two kernels beside it (no math): the memory-side ceiling of each read / write mix
+    uint16_t *y;
+    cudaMalloc(&y, 2ull * planes * 256 * 256);
+    run<0, 1>("cp.async + down-2 stores", x, planes, h, w, sink, y);
+    run<0, 2>("cp.async + blur stores", x, planes, h, w, sink, y);
+    run<1, 1>("bulk + down-2 stores", x, planes, h, w, sink, y);
+    run<1, 2>("bulk + blur stores", x, planes, h, w, sink, y);
     return 0;
 }
