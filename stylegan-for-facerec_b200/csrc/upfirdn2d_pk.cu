@@ -49,6 +49,9 @@ constexpr int PK_THREADS = 32 * PK_WARPS;
 #ifndef PK_RB_N
 #define PK_RB_N 3                // batches in the ring (modes with 4-row batches, up to 4 groups per warp)
 #endif
+#ifndef PK_BULK
+#define PK_BULK 1               // rows by cp.async.bulk + mbarrier where that is faster (0: 16-byte cp.async per lane everywhere)
+#endif
 #ifndef PK_CTAS_N
 #define PK_CTAS_N 5
 #endif
@@ -200,8 +203,20 @@ upfirdn2d_pk_kernel(T *__restrict__ out, const float *__restrict__ taps, const U
     extern __shared__ __align__(16) unsigned char pk_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> WLOG2, t = lane & (WL - 1);
-    uint32_t ring = smem_u32(pk_smem) + (uint32_t)warp * (RING + 512) + (uint32_t)g * GB;   // this group's part of slot 0
-    const uint32_t scratch = smem_u32(pk_smem) + (uint32_t)warp * (RING + 512) + RING + 16u * lane;   // see pf_batch
+    // rows by cp.async.bulk: only where it measured faster -- one group per warp and batches of 8 rows (the 2^k + 1 wide blur
+    // planes from 129 outputs up: 0.78 -> 0.81); with several groups per warp (many small copies) or 4-row batches (an
+    // mbarrier round trip per 4 rows) it measured slower (down-2 0.69 -> 0.62, 32^2 planes 0.66 -> 0.45)
+    constexpr bool BULK = PK_BULK && QS == 8 && NS == 1;
+    constexpr int WSTRIDE = RING + 512 + 64;                       // per warp: the ring, 16 bytes of scratch per lane, RB mbarriers
+    uint32_t ring = smem_u32(pk_smem) + (uint32_t)warp * WSTRIDE + (uint32_t)g * GB;   // this group's part of slot 0
+    const uint32_t scratch = smem_u32(pk_smem) + (uint32_t)warp * WSTRIDE + RING + 16u * lane;   // see pf_batch
+    uint64_t *full = reinterpret_cast<uint64_t *>(pk_smem + (size_t)warp * WSTRIDE + RING + 512);   // full[b]: batch slot b has landed
+    if (BULK && lane == 0) {
+#pragma unroll
+        for (int b = 0; b < RB; ++b) mbar_init(full + b, NS);      // one arrival per group leader and batch
+        fence_barrier_init();
+    }
+    __syncwarp();
     asm volatile("" : "+r"(ring));                                 // keep it in a register (ptxas re-derives it from S2R otherwise)
 
     // flipped taps, zero padded to 4 x 4: kf[a][b] multiplies the sample a rows / b columns after the window's first
@@ -297,10 +312,60 @@ upfirdn2d_pk_kernel(T *__restrict__ out, const float *__restrict__ taps, const U
         pf_a = a0 - it.u0 * pitch + 16ull * t;
     };
     if (pf_live) pf_open();
-    auto pf_batch = [&]() {                                        // one batch of rows (never straddles items), one commit group
+    int pf_b = 0;                                                  // batch slot (0 .. RB - 1) the next batch goes to
+    auto pf_batch = [&]() {                                        // one batch of rows (never straddles items)
         if (pf_live) {
             const uint32_t dst0 = ring + pf_off + 16u * t;
-            if (pf_safe) {
+            if constexpr (BULK) {
+                // Rows as ONE cp.async.bulk each (the TMA engine, 16-byte aligned start, (WL + 2) * 16 bytes), issued by the
+                // group's first lane and counted on the batch's mbarrier: nothing of the row passes the LSU / L1 data pipe on
+                // its way in (tools/probes/rowload_probe.cu: +3 .. 9 % on the memory-side ceiling of this walk).  Rows outside the plane are zeroed by the lanes; a band that touches either end of the
+                // tensor is fetched by every lane with clamped 16-byte cp.async instead and waited for on the spot.
+                const bool unsafe = !pf_safe;
+                const bool any_unsafe = __any_sync(0xffffffffu, unsafe);
+                int rows_ok = 0;
+#pragma unroll
+                for (int j = 0; j < BATCH; ++j) {
+                    const bool in_item = (unsigned)(pf_s + j) < (unsigned)pf_need;
+                    const bool row_ok = in_item && (unsigned)(pf_iy + j) < (unsigned)p.in_h && !(PK_KO & 4);
+                    const uint32_t dst = dst0 + j * SLOT;
+                    if (!unsafe) {
+                        pk_sts128_zero_if(dst, in_item && !row_ok);
+                        pk_sts128_zero_if(dst + 16u * WL, in_item && !row_ok && t < 2);
+                        rows_ok += row_ok ? 1 : 0;
+                    } else {
+                        const unsigned long long src = (pf_a + j * pitch) & ~15ull;
+                        auto copy = [&](uint32_t d, unsigned long long ca) {
+                            const long long rem = (long long)(p.xe - ca);
+                            const int bytes = (!row_ok || ca < p.xb || rem <= 0) ? 0 : (rem < 16 ? (int)rem : 16);
+                            pk_cp16(d, bytes ? ca : p.xb, bytes);
+                        };
+                        copy(dst, src);
+                        if (t < 2) copy(dst + 16u * WL, src + 16ull * WL);
+                    }
+                }
+                if (any_unsafe) {                                  // (warp-uniform) the clamped copies land before the arrival below
+                    pk_commit();
+                    pk_wait<0>();
+                    __syncwarp();
+                }
+                if (t == 0) {
+                    uint64_t *bar = full + pf_b;
+                    if (unsafe || rows_ok == 0) {
+                        mbar_arrive(bar);
+                    } else {
+                        fence_proxy_async();                       // the slots were read / patched through the generic proxy
+                        mbar_arrive_expect_tx(bar, (uint32_t)(rows_ok * GB));
+#pragma unroll
+                        for (int j = 0; j < BATCH; ++j) {
+                            const bool row_ok = (unsigned)(pf_s + j) < (unsigned)pf_need && (unsigned)(pf_iy + j) < (unsigned)p.in_h && !(PK_KO & 4);
+                            if (row_ok)
+                                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst0 + j * SLOT),
+                                             "l"((pf_a + j * pitch) & ~15ull), "r"(GB), "r"(smem_u32(bar)) : "memory");
+                        }
+                    }
+                }
+            } else if (pf_safe) {
 #pragma unroll
                 for (int j = 0; j < BATCH; ++j) {
                     const bool in_item = (unsigned)(pf_s + j) < (unsigned)pf_need;
@@ -335,14 +400,17 @@ upfirdn2d_pk_kernel(T *__restrict__ out, const float *__restrict__ taps, const U
                 if (pf_live) pf_open();
             }
         }
-        pk_commit();
+        if constexpr (!BULK) pk_commit();
         pf_off += BATCH * SLOT;
         if (pf_off == RING) pf_off = 0;
+        pf_b = pf_b + 1 == RB ? 0 : pf_b + 1;
     };
 #pragma unroll 1
     for (int d = 0; d < RB - 1; ++d) pf_batch();
 
     uint32_t cs_off = 0;                                           // ring offset of the batch the consumer reads next
+    int cs_b = 0;                                                  // ... its batch slot and the phase of that slot's mbarrier
+    uint32_t cs_par = 0;
     for (long long item = item0; item < p.items; item += stride) {
         const Item it = decode(item);
         const int nrows = it.live ? max(0, min(p.rh, p.out_h - it.y0)) : 0;   // output rows of this lane's band
@@ -372,7 +440,12 @@ upfirdn2d_pk_kernel(T *__restrict__ out, const float *__restrict__ taps, const U
             for (int i = 0; i < TX / 2; ++i) acc[r][i] = make_float2(0.f, 0.f);
 
         for (int sb = -it.u0; sb < need; sb += BATCH) {
-            pk_wait<RB - 2>();                                     // this lane's copies of the batch have landed
+            if constexpr (BULK) {
+                mbar_wait(full + cs_b, cs_par);                    // the batch has landed (every group's rows)
+                if (++cs_b == RB) { cs_b = 0; cs_par ^= 1u; }
+            } else {
+                pk_wait<RB - 2>();                                 // this lane's copies of the batch have landed
+            }
             __syncwarp();                                          // ... and everybody's; every lane is done with the previous batch
             const uint32_t line0 = ring + cs_off;
             if (any_fix) {
@@ -499,7 +572,7 @@ static bool pk_debug() {
 template <typename T, int DOWN, int WLOG2, int QS>
 static int pk_launch_t(void *out, const float *taps, const UfdPkParams &p, int grid, cudaStream_t st) {
     constexpr int WL = 1 << WLOG2, NS = 32 >> WLOG2;
-    constexpr size_t smem = (size_t)PK_WARPS * (PkMode<QS, NS>::RB * PkMode<QS, NS>::BATCH * NS * (WL + 2) * 16 + 512);
+    constexpr size_t smem = (size_t)PK_WARPS * (PkMode<QS, NS>::RB * PkMode<QS, NS>::BATCH * NS * (WL + 2) * 16 + 512 + 64);
     static_assert(smem <= 48 * 1024, "dynamic shared memory without the opt-in attribute");
     upfirdn2d_pk_kernel<T, DOWN, WLOG2, QS><<<grid, PK_THREADS, smem, st>>>((T *)out, taps, p);
     SG2_LAUNCH_CHECK();
