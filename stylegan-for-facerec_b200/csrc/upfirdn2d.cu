@@ -337,7 +337,7 @@ extern "C" int sg2_upfirdn2d(void *out, const void *x, const float *kernel, int6
             SG2_LAUNCH_CHECK();
             return SG2_OK;
         }
-        if (sym) {   // the three model geometries: row-streaming TMA kernel (upfirdn2d_stream.cu); 1 = not applicable
+        if (sym) {   // the three model geometries: row-streaming kernel (upfirdn2d_stream.cu); 1 = not applicable
             static const char *env_tiled = getenv("SG2_UPFIRDN_TILED");     // A/B switch: force the tiled kernels
             if (!env_tiled || atoi(env_tiled) == 0) {
                 const int rc = launch_upfirdn2d_stream<T>(out, x, kernel, major, in_h, in_w, out_h, out_w, kh, kw, up_x, down_x,

@@ -16,7 +16,10 @@
 //   * every input row is read from HBM once per band; it updates the <= 4 output rows it contributes
 //     to (accumulators in registers, polyphase taps resolved at compile time: no multiplies by the
 //     inserted zeros) and the finished output row leaves with one 8/16-byte store per lane;
-//   * no block-wide barrier anywhere: warps run independently (__syncwarp only).
+//   * no block-wide barrier anywhere: warps run independently (__syncwarp only);
+//   * round 2: rows as 16-byte (fp32 down-sampling) / 8-byte (2-byte up-sampling) vectors when pitch and base allow (template
+//     parameter VD), the up-sampling accumulators as row pairs on packed fma.rn.f32x2.  Blur and down-sampling in 2-byte
+//     storage run on upfirdn2d_pk.cu instead (this kernel is their fall-back).
 //
 // fp32 accumulation for every storage dtype; per output the taps are applied in the same order as
 // the reference kernel (rows, then columns), so fp32 results match it to the last bits.
